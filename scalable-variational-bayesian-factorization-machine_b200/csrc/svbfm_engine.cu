@@ -1,0 +1,693 @@
+// csrc/svbfm_engine.cu -- C-ABI (include/svbfm.h) and launch scheduling of the VB / MCMC sweep on one B200.
+//
+// An iteration is a fixed sequence of launches on one stream with every scalar (alpha, sigma_0, w0, sum T,
+// hyper-parameters, counters, evaluation sums) resident on the device; the host only enqueues, and reads the
+// per-iteration stats slots once at the end of svbfm_run / svbfm_*_sweep. When a communicator is attached,
+// the per-run column sums and the few scalar sums go through ncclAllReduce on the same stream.
+#include <dlfcn.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include "svbfm_kernels.cuh"
+
+using namespace svb;
+
+static thread_local std::string g_create_error;
+
+// ---------------------------------------------------------------------------------------------- NCCL (dlopen)
+struct Id128 { char b[SVBFM_COMM_ID_BYTES]; };
+namespace {
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Id128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static Nccl g_nccl;
+static std::once_flag g_nccl_once;
+
+static bool nccl_load() {
+    std::call_once(g_nccl_once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+        for (int i = 0; names[i] && !g_nccl.lib; i++) g_nccl.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if (!g_nccl.lib) return;
+        g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+        g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+        g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+        g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+        g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    });
+    return g_nccl.lib && g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
+}
+
+namespace svb {
+int allreduce(Engine* E, void* buf, size_t count, int dtype, int op) {
+    if (E->world <= 1 || count == 0) return 0;
+    int r = g_nccl.AllReduce(buf, buf, count, dtype, op, E->nccl_comm, E->stream);
+    if (r != 0) return fail(E, SVBFM_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    return 0;
+}
+}  // namespace svb
+static inline int allreduce_sum_f64(Engine* E, double* buf, size_t n) { return allreduce(E, buf, n, 8 /*ncclDouble*/, 0 /*ncclSum*/); }
+
+// ---------------------------------------------------------------------------------------------- helpers
+static inline unsigned nblk(uint64_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t); }
+#define LAUNCHED(E) ((E)->launches++)
+// reduction scratch layout (doubles): [0, RGRID*4) block partials | [RGRID*4, +8) final sums | group partials
+#define SCR_FINAL ((size_t)SV_RGRID * 4)
+#define SCR_GROUP ((size_t)SV_RGRID * 4 + 8)
+static cudaError_t copy_sync(Engine* E, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, E->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(E->stream);
+}
+#define RED(sc, k) (reinterpret_cast<double*>(reinterpret_cast<char*>(sc) + offsetof(Scalars, red)) + (k))
+
+static RowView row_view(const DevSplit& S) { return RowView{S.rowptr, S.rcol, S.rval, S.uniformF}; }
+static int fmt_of(const DevSplit& S) { return S.uniformF == 2 ? 2 : (S.uniformF > 0 ? 1 : 0); }
+
+// dispatch on (row format, all-ones)
+#define DISPATCH_FMT(S, CALL)                                                            \
+    do {                                                                                 \
+        int _ft = fmt_of(S);                                                             \
+        if ((S).all_ones) {                                                              \
+            if (_ft == 2) { CALL(2, true); } else if (_ft == 1) { CALL(1, true); } else { CALL(0, true); }   \
+        } else {                                                                         \
+            if (_ft == 2) { CALL(2, false); } else if (_ft == 1) { CALL(1, false); } else { CALL(0, false); } \
+        }                                                                                \
+    } while (0)
+
+static int check_launch(Engine* E, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(E, SVBFM_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- one run sweep
+template <int KIND>
+static int sweep_run(Engine* E, const Run& r, int f) {
+    const DevSplit& S = E->tr;
+    cudaStream_t st = E->stream;
+    uint32_t ntiles = r.tile_end - r.tile_begin;
+    constexpr bool IS_V = (KIND == KIND_VB_V || KIND == KIND_MC_V || KIND == KIND_VBO_V);
+    double2* pf = IS_V ? E->d_pv + (size_t)f * E->D : E->d_pw;
+    SweepArgs a{};
+    a.tile_col = E->d_tile_col; a.tile_begin = E->d_tile_begin; a.colptr = S.colptr; a.crow = S.crow; a.cval = S.cval;
+    a.rv = row_view(S); a.e = E->d_e; a.pf = pf; a.partial = E->d_partial; a.delta = E->d_delta;
+    a.tile0 = r.tile_begin; a.ntiles = ntiles; a.tile_entries = E->tile_entries; a.in_batch = nullptr;
+    if (ntiles) {
+        unsigned grid = (ntiles + 7) / 8;
+        if constexpr (IS_V) {
+#define CALL_R(FT, ONES) k_sweep_reduce<KIND, FT, ONES><<<grid, 256, 0, st>>>(a)
+            DISPATCH_FMT(S, CALL_R);
+#undef CALL_R
+        } else {
+            if (S.all_ones) k_sweep_reduce<KIND, 0, true><<<grid, 256, 0, st>>>(a);
+            else k_sweep_reduce<KIND, 0, false><<<grid, 256, 0, st>>>(a);
+        }
+        LAUNCHED(E);
+    }
+    uint32_t nheavy = r.heavy_end - r.heavy_begin;
+    if (nheavy) { k_combine_heavy<<<nheavy, 128, 0, st>>>(E->d_heavy_cols, r.heavy_begin, E->d_col_tile0, E->d_partial, E->d_colsum); LAUNCHED(E); }
+    uint32_t ncols = r.col_end - r.col_begin;
+    bool from_colsum = false;
+    if (E->world > 1) {
+        k_combine_light<<<nblk(ncols), 256, 0, st>>>(r.col_begin, r.col_end, E->d_col_tile0, E->d_partial, E->d_colsum); LAUNCHED(E);
+        if (int rc = allreduce_sum_f64(E, E->d_colsum + (size_t)r.col_begin * 4, (size_t)ncols * 4)) return rc;
+        from_colsum = true;
+    }
+    FinalizeArgs fa{};
+    fa.c0 = r.col_begin; fa.c1 = r.col_end; fa.f = IS_V ? f : -1; fa.K = E->K;
+    fa.col_tile0 = E->d_col_tile0; fa.partial = E->d_partial; fa.colsum = E->d_colsum; fa.from_colsum = from_colsum;
+    fa.pf = pf; fa.group = E->d_group; fa.hyper = IS_V ? E->d_hyper_v : E->d_hyper_w;
+    fa.hyper_mu = IS_V ? E->d_mu_v : E->d_mu_w; fa.sc = E->d_sc; fa.delta = E->d_delta; fa.dT = E->d_dT;
+    fa.seed = E->cfg.seed; fa.do_sample = E->cfg.do_sample;
+    k_finalize<KIND><<<nblk(ncols), 256, 0, st>>>(fa); LAUNCHED(E);
+    if (ntiles) {
+        unsigned grid = (ntiles + 7) / 8;
+        if constexpr (IS_V) {
+#define CALL_A(FT, ONES) k_sweep_apply<true, FT, ONES><<<grid, 256, 0, st>>>(a)
+            DISPATCH_FMT(S, CALL_A);
+#undef CALL_A
+        } else {
+            if (S.all_ones) k_sweep_apply<false, 0, true><<<grid, 256, 0, st>>>(a);
+            else k_sweep_apply<false, 0, false><<<grid, 256, 0, st>>>(a);
+        }
+        LAUNCHED(E);
+    }
+    return check_launch(E, "sweep_run");
+}
+
+// sum e, sum e^2, sum clamp(e)^2 -> red[0..2] (global)
+static int reduce_e(Engine* E) {
+    cudaStream_t st = E->stream;
+    k_reduce_e<<<SV_RGRID, 256, 0, st>>>(E->d_e, E->tr.n, E->d_sc, E->d_red_partial); LAUNCHED(E);
+    k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_RGRID, 3, RED(E->d_sc, 0), 0); LAUNCHED(E);
+    return allreduce_sum_f64(E, RED(E->d_sc, 0), 3);
+}
+
+static int group_sums(Engine* E, bool mcmc) {
+    cudaStream_t st = E->stream;
+    double* partial = E->d_red_partial + SCR_GROUP;
+    dim3 grid(SV_GGRID, E->K + 1);
+    if (mcmc) k_group_sums<true><<<grid, 256, 0, st>>>(E->d_pw, E->d_pv, E->D, E->G, E->d_group, partial);
+    else k_group_sums<false><<<grid, 256, 0, st>>>(E->d_pw, E->d_pv, E->D, E->G, E->d_group, partial);
+    LAUNCHED(E);
+    uint32_t nrows = (uint32_t)(E->K + 1) * E->G * 2;
+    k_group_sums_final<<<nrows, 64, 0, st>>>(partial, nrows, E->d_grp_sums); LAUNCHED(E);
+    return check_launch(E, "group_sums");
+}
+
+template <int MODE>
+static int predict(Engine* E, const DevSplit& S, double* e_out, int red_slot, int nred) {
+    cudaStream_t st = E->stream;
+    PredictArgs a{};
+    a.rv = row_view(S); a.y = S.y; a.n = S.n; a.pw = E->d_pw; a.pv = E->d_pv; a.D = E->D; a.K = E->K;
+    a.k0 = E->cfg.k0; a.k1 = E->cfg.k1; a.sc = E->d_sc; a.e = e_out; a.pred = E->d_pred_test; a.pred_sum = E->d_pred_sum;
+    a.partial = E->d_red_partial; a.in_batch = nullptr;
+    unsigned grid = std::max(1u, std::min<unsigned>(nblk(S.n), SV_RGRID));
+#define CALL_P(FT, ONES) k_predict<MODE, FT, ONES><<<grid, 256, 0, st>>>(a)
+    DISPATCH_FMT(S, CALL_P);
+#undef CALL_P
+    LAUNCHED(E);
+    k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, grid, 4, E->d_red_partial + SCR_FINAL, 0); LAUNCHED(E);
+    // move the first nred sums into red[red_slot..]
+    SV_CUDA(E, cudaMemcpyAsync(RED(E->d_sc, red_slot), E->d_red_partial + SCR_FINAL, sizeof(double) * nred, cudaMemcpyDeviceToDevice, st));
+    if (int rc = allreduce_sum_f64(E, RED(E->d_sc, red_slot), nred)) return rc;
+    return check_launch(E, "predict");
+}
+
+// ---------------------------------------------------------------------------------------------- iterations
+struct IterEvents { cudaEvent_t t0, t1, t2; };
+
+static int vb_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
+    cudaStream_t st = E->stream;
+    DevStats* stp = E->d_stats + slot;
+    if (ev) cudaEventRecord(ev->t0, st);
+    if (E->cfg.k0) {                                               // update_w0 (vb.h:385-387)
+        if (int rc = reduce_e(E)) return rc;
+        k_vb_w0<<<1, 1, 0, st>>>(E->d_sc); LAUNCHED(E);
+        k_shift_e<<<SV_RGRID, 256, 0, st>>>(E->d_e, E->tr.n, E->d_sc); LAUNCHED(E);
+    }
+    if (E->cfg.k1)                                                 // update_w, all columns (vb.h:390-406)
+        for (const Run& r : E->runs)
+            if (int rc = sweep_run<KIND_VB_W>(E, r, -1)) return rc;
+    for (int f = 0; f < E->K; f++)                                 // update_v (vb.h:409-440)
+        for (const Run& r : E->runs)
+            if (int rc = sweep_run<KIND_VB_V>(E, r, f)) return rc;
+    // hyper-parameters + free energy (vb.h:446-500)
+    if (int rc = reduce_e(E)) return rc;
+    k_reduce_dT<<<SV_GGRID, 256, 0, st>>>(E->d_dT, E->D, E->d_red_partial); LAUNCHED(E);
+    k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_GGRID, 1, &E->d_sc->sum_t, 1); LAUNCHED(E);
+    if (int rc = group_sums(E, false)) return rc;
+    k_vb_hyper<<<1, 1, 0, st>>>(E->d_sc, E->d_grp_sums, E->d_n_per_group, E->G, E->K, E->d_hyper_w, E->d_hyper_v, stp); LAUNCHED(E);
+    if (ev) cudaEventRecord(ev->t1, st);
+    // test prediction + evaluation (vbs.h:125-222)
+    if (int rc = predict<PRED_VB_TEST>(E, E->te, nullptr, 3, 1)) return rc;
+    k_finish_iter<<<1, 1, 0, st>>>(E->d_sc, stp, SVBFM_VB); LAUNCHED(E);
+    if (ev) cudaEventRecord(ev->t2, st);
+    return check_launch(E, "vb_iteration");
+}
+
+static int mcmc_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
+    cudaStream_t st = E->stream;
+    DevStats* stp = E->d_stats + slot;
+    if (ev) cudaEventRecord(ev->t0, st);
+    if (int rc = reduce_e(E)) return rc;                           // sum e, sum e^2 for alpha and w0
+    if (int rc = group_sums(E, true)) return rc;
+    k_mcmc_hyper<<<1, 1, 0, st>>>(E->d_sc, E->d_grp_sums, E->d_n_per_group, E->G, E->K, E->cfg.k0, E->cfg.k1, E->d_hyper_w, E->d_mu_w,
+                                  E->d_hyper_v, E->d_mu_v, E->cfg.seed, E->cfg.do_sample, E->cfg.do_multilevel); LAUNCHED(E);
+    if (E->cfg.k0) { k_shift_e<<<SV_RGRID, 256, 0, st>>>(E->d_e, E->tr.n, E->d_sc); LAUNCHED(E); }
+    if (E->cfg.k1)
+        for (const Run& r : E->runs)
+            if (int rc = sweep_run<KIND_MC_W>(E, r, -1)) return rc;
+    for (int f = 0; f < E->K; f++)
+        for (const Run& r : E->runs)
+            if (int rc = sweep_run<KIND_MC_V>(E, r, f)) return rc;
+    if (ev) cudaEventRecord(ev->t1, st);
+    // re-prediction of train and test (mcmcs.h:134-174)
+    if (E->cfg.flags & SVBFM_FLAG_MCMC_NO_REPREDICT) {
+        unsigned grid = std::max(1u, std::min<unsigned>(nblk(E->tr.n), SV_RGRID));
+        k_train_sse_from_e<<<grid, 256, 0, st>>>(E->d_e, E->tr.y, E->tr.n, E->d_sc, E->d_red_partial); LAUNCHED(E);
+        k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, grid, 4, E->d_red_partial + SCR_FINAL, 0); LAUNCHED(E);
+        SV_CUDA(E, cudaMemcpyAsync(RED(E->d_sc, 5), E->d_red_partial + SCR_FINAL, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        if (int rc = allreduce_sum_f64(E, RED(E->d_sc, 5), 1)) return rc;
+    } else {
+        if (int rc = predict<PRED_MC_TRAIN>(E, E->tr, E->d_e, 5, 1)) return rc;
+    }
+    if (int rc = predict<PRED_MC_TEST>(E, E->te, nullptr, 3, 2)) return rc;
+    k_finish_iter<<<1, 1, 0, st>>>(E->d_sc, stp, SVBFM_MCMC); LAUNCHED(E);
+    if (ev) cudaEventRecord(ev->t2, st);
+    return check_launch(E, "mcmc_iteration");
+}
+
+static int ensure_stats(Engine* E, uint32_t n) {
+    if (E->stats_cap >= n) return 0;
+    cudaFree(E->d_stats); E->d_stats = nullptr;
+    if (dev_alloc(E, &E->d_stats, n)) return SVBFM_ERR_OOM;
+    E->stats_cap = n;
+    return 0;
+}
+
+static int run_iterations(Engine* E, uint32_t n_iter, svbfm_iter_stats* out) {
+    if (!E->begun) return fail(E, SVBFM_ERR_ARG, "svbfm_begin must be called first");
+    if (E->cfg.method == SVBFM_VB_ONLINE) return fail(E, SVBFM_ERR_ARG, "use svbfm_vb_online_epoch for vb_online");
+    if (n_iter == 0) return 0;
+    if (int rc = ensure_stats(E, n_iter)) return rc;
+    SV_CUDA(E, cudaMemsetAsync(E->d_stats, 0, sizeof(DevStats) * n_iter, E->stream));
+    std::vector<IterEvents> ev(n_iter);
+    for (auto& e : ev) { cudaEventCreate(&e.t0); cudaEventCreate(&e.t1); cudaEventCreate(&e.t2); }
+    int rc = 0;
+    for (uint32_t it = 0; it < n_iter && !rc; it++)
+        rc = (E->cfg.method == SVBFM_VB) ? vb_iteration(E, it, &ev[it]) : mcmc_iteration(E, it, &ev[it]);
+    std::vector<DevStats> hs(n_iter);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(hs.data(), E->d_stats, sizeof(DevStats) * n_iter, cudaMemcpyDeviceToHost, E->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(E->stream);
+        if (e != cudaSuccess) rc = fail(E, SVBFM_ERR_CUDA, std::string("iteration: ") + cudaGetErrorString(e));
+    }
+    if (!rc && out)
+        for (uint32_t it = 0; it < n_iter; it++) {
+            svbfm_iter_stats& o = out[it];
+            memset(&o, 0, sizeof(o));
+            o.test_rmse = hs[it].test_rmse; o.train_stat = hs[it].train_stat; o.free_energy = hs[it].free_energy;
+            o.alpha = hs[it].alpha; o.rmse_this = hs[it].rmse_this; o.has_free_energy = hs[it].has_fe != 0.0;
+            o.nan_inf_count = (uint32_t)hs[it].nan_inf;
+            cudaEventElapsedTime(&o.sweep_ms, ev[it].t0, ev[it].t1);
+            cudaEventElapsedTime(&o.predict_ms, ev[it].t1, ev[it].t2);
+        }
+    for (auto& e : ev) { cudaEventDestroy(e.t0); cudaEventDestroy(e.t1); cudaEventDestroy(e.t2); }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- C-ABI
+extern "C" {
+
+int svbfm_abi_version(void) { return SVBFM_ABI_VERSION; }
+
+const char* svbfm_last_error(const svbfm_t* h) {
+    if (!h) return g_create_error.c_str();
+    return reinterpret_cast<const Engine*>(h)->err.c_str();
+}
+
+int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
+    if (!out || !cfg) { g_create_error = "svbfm_create: null argument"; return SVBFM_ERR_ARG; }
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(svbfm_config)) { g_create_error = "svbfm_create: struct_size mismatch (ABI)"; return SVBFM_ERR_ARG; }
+    if (cfg->method < SVBFM_VB || cfg->method > SVBFM_MCMC) { g_create_error = "svbfm_create: unknown method"; return SVBFM_ERR_ARG; }
+    if (cfg->task != 0) { g_create_error = "svbfm_create: only regression (task 0) is implemented on this path"; return SVBFM_ERR_ARG; }
+    if (cfg->num_factor < 0 || cfg->num_attribute == 0) { g_create_error = "svbfm_create: bad dimensions"; return SVBFM_ERR_ARG; }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("svbfm_create: no CUDA device (") + cudaGetErrorString(ce) + "); there is no CPU fallback";
+        return SVBFM_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "svbfm_create: device ordinal out of range"; return SVBFM_ERR_ARG; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cfg->device);
+    if (prop.major < 10) {
+        g_create_error = std::string("svbfm_create: device '") + prop.name + "' is not sm_100 (kernels are built for sm_100a only)";
+        return SVBFM_ERR_CUDA;
+    }
+    ce = cudaSetDevice(cfg->device);
+    if (ce != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(ce); return SVBFM_ERR_CUDA; }
+    Engine* E = new Engine();
+    E->cfg = *cfg; E->dev = cfg->device; E->D = cfg->num_attribute; E->K = cfg->num_factor;
+    E->tile_entries = cfg->tile_entries ? cfg->tile_entries : 1024;
+    ce = cudaStreamCreateWithFlags(&E->own_stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(ce); delete E; return SVBFM_ERR_CUDA; }
+    E->stream = E->own_stream;
+    E->G = 1;
+    E->h_group.assign(E->D, 0);
+    E->h_n_per_group.assign(1, E->D);
+    *out = reinterpret_cast<svbfm_t*>(E);
+    // device state
+    size_t D = E->D, K = (size_t)E->K;
+    int rc = 0;
+    rc |= dev_alloc(E, &E->d_group, D);
+    rc |= dev_alloc(E, &E->d_pw, D);
+    rc |= dev_alloc(E, &E->d_pv, K * D);
+    rc |= dev_alloc(E, &E->d_sc, 1);
+    rc |= dev_alloc(E, &E->d_colsum, D * 4);
+    rc |= dev_alloc(E, &E->d_delta, D);
+    rc |= dev_alloc(E, &E->d_dT, D);
+    rc |= dev_alloc(E, &E->d_red_partial, SCR_GROUP + (K + 1) * 64 /*max groups*/ * 2 * SV_GGRID);
+    if (rc) { g_create_error = E->err; svbfm_destroy(*out); *out = nullptr; return SVBFM_ERR_OOM; }
+    cudaMemsetAsync(E->d_group, 0, D * 4, E->stream);
+    cudaMemsetAsync(E->d_dT, 0, D * 8, E->stream);
+    cudaMemsetAsync(E->d_delta, 0, D * 8, E->stream);
+    cudaMemsetAsync(E->d_colsum, 0, D * 32, E->stream);
+    cudaMemsetAsync(E->d_sc, 0, sizeof(Scalars), E->stream);
+    cudaStreamSynchronize(E->stream);
+    // default groups
+    std::vector<uint32_t> g0(E->D, 0);
+    if (svbfm_set_groups(*out, g0.data(), 1)) { g_create_error = E->err; svbfm_destroy(*out); *out = nullptr; return SVBFM_ERR_CUDA; }
+    return SVBFM_OK;
+}
+
+void svbfm_destroy(svbfm_t* h) {
+    if (!h) return;
+    Engine* E = reinterpret_cast<Engine*>(h);
+    cudaSetDevice(E->dev);
+    cudaStreamSynchronize(E->stream);
+    if (E->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(E->nccl_comm);
+    free_split(E, E->tr); free_split(E, E->te);
+    void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
+                    E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
+                    E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
+                    E->d_pred_sum, E->d_stats};
+    for (void* p : ptrs) cudaFree(p);
+    if (E->own_stream) cudaStreamDestroy(E->own_stream);
+    delete E;
+}
+
+int svbfm_set_stream(svbfm_t* h, void* cuda_stream) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E) return SVBFM_ERR_ARG;
+    cudaStreamSynchronize(E->stream);
+    E->stream = cuda_stream ? (cudaStream_t)cuda_stream : E->own_stream;
+    return SVBFM_OK;
+}
+
+int svbfm_comm_get_unique_id(uint8_t id[SVBFM_COMM_ID_BYTES]) {
+    if (!nccl_load()) { g_create_error = "NCCL (libnccl.so.2) could not be loaded"; return SVBFM_ERR_NCCL; }
+    int r = g_nccl.GetUniqueId(id);
+    if (r != 0) { g_create_error = "ncclGetUniqueId failed"; return SVBFM_ERR_NCCL; }
+    return SVBFM_OK;
+}
+
+int svbfm_comm_init(svbfm_t* h, const uint8_t id[SVBFM_COMM_ID_BYTES], int32_t rank, int32_t world_size) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E || !id || world_size < 1 || rank < 0 || rank >= world_size) return fail(E, SVBFM_ERR_ARG, "svbfm_comm_init: bad arguments");
+    if (E->tr.n || E->te.n) return fail(E, SVBFM_ERR_ARG, "svbfm_comm_init must precede svbfm_set_csc");
+    if (world_size == 1) { E->rank = 0; E->world = 1; return SVBFM_OK; }
+    if (!nccl_load()) return fail(E, SVBFM_ERR_NCCL, "NCCL (libnccl.so.2) could not be loaded");
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    Id128 uid;
+    memcpy(uid.b, id, SVBFM_COMM_ID_BYTES);
+    int r = g_nccl.CommInitRank(&E->nccl_comm, world_size, uid, rank);
+    if (r != 0) return fail(E, SVBFM_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    E->rank = rank; E->world = world_size;
+    return SVBFM_OK;
+}
+
+int svbfm_set_groups(svbfm_t* h, const uint32_t* attr_group, uint32_t num_groups) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E || !attr_group || num_groups == 0) return fail(E, SVBFM_ERR_ARG, "svbfm_set_groups: bad arguments");
+    if (num_groups > 64) return fail(E, SVBFM_ERR_ARG, "svbfm_set_groups: more than 64 attribute groups are not supported");
+    if (E->begun) return fail(E, SVBFM_ERR_ARG, "svbfm_set_groups after svbfm_begin");
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    std::vector<double> npg(num_groups, 0.0);
+    for (uint32_t j = 0; j < E->D; j++) {
+        if (attr_group[j] >= num_groups) return fail(E, SVBFM_ERR_ARG, "svbfm_set_groups: group id out of range");
+        npg[attr_group[j]] += 1.0;                       // DataMetaInfo::num_attr_per_group counts ALL D attributes (Data.h:58-60)
+    }
+    E->G = num_groups;
+    E->h_group.assign(attr_group, attr_group + E->D);
+    E->h_n_per_group.resize(num_groups);
+    for (uint32_t g = 0; g < num_groups; g++) E->h_n_per_group[g] = (uint32_t)npg[g];
+    SV_CUDA(E, copy_sync(E, E->d_group, attr_group, (size_t)E->D * 4, cudaMemcpyHostToDevice));
+    void* old[] = {E->d_n_per_group, E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_grp_sums};
+    for (void* p : old) cudaFree(p);
+    E->d_n_per_group = E->d_hyper_w = E->d_hyper_v = E->d_mu_w = E->d_mu_v = E->d_grp_sums = nullptr;
+    size_t G = num_groups, K = (size_t)E->K;
+    int rc = 0;
+    rc |= dev_alloc(E, &E->d_n_per_group, G);
+    rc |= dev_alloc(E, &E->d_hyper_w, G);
+    rc |= dev_alloc(E, &E->d_hyper_v, G * std::max<size_t>(K, 1));
+    rc |= dev_alloc(E, &E->d_mu_w, G);
+    rc |= dev_alloc(E, &E->d_mu_v, G * std::max<size_t>(K, 1));
+    rc |= dev_alloc(E, &E->d_grp_sums, (K + 1) * G * 2);
+    if (rc) return SVBFM_ERR_OOM;
+    SV_CUDA(E, copy_sync(E, E->d_n_per_group, npg.data(), G * 8, cudaMemcpyHostToDevice));
+    // initial hyper-parameters: vb sigma_w = sigma_v = 1 (vb.h:707-708); mcmc lambda = reg, mu = 0 (mcmc.h:1109-1117, libfm.cpp:372-405)
+    bool mc = E->cfg.method == SVBFM_MCMC;
+    std::vector<double> hw(G, mc ? E->cfg.regw : 1.0), hv(G * std::max<size_t>(K, 1), mc ? E->cfg.regv : 1.0), z(G * std::max<size_t>(K, 1), 0.0);
+    SV_CUDA(E, copy_sync(E, E->d_hyper_w, hw.data(), G * 8, cudaMemcpyHostToDevice));
+    SV_CUDA(E, copy_sync(E, E->d_hyper_v, hv.data(), hv.size() * 8, cudaMemcpyHostToDevice));
+    SV_CUDA(E, copy_sync(E, E->d_mu_w, z.data(), G * 8, cudaMemcpyHostToDevice));
+    SV_CUDA(E, copy_sync(E, E->d_mu_v, z.data(), z.size() * 8, cudaMemcpyHostToDevice));
+    return SVBFM_OK;
+}
+
+int svbfm_set_csc(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_cols, const uint64_t* colptr, const uint32_t* case_id,
+                  const float* x, const float* target) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E || !colptr || (split != SVBFM_TRAIN && split != SVBFM_TEST)) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc: bad arguments");
+    if (colptr[num_cols] > 0 && (!case_id || !x)) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc: null entry arrays");
+    if (num_cases > 0 && !target) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc: null target");
+    if (E->begun) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc after svbfm_begin");
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    bool is_train = split == SVBFM_TRAIN;
+    DevSplit& S = is_train ? E->tr : E->te;
+    int rc = ingest_split(E, S, is_train, num_cases, num_cols, colptr, case_id, x, target);
+    if (rc) return rc;
+    // global case counts
+    double cnt = (double)num_cases, *d_cnt = RED(E->d_sc, 7);
+    SV_CUDA(E, cudaMemcpyAsync(d_cnt, &cnt, 8, cudaMemcpyHostToDevice, E->stream));
+    if (int r2 = allreduce_sum_f64(E, d_cnt, 1)) return r2;
+    SV_CUDA(E, cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, E->stream));
+    SV_CUDA(E, cudaStreamSynchronize(E->stream));
+    if (is_train) {
+        E->n_total = (uint64_t)cnt;
+        cudaFree(E->d_e); cudaFree(E->d_partial); E->d_e = nullptr; E->d_partial = nullptr;
+        if (dev_alloc(E, &E->d_e, num_cases)) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->d_partial, (size_t)E->n_tiles * 4)) return SVBFM_ERR_OOM;
+    } else {
+        E->nt_total = (uint64_t)cnt;
+        cudaFree(E->d_pred_test); cudaFree(E->d_pred_sum); E->d_pred_test = nullptr; E->d_pred_sum = nullptr;
+        if (dev_alloc(E, &E->d_pred_test, num_cases)) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->d_pred_sum, num_cases)) return SVBFM_ERR_OOM;
+        SV_CUDA(E, cudaMemsetAsync(E->d_pred_sum, 0, std::max<size_t>(num_cases, 1) * 8, E->stream));
+        SV_CUDA(E, cudaMemsetAsync(E->d_pred_test, 0, std::max<size_t>(num_cases, 1) * 8, E->stream));
+        SV_CUDA(E, cudaStreamSynchronize(E->stream));
+    }
+    return SVBFM_OK;
+}
+
+int svbfm_set_state(svbfm_t* h, double w0_mean, double w0_var, const double* w_mean, const double* w_var, const double* v_mean,
+                    const double* v_var) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E || !w_mean || (E->K > 0 && !v_mean)) return fail(E, SVBFM_ERR_ARG, "svbfm_set_state: null argument");
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    size_t D = E->D, KD = (size_t)E->K * D;
+    double *tm = nullptr, *tv = nullptr;
+    SV_CUDA(E, cudaMalloc((void**)&tm, std::max<size_t>(KD, D) * 8));
+    SV_CUDA(E, cudaMalloc((void**)&tv, std::max<size_t>(KD, D) * 8));
+    cudaStream_t st = E->stream;
+    SV_CUDA(E, cudaMemcpyAsync(tm, w_mean, D * 8, cudaMemcpyHostToDevice, st));
+    if (w_var) SV_CUDA(E, cudaMemcpyAsync(tv, w_var, D * 8, cudaMemcpyHostToDevice, st));
+    k_pack<<<nblk(D), 256, 0, st>>>(tm, w_var ? tv : nullptr, D, E->d_pw);
+    SV_CUDA(E, cudaStreamSynchronize(st));
+    if (KD) {
+        SV_CUDA(E, cudaMemcpyAsync(tm, v_mean, KD * 8, cudaMemcpyHostToDevice, st));
+        if (v_var) SV_CUDA(E, cudaMemcpyAsync(tv, v_var, KD * 8, cudaMemcpyHostToDevice, st));
+        k_pack<<<nblk(KD), 256, 0, st>>>(tm, v_var ? tv : nullptr, KD, E->d_pv);
+        SV_CUDA(E, cudaStreamSynchronize(st));
+    }
+    cudaFree(tm); cudaFree(tv);
+    Scalars sc;
+    SV_CUDA(E, copy_sync(E, &sc, E->d_sc, sizeof(sc), cudaMemcpyDeviceToHost));
+    sc.w0_mean = w0_mean; sc.w0_var = w0_var;
+    if (!E->have_state) {
+        sc.alpha = 1.0;                                              // vb.h:693 / mcmc.h:1105
+        sc.sigma_0 = (E->cfg.method == SVBFM_MCMC) ? E->cfg.reg0 : 1.0;   // vb.h:694 / libfm.cpp:373
+        sc.min_target = E->cfg.min_target; sc.max_target = E->cfg.max_target;
+        sc.iter = 0; sc.nan_inf = 0; sc.alpha_ok = 1;
+        sc.nat_mu_0 = 0.0; sc.nat_sg_0 = (w0_var != 0.0) ? 1.0 / w0_var : 0.0; sc.rho_0 = 1.0; sc.t_w0 = 0;   // vbo.h:683-701
+    }
+    SV_CUDA(E, copy_sync(E, E->d_sc, &sc, sizeof(sc), cudaMemcpyHostToDevice));
+    E->have_state = true;
+    return check_launch(E, "set_state");
+}
+
+int svbfm_get_state(svbfm_t* h, double* w0_mean, double* w0_var, double* w_mean, double* w_var, double* v_mean, double* v_var) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E) return SVBFM_ERR_ARG;
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    size_t D = E->D, KD = (size_t)E->K * D;
+    cudaStream_t st = E->stream;
+    double *tm = nullptr, *tv = nullptr;
+    SV_CUDA(E, cudaMalloc((void**)&tm, std::max<size_t>(KD, D) * 8));
+    SV_CUDA(E, cudaMalloc((void**)&tv, std::max<size_t>(KD, D) * 8));
+    k_unpack<<<nblk(D), 256, 0, st>>>(E->d_pw, D, tm, tv);
+    if (w_mean) SV_CUDA(E, cudaMemcpyAsync(w_mean, tm, D * 8, cudaMemcpyDeviceToHost, st));
+    if (w_var) SV_CUDA(E, cudaMemcpyAsync(w_var, tv, D * 8, cudaMemcpyDeviceToHost, st));
+    SV_CUDA(E, cudaStreamSynchronize(st));
+    if (KD) {
+        k_unpack<<<nblk(KD), 256, 0, st>>>(E->d_pv, KD, tm, tv);
+        if (v_mean) SV_CUDA(E, cudaMemcpyAsync(v_mean, tm, KD * 8, cudaMemcpyDeviceToHost, st));
+        if (v_var) SV_CUDA(E, cudaMemcpyAsync(v_var, tv, KD * 8, cudaMemcpyDeviceToHost, st));
+        SV_CUDA(E, cudaStreamSynchronize(st));
+    }
+    cudaFree(tm); cudaFree(tv);
+    Scalars sc;
+    SV_CUDA(E, copy_sync(E, &sc, E->d_sc, sizeof(sc), cudaMemcpyDeviceToHost));
+    if (w0_mean) *w0_mean = sc.w0_mean;
+    if (w0_var) *w0_var = sc.w0_var;
+    return check_launch(E, "get_state");
+}
+
+int svbfm_get_hyper(svbfm_t* h, double* alpha, double* sigma_0, double* sigma_w, double* sigma_v) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E) return SVBFM_ERR_ARG;
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    SV_CUDA(E, cudaStreamSynchronize(E->stream));
+    Scalars sc;
+    SV_CUDA(E, copy_sync(E, &sc, E->d_sc, sizeof(sc), cudaMemcpyDeviceToHost));
+    if (alpha) *alpha = sc.alpha;
+    if (sigma_0) *sigma_0 = sc.sigma_0;
+    if (sigma_w) SV_CUDA(E, copy_sync(E, sigma_w, E->d_hyper_w, (size_t)E->G * 8, cudaMemcpyDeviceToHost));
+    if (sigma_v && E->K) SV_CUDA(E, copy_sync(E, sigma_v, E->d_hyper_v, (size_t)E->G * E->K * 8, cudaMemcpyDeviceToHost));
+    return SVBFM_OK;
+}
+
+int svbfm_set_hyper(svbfm_t* h, double alpha, double sigma_0, const double* sigma_w, const double* sigma_v) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E) return SVBFM_ERR_ARG;
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    SV_CUDA(E, cudaStreamSynchronize(E->stream));
+    Scalars sc;
+    SV_CUDA(E, copy_sync(E, &sc, E->d_sc, sizeof(sc), cudaMemcpyDeviceToHost));
+    sc.alpha = alpha; sc.sigma_0 = sigma_0;
+    SV_CUDA(E, copy_sync(E, E->d_sc, &sc, sizeof(sc), cudaMemcpyHostToDevice));
+    if (sigma_w) SV_CUDA(E, copy_sync(E, E->d_hyper_w, sigma_w, (size_t)E->G * 8, cudaMemcpyHostToDevice));
+    if (sigma_v && E->K) SV_CUDA(E, copy_sync(E, E->d_hyper_v, sigma_v, (size_t)E->G * E->K * 8, cudaMemcpyHostToDevice));
+    return SVBFM_OK;
+}
+
+int svbfm_begin(svbfm_t* h) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E) return SVBFM_ERR_ARG;
+    if (!E->have_state) return fail(E, SVBFM_ERR_ARG, "svbfm_begin: svbfm_set_state must be called first");
+    if (!E->d_e || !E->d_pred_test) return fail(E, SVBFM_ERR_ARG, "svbfm_begin: train and test data must be set first");
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    cudaStream_t st = E->stream;
+    Scalars sc;
+    SV_CUDA(E, copy_sync(E, &sc, E->d_sc, sizeof(sc), cudaMemcpyDeviceToHost));
+    sc.n_total = (double)E->n_total; sc.nt_total = (double)E->nt_total; sc.sum_t = 0.0; sc.w0_delta = 0.0;
+    SV_CUDA(E, copy_sync(E, E->d_sc, &sc, sizeof(sc), cudaMemcpyHostToDevice));
+    if (int rc = ensure_stats(E, 16)) return rc;
+    if (E->cfg.method == SVBFM_VB) {
+        // initial y-hat and T over train (vbs.h:37-44): e_i = y_i - yhat_i ; sum_t = sum_i T_i
+        if (int rc = predict<PRED_VB_TRAIN>(E, E->tr, E->d_e, 6, 1)) return rc;
+        SV_CUDA(E, cudaMemcpyAsync(&E->d_sc->sum_t, RED(E->d_sc, 6), 8, cudaMemcpyDeviceToDevice, st));
+    } else if (E->cfg.method == SVBFM_MCMC) {
+        if (int rc = predict<PRED_MC_TRAIN>(E, E->tr, E->d_e, 6, 1)) return rc;     // e = yhat - y (mcmcs.h:75-80)
+    }
+    SV_CUDA(E, cudaStreamSynchronize(st));
+    E->begun = true;
+    return check_launch(E, "begin");
+}
+
+int svbfm_run(svbfm_t* h, uint32_t n_iter, svbfm_iter_stats* out) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E) return SVBFM_ERR_ARG;
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    return run_iterations(E, n_iter, out);
+}
+int svbfm_vb_sweep(svbfm_t* h, svbfm_iter_stats* out) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E) return SVBFM_ERR_ARG;
+    if (E->cfg.method != SVBFM_VB) return fail(E, SVBFM_ERR_ARG, "svbfm_vb_sweep on a non-vb handle");
+    return svbfm_run(h, 1, out);
+}
+int svbfm_mcmc_sweep(svbfm_t* h, svbfm_iter_stats* out) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E) return SVBFM_ERR_ARG;
+    if (E->cfg.method != SVBFM_MCMC) return fail(E, SVBFM_ERR_ARG, "svbfm_mcmc_sweep on a non-mcmc handle");
+    return svbfm_run(h, 1, out);
+}
+int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t num_batch, svbfm_iter_stats* out) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    (void)batch_of_case; (void)num_batch; (void)out;
+    return fail(E, SVBFM_ERR_ARG, "svbfm_vb_online_epoch: not implemented yet");
+}
+
+int svbfm_predict(svbfm_t* h, int32_t split, double* out) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E || !out) return SVBFM_ERR_ARG;
+    if (split != SVBFM_TEST) return fail(E, SVBFM_ERR_ARG, "svbfm_predict: only the test split holds predictions");
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    SV_CUDA(E, cudaStreamSynchronize(E->stream));
+    size_t n = E->te.n;
+    if (E->cfg.method == SVBFM_MCMC) {
+        std::vector<double> s(n);
+        SV_CUDA(E, copy_sync(E, s.data(), E->d_pred_sum, n * 8, cudaMemcpyDeviceToHost));
+        Scalars sc;
+        SV_CUDA(E, copy_sync(E, &sc, E->d_sc, sizeof(sc), cudaMemcpyDeviceToHost));
+        double it = sc.iter ? (double)sc.iter : 1.0;
+        for (size_t i = 0; i < n; i++) out[i] = std::fmax(sc.min_target, std::fmin(sc.max_target, s[i] / it));   // mcmc.h:355-379
+    } else {
+        SV_CUDA(E, copy_sync(E, out, E->d_pred_test, n * 8, cudaMemcpyDeviceToHost));
+    }
+    return SVBFM_OK;
+}
+
+int svbfm_get_residuals(svbfm_t* h, double* e) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E || !e || !E->d_e) return SVBFM_ERR_ARG;
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    uint32_t n = E->tr.n;
+    double* tmp = nullptr;
+    SV_CUDA(E, cudaMalloc((void**)&tmp, std::max<size_t>(n, 1) * 8));
+    k_unpermute<<<nblk(n), 256, 0, E->stream>>>(E->d_e, E->tr.perm, n, tmp);
+    SV_CUDA(E, cudaMemcpyAsync(e, tmp, (size_t)n * 8, cudaMemcpyDeviceToHost, E->stream));
+    SV_CUDA(E, cudaStreamSynchronize(E->stream));
+    cudaFree(tmp);
+    return check_launch(E, "get_residuals");
+}
+
+int svbfm_get_sum_t(svbfm_t* h, double* sum_t) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E || !sum_t) return SVBFM_ERR_ARG;
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    SV_CUDA(E, cudaStreamSynchronize(E->stream));
+    SV_CUDA(E, copy_sync(E, sum_t, &E->d_sc->sum_t, 8, cudaMemcpyDeviceToHost));
+    return SVBFM_OK;
+}
+
+int svbfm_get_info(svbfm_t* h, svbfm_info* out) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E || !out) return SVBFM_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    out->num_runs = (uint32_t)E->runs.size();
+    out->num_tiles = E->n_tiles;
+    out->uniform_row_nnz = E->tr.uniformF;
+    out->all_ones = E->tr.all_ones;
+    out->kernel_launches = E->launches;
+    out->device_bytes = E->dev_bytes;
+    out->train_nnz = E->tr.nnz;
+    out->rows_reordered = E->rows_reordered;
+    out->world_size = (uint32_t)E->world;
+    return SVBFM_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- host helpers
+// Exported for the Python mirror of the learner shells (the C++ shells include host/init_state.h directly).
+#include "../host/init_state.h"
+extern "C" {
+// replaces: srand(time) + fm.init() + fm.w.init_normal + fm_learn_vb::init draws (see host/init_state.h)
+int svbfm_host_init_state(long seed, uint32_t D, int32_t K, double init_stdev, int32_t method, double* w0_mean, double* w0_var,
+                          double* w_mean, double* w_var, double* v_mean, double* v_var) {
+    svbfm_host::InitialState s;
+    svbfm_host::init_state(seed, D, K, init_stdev, method, s);
+    if (w0_mean) *w0_mean = s.w0_mean;
+    if (w0_var) *w0_var = s.w0_var;
+    size_t KD = (size_t)K * D;
+    if (w_mean) memcpy(w_mean, s.w_mean.data(), (size_t)D * 8);
+    if (w_var) memcpy(w_var, s.w_var.data(), (size_t)D * 8);
+    if (v_mean) memcpy(v_mean, s.v_mean.data(), KD * 8);
+    if (v_var) memcpy(v_var, s.v_var.data(), KD * 8);
+    return 0;
+}
+// replaces: std::random_shuffle(shuffle, shuffle + n) on the libc stream (fm_learn_vb_online_simultaneous.h:74)
+int svbfm_host_random_shuffle(uint32_t* a, uint32_t n) { svbfm_host::libc_random_shuffle(a, n); return 0; }
+}

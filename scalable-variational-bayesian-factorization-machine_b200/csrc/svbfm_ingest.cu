@@ -1,0 +1,358 @@
+// csrc/svbfm_ingest.cu -- device ingest of one data split handed over as CSC (reference DataSubset::data_t).
+//
+//   CSC (caller) --H2D--> stable radix sort by case id --> CSR (features ascending inside each case)
+//   train only:  need[j] = max "previous feature of the same case" over column j  --> field runs (host scan)
+//                case re-ordering so that run 0 streams, CSC rebuilt by a stable sort by feature id
+//                warp tiles (<= tile_entries CSC entries of ONE column) + list of heavy columns
+//
+// Replaces, for the device side, Data::create_data_t (reference src/libfm/src/Data.h:457-509) -- here in the
+// CSC -> CSR direction -- and adds the field-run scheduler the reference does not need (it sweeps columns one
+// by one, fm_learn_vb.h:395, 427). CUB is used for the two radix sorts and one scan: ingest plumbing, not the
+// sweep.
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cstring>
+#include "svbfm_internal.h"
+
+namespace svb {
+
+int fail(Engine* E, int code, const std::string& msg) {
+    if (E) E->err = msg;
+    return code;
+}
+
+static __global__ void k_any_not_one(const float* __restrict__ x, uint64_t n, uint32_t* flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < n; i += stride) bad |= (x[i] != 1.0f);
+    if (bad) *flag = 1;
+}
+
+// feature id of every CSC entry: upper_bound over colptr
+static __global__ void k_col_of_entry(const uint64_t* __restrict__ colptr, uint32_t ncols, uint64_t nnz, uint32_t* __restrict__ out) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    uint32_t lo = 0, hi = ncols;   // find j with colptr[j] <= p < colptr[j+1]
+    while (hi - lo > 1) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (colptr[mid] <= p) lo = mid; else hi = mid;
+    }
+    out[p] = lo;
+}
+
+static __global__ void k_iota(uint32_t* a, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (uint32_t)i;
+}
+
+static __global__ void k_check_case_ids(const uint32_t* __restrict__ ids, uint64_t nnz, uint32_t n, uint32_t* flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz && ids[i] >= n) *flag = 1;
+}
+
+// rowptr[i] = first position in sorted_keys with key >= i   (i in [0, n])
+static __global__ void k_rowptr_from_sorted(const uint32_t* __restrict__ keys, uint64_t nnz, uint32_t n, uint64_t* __restrict__ rowptr) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    uint64_t lo = 0, hi = nnz;
+    while (lo < hi) {
+        uint64_t mid = lo + (hi - lo) / 2;
+        if (keys[mid] < (uint32_t)i) lo = mid + 1; else hi = mid;
+    }
+    rowptr[i] = lo;
+}
+
+static __global__ void k_gather_u32(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t n, uint32_t* __restrict__ dst) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+static __global__ void k_gather_f32(const float* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t n, float* __restrict__ dst) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
+// per case: duplicate feature ids, row-length uniformity, and need[] for the run scheduler
+static __global__ void k_scan_rows(const uint64_t* __restrict__ rowptr, const uint32_t* __restrict__ rcol, uint32_t n,
+                                   uint32_t* __restrict__ need /*[ncols] or null*/, uint32_t* flags /*[0]=dup [1]=non-uniform*/) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t b = rowptr[i], e = rowptr[i + 1];
+    if ((e - b) != (rowptr[1] - rowptr[0])) flags[1] = 1;
+    for (uint64_t k = b + 1; k < e; k++) {
+        uint32_t c0 = rcol[k - 1], c1 = rcol[k];
+        if (c0 == c1) flags[0] = 1;
+        if (need) atomicMax(&need[c1], c0 + 1);   // column c1 must start a new run if c0 is inside the current run
+    }
+}
+
+static __global__ void k_invert_perm(const uint32_t* __restrict__ perm, uint32_t n, uint32_t* __restrict__ inv, uint32_t* not_identity) {
+    uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    uint32_t o = perm[d];
+    inv[o] = d;
+    if (o != d) *not_identity = 1;
+}
+
+static __global__ void k_row_lengths_perm(const uint64_t* __restrict__ rowptr, const uint32_t* __restrict__ perm, uint32_t n, uint64_t* __restrict__ len) {
+    uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n) { uint32_t o = perm[d]; len[d] = rowptr[o + 1] - rowptr[o]; }
+    if (d == n) len[d] = 0;
+}
+
+static __global__ void k_permute_rows(const uint64_t* __restrict__ old_ptr, const uint32_t* __restrict__ old_col, const float* __restrict__ old_val,
+                                      const uint32_t* __restrict__ perm, uint32_t n, const uint64_t* __restrict__ new_ptr,
+                                      uint32_t* __restrict__ new_col, float* __restrict__ new_val, uint32_t* __restrict__ new_row_of_entry) {
+    uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    uint32_t o = perm[d];
+    uint64_t src = old_ptr[o], dst = new_ptr[d], len = old_ptr[o + 1] - src;
+    for (uint64_t k = 0; k < len; k++) {
+        new_col[dst + k] = old_col[src + k];
+        if (old_val) new_val[dst + k] = old_val[src + k];
+        new_row_of_entry[dst + k] = d;
+    }
+}
+
+static __global__ void k_permute_f32(const float* __restrict__ src, const uint32_t* __restrict__ perm, uint32_t n, float* __restrict__ dst) {
+    uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n) dst[d] = src[perm[d]];
+}
+
+static inline unsigned nblk(uint64_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t); }
+
+static int bits_for(uint64_t n) {
+    int b = 1;
+    while (b < 32 && (1ull << b) < n) b++;
+    return b;
+}
+
+// stable sort of (key, value) pairs by key; returns device arrays (caller frees with cudaFree)
+static int sort_pairs(Engine* E, const uint32_t* keys_in, const uint32_t* vals_in, uint64_t n, uint64_t key_range,
+                      uint32_t** keys_out, uint32_t** vals_out) {
+    SV_CUDA(E, cudaMalloc((void**)keys_out, std::max<uint64_t>(n, 1) * 4));
+    SV_CUDA(E, cudaMalloc((void**)vals_out, std::max<uint64_t>(n, 1) * 4));
+    if (n == 0) return 0;
+    size_t tmp_bytes = 0;
+    int end_bit = bits_for(key_range);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, *keys_out, vals_in, *vals_out, (int64_t)n, 0, end_bit, E->stream);
+    void* tmp = nullptr;
+    SV_CUDA(E, cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, *keys_out, vals_in, *vals_out, (int64_t)n, 0, end_bit, E->stream);
+    cudaError_t e2 = cudaStreamSynchronize(E->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(E, SVBFM_ERR_CUDA, std::string("radix sort: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return 0;
+}
+
+void free_split(Engine* E, DevSplit& S) {
+    (void)E;
+    cudaFree(S.colptr); cudaFree(S.crow); cudaFree(S.cval); cudaFree(S.rowptr); cudaFree(S.rcol); cudaFree(S.rval);
+    cudaFree(S.y); cudaFree(S.perm);
+    S = DevSplit();
+}
+
+int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t ncols, const uint64_t* colptr, const uint32_t* case_id,
+                 const float* x, const float* target) {
+    cudaStream_t st = E->stream;
+    free_split(E, S);
+    if (ncols > E->D) return fail(E, SVBFM_ERR_ARG, "set_csc: num_cols exceeds num_attribute");
+    if (colptr[0] != 0) return fail(E, SVBFM_ERR_ARG, "set_csc: colptr[0] != 0");
+    for (uint32_t j = 0; j < ncols; j++)
+        if (colptr[j + 1] < colptr[j]) return fail(E, SVBFM_ERR_ARG, "set_csc: colptr not monotone");
+    uint64_t nnz = colptr[ncols];
+    if (nnz >= (1ull << 32)) return fail(E, SVBFM_ERR_ARG, "set_csc: more than 2^32-1 entries per rank are not supported");
+    S.n = n; S.n_cols = ncols; S.nnz = nnz;
+    // mcmc also draws the attributes that never occur in train (reference fm_learn_mcmc.h:449-457, 568-577):
+    // they become empty trailing columns of the last run.
+    S.ncols_ext = (is_train && E->cfg.method == SVBFM_MCMC) ? E->D : ncols;
+    S.h_colptr.assign(colptr, colptr + ncols + 1);
+    S.h_colptr.resize((size_t)S.ncols_ext + 1, nnz);
+
+    if (dev_alloc(E, &S.colptr, (size_t)S.ncols_ext + 1)) return SVBFM_ERR_OOM;
+    if (dev_alloc(E, &S.crow, nnz)) return SVBFM_ERR_OOM;
+    if (dev_alloc(E, &S.y, n)) return SVBFM_ERR_OOM;
+    float* d_x = nullptr;
+    SV_CUDA(E, cudaMalloc((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4));
+    SV_CUDA(E, cudaMemcpyAsync(S.colptr, S.h_colptr.data(), ((size_t)S.ncols_ext + 1) * 8, cudaMemcpyHostToDevice, st));
+    SV_CUDA(E, cudaMemcpyAsync(S.crow, case_id, nnz * 4, cudaMemcpyHostToDevice, st));
+    SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, st));
+    SV_CUDA(E, cudaMemcpyAsync(S.y, target, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+
+    uint32_t* d_flags = nullptr;   // [0] any x != 1  [1] case id out of range  [2] duplicate feature in a case  [3] non-uniform  [4] perm not identity
+    SV_CUDA(E, cudaMalloc((void**)&d_flags, 8 * 4));
+    SV_CUDA(E, cudaMemsetAsync(d_flags, 0, 8 * 4, st));
+    if (nnz) {
+        k_any_not_one<<<std::min<unsigned>(nblk(nnz), 148 * 16), 256, 0, st>>>(d_x, nnz, d_flags + 0);
+        k_check_case_ids<<<nblk(nnz), 256, 0, st>>>(S.crow, nnz, n, d_flags + 1);
+    }
+    // CSC -> CSR: feature id per entry, stable sort by case id
+    uint32_t *d_colof = nullptr, *d_idx = nullptr, *d_skeys = nullptr, *d_sidx = nullptr;
+    SV_CUDA(E, cudaMalloc((void**)&d_colof, std::max<uint64_t>(nnz, 1) * 4));
+    SV_CUDA(E, cudaMalloc((void**)&d_idx, std::max<uint64_t>(nnz, 1) * 4));
+    if (nnz) {
+        k_col_of_entry<<<nblk(nnz), 256, 0, st>>>(S.colptr, ncols, nnz, d_colof);
+        k_iota<<<nblk(nnz), 256, 0, st>>>(d_idx, nnz);
+    }
+    uint32_t h_flags[8];
+    SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
+    SV_CUDA(E, cudaStreamSynchronize(st));
+    if (h_flags[1]) { cudaFree(d_x); cudaFree(d_flags); cudaFree(d_colof); cudaFree(d_idx); return fail(E, SVBFM_ERR_ARG, "set_csc: case id out of range"); }
+    S.all_ones = (h_flags[0] == 0);
+    if (int r = sort_pairs(E, S.crow, d_idx, nnz, std::max<uint32_t>(n, 1), &d_skeys, &d_sidx)) return r;
+    cudaFree(d_idx);
+    uint64_t* d_rowptr = nullptr;
+    SV_CUDA(E, cudaMalloc((void**)&d_rowptr, ((size_t)n + 1) * 8));
+    k_rowptr_from_sorted<<<nblk((uint64_t)n + 1), 256, 0, st>>>(d_skeys, nnz, n, d_rowptr);
+    cudaFree(d_skeys);
+    uint32_t* d_rcol = nullptr; float* d_rval = nullptr;
+    SV_CUDA(E, cudaMalloc((void**)&d_rcol, std::max<uint64_t>(nnz, 1) * 4));
+    if (!S.all_ones) SV_CUDA(E, cudaMalloc((void**)&d_rval, std::max<uint64_t>(nnz, 1) * 4));
+    if (nnz) {
+        k_gather_u32<<<nblk(nnz), 256, 0, st>>>(d_colof, d_sidx, nnz, d_rcol);
+        if (!S.all_ones) k_gather_f32<<<nblk(nnz), 256, 0, st>>>(d_x, d_sidx, nnz, d_rval);
+    }
+    cudaFree(d_sidx); cudaFree(d_colof);
+
+    // per-case scan: duplicates, uniform length, need[]
+    uint32_t* d_need = nullptr;
+    if (is_train) {
+        SV_CUDA(E, cudaMalloc((void**)&d_need, std::max<uint32_t>(S.ncols_ext, 1) * 4));
+        SV_CUDA(E, cudaMemsetAsync(d_need, 0, std::max<uint32_t>(S.ncols_ext, 1) * 4, st));
+    }
+    if (n) k_scan_rows<<<nblk(n), 256, 0, st>>>(d_rowptr, d_rcol, n, d_need, d_flags + 2);
+    SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
+    SV_CUDA(E, cudaStreamSynchronize(st));
+    if (h_flags[2]) {
+        cudaFree(d_x); cudaFree(d_flags); cudaFree(d_rowptr); cudaFree(d_rcol); cudaFree(d_rval); cudaFree(d_need);
+        return fail(E, SVBFM_ERR_DATA, "set_csc: a feature id occurs twice in one case; not supported");
+    }
+    bool uniform = (n > 0) && (h_flags[3] == 0);
+    uint32_t F = uniform ? (uint32_t)(nnz / n) : 0;
+    if (E->world > 1) {   // all ranks must agree on the kernel variant? no: variants are rank-local; only runs must agree
+    }
+
+    if (is_train) {
+        // ---- field runs (global when sharded: need[] is max-reduced over ranks)
+        if (int r = allreduce(E, d_need, S.ncols_ext, 3 /*ncclUint32*/, 2 /*ncclMax*/)) return r;
+        std::vector<uint32_t> need(S.ncols_ext);
+        SV_CUDA(E, cudaMemcpyAsync(need.data(), d_need, (size_t)S.ncols_ext * 4, cudaMemcpyDeviceToHost, st));
+        SV_CUDA(E, cudaStreamSynchronize(st));
+        cudaFree(d_need);
+        E->runs.clear();
+        uint32_t run_start = 0;
+        for (uint32_t j = 0; j < S.ncols_ext; j++) {
+            if (need[j] > run_start) {   // a case of column j already has a feature inside [run_start, j)
+                Run r; r.col_begin = run_start; r.col_end = j;
+                E->runs.push_back(r);
+                run_start = j;
+            }
+        }
+        if (S.ncols_ext > 0) { Run r; r.col_begin = run_start; r.col_end = S.ncols_ext; E->runs.push_back(r); }
+        for (auto& r : E->runs) r.nnz = S.h_colptr[r.col_end] - S.h_colptr[r.col_begin];
+
+        // ---- case re-ordering: device order = order of the cases inside run 0 (when run 0 holds every case once)
+        bool reorder = !(E->cfg.flags & SVBFM_FLAG_NO_ROW_REORDER) && !E->runs.empty() && E->runs[0].nnz == n && n > 0 && nnz > 0;
+        if (reorder) {
+            uint32_t *d_perm = nullptr, *d_inv = nullptr;
+            SV_CUDA(E, cudaMalloc((void**)&d_perm, (size_t)n * 4));
+            SV_CUDA(E, cudaMalloc((void**)&d_inv, (size_t)n * 4));
+            SV_CUDA(E, cudaMemcpyAsync(d_perm, S.crow + S.h_colptr[E->runs[0].col_begin], (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+            k_invert_perm<<<nblk(n), 256, 0, st>>>(d_perm, n, d_inv, d_flags + 4);
+            SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
+            SV_CUDA(E, cudaStreamSynchronize(st));
+            cudaFree(d_inv);
+            if (h_flags[4]) {
+                // new CSR = cases gathered in device order
+                uint64_t *d_len = nullptr, *d_newptr = nullptr;
+                SV_CUDA(E, cudaMalloc((void**)&d_len, ((size_t)n + 1) * 8));
+                SV_CUDA(E, cudaMalloc((void**)&d_newptr, ((size_t)n + 1) * 8));
+                k_row_lengths_perm<<<nblk((uint64_t)n + 1), 256, 0, st>>>(d_rowptr, d_perm, n, d_len);
+                size_t tmp_bytes = 0;
+                cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_newptr, (int64_t)n + 1, st);
+                void* tmp = nullptr;
+                SV_CUDA(E, cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+                cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_len, d_newptr, (int64_t)n + 1, st);
+                uint32_t *d_ncol = nullptr, *d_nrow = nullptr; float* d_nval = nullptr;
+                SV_CUDA(E, cudaMalloc((void**)&d_ncol, nnz * 4));
+                SV_CUDA(E, cudaMalloc((void**)&d_nrow, nnz * 4));
+                if (!S.all_ones) SV_CUDA(E, cudaMalloc((void**)&d_nval, nnz * 4));
+                k_permute_rows<<<nblk(n), 256, 0, st>>>(d_rowptr, d_rcol, d_rval, d_perm, n, d_newptr, d_ncol, d_nval, d_nrow);
+                SV_CUDA(E, cudaStreamSynchronize(st));
+                cudaFree(tmp); cudaFree(d_len);
+                cudaFree(d_rowptr); cudaFree(d_rcol); cudaFree(d_rval);
+                d_rowptr = d_newptr; d_rcol = d_ncol; d_rval = d_nval;
+                // new CSC = stable sort of the new CSR entries by feature id (case ids stay ascending per column)
+                uint32_t *d_eidx = nullptr, *d_k2 = nullptr, *d_v2 = nullptr;
+                SV_CUDA(E, cudaMalloc((void**)&d_eidx, nnz * 4));
+                k_iota<<<nblk(nnz), 256, 0, st>>>(d_eidx, nnz);
+                if (int r = sort_pairs(E, d_rcol, d_eidx, nnz, std::max<uint32_t>(ncols, 1), &d_k2, &d_v2)) return r;
+                cudaFree(d_eidx); cudaFree(d_k2);
+                k_gather_u32<<<nblk(nnz), 256, 0, st>>>(d_nrow, d_v2, nnz, S.crow);
+                if (!S.all_ones) {
+                    float* d_cv = nullptr;
+                    SV_CUDA(E, cudaMalloc((void**)&d_cv, nnz * 4));
+                    k_gather_f32<<<nblk(nnz), 256, 0, st>>>(d_rval, d_v2, nnz, d_cv);
+                    SV_CUDA(E, cudaStreamSynchronize(st));
+                    cudaFree(d_x); d_x = d_cv;
+                }
+                SV_CUDA(E, cudaStreamSynchronize(st));
+                cudaFree(d_v2); cudaFree(d_nrow);
+                float* d_y2 = nullptr;
+                SV_CUDA(E, cudaMalloc((void**)&d_y2, (size_t)n * 4));
+                k_permute_f32<<<nblk(n), 256, 0, st>>>(S.y, d_perm, n, d_y2);
+                SV_CUDA(E, cudaStreamSynchronize(st));
+                cudaFree(S.y); S.y = d_y2;
+                S.perm = d_perm; E->dev_bytes += (size_t)n * 4;
+                E->rows_reordered = true;
+            } else {
+                cudaFree(d_perm);
+            }
+        }
+    }
+    cudaFree(d_flags);
+    // keep
+    S.rcol = d_rcol; E->dev_bytes += nnz * 4;
+    S.rval = d_rval; if (d_rval) E->dev_bytes += nnz * 4;
+    if (S.all_ones) { cudaFree(d_x); S.cval = nullptr; } else { S.cval = d_x; E->dev_bytes += nnz * 4; }
+    S.uniformF = F;
+    if (F > 0) { cudaFree(d_rowptr); S.rowptr = nullptr; } else { S.rowptr = d_rowptr; E->dev_bytes += ((size_t)n + 1) * 8; }
+
+    if (is_train) {
+        // ---- warp tiles + heavy columns (host, O(#columns))
+        uint32_t T = E->tile_entries;
+        std::vector<uint32_t> tile_col, col_tile0((size_t)S.ncols_ext + 1), heavy;
+        std::vector<uint64_t> tile_begin;
+        for (auto& r : E->runs) {
+            r.tile_begin = (uint32_t)tile_col.size();
+            r.heavy_begin = (uint32_t)heavy.size();
+            for (uint32_t j = r.col_begin; j < r.col_end; j++) {
+                col_tile0[j] = (uint32_t)tile_col.size();
+                uint64_t b = S.h_colptr[j], e = S.h_colptr[j + 1];
+                uint64_t nt = (e - b + T - 1) / T;
+                for (uint64_t p = b; p < e; p += T) { tile_col.push_back(j); tile_begin.push_back(p); }
+                if (nt > 8) heavy.push_back(j);
+            }
+            r.tile_end = (uint32_t)tile_col.size();
+            r.heavy_end = (uint32_t)heavy.size();
+        }
+        col_tile0[S.ncols_ext] = (uint32_t)tile_col.size();
+        E->n_tiles = (uint32_t)tile_col.size();
+        E->n_heavy = (uint32_t)heavy.size();
+        cudaFree(E->d_tile_col); cudaFree(E->d_tile_begin); cudaFree(E->d_col_tile0); cudaFree(E->d_heavy_cols);
+        E->d_tile_col = nullptr; E->d_tile_begin = nullptr; E->d_col_tile0 = nullptr; E->d_heavy_cols = nullptr;
+        if (dev_alloc(E, &E->d_tile_col, tile_col.size())) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->d_tile_begin, tile_begin.size())) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->d_col_tile0, col_tile0.size())) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->d_heavy_cols, heavy.size())) return SVBFM_ERR_OOM;
+        SV_CUDA(E, cudaMemcpyAsync(E->d_tile_col, tile_col.data(), tile_col.size() * 4, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemcpyAsync(E->d_tile_begin, tile_begin.data(), tile_begin.size() * 8, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemcpyAsync(E->d_col_tile0, col_tile0.data(), col_tile0.size() * 4, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemcpyAsync(E->d_heavy_cols, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaStreamSynchronize(st));
+    }
+    SV_CUDA(E, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace svb

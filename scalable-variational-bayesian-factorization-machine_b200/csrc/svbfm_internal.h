@@ -1,0 +1,161 @@
+// csrc/svbfm_internal.h -- shared between svbfm_engine.cu (kernels + C-ABI) and svbfm_ingest.cu (device ingest).
+//
+// Device layout (DESIGN.md "Data layout in HBM"):
+//   * residuals e_i: fp64 SoA, one per train case, in DEVICE case order (cases are re-ordered so that the
+//     first field run streams; perm[] maps device order -> caller order).
+//   * design matrix twice: CSC per column (colptr u64, case id u32, x f32) for the column sweeps and CSR per
+//     case (rowptr u64 or implicit i*F, feature id u32, x f32) for "the other fields of this case".
+//     x arrays are elided when every x == 1.0f (one-hot data).
+//   * parameters: double2 {mean, var} per (factor, feature), row-major [f][j] like DMatrix::value[f][j]
+//     (reference src/util/matrix.h:91-109); one factor row (D*16 B) is L2 resident during its sweep.
+//   * no per-case T_i, q_i, S2_i, S3_i arrays: only sum_i T_i is ever consumed (vb.h:446-454, 659-663), and
+//     q/S2/S3 minus the own column are re-derived from the case's other features (SURVEY.md section 8d caveat).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/svbfm.h"
+
+namespace svb {
+
+struct DevSplit {
+    uint32_t n = 0;          // local cases
+    uint32_t n_cols = 0;     // columns present in this split's data_t (max feature id + 1)
+    uint64_t nnz = 0;
+    uint64_t* colptr = nullptr;   // [ncols_ext+1] (mcmc train: extended to D with empty columns)
+    uint32_t ncols_ext = 0;
+    uint32_t* crow = nullptr;     // [nnz] case ids, ascending inside each column (device order)
+    float* cval = nullptr;        // [nnz] or null when all_ones
+    uint64_t* rowptr = nullptr;   // [n+1] or null when uniformF > 0
+    uint32_t* rcol = nullptr;     // [nnz] feature ids, ascending inside each case
+    float* rval = nullptr;        // [nnz] or null when all_ones
+    uint32_t uniformF = 0;
+    bool all_ones = false;
+    float* y = nullptr;           // [n] device order
+    uint32_t* perm = nullptr;     // [n] device order -> caller order, null = identity
+    std::vector<uint64_t> h_colptr;   // host copy (tiles, runs)
+};
+
+// One maximal group of consecutive, pairwise case-disjoint columns: updating all of them in one launch
+// equals the reference's ascending sequential order (fm_learn_vb.h:395-405, 427-438).
+struct Run {
+    uint32_t col_begin = 0, col_end = 0;
+    uint32_t tile_begin = 0, tile_end = 0;      // range in the global tile arrays
+    uint32_t heavy_begin = 0, heavy_end = 0;    // range in heavy_cols
+    uint64_t nnz = 0;
+};
+
+struct RowView {
+    const uint64_t* rowptr;
+    const uint32_t* rcol;
+    const float* rval;
+    uint32_t F;
+};
+
+// device-resident scalar state; kernels read it, single-thread kernels update it
+struct Scalars {
+    double alpha, sigma_0;        // vb: alpha, sigma_0          mcmc: alpha, reg0
+    double w0_mean, w0_var;       // vb: mu_0', sigma_0'         mcmc: w0, unused
+    double sum_t;                 // sum_i T_i (global)
+    double n_total, nt_total;     // global number of train / test cases
+    double w0_delta;              // pending shift of every e_i
+    double red[8];                // reduction results (global after allreduce)
+    double min_target, max_target;
+    double nat_mu_0, nat_sg_0, rho_0;   // vb_online natural parameters / rate of w0 and the hyper-parameters
+    double batch_n;               // vb_online: (global) number of cases in the current batch
+    unsigned long long nan_inf;
+    uint32_t iter;
+    uint32_t t_w0;
+    int32_t alpha_ok;
+    int32_t pad;
+};
+
+// stats slot written on the device once per iteration
+struct DevStats {
+    double test_rmse, train_stat, free_energy, alpha, rmse_this;
+    double has_fe, nan_inf, pad;
+};
+
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+
+struct Engine {
+    svbfm_config cfg{};
+    std::string err;
+    int dev = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    uint32_t D = 0, G = 1;
+    int K = 0;
+    // groups
+    std::vector<uint32_t> h_group, h_n_per_group;
+    uint32_t* d_group = nullptr;
+    double* d_n_per_group = nullptr;
+    // data
+    DevSplit tr, te;
+    std::vector<Run> runs;
+    uint32_t* d_tile_col = nullptr;
+    uint64_t* d_tile_begin = nullptr;
+    uint32_t* d_col_tile0 = nullptr;   // [ncols_ext+1] first tile of each column
+    uint32_t* d_heavy_cols = nullptr;
+    uint32_t n_tiles = 0, n_heavy = 0, tile_entries = 1024;
+    bool rows_reordered = false;
+    // state
+    double2* d_pw = nullptr;          // [D]
+    double2* d_pv = nullptr;          // [K][D]
+    double* d_hyper_w = nullptr;      // vb: sigma_w[G]      mcmc: w_lambda[G]
+    double* d_hyper_v = nullptr;      // vb: sigma_v[G][K]   mcmc: v_lambda[G][K]
+    double* d_mu_w = nullptr;         // mcmc: w_mu[G]
+    double* d_mu_v = nullptr;         // mcmc: v_mu[G][K]
+    Scalars* d_sc = nullptr;
+    bool have_state = false, begun = false;
+    // vb_online per-parameter natural state
+    double2* d_nat_w = nullptr;       // [D]   {eta1, eta2}
+    double2* d_nat_v = nullptr;       // [K][D]
+    uint32_t* d_t_w = nullptr;        // [D] t_wj
+    uint32_t* d_t_v = nullptr;        // [D] t_vj
+    double* d_col_count = nullptr;    // [D] global count of each feature in train
+    // work buffers
+    double* d_e = nullptr;            // [n]
+    double* d_partial = nullptr;      // [n_tiles][4]
+    double* d_colsum = nullptr;       // [D][4]
+    double* d_delta = nullptr;        // [D]
+    double* d_dT = nullptr;           // [D]
+    double* d_red_partial = nullptr;  // reduction scratch
+    double* d_grp_sums = nullptr;     // [(K+1)][G][2]
+    double* d_pred_test = nullptr;    // [nt] last prediction (vb: clamped)
+    double* d_pred_sum = nullptr;     // [nt] mcmc running sum of clamped predictions
+    DevStats* d_stats = nullptr;
+    uint32_t stats_cap = 0;
+    uint64_t launches = 0;
+    uint64_t dev_bytes = 0;
+    // multi-GPU
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    uint64_t n_total = 0, nt_total = 0;
+};
+
+// svbfm_ingest.cu
+int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t num_cases, uint32_t num_cols, const uint64_t* colptr,
+                 const uint32_t* case_id, const float* x, const float* target);
+void free_split(Engine* E, DevSplit& S);
+int allreduce(Engine* E, void* buf, size_t count, int dtype /*nccl*/, int op /*nccl*/);
+
+// error helpers
+int fail(Engine* E, int code, const std::string& msg);
+#define SV_CUDA(E, call)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t _e = (call);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            return svb::fail((E), SVBFM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));   \
+    } while (0)
+
+template <typename T>
+int dev_alloc(Engine* E, T** p, size_t count) {
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) return fail(E, SVBFM_ERR_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    E->dev_bytes += count * sizeof(T);
+    return 0;
+}
+
+}  // namespace svb

@@ -1,0 +1,737 @@
+// csrc/svbfm_kernels.cuh -- hand-written sm_100a kernels of the VB / MCMC coordinate sweep.
+//
+// One FIELD RUN (consecutive, case-disjoint columns) of one factor is swept by
+//     k_sweep_reduce   warp per tile (<= tile_entries CSC entries of one column): per-entry terms -> warp
+//                      shuffle reduction -> one partial {A,B,C1,C2} per tile          (gather e_i, other-field params)
+//     k_combine_*      tiles -> column sums (heavy columns by a CTA; all columns when an allreduce follows)
+//     k_finalize       thread per column: posterior mean/variance (VB), Gaussian draw (MCMC), natural-parameter
+//                      step (vb_online); non-finite guards; delta_j; d(sum T)_j
+//     k_sweep_apply    warp per tile: e_i += x*h*delta_j                               (scatter e_i)
+// which is the reference's update_v / update_w / draw_v / draw_w (fm_learn_vb.h:527-644,
+// fm_learn_mcmc.h:671-718,780-835, fm_learn_vb_online.h:499-627) for every column of the run at once.
+//
+// All sums are deterministic (fixed tile order, tree reductions); no floating-point atomics.
+#pragma once
+#include "svbfm_internal.h"
+
+namespace svb {
+
+enum { KIND_VB_W = 0, KIND_VB_V = 1, KIND_MC_W = 2, KIND_MC_V = 3, KIND_VBO_W = 4, KIND_VBO_V = 5 };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic block reduction of NV values; result valid in thread 0
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /*[NV*32]*/) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = warp_sum(v[k]);
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < NV; k++) smem[k * 32 + w] = v[k];
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double x = (lane < nw) ? smem[k * 32 + lane] : 0.0;
+            v[k] = warp_sum(x);
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// "other fields of case i": h = sum_{c != j} mu_c x_c ; h1 = sum sigma_c x_c^2 ; h2 = sum mu_c^2 x_c^2
+// (= q_i - x mu_j, S2_i - x^2 sigma_j, S3_i - x^2 mu_j^2 of fm_learn_vb.h:592-593, 628-630)
+template <int FT, bool ONES, bool VAR>
+__device__ __forceinline__ void others(const RowView& rv, const double2* __restrict__ pf, uint32_t i, uint32_t j,
+                                       double& h, double& h1, double& h2) {
+    h = 0.0; h1 = 0.0; h2 = 0.0;
+    if constexpr (FT == 2) {
+        uint2 c = __ldg(reinterpret_cast<const uint2*>(rv.rcol) + i);
+        bool first = (c.x == j);
+        uint32_t o = first ? c.y : c.x;
+        double2 P = __ldg(&pf[o]);
+        if constexpr (ONES) {
+            h = P.x;
+            if constexpr (VAR) { h1 = P.y; h2 = P.x * P.x; }
+        } else {
+            float2 xv = __ldg(reinterpret_cast<const float2*>(rv.rval) + i);
+            float x = first ? xv.y : xv.x;
+            h = P.x * x;
+            if constexpr (VAR) { h1 = P.y * x * x; h2 = P.x * P.x * x * x; }
+        }
+    } else {
+        uint64_t b, e;
+        if constexpr (FT == 1) { b = (uint64_t)i * rv.F; e = b + rv.F; }
+        else { b = __ldg(&rv.rowptr[i]); e = __ldg(&rv.rowptr[i + 1]); }
+        for (uint64_t k = b; k < e; k++) {
+            uint32_t c = __ldg(&rv.rcol[k]);
+            if (c == j) continue;
+            double2 P = __ldg(&pf[c]);
+            if constexpr (ONES) {
+                h += P.x;
+                if constexpr (VAR) { h1 += P.y; h2 += P.x * P.x; }
+            } else {
+                float x = __ldg(&rv.rval[k]);
+                h += P.x * x;
+                if constexpr (VAR) { h1 += P.y * x * x; h2 += P.x * P.x * x * x; }
+            }
+        }
+    }
+}
+
+struct SweepArgs {
+    const uint32_t* tile_col;
+    const uint64_t* tile_begin;
+    const uint64_t* colptr;
+    const uint32_t* crow;
+    const float* cval;
+    RowView rv;
+    double* e;
+    const double2* pf;        // params of this factor ([D]) or the w params
+    double* partial;          // [n_tiles][4]
+    const double* delta;      // [D]
+    uint32_t tile0, ntiles, tile_entries;
+    const uint8_t* in_batch;  // vb_online: 1 when the case belongs to the current batch (null otherwise)
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// per-entry terms of one column (pass 1 of update_v/update_w/draw_v/draw_w)
+template <int KIND, int FT, bool ONES>
+__global__ void __launch_bounds__(256) k_sweep_reduce(SweepArgs a) {
+    uint32_t w = (blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5);
+    if (w >= a.ntiles) return;
+    uint32_t t = a.tile0 + w, lane = threadIdx.x & 31;
+    uint32_t j = __ldg(&a.tile_col[t]);
+    uint64_t b = __ldg(&a.tile_begin[t]);
+    uint64_t cend = __ldg(&a.colptr[j + 1]);
+    uint64_t e_ = b + a.tile_entries < cend ? b + a.tile_entries : cend;
+    double2 Pj = __ldg(&a.pf[j]);
+    double mu = Pj.x;
+    double A = 0.0, B = 0.0, C1 = 0.0, C2 = 0.0;
+    for (uint64_t p = b + lane; p < e_; p += 32) {
+        uint32_t i = __ldg(&a.crow[p]);
+        float xf = 1.0f;
+        if constexpr (!ONES) xf = __ldg(&a.cval[p]);
+        double ei = a.e[i];
+        double xx = (double)(xf * xf);     // the reference forms x*x in float (FM_FLOAT), then promotes
+        if constexpr (KIND == KIND_VB_W || KIND == KIND_VBO_W) {
+            A += xf * (ei + xf * mu);                              // vb.h:537
+            B += xx;                                               // vb.h:538
+        } else if constexpr (KIND == KIND_MC_W) {
+            A += xf * (ei - mu * xf);                              // mcmc.h:677
+            B += xx;
+        } else if constexpr (KIND == KIND_VB_V || KIND == KIND_VBO_V) {
+            double h, h1, h2;
+            others<FT, ONES, true>(a.rv, a.pf, i, j, h, h1, h2);
+            A += xf * h * (ei + xf * mu * h);                      // vb.h:594
+            B += xx * h * h + xx * h1;                             // vb.h:595
+            C1 += xx * h1;                                         // sum of pass-2 h1 (vb.h:629)
+            C2 += xx * h2;                                         // sum of pass-2 h2 (vb.h:630)
+        } else {                                                   // KIND_MC_V
+            double h, h1, h2;
+            others<FT, ONES, false>(a.rv, a.pf, i, j, h, h1, h2);
+            double hh = xf * h;                                    // mcmc.h:789
+            A += hh * ei;                                          // mcmc.h:790
+            B += hh * hh;                                          // mcmc.h:791
+        }
+    }
+    A = warp_sum(A); B = warp_sum(B);
+    if constexpr (KIND == KIND_VB_V || KIND == KIND_VBO_V) { C1 = warp_sum(C1); C2 = warp_sum(C2); }
+    if (lane == 0) {
+        double2* out = reinterpret_cast<double2*>(a.partial + (size_t)t * 4);
+        out[0] = make_double2(A, B);
+        out[1] = make_double2(C1, C2);
+    }
+}
+
+// tiles -> column sums. heavy: one CTA per heavy column (list). all: one thread per column (light only) --
+// used when the column sums travel through an allreduce.
+__global__ void __launch_bounds__(128) k_combine_heavy(const uint32_t* __restrict__ heavy_cols, uint32_t h0, const uint32_t* __restrict__ col_tile0,
+                                                       const double* __restrict__ partial, double* __restrict__ colsum) {
+    __shared__ double sm[4 * 32];
+    uint32_t j = heavy_cols[h0 + blockIdx.x];
+    uint32_t t0 = col_tile0[j], t1 = col_tile0[j + 1];
+    double v[4] = {0, 0, 0, 0};
+    for (uint32_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        const double2* p = reinterpret_cast<const double2*>(partial + (size_t)t * 4);
+        double2 a = p[0], b = p[1];
+        v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
+    }
+    block_sum<4>(v, sm);
+    if (threadIdx.x == 0) {
+        double2* o = reinterpret_cast<double2*>(colsum + (size_t)j * 4);
+        o[0] = make_double2(v[0], v[1]);
+        o[1] = make_double2(v[2], v[3]);
+    }
+}
+
+__device__ __forceinline__ void load_colsum(uint32_t j, const uint32_t* __restrict__ col_tile0, const double* __restrict__ partial,
+                                            const double* __restrict__ colsum, bool from_colsum, double& A, double& B, double& C1, double& C2) {
+    uint32_t t0 = col_tile0[j], t1 = col_tile0[j + 1];
+    if (from_colsum || (t1 - t0) > 8) {
+        const double2* p = reinterpret_cast<const double2*>(colsum + (size_t)j * 4);
+        double2 a = p[0], b = p[1];
+        A = a.x; B = a.y; C1 = b.x; C2 = b.y;
+    } else {
+        A = B = C1 = C2 = 0.0;
+        for (uint32_t t = t0; t < t1; t++) {
+            const double2* p = reinterpret_cast<const double2*>(partial + (size_t)t * 4);
+            double2 a = p[0], b = p[1];
+            A += a.x; B += a.y; C1 += b.x; C2 += b.y;
+        }
+    }
+}
+
+__global__ void k_combine_light(uint32_t c0, uint32_t c1, const uint32_t* __restrict__ col_tile0, const double* __restrict__ partial,
+                                double* __restrict__ colsum) {
+    uint32_t j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c1) return;
+    if (col_tile0[j + 1] - col_tile0[j] > 8) return;   // heavy: written by k_combine_heavy
+    double A, B, C1, C2;
+    load_colsum(j, col_tile0, partial, colsum, false, A, B, C1, C2);
+    double2* o = reinterpret_cast<double2*>(colsum + (size_t)j * 4);
+    o[0] = make_double2(A, B);
+    o[1] = make_double2(C1, C2);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// counter-based RNG (Philox4x32-10, Salmon et al. 2011) -- replaces the reference's libc rand() stream
+// (src/util/random.h:150-176) for MCMC draws; matched in distribution, identical on every rank.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0; k.y += W1;
+    }
+    return c;
+}
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b) {   // (0,1), 53 bits
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    uint4 r = philox4x32_10(make_uint4(c0, c1, c2, c3), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    double u1 = u01(r.x, r.y), u2 = u01(r.z, r.w);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+struct FinalizeArgs {
+    uint32_t c0, c1;             // column range of the run
+    int f;                       // factor (or -1 for w)
+    int K;
+    const uint32_t* col_tile0;
+    const double* partial;
+    const double* colsum;
+    bool from_colsum;
+    double2* pf;                 // params to update ([D])
+    const uint32_t* group;
+    const double* hyper;         // vb: sigma_w[G] or sigma_v[G][K]; mcmc: lambda
+    const double* hyper_mu;      // mcmc: mu per group
+    Scalars* sc;
+    double* delta;               // [D]
+    double* dT;                  // [D]
+    uint64_t seed; int do_sample;
+    // vb_online
+    double2* nat;                // [D] natural params of this factor
+    uint32_t* t_cnt;             // [D] t_wj (w) or t_vj (v)
+    const double* col_count;     // [D]
+    const uint64_t* colptr;      // batch column sizes come from colsum C-slot instead (see engine)
+    int update_t;                // vb_online: 1 when this sweep advances t_cnt (w: always; v: f == 0)
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
+    static_assert(KIND <= KIND_MC_V, "vb_online uses k_finalize_vbo");
+    uint32_t j = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.c1) return;
+    double A, B, C1, C2;
+    load_colsum(j, a.col_tile0, a.partial, a.colsum, a.from_colsum, A, B, C1, C2);
+    uint32_t g = a.group[j];
+    double hy = (a.f < 0) ? a.hyper[g] : a.hyper[(size_t)g * a.K + a.f];
+    double alpha = a.sc->alpha;
+    double2 P = a.pf[j];
+    double mu_old = P.x, sg_old = P.y;
+    unsigned bad = 0;
+    if constexpr (KIND == KIND_VB_W || KIND == KIND_VB_V) {
+        double sg = 1.0 / (hy + alpha * B);                 // vb.h:540 / :597
+        double mu = sg * alpha * A;                          // vb.h:541 / :598
+        if (isnan(sg) || isinf(sg)) { sg = sg_old; bad++; }  // vb.h:545-549 / :600-604
+        bool skip = false;
+        if (isnan(mu) || isinf(mu)) { mu = mu_old; bad++; skip = true; }   // vb.h:552-565 / :606-619 (pass 2 skipped)
+        a.pf[j] = make_double2(mu, sg);
+        a.delta[j] = skip ? 0.0 : (mu_old - mu);
+        if (!skip) {
+            if constexpr (KIND == KIND_VB_W) a.dT[j] += B * (sg - sg_old);                                    // vb.h:572
+            else a.dT[j] += (C1 + C2) * (sg - sg_old) + C1 * (mu * mu - mu_old * mu_old);                        // vb.h:639-640
+        }
+    } else if constexpr (KIND == KIND_MC_W || KIND == KIND_MC_V) {
+        double v_old = mu_old;
+        double hm = (a.f < 0) ? a.hyper_mu[g] : a.hyper_mu[(size_t)g * a.K + a.f];
+        if constexpr (KIND == KIND_MC_V) A -= v_old * B;                      // mcmc.h:793
+        double s2 = 1.0 / (hy + alpha * B);                                  // mcmc.h:680 / :794
+        double mean = -s2 * (alpha * A - hm * hy);                           // mcmc.h:681 / :795
+        double v;
+        if (isnan(s2) || isinf(s2)) v = 0.0;                                 // mcmc.h:686-687 / :800-801
+        else if (a.do_sample) {
+            double sd = sqrt(s2);
+            if (sd == 0.0 || isnan(sd)) v = mean;                            // random.h:166-172
+            else v = mean + sd * philox_normal(a.seed, j, (uint32_t)(a.f + 1), a.sc->iter, 0x5eed0001u);
+        } else v = mean;
+        bool skip = false;
+        if (isnan(v) || isinf(v)) { v = v_old; bad++; skip = true; }         // mcmc.h:697-710 / :811-824
+        a.pf[j] = make_double2(v, 0.0);
+        a.delta[j] = skip ? 0.0 : (v - v_old);                               // e -= h (v_old - v)  (mcmc.h:716 / :833)
+    }
+    if (bad) atomicAdd(&a.sc->nan_inf, (unsigned long long)bad);
+}
+
+// vb_online finalize: natural-parameter step. `cnt` = number of batch entries of the column (exact in fp64).
+//   eta2 <- mean_n[(1-rho) eta2_old + rho (prior + alpha c_j B_n)] = (1-rho) eta2_old + rho (prior + alpha c_j B/cnt)
+//   eta1 <- (1-rho) eta1_old + rho c_j alpha A/cnt ;  mu = eta1/eta2 ; sigma = 1/eta2
+template <int KIND>
+__global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, const double* __restrict__ cnt_arr, double lamda, uint32_t t0) {
+    uint32_t j = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.c1) return;
+    double cnt = cnt_arr[j];
+    if (cnt == 0.0) { a.delta[j] = 0.0; return; }            // empty columns are skipped (vbo.h:367, 394)
+    double A, B, C1, C2;
+    load_colsum(j, a.col_tile0, a.partial, a.colsum, a.from_colsum, A, B, C1, C2);
+    uint32_t g = a.group[j];
+    double hy = (a.f < 0) ? a.hyper[g] : a.hyper[(size_t)g * a.K + a.f];
+    double alpha = a.sc->alpha;
+    double2 P = a.pf[j];
+    double mu_dash = P.x, sg_dash = P.y;
+    double2 N = a.nat[j];                                     // {eta1, eta2}
+    uint32_t tc = a.t_cnt[j];
+    double rho = pow((double)(t0 + tc), -lamda);              // vbo.h:521 / :406 (rate in force for this batch)
+    double cj = a.col_count[j];
+    double eta2 = (1.0 - rho) * N.y + rho * (hy + alpha * cj * (B / cnt));      // vbo.h:515 / :579
+    double eta1 = (1.0 - rho) * N.x + rho * cj * alpha * (A / cnt);             // vbo.h:516 / :580
+    a.nat[j] = make_double2(eta1, eta2);
+    if (a.update_t) a.t_cnt[j] = tc + (uint32_t)cnt;          // vbo.h:520 / :401
+    double mu = eta1 / eta2, sg = 1.0 / eta2;                 // vbo.h:524-525 / :586-587
+    unsigned bad = 0;
+    if (isnan(sg) || isinf(sg)) { sg = sg_dash; bad++; }
+    bool skip = false;
+    if (isnan(mu) || isinf(mu)) { mu = mu_dash; bad++; skip = true; }
+    a.pf[j] = make_double2(mu, sg);
+    a.delta[j] = skip ? 0.0 : (mu_dash - mu);
+    if (!skip) {
+        if constexpr (KIND == KIND_VBO_W) a.dT[j] += B * (sg - sg_dash);
+        else a.dT[j] += (C1 + C2) * (sg - sg_dash) + C1 * (mu * mu - mu_dash * mu_dash);
+    }
+    if (bad) atomicAdd(&a.sc->nan_inf, (unsigned long long)bad);
+}
+
+// pass 2: e_i += x * h * delta_j   (vb.h:571 / :638; mcmc.h:716 / :833)
+template <bool IS_V, int FT, bool ONES>
+__global__ void __launch_bounds__(256) k_sweep_apply(SweepArgs a) {
+    uint32_t w = (blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5);
+    if (w >= a.ntiles) return;
+    uint32_t t = a.tile0 + w, lane = threadIdx.x & 31;
+    uint32_t j = __ldg(&a.tile_col[t]);
+    double d = __ldg(&a.delta[j]);
+    if (d == 0.0) return;
+    uint64_t b = __ldg(&a.tile_begin[t]);
+    uint64_t cend = __ldg(&a.colptr[j + 1]);
+    uint64_t e_ = b + a.tile_entries < cend ? b + a.tile_entries : cend;
+    for (uint64_t p = b + lane; p < e_; p += 32) {
+        uint32_t i = __ldg(&a.crow[p]);
+        float xf = 1.0f;
+        if constexpr (!ONES) xf = __ldg(&a.cval[p]);
+        double hh = xf;
+        if constexpr (IS_V) {
+            double h, h1, h2;
+            others<FT, ONES, false>(a.rv, a.pf, i, j, h, h1, h2);
+            hh = xf * h;
+        }
+        a.e[i] += hh * d;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dense passes over the residuals
+#define SV_RGRID 1184   // 148 SMs x 8
+
+// partial[b*3 + {0,1,2}] = sum e, sum e^2, sum clamp(e)^2  (vb.h:513, :451, vbs.h:153-162)
+__global__ void __launch_bounds__(256) k_reduce_e(const double* __restrict__ e, uint32_t n, const Scalars* sc, double* __restrict__ partial) {
+    __shared__ double sm[3 * 32];
+    double lo = sc->min_target, hi = sc->max_target;
+    double v[3] = {0, 0, 0};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double x = e[i];
+        v[0] += x; v[1] += x * x;
+        double p = fmax(lo, fmin(hi, x));
+        v[2] += p * p;
+    }
+    block_sum<3>(v, sm);
+    if (threadIdx.x == 0) { partial[blockIdx.x * 3 + 0] = v[0]; partial[blockIdx.x * 3 + 1] = v[1]; partial[blockIdx.x * 3 + 2] = v[2]; }
+}
+
+// out[k] (+)= sum_b partial[b*nv + k]
+__global__ void __launch_bounds__(256) k_reduce_final(const double* __restrict__ partial, uint32_t nblocks, uint32_t nv, double* __restrict__ out, int accumulate) {
+    __shared__ double sm[32];
+    for (uint32_t k = 0; k < nv; k++) {
+        double v[1] = {0.0};
+        for (uint32_t b = threadIdx.x; b < nblocks; b += blockDim.x) v[0] += partial[(size_t)b * nv + k];
+        block_sum<1>(v, sm);
+        if (threadIdx.x == 0) out[k] = accumulate ? out[k] + v[0] : v[0];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_shift_e(double* __restrict__ e, uint32_t n, const Scalars* sc) {
+    double d = sc->w0_delta;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) e[i] += d;
+}
+
+// sum over columns of dT[j]; zeroes dT
+__global__ void __launch_bounds__(256) k_reduce_dT(double* __restrict__ dT, uint32_t n, double* __restrict__ partial) {
+    __shared__ double sm[32];
+    double v[1] = {0.0};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { v[0] += dT[i]; dT[i] = 0.0; }
+    block_sum<1>(v, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// case-wise prediction (replaces the 2K+1 CSC scatter passes of predict_data_and_write_to_eterms,
+// fm_learn_vb.h:70-203 / fm_learn_mcmc.h:117-348, and of predict_t_and_write_to_qterms, vb.h:207-312)
+enum { PRED_VB_TRAIN = 0, PRED_VB_TEST = 1, PRED_MC_TRAIN = 2, PRED_MC_TEST = 3 };
+
+struct PredictArgs {
+    RowView rv;
+    const float* y;
+    uint32_t n;
+    const double2* pw;
+    const double2* pv;
+    uint32_t D; int K, k0, k1;
+    const Scalars* sc;
+    double* e;            // train: residual out
+    double* pred;         // test: prediction out (vb: clamped)
+    double* pred_sum;     // mcmc test: running sum of clamped predictions
+    double* partial;      // [grid][4]
+    const uint8_t* in_batch;   // vb_online: restrict to the cases of the current batch
+};
+
+template <int MODE, int FT, bool ONES>
+__global__ void __launch_bounds__(256) k_predict(PredictArgs a) {
+    __shared__ double sm[4 * 32];
+    double acc[4] = {0, 0, 0, 0};
+    const double w0 = a.sc->w0_mean, w0v = a.sc->w0_var;
+    const double lo = a.sc->min_target, hi = a.sc->max_target;
+    const double inv_it = 1.0 / (double)(a.sc->iter + 1);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+        if (MODE == PRED_VB_TRAIN && a.in_batch && !a.in_batch[i]) continue;
+        uint64_t b, e_;
+        uint32_t c2[2] = {0, 0}; float x2[2] = {1.0f, 1.0f};
+        if constexpr (FT == 2) {
+            uint2 c = __ldg(reinterpret_cast<const uint2*>(a.rv.rcol) + i);
+            c2[0] = c.x; c2[1] = c.y;
+            if constexpr (!ONES) { float2 xv = __ldg(reinterpret_cast<const float2*>(a.rv.rval) + i); x2[0] = xv.x; x2[1] = xv.y; }
+            b = 0; e_ = 2;
+        } else if constexpr (FT == 1) { b = (uint64_t)i * a.rv.F; e_ = b + a.rv.F; }
+        else { b = __ldg(&a.rv.rowptr[i]); e_ = __ldg(&a.rv.rowptr[i + 1]); }
+        auto col = [&](uint64_t k) -> uint32_t { if constexpr (FT == 2) return c2[k]; else return __ldg(&a.rv.rcol[k]); };
+        auto val = [&](uint64_t k) -> float { if constexpr (ONES) return 1.0f; else if constexpr (FT == 2) return x2[k]; else return __ldg(&a.rv.rval[k]); };
+        double lin = 0.0, tw = 0.0;
+        for (uint64_t k = b; k < e_; k++) {
+            double2 P = __ldg(&a.pw[col(k)]);
+            float x = val(k);
+            lin += P.x * x;                                     // vb.h:184
+            if constexpr (MODE == PRED_VB_TRAIN) tw += P.y * x * x;   // vb.h:298
+        }
+        double pair = 0.0, sq = 0.0, tt = 0.0, tr = 0.0;
+        for (int f = 0; f < a.K; f++) {
+            const double2* pf = a.pv + (size_t)f * a.D;
+            double s = 0.0, Q = 0.0, Z = 0.0;
+            for (uint64_t k = b; k < e_; k++) {
+                double2 P = __ldg(&pf[col(k)]);
+                float x = val(k);
+                s += P.x * x;                                   // vb.h:115
+                sq += 0.5 * P.x * P.x * x * x;                  // vb.h:159
+                if constexpr (MODE == PRED_VB_TRAIN) {
+                    Q += P.x * x * P.x * x;                     // vb.h:241
+                    Z += P.y * x * x;                           // vb.h:242
+                    tr += (P.x * P.x * x * x * x * x * P.y + 0.5 * x * x * x * x * P.y * P.y);   // vb.h:277-278
+                }
+            }
+            pair += 0.5 * s * s;                                // vb.h:128
+            if constexpr (MODE == PRED_VB_TRAIN) tt += (0.5 * Z * Z + Z * Q);   // vb.h:250
+        }
+        double q_all = -sq;
+        if (a.k1) q_all += lin;
+        double yhat = pair + q_all;
+        if (a.k0) yhat += w0;                                   // vb.h:196-199
+        double y = (double)__ldg(&a.y[i]);
+        if constexpr (MODE == PRED_VB_TRAIN) {
+            double T = tt - tr;
+            if (a.k1) T += tw;
+            if (a.k0) T += w0v;                                 // vb.h:306-309
+            a.e[i] = y - yhat;                                  // vbs.h:43
+            acc[0] += T;
+        } else if constexpr (MODE == PRED_VB_TEST) {
+            double p = fmax(lo, fmin(hi, yhat));                // vbs.h:146-147
+            a.pred[i] = p;
+            double err = p - y;                                 // vbs.h:270-271
+            acc[0] += err * err;
+        } else if constexpr (MODE == PRED_MC_TRAIN) {
+            double p = fmax(lo, fmin(hi, yhat));                // mcmcs.h:167-171
+            double err = p - y;
+            acc[0] += err * err;
+            a.e[i] = yhat - y;                                  // mcmcs.h:172
+        } else {
+            a.pred[i] = yhat;                                   // mcmcs.h:156
+            double p = fmax(lo, fmin(hi, yhat));
+            double s = a.pred_sum[i] + p;                       // mcmcs.h:159
+            a.pred_sum[i] = s;
+            double e1 = p - y;                                  // rmse_this (mcmcs.h:240)
+            double pm = fmax(lo, fmin(hi, s * inv_it));         // mcmcs.h:241 with normalizer 1/(i+1)
+            double e2 = pm - y;
+            acc[0] += e1 * e1; acc[1] += e2 * e2;
+        }
+    }
+    block_sum<4>(acc, sm);
+    if (threadIdx.x == 0)
+        for (int k = 0; k < 4; k++) a.partial[blockIdx.x * 4 + k] = acc[k];
+}
+
+// mcmc without re-prediction: Train= from the cached residuals (yhat = e + y)
+__global__ void __launch_bounds__(256) k_train_sse_from_e(const double* __restrict__ e, const float* __restrict__ y, uint32_t n, const Scalars* sc,
+                                                          double* __restrict__ partial) {
+    __shared__ double sm[4 * 32];
+    double acc[4] = {0, 0, 0, 0};
+    double lo = sc->min_target, hi = sc->max_target;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double yy = (double)y[i];
+        double p = fmax(lo, fmin(hi, e[i] + yy));
+        acc[0] += (p - yy) * (p - yy);
+    }
+    block_sum<4>(acc, sm);
+    if (threadIdx.x == 0)
+        for (int k = 0; k < 4; k++) partial[blockIdx.x * 4 + k] = acc[k];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-group column sums for the hyper-parameter updates. row r of the grid's y dimension: r = 0 -> w, r = f+1 -> v_f
+//   vb  : S = sum (mu^2 + sigma), L = sum log(sigma)         (vb.h:477-498, 665-677)
+//   mcmc: S = sum v,              L = sum v^2                (mcmc.h:938-941, 979-982, 1020-1023, 1061-1064)
+#define SV_GGRID 64
+template <bool MCMC>
+__global__ void __launch_bounds__(256) k_group_sums(const double2* __restrict__ pw, const double2* __restrict__ pv, uint32_t D, uint32_t G,
+                                                    const uint32_t* __restrict__ group, double* __restrict__ partial /*[K+1][G][2][SV_GGRID]*/) {
+    __shared__ double sm[2 * 32];
+    uint32_t r = blockIdx.y;
+    const double2* p = (r == 0) ? pw : pv + (size_t)(r - 1) * D;
+    for (uint32_t g = 0; g < G; g++) {
+        double v[2] = {0.0, 0.0};
+        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < D; j += gridDim.x * blockDim.x) {
+            if (G > 1 && group[j] != g) continue;
+            double2 P = p[j];
+            if (MCMC) { v[0] += P.x; v[1] += P.x * P.x; }
+            else { v[0] += P.x * P.x + P.y; v[1] += log(P.y); }
+        }
+        block_sum<2>(v, sm);
+        if (threadIdx.x == 0) {
+            size_t base = (((size_t)r * G + g) * 2) * SV_GGRID;
+            partial[base + blockIdx.x] = v[0];
+            partial[base + SV_GGRID + blockIdx.x] = v[1];
+        }
+    }
+}
+__global__ void __launch_bounds__(64) k_group_sums_final(const double* __restrict__ partial, uint32_t nrows /*(K+1)*G*2*/, double* __restrict__ out) {
+    uint32_t r = blockIdx.x;
+    if (r >= nrows) return;
+    __shared__ double sm[32];
+    double v[1] = {0.0};
+    for (uint32_t b = threadIdx.x; b < SV_GGRID; b += blockDim.x) v[0] += partial[(size_t)r * SV_GGRID + b];
+    block_sum<1>(v, sm);
+    if (threadIdx.x == 0) out[r] = v[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// scalar (single-thread) kernels: the O(1) / O(G*K) parts of update_all / draw_all
+
+// update_w0 (vb.h:504-525). red[0] = global sum e
+__global__ void k_vb_w0(Scalars* sc) {
+    double N = sc->n_total;
+    double sigma_old = sc->w0_var, mu_old = sc->w0_mean;
+    sc->w0_var = 1.0 / (sc->sigma_0 + N * sc->alpha);
+    double w0_temp = sc->red[0] + N * mu_old;              // sum_i (e_i + mu_0')
+    sc->w0_mean = sc->w0_var * sc->alpha * w0_temp;
+    sc->w0_delta = mu_old - sc->w0_mean;                   // vb.h:518
+    sc->sum_t += N * (sc->w0_var - sigma_old);             // vb.h:519 summed over cases
+}
+
+// alpha, sigma_0, sigma_w, sigma_v, free energy (vb.h:446-500, 646-681). grp[(r*G+g)*2 + {0,1}] = S, L
+// red[1] = global sum e^2, red[2] = global sum clamp(e)^2
+__global__ void k_vb_hyper(Scalars* sc, const double* __restrict__ grp, const double* __restrict__ n_per_group, uint32_t G, int K,
+                           double* __restrict__ sigma_w, double* __restrict__ sigma_v, DevStats* st) {
+    double N = sc->n_total;
+    double temp = sc->red[1] + sc->sum_t;                  // sum_i (e_i^2 + T_i)
+    st->train_stat = sqrt(sc->red[2] / N);                 // vbs.h:162
+    double alpha_old = sc->alpha;
+    double alpha = N / temp;
+    if (isnan(alpha) || isinf(alpha)) {                    // vb.h:456-469: revert and RETURN (no sigma updates, no free energy)
+        sc->nan_inf += 1; sc->alpha = alpha_old; sc->alpha_ok = 0;
+        st->has_fe = 0.0; st->free_energy = 0.0; st->alpha = alpha_old;
+        return;
+    }
+    sc->alpha = alpha; sc->alpha_ok = 1;
+    sc->sigma_0 = 1.0 / (sc->w0_mean * sc->w0_mean + sc->w0_var);      // vb.h:473
+    double fe = -0.5 * alpha * temp - .5 * N * log(2 * 3.14 * (1.0 / alpha));          // vb.h:662-663 (3.14 is the reference's pi)
+    fe += -0.5 * sc->sigma_0 * (sc->w0_mean * sc->w0_mean + sc->w0_var) + 0.5 * log(sc->w0_var * sc->sigma_0) + .5;   // vb.h:664
+    for (uint32_t g = 0; g < G; g++) {
+        double S = grp[((size_t)0 * G + g) * 2 + 0], L = grp[((size_t)0 * G + g) * 2 + 1], ng = n_per_group[g];
+        double sw = ng / S;                                 // vb.h:482
+        sigma_w[g] = sw;
+        fe += -0.5 * sw * S + 0.5 * (L + ng * log(sw)) + .5 * ng;       // vb.h:665-669 summed over the group
+    }
+    for (int f = 0; f < K; f++)
+        for (uint32_t g = 0; g < G; g++) {
+            double S = grp[((size_t)(f + 1) * G + g) * 2 + 0], L = grp[((size_t)(f + 1) * G + g) * 2 + 1], ng = n_per_group[g];
+            double sv = ng / S;                             // vb.h:496
+            sigma_v[(size_t)g * K + f] = sv;
+            fe += -0.5 * sv * S + 0.5 * (L + ng * log(sv)) + .5 * ng;   // vb.h:670-677
+        }
+    st->free_energy = fe; st->has_fe = 1.0; st->alpha = alpha;
+}
+
+// scalar RNG stream for the hyper-prior draws
+struct ScalarRng {
+    uint64_t seed; uint32_t iter, n;
+    __device__ double uniform() { uint4 r = philox4x32_10(make_uint4(n++, 0xa11ce, iter, 0x5eed0002u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))); return u01(r.x, r.y); }
+    __device__ double normal() { return philox_normal(seed, n++, 0xb0b, iter, 0x5eed0003u); }
+    __device__ double gamma(double alpha) {                 // Marsaglia-Tsang, as random.h:118-144
+        if (alpha < 1.0) { double u = uniform(); return gamma(alpha + 1.0) * pow(u, 1.0 / alpha); }
+        double d = alpha - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d), x, v, u;
+        do {
+            do { x = normal(); v = 1.0 + c * x; } while (v <= 0.0);
+            v = v * v * v;
+            u = uniform();
+        } while ((u >= (1.0 - 0.0331 * (x * x) * (x * x))) && (log(u) >= (0.5 * x * x + d * (1.0 - v + log(v)))));
+        return d * v;
+    }
+    __device__ double gaussian(double mean, double sd) { if (sd == 0.0 || isnan(sd)) return mean; return mean + sd * normal(); }
+};
+
+// draw_alpha, draw_w0, draw_w_lambda, draw_w_mu, draw_v_lambda, draw_v_mu (mcmc.h:901-929, 628-668, 931-1089).
+// red[0] = sum e, red[1] = sum e^2 (global); grp[(r*G+g)*2 + {0,1}] = sum v, sum v^2.
+__global__ void k_mcmc_hyper(Scalars* sc, const double* __restrict__ grp, const double* __restrict__ n_per_group, uint32_t G, int K, int k0, int k1,
+                             double* __restrict__ w_lambda, double* __restrict__ w_mu, double* __restrict__ v_lambda, double* __restrict__ v_mu,
+                             uint64_t seed, int do_sample, int do_multilevel) {
+    const double alpha_0 = 1.0, gamma_0 = 1.0, beta_0 = 1.0, mu_0 = 0.0, w0_mean_0 = 0.0;   // mcmc.h:1100-1107
+    ScalarRng rng{seed, sc->iter, 0};
+    double N = sc->n_total;
+    unsigned bad = 0;
+    // alpha (mcmc.h:901-929)
+    if (!do_multilevel) sc->alpha = alpha_0;
+    else {
+        double a_old = sc->alpha;
+        double a = rng.gamma((alpha_0 + N) / 2.0) / ((gamma_0 + sc->red[1]) / 2.0);
+        if (isnan(a) || isinf(a)) { a = a_old; bad++; }
+        sc->alpha = a;
+    }
+    // w0 (mcmc.h:628-668)
+    sc->w0_delta = 0.0;
+    if (k0) {
+        double reg0 = sc->sigma_0, w0 = sc->w0_mean;
+        double w0_mean = sc->red[0] - N * w0;               // sum_i (e_i - w0)
+        double s2 = 1.0 / (reg0 + sc->alpha * N);
+        w0_mean = -s2 * (sc->alpha * w0_mean - w0_mean_0 * reg0);
+        double w0n = do_sample ? rng.gaussian(w0_mean, sqrt(s2)) : w0_mean;
+        if (isnan(w0n) || isinf(w0n)) { bad++; }
+        else { sc->w0_mean = w0n; sc->w0_delta = w0n - w0; }   // e -= (w0_old - w0)
+    }
+    if (k1) {
+        if (do_multilevel) {                                // draw_w_lambda (mcmc.h:970-1007)
+            for (uint32_t g = 0; g < G; g++) {
+                double S1 = grp[((size_t)0 * G + g) * 2 + 0], S2 = grp[((size_t)0 * G + g) * 2 + 1], ng = n_per_group[g], m = w_mu[g];
+                double gam = beta_0 * (m - mu_0) * (m - mu_0) + gamma_0 + (S2 - 2.0 * m * S1 + ng * m * m);
+                double a = alpha_0 + ng + 1, old = w_lambda[g];
+                double l = do_sample ? rng.gamma(a / 2.0) / (gam / 2.0) : a / gam;
+                if (isnan(l) || isinf(l)) { l = old; bad++; w_lambda[g] = l; break; }
+                w_lambda[g] = l;
+            }
+            for (uint32_t g = 0; g < G; g++) {              // draw_w_mu (mcmc.h:931-968)
+                double S1 = grp[((size_t)0 * G + g) * 2 + 0], ng = n_per_group[g];
+                double mean = (S1 + beta_0 * mu_0) / (ng + beta_0);
+                double s2 = 1.0 / ((ng + beta_0) * w_lambda[g]), old = w_mu[g];
+                double m = do_sample ? rng.gaussian(mean, sqrt(s2)) : mean;
+                if (isnan(m) || isinf(m)) { w_mu[g] = old; bad++; break; }
+                w_mu[g] = m;
+            }
+        } else for (uint32_t g = 0; g < G; g++) w_mu[g] = mu_0;
+    }
+    if (K > 0) {
+        if (do_multilevel) {
+            bool stop = false;
+            for (int f = 0; f < K && !stop; f++)            // draw_v_lambda (mcmc.h:1051-1089)
+                for (uint32_t g = 0; g < G; g++) {
+                    double S1 = grp[((size_t)(f + 1) * G + g) * 2 + 0], S2 = grp[((size_t)(f + 1) * G + g) * 2 + 1], ng = n_per_group[g];
+                    double m = v_mu[(size_t)g * K + f];
+                    double gam = beta_0 * (m - mu_0) * (m - mu_0) + gamma_0 + (S2 - 2.0 * m * S1 + ng * m * m);
+                    double a = alpha_0 + ng + 1, old = v_lambda[(size_t)g * K + f];
+                    double l = do_sample ? rng.gamma(a / 2.0) / (gam / 2.0) : a / gam;
+                    if (isnan(l) || isinf(l)) { v_lambda[(size_t)g * K + f] = old; bad++; stop = true; break; }
+                    v_lambda[(size_t)g * K + f] = l;
+                }
+            stop = false;
+            for (int f = 0; f < K && !stop; f++)            // draw_v_mu (mcmc.h:1011-1049)
+                for (uint32_t g = 0; g < G; g++) {
+                    double S1 = grp[((size_t)(f + 1) * G + g) * 2 + 0], ng = n_per_group[g];
+                    double mean = (S1 + beta_0 * mu_0) / (ng + beta_0);
+                    double s2 = 1.0 / ((ng + beta_0) * v_lambda[(size_t)g * K + f]), old = v_mu[(size_t)g * K + f];
+                    double m = do_sample ? rng.gaussian(mean, sqrt(s2)) : mean;
+                    if (isnan(m) || isinf(m)) { v_mu[(size_t)g * K + f] = old; bad++; stop = true; break; }
+                    v_mu[(size_t)g * K + f] = m;
+                }
+        } else for (size_t i = 0; i < (size_t)G * K; i++) v_mu[i] = mu_0;
+    }
+    sc->nan_inf += bad;
+}
+
+// end of an iteration: evaluation numbers -> stats slot. red[3] = test sse (this), red[4] = test sse (running mean),
+// red[5] = train sse (mcmc)
+__global__ void k_finish_iter(Scalars* sc, DevStats* st, int method) {
+    double nt = sc->nt_total, N = sc->n_total;
+    if (method == SVBFM_MCMC) {
+        st->rmse_this = sqrt(sc->red[3] / nt);
+        st->test_rmse = sqrt(sc->red[4] / nt);
+        st->train_stat = sqrt(sc->red[5] / N);
+        st->alpha = sc->alpha; st->has_fe = 0.0; st->free_energy = 0.0;
+    } else {
+        st->test_rmse = sqrt(sc->red[3] / nt);
+        st->rmse_this = st->test_rmse;
+    }
+    st->nan_inf = (double)sc->nan_inf;
+    sc->nan_inf = 0;
+    sc->iter += 1;
+}
+
+// state pack/unpack
+__global__ void k_pack(const double* __restrict__ mean, const double* __restrict__ var, size_t n, double2* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2(mean[i], var ? var[i] : 0.0);
+}
+__global__ void k_unpack(const double2* __restrict__ in, size_t n, double* __restrict__ mean, double* __restrict__ var) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { double2 p = in[i]; if (mean) mean[i] = p.x; if (var) var[i] = p.y; }
+}
+__global__ void k_fill_f64(double* a, size_t n, double v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+__global__ void k_unpermute(const double* __restrict__ src, const uint32_t* __restrict__ perm, uint32_t n, double* __restrict__ dst) {
+    uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n) dst[perm ? perm[d] : d] = src[d];
+}
+
+}  // namespace svb

@@ -1,0 +1,109 @@
+"""-m gpu: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances: VB is floating point with a different (field-parallel, tree-reduced) summation order than the
+reference's sequential loops: north_star allows 1e-4 relative on test RMSE and free energy per iteration;
+these tests hold it to 1e-7 on small inputs. MCMC uses a different RNG stream, so it is matched in
+distribution (0.5 % on >= 1M rows; a looser bound on the small cases here) and exactly with sampling off."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import svbfm_b200 as sv
+from helpers import make_learner, ragged, rel, to_csc, two_field
+
+pytestmark = pytest.mark.gpu
+
+VB_TOL = 1e-7
+
+
+def run_vb(tr, te, K, iters, **kw):
+    orc = ob.Oracle("vb", tr, te, K=K, seed=42, k0=kw.get("k0", 1), k1=kw.get("k1", 1), groups=kw.get("groups"))
+    L = make_learner("vb", tr, te, K, num_iter=iters, **kw)
+    hist = L.learn(to_csc(tr), to_csc(te))
+    for it, s in enumerate(hist):
+        o = orc.iterate()
+        assert rel(s.test_rmse, o.test_rmse) < VB_TOL, (it, s.test_rmse, o.test_rmse)
+        assert rel(s.train_stat, o.train_stat) < VB_TOL, (it, s.train_stat, o.train_stat)
+        assert s.has_free_energy == o.has_free_energy
+        assert rel(s.free_energy, o.free_energy) < VB_TOL, (it, s.free_energy, o.free_energy)
+        assert rel(s.alpha, o.alpha) < VB_TOL
+    return L, orc
+
+
+def test_vb_two_field_onehot(built):
+    tr, te = two_field(20000, 2000, 300, 200)
+    L, orc = run_vb(tr, te, K=4, iters=8)
+    info = L.engine.info()
+    assert info["num_runs"] == 2 and info["all_ones"] == 1 and info["uniform_row_nnz"] == 2 and info["rows_reordered"] == 1
+    # state and residuals agree with the oracle's caches (caller case order)
+    e_o, t_o = orc.get_train_cache()
+    e = L.engine.get_residuals()
+    assert np.max(np.abs(e - e_o)) < 1e-9
+    assert rel(L.engine.get_sum_t(), t_o.sum()) < 1e-10
+    so, sg = orc.get_state(), L.engine.get_state()
+    for k in ("w_mean", "w_var", "v_mean", "v_var"):
+        assert np.max(np.abs(so[k] - sg[k])) < 1e-9, k
+    ho, hg = orc.get_hyper(), L.engine.get_hyper()
+    assert np.allclose(ho["sigma_v"], hg["sigma_v"], rtol=1e-9) and np.allclose(ho["sigma_w"], hg["sigma_w"], rtol=1e-9)
+    assert np.max(np.abs(L.engine.predict() - orc.get_test_pred())) < 1e-9
+
+
+def test_vb_values_no_reorder(built):
+    tr, te = two_field(5000, 500, 100, 80, seed=5, values=True)
+    L, _ = run_vb(tr, te, K=3, iters=5, flags=sv.FLAG_NO_ROW_REORDER)
+    assert L.engine.info()["all_ones"] == 0
+
+
+def test_vb_ragged_multihot(built):
+    tr, te = ragged(3000, 400, 60)
+    L, _ = run_vb(tr, te, K=3, iters=4)
+    assert L.engine.info()["uniform_row_nnz"] == 0 and L.engine.info()["num_runs"] > 2
+
+
+def test_vb_groups_and_small_tiles(built):
+    tr, te = two_field(8000, 800, 150, 120, seed=9)
+    D = max(tr.n_feat, te.n_feat) + 1
+    groups = np.zeros(D, dtype=np.uint32)
+    groups[150:] = 1
+    L, _ = run_vb(tr, te, K=2, iters=4, groups=groups, tile_entries=32)   # tile_entries=32 forces heavy columns
+    assert L.engine.info()["num_tiles"] > 270
+
+
+@pytest.mark.parametrize("k0,k1", [(0, 1), (1, 0), (0, 0)])
+def test_vb_k0_k1_switches(built, k0, k1):
+    tr, te = two_field(4000, 400, 80, 60, seed=11)
+    run_vb(tr, te, K=2, iters=3, k0=k0, k1=k1)
+
+
+def test_vb_k_zero_and_empty_test_columns(built):
+    tr, te = two_field(3000, 300, 50, 40, seed=13)
+    run_vb(tr, te, K=0, iters=3)
+
+
+def test_mcmc_als_exact(built):
+    """do_sample=0 (-method als): no random numbers, so the sweep must match the oracle to rounding."""
+    tr, te = two_field(20000, 2000, 300, 200, seed=21)
+    orc = ob.Oracle("mcmc", tr, te, K=4, seed=42, do_sample=False, do_multilevel=False)
+    L = make_learner("mcmc", tr, te, 4, num_iter=6, do_sample=False, do_multilevel=False)
+    L.fm.reg0, L.fm.regw, L.fm.regv = 0.0, 0.0, 0.0
+    hist = L.learn(to_csc(tr), to_csc(te))
+    for it, s in enumerate(hist):
+        o = orc.iterate()
+        assert rel(s.test_rmse, o.test_rmse) < 1e-7, (it, s.test_rmse, o.test_rmse)
+        assert rel(s.train_stat, o.train_stat) < 1e-7, (it, s.train_stat, o.train_stat)
+        assert rel(s.rmse_this, o.rmse_this) < 1e-7
+
+
+def test_mcmc_sampling_distribution(built):
+    tr, te = two_field(200000, 20000, 1000, 800, seed=23)
+    orc_vals = []
+    for seed in (42, 43, 44):
+        orc = ob.Oracle("mcmc", tr, te, K=4, seed=seed)
+        for _ in range(15):
+            o = orc.iterate()
+        orc_vals.append(o.test_rmse)
+    L = make_learner("mcmc", tr, te, 4, num_iter=15)
+    hist = L.learn(to_csc(tr), to_csc(te))
+    ref = float(np.mean(orc_vals))
+    assert rel(hist[-1].test_rmse, ref) < 0.005 + 2 * (max(orc_vals) - min(orc_vals)) / ref, (hist[-1].test_rmse, orc_vals)
+    assert np.isfinite(hist[-1].train_stat) and hist[-1].nan_inf_count == 0
