@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- VB sweep throughput (ratings x k / s) of the B200 engine on synthetic MovieLens-shaped ratings.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference --steps K --warmup W    (the reference's own CPU libFM, oracle/_ref)
+
+A step is one full VB iteration (update_all equivalent + test prediction/evaluation) over the workload.
+`value` is measured with the data resident in HBM (CUDA events on the engine's stream, max over ranks);
+`e2e` is the same metric through the learner interface with HOST buffers: every step uploads the CSC
+design matrix, targets and initial state from pinned host memory, ingests them on the device, runs one
+iteration and reads the iteration's statistics back.
+
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_RATING_K = 216.0     # cached-state algorithm, two one-hot fields, fp64 state
+OWN_BYTES_PER_RATING_K = 2 * (4 + 8 + 8) + 2 * (4 + 8 + 8 + 8)   # this engine: see DESIGN.md "Kernels"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="kdd200m", choices=["ml1m", "ml10m", "netflix", "kdd200m"])
+    ap.add_argument("--rows", type=int, default=0, help="override the number of train ratings (debug)")
+    ap.add_argument("--k", type=int, default=0, help="override the number of factors (debug)")
+    ap.add_argument("--method", default="vb", choices=["vb", "mcmc"])
+    ap.add_argument("--cpu-rows", type=int, default=400_000, help="ratings in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def run_reference_cpu(shape, K, n_rows, n_test, iters, method="vb"):
+    """Times the reference's own CPU implementation on a bounded sample of the workload.
+    oracle/_ref/libFM (the unmodified reference, `-rlog` time_learn per iteration) when present, else the C port."""
+    import numpy as np
+    import svbfm_b200 as sv
+    synth = sv.submodule("synth")
+    U, I = shape[0], shape[1]
+    model = synth.planted_model(U, I, 20261017)
+    u, i, y = synth.ratings(n_rows, U, I, model, 20261018)
+    ut, it, yt = synth.ratings(n_test, U, I, model, 20261019)
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "libFM")
+    sample = f"first {n_rows} train / {n_test} test ratings of the same synthetic workload (U={U}, I={I}), K={K}, {iters} iterations"
+    if os.path.exists(ref_bin):
+        with tempfile.TemporaryDirectory() as td:
+            synth.write_libfm_text(os.path.join(td, "tr"), u, i, y, U)
+            synth.write_libfm_text(os.path.join(td, "te"), ut, it, yt, U)
+            env = dict(os.environ, FAKE_TIME="42", LD_PRELOAD=os.path.join(ROOT, "oracle", "_ref", "fixtime.so"))
+            t0 = time.time()
+            subprocess.run([ref_bin, "-task", "r", "-train", "tr", "-test", "te", "-dim", f"1,1,{K}", "-method", method, "-iter", str(iters),
+                            "-rlog", "log.tsv"], cwd=td, env=env, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            wall = time.time() - t0
+            rows = [l.rstrip("\n").split("\t") for l in open(os.path.join(td, "log.tsv"))]
+            col = rows[0].index("time_learn")
+            times = [float(r[col]) for r in rows[1:] if len(r) > col and r[col] not in ("", "nan")]
+        return dict(kind="reference", times=times, wall=wall, sample=sample, cores=1)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_binding as ob   # CPU baseline leg: the one place bench.py may execute oracle/
+    tr = ob.Csr(*synth.to_csr(u, i, y, U))
+    te = ob.Csr(*synth.to_csr(ut, it, yt, U))
+    orc = ob.Oracle(method, tr, te, K=K, seed=42)
+    orc.begin()
+    times = []
+    for _ in range(iters):
+        t0 = time.time()
+        orc.iterate()
+        times.append(time.time() - t0)
+    return dict(kind="port", times=times, wall=sum(times), sample=sample, cores=1)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for l in self.proc.stdout:
+            self.lines.append(l.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    a = parse_args()
+    import numpy as np
+    import svbfm_b200 as sv
+    synth = sv.submodule("synth")
+    U, I, N, Nt, K = synth.SHAPES[a.workload]
+    if a.rows:
+        Nt = max(1000, int(Nt * a.rows / N)); N = a.rows
+    if a.k:
+        K = a.k
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"{a.workload}: {N} ratings, {U} users x {I} items (two one-hot fields, Zipf(1) popularity), {Nt} test ratings, {a.method} K={K}"
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        iters = a.warmup + a.steps
+        n_rows = min(N, a.cpu_rows)
+        r = run_reference_cpu((U, I), K, n_rows, max(1000, n_rows // 10), iters, a.method)
+        t = r["times"][a.warmup:] if len(r["times"]) > a.warmup else r["times"]
+        per = sum(t) / max(len(t), 1)
+        v = n_rows * K / per
+        cb = dict(value=v, unit="ratings*k/s", cores=r["cores"], kind=r["kind"], sample=r["sample"])
+        print(json.dumps({"impl": "reference", "metric": "vb_sweep_ratings_x_k_per_sec", "value": v, "unit": "ratings*k/s", "n_gpus": a.gpus,
+                          "steps": a.steps, "warmup": a.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload, "cpu_sample_rows": n_rows},
+                          "cpu_baseline": cb, "e2e": {"value": v, "unit": "ratings*k/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic data on the device (same stream of random numbers on every rank), this rank's contiguous case shard
+    u, it, y = synth.ratings_torch(N, U, I, 20261018, dev)
+    ut, itt, yt = synth.ratings_torch(Nt, U, I, 20261019, dev)
+    D = U + I + 1                                         # libfm.cpp:215: max(train, test num_feature) + 1
+
+    def shard(n):
+        return (n * rank) // world, (n * (rank + 1)) // world
+
+    def host_csc(uu, ii, yy, lo, hi):
+        colptr, case_id = synth.csc_two_field_torch(uu[lo:hi], ii[lo:hi], U, I)
+        n = hi - lo
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+        cp, ci, ty = pin(colptr), pin(case_id), pin(yy[lo:hi].contiguous())
+        x = torch.ones(2 * n, dtype=torch.float32).pin_memory()
+        d = sv.CscData.__new__(sv.CscData)
+        d.colptr, d.case_id, d.x, d.target = cp.numpy().view(np.uint64), ci.numpy().view(np.uint32), x.numpy(), ty.numpy()
+        d.num_cases, d.num_feature = n, U + I
+        d._keep = (cp, ci, x, ty)
+        return d
+
+    lo, hi = shard(N)
+    tlo, thi = shard(Nt)
+    train = host_csc(u, it, y, lo, hi)
+    test = host_csc(ut, itt, yt, tlo, thi)
+    ymin, ymax = float(y.min()), float(y.max())
+    del u, it, y, ut, itt, yt
+    torch.cuda.empty_cache()
+    g = torch.Generator(device=dev); g.manual_seed(42)
+    state = dict(w0_mean=0.0, w0_var=0.02 if a.method == "vb" else 0.0,
+                 w_mean=(0.1 * torch.randn(D, generator=g, device=dev, dtype=torch.float64)).cpu().pin_memory().numpy(),
+                 w_var=np.full(D, 0.02), v_mean=(0.1 * torch.randn(K, D, generator=g, device=dev, dtype=torch.float64)).cpu().pin_memory().numpy(),
+                 v_var=np.full((K, D), 0.02))
+    torch.cuda.empty_cache()
+
+    uid = None
+    if world > 1:
+        idt = torch.zeros(sv.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf = (sv.C.c_uint8 * sv.COMM_ID_BYTES)()
+            assert sv.lib().svbfm_comm_get_unique_id(buf) == 0
+            idt.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        uid = bytes(idt.cpu().tolist())
+
+    def make_engine():
+        E = sv.Engine(a.method, D, K, 1, 1, ymin, ymax, device=local, seed=42)
+        if world > 1:
+            E.comm_init(uid, rank, world)
+        E.set_csc(sv.TRAIN, train)
+        E.set_csc(sv.TEST, test)
+        E.set_state(state)
+        E.begin()
+        return E
+
+    # ---- device-resident throughput
+    E = make_engine()
+    info0 = E.info()
+    E.run(a.warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    E.set_profile(True)
+    l0 = E.info()["kernel_launches"]
+    barrier()
+    w0 = time.perf_counter()
+    hist = E.run(a.steps)
+    barrier()
+    wall = time.perf_counter() - w0
+    launches = E.info()["kernel_launches"] - l0
+    prof = E.get_profile()
+    E.set_profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(s.sweep_ms + s.predict_ms for s in hist)
+    sweep_ms = sum(s.sweep_ms for s in hist)
+    tt = torch.tensor([dev_ms, sweep_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, sweep_ms, wall_ms = [float(x) for x in tt.cpu()]
+    ms_per_step = dev_ms / a.steps
+    value = N * K / (ms_per_step * 1e-3)
+    last = hist[-1]
+    E.close()
+    del E
+
+    # ---- end to end through the learner interface with host buffers
+    e2e = None
+    if not a.no_e2e:
+        h2d = sum(x.nbytes for x in (train.colptr, train.case_id, train.x, train.target, test.colptr, test.case_id, test.x, test.target))
+        h2d += state["w_mean"].nbytes + state["w_var"].nbytes + state["v_mean"].nbytes + state["v_var"].nbytes
+        ts = []
+        for s in range(max(1, min(a.steps, 3)) + 1):
+            barrier()
+            t0 = time.perf_counter()
+            E2 = make_engine()
+            st = E2.run(1)[0]
+            _ = st.test_rmse                       # statistics are read back inside run()
+            barrier()
+            ts.append(time.perf_counter() - t0)
+            E2.close()
+        t_e2e = sum(ts[1:]) / len(ts[1:])          # first pass warms allocator / module load
+        tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.cpu()[0])
+        e2e = {"value": N * K / t_e2e, "unit": "ratings*k/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 64,
+               "ms_per_step": t_e2e * 1e3, "step": "create + set_csc(train,test) from pinned host + set_state + begin + 1 iteration + stats readback"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    sweep_per_step = sweep_ms / a.steps
+    achieved = (N / world) * K * ALGO_BYTES_PER_RATING_K / (sweep_per_step * 1e-3) / 1e9     # per GPU
+    rv = prof["reduce_v"]
+    n_local = hi - lo
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src,
+                "definition": "N*K*216 B (SURVEY 8d algorithmic bytes of the cached-state algorithm) / sweep time, per GPU; "
+                              "may exceed what the engine really moves because it re-derives q,S2,S3 instead of caching them",
+                "own_bytes_per_rating_k": OWN_BYTES_PER_RATING_K,
+                "own_achieved": (N / world) * K * OWN_BYTES_PER_RATING_K / (sweep_per_step * 1e-3) / 1e9,
+                "dominant_kernel": {"name": "k_sweep_reduce<VB_V>", "launches": rv["launches"],
+                                    "avg_ms": rv["ms"] / max(rv["launches"], 1),
+                                    "share_of_sweep": rv["ms"] / max(sweep_ms, 1e-9),
+                                    "algorithmic_bytes_per_launch": n_local * 48.0,
+                                    "achieved_GBps": n_local * 48.0 / (rv["ms"] / max(rv["launches"], 1) * 1e-3) / 1e9 if rv["launches"] else None},
+                "kernel_classes_ms": {k: v["ms"] for k, v in prof.items()}}
+    cpu_baseline = None
+    if world == 1 and not a.no_cpu_baseline:
+        n_rows = min(N, a.cpu_rows)
+        r = run_reference_cpu((U, I), K, n_rows, max(1000, n_rows // 10), 3, a.method)
+        t = r["times"][1:] if len(r["times"]) > 1 else r["times"]
+        cpu_baseline = dict(value=n_rows * K / (sum(t) / len(t)), unit="ratings*k/s", cores=r["cores"], kind=r["kind"], sample=r["sample"],
+                            host_cores_available=os.cpu_count())
+    out = {"metric": "vb_sweep_ratings_x_k_per_sec", "value": value, "unit": "ratings*k/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload, "sharding": f"{world} contiguous case shards, NCCL allreduce of column sums per field run" if world > 1 else "single GPU",
+                      "l2": "inputs (residuals + design matrix) are far larger than the 126 MB L2; no flush needed",
+                      "field_runs": info0["num_runs"], "tiles": info0["num_tiles"], "rows_reordered": info0["rows_reordered"]},
+           "sweep_only_ms_per_step": sweep_per_step, "wall_ms_per_step": wall_ms / a.steps,
+           "test_rmse_last": last.test_rmse, "free_energy_last": last.free_energy,
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -58,7 +58,7 @@ ABI_SYMBOLS = [
     "svbfm_comm_init", "svbfm_set_groups", "svbfm_set_csc", "svbfm_set_state", "svbfm_get_state",
     "svbfm_get_hyper", "svbfm_set_hyper", "svbfm_begin", "svbfm_vb_sweep", "svbfm_mcmc_sweep",
     "svbfm_vb_online_epoch", "svbfm_run", "svbfm_predict", "svbfm_get_residuals", "svbfm_get_sum_t",
-    "svbfm_get_info", "svbfm_set_stream", "svbfm_host_init_state", "svbfm_host_random_shuffle",
+    "svbfm_get_info", "svbfm_set_stream", "svbfm_set_profile", "svbfm_get_profile", "svbfm_host_init_state", "svbfm_host_random_shuffle",
 ]
 
 _lib = None
@@ -95,6 +95,8 @@ def lib():
         L.svbfm_get_sum_t.argtypes = [vp, C.POINTER(C.c_double)]
         L.svbfm_get_info.argtypes = [vp, C.POINTER(Info)]
         L.svbfm_set_stream.argtypes = [vp, vp]
+        L.svbfm_set_profile.argtypes = [vp, C.c_int32]
+        L.svbfm_get_profile.argtypes = [vp, vp, vp]
         L.svbfm_host_init_state.argtypes = [C.c_long, C.c_uint32, C.c_int32, C.c_double, C.c_int32,
                                             C.POINTER(C.c_double), C.POINTER(C.c_double), vp, vp, vp, vp]
         L.svbfm_host_random_shuffle.argtypes = [vp, C.c_uint32]
@@ -239,6 +241,16 @@ class Engine:
         v = C.c_double()
         self._ck(lib().svbfm_get_sum_t(self.h, C.byref(v)), "svbfm_get_sum_t")
         return v.value
+
+    def set_profile(self, on):
+        self._ck(lib().svbfm_set_profile(self.h, int(on)), "svbfm_set_profile")
+
+    def get_profile(self):
+        ms = np.zeros(6)
+        cnt = np.zeros(6, dtype=np.uint64)
+        self._ck(lib().svbfm_get_profile(self.h, _p(ms), _p(cnt)), "svbfm_get_profile")
+        names = ["reduce_v", "finalize_v", "apply_v", "reduce_w", "finalize_w", "apply_w"]
+        return {n: dict(ms=float(m), launches=int(c)) for n, m, c in zip(names, ms, cnt)}
 
     def info(self):
         i = Info()

@@ -87,6 +87,17 @@ static int check_launch(Engine* E, const char* what) {
     return 0;
 }
 
+// profiling spans: events on the launching stream around one kernel class
+struct ProfScope {
+    Engine* E; int cls; cudaEvent_t a = nullptr;
+    ProfScope(Engine* E_, int cls_) : E(E_), cls(cls_) {
+        if (E->profile) { cudaEventCreate(&a); cudaEventRecord(a, E->stream); }
+    }
+    ~ProfScope() {
+        if (a) { cudaEvent_t b; cudaEventCreate(&b); cudaEventRecord(b, E->stream); E->prof_spans.push_back({cls, a, b}); }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------- one run sweep
 template <int KIND>
 static int sweep_run(Engine* E, const Run& r, int f) {
@@ -99,7 +110,9 @@ static int sweep_run(Engine* E, const Run& r, int f) {
     a.tile_col = E->d_tile_col; a.tile_begin = E->d_tile_begin; a.colptr = S.colptr; a.crow = S.crow; a.cval = S.cval;
     a.rv = row_view(S); a.e = E->d_e; a.pf = pf; a.partial = E->d_partial; a.delta = E->d_delta;
     a.tile0 = r.tile_begin; a.ntiles = ntiles; a.tile_entries = E->tile_entries; a.in_batch = nullptr;
+    const int pc = IS_V ? 0 : 3;
     if (ntiles) {
+        ProfScope ps(E, pc + 0);
         unsigned grid = (ntiles + 7) / 8;
         if constexpr (IS_V) {
 #define CALL_R(FT, ONES) k_sweep_reduce<KIND, FT, ONES><<<grid, 256, 0, st>>>(a)
@@ -112,6 +125,8 @@ static int sweep_run(Engine* E, const Run& r, int f) {
         LAUNCHED(E);
     }
     uint32_t nheavy = r.heavy_end - r.heavy_begin;
+    {
+    ProfScope ps(E, pc + 1);
     if (nheavy) { k_combine_heavy<<<nheavy, 128, 0, st>>>(E->d_heavy_cols, r.heavy_begin, E->d_col_tile0, E->d_partial, E->d_colsum); LAUNCHED(E); }
     uint32_t ncols = r.col_end - r.col_begin;
     bool from_colsum = false;
@@ -127,7 +142,9 @@ static int sweep_run(Engine* E, const Run& r, int f) {
     fa.hyper_mu = IS_V ? E->d_mu_v : E->d_mu_w; fa.sc = E->d_sc; fa.delta = E->d_delta; fa.dT = E->d_dT;
     fa.seed = E->cfg.seed; fa.do_sample = E->cfg.do_sample;
     k_finalize<KIND><<<nblk(ncols), 256, 0, st>>>(fa); LAUNCHED(E);
+    }
     if (ntiles) {
+        ProfScope ps(E, pc + 2);
         unsigned grid = (ntiles + 7) / 8;
         if constexpr (IS_V) {
 #define CALL_A(FT, ONES) k_sweep_apply<true, FT, ONES><<<grid, 256, 0, st>>>(a)
@@ -649,6 +666,29 @@ int svbfm_get_sum_t(svbfm_t* h, double* sum_t) {
     SV_CUDA(E, cudaSetDevice(E->dev));
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
     SV_CUDA(E, copy_sync(E, sum_t, &E->d_sc->sum_t, 8, cudaMemcpyDeviceToHost));
+    return SVBFM_OK;
+}
+
+int svbfm_set_profile(svbfm_t* h, int32_t enabled) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E) return SVBFM_ERR_ARG;
+    E->profile = enabled != 0;
+    return SVBFM_OK;
+}
+
+int svbfm_get_profile(svbfm_t* h, double ms[SVBFM_PROFILE_CLASSES], uint64_t launches[SVBFM_PROFILE_CLASSES]) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E || !ms || !launches) return SVBFM_ERR_ARG;
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    SV_CUDA(E, cudaStreamSynchronize(E->stream));
+    for (int c = 0; c < SVBFM_PROFILE_CLASSES; c++) { ms[c] = 0.0; launches[c] = 0; }
+    for (auto& sp : E->prof_spans) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, sp.a, sp.b);
+        ms[sp.cls] += t; launches[sp.cls] += 1;
+        cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+    }
+    E->prof_spans.clear();
     return SVBFM_OK;
 }
 

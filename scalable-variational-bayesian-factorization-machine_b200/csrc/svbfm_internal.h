@@ -128,6 +128,10 @@ struct Engine {
     uint32_t stats_cap = 0;
     uint64_t launches = 0;
     uint64_t dev_bytes = 0;
+    // profiling (svbfm_set_profile): events around each kernel class of the sweeps
+    bool profile = false;
+    struct ProfSpan { int cls; cudaEvent_t a, b; };
+    std::vector<ProfSpan> prof_spans;
     // multi-GPU
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;

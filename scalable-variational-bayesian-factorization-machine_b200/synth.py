@@ -60,3 +60,52 @@ def csc_two_field(u, i, y, U, I, num_cols=None):
     np.cumsum(cnt, out=colptr[1:])
     case_id = np.concatenate([ou, oi]).astype(np.uint32)
     return colptr, case_id, np.ones(2 * n, dtype=np.float32)
+
+
+# ---- torch generator for the large configs (runs on the GPU; same distributions as above) -----------------
+def ratings_torch(n, U, I, seed, device, chunk=25_000_000, model_seed=20261017):
+    """Returns (user int32[n], item int32[n], y float32[n]) on `device`; deterministic for a given seed."""
+    import torch
+    gm = torch.Generator(device=device)
+    gm.manual_seed(model_seed)
+    bu = torch.randn(U, generator=gm, device=device) * 0.4
+    bi = torch.randn(I, generator=gm, device=device) * 0.4
+    P = torch.randn(U, 8, generator=gm, device=device) * 0.3
+    Q = torch.randn(I, 8, generator=gm, device=device) * 0.3
+    perm_u = torch.randperm(U, generator=gm, device=device)
+    perm_i = torch.randperm(I, generator=gm, device=device)
+    cdf_u = torch.cumsum(1.0 / torch.arange(1, U + 1, device=device, dtype=torch.float64), 0)
+    cdf_u /= cdf_u[-1].clone()
+    cdf_i = torch.cumsum(1.0 / torch.arange(1, I + 1, device=device, dtype=torch.float64), 0)
+    cdf_i /= cdf_i[-1].clone()
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    u = torch.empty(n, dtype=torch.int32, device=device)
+    it = torch.empty(n, dtype=torch.int32, device=device)
+    y = torch.empty(n, dtype=torch.float32, device=device)
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        ru = torch.searchsorted(cdf_u, torch.rand(b - a, generator=g, device=device, dtype=torch.float64)).clamp_(max=U - 1)
+        ri = torch.searchsorted(cdf_i, torch.rand(b - a, generator=g, device=device, dtype=torch.float64)).clamp_(max=I - 1)
+        uu, ii = perm_u[ru], perm_i[ri]
+        s = 3.5 + bu[uu] + bi[ii] + (P[uu] * Q[ii]).sum(1) + 0.8 * torch.randn(b - a, generator=g, device=device)
+        u[a:b] = uu.to(torch.int32)
+        it[a:b] = ii.to(torch.int32)
+        y[a:b] = s.round_().clamp_(1, 5)
+    return u, it, y
+
+
+def csc_two_field_torch(u, it, U, I, num_cols=None):
+    """CSC of the two one-hot fields built with torch sorts on the device. Returns (colptr int64[nc+1], case_id int32[2n])."""
+    import torch
+    nc = int(num_cols) if num_cols is not None else U + I
+    n = u.numel()
+    case_id = torch.empty(2 * n, dtype=torch.int32, device=u.device)
+    case_id[:n] = torch.sort(u, stable=True)[1].to(torch.int32)
+    case_id[n:] = torch.sort(it, stable=True)[1].to(torch.int32)
+    cnt = torch.zeros(nc, dtype=torch.int64, device=u.device)
+    cnt[:U] = torch.bincount(u, minlength=U)
+    cnt[U:U + I] = torch.bincount(it, minlength=I)
+    colptr = torch.zeros(nc + 1, dtype=torch.int64, device=u.device)
+    colptr[1:] = torch.cumsum(cnt, 0)
+    return colptr, case_id
