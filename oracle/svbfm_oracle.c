@@ -211,6 +211,14 @@ int orc_set_mcmc_options(orc_t *h, int do_sample, int do_multilevel) {
     h->do_sample = do_sample; h->do_multilevel = do_multilevel; return 0;
 }
 int orc_set_num_batch(orc_t *h, uint32_t nb) { h->num_batch = nb; return 0; }
+/* -regular r0,r1,r2 for mcmc/als (libfm.cpp:367-405): call after orc_init */
+int orc_set_regular(orc_t *h, double r0, double rw, double rv) {
+    if (h->method != ORC_MCMC || !h->w_lambda) return -1;
+    h->reg0 = r0;
+    for (uint32_t g = 0; g < h->G; g++) h->w_lambda[g] = rw;
+    for (size_t i = 0; i < (size_t)h->G * h->K; i++) h->v_lambda[i] = rv;
+    return 0;
+}
 
 static double *dalloc(size_t n) { return (double *)calloc(n ? n : 1, sizeof(double)); }
 

@@ -50,6 +50,7 @@ int    orc_begin(orc_t* h);
  * vb_online -> one epoch over num_batch batches */
 int    orc_iterate(orc_t* h, orc_stats* out);
 int    orc_set_num_batch(orc_t* h, uint32_t num_batch);
+int    orc_set_regular(orc_t* h, double r0, double rw, double rv);   /* mcmc/als -regular (libfm.cpp:367-405); after orc_init */
 
 /* state access (row-major [K][D] for the matrices, like DMatrix::value[f][j]) */
 int    orc_get_state(orc_t* h, double* w0_mean, double* w0_var, double* w_mean /*[D]*/, double* w_var /*[D]*/,

@@ -143,7 +143,17 @@ static int sweep_run(Engine* E, const Run& r, int f) {
     fa.seed = E->cfg.seed; fa.do_sample = E->cfg.do_sample;
     k_finalize<KIND><<<nblk(ncols), 256, 0, st>>>(fa); LAUNCHED(E);
     }
-    if (ntiles) {
+    if (ntiles && r.nnz * 4 >= (uint64_t)S.n) {
+        // run touches a large share of the cases: streaming pass in case order
+        ProfScope ps(E, pc + 2);
+        RowApplyArgs ra{};
+        ra.rv = row_view(S); ra.n = S.n; ra.c0 = r.col_begin; ra.c1 = r.col_end; ra.e = E->d_e; ra.pf = pf; ra.delta = E->d_delta;
+        unsigned grid = std::max(1u, std::min<unsigned>(nblk(S.n), 148 * 16));
+#define CALL_RA(FT, ONES) k_row_apply<IS_V, FT, ONES><<<grid, 256, 0, st>>>(ra)
+        DISPATCH_FMT(S, CALL_RA);
+#undef CALL_RA
+        LAUNCHED(E);
+    } else if (ntiles) {
         ProfScope ps(E, pc + 2);
         unsigned grid = (ntiles + 7) / 8;
         if constexpr (IS_V) {

@@ -357,6 +357,65 @@ __global__ void __launch_bounds__(256) k_sweep_apply(SweepArgs a) {
     }
 }
 
+// pass 2 in CASE order (streaming): the run's columns are case-disjoint, so every case has at most one feature
+// inside [c0, c1); e_i += x * h * delta_j with delta and the parameters served from L2. Used when the run covers
+// a large share of the cases; the CSC-order kernel above is kept for small runs.
+struct RowApplyArgs {
+    RowView rv;
+    uint32_t n, c0, c1;
+    double* e;
+    const double2* pf;
+    const double* delta;
+};
+
+template <bool IS_V, int FT, bool ONES>
+__global__ void __launch_bounds__(256) k_row_apply(RowApplyArgs a) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+        if constexpr (FT == 2) {
+            uint2 c = __ldg(reinterpret_cast<const uint2*>(a.rv.rcol) + i);
+            bool in0 = (c.x >= a.c0) & (c.x < a.c1), in1 = (c.y >= a.c0) & (c.y < a.c1);
+            if (!(in0 | in1)) continue;
+            uint32_t j = in0 ? c.x : c.y, o = in0 ? c.y : c.x;
+            double d = __ldg(&a.delta[j]);
+            if (d == 0.0) continue;
+            float xj = 1.0f, xo = 1.0f;
+            if constexpr (!ONES) {
+                float2 xv = __ldg(reinterpret_cast<const float2*>(a.rv.rval) + i);
+                xj = in0 ? xv.x : xv.y; xo = in0 ? xv.y : xv.x;
+            }
+            double hh = xj;
+            if constexpr (IS_V) hh = xj * (__ldg(&a.pf[o]).x * xo);
+            a.e[i] += hh * d;
+        } else {
+            uint64_t b, e_;
+            if constexpr (FT == 1) { b = (uint64_t)i * a.rv.F; e_ = b + a.rv.F; }
+            else { b = __ldg(&a.rv.rowptr[i]); e_ = __ldg(&a.rv.rowptr[i + 1]); }
+            uint64_t own = e_;
+            for (uint64_t k = b; k < e_; k++) {
+                uint32_t c = __ldg(&a.rv.rcol[k]);
+                if (c >= a.c0 && c < a.c1) { own = k; break; }
+            }
+            if (own == e_) continue;
+            uint32_t j = __ldg(&a.rv.rcol[own]);
+            double d = __ldg(&a.delta[j]);
+            if (d == 0.0) continue;
+            float xj = 1.0f;
+            if constexpr (!ONES) xj = __ldg(&a.rv.rval[own]);
+            double hh = xj;
+            if constexpr (IS_V) {
+                double h = 0.0;
+                for (uint64_t k = b; k < e_; k++) {
+                    if (k == own) continue;
+                    double m = __ldg(&a.pf[__ldg(&a.rv.rcol[k])]).x;
+                    if constexpr (ONES) h += m; else h += m * __ldg(&a.rv.rval[k]);
+                }
+                hh = xj * h;
+            }
+            a.e[i] += hh * d;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // dense passes over the residuals
 #define SV_RGRID 1184   // 148 SMs x 8

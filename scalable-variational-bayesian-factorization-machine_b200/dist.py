@@ -1,0 +1,43 @@
+"""Host-side logic of the row-sharded multi-GPU path: one process per GPU, cases split
+into contiguous shards, features and parameters replicated. The only exchange on the data path is the
+allreduce of the per-run column sums, done inside the engine by NCCL; this module holds what the host does:
+shard bounds, shard extraction from a CSC data set and the distribution of the NCCL unique id."""
+import numpy as np
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous, balanced case ranges: [n*rank/world, n*(rank+1)/world)."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def shard_csc(data, rank, world):
+    """Cases [lo, hi) of a CscData with local case ids (ascending order inside every column is preserved)."""
+    import sys
+    CscData = sys.modules[__name__.rsplit('.', 1)[0]].CscData   # the package is loaded by path (svbfm_b200.py)
+    lo, hi = shard_bounds(data.num_cases, rank, world)
+    keep = (data.case_id >= lo) & (data.case_id < hi)
+    col_of = np.repeat(np.arange(data.num_feature, dtype=np.int64), np.diff(data.colptr.astype(np.int64)))
+    colptr = np.zeros(data.num_feature + 1, dtype=np.uint64)
+    np.cumsum(np.bincount(col_of[keep], minlength=data.num_feature), out=colptr[1:])
+    return CscData(colptr, (data.case_id[keep] - lo).astype(np.uint32), data.x[keep], data.target[lo:hi])
+
+
+def broadcast_unique_id(get_id, rank, device=None):
+    """Rank 0 calls get_id() -> bytes; every rank returns the same bytes (torch.distributed broadcast; gloo or nccl)."""
+    import torch
+    import torch.distributed as dist
+    buf = torch.zeros(128, dtype=torch.uint8, device=device if device is not None else "cpu")
+    if rank == 0:
+        buf.copy_(torch.tensor(list(get_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    return bytes(buf.cpu().tolist())
+
+
+def w_column_sums(data, e, mu_w):
+    """Per-column sufficient statistics of the w sweep on a shard: A_j = sum x (e_i + x mu_j), B_j = sum x^2
+    (fm_learn_vb.h:534-539). numpy, used by the gloo test of the sharding algebra."""
+    col_of = np.repeat(np.arange(data.num_feature, dtype=np.int64), np.diff(data.colptr.astype(np.int64)))
+    x = data.x.astype(np.float64)
+    A = np.bincount(col_of, weights=x * (e[data.case_id] + x * mu_w[col_of]), minlength=data.num_feature)
+    B = np.bincount(col_of, weights=x * x, minlength=data.num_feature)
+    return A, B

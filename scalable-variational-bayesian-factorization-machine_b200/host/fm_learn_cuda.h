@@ -1,0 +1,260 @@
+// host/fm_learn_cuda.h -- the learner shells: same interface as the reference's `class fm_learn`
+// (src/libfm/src/fm_learn.h:38-265) and its vb / vb_online / mcmc subclasses, with the sweep delegated to the
+// CUDA engine through the C-ABI (include/svbfm.h). What stays on the host is what the reference also does on
+// the host around the sweep: the libc-rand() initial state, the per-iteration files in the CWD
+// (test_rmse_<k0k1K>_<method>, free_energy_<k0k1K>_vb), the "#Iter=" lines and the -rlog fields.
+#pragma once
+#include <sys/resource.h>
+#include <cmath>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <limits>
+#include <sstream>
+#include "../../include/svbfm.h"
+#include "data.h"
+#include "init_state.h"
+#include "rlog.h"
+
+namespace svbfm_host {
+
+struct fm_model {                     // the fields of fm_model the drivers set (src/fm_core/fm_model.h:35-64; libfm.cpp:259-274)
+    uint32_t num_attribute = 0;
+    bool k0 = true, k1 = true;
+    int num_factor = 0;
+    double init_stdev = 0.01, init_mean = 0.0, stdev = 1.0;
+    double reg0 = 0.0, regw = 0.0, regv = 0.0;
+    void debug() const {
+        std::cout << "num_attributes=" << num_attribute << std::endl << "use w0=" << k0 << std::endl << "use w1=" << k1 << std::endl
+                  << "dim v =" << num_factor << std::endl << "reg_w0=" << reg0 << std::endl << "reg_w=" << regw << std::endl
+                  << "reg_v=" << regv << std::endl << "init ~ N(" << init_mean << "," << init_stdev << ")" << std::endl;
+    }
+};
+
+inline double user_time() {          // getusertime (src/util/util.h:70-80)
+    struct rusage ru;
+    getrusage(RUSAGE_SELF, &ru);
+    return (double)ru.ru_utime.tv_sec + (double)ru.ru_utime.tv_usec / 1e6;
+}
+
+struct ShardInfo { int rank = 0, world = 1; uint8_t comm_id[SVBFM_COMM_ID_BYTES] = {0}; };
+
+class fm_learn {
+public:
+    MetaInfo* meta = nullptr;
+    fm_model* fm = nullptr;
+    double min_target = 0, max_target = 0;
+    int task = 0;                    // 0 = regression, 1 = classification (not on this path)
+    DataSet* validation = nullptr;
+    RLog* log = nullptr;
+    unsigned num_iter = 100, num_eval_cases = 0;
+    long seed = 0;
+    int device = 0;
+    ShardInfo shard;
+    virtual ~fm_learn() {}
+    virtual void init() {            // fm_learn::init (fm_learn.h:80-100)
+        if (log) {
+            if (task == 0) { log->addField("rmse", nan_()); log->addField("mae", nan_()); }
+            else if (task == 1) log->addField("accuracy", nan_());
+            else throw std::string("unknown task");
+            log->addField("time_pred", nan_()); log->addField("time_learn", nan_());
+            log->addField("time_learn2", nan_()); log->addField("time_learn4", nan_());
+        }
+    }
+    virtual void learn(DataSet& train, DataSet& test) = 0;
+    virtual void predict(DataSet& data, std::vector<double>& out) = 0;
+    virtual double evaluate(DataSet&) { return nan_(); }          // vb.h:27 / mcmc.h:69
+    virtual void debug() {
+        std::cout << "task=" << task << std::endl << "min_target=" << min_target << std::endl << "max_target=" << max_target << std::endl;
+    }
+protected:
+    static double nan_() { return std::numeric_limits<double>::quiet_NaN(); }
+};
+
+// common CUDA plumbing of the three learners
+class fm_learn_cuda : public fm_learn {
+public:
+    int method = SVBFM_VB;
+    bool do_sample = true, do_multilevel = true;
+    ~fm_learn_cuda() override { if (h_) svbfm_destroy(h_); }
+
+    void init() override {
+        fm_learn::init();
+        if (task != 0) throw std::string("task not supported on the CUDA path (regression only)");
+        init_state(seed, fm->num_attribute, fm->num_factor, fm->init_stdev, method, state_);   // host/init_state.h
+        if (log) {                   // fm_learn_vb::init / fm_learn_mcmc::init log fields (vb.h:714-742, mcmc.h:1120-1150)
+            log->addField("alpha", nan_());
+            log->addField("rmse_mcmc_this", nan_());
+            log->addField("rmse_mcmc_all", nan_());
+            if (method == SVBFM_MCMC) log->addField("rmse_mcmc_all_but5", nan_());
+            for (uint32_t g = 0; g < meta->num_attr_groups; g++) {
+                std::ostringstream a, b;
+                a << "wmu[" << g << "]"; b << "wlambda[" << g << "]";
+                log->addField(a.str(), nan_()); log->addField(b.str(), nan_());
+                for (int f = 0; f < fm->num_factor; f++) {
+                    std::ostringstream c, d;
+                    c << "vmu[" << g << "," << f << "]"; d << "vlambda[" << g << "," << f << "]";
+                    log->addField(c.str(), nan_()); log->addField(d.str(), nan_());
+                }
+            }
+        }
+    }
+
+    void predict(DataSet& data, std::vector<double>& out) override {
+        out.assign(data.num_cases, 0.0);
+        ck(svbfm_predict(h_, SVBFM_TEST, out.data()), "svbfm_predict");
+    }
+    void debug() override { fm_learn::debug(); std::cout << "num_eval_cases=" << num_eval_cases << std::endl; }
+
+protected:
+    svbfm_t* h_ = nullptr;
+    InitialState state_;
+    std::string tag_;                // "<k0><k1><K>"
+
+    void ck(int rc, const char* what) {
+        if (rc != 0) throw std::string(what) + ": " + svbfm_last_error(h_);     // -> "ERROR: ..." in main (libfm.cpp:521-525)
+    }
+    bool root() const { return shard.rank == 0; }
+
+    void open_engine(DataSet& train, DataSet& test) {
+        svbfm_config c;
+        memset(&c, 0, sizeof(c));
+        c.struct_size = sizeof(c); c.method = method; c.num_attribute = fm->num_attribute; c.num_factor = fm->num_factor;
+        c.k0 = fm->k0; c.k1 = fm->k1; c.task = 0; c.min_target = min_target; c.max_target = max_target; c.device = device;
+        c.do_sample = do_sample; c.do_multilevel = do_multilevel; c.seed = (uint64_t)seed; c.reg0 = fm->reg0; c.regw = fm->regw; c.regv = fm->regv;
+        int rc = svbfm_create(&h_, &c);
+        if (rc != 0) throw std::string("svbfm_create: ") + svbfm_last_error(nullptr);
+        if (shard.world > 1) ck(svbfm_comm_init(h_, shard.comm_id, shard.rank, shard.world), "svbfm_comm_init");
+        ck(svbfm_set_groups(h_, meta->attr_group.data(), meta->num_attr_groups), "svbfm_set_groups");
+        push(SVBFM_TRAIN, train);
+        push(SVBFM_TEST, test);
+        ck(svbfm_set_state(h_, state_.w0_mean, state_.w0_var, state_.w_mean.data(), state_.w_var.data(), state_.v_mean.data(), state_.v_var.data()),
+           "svbfm_set_state");
+        std::ostringstream t;
+        t << fm->k0 << fm->k1 << fm->num_factor;
+        tag_ = t.str();
+    }
+
+    // hands data_t + target of this rank's shard of cases to the engine
+    void push(int split, DataSet& d) {
+        if (shard.world <= 1) {
+            ck(svbfm_set_csc(h_, split, d.num_cases, d.xt.num_rows, d.xt.ptr.data(), d.xt.id.data(), d.xt.val.data(), d.target.data()), "svbfm_set_csc");
+            return;
+        }
+        uint32_t lo = (uint32_t)((uint64_t)d.num_cases * shard.rank / shard.world), hi = (uint32_t)((uint64_t)d.num_cases * (shard.rank + 1) / shard.world);
+        SparseMatrix s;
+        s.num_rows = d.xt.num_rows; s.ptr.assign(1, 0);
+        for (uint32_t j = 0; j < d.xt.num_rows; j++) {
+            for (uint64_t p = d.xt.ptr[j]; p < d.xt.ptr[j + 1]; p++)
+                if (d.xt.id[p] >= lo && d.xt.id[p] < hi) { s.id.push_back(d.xt.id[p] - lo); s.val.push_back(d.xt.val[p]); }
+            s.ptr.push_back(s.id.size());
+        }
+        ck(svbfm_set_csc(h_, split, hi - lo, s.num_rows, s.ptr.data(), s.id.data(), s.val.data(), d.target.data() + lo), "svbfm_set_csc");
+    }
+
+    void truncate_file(const std::string& name) { if (root()) { std::ofstream f(name.c_str()); } }
+    void append_value(const std::string& name, double v) { if (root()) { std::ofstream f(name.c_str(), std::ios_base::app); f << v << "\n"; } }
+};
+
+// fm_learn_vb_simultaneous (src/libfm/src/fm_learn_vb_simultaneous.h:15-259)
+class fm_learn_vb_cuda : public fm_learn_cuda {
+public:
+    fm_learn_vb_cuda() { method = SVBFM_VB; }
+    void learn(DataSet& train, DataSet& test) override {
+        open_engine(train, test);
+        ck(svbfm_begin(h_), "svbfm_begin");
+        truncate_file("test_rmse_" + tag_ + "_vb");                 // vbs.h:66-73
+        truncate_file("free_energy_" + tag_ + "_vb");
+        for (unsigned i = 0; i < num_iter; i++) {
+            double t0 = user_time(); clock_t c0 = clock(); time_t w0 = time(nullptr);
+            svbfm_iter_stats s;
+            ck(svbfm_vb_sweep(h_, &s), "svbfm_vb_sweep");
+            if (s.nan_inf_count > 0 && root()) std::cout << "#nans/infs reverted:\t" << s.nan_inf_count << std::endl;
+            if (s.has_free_energy) {
+                append_value("free_energy_" + tag_ + "_vb", -s.free_energy);                          // vb.h:678 (file holds -F)
+                if (root()) std::cout << "free energy " << s.free_energy << std::endl;                 // vb.h:680
+            }
+            append_value("test_rmse_" + tag_ + "_vb", s.test_rmse);                                   // vbs.h:221
+            if (root())
+                std::cout << "#Iter=" << std::setw(3) << i << "\tTrain=" << s.train_stat << "\tTest=" << s.test_rmse << std::endl;   // vbs.h:222
+            if (log && root()) {
+                log->log("time_learn", user_time() - t0);
+                log->log("time_learn2", (double)(clock() - c0) / CLOCKS_PER_SEC);
+                log->log("time_learn4", (double)(time(nullptr) - w0));
+                log->log("alpha", s.alpha);
+                log->log("rmse_mcmc_this", s.test_rmse);
+                log->newLine();
+            }
+        }
+    }
+};
+
+// fm_learn_mcmc_simultaneous (src/libfm/src/fm_learn_mcmc_simultaneous.h:47-305)
+class fm_learn_mcmc_cuda : public fm_learn_cuda {
+public:
+    fm_learn_mcmc_cuda() { method = SVBFM_MCMC; }
+    void learn(DataSet& train, DataSet& test) override {
+        open_engine(train, test);
+        ck(svbfm_begin(h_), "svbfm_begin");
+        truncate_file("test_rmse_" + tag_ + "_mcmc");               // mcmcs.h:60-62
+        for (unsigned i = 0; i < num_iter; i++) {
+            double t0 = user_time(); clock_t c0 = clock(); time_t w0 = time(nullptr);
+            svbfm_iter_stats s;
+            ck(svbfm_mcmc_sweep(h_, &s), "svbfm_mcmc_sweep");
+            if (s.nan_inf_count > 0 && root()) std::cout << "#nans/infs reverted:\t" << s.nan_inf_count << std::endl;
+            if (root())
+                std::cout << "#Iter=" << std::setw(3) << i << "\tTrain=" << s.train_stat << "\tTest=" << s.test_rmse << std::endl;   // mcmcs.h:244
+            append_value("test_rmse_" + tag_ + "_mcmc", s.test_rmse);                                  // mcmcs.h:245
+            if (log && root()) {
+                log->log("time_learn", user_time() - t0);
+                log->log("time_learn2", (double)(clock() - c0) / CLOCKS_PER_SEC);
+                log->log("time_learn4", (double)(time(nullptr) - w0));
+                log->log("alpha", s.alpha);
+                log->log("rmse", s.test_rmse);
+                log->log("rmse_mcmc_this", s.rmse_this);
+                log->log("rmse_mcmc_all", s.test_rmse);
+                log->newLine();
+            }
+        }
+    }
+};
+
+// fm_learn_vb_online_simultaneous (src/libfm/src/fm_learn_vb_online_simultaneous.h:18-290). The reference
+// re-reads the training file and writes one text file per batch every epoch; here the file is parsed once
+// and only the case -> batch rule (vbos.h:74-95, libc shuffle stream) is replayed.
+class fm_learn_vb_online_cuda : public fm_learn_cuda {
+public:
+    unsigned num_batch = 50;
+    std::string training_file, testing_file;
+    fm_learn_vb_online_cuda() { method = SVBFM_VB_ONLINE; }
+    void learn(DataSet& train, DataSet& test) override {
+        open_engine(train, test);
+        ck(svbfm_begin(h_), "svbfm_begin");
+        truncate_file("test_rmse_" + tag_ + "_vb_online");           // vbos.h:45-52
+        truncate_file("free_energy_" + tag_ + "_vb_online");
+        uint32_t n = train.num_cases;
+        uint32_t size_except_last = (uint32_t)std::ceil((double)n / num_batch);
+        std::vector<uint32_t> shuffle(n), batch(n);
+        for (uint32_t i = 0; i < n; i++) shuffle[i] = i + 1;
+        uint32_t lo = (uint32_t)((uint64_t)n * shard.rank / shard.world), hi = (uint32_t)((uint64_t)n * (shard.rank + 1) / shard.world);
+        for (unsigned k = 0; k < num_iter; k++) {
+            double t0 = user_time(); clock_t c0 = clock(); time_t w0 = time(nullptr);
+            libc_random_shuffle(shuffle.data(), n);                   // vbos.h:74
+            for (uint32_t r = 0; r < n; r++) batch[r] = (uint32_t)std::ceil((double)shuffle[r] / size_except_last) - 1;   // vbos.h:93
+            svbfm_iter_stats s;
+            ck(svbfm_vb_online_epoch(h_, batch.data() + lo, num_batch, &s), "svbfm_vb_online_epoch");
+            (void)hi;
+            if (root()) std::cout << "#Iter=" << std::setw(3) << k << "\tTest=" << s.test_rmse << std::endl;     // vbos.h:244
+            append_value("test_rmse_" + tag_ + "_vb_online", s.test_rmse);                                  // vbos.h:243
+            if (log && root()) {
+                log->log("time_learn", user_time() - t0);
+                log->log("time_learn2", (double)(clock() - c0) / CLOCKS_PER_SEC);
+                log->log("time_learn4", (double)(time(nullptr) - w0));
+                log->log("rmse_mcmc_this", s.test_rmse);
+                log->newLine();
+            }
+        }
+    }
+};
+
+}  // namespace svbfm_host

@@ -1,0 +1,130 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*: small seeded data sets (libFM text), and the outputs of the UNMODIFIED reference
+binaries (oracle/_ref/{libFM,convert,transpose}, built from /root/reference by oracle/Makefile) on them with
+a fixed seed (oracle/fixtime.c). Run in the authoring container only:
+
+    python tests/golden/make_golden.py
+
+The committed files are what the CPU tests pin the oracle with and what the GPU tests compare the CUDA path to.
+"""
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.path.join(ROOT, "oracle", "_ref")
+sys.path.insert(0, ROOT)
+
+
+def write_two_field(path, n, U, I, seed):
+    r = np.random.default_rng(seed)
+    pu = 1.0 / np.arange(1, U + 1); pu /= pu.sum()
+    pi = 1.0 / np.arange(1, I + 1); pi /= pi.sum()
+    bu, bi = r.normal(0, 0.4, U), r.normal(0, 0.4, I)
+    P, Q = r.normal(0, 0.3, (U, 4)), r.normal(0, 0.3, (I, 4))
+    rr = np.random.default_rng(seed + 1000)
+    u, i = rr.choice(U, n, p=pu), rr.choice(I, n, p=pi)
+    y = np.clip(np.round(3.5 + bu[u] + bi[i] + (P[u] * Q[i]).sum(1) + rr.normal(0, 0.8, n)), 1, 5).astype(int)
+    with open(path, "w") as f:
+        for a, b, c in zip(y, u, i):
+            f.write(f"{a} {b}:1 {U + c}:1\n")
+
+
+def write_ragged(path, n, D, seed, comments=False):
+    r = np.random.default_rng(seed)
+    with open(path, "w") as f:
+        if comments:
+            f.write("# a comment line, then an empty line\n\n")
+        for k in range(n):
+            m = int(r.integers(0, 5))
+            cols = np.sort(r.choice(D, size=m, replace=False))
+            vals = np.round(r.uniform(0.2, 2.0, m), 3)
+            y = round(float(r.normal(0, 1)), 3)
+            lead = "  " if (comments and k % 7 == 0) else ""
+            tail = "   # trailing" if (comments and k % 11 == 0) else ""
+            f.write(lead + f"{y}" + "".join(f" {c}:{v}" for c, v in zip(cols, vals)) + tail + "\n")
+
+
+def run_ref(workdir, args, seed):
+    env = dict(os.environ, FAKE_TIME=str(seed), LD_PRELOAD=os.path.join(REF, "fixtime.so"))
+    p = subprocess.run([os.path.join(REF, "libFM")] + args, cwd=workdir, env=env, capture_output=True, text=True, check=True)
+    return p.stdout
+
+
+def read_floats(path):
+    return [float(x) for x in open(path).read().split()] if os.path.exists(path) else []
+
+
+def main():
+    assert os.path.exists(os.path.join(REF, "libFM")), "run `make -C oracle ref` first"
+    write_two_field(os.path.join(HERE, "g1_train.libfm"), 3000, 120, 90, 11)
+    write_two_field(os.path.join(HERE, "g1_test.libfm"), 400, 120, 90, 12)
+    write_ragged(os.path.join(HERE, "g2_train.libfm"), 1500, 40, 21, comments=True)
+    write_ragged(os.path.join(HERE, "g2_test.libfm"), 200, 40, 22)
+    # g3: ragged WITHOUT comment/blank lines. The reference's vb_online maps raw FILE lines (comments included) to
+    # batches and stops after num_cases raw lines (vbos.h:87-95), so it silently drops trailing cases of a file
+    # that has comment lines; that artefact is not restated, hence a clean file for the vb_online case.
+    write_ragged(os.path.join(HERE, "g3_train.libfm"), 1200, 40, 23)
+    shutil.copy(os.path.join(HERE, "g2_test.libfm"), os.path.join(HERE, "g3_test.libfm"))
+    D2 = 41   # max(train, test num_feature) + 1 with ids < 40
+    groups = (np.arange(D2) * 3 // D2).astype(int)
+    with open(os.path.join(HERE, "g2_meta.txt"), "w") as f:
+        f.write("\n".join(str(g) for g in groups) + "\n")
+
+    cases = [
+        dict(name="g1_vb_114", data="g1", method="vb", dim="1,1,4", iters=10, seed=42),
+        dict(name="g1_vb_012", data="g1", method="vb", dim="0,1,2", iters=5, seed=7),
+        dict(name="g1_vb_100", data="g1", method="vb", dim="1,0,0", iters=4, seed=7),
+        dict(name="g1_mcmc_114", data="g1", method="mcmc", dim="1,1,4", iters=10, seed=42),
+        dict(name="g1_als_113", data="g1", method="als", dim="1,1,3", iters=6, seed=5, extra=["-regular", "0.5,1,2"]),
+        dict(name="g1_vbo_113", data="g1", method="vb_online", dim="1,1,3", iters=4, seed=42, extra=["-batch", "5"]),
+        dict(name="g2_vb_113_meta", data="g2", method="vb", dim="1,1,3", iters=6, seed=9, meta=True),
+        dict(name="g2_mcmc_112_meta", data="g2", method="mcmc", dim="1,1,2", iters=6, seed=9, meta=True),
+        dict(name="g3_vbo_112", data="g3", method="vb_online", dim="1,1,2", iters=3, seed=3, extra=["-batch", "4"]),
+    ]
+    golden = {"cases": []}
+    for c in cases:
+        with tempfile.TemporaryDirectory() as td:
+            for s in ("train", "test"):
+                shutil.copy(os.path.join(HERE, f"{c['data']}_{s}.libfm"), os.path.join(td, s))
+            args = ["-task", "r", "-train", "train", "-test", "test", "-dim", c["dim"], "-method", c["method"], "-iter", str(c["iters"])]
+            if c.get("meta"):
+                shutil.copy(os.path.join(HERE, "g2_meta.txt"), os.path.join(td, "meta"))
+                args += ["-meta", "meta"]
+            args += c.get("extra", [])
+            out = run_ref(td, args, c["seed"])
+            k = c["dim"].split(",")
+            tag = f"{int(k[0] != '0')}{int(k[1] != '0')}{k[2]}"
+            m = "mcmc" if c["method"] == "als" else c["method"]
+            rec = dict(c)
+            rec["test_rmse"] = read_floats(os.path.join(td, f"test_rmse_{tag}_{m}"))
+            rec["neg_free_energy"] = read_floats(os.path.join(td, f"free_energy_{tag}_vb"))   # vb_online also appends here (vbo.h:637)
+            rec["train_stat"] = [float(l.split("Train=")[1].split("\t")[0]) for l in out.splitlines() if l.startswith("#Iter=") and "Train=" in l]
+            assert len(rec["test_rmse"]) == c["iters"], (c["name"], rec["test_rmse"], out[-2000:])
+            golden["cases"].append(rec)
+            print(c["name"], rec["test_rmse"][-1], rec["neg_free_energy"][-1:] )
+    # formats: reference convert / transpose outputs for both data sets (committed bytes)
+    for d in ("g1", "g2"):
+        with tempfile.TemporaryDirectory() as td:
+            src = os.path.join(HERE, f"{d}_train.libfm")
+            subprocess.run([os.path.join(REF, "convert"), "--ifile", src, "--ofilex", os.path.join(td, "a.x"), "--ofiley", os.path.join(td, "a.y")],
+                           check=True, capture_output=True)
+            subprocess.run([os.path.join(REF, "transpose"), "--ifile", os.path.join(td, "a.x"), "--ofile", os.path.join(td, "a.xt")],
+                           check=True, capture_output=True)
+            for ext in ("x", "y", "xt"):
+                shutil.copy(os.path.join(td, f"a.{ext}"), os.path.join(HERE, f"{d}_train.{ext}"))
+    # RNG known answers: first draws of the reference's generators after srand(42), via its own binary is not
+    # possible (no CLI for it), so they are pinned indirectly by the vb/mcmc runs above (initial state).
+    with open(os.path.join(HERE, "golden.json"), "w") as f:
+        json.dump(golden, f, indent=1)
+    print("wrote", os.path.join(HERE, "golden.json"))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,80 @@
+"""-m gpu: the drop-in path end to end. The libFM-compatible CLI (host/libfm.cpp -> C-ABI -> CUDA) is run on the
+committed golden inputs with the same seed the reference binary was run with, and the files it writes into the CWD
+(test_rmse_<k0k1K>_<method>, free_energy_<k0k1K>_vb) are compared with the reference's own files.
+Tolerance: north_star's 1e-4 relative per iteration for VB / ALS (values carry 6 significant digits); sampled MCMC
+uses another RNG stream and is only checked for sanity here (distribution parity: test_gpu_parity.py)."""
+import json
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import svbfm_b200 as sv
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+GOLD = json.load(open(os.path.join(G, "golden.json")))["cases"]
+EXE = os.path.join(sv.PKG_DIR, "bin", "libFM")
+TOL = 1e-4
+
+
+def floats(path):
+    return [float(x) for x in open(path).read().split()]
+
+
+@pytest.mark.parametrize("c", [c for c in GOLD if c["method"] != "vb_online"], ids=lambda c: c["name"])
+def test_cli_reproduces_reference_files(built, tmp_path, c):
+    for s in ("train", "test"):
+        shutil.copy(os.path.join(G, f"{c['data']}_{s}.libfm"), tmp_path / s)
+    args = [EXE, "-task", "r", "-train", "train", "-test", "test", "-dim", c["dim"], "-method", c["method"], "-iter", str(c["iters"]),
+            "-seed", str(c["seed"]), "-rlog", "log.tsv", "-out", "pred.txt"]
+    if c.get("meta"):
+        shutil.copy(os.path.join(G, "g2_meta.txt"), tmp_path / "meta")
+        args += ["-meta", "meta"]
+    args += c.get("extra", [])
+    p = subprocess.run(args, cwd=tmp_path, capture_output=True, text=True)
+    assert "ERROR" not in p.stderr, p.stderr
+    k = c["dim"].split(",")
+    tag = f"{int(k[0] != '0')}{int(k[1] != '0')}{k[2]}"
+    m = "mcmc" if c["method"] == "als" else c["method"]
+    rmse = floats(tmp_path / f"test_rmse_{tag}_{m}")
+    assert len(rmse) == c["iters"]
+    exact = c["method"] in ("vb", "als")
+    if exact:
+        for it, (a, b) in enumerate(zip(rmse, c["test_rmse"])):
+            assert abs(a - b) <= TOL * b, (it, a, b)
+        train = [float(l.split("Train=")[1].split("\t")[0]) for l in p.stdout.splitlines() if l.startswith("#Iter=")]
+        for a, b in zip(train, c["train_stat"]):
+            assert abs(a - b) <= TOL * b
+    else:
+        assert abs(rmse[-1] - c["test_rmse"][-1]) < 0.05 * c["test_rmse"][-1]
+    if c["method"] == "vb":
+        fe = floats(tmp_path / f"free_energy_{tag}_vb")
+        assert len(fe) == len(c["neg_free_energy"])
+        for a, b in zip(fe, c["neg_free_energy"]):
+            assert abs(a - b) <= TOL * abs(b), (a, b)
+    pred = floats(tmp_path / "pred.txt")
+    assert len(pred) == sum(1 for _ in open(tmp_path / "test")) and np.all(np.isfinite(pred))
+    log = [l.split("\t") for l in open(tmp_path / "log.tsv").read().splitlines()]
+    assert "time_learn" in log[0] and len(log) == c["iters"] + 1
+
+
+def test_cli_binary_input_equals_text_input(built, tmp_path):
+    """`-train name` with name.x / name.xt / name.y next to it (Data.h:112-117) gives the same numbers as the text file."""
+    c = GOLD[0]
+    BIN = os.path.join(sv.PKG_DIR, "bin")
+    for s in ("train", "test"):
+        src = os.path.join(G, f"{c['data']}_{s}.libfm")
+        subprocess.run([os.path.join(BIN, "convert"), "--ifile", src, "--ofilex", str(tmp_path / f"{s}.x"), "--ofiley", str(tmp_path / f"{s}.y")],
+                       check=True, capture_output=True)
+        subprocess.run([os.path.join(BIN, "transpose"), "--ifile", str(tmp_path / f"{s}.x"), "--ofile", str(tmp_path / f"{s}.xt")], check=True, capture_output=True)
+    p = subprocess.run([EXE, "-task", "r", "-train", "train", "-test", "test", "-dim", c["dim"], "-method", "vb", "-iter", "3", "-seed", str(c["seed"])],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert "ERROR" not in p.stderr, p.stderr
+    rmse = floats(tmp_path / "test_rmse_114_vb")
+    for a, b in zip(rmse, c["test_rmse"][:3]):
+        assert abs(a - b) <= TOL * b
