@@ -72,6 +72,7 @@ typedef struct svbfm_iter_stats {
     uint32_t nan_inf_count;    /* sum of the reference's nan_ and inf_ counters for this iteration */
     float sweep_ms;            /* device time of the update_all / draw_all equivalent (CUDA events) */
     float predict_ms;          /* device time of the test (and mcmc: train) prediction + evaluation */
+    double free_energy_first;  /* vb_online: +F after batch 1 of the epoch (free_energy holds batch B's); else = free_energy */
 } svbfm_iter_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */

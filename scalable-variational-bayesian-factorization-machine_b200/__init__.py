@@ -40,7 +40,8 @@ class Config(C.Structure):
 class IterStats(C.Structure):
     _fields_ = [("test_rmse", C.c_double), ("train_stat", C.c_double), ("free_energy", C.c_double),
                 ("alpha", C.c_double), ("rmse_this", C.c_double), ("has_free_energy", C.c_int32),
-                ("nan_inf_count", C.c_uint32), ("sweep_ms", C.c_float), ("predict_ms", C.c_float)]
+                ("nan_inf_count", C.c_uint32), ("sweep_ms", C.c_float), ("predict_ms", C.c_float),
+                ("free_energy_first", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

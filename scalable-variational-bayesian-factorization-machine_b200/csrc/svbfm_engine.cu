@@ -100,7 +100,7 @@ struct ProfScope {
 
 // ---------------------------------------------------------------------------------------------- one run sweep
 template <int KIND>
-static int sweep_run(Engine* E, const Run& r, int f) {
+static int sweep_run(Engine* E, const Run& r, int f, int batch = -1) {
     const DevSplit& S = E->tr;
     cudaStream_t st = E->stream;
     uint32_t ntiles = r.tile_end - r.tile_begin;
@@ -109,7 +109,8 @@ static int sweep_run(Engine* E, const Run& r, int f) {
     SweepArgs a{};
     a.tile_col = E->d_tile_col; a.tile_begin = E->d_tile_begin; a.colptr = S.colptr; a.crow = S.crow; a.cval = S.cval;
     a.rv = row_view(S); a.e = E->d_e; a.pf = pf; a.partial = E->d_partial; a.delta = E->d_delta;
-    a.tile0 = r.tile_begin; a.ntiles = ntiles; a.tile_entries = E->tile_entries; a.in_batch = nullptr;
+    a.tile0 = r.tile_begin; a.ntiles = ntiles; a.tile_entries = E->tile_entries;
+    a.cbatch = batch >= 0 ? E->d_cbatch : nullptr; a.batch = batch >= 0 ? (uint32_t)batch : 0u;
     const int pc = IS_V ? 0 : 3;
     if (ntiles) {
         ProfScope ps(E, pc + 0);
@@ -141,13 +142,24 @@ static int sweep_run(Engine* E, const Run& r, int f) {
     fa.pf = pf; fa.group = E->d_group; fa.hyper = IS_V ? E->d_hyper_v : E->d_hyper_w;
     fa.hyper_mu = IS_V ? E->d_mu_v : E->d_mu_w; fa.sc = E->d_sc; fa.delta = E->d_delta; fa.dT = E->d_dT;
     fa.seed = E->cfg.seed; fa.do_sample = E->cfg.do_sample;
-    k_finalize<KIND><<<nblk(ncols), 256, 0, st>>>(fa); LAUNCHED(E);
+    if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V) {
+        fa.nat = IS_V ? E->d_nat_v + (size_t)f * E->D : E->d_nat_w;
+        fa.t_cnt = IS_V ? E->d_t_v : E->d_t_w;
+        fa.col_count = E->d_col_count;
+        fa.update_t = IS_V ? (f == E->K - 1) : 1;      // t_vj advances once per batch (vbo.h:399-402), t_wj per w update (:520)
+        int update_params = IS_V ? 1 : (E->cfg.k1 != 0);   // with k1 = 0 the w pass only counts the batch entries per column
+        k_finalize_vbo<KIND><<<nblk(ncols), 256, 0, st>>>(fa, E->d_cnt_col, 0.5, 1u, update_params);
+    } else {
+        k_finalize<KIND><<<nblk(ncols), 256, 0, st>>>(fa);
+    }
+    LAUNCHED(E);
     }
     if (ntiles && r.nnz * 4 >= (uint64_t)S.n) {
         // run touches a large share of the cases: streaming pass in case order
         ProfScope ps(E, pc + 2);
         RowApplyArgs ra{};
         ra.rv = row_view(S); ra.n = S.n; ra.c0 = r.col_begin; ra.c1 = r.col_end; ra.e = E->d_e; ra.pf = pf; ra.delta = E->d_delta;
+        ra.rbatch = batch >= 0 ? E->d_rbatch : nullptr; ra.batch = batch >= 0 ? (uint32_t)batch : 0u;
         unsigned grid = std::max(1u, std::min<unsigned>(nblk(S.n), 148 * 16));
 #define CALL_RA(FT, ONES) k_row_apply<IS_V, FT, ONES><<<grid, 256, 0, st>>>(ra)
         DISPATCH_FMT(S, CALL_RA);
@@ -170,9 +182,9 @@ static int sweep_run(Engine* E, const Run& r, int f) {
 }
 
 // sum e, sum e^2, sum clamp(e)^2 -> red[0..2] (global)
-static int reduce_e(Engine* E) {
+static int reduce_e(Engine* E, int batch = -1) {
     cudaStream_t st = E->stream;
-    k_reduce_e<<<SV_RGRID, 256, 0, st>>>(E->d_e, E->tr.n, E->d_sc, E->d_red_partial); LAUNCHED(E);
+    k_reduce_e<<<SV_RGRID, 256, 0, st>>>(E->d_e, E->tr.n, E->d_sc, E->d_red_partial, batch >= 0 ? E->d_rbatch : nullptr, batch >= 0 ? (uint32_t)batch : 0u); LAUNCHED(E);
     k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_RGRID, 3, RED(E->d_sc, 0), 0); LAUNCHED(E);
     return allreduce_sum_f64(E, RED(E->d_sc, 0), 3);
 }
@@ -190,12 +202,13 @@ static int group_sums(Engine* E, bool mcmc) {
 }
 
 template <int MODE>
-static int predict(Engine* E, const DevSplit& S, double* e_out, int red_slot, int nred) {
+static int predict(Engine* E, const DevSplit& S, double* e_out, int red_slot, int nred, int batch = -1) {
     cudaStream_t st = E->stream;
     PredictArgs a{};
     a.rv = row_view(S); a.y = S.y; a.n = S.n; a.pw = E->d_pw; a.pv = E->d_pv; a.D = E->D; a.K = E->K;
     a.k0 = E->cfg.k0; a.k1 = E->cfg.k1; a.sc = E->d_sc; a.e = e_out; a.pred = E->d_pred_test; a.pred_sum = E->d_pred_sum;
-    a.partial = E->d_red_partial; a.in_batch = nullptr;
+    a.partial = E->d_red_partial;
+    a.rbatch = batch >= 0 ? E->d_rbatch : nullptr; a.batch = batch >= 0 ? (uint32_t)batch : 0u;
     unsigned grid = std::max(1u, std::min<unsigned>(nblk(S.n), SV_RGRID));
 #define CALL_P(FT, ONES) k_predict<MODE, FT, ONES><<<grid, 256, 0, st>>>(a)
     DISPATCH_FMT(S, CALL_P);
@@ -303,7 +316,7 @@ static int run_iterations(Engine* E, uint32_t n_iter, svbfm_iter_stats* out) {
             memset(&o, 0, sizeof(o));
             o.test_rmse = hs[it].test_rmse; o.train_stat = hs[it].train_stat; o.free_energy = hs[it].free_energy;
             o.alpha = hs[it].alpha; o.rmse_this = hs[it].rmse_this; o.has_free_energy = hs[it].has_fe != 0.0;
-            o.nan_inf_count = (uint32_t)hs[it].nan_inf;
+            o.nan_inf_count = (uint32_t)hs[it].nan_inf; o.free_energy_first = hs[it].free_energy;
             cudaEventElapsedTime(&o.sweep_ms, ev[it].t0, ev[it].t1);
             cudaEventElapsedTime(&o.predict_ms, ev[it].t1, ev[it].t2);
         }
@@ -343,6 +356,13 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     }
     ce = cudaSetDevice(cfg->device);
     if (ce != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(ce); return SVBFM_ERR_CUDA; }
+    {
+        // The sweeps of every field but the first gather 8-16 B per case at random; with the default L2 fetch
+        // granularity each miss moves 128 B from HBM (ncu: 8 sectors per entry, profiles/r01_*). Ask for 32 B.
+        size_t gran = 32;
+        if (const char* s = getenv("SVBFM_L2_FETCH")) gran = (size_t)atoi(s);
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    }
     Engine* E = new Engine();
     E->cfg = *cfg; E->dev = cfg->device; E->D = cfg->num_attribute; E->K = cfg->num_factor;
     E->tile_entries = cfg->tile_entries ? cfg->tile_entries : 1024;
@@ -387,7 +407,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats};
+                    E->d_pred_sum, E->d_stats, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) cudaFree(p);
     if (E->own_stream) cudaStreamDestroy(E->own_stream);
     delete E;
@@ -607,6 +627,21 @@ int svbfm_begin(svbfm_t* h) {
     } else if (E->cfg.method == SVBFM_MCMC) {
         if (int rc = predict<PRED_MC_TRAIN>(E, E->tr, E->d_e, 6, 1)) return rc;     // e = yhat - y (mcmcs.h:75-80)
     }
+    else {   // vb_online: global count of every feature in the training data (vbo.h:704-726) and the natural parameters
+        if (!E->d_col_count) {
+            if (dev_alloc(E, &E->d_col_count, E->D)) return SVBFM_ERR_OOM;
+            if (dev_alloc(E, &E->d_nat_w, E->D)) return SVBFM_ERR_OOM;
+            if (dev_alloc(E, &E->d_nat_v, (size_t)E->K * E->D)) return SVBFM_ERR_OOM;
+            if (dev_alloc(E, &E->d_t_w, E->D)) return SVBFM_ERR_OOM;
+            if (dev_alloc(E, &E->d_t_v, E->D)) return SVBFM_ERR_OOM;
+        }
+        k_col_counts<<<nblk(E->D), 256, 0, st>>>(E->tr.colptr, E->tr.ncols_ext, E->D, E->d_col_count); LAUNCHED(E);
+        if (int rc = allreduce_sum_f64(E, E->d_col_count, E->D)) return rc;
+        k_nat_from_params<<<nblk(E->D), 256, 0, st>>>(E->d_pw, E->D, E->d_nat_w); LAUNCHED(E);
+        if (E->K) { k_nat_from_params<<<nblk((size_t)E->K * E->D), 256, 0, st>>>(E->d_pv, (size_t)E->K * E->D, E->d_nat_v); LAUNCHED(E); }
+        SV_CUDA(E, cudaMemsetAsync(E->d_t_w, 0, (size_t)E->D * 4, st));
+        SV_CUDA(E, cudaMemsetAsync(E->d_t_v, 0, (size_t)E->D * 4, st));
+    }
     SV_CUDA(E, cudaStreamSynchronize(st));
     E->begun = true;
     return check_launch(E, "begin");
@@ -631,9 +666,86 @@ int svbfm_mcmc_sweep(svbfm_t* h, svbfm_iter_stats* out) {
     return svbfm_run(h, 1, out);
 }
 int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t num_batch, svbfm_iter_stats* out) {
+    // One epoch of fm_learn_vb_online_simultaneous::_learn (vbos.h:66-288). Batches are case subsets of the resident
+    // design matrix, selected by a 16-bit batch id per case / per CSC entry; nothing goes through the disk.
     Engine* E = reinterpret_cast<Engine*>(h);
-    (void)batch_of_case; (void)num_batch; (void)out;
-    return fail(E, SVBFM_ERR_ARG, "svbfm_vb_online_epoch: not implemented yet");
+    if (!E || !batch_of_case || num_batch == 0) return fail(E, SVBFM_ERR_ARG, "svbfm_vb_online_epoch: bad arguments");
+    if (E->cfg.method != SVBFM_VB_ONLINE) return fail(E, SVBFM_ERR_ARG, "svbfm_vb_online_epoch on a non vb_online handle");
+    if (!E->begun) return fail(E, SVBFM_ERR_ARG, "svbfm_begin must be called first");
+    if (num_batch > 65535) return fail(E, SVBFM_ERR_ARG, "svbfm_vb_online_epoch: at most 65535 batches");
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    cudaStream_t st = E->stream;
+    const DevSplit& S = E->tr;
+    for (uint32_t i = 0; i < S.n; i++)
+        if (batch_of_case[i] >= num_batch) return fail(E, SVBFM_ERR_ARG, "svbfm_vb_online_epoch: batch id out of range");
+    if (!E->d_rbatch) {
+        if (dev_alloc(E, &E->d_rbatch, S.n)) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->d_cbatch, S.nnz)) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->d_cnt_col, E->D)) return SVBFM_ERR_OOM;
+    }
+    if (E->batch_cap < num_batch) {
+        cudaFree(E->d_batch_cnt); cudaFree(E->d_batch_n); E->d_batch_cnt = nullptr; E->d_batch_n = nullptr;
+        if (dev_alloc(E, &E->d_batch_cnt, num_batch)) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->d_batch_n, num_batch)) return SVBFM_ERR_OOM;
+        E->batch_cap = num_batch;
+    }
+    uint32_t* d_boc = nullptr;
+    SV_CUDA(E, cudaMalloc((void**)&d_boc, std::max<size_t>(S.n, 1) * 4));
+    SV_CUDA(E, cudaMemcpyAsync(d_boc, batch_of_case, (size_t)S.n * 4, cudaMemcpyHostToDevice, st));
+    SV_CUDA(E, cudaMemsetAsync(E->d_batch_cnt, 0, (size_t)num_batch * 8, st));
+    if (S.n) {
+        k_vbo_set_rbatch<<<nblk(S.n), 256, 0, st>>>(d_boc, S.perm, S.n, E->d_rbatch); LAUNCHED(E);
+        k_vbo_batch_counts<<<nblk(S.n), 256, 0, st>>>(E->d_rbatch, S.n, E->d_batch_cnt); LAUNCHED(E);
+    }
+    if (S.nnz) { k_vbo_set_cbatch<<<nblk(S.nnz), 256, 0, st>>>(S.crow, S.nnz, E->d_rbatch, E->d_cbatch); LAUNCHED(E); }
+    k_u64_to_f64<<<nblk(num_batch), 256, 0, st>>>(E->d_batch_cnt, num_batch, E->d_batch_n); LAUNCHED(E);
+    if (int rc = allreduce_sum_f64(E, E->d_batch_n, num_batch)) return rc;
+    if (int rc = ensure_stats(E, 1)) return rc;
+    SV_CUDA(E, cudaMemsetAsync(E->d_stats, 0, sizeof(DevStats), st));
+    cudaEvent_t t0, t1, t2;
+    cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
+    cudaEventRecord(t0, st);
+    for (uint32_t b = 0; b < num_batch; b++) {
+        k_vbo_batch_begin<<<1, 1, 0, st>>>(E->d_sc, E->d_batch_n, b); LAUNCHED(E);
+        // fresh y-hat, T for the cases of the batch (vbos.h:120-127)
+        if (int rc = predict<PRED_VB_TRAIN>(E, S, E->d_e, 6, 1, (int)b)) return rc;
+        SV_CUDA(E, cudaMemcpyAsync(&E->d_sc->sum_t, RED(E->d_sc, 6), 8, cudaMemcpyDeviceToDevice, st));
+        if (E->cfg.k0) {                                           // update_w0 (vbo.h:356-358)
+            if (int rc = reduce_e(E, (int)b)) return rc;
+            k_vbo_w0<<<1, 1, 0, st>>>(E->d_sc); LAUNCHED(E);
+            k_shift_e<<<SV_RGRID, 256, 0, st>>>(E->d_e, S.n, E->d_sc); LAUNCHED(E);
+        }
+        for (const Run& r : E->runs)                               // update_w; also counts |Omega_j^b| (vbo.h:360-373)
+            if (int rc = sweep_run<KIND_VBO_W>(E, r, -1, (int)b)) return rc;
+        for (int f = 0; f < E->K; f++)                             // update_v (vbo.h:375-408)
+            for (const Run& r : E->runs)
+                if (int rc = sweep_run<KIND_VBO_V>(E, r, f, (int)b)) return rc;
+        if (int rc = reduce_e(E, (int)b)) return rc;
+        k_reduce_dT<<<SV_GGRID, 256, 0, st>>>(E->d_dT, E->D, E->d_red_partial); LAUNCHED(E);
+        k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_GGRID, 1, &E->d_sc->sum_t, 1); LAUNCHED(E);
+        if (int rc = group_sums(E, false)) return rc;
+        int want_fe = (b == 0 || b + 1 == num_batch);              // vbos.h:143-146
+        k_vbo_hyper<<<1, 1, 0, st>>>(E->d_sc, E->d_grp_sums, E->d_n_per_group, E->G, E->K, E->d_hyper_w, E->d_hyper_v, E->d_stats, want_fe, b == 0, 0.5);
+        LAUNCHED(E);
+    }
+    cudaEventRecord(t1, st);
+    if (int rc = predict<PRED_VB_TEST>(E, E->te, nullptr, 3, 1)) return rc;   // vbos.h:190-244
+    k_finish_iter<<<1, 1, 0, st>>>(E->d_sc, E->d_stats, SVBFM_VB_ONLINE); LAUNCHED(E);
+    cudaEventRecord(t2, st);
+    DevStats hs;
+    cudaError_t ce = cudaMemcpyAsync(&hs, E->d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(d_boc);
+    if (ce != cudaSuccess) return fail(E, SVBFM_ERR_CUDA, std::string("vb_online epoch: ") + cudaGetErrorString(ce));
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        out->test_rmse = hs.test_rmse; out->rmse_this = hs.test_rmse; out->train_stat = NAN; out->free_energy = hs.free_energy;
+        out->free_energy_first = hs.pad; out->alpha = hs.alpha; out->has_free_energy = hs.has_fe != 0.0; out->nan_inf_count = (uint32_t)hs.nan_inf;
+        cudaEventElapsedTime(&out->sweep_ms, t0, t1);
+        cudaEventElapsedTime(&out->predict_ms, t1, t2);
+    }
+    cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2);
+    return check_launch(E, "vb_online_epoch");
 }
 
 int svbfm_predict(svbfm_t* h, int32_t split, double* out) {

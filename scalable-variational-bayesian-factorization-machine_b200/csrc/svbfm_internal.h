@@ -114,6 +114,12 @@ struct Engine {
     uint32_t* d_t_w = nullptr;        // [D] t_wj
     uint32_t* d_t_v = nullptr;        // [D] t_vj
     double* d_col_count = nullptr;    // [D] global count of each feature in train
+    uint16_t* d_rbatch = nullptr;     // [n] batch of every case (device order), this epoch
+    uint16_t* d_cbatch = nullptr;     // [nnz] batch of the case of every CSC entry
+    double* d_cnt_col = nullptr;      // [D] batch entries per column (written by the w pass)
+    unsigned long long* d_batch_cnt = nullptr;
+    double* d_batch_n = nullptr;      // [num_batch] global batch sizes
+    uint32_t batch_cap = 0;
     // work buffers
     double* d_e = nullptr;            // [n]
     double* d_partial = nullptr;      // [n_tiles][4]

@@ -97,7 +97,8 @@ struct SweepArgs {
     double* partial;          // [n_tiles][4]
     const double* delta;      // [D]
     uint32_t tile0, ntiles, tile_entries;
-    const uint8_t* in_batch;  // vb_online: 1 when the case belongs to the current batch (null otherwise)
+    const uint16_t* cbatch;   // vb_online: batch id of the case of every CSC entry (null otherwise)
+    uint32_t batch;           // vb_online: current batch
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -115,6 +116,8 @@ __global__ void __launch_bounds__(256) k_sweep_reduce(SweepArgs a) {
     double mu = Pj.x;
     double A = 0.0, B = 0.0, C1 = 0.0, C2 = 0.0;
     for (uint64_t p = b + lane; p < e_; p += 32) {
+        if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V)
+            if (__ldg(&a.cbatch[p]) != a.batch) continue;          // entry belongs to another batch (vbos.h:103-109)
         uint32_t i = __ldg(&a.crow[p]);
         float xf = 1.0f;
         if constexpr (!ONES) xf = __ldg(&a.cval[p]);
@@ -123,6 +126,7 @@ __global__ void __launch_bounds__(256) k_sweep_reduce(SweepArgs a) {
         if constexpr (KIND == KIND_VB_W || KIND == KIND_VBO_W) {
             A += xf * (ei + xf * mu);                              // vb.h:537
             B += xx;                                               // vb.h:538
+            if constexpr (KIND == KIND_VBO_W) C1 += 1.0;           // |Omega_j^b|: batch entries of the column
         } else if constexpr (KIND == KIND_MC_W) {
             A += xf * (ei - mu * xf);                              // mcmc.h:677
             B += xx;
@@ -143,6 +147,7 @@ __global__ void __launch_bounds__(256) k_sweep_reduce(SweepArgs a) {
     }
     A = warp_sum(A); B = warp_sum(B);
     if constexpr (KIND == KIND_VB_V || KIND == KIND_VBO_V) { C1 = warp_sum(C1); C2 = warp_sum(C2); }
+    if constexpr (KIND == KIND_VBO_W) C1 = warp_sum(C1);
     if (lane == 0) {
         double2* out = reinterpret_cast<double2*>(a.partial + (size_t)t * 4);
         out[0] = make_double2(A, B);
@@ -297,13 +302,15 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
 //   eta2 <- mean_n[(1-rho) eta2_old + rho (prior + alpha c_j B_n)] = (1-rho) eta2_old + rho (prior + alpha c_j B/cnt)
 //   eta1 <- (1-rho) eta1_old + rho c_j alpha A/cnt ;  mu = eta1/eta2 ; sigma = 1/eta2
 template <int KIND>
-__global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, const double* __restrict__ cnt_arr, double lamda, uint32_t t0) {
+__global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __restrict__ cnt_arr, double lamda, uint32_t t0, int update_params) {
     uint32_t j = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= a.c1) return;
-    double cnt = cnt_arr[j];
-    if (cnt == 0.0) { a.delta[j] = 0.0; return; }            // empty columns are skipped (vbo.h:367, 394)
     double A, B, C1, C2;
     load_colsum(j, a.col_tile0, a.partial, a.colsum, a.from_colsum, A, B, C1, C2);
+    double cnt;
+    if constexpr (KIND == KIND_VBO_W) { cnt = C1; cnt_arr[j] = cnt; }   // the w pass also counts the batch entries of the column
+    else cnt = cnt_arr[j];
+    if (cnt == 0.0 || !update_params) { a.delta[j] = 0.0; return; }     // empty columns are skipped (vbo.h:367, 394)
     uint32_t g = a.group[j];
     double hy = (a.f < 0) ? a.hyper[g] : a.hyper[(size_t)g * a.K + a.f];
     double alpha = a.sc->alpha;
@@ -344,6 +351,7 @@ __global__ void __launch_bounds__(256) k_sweep_apply(SweepArgs a) {
     uint64_t cend = __ldg(&a.colptr[j + 1]);
     uint64_t e_ = b + a.tile_entries < cend ? b + a.tile_entries : cend;
     for (uint64_t p = b + lane; p < e_; p += 32) {
+        if (a.cbatch && __ldg(&a.cbatch[p]) != a.batch) continue;
         uint32_t i = __ldg(&a.crow[p]);
         float xf = 1.0f;
         if constexpr (!ONES) xf = __ldg(&a.cval[p]);
@@ -366,11 +374,14 @@ struct RowApplyArgs {
     double* e;
     const double2* pf;
     const double* delta;
+    const uint16_t* rbatch;   // vb_online: batch id per case (null otherwise)
+    uint32_t batch;
 };
 
 template <bool IS_V, int FT, bool ONES>
 __global__ void __launch_bounds__(256) k_row_apply(RowApplyArgs a) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+        if (a.rbatch && __ldg(&a.rbatch[i]) != a.batch) continue;
         if constexpr (FT == 2) {
             uint2 c = __ldg(reinterpret_cast<const uint2*>(a.rv.rcol) + i);
             bool in0 = (c.x >= a.c0) & (c.x < a.c1), in1 = (c.y >= a.c0) & (c.y < a.c1);
@@ -421,11 +432,13 @@ __global__ void __launch_bounds__(256) k_row_apply(RowApplyArgs a) {
 #define SV_RGRID 1184   // 148 SMs x 8
 
 // partial[b*3 + {0,1,2}] = sum e, sum e^2, sum clamp(e)^2  (vb.h:513, :451, vbs.h:153-162)
-__global__ void __launch_bounds__(256) k_reduce_e(const double* __restrict__ e, uint32_t n, const Scalars* sc, double* __restrict__ partial) {
+__global__ void __launch_bounds__(256) k_reduce_e(const double* __restrict__ e, uint32_t n, const Scalars* sc, double* __restrict__ partial,
+                                                  const uint16_t* __restrict__ rbatch, uint32_t batch) {
     __shared__ double sm[3 * 32];
     double lo = sc->min_target, hi = sc->max_target;
     double v[3] = {0, 0, 0};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (rbatch && rbatch[i] != batch) continue;
         double x = e[i];
         v[0] += x; v[1] += x * x;
         double p = fmax(lo, fmin(hi, x));
@@ -477,7 +490,8 @@ struct PredictArgs {
     double* pred;         // test: prediction out (vb: clamped)
     double* pred_sum;     // mcmc test: running sum of clamped predictions
     double* partial;      // [grid][4]
-    const uint8_t* in_batch;   // vb_online: restrict to the cases of the current batch
+    const uint16_t* rbatch;    // vb_online: restrict to the cases of the current batch
+    uint32_t batch;
 };
 
 template <int MODE, int FT, bool ONES>
@@ -488,7 +502,7 @@ __global__ void __launch_bounds__(256) k_predict(PredictArgs a) {
     const double lo = a.sc->min_target, hi = a.sc->max_target;
     const double inv_it = 1.0 / (double)(a.sc->iter + 1);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
-        if (MODE == PRED_VB_TRAIN && a.in_batch && !a.in_batch[i]) continue;
+        if (MODE == PRED_VB_TRAIN && a.rbatch && __ldg(&a.rbatch[i]) != a.batch) continue;
         uint64_t b, e_;
         uint32_t c2[2] = {0, 0}; float x2[2] = {1.0f, 1.0f};
         if constexpr (FT == 2) {
@@ -755,6 +769,94 @@ __global__ void k_mcmc_hyper(Scalars* sc, const double* __restrict__ grp, const 
         } else for (size_t i = 0; i < (size_t)G * K; i++) v_mu[i] = mu_0;
     }
     sc->nan_inf += bad;
+}
+
+// ---- vb_online scalars (fm_learn_vb_online.h) ---------------------------------------------------------------
+// start of a batch: batch size (global), fresh sum_t slot
+__global__ void k_vbo_batch_begin(Scalars* sc, const double* __restrict__ batch_n, uint32_t b) {
+    sc->batch_n = batch_n[b];
+    sc->sum_t = 0.0;
+    sc->w0_delta = 0.0;
+}
+
+// update_w0 (vbo.h:471-497). red[0] = sum over the batch of e_i. Every summand of eta2 is the same value and eta1 is
+// linear in e_i, so the reference's per-case averages reduce to the expressions below.
+__global__ void k_vbo_w0(Scalars* sc) {
+    double bs = sc->batch_n, N = sc->n_total, rho = sc->rho_0;
+    if (bs <= 0.0) { sc->w0_delta = 0.0; return; }
+    double mu_dash = sc->w0_mean, sg_dash = sc->w0_var;
+    double eta2 = (1.0 - rho) * sc->nat_sg_0 + rho * (sc->sigma_0 + N * sc->alpha);                     // vbo.h:483
+    double eta1 = (1.0 - rho) * sc->nat_mu_0 + rho * N * sc->alpha * (sc->red[0] / bs + mu_dash);       // vbo.h:484, averaged (:488)
+    sc->nat_mu_0 = eta1; sc->nat_sg_0 = eta2;
+    sc->w0_mean = eta1 / eta2;                                                                          // vbo.h:490
+    sc->w0_var = 1.0 / eta2;                                                                            // vbo.h:491
+    sc->w0_delta = mu_dash - sc->w0_mean;                                                               // vbo.h:494
+    sc->sum_t += bs * (sc->w0_var - sg_dash);                                                           // vbo.h:495 summed
+}
+
+// hyper-parameter blend + (first / last batch) free energy (vbo.h:412-467, 629-664). red[1] = batch sum e^2.
+__global__ void k_vbo_hyper(Scalars* sc, const double* __restrict__ grp, const double* __restrict__ n_per_group, uint32_t G, int K,
+                            double* __restrict__ sigma_w, double* __restrict__ sigma_v, DevStats* st, int want_fe, int first_batch, double lamda) {
+    double bs = sc->batch_n, rho = sc->rho_0;
+    double temp = sc->red[1] + sc->sum_t;
+    double alpha_old = sc->alpha;
+    double alpha = (1.0 - rho) * alpha_old + rho * (bs / temp);                                         // vbo.h:419
+    bool ok = !(isnan(alpha) || isinf(alpha));
+    if (!ok) { sc->nan_inf += 1; alpha = alpha_old; }                                                   // vbo.h:421-434: revert and return
+    sc->alpha = alpha;
+    if (ok) {
+        sc->sigma_0 = (1.0 - rho) * sc->sigma_0 + rho * (1.0 / (sc->w0_mean * sc->w0_mean + sc->w0_var));   // vbo.h:438
+        for (uint32_t g = 0; g < G; g++)
+            sigma_w[g] = (1.0 - rho) * sigma_w[g] + rho * (n_per_group[g] / grp[((size_t)0 * G + g) * 2 + 0]);   // vbo.h:448
+        for (int f = 0; f < K; f++)
+            for (uint32_t g = 0; g < G; g++)
+                sigma_v[(size_t)g * K + f] = (1.0 - rho) * sigma_v[(size_t)g * K + f] + rho * (n_per_group[g] / grp[((size_t)(f + 1) * G + g) * 2 + 0]);   // vbo.h:462
+        sc->t_w0 += 1;                                                                                  // vbo.h:466-467
+        sc->rho_0 = pow((double)(1u + sc->t_w0), -lamda);
+    }
+    if (want_fe) {                                                                                      // vbos.h:143-146 -> vbo.h:629-664
+        double fe = -0.5 * sc->alpha * temp - .5 * bs * log(2 * 3.14 * (1.0 / sc->alpha));
+        fe += -0.5 * sc->sigma_0 * (sc->w0_mean * sc->w0_mean + sc->w0_var) + 0.5 * log(sc->w0_var * sc->sigma_0) + .5;
+        for (uint32_t g = 0; g < G; g++) {
+            double S = grp[((size_t)0 * G + g) * 2 + 0], L = grp[((size_t)0 * G + g) * 2 + 1], ng = n_per_group[g];
+            fe += -0.5 * sigma_w[g] * S + 0.5 * (L + ng * log(sigma_w[g])) + .5 * ng;
+        }
+        for (int f = 0; f < K; f++)
+            for (uint32_t g = 0; g < G; g++) {
+                double S = grp[((size_t)(f + 1) * G + g) * 2 + 0], L = grp[((size_t)(f + 1) * G + g) * 2 + 1], ng = n_per_group[g];
+                double sv = sigma_v[(size_t)g * K + f];
+                fe += -0.5 * sv * S + 0.5 * (L + ng * log(sv)) + .5 * ng;
+            }
+        if (first_batch) st->pad = fe;            // free energy of batch 1 (exported as free_energy_first)
+        st->free_energy = fe; st->has_fe = 1.0;   // batch B overwrites: the epoch's last value
+    }
+    st->alpha = sc->alpha;
+}
+
+// vb_online: batch id of every case in device order, and of the case of every CSC entry
+__global__ void k_vbo_set_rbatch(const uint32_t* __restrict__ batch_of_case, const uint32_t* __restrict__ perm, uint32_t n, uint16_t* __restrict__ rbatch) {
+    uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n) rbatch[d] = (uint16_t)batch_of_case[perm ? perm[d] : d];
+}
+__global__ void k_vbo_set_cbatch(const uint32_t* __restrict__ crow, uint64_t nnz, const uint16_t* __restrict__ rbatch, uint16_t* __restrict__ cbatch) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < nnz) cbatch[p] = rbatch[crow[p]];
+}
+__global__ void k_vbo_batch_counts(const uint16_t* __restrict__ rbatch, uint32_t n, unsigned long long* __restrict__ counts) {
+    uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n) atomicAdd(&counts[rbatch[d]], 1ull);     // integer atomics: order-independent
+}
+__global__ void k_u64_to_f64(const unsigned long long* __restrict__ in, uint32_t n, double* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+__global__ void k_col_counts(const uint64_t* __restrict__ colptr, uint32_t ncols, uint32_t D, double* __restrict__ out) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < D) out[j] = j < ncols ? (double)(colptr[j + 1] - colptr[j]) : 0.0;
+}
+__global__ void k_nat_from_params(const double2* __restrict__ p, size_t n, double2* __restrict__ nat) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { double2 P = p[i]; nat[i] = make_double2(P.x / P.y, 1.0 / P.y); }      // vbo.h:750-765
 }
 
 // end of an iteration: evaluation numbers -> stats slot. red[3] = test sse (this), red[4] = test sse (running mean),

@@ -231,7 +231,7 @@ public:
         open_engine(train, test);
         ck(svbfm_begin(h_), "svbfm_begin");
         truncate_file("test_rmse_" + tag_ + "_vb_online");           // vbos.h:45-52
-        truncate_file("free_energy_" + tag_ + "_vb_online");
+        truncate_file("free_energy_" + tag_ + "_vb_online");         // stays empty: free_energy() appends to the _vb file (vbo.h:637)
         uint32_t n = train.num_cases;
         uint32_t size_except_last = (uint32_t)std::ceil((double)n / num_batch);
         std::vector<uint32_t> shuffle(n), batch(n);
@@ -244,6 +244,11 @@ public:
             svbfm_iter_stats s;
             ck(svbfm_vb_online_epoch(h_, batch.data() + lo, num_batch, &s), "svbfm_vb_online_epoch");
             (void)hi;
+            if (s.has_free_energy) {                                  // batch 1 and batch B of the epoch (vbos.h:143-146)
+                if (num_batch > 1) { append_value("free_energy_" + tag_ + "_vb", -s.free_energy_first); if (root()) std::cout << "free energy " << s.free_energy_first << std::endl; }
+                append_value("free_energy_" + tag_ + "_vb", -s.free_energy);
+                if (root()) std::cout << "free energy " << s.free_energy << std::endl;
+            }
             if (root()) std::cout << "#Iter=" << std::setw(3) << k << "\tTest=" << s.test_rmse << std::endl;     // vbos.h:244
             append_value("test_rmse_" + tag_ + "_vb_online", s.test_rmse);                                  // vbos.h:243
             if (log && root()) {

@@ -107,3 +107,40 @@ def test_mcmc_sampling_distribution(built):
     ref = float(np.mean(orc_vals))
     assert rel(hist[-1].test_rmse, ref) < 0.005 + 2 * (max(orc_vals) - min(orc_vals)) / ref, (hist[-1].test_rmse, orc_vals)
     assert np.isfinite(hist[-1].train_stat) and hist[-1].nan_inf_count == 0
+
+
+def test_vb_online_vs_oracle(built):
+    """vb_online: same libc shuffle stream, batches as case subsets of the resident matrix (no batch files).
+    The oracle is run to completion first: both sides replay the process-global libc rand() stream."""
+    tr, te = two_field(6000, 600, 100, 80, seed=31)
+    want = []
+    orc = ob.Oracle("vb_online", tr, te, K=3, seed=42, num_batch=5)
+    for _ in range(4):
+        s = orc.iterate()
+        want.append((s.test_rmse, s.free_energy, s.alpha))
+    so = orc.get_state()
+    L = make_learner("vb_online", tr, te, 3, num_iter=4, num_batch=5)
+    hist = L.learn(to_csc(tr), to_csc(te))
+    for it, s in enumerate(hist):
+        assert rel(s.test_rmse, want[it][0]) < VB_TOL, (it, s.test_rmse, want[it][0])
+        assert s.has_free_energy and rel(s.free_energy, want[it][1]) < VB_TOL, (it, s.free_energy, want[it][1])
+        assert rel(s.alpha, want[it][2]) < VB_TOL
+    sg = L.engine.get_state()
+    for k in ("w_mean", "w_var", "v_mean", "v_var"):
+        assert np.max(np.abs(so[k] - sg[k])) < 1e-9, k
+
+
+def test_vb_online_ragged_groups(built):
+    tr, te = ragged(2500, 300, 40, seed=41)
+    D = max(tr.n_feat, te.n_feat)
+    groups = (np.arange(D) * 2 // D).astype(np.uint32)
+    want = []
+    orc = ob.Oracle("vb_online", tr, te, K=2, seed=7, num_batch=4, groups=groups)
+    for _ in range(3):
+        s = orc.iterate()
+        want.append((s.test_rmse, s.free_energy))
+    L = make_learner("vb_online", tr, te, 2, seed=7, num_iter=3, num_batch=4, groups=groups)
+    hist = L.learn(to_csc(tr), to_csc(te))
+    for it, s in enumerate(hist):
+        assert rel(s.test_rmse, want[it][0]) < VB_TOL, (it, s.test_rmse, want[it][0])
+        assert rel(s.free_energy, want[it][1]) < VB_TOL
