@@ -108,7 +108,7 @@ static int sweep_run(Engine* E, const Run& r, int f, int batch = -1) {
     double2* pf = IS_V ? E->d_pv + (size_t)f * E->D : E->d_pw;
     SweepArgs a{};
     a.tile_col = E->d_tile_col; a.tile_begin = E->d_tile_begin; a.colptr = S.colptr; a.crow = S.crow; a.cval = S.cval;
-    a.rv = row_view(S); a.e = E->d_e; a.pf = pf; a.partial = E->d_partial; a.delta = E->d_delta;
+    a.rv = row_view(S); a.ov = OtherView{S.cother, S.cother_val}; a.e = E->d_e; a.pf = pf; a.partial = E->d_partial; a.delta = E->d_delta;
     a.tile0 = r.tile_begin; a.ntiles = ntiles; a.tile_entries = E->tile_entries;
     a.cbatch = batch >= 0 ? E->d_cbatch : nullptr; a.batch = batch >= 0 ? (uint32_t)batch : 0u;
     const int pc = IS_V ? 0 : 3;

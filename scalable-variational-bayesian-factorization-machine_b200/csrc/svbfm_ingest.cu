@@ -119,6 +119,24 @@ static __global__ void k_permute_f32(const float* __restrict__ src, const uint32
     if (d < n) dst[d] = src[perm[d]];
 }
 
+// F == 2: the other entry of the case of every CSC entry (entry-aligned, streamed by the sweeps)
+static __global__ void k_other_of_entry(const uint64_t* __restrict__ colptr, uint32_t ncols, uint64_t nnz, const uint32_t* __restrict__ crow,
+                                        const uint32_t* __restrict__ rcol, const float* __restrict__ rval, uint32_t* __restrict__ ocol,
+                                        float* __restrict__ oval) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    uint32_t lo = 0, hi = ncols;
+    while (hi - lo > 1) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (colptr[mid] <= p) lo = mid; else hi = mid;
+    }
+    uint32_t i = crow[p];
+    uint2 c = reinterpret_cast<const uint2*>(rcol)[i];
+    bool first = (c.x == lo);
+    ocol[p] = first ? c.y : c.x;
+    if (oval) { float2 x = reinterpret_cast<const float2*>(rval)[i]; oval[p] = first ? x.y : x.x; }
+}
+
 static inline unsigned nblk(uint64_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t); }
 
 static int bits_for(uint64_t n) {
@@ -148,7 +166,7 @@ static int sort_pairs(Engine* E, const uint32_t* keys_in, const uint32_t* vals_i
 void free_split(Engine* E, DevSplit& S) {
     (void)E;
     cudaFree(S.colptr); cudaFree(S.crow); cudaFree(S.cval); cudaFree(S.rowptr); cudaFree(S.rcol); cudaFree(S.rval);
-    cudaFree(S.y); cudaFree(S.perm);
+    cudaFree(S.y); cudaFree(S.perm); cudaFree(S.cother); cudaFree(S.cother_val);
     S = DevSplit();
 }
 
@@ -318,6 +336,12 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     S.uniformF = F;
     if (F > 0) { cudaFree(d_rowptr); S.rowptr = nullptr; } else { S.rowptr = d_rowptr; E->dev_bytes += ((size_t)n + 1) * 8; }
 
+    if (is_train && F == 2 && nnz) {
+        if (dev_alloc(E, &S.cother, nnz)) return SVBFM_ERR_OOM;
+        if (!S.all_ones && dev_alloc(E, &S.cother_val, nnz)) return SVBFM_ERR_OOM;
+        k_other_of_entry<<<nblk(nnz), 256, 0, st>>>(S.colptr, ncols, nnz, S.crow, S.rcol, S.rval, S.cother, S.cother_val);
+        SV_CUDA(E, cudaStreamSynchronize(st));
+    }
     if (is_train) {
         // ---- warp tiles + heavy columns (host, O(#columns))
         uint32_t T = E->tile_entries;

@@ -30,6 +30,8 @@ struct DevSplit {
     uint64_t* rowptr = nullptr;   // [n+1] or null when uniformF > 0
     uint32_t* rcol = nullptr;     // [nnz] feature ids, ascending inside each case
     float* rval = nullptr;        // [nnz] or null when all_ones
+    uint32_t* cother = nullptr;   // [nnz] F == 2 (train): feature id of the case's other entry, aligned with the CSC entries
+    float* cother_val = nullptr;  // [nnz] its x (null when all_ones)
     uint32_t uniformF = 0;
     bool all_ones = false;
     float* y = nullptr;           // [n] device order

@@ -47,21 +47,23 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /*[NV*32
 // ---------------------------------------------------------------------------------------------------------
 // "other fields of case i": h = sum_{c != j} mu_c x_c ; h1 = sum sigma_c x_c^2 ; h2 = sum mu_c^2 x_c^2
 // (= q_i - x mu_j, S2_i - x^2 sigma_j, S3_i - x^2 mu_j^2 of fm_learn_vb.h:592-593, 628-630)
+struct OtherView {            // F == 2 only: for every CSC entry, the feature id (and x) of the case's OTHER entry,
+    const uint32_t* col;      // stored entry-aligned so that the sweep streams it instead of gathering the CSR row
+    const float* val;
+};
+
 template <int FT, bool ONES, bool VAR>
-__device__ __forceinline__ void others(const RowView& rv, const double2* __restrict__ pf, uint32_t i, uint32_t j,
+__device__ __forceinline__ void others(const RowView& rv, const OtherView& ov, const double2* __restrict__ pf, uint64_t p, uint32_t i, uint32_t j,
                                        double& h, double& h1, double& h2) {
     h = 0.0; h1 = 0.0; h2 = 0.0;
     if constexpr (FT == 2) {
-        uint2 c = __ldg(reinterpret_cast<const uint2*>(rv.rcol) + i);
-        bool first = (c.x == j);
-        uint32_t o = first ? c.y : c.x;
+        uint32_t o = __ldcs(&ov.col[p]);
         double2 P = __ldg(&pf[o]);
         if constexpr (ONES) {
             h = P.x;
             if constexpr (VAR) { h1 = P.y; h2 = P.x * P.x; }
         } else {
-            float2 xv = __ldg(reinterpret_cast<const float2*>(rv.rval) + i);
-            float x = first ? xv.y : xv.x;
+            float x = __ldcs(&ov.val[p]);
             h = P.x * x;
             if constexpr (VAR) { h1 = P.y * x * x; h2 = P.x * P.x * x * x; }
         }
@@ -92,6 +94,7 @@ struct SweepArgs {
     const uint32_t* crow;
     const float* cval;
     RowView rv;
+    OtherView ov;
     double* e;
     const double2* pf;        // params of this factor ([D]) or the w params
     double* partial;          // [n_tiles][4]
@@ -115,34 +118,50 @@ __global__ void __launch_bounds__(256) k_sweep_reduce(SweepArgs a) {
     double2 Pj = __ldg(&a.pf[j]);
     double mu = Pj.x;
     double A = 0.0, B = 0.0, C1 = 0.0, C2 = 0.0;
-    for (uint64_t p = b + lane; p < e_; p += 32) {
-        if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V)
-            if (__ldg(&a.cbatch[p]) != a.batch) continue;          // entry belongs to another batch (vbos.h:103-109)
-        uint32_t i = __ldg(&a.crow[p]);
-        float xf = 1.0f;
-        if constexpr (!ONES) xf = __ldg(&a.cval[p]);
-        double ei = a.e[i];
-        double xx = (double)(xf * xf);     // the reference forms x*x in float (FM_FLOAT), then promotes
-        if constexpr (KIND == KIND_VB_W || KIND == KIND_VBO_W) {
-            A += xf * (ei + xf * mu);                              // vb.h:537
-            B += xx;                                               // vb.h:538
-            if constexpr (KIND == KIND_VBO_W) C1 += 1.0;           // |Omega_j^b|: batch entries of the column
-        } else if constexpr (KIND == KIND_MC_W) {
-            A += xf * (ei - mu * xf);                              // mcmc.h:677
-            B += xx;
-        } else if constexpr (KIND == KIND_VB_V || KIND == KIND_VBO_V) {
-            double h, h1, h2;
-            others<FT, ONES, true>(a.rv, a.pf, i, j, h, h1, h2);
-            A += xf * h * (ei + xf * mu * h);                      // vb.h:594
-            B += xx * h * h + xx * h1;                             // vb.h:595
-            C1 += xx * h1;                                         // sum of pass-2 h1 (vb.h:629)
-            C2 += xx * h2;                                         // sum of pass-2 h2 (vb.h:630)
-        } else {                                                   // KIND_MC_V
-            double h, h1, h2;
-            others<FT, ONES, false>(a.rv, a.pf, i, j, h, h1, h2);
-            double hh = xf * h;                                    // mcmc.h:789
-            A += hh * ei;                                          // mcmc.h:790
-            B += hh * hh;                                          // mcmc.h:791
+    constexpr int U = 4;                     // entries per lane in flight: the loads of a batch are issued back to back
+    for (uint64_t p0 = b + lane; p0 < e_; p0 += 32 * U) {
+        bool ok[U]; uint32_t ci[U]; float xs[U]; double es[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            uint64_t p = p0 + (uint64_t)u * 32;
+            ok[u] = p < e_;
+            if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V)
+                if (ok[u]) ok[u] = (__ldcs(&a.cbatch[p]) == a.batch);   // entry of another batch (vbos.h:103-109)
+            ci[u] = ok[u] ? __ldcs(&a.crow[p]) : 0u;
+            xs[u] = 1.0f;
+            if constexpr (!ONES) if (ok[u]) xs[u] = __ldcs(&a.cval[p]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) es[u] = ok[u] ? a.e[ci[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!ok[u]) continue;
+            uint64_t p = p0 + (uint64_t)u * 32;
+            uint32_t i = ci[u];
+            float xf = xs[u];
+            double ei = es[u];
+            double xx = (double)(xf * xf);     // the reference forms x*x in float (FM_FLOAT), then promotes
+            if constexpr (KIND == KIND_VB_W || KIND == KIND_VBO_W) {
+                A += xf * (ei + xf * mu);                              // vb.h:537
+                B += xx;                                               // vb.h:538
+                if constexpr (KIND == KIND_VBO_W) C1 += 1.0;           // |Omega_j^b|: batch entries of the column
+            } else if constexpr (KIND == KIND_MC_W) {
+                A += xf * (ei - mu * xf);                              // mcmc.h:677
+                B += xx;
+            } else if constexpr (KIND == KIND_VB_V || KIND == KIND_VBO_V) {
+                double h, h1, h2;
+                others<FT, ONES, true>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
+                A += xf * h * (ei + xf * mu * h);                      // vb.h:594
+                B += xx * h * h + xx * h1;                             // vb.h:595
+                C1 += xx * h1;                                         // sum of pass-2 h1 (vb.h:629)
+                C2 += xx * h2;                                         // sum of pass-2 h2 (vb.h:630)
+            } else {                                                   // KIND_MC_V
+                double h, h1, h2;
+                others<FT, ONES, false>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
+                double hh = xf * h;                                    // mcmc.h:789
+                A += hh * ei;                                          // mcmc.h:790
+                B += hh * hh;                                          // mcmc.h:791
+            }
         }
     }
     A = warp_sum(A); B = warp_sum(B);
@@ -358,7 +377,7 @@ __global__ void __launch_bounds__(256) k_sweep_apply(SweepArgs a) {
         double hh = xf;
         if constexpr (IS_V) {
             double h, h1, h2;
-            others<FT, ONES, false>(a.rv, a.pf, i, j, h, h1, h2);
+            others<FT, ONES, false>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
             hh = xf * h;
         }
         a.e[i] += hh * d;
