@@ -205,20 +205,20 @@ def main():
                  v_var=np.full((K, D), 0.02))
     torch.cuda.empty_cache()
 
-    uid = None
-    if world > 1:
+    def new_uid():
+        """A fresh NCCL unique id per communicator: rank 0 asks the library, torch.distributed broadcasts the bytes."""
         idt = torch.zeros(sv.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
         if rank == 0:
             buf = (sv.C.c_uint8 * sv.COMM_ID_BYTES)()
             assert sv.lib().svbfm_comm_get_unique_id(buf) == 0
             idt.copy_(torch.tensor(list(buf), dtype=torch.uint8))
         dist.broadcast(idt, 0)
-        uid = bytes(idt.cpu().tolist())
+        return bytes(idt.cpu().tolist())
 
     def make_engine():
         E = sv.Engine(a.method, D, K, 1, 1, ymin, ymax, device=local, seed=42)
         if world > 1:
-            E.comm_init(uid, rank, world)
+            E.comm_init(new_uid(), rank, world)
         E.set_csc(sv.TRAIN, train)
         E.set_csc(sv.TEST, test)
         E.set_state(state)
