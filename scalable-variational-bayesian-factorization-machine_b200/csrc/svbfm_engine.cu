@@ -107,7 +107,7 @@ static int sweep_run(Engine* E, const Run& r, int f, int batch = -1) {
     constexpr bool IS_V = (KIND == KIND_VB_V || KIND == KIND_MC_V || KIND == KIND_VBO_V);
     double2* pf = IS_V ? E->d_pv + (size_t)f * E->D : E->d_pw;
     SweepArgs a{};
-    a.tile_col = E->d_tile_col; a.tile_begin = E->d_tile_begin; a.colptr = S.colptr; a.crow = S.crow; a.cval = S.cval;
+    a.tile_col = E->d_tile_col; a.tile_begin = E->d_tile_begin; a.tile_len = E->d_tile_len; a.exec_order = E->d_exec_order; a.colptr = S.colptr; a.crow = S.crow; a.cval = S.cval;
     a.rv = row_view(S); a.ov = OtherView{S.cother, S.cother_val}; a.e = E->d_e; a.pf = pf; a.partial = E->d_partial; a.delta = E->d_delta;
     a.tile0 = r.tile_begin; a.ntiles = ntiles; a.tile_entries = E->tile_entries;
     a.cbatch = batch >= 0 ? E->d_cbatch : nullptr; a.batch = batch >= 0 ? (uint32_t)batch : 0u;
@@ -404,7 +404,7 @@ void svbfm_destroy(svbfm_t* h) {
     cudaStreamSynchronize(E->stream);
     if (E->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(E->nccl_comm);
     free_split(E, E->tr); free_split(E, E->te);
-    void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
+    void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
                     E->d_pred_sum, E->d_stats, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};

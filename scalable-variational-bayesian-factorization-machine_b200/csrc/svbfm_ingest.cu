@@ -137,6 +137,21 @@ static __global__ void k_other_of_entry(const uint64_t* __restrict__ colptr, uin
     if (oval) { float2 x = reinterpret_cast<const float2*>(rval)[i]; oval[p] = first ? x.y : x.x; }
 }
 
+// cuts[c][k] = first entry of column cols[c] whose case id is >= k * block_cases  (k = 0..NB)
+static __global__ void k_block_cuts(const uint32_t* __restrict__ cols, const uint64_t* __restrict__ colptr, const uint32_t* __restrict__ crow,
+                                    uint32_t block_cases, uint32_t NB, uint64_t* __restrict__ cuts) {
+    uint32_t c = blockIdx.x, k = blockIdx.y * blockDim.x + threadIdx.x;
+    if (k > NB) return;
+    uint32_t j = cols[c];
+    uint64_t lo = colptr[j], hi = colptr[j + 1];
+    uint64_t key = (uint64_t)k * block_cases;
+    while (lo < hi) {
+        uint64_t mid = lo + (hi - lo) / 2;
+        if ((uint64_t)crow[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    cuts[(size_t)c * (NB + 1) + k] = lo;
+}
+
 static inline unsigned nblk(uint64_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t); }
 
 static int bits_for(uint64_t n) {
@@ -343,34 +358,87 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         SV_CUDA(E, cudaStreamSynchronize(st));
     }
     if (is_train) {
-        // ---- warp tiles + heavy columns (host, O(#columns))
+        // ---- warp tiles (host). A tile = <= T consecutive CSC entries of ONE column; a column's tiles are consecutive
+        // tile ids (fixed summation order). Runs whose case ids are not sequential ("gather runs") read e_i at random:
+        // every miss moves a 128 B HBM line for 8 useful bytes (profiles/r01_v2_*). For their big columns the entry list
+        // is cut at case-block boundaries (blocks of `block_cases` cases, e-block sized for L2) and the tiles are EXECUTED
+        // block-major (exec_order), so that the warps in flight gather from one L2-resident block of e.
         uint32_t T = E->tile_entries;
-        std::vector<uint32_t> tile_col, col_tile0((size_t)S.ncols_ext + 1), heavy;
+        uint32_t block_cases = 4u << 20;
+        if (const char* sb = getenv("SVBFM_BLOCK_CASES")) block_cases = (uint32_t)atol(sb);
+        uint32_t NB = (block_cases && n) ? (uint32_t)(((uint64_t)n + block_cases - 1) / block_cases) : 1;
+        std::vector<uint32_t> tile_col, tile_len, col_tile0((size_t)S.ncols_ext + 1), heavy, exec_order, tile_block;
         std::vector<uint64_t> tile_begin;
+        // columns to cut: gather runs only, and only when there is more than one block
+        std::vector<uint32_t> cut_cols;
+        for (size_t ri = 0; ri < E->runs.size(); ri++) {
+            const Run& r = E->runs[ri];
+            bool sequential = (ri == 0 && E->rows_reordered);
+            if (sequential || NB <= 1) continue;
+            for (uint32_t j = r.col_begin; j < r.col_end; j++)
+                if (S.h_colptr[j + 1] - S.h_colptr[j] >= (uint64_t)16 * NB) cut_cols.push_back(j);
+        }
+        std::vector<uint64_t> cuts;   // [cut_cols][NB+1] absolute entry positions
+        if (!cut_cols.empty()) {
+            uint32_t* d_cc = nullptr; uint64_t* d_cuts = nullptr;
+            SV_CUDA(E, cudaMalloc((void**)&d_cc, cut_cols.size() * 4));
+            SV_CUDA(E, cudaMalloc((void**)&d_cuts, cut_cols.size() * (size_t)(NB + 1) * 8));
+            SV_CUDA(E, cudaMemcpyAsync(d_cc, cut_cols.data(), cut_cols.size() * 4, cudaMemcpyHostToDevice, st));
+            dim3 grid((unsigned)cut_cols.size(), (NB + 1 + 63) / 64);
+            k_block_cuts<<<grid, 64, 0, st>>>(d_cc, S.colptr, S.crow, block_cases, NB, d_cuts);
+            cuts.resize(cut_cols.size() * (size_t)(NB + 1));
+            SV_CUDA(E, cudaMemcpyAsync(cuts.data(), d_cuts, cuts.size() * 8, cudaMemcpyDeviceToHost, st));
+            SV_CUDA(E, cudaStreamSynchronize(st));
+            cudaFree(d_cc); cudaFree(d_cuts);
+        }
+        size_t cc = 0;
         for (auto& r : E->runs) {
             r.tile_begin = (uint32_t)tile_col.size();
             r.heavy_begin = (uint32_t)heavy.size();
             for (uint32_t j = r.col_begin; j < r.col_end; j++) {
                 col_tile0[j] = (uint32_t)tile_col.size();
                 uint64_t b = S.h_colptr[j], e = S.h_colptr[j + 1];
-                uint64_t nt = (e - b + T - 1) / T;
-                for (uint64_t p = b; p < e; p += T) { tile_col.push_back(j); tile_begin.push_back(p); }
-                if (nt > 8) heavy.push_back(j);
+                if (cc < cut_cols.size() && cut_cols[cc] == j) {
+                    const uint64_t* cp = &cuts[cc * (size_t)(NB + 1)];
+                    for (uint32_t k = 0; k < NB; k++)
+                        for (uint64_t p = cp[k]; p < cp[k + 1]; p += T) {
+                            tile_col.push_back(j); tile_begin.push_back(p); tile_len.push_back((uint32_t)std::min<uint64_t>(T, cp[k + 1] - p));
+                            tile_block.push_back(k);
+                        }
+                    cc++;
+                } else {
+                    for (uint64_t p = b; p < e; p += T) {
+                        tile_col.push_back(j); tile_begin.push_back(p); tile_len.push_back((uint32_t)std::min<uint64_t>(T, e - p));
+                        tile_block.push_back(NB);   // not cut: executed after the block-major part, in column order
+                    }
+                }
+                if (tile_col.size() - col_tile0[j] > 8) heavy.push_back(j);
             }
             r.tile_end = (uint32_t)tile_col.size();
             r.heavy_end = (uint32_t)heavy.size();
+            // execution order of this run: stable by block id
+            std::vector<uint32_t> ord(r.tile_end - r.tile_begin);
+            for (uint32_t t = 0; t < ord.size(); t++) ord[t] = r.tile_begin + t;
+            std::stable_sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) { return tile_block[x] < tile_block[y]; });
+            exec_order.insert(exec_order.end(), ord.begin(), ord.end());
         }
         col_tile0[S.ncols_ext] = (uint32_t)tile_col.size();
         E->n_tiles = (uint32_t)tile_col.size();
         E->n_heavy = (uint32_t)heavy.size();
         cudaFree(E->d_tile_col); cudaFree(E->d_tile_begin); cudaFree(E->d_col_tile0); cudaFree(E->d_heavy_cols);
+        cudaFree(E->d_tile_len); cudaFree(E->d_exec_order);
         E->d_tile_col = nullptr; E->d_tile_begin = nullptr; E->d_col_tile0 = nullptr; E->d_heavy_cols = nullptr;
+        E->d_tile_len = nullptr; E->d_exec_order = nullptr;
         if (dev_alloc(E, &E->d_tile_col, tile_col.size())) return SVBFM_ERR_OOM;
         if (dev_alloc(E, &E->d_tile_begin, tile_begin.size())) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->d_tile_len, tile_len.size())) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->d_exec_order, exec_order.size())) return SVBFM_ERR_OOM;
         if (dev_alloc(E, &E->d_col_tile0, col_tile0.size())) return SVBFM_ERR_OOM;
         if (dev_alloc(E, &E->d_heavy_cols, heavy.size())) return SVBFM_ERR_OOM;
         SV_CUDA(E, cudaMemcpyAsync(E->d_tile_col, tile_col.data(), tile_col.size() * 4, cudaMemcpyHostToDevice, st));
         SV_CUDA(E, cudaMemcpyAsync(E->d_tile_begin, tile_begin.data(), tile_begin.size() * 8, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemcpyAsync(E->d_tile_len, tile_len.data(), tile_len.size() * 4, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemcpyAsync(E->d_exec_order, exec_order.data(), exec_order.size() * 4, cudaMemcpyHostToDevice, st));
         SV_CUDA(E, cudaMemcpyAsync(E->d_col_tile0, col_tile0.data(), col_tile0.size() * 4, cudaMemcpyHostToDevice, st));
         SV_CUDA(E, cudaMemcpyAsync(E->d_heavy_cols, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice, st));
         SV_CUDA(E, cudaStreamSynchronize(st));

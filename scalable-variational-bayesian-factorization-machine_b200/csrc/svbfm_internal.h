@@ -97,6 +97,8 @@ struct Engine {
     std::vector<Run> runs;
     uint32_t* d_tile_col = nullptr;
     uint64_t* d_tile_begin = nullptr;
+    uint32_t* d_tile_len = nullptr;
+    uint32_t* d_exec_order = nullptr;  // per run: tile ids in execution order (block-major for cut columns)
     uint32_t* d_col_tile0 = nullptr;   // [ncols_ext+1] first tile of each column
     uint32_t* d_heavy_cols = nullptr;
     uint32_t n_tiles = 0, n_heavy = 0, tile_entries = 1024;

@@ -90,6 +90,8 @@ __device__ __forceinline__ void others(const RowView& rv, const OtherView& ov, c
 struct SweepArgs {
     const uint32_t* tile_col;
     const uint64_t* tile_begin;
+    const uint32_t* tile_len;
+    const uint32_t* exec_order;   // [tile0 + w] -> tile id executed by warp w of the launch
     const uint64_t* colptr;
     const uint32_t* crow;
     const float* cval;
@@ -110,11 +112,10 @@ template <int KIND, int FT, bool ONES>
 __global__ void __launch_bounds__(256) k_sweep_reduce(SweepArgs a) {
     uint32_t w = (blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5);
     if (w >= a.ntiles) return;
-    uint32_t t = a.tile0 + w, lane = threadIdx.x & 31;
+    uint32_t t = __ldg(&a.exec_order[a.tile0 + w]), lane = threadIdx.x & 31;
     uint32_t j = __ldg(&a.tile_col[t]);
     uint64_t b = __ldg(&a.tile_begin[t]);
-    uint64_t cend = __ldg(&a.colptr[j + 1]);
-    uint64_t e_ = b + a.tile_entries < cend ? b + a.tile_entries : cend;
+    uint64_t e_ = b + __ldg(&a.tile_len[t]);
     double2 Pj = __ldg(&a.pf[j]);
     double mu = Pj.x;
     double A = 0.0, B = 0.0, C1 = 0.0, C2 = 0.0;
@@ -362,13 +363,12 @@ template <bool IS_V, int FT, bool ONES>
 __global__ void __launch_bounds__(256) k_sweep_apply(SweepArgs a) {
     uint32_t w = (blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5);
     if (w >= a.ntiles) return;
-    uint32_t t = a.tile0 + w, lane = threadIdx.x & 31;
+    uint32_t t = __ldg(&a.exec_order[a.tile0 + w]), lane = threadIdx.x & 31;
     uint32_t j = __ldg(&a.tile_col[t]);
     double d = __ldg(&a.delta[j]);
     if (d == 0.0) return;
     uint64_t b = __ldg(&a.tile_begin[t]);
-    uint64_t cend = __ldg(&a.colptr[j + 1]);
-    uint64_t e_ = b + a.tile_entries < cend ? b + a.tile_entries : cend;
+    uint64_t e_ = b + __ldg(&a.tile_len[t]);
     for (uint64_t p = b + lane; p < e_; p += 32) {
         if (a.cbatch && __ldg(&a.cbatch[p]) != a.batch) continue;
         uint32_t i = __ldg(&a.crow[p]);

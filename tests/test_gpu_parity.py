@@ -144,3 +144,15 @@ def test_vb_online_ragged_groups(built):
     for it, s in enumerate(hist):
         assert rel(s.test_rmse, want[it][0]) < VB_TOL, (it, s.test_rmse, want[it][0])
         assert rel(s.free_energy, want[it][1]) < VB_TOL
+
+
+def test_vb_block_cut_tiles(built, monkeypatch):
+    """Big columns of gather runs are cut at case-block boundaries and executed block-major (L2 blocking):
+    only the schedule changes, the sums per column keep their tile order."""
+    monkeypatch.setenv("SVBFM_BLOCK_CASES", "1000")
+    tr, te = two_field(20000, 2000, 300, 200, seed=61)
+    L, _ = run_vb(tr, te, K=3, iters=4, tile_entries=64)
+    assert L.engine.info()["num_tiles"] > 700
+    monkeypatch.setenv("SVBFM_BLOCK_CASES", "700")
+    tr, te = ragged(6000, 300, 30, seed=62)
+    run_vb(tr, te, K=2, iters=3, tile_entries=32)
