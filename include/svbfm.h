@@ -148,6 +148,8 @@ typedef struct svbfm_info {
     uint64_t train_nnz;
     uint32_t rows_reordered;
     uint32_t world_size;
+    uint32_t fused_schedule;   /* 1 when the two-field fused schedule (pass 2 folded into the next pass 1) is in use */
+    uint32_t reserved;
 } svbfm_info;
 int svbfm_get_info(svbfm_t* h, svbfm_info* out);
 /* per-kernel-class device time (CUDA events on the launching stream), for bench.py's roofline block.

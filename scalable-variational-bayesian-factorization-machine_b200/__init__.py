@@ -50,7 +50,8 @@ class IterStats(C.Structure):
 class Info(C.Structure):
     _fields_ = [("num_runs", C.c_uint32), ("num_tiles", C.c_uint32), ("uniform_row_nnz", C.c_uint32),
                 ("all_ones", C.c_uint32), ("kernel_launches", C.c_uint64), ("device_bytes", C.c_uint64),
-                ("train_nnz", C.c_uint64), ("rows_reordered", C.c_uint32), ("world_size", C.c_uint32)]
+                ("train_nnz", C.c_uint64), ("rows_reordered", C.c_uint32), ("world_size", C.c_uint32),
+                ("fused_schedule", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 # every symbol include/svbfm.h declares (tests/test_abi.py checks the library exports exactly these)

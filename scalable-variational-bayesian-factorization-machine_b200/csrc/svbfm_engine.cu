@@ -98,6 +98,43 @@ struct ProfScope {
     }
 };
 
+// tiles -> column sums (-> allreduce when sharded) -> per-column update
+template <int KIND>
+static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1) {
+    cudaStream_t st = E->stream;
+    constexpr bool IS_V = (KIND == KIND_VB_V || KIND == KIND_MC_V || KIND == KIND_VBO_V);
+    double2* pf = IS_V ? E->d_pv + (size_t)f * E->D : E->d_pw;
+    (void)batch;
+    ProfScope ps(E, (IS_V ? 0 : 3) + 1);
+    uint32_t nheavy = r.heavy_end - r.heavy_begin;
+    if (nheavy) { k_combine_heavy<<<nheavy, 128, 0, st>>>(E->d_heavy_cols, r.heavy_begin, E->d_col_tile0, E->d_partial, E->d_colsum); LAUNCHED(E); }
+    uint32_t ncols = r.col_end - r.col_begin;
+    bool from_colsum = false;
+    if (E->world > 1) {
+        k_combine_light<<<nblk(ncols), 256, 0, st>>>(r.col_begin, r.col_end, E->d_col_tile0, E->d_partial, E->d_colsum); LAUNCHED(E);
+        if (int rc = allreduce_sum_f64(E, E->d_colsum + (size_t)r.col_begin * 4, (size_t)ncols * 4)) return rc;
+        from_colsum = true;
+    }
+    FinalizeArgs fa{};
+    fa.c0 = r.col_begin; fa.c1 = r.col_end; fa.f = IS_V ? f : -1; fa.K = E->K;
+    fa.col_tile0 = E->d_col_tile0; fa.partial = E->d_partial; fa.colsum = E->d_colsum; fa.from_colsum = from_colsum;
+    fa.pf = pf; fa.group = E->d_group; fa.hyper = IS_V ? E->d_hyper_v : E->d_hyper_w;
+    fa.hyper_mu = IS_V ? E->d_mu_v : E->d_mu_w; fa.sc = E->d_sc; fa.delta = E->d_delta; fa.mu_prev = E->d_mu_prev; fa.dT = E->d_dT;
+    fa.seed = E->cfg.seed; fa.do_sample = E->cfg.do_sample;
+    if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V) {
+        fa.nat = IS_V ? E->d_nat_v + (size_t)f * E->D : E->d_nat_w;
+        fa.t_cnt = IS_V ? E->d_t_v : E->d_t_w;
+        fa.col_count = E->d_col_count;
+        fa.update_t = IS_V ? (f == E->K - 1) : 1;      // t_vj advances once per batch (vbo.h:399-402), t_wj per w update (:520)
+        int update_params = IS_V ? 1 : (E->cfg.k1 != 0);   // with k1 = 0 the w pass only counts the batch entries per column
+        k_finalize_vbo<KIND><<<nblk(ncols), 256, 0, st>>>(fa, E->d_cnt_col, 0.5, 1u, update_params);
+    } else {
+        k_finalize<KIND><<<nblk(ncols), 256, 0, st>>>(fa);
+    }
+    LAUNCHED(E);
+    return check_launch(E, "combine_finalize");
+}
+
 // ---------------------------------------------------------------------------------------------- one run sweep
 template <int KIND>
 static int sweep_run(Engine* E, const Run& r, int f, int batch = -1) {
@@ -125,35 +162,7 @@ static int sweep_run(Engine* E, const Run& r, int f, int batch = -1) {
         }
         LAUNCHED(E);
     }
-    uint32_t nheavy = r.heavy_end - r.heavy_begin;
-    {
-    ProfScope ps(E, pc + 1);
-    if (nheavy) { k_combine_heavy<<<nheavy, 128, 0, st>>>(E->d_heavy_cols, r.heavy_begin, E->d_col_tile0, E->d_partial, E->d_colsum); LAUNCHED(E); }
-    uint32_t ncols = r.col_end - r.col_begin;
-    bool from_colsum = false;
-    if (E->world > 1) {
-        k_combine_light<<<nblk(ncols), 256, 0, st>>>(r.col_begin, r.col_end, E->d_col_tile0, E->d_partial, E->d_colsum); LAUNCHED(E);
-        if (int rc = allreduce_sum_f64(E, E->d_colsum + (size_t)r.col_begin * 4, (size_t)ncols * 4)) return rc;
-        from_colsum = true;
-    }
-    FinalizeArgs fa{};
-    fa.c0 = r.col_begin; fa.c1 = r.col_end; fa.f = IS_V ? f : -1; fa.K = E->K;
-    fa.col_tile0 = E->d_col_tile0; fa.partial = E->d_partial; fa.colsum = E->d_colsum; fa.from_colsum = from_colsum;
-    fa.pf = pf; fa.group = E->d_group; fa.hyper = IS_V ? E->d_hyper_v : E->d_hyper_w;
-    fa.hyper_mu = IS_V ? E->d_mu_v : E->d_mu_w; fa.sc = E->d_sc; fa.delta = E->d_delta; fa.dT = E->d_dT;
-    fa.seed = E->cfg.seed; fa.do_sample = E->cfg.do_sample;
-    if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V) {
-        fa.nat = IS_V ? E->d_nat_v + (size_t)f * E->D : E->d_nat_w;
-        fa.t_cnt = IS_V ? E->d_t_v : E->d_t_w;
-        fa.col_count = E->d_col_count;
-        fa.update_t = IS_V ? (f == E->K - 1) : 1;      // t_vj advances once per batch (vbo.h:399-402), t_wj per w update (:520)
-        int update_params = IS_V ? 1 : (E->cfg.k1 != 0);   // with k1 = 0 the w pass only counts the batch entries per column
-        k_finalize_vbo<KIND><<<nblk(ncols), 256, 0, st>>>(fa, E->d_cnt_col, 0.5, 1u, update_params);
-    } else {
-        k_finalize<KIND><<<nblk(ncols), 256, 0, st>>>(fa);
-    }
-    LAUNCHED(E);
-    }
+    if (int rc = combine_finalize<KIND>(E, r, f, batch)) return rc;
     if (ntiles && r.nnz * 4 >= (uint64_t)S.n) {
         // run touches a large share of the cases: streaming pass in case order
         ProfScope ps(E, pc + 2);
@@ -179,6 +188,58 @@ static int sweep_run(Engine* E, const Run& r, int f, int batch = -1) {
         LAUNCHED(E);
     }
     return check_launch(E, "sweep_run");
+}
+
+// Fused schedule (two complete one-hot fields, device case order = run 0): see k_fused_stream.
+static bool fused_ok(const Engine* E) {
+    const DevSplit& S = E->tr;
+    return !getenv("SVBFM_NO_FUSE") && E->cfg.method != SVBFM_VB_ONLINE && E->runs.size() == 2 && S.uniformF == 2 && E->rows_reordered &&
+           E->runs[0].nnz == S.n && E->runs[1].nnz == S.n && S.cother && E->d_mu_prev && E->K > 0;
+}
+
+template <int KIND, bool REDUCE>
+static void launch_fused(Engine* E, int f, bool pending) {
+    const DevSplit& S = E->tr;
+    const Run& r0 = E->runs[0];
+    FusedArgs a{};
+    a.tile_col = E->d_tile_col; a.tile_begin = E->d_tile_begin; a.tile_len = E->d_tile_len; a.exec_order = E->d_exec_order;
+    a.tile0 = r0.tile_begin; a.ntiles = r0.tile_end - r0.tile_begin; a.entry0 = S.h_colptr[r0.col_begin];
+    a.cval = S.cval; a.ov = OtherView{S.cother, S.cother_val}; a.e = E->d_e;
+    a.pf = REDUCE ? E->d_pv + (size_t)f * E->D : nullptr;
+    a.pf_prev = pending ? E->d_pv + (size_t)(f - 1) * E->D : nullptr;
+    a.delta = E->d_delta; a.mu_prev = E->d_mu_prev; a.partial = E->d_partial;
+    unsigned grid = (a.ntiles + 7) / 8;
+    if (S.all_ones) k_fused_stream<KIND, true, REDUCE><<<grid, 256, 0, E->stream>>>(a);
+    else k_fused_stream<KIND, false, REDUCE><<<grid, 256, 0, E->stream>>>(a);
+    LAUNCHED(E);
+}
+
+template <int KIND>   // KIND_VB_V or KIND_MC_V
+static int sweep_factors_fused(Engine* E) {
+    const DevSplit& S = E->tr;
+    const Run &r0 = E->runs[0], &r1 = E->runs[1];
+    cudaStream_t st = E->stream;
+    for (int f = 0; f < E->K; f++) {
+        { ProfScope ps(E, 0); launch_fused<KIND, true>(E, f, f > 0); }                 // pending pass 2 of factor f-1 + pass 1 of run 0
+        if (int rc = combine_finalize<KIND>(E, r0, f)) return rc;
+        {
+            ProfScope ps(E, 0);                                                        // pass 1 of run 1, run 0's pass 2 added on the fly
+            SweepArgs a{};
+            a.tile_col = E->d_tile_col; a.tile_begin = E->d_tile_begin; a.tile_len = E->d_tile_len; a.exec_order = E->d_exec_order;
+            a.colptr = S.colptr; a.crow = S.crow; a.cval = S.cval; a.rv = row_view(S); a.ov = OtherView{S.cother, S.cother_val};
+            a.e = E->d_e; a.pf = E->d_pv + (size_t)f * E->D; a.partial = E->d_partial; a.delta = E->d_delta; a.pend_delta = E->d_delta;
+            a.tile0 = r1.tile_begin; a.ntiles = r1.tile_end - r1.tile_begin; a.tile_entries = E->tile_entries;
+            unsigned grid = (a.ntiles + 7) / 8;
+            if (a.ntiles) {
+                if (S.all_ones) k_sweep_reduce<KIND, 2, true><<<grid, 256, 0, st>>>(a);
+                else k_sweep_reduce<KIND, 2, false><<<grid, 256, 0, st>>>(a);
+                LAUNCHED(E);
+            }
+        }
+        if (int rc = combine_finalize<KIND>(E, r1, f)) return rc;
+    }
+    { ProfScope ps(E, 2); launch_fused<KIND, false>(E, E->K, true); }                  // flush the last factor's pass 2
+    return check_launch(E, "sweep_factors_fused");
 }
 
 // sum e, sum e^2, sum clamp(e)^2 -> red[0..2] (global)
@@ -236,9 +297,13 @@ static int vb_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
     if (E->cfg.k1)                                                 // update_w, all columns (vb.h:390-406)
         for (const Run& r : E->runs)
             if (int rc = sweep_run<KIND_VB_W>(E, r, -1)) return rc;
-    for (int f = 0; f < E->K; f++)                                 // update_v (vb.h:409-440)
-        for (const Run& r : E->runs)
-            if (int rc = sweep_run<KIND_VB_V>(E, r, f)) return rc;
+    if (fused_ok(E)) {                                             // update_v (vb.h:409-440)
+        if (int rc = sweep_factors_fused<KIND_VB_V>(E)) return rc;
+    } else {
+        for (int f = 0; f < E->K; f++)
+            for (const Run& r : E->runs)
+                if (int rc = sweep_run<KIND_VB_V>(E, r, f)) return rc;
+    }
     // hyper-parameters + free energy (vb.h:446-500)
     if (int rc = reduce_e(E)) return rc;
     k_reduce_dT<<<SV_GGRID, 256, 0, st>>>(E->d_dT, E->D, E->d_red_partial); LAUNCHED(E);
@@ -265,9 +330,13 @@ static int mcmc_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
     if (E->cfg.k1)
         for (const Run& r : E->runs)
             if (int rc = sweep_run<KIND_MC_W>(E, r, -1)) return rc;
-    for (int f = 0; f < E->K; f++)
-        for (const Run& r : E->runs)
-            if (int rc = sweep_run<KIND_MC_V>(E, r, f)) return rc;
+    if (fused_ok(E)) {
+        if (int rc = sweep_factors_fused<KIND_MC_V>(E)) return rc;
+    } else {
+        for (int f = 0; f < E->K; f++)
+            for (const Run& r : E->runs)
+                if (int rc = sweep_run<KIND_MC_V>(E, r, f)) return rc;
+    }
     if (ev) cudaEventRecord(ev->t1, st);
     // re-prediction of train and test (mcmcs.h:134-174)
     if (E->cfg.flags & SVBFM_FLAG_MCMC_NO_REPREDICT) {
@@ -382,6 +451,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     rc |= dev_alloc(E, &E->d_sc, 1);
     rc |= dev_alloc(E, &E->d_colsum, D * 4);
     rc |= dev_alloc(E, &E->d_delta, D);
+    rc |= dev_alloc(E, &E->d_mu_prev, D);
     rc |= dev_alloc(E, &E->d_dT, D);
     rc |= dev_alloc(E, &E->d_red_partial, SCR_GROUP + (K + 1) * 64 /*max groups*/ * 2 * SV_GGRID);
     if (rc) { g_create_error = E->err; svbfm_destroy(*out); *out = nullptr; return SVBFM_ERR_OOM; }
@@ -407,7 +477,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_mu_prev, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) cudaFree(p);
     if (E->own_stream) cudaStreamDestroy(E->own_stream);
     delete E;
@@ -827,6 +897,7 @@ int svbfm_get_info(svbfm_t* h, svbfm_info* out) {
     out->train_nnz = E->tr.nnz;
     out->rows_reordered = E->rows_reordered;
     out->world_size = (uint32_t)E->world;
+    out->fused_schedule = fused_ok(E) ? 1u : 0u;
     return SVBFM_OK;
 }
 

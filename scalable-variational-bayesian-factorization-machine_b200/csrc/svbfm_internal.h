@@ -129,6 +129,7 @@ struct Engine {
     double* d_partial = nullptr;      // [n_tiles][4]
     double* d_colsum = nullptr;       // [D][4]
     double* d_delta = nullptr;        // [D]
+    double* d_mu_prev = nullptr;      // [D] parameter mean before its latest update (fused schedule)
     double* d_dT = nullptr;           // [D]
     double* d_red_partial = nullptr;  // reduction scratch
     double* d_grp_sums = nullptr;     // [(K+1)][G][2]

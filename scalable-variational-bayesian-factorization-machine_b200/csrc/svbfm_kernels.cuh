@@ -101,6 +101,7 @@ struct SweepArgs {
     const double2* pf;        // params of this factor ([D]) or the w params
     double* partial;          // [n_tiles][4]
     const double* delta;      // [D]
+    const double* pend_delta; // F == 2 fused schedule: deltas of the previous run, not yet applied to e (null otherwise)
     uint32_t tile0, ntiles, tile_entries;
     const uint16_t* cbatch;   // vb_online: batch id of the case of every CSC entry (null otherwise)
     uint32_t batch;           // vb_online: current batch
@@ -150,6 +151,13 @@ __global__ void __launch_bounds__(256) k_sweep_reduce(SweepArgs a) {
                 A += xf * (ei - mu * xf);                              // mcmc.h:677
                 B += xx;
             } else if constexpr (KIND == KIND_VB_V || KIND == KIND_VBO_V) {
+                if constexpr (FT == 2)
+                    if (a.pend_delta) {      // pass 2 of the previous run folded in: e_i += x_o (mu_j x_j) delta_o   (vb.h:628, 638)
+                        uint32_t o = __ldcs(&a.ov.col[p]);
+                        float xo = 1.0f;
+                        if constexpr (!ONES) xo = __ldcs(&a.ov.val[p]);
+                        ei += (xo * (mu * xf)) * __ldg(&a.pend_delta[o]);
+                    }
                 double h, h1, h2;
                 others<FT, ONES, true>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
                 A += xf * h * (ei + xf * mu * h);                      // vb.h:594
@@ -157,6 +165,13 @@ __global__ void __launch_bounds__(256) k_sweep_reduce(SweepArgs a) {
                 C1 += xx * h1;                                         // sum of pass-2 h1 (vb.h:629)
                 C2 += xx * h2;                                         // sum of pass-2 h2 (vb.h:630)
             } else {                                                   // KIND_MC_V
+                if constexpr (FT == 2)
+                    if (a.pend_delta) {      // mcmc.h:831-833 of the previous run folded in
+                        uint32_t o = __ldcs(&a.ov.col[p]);
+                        float xo = 1.0f;
+                        if constexpr (!ONES) xo = __ldcs(&a.ov.val[p]);
+                        ei += (xo * (mu * xf)) * __ldg(&a.pend_delta[o]);
+                    }
                 double h, h1, h2;
                 others<FT, ONES, false>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
                 double hh = xf * h;                                    // mcmc.h:789
@@ -262,6 +277,7 @@ struct FinalizeArgs {
     const double* hyper_mu;      // mcmc: mu per group
     Scalars* sc;
     double* delta;               // [D]
+    double* mu_prev;             // [D] mean before this update (fused schedule), may be null
     double* dT;                  // [D]
     uint64_t seed; int do_sample;
     // vb_online
@@ -293,6 +309,7 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
         if (isnan(mu) || isinf(mu)) { mu = mu_old; bad++; skip = true; }   // vb.h:552-565 / :606-619 (pass 2 skipped)
         a.pf[j] = make_double2(mu, sg);
         a.delta[j] = skip ? 0.0 : (mu_old - mu);
+        if (a.mu_prev) a.mu_prev[j] = mu_old;
         if (!skip) {
             if constexpr (KIND == KIND_VB_W) a.dT[j] += B * (sg - sg_old);                                    // vb.h:572
             else a.dT[j] += (C1 + C2) * (sg - sg_old) + C1 * (mu * mu - mu_old * mu_old);                        // vb.h:639-640
@@ -314,6 +331,7 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
         if (isnan(v) || isinf(v)) { v = v_old; bad++; skip = true; }         // mcmc.h:697-710 / :811-824
         a.pf[j] = make_double2(v, 0.0);
         a.delta[j] = skip ? 0.0 : (v - v_old);                               // e -= h (v_old - v)  (mcmc.h:716 / :833)
+        if (a.mu_prev) a.mu_prev[j] = v_old;
     }
     if (bad) atomicAdd(&a.sc->nan_inf, (unsigned long long)bad);
 }
@@ -381,6 +399,96 @@ __global__ void __launch_bounds__(256) k_sweep_apply(SweepArgs a) {
             hh = xf * h;
         }
         a.e[i] += hh * d;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused schedule for two complete one-hot fields (every case has exactly one feature in run 0 and one in run 1, and
+// the device case order is run 0's order, so case i = p - entry0 for CSC entry p of run 0).
+// One streaming kernel per factor f over run 0:
+//     e_i += pass 2 of run 0, factor f-1        (vb.h:638 with h from the item mean BEFORE its f-1 update: mu_prev)
+//     e_i += pass 2 of run 1, factor f-1        (h from the user mean of factor f-1, already updated)
+//     store e_i ; pass 1 of run 0, factor f     (vb.h:587-596)
+// Run 1's pass 1 adds run 0's pending pass 2 on the fly (k_sweep_reduce, pend_delta) and does not write e. This
+// removes both k_row_apply launches of a factor. REDUCE = false flushes the pending updates after the last factor.
+struct FusedArgs {
+    const uint32_t* tile_col;
+    const uint64_t* tile_begin;
+    const uint32_t* tile_len;
+    const uint32_t* exec_order;
+    uint32_t tile0, ntiles;
+    uint64_t entry0;
+    const float* cval;
+    OtherView ov;
+    double* e;
+    const double2* pf;        // parameters of factor f
+    const double2* pf_prev;   // parameters of factor f-1 (null: nothing pending)
+    const double* delta;      // [D] deltas of factor f-1, both runs
+    const double* mu_prev;    // [D] means before their factor f-1 update
+    double* partial;
+};
+
+template <int KIND, bool ONES, bool REDUCE>
+__global__ void __launch_bounds__(256) k_fused_stream(FusedArgs a) {
+    uint32_t w = (blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5);
+    if (w >= a.ntiles) return;
+    uint32_t t = __ldg(&a.exec_order[a.tile0 + w]), lane = threadIdx.x & 31;
+    uint32_t j = __ldg(&a.tile_col[t]);
+    uint64_t b = __ldg(&a.tile_begin[t]);
+    uint64_t e_ = b + __ldg(&a.tile_len[t]);
+    double mu = 0.0, mu_p = 0.0, dU = 0.0;
+    if constexpr (REDUCE) mu = __ldg(&a.pf[j]).x;
+    const bool pending = a.pf_prev != nullptr;
+    if (pending) { mu_p = __ldg(&a.pf_prev[j]).x; dU = __ldg(&a.delta[j]); }
+    double A = 0.0, B = 0.0, C1 = 0.0, C2 = 0.0;
+    constexpr int U = 4;
+    for (uint64_t p0 = b + lane; p0 < e_; p0 += 32 * U) {
+        bool ok[U]; uint32_t oc[U]; float xs[U], xo[U]; double es[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            uint64_t p = p0 + (uint64_t)u * 32;
+            ok[u] = p < e_;
+            oc[u] = ok[u] ? __ldcs(&a.ov.col[p]) : 0u;
+            xs[u] = 1.0f; xo[u] = 1.0f;
+            if constexpr (!ONES) if (ok[u]) { xs[u] = __ldcs(&a.cval[p]); xo[u] = __ldcs(&a.ov.val[p]); }
+            es[u] = ok[u] ? a.e[p - a.entry0] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!ok[u]) continue;
+            uint64_t i = p0 + (uint64_t)u * 32 - a.entry0;
+            float xf = xs[u], xof = xo[u];
+            double ei = es[u];
+            if (pending) {
+                ei += (xf * (__ldg(&a.mu_prev[oc[u]]) * xof)) * dU;               // run 0, factor f-1
+                ei += (xof * (mu_p * xf)) * __ldg(&a.delta[oc[u]]);                // run 1, factor f-1
+                a.e[i] = ei;
+            }
+            if constexpr (REDUCE) {
+                double2 P = __ldg(&a.pf[oc[u]]);
+                double xx = (double)(xf * xf);
+                if constexpr (KIND == KIND_VB_V) {
+                    double h = P.x * xof, h1 = P.y * xof * xof, h2 = P.x * P.x * xof * xof;
+                    A += xf * h * (ei + xf * mu * h);
+                    B += xx * h * h + xx * h1;
+                    C1 += xx * h1;
+                    C2 += xx * h2;
+                } else {   // KIND_MC_V
+                    double hh = xf * (P.x * xof);
+                    A += hh * ei;
+                    B += hh * hh;
+                }
+            }
+        }
+    }
+    if constexpr (REDUCE) {
+        A = warp_sum(A); B = warp_sum(B);
+        if constexpr (KIND == KIND_VB_V) { C1 = warp_sum(C1); C2 = warp_sum(C2); }
+        if (lane == 0) {
+            double2* out = reinterpret_cast<double2*>(a.partial + (size_t)t * 4);
+            out[0] = make_double2(A, B);
+            out[1] = make_double2(C1, C2);
+        }
     }
 }
 

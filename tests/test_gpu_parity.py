@@ -34,7 +34,7 @@ def test_vb_two_field_onehot(built):
     tr, te = two_field(20000, 2000, 300, 200)
     L, orc = run_vb(tr, te, K=4, iters=8)
     info = L.engine.info()
-    assert info["num_runs"] == 2 and info["all_ones"] == 1 and info["uniform_row_nnz"] == 2 and info["rows_reordered"] == 1
+    assert info["num_runs"] == 2 and info["all_ones"] == 1 and info["uniform_row_nnz"] == 2 and info["rows_reordered"] == 1 and info["fused_schedule"] == 1
     # state and residuals agree with the oracle's caches (caller case order)
     e_o, t_o = orc.get_train_cache()
     e = L.engine.get_residuals()
@@ -156,3 +156,25 @@ def test_vb_block_cut_tiles(built, monkeypatch):
     monkeypatch.setenv("SVBFM_BLOCK_CASES", "700")
     tr, te = ragged(6000, 300, 30, seed=62)
     run_vb(tr, te, K=2, iters=3, tile_entries=32)
+
+
+def test_fused_equals_unfused_schedule(built, monkeypatch):
+    """The fused two-field schedule and the general per-run schedule are the same algorithm: identical statistics
+    to rounding, on one-hot data and on two-field data with real values."""
+    for values in (False, True):
+        tr, te = two_field(15000, 1500, 250, 180, seed=71, values=values)
+        out = []
+        for nofuse in ("", "1"):
+            if nofuse:
+                monkeypatch.setenv("SVBFM_NO_FUSE", "1")
+            else:
+                monkeypatch.delenv("SVBFM_NO_FUSE", raising=False)
+            L = make_learner("vb", tr, te, 3, num_iter=4)
+            hist = L.learn(to_csc(tr), to_csc(te))
+            assert L.engine.info()["fused_schedule"] == (0 if nofuse else 1)
+            out.append([(s.test_rmse, s.free_energy, s.train_stat) for s in hist])
+            L.engine.close()
+        for a, b in zip(*out):
+            assert all(rel(x, y) < 1e-10 for x, y in zip(a, b)), (a, b)
+        monkeypatch.delenv("SVBFM_NO_FUSE", raising=False)
+        run_vb(tr, te, K=3, iters=4)
