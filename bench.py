@@ -25,7 +25,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_RATING_K = 216.0     # cached-state algorithm, two one-hot fields, fp64 state
-OWN_BYTES_PER_RATING_K = 2 * (4 + 8 + 8) + 2 * (4 + 8 + 8 + 8)   # this engine: see DESIGN.md "Kernels"
 
 
 def parse_args():
@@ -293,19 +292,35 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     sweep_per_step = sweep_ms / a.steps
     achieved = (N / world) * K * ALGO_BYTES_PER_RATING_K / (sweep_per_step * 1e-3) / 1e9     # per GPU
-    rv = prof["reduce_v"]
     n_local = hi - lo
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    fused = bool(info0.get("fused_schedule"))
+    # own algorithmic bytes per rating*k: fused = stream (cother 4 + e 8r+8w) + gather pass 1 (crow 4 + cother 4 + e 8)
+    own_bytes = 36.0 if fused else 80.0
+    # per-class model bytes per entry under SURVEY's 216 B accounting: pass 1 = 8 B CSC entry + 40 B state, pass 2 = 40 B state write
+    model_bytes = {"reduce_v": 48.0, "apply_v": 40.0, "fused_stream_v": 128.0, "fused_flush_v": 80.0}
+    kname = {"reduce_v": "k_sweep_reduce<VB_V> (pass 1" + (", gather run" if fused else "") + ")", "apply_v": "k_row_apply<VB_V> (pass 2)",
+             "fused_stream_v": "k_fused_stream<VB_V> (pending pass 2 of both runs + pass 1 of run 0)", "fused_flush_v": "k_fused_stream<flush>"}
+    dom = max((k for k in model_bytes if prof[k]["launches"]), key=lambda k: prof[k]["ms"], default="reduce_v")
+    dk = prof[dom]
+    dk_avg = dk["ms"] / max(dk["launches"], 1)
+    traffic = None
+    try:     # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        if a.workload == tj.get("workload") and world == 1:
+            traffic = tj["dram_bytes_per_launch"].get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src,
                 "definition": "N*K*216 B (SURVEY 8d algorithmic bytes of the cached-state algorithm) / sweep time, per GPU; "
                               "may exceed what the engine really moves because it re-derives q,S2,S3 instead of caching them",
-                "own_bytes_per_rating_k": OWN_BYTES_PER_RATING_K,
-                "own_achieved": (N / world) * K * OWN_BYTES_PER_RATING_K / (sweep_per_step * 1e-3) / 1e9,
-                "dominant_kernel": {"name": "k_sweep_reduce<VB_V>", "launches": rv["launches"],
-                                    "avg_ms": rv["ms"] / max(rv["launches"], 1),
-                                    "share_of_sweep": rv["ms"] / max(sweep_ms, 1e-9),
-                                    "algorithmic_bytes_per_launch": n_local * 48.0,
-                                    "achieved_GBps": n_local * 48.0 / (rv["ms"] / max(rv["launches"], 1) * 1e-3) / 1e9 if rv["launches"] else None},
+                "own_bytes_per_rating_k": own_bytes,
+                "own_achieved": (N / world) * K * own_bytes / (sweep_per_step * 1e-3) / 1e9,
+                "dominant_kernel": {"name": kname[dom], "launches": dk["launches"], "avg_ms": dk_avg,
+                                    "share_of_sweep": dk["ms"] / max(sweep_ms, 1e-9),
+                                    "algorithmic_bytes_per_launch": n_local * model_bytes[dom],
+                                    "achieved_GBps": n_local * model_bytes[dom] / (dk_avg * 1e-3) / 1e9 if dk["launches"] else None,
+                                    "traffic_bytes_per_launch": traffic},
                 "kernel_classes_ms": {k: v["ms"] for k, v in prof.items()}}
     cpu_baseline = None
     if world == 1 and not a.no_cpu_baseline:
@@ -318,7 +333,8 @@ def main():
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload, "sharding": f"{world} contiguous case shards, NCCL allreduce of column sums per field run" if world > 1 else "single GPU",
                       "l2": "inputs (residuals + design matrix) are far larger than the 126 MB L2; no flush needed",
-                      "field_runs": info0["num_runs"], "tiles": info0["num_tiles"], "rows_reordered": info0["rows_reordered"]},
+                      "field_runs": info0["num_runs"], "tiles": info0["num_tiles"], "rows_reordered": info0["rows_reordered"],
+                      "fused_schedule": info0.get("fused_schedule", 0)},
            "sweep_only_ms_per_step": sweep_per_step, "wall_ms_per_step": wall_ms / a.steps,
            "test_rmse_last": last.test_rmse, "free_energy_last": last.free_energy,
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}

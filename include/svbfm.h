@@ -153,8 +153,9 @@ typedef struct svbfm_info {
 } svbfm_info;
 int svbfm_get_info(svbfm_t* h, svbfm_info* out);
 /* per-kernel-class device time (CUDA events on the launching stream), for bench.py's roofline block.
- * classes: 0 reduce_v, 1 combine+finalize_v, 2 apply_v, 3 reduce_w, 4 combine+finalize_w, 5 apply_w */
-#define SVBFM_PROFILE_CLASSES 6
+ * classes: 0 reduce_v (k_sweep_reduce), 1 combine+finalize_v, 2 apply_v, 3 reduce_w, 4 combine+finalize_w, 5 apply_w,
+ *          6 fused_stream_v (k_fused_stream: pending pass 2 + pass 1 of run 0), 7 fused_flush_v */
+#define SVBFM_PROFILE_CLASSES 8
 int svbfm_set_profile(svbfm_t* h, int32_t enabled);
 int svbfm_get_profile(svbfm_t* h, double ms[SVBFM_PROFILE_CLASSES], uint64_t launches[SVBFM_PROFILE_CLASSES]); /* reads and resets */
 /* run on an externally owned CUDA stream (cudaStream_t); NULL restores the handle's own stream */

@@ -248,10 +248,10 @@ class Engine:
         self._ck(lib().svbfm_set_profile(self.h, int(on)), "svbfm_set_profile")
 
     def get_profile(self):
-        ms = np.zeros(6)
-        cnt = np.zeros(6, dtype=np.uint64)
+        ms = np.zeros(8)
+        cnt = np.zeros(8, dtype=np.uint64)
         self._ck(lib().svbfm_get_profile(self.h, _p(ms), _p(cnt)), "svbfm_get_profile")
-        names = ["reduce_v", "finalize_v", "apply_v", "reduce_w", "finalize_w", "apply_w"]
+        names = ["reduce_v", "finalize_v", "apply_v", "reduce_w", "finalize_w", "apply_w", "fused_stream_v", "fused_flush_v"]
         return {n: dict(ms=float(m), launches=int(c)) for n, m, c in zip(names, ms, cnt)}
 
     def info(self):

@@ -100,7 +100,7 @@ struct ProfScope {
 
 // tiles -> column sums (-> allreduce when sharded) -> per-column update
 template <int KIND>
-static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1) {
+static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, int pack_mode = 0) {
     cudaStream_t st = E->stream;
     constexpr bool IS_V = (KIND == KIND_VB_V || KIND == KIND_MC_V || KIND == KIND_VBO_V);
     double2* pf = IS_V ? E->d_pv + (size_t)f * E->D : E->d_pw;
@@ -121,6 +121,7 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1) {
     fa.pf = pf; fa.group = E->d_group; fa.hyper = IS_V ? E->d_hyper_v : E->d_hyper_w;
     fa.hyper_mu = IS_V ? E->d_mu_v : E->d_mu_w; fa.sc = E->d_sc; fa.delta = E->d_delta; fa.mu_prev = E->d_mu_prev; fa.dT = E->d_dT;
     fa.seed = E->cfg.seed; fa.do_sample = E->cfg.do_sample;
+    fa.cpack = pack_mode ? E->d_cpack : nullptr; fa.pack_mode = pack_mode; fa.D = E->D;
     if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V) {
         fa.nat = IS_V ? E->d_nat_v + (size_t)f * E->D : E->d_nat_w;
         fa.t_cnt = IS_V ? E->d_t_v : E->d_t_w;
@@ -207,7 +208,7 @@ static void launch_fused(Engine* E, int f, bool pending) {
     a.cval = S.cval; a.ov = OtherView{S.cother, S.cother_val}; a.e = E->d_e;
     a.pf = REDUCE ? E->d_pv + (size_t)f * E->D : nullptr;
     a.pf_prev = pending ? E->d_pv + (size_t)(f - 1) * E->D : nullptr;
-    a.delta = E->d_delta; a.mu_prev = E->d_mu_prev; a.partial = E->d_partial;
+    a.delta = E->d_delta; a.cpack = E->d_cpack; a.partial = E->d_partial;
     unsigned grid = (a.ntiles + 7) / 8;
     if (S.all_ones) k_fused_stream<KIND, true, REDUCE><<<grid, 256, 0, E->stream>>>(a);
     else k_fused_stream<KIND, false, REDUCE><<<grid, 256, 0, E->stream>>>(a);
@@ -219,15 +220,16 @@ static int sweep_factors_fused(Engine* E) {
     const DevSplit& S = E->tr;
     const Run &r0 = E->runs[0], &r1 = E->runs[1];
     cudaStream_t st = E->stream;
+    k_pack_cols<<<nblk(r1.col_end - r1.col_begin), 256, 0, st>>>(r1.col_begin, r1.col_end, E->d_pv, E->d_cpack); LAUNCHED(E);
     for (int f = 0; f < E->K; f++) {
-        { ProfScope ps(E, 0); launch_fused<KIND, true>(E, f, f > 0); }                 // pending pass 2 of factor f-1 + pass 1 of run 0
-        if (int rc = combine_finalize<KIND>(E, r0, f)) return rc;
+        { ProfScope ps(E, 6); launch_fused<KIND, true>(E, f, f > 0); }                 // pending pass 2 of factor f-1 + pass 1 of run 0
+        if (int rc = combine_finalize<KIND>(E, r0, f, -1, 1)) return rc;
         {
             ProfScope ps(E, 0);                                                        // pass 1 of run 1, run 0's pass 2 added on the fly
             SweepArgs a{};
             a.tile_col = E->d_tile_col; a.tile_begin = E->d_tile_begin; a.tile_len = E->d_tile_len; a.exec_order = E->d_exec_order;
             a.colptr = S.colptr; a.crow = S.crow; a.cval = S.cval; a.rv = row_view(S); a.ov = OtherView{S.cother, S.cother_val};
-            a.e = E->d_e; a.pf = E->d_pv + (size_t)f * E->D; a.partial = E->d_partial; a.delta = E->d_delta; a.pend_delta = E->d_delta;
+            a.e = E->d_e; a.pf = E->d_pv + (size_t)f * E->D; a.partial = E->d_partial; a.delta = E->d_delta; a.cpack = E->d_cpack;
             a.tile0 = r1.tile_begin; a.ntiles = r1.tile_end - r1.tile_begin; a.tile_entries = E->tile_entries;
             unsigned grid = (a.ntiles + 7) / 8;
             if (a.ntiles) {
@@ -236,9 +238,9 @@ static int sweep_factors_fused(Engine* E) {
                 LAUNCHED(E);
             }
         }
-        if (int rc = combine_finalize<KIND>(E, r1, f)) return rc;
+        if (int rc = combine_finalize<KIND>(E, r1, f, -1, f + 1 < E->K ? 2 : 3)) return rc;
     }
-    { ProfScope ps(E, 2); launch_fused<KIND, false>(E, E->K, true); }                  // flush the last factor's pass 2
+    { ProfScope ps(E, 7); launch_fused<KIND, false>(E, E->K, true); }                  // flush the last factor's pass 2
     return check_launch(E, "sweep_factors_fused");
 }
 
@@ -452,6 +454,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     rc |= dev_alloc(E, &E->d_colsum, D * 4);
     rc |= dev_alloc(E, &E->d_delta, D);
     rc |= dev_alloc(E, &E->d_mu_prev, D);
+    rc |= dev_alloc(E, &E->d_cpack, D);
     rc |= dev_alloc(E, &E->d_dT, D);
     rc |= dev_alloc(E, &E->d_red_partial, SCR_GROUP + (K + 1) * 64 /*max groups*/ * 2 * SV_GGRID);
     if (rc) { g_create_error = E->err; svbfm_destroy(*out); *out = nullptr; return SVBFM_ERR_OOM; }
@@ -477,7 +480,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_mu_prev, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_mu_prev, E->d_cpack, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) cudaFree(p);
     if (E->own_stream) cudaStreamDestroy(E->own_stream);
     delete E;

@@ -367,6 +367,8 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         uint32_t block_cases = 4u << 20;
         if (const char* sb = getenv("SVBFM_BLOCK_CASES")) block_cases = (uint32_t)atol(sb);
         uint32_t NB = (block_cases && n) ? (uint32_t)(((uint64_t)n + block_cases - 1) / block_cases) : 1;
+        uint64_t cut_min = 16;   // a column is cut when it has at least cut_min entries per block on average
+        if (const char* sc = getenv("SVBFM_CUT_MIN")) cut_min = (uint64_t)atol(sc);
         std::vector<uint32_t> tile_col, tile_len, col_tile0((size_t)S.ncols_ext + 1), heavy, exec_order, tile_block;
         std::vector<uint64_t> tile_begin;
         // columns to cut: gather runs only, and only when there is more than one block
@@ -376,7 +378,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
             bool sequential = (ri == 0 && E->rows_reordered);
             if (sequential || NB <= 1) continue;
             for (uint32_t j = r.col_begin; j < r.col_end; j++)
-                if (S.h_colptr[j + 1] - S.h_colptr[j] >= (uint64_t)16 * NB) cut_cols.push_back(j);
+                if (S.h_colptr[j + 1] - S.h_colptr[j] >= cut_min * NB) cut_cols.push_back(j);
         }
         std::vector<uint64_t> cuts;   // [cut_cols][NB+1] absolute entry positions
         if (!cut_cols.empty()) {

@@ -19,6 +19,8 @@
 
 namespace svb {
 
+struct ColPack;
+
 struct DevSplit {
     uint32_t n = 0;          // local cases
     uint32_t n_cols = 0;     // columns present in this split's data_t (max feature id + 1)
@@ -130,6 +132,7 @@ struct Engine {
     double* d_colsum = nullptr;       // [D][4]
     double* d_delta = nullptr;        // [D]
     double* d_mu_prev = nullptr;      // [D] parameter mean before its latest update (fused schedule)
+    struct ColPack* d_cpack = nullptr; // [D] fused schedule: 32-byte per-column records gathered by the sweeps
     double* d_dT = nullptr;           // [D]
     double* d_red_partial = nullptr;  // reduction scratch
     double* d_grp_sums = nullptr;     // [(K+1)][G][2]

@@ -52,6 +52,9 @@ struct OtherView {            // F == 2 only: for every CSC entry, the feature i
     const float* val;
 };
 
+// fused schedule: everything a case needs from its OTHER column in one 32-byte record (one LDG.E.256 gather)
+struct alignas(32) ColPack { double mu, sg, delta, mu_prev; };
+
 template <int FT, bool ONES, bool VAR>
 __device__ __forceinline__ void others(const RowView& rv, const OtherView& ov, const double2* __restrict__ pf, uint64_t p, uint32_t i, uint32_t j,
                                        double& h, double& h1, double& h2) {
@@ -101,7 +104,7 @@ struct SweepArgs {
     const double2* pf;        // params of this factor ([D]) or the w params
     double* partial;          // [n_tiles][4]
     const double* delta;      // [D]
-    const double* pend_delta; // F == 2 fused schedule: deltas of the previous run, not yet applied to e (null otherwise)
+    const ColPack* cpack;     // F == 2 fused schedule: {mu, sigma, delta, -} of the other column; delta = pass 2 of the previous run, not yet applied to e
     uint32_t tile0, ntiles, tile_entries;
     const uint16_t* cbatch;   // vb_online: batch id of the case of every CSC entry (null otherwise)
     uint32_t batch;           // vb_online: current batch
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(256) k_sweep_reduce(SweepArgs a) {
     double2 Pj = __ldg(&a.pf[j]);
     double mu = Pj.x;
     double A = 0.0, B = 0.0, C1 = 0.0, C2 = 0.0;
-    constexpr int U = 4;                     // entries per lane in flight: the loads of a batch are issued back to back
+    constexpr int U = 4;                     // entries per lane in flight (8 was slower: fewer resident warps): the loads of a batch are issued back to back
     for (uint64_t p0 = b + lane; p0 < e_; p0 += 32 * U) {
         bool ok[U]; uint32_t ci[U]; float xs[U]; double es[U];
 #pragma unroll
@@ -151,29 +154,33 @@ __global__ void __launch_bounds__(256) k_sweep_reduce(SweepArgs a) {
                 A += xf * (ei - mu * xf);                              // mcmc.h:677
                 B += xx;
             } else if constexpr (KIND == KIND_VB_V || KIND == KIND_VBO_V) {
-                if constexpr (FT == 2)
-                    if (a.pend_delta) {      // pass 2 of the previous run folded in: e_i += x_o (mu_j x_j) delta_o   (vb.h:628, 638)
+                double h, h1, h2;
+                if constexpr (FT == 2) {
+                    if (a.cpack) {           // fused schedule: other column's record; pass 2 of the previous run folded in (vb.h:628, 638)
                         uint32_t o = __ldcs(&a.ov.col[p]);
                         float xo = 1.0f;
                         if constexpr (!ONES) xo = __ldcs(&a.ov.val[p]);
-                        ei += (xo * (mu * xf)) * __ldg(&a.pend_delta[o]);
-                    }
-                double h, h1, h2;
-                others<FT, ONES, true>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
+                        ColPack g = a.cpack[o];
+                        ei += (xo * (mu * xf)) * g.delta;
+                        h = g.mu * xo; h1 = g.sg * xo * xo; h2 = g.mu * g.mu * xo * xo;
+                    } else others<FT, ONES, true>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
+                } else others<FT, ONES, true>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
                 A += xf * h * (ei + xf * mu * h);                      // vb.h:594
                 B += xx * h * h + xx * h1;                             // vb.h:595
                 C1 += xx * h1;                                         // sum of pass-2 h1 (vb.h:629)
                 C2 += xx * h2;                                         // sum of pass-2 h2 (vb.h:630)
             } else {                                                   // KIND_MC_V
-                if constexpr (FT == 2)
-                    if (a.pend_delta) {      // mcmc.h:831-833 of the previous run folded in
+                double h, h1, h2;
+                if constexpr (FT == 2) {
+                    if (a.cpack) {           // mcmc.h:831-833 of the previous run folded in
                         uint32_t o = __ldcs(&a.ov.col[p]);
                         float xo = 1.0f;
                         if constexpr (!ONES) xo = __ldcs(&a.ov.val[p]);
-                        ei += (xo * (mu * xf)) * __ldg(&a.pend_delta[o]);
-                    }
-                double h, h1, h2;
-                others<FT, ONES, false>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
+                        ColPack g = a.cpack[o];
+                        ei += (xo * (mu * xf)) * g.delta;
+                        h = g.mu * xo;
+                    } else others<FT, ONES, false>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
+                } else others<FT, ONES, false>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
                 double hh = xf * h;                                    // mcmc.h:789
                 A += hh * ei;                                          // mcmc.h:790
                 B += hh * hh;                                          // mcmc.h:791
@@ -278,6 +285,9 @@ struct FinalizeArgs {
     Scalars* sc;
     double* delta;               // [D]
     double* mu_prev;             // [D] mean before this update (fused schedule), may be null
+    ColPack* cpack;              // [D] fused schedule record of this column (null otherwise)
+    int pack_mode;               // 1: {new mu, new sigma} of this factor; 2: {mu, sigma} of the NEXT factor (pf + D); 3: zeros
+    uint32_t D;
     double* dT;                  // [D]
     uint64_t seed; int do_sample;
     // vb_online
@@ -310,6 +320,10 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
         a.pf[j] = make_double2(mu, sg);
         a.delta[j] = skip ? 0.0 : (mu_old - mu);
         if (a.mu_prev) a.mu_prev[j] = mu_old;
+        if (a.cpack) {
+            double2 Q = a.pack_mode == 1 ? make_double2(mu, sg) : (a.pack_mode == 2 ? a.pf[(size_t)a.D + j] : make_double2(0.0, 0.0));
+            a.cpack[j] = ColPack{Q.x, Q.y, skip ? 0.0 : (mu_old - mu), mu_old};
+        }
         if (!skip) {
             if constexpr (KIND == KIND_VB_W) a.dT[j] += B * (sg - sg_old);                                    // vb.h:572
             else a.dT[j] += (C1 + C2) * (sg - sg_old) + C1 * (mu * mu - mu_old * mu_old);                        // vb.h:639-640
@@ -332,6 +346,10 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
         a.pf[j] = make_double2(v, 0.0);
         a.delta[j] = skip ? 0.0 : (v - v_old);                               // e -= h (v_old - v)  (mcmc.h:716 / :833)
         if (a.mu_prev) a.mu_prev[j] = v_old;
+        if (a.cpack) {
+            double2 Q = a.pack_mode == 1 ? make_double2(v, 0.0) : (a.pack_mode == 2 ? a.pf[(size_t)a.D + j] : make_double2(0.0, 0.0));
+            a.cpack[j] = ColPack{Q.x, Q.y, skip ? 0.0 : (v - v_old), v_old};
+        }
     }
     if (bad) atomicAdd(&a.sc->nan_inf, (unsigned long long)bad);
 }
@@ -423,8 +441,8 @@ struct FusedArgs {
     double* e;
     const double2* pf;        // parameters of factor f
     const double2* pf_prev;   // parameters of factor f-1 (null: nothing pending)
-    const double* delta;      // [D] deltas of factor f-1, both runs
-    const double* mu_prev;    // [D] means before their factor f-1 update
+    const double* delta;      // [D] deltas of factor f-1 (own column of the tile)
+    const ColPack* cpack;     // [D] other column: {mu_f, sigma_f, delta_{f-1}, mean before its f-1 update}
     double* partial;
 };
 
@@ -459,13 +477,14 @@ __global__ void __launch_bounds__(256) k_fused_stream(FusedArgs a) {
             uint64_t i = p0 + (uint64_t)u * 32 - a.entry0;
             float xf = xs[u], xof = xo[u];
             double ei = es[u];
+            ColPack g = a.cpack[oc[u]];
             if (pending) {
-                ei += (xf * (__ldg(&a.mu_prev[oc[u]]) * xof)) * dU;               // run 0, factor f-1
-                ei += (xof * (mu_p * xf)) * __ldg(&a.delta[oc[u]]);                // run 1, factor f-1
+                ei += (xf * (g.mu_prev * xof)) * dU;                               // run 0, factor f-1
+                ei += (xof * (mu_p * xf)) * g.delta;                               // run 1, factor f-1
                 a.e[i] = ei;
             }
             if constexpr (REDUCE) {
-                double2 P = __ldg(&a.pf[oc[u]]);
+                double2 P = make_double2(g.mu, g.sg);
                 double xx = (double)(xf * xf);
                 if constexpr (KIND == KIND_VB_V) {
                     double h = P.x * xof, h1 = P.y * xof * xof, h2 = P.x * P.x * xof * xof;
@@ -1002,6 +1021,12 @@ __global__ void k_finish_iter(Scalars* sc, DevStats* st, int method) {
     st->nan_inf = (double)sc->nan_inf;
     sc->nan_inf = 0;
     sc->iter += 1;
+}
+
+// fused schedule: records of a column range before the first factor {mu, sigma, 0, 0}
+__global__ void k_pack_cols(uint32_t c0, uint32_t c1, const double2* __restrict__ pf, ColPack* __restrict__ cpack) {
+    uint32_t j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < c1) { double2 P = pf[j]; cpack[j] = ColPack{P.x, P.y, 0.0, 0.0}; }
 }
 
 // state pack/unpack
