@@ -36,7 +36,8 @@ def parse_args():
     ap.add_argument("--workload", default="kdd200m", choices=["ml1m", "ml10m", "netflix", "kdd200m"])
     ap.add_argument("--rows", type=int, default=0, help="override the number of train ratings (debug)")
     ap.add_argument("--k", type=int, default=0, help="override the number of factors (debug)")
-    ap.add_argument("--method", default="vb", choices=["vb", "mcmc"])
+    ap.add_argument("--method", default="vb", choices=["vb", "mcmc", "vb_online"])
+    ap.add_argument("--batches", type=int, default=100, help="vb_online: number of batches per epoch (a step is one epoch)")
     ap.add_argument("--cpu-rows", type=int, default=400_000, help="ratings in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -152,7 +153,7 @@ def main():
         per = sum(t) / max(len(t), 1)
         v = n_rows * K / per
         cb = dict(value=v, unit="ratings*k/s", cores=r["cores"], kind=r["kind"], sample=r["sample"])
-        print(json.dumps({"impl": "reference", "metric": "vb_sweep_ratings_x_k_per_sec", "value": v, "unit": "ratings*k/s", "n_gpus": a.gpus,
+        print(json.dumps({"impl": "reference", "metric": a.method + "_sweep_ratings_x_k_per_sec", "value": v, "unit": "ratings*k/s", "n_gpus": a.gpus,
                           "steps": a.steps, "warmup": a.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload, "cpu_sample_rows": n_rows},
                           "cpu_baseline": cb, "e2e": {"value": v, "unit": "ratings*k/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -173,7 +174,7 @@ def main():
     # ---- synthetic data on the device (same stream of random numbers on every rank), this rank's contiguous case shard
     u, it, y = synth.ratings_torch(N, U, I, 20261018, dev)
     ut, itt, yt = synth.ratings_torch(Nt, U, I, 20261019, dev)
-    D = U + I + 1                                         # libfm.cpp:215: max(train, test num_feature) + 1
+    D = U + I + (0 if a.method == "vb_online" else 1)     # libfm.cpp:215: max(train, test num_feature) + 1 (vb_online: max id + 1)
 
     def shard(n):
         return (n * rank) // world, (n * (rank + 1)) // world
@@ -198,7 +199,7 @@ def main():
     del u, it, y, ut, itt, yt
     torch.cuda.empty_cache()
     g = torch.Generator(device=dev); g.manual_seed(42)
-    state = dict(w0_mean=0.0, w0_var=0.02 if a.method == "vb" else 0.0,
+    state = dict(w0_mean=0.0, w0_var=0.0 if a.method == "mcmc" else 0.02,
                  w_mean=(0.1 * torch.randn(D, generator=g, device=dev, dtype=torch.float64)).cpu().pin_memory().numpy(),
                  w_var=np.full(D, 0.02), v_mean=(0.1 * torch.randn(K, D, generator=g, device=dev, dtype=torch.float64)).cpu().pin_memory().numpy(),
                  v_var=np.full((K, D), 0.02))
@@ -214,20 +215,42 @@ def main():
         dist.broadcast(idt, 0)
         return bytes(idt.cpu().tolist())
 
+    phase_ms = {}
+
     def make_engine():
+        def tick(name, t0):
+            torch.cuda.synchronize()
+            phase_ms[name] = phase_ms.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
         E = sv.Engine(a.method, D, K, 1, 1, ymin, ymax, device=local, seed=42)
         if world > 1:
             E.comm_init(new_uid(), rank, world)
+        tick("create", t0); t0 = time.perf_counter()
         E.set_csc(sv.TRAIN, train)
+        tick("set_csc_train", t0); t0 = time.perf_counter()
         E.set_csc(sv.TEST, test)
+        tick("set_csc_test", t0); t0 = time.perf_counter()
         E.set_state(state)
+        tick("set_state", t0); t0 = time.perf_counter()
         E.begin()
+        tick("begin", t0)
         return E
+
+    batch_of_case = None
+    if a.method == "vb_online":     # case -> batch like vbos.h:74-95 (a shuffled balanced split), fixed for the run
+        n_loc = hi - lo
+        size = -(-n_loc // a.batches)
+        batch_of_case = (np.random.default_rng(7 + rank).permutation(n_loc) // size).astype(np.uint32)
+
+    def run_steps(E, k):
+        if a.method == "vb_online":
+            return [E.vb_online_epoch(batch_of_case, a.batches) for _ in range(k)]
+        return E.run(k)
 
     # ---- device-resident throughput
     E = make_engine()
     info0 = E.info()
-    E.run(a.warmup)
+    run_steps(E, a.warmup)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -236,7 +259,7 @@ def main():
     l0 = E.info()["kernel_launches"]
     barrier()
     w0 = time.perf_counter()
-    hist = E.run(a.steps)
+    hist = run_steps(E, a.steps)
     barrier()
     wall = time.perf_counter() - w0
     launches = E.info()["kernel_launches"] - l0
@@ -262,10 +285,11 @@ def main():
         h2d += state["w_mean"].nbytes + state["w_var"].nbytes + state["v_mean"].nbytes + state["v_var"].nbytes
         ts = []
         for s in range(max(1, min(a.steps, 3)) + 1):
+            phase_ms.clear()
             barrier()
             t0 = time.perf_counter()
             E2 = make_engine()
-            st = E2.run(1)[0]
+            st = run_steps(E2, 1)[0]
             _ = st.test_rmse                       # statistics are read back inside run()
             barrier()
             ts.append(time.perf_counter() - t0)
@@ -276,7 +300,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_e2e = float(tt.cpu()[0])
         e2e = {"value": N * K / t_e2e, "unit": "ratings*k/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 64,
-               "ms_per_step": t_e2e * 1e3, "step": "create + set_csc(train,test) from pinned host + set_state + begin + 1 iteration + stats readback"}
+               "ms_per_step": t_e2e * 1e3, "last_step_phases_ms": dict(phase_ms), "step": "create + set_csc(train,test) from pinned host + set_state + begin + 1 iteration + stats readback"}
 
     if rank != 0:
         if world > 1:
@@ -329,7 +353,7 @@ def main():
         t = r["times"][1:] if len(r["times"]) > 1 else r["times"]
         cpu_baseline = dict(value=n_rows * K / (sum(t) / len(t)), unit="ratings*k/s", cores=r["cores"], kind=r["kind"], sample=r["sample"],
                             host_cores_available=os.cpu_count())
-    out = {"metric": "vb_sweep_ratings_x_k_per_sec", "value": value, "unit": "ratings*k/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+    out = {"metric": a.method + "_sweep_ratings_x_k_per_sec", "value": value, "unit": "ratings*k/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload, "sharding": f"{world} contiguous case shards, NCCL allreduce of column sums per field run" if world > 1 else "single GPU",
                       "l2": "inputs (residuals + design matrix) are far larger than the 126 MB L2; no flush needed",
