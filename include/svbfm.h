@@ -124,6 +124,9 @@ int svbfm_mcmc_sweep(svbfm_t* h, svbfm_iter_stats* out);
  * is the batch of local train case i (the host replays std::random_shuffle, vbos.h:74-95);
  * total_cases = global number of train cases (`_size`, vbos.h:141). */
 int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t num_batch, svbfm_iter_stats* out);
+/* forget data + state of a handle but keep the device context, communicator and groups (a long-lived service handle:
+ * the next learn() starts again at svbfm_set_csc). No reference counterpart: the reference builds a new learner per process. */
+int svbfm_reset(svbfm_t* h);
 /* n iterations back to back without a host round trip in between; out[n_iter] filled at the end */
 int svbfm_run(svbfm_t* h, uint32_t n_iter, svbfm_iter_stats* out);
 

@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "svbfm_create", "svbfm_destroy", "svbfm_last_error", "svbfm_abi_version", "svbfm_comm_get_unique_id",
     "svbfm_comm_init", "svbfm_set_groups", "svbfm_set_csc", "svbfm_set_state", "svbfm_get_state",
     "svbfm_get_hyper", "svbfm_set_hyper", "svbfm_begin", "svbfm_vb_sweep", "svbfm_mcmc_sweep",
-    "svbfm_vb_online_epoch", "svbfm_run", "svbfm_predict", "svbfm_get_residuals", "svbfm_get_sum_t",
+    "svbfm_vb_online_epoch", "svbfm_run", "svbfm_reset", "svbfm_predict", "svbfm_get_residuals", "svbfm_get_sum_t",
     "svbfm_get_info", "svbfm_set_stream", "svbfm_set_profile", "svbfm_get_profile", "svbfm_host_init_state", "svbfm_host_random_shuffle",
 ]
 
@@ -92,6 +92,7 @@ def lib():
         L.svbfm_mcmc_sweep.argtypes = [vp, C.POINTER(IterStats)]
         L.svbfm_vb_online_epoch.argtypes = [vp, vp, C.c_uint32, C.POINTER(IterStats)]
         L.svbfm_run.argtypes = [vp, C.c_uint32, C.POINTER(IterStats)]
+        L.svbfm_reset.argtypes = [vp]
         L.svbfm_predict.argtypes = [vp, C.c_int32, vp]
         L.svbfm_get_residuals.argtypes = [vp, vp]
         L.svbfm_get_sum_t.argtypes = [vp, C.POINTER(C.c_double)]
@@ -211,6 +212,9 @@ class Engine:
 
     def begin(self):
         self._ck(lib().svbfm_begin(self.h), "svbfm_begin")
+
+    def reset(self):
+        self._ck(lib().svbfm_reset(self.h), "svbfm_reset")
 
     def run(self, n_iter):
         out = (IterStats * n_iter)()

@@ -358,7 +358,7 @@ static int mcmc_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
 
 static int ensure_stats(Engine* E, uint32_t n) {
     if (E->stats_cap >= n) return 0;
-    cudaFree(E->d_stats); E->d_stats = nullptr;
+    cudaFreeAsync(E->d_stats, E->stream); E->d_stats = nullptr;
     if (dev_alloc(E, &E->d_stats, n)) return SVBFM_ERR_OOM;
     E->stats_cap = n;
     return 0;
@@ -437,6 +437,14 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     Engine* E = new Engine();
     E->cfg = *cfg; E->dev = cfg->device; E->D = cfg->num_attribute; E->K = cfg->num_factor;
     E->tile_entries = cfg->tile_entries ? cfg->tile_entries : 1024;
+    {   // stream-ordered allocations from the device's default pool, never handed back to the OS between learn() calls:
+        // ingest allocates and frees tens of GB of scratch; plain cudaMalloc/cudaFree would dominate set_csc
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     ce = cudaStreamCreateWithFlags(&E->own_stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(ce); delete E; return SVBFM_ERR_CUDA; }
     E->stream = E->own_stream;
@@ -481,7 +489,8 @@ void svbfm_destroy(svbfm_t* h) {
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
                     E->d_pred_sum, E->d_stats, E->d_mu_prev, E->d_cpack, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
-    for (void* p : ptrs) cudaFree(p);
+    for (void* p : ptrs) cudaFreeAsync(p, E->stream);
+    cudaStreamSynchronize(E->stream);
     if (E->own_stream) cudaStreamDestroy(E->own_stream);
     delete E;
 }
@@ -533,7 +542,7 @@ int svbfm_set_groups(svbfm_t* h, const uint32_t* attr_group, uint32_t num_groups
     for (uint32_t g = 0; g < num_groups; g++) E->h_n_per_group[g] = (uint32_t)npg[g];
     SV_CUDA(E, copy_sync(E, E->d_group, attr_group, (size_t)E->D * 4, cudaMemcpyHostToDevice));
     void* old[] = {E->d_n_per_group, E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_grp_sums};
-    for (void* p : old) cudaFree(p);
+    for (void* p : old) cudaFreeAsync(p, E->stream);
     E->d_n_per_group = E->d_hyper_w = E->d_hyper_v = E->d_mu_w = E->d_mu_v = E->d_grp_sums = nullptr;
     size_t G = num_groups, K = (size_t)E->K;
     int rc = 0;
@@ -575,12 +584,12 @@ int svbfm_set_csc(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_co
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
     if (is_train) {
         E->n_total = (uint64_t)cnt;
-        cudaFree(E->d_e); cudaFree(E->d_partial); E->d_e = nullptr; E->d_partial = nullptr;
+        cudaFreeAsync(E->d_e, E->stream); cudaFreeAsync(E->d_partial, E->stream); E->d_e = nullptr; E->d_partial = nullptr;
         if (dev_alloc(E, &E->d_e, num_cases)) return SVBFM_ERR_OOM;
         if (dev_alloc(E, &E->d_partial, (size_t)E->n_tiles * 4)) return SVBFM_ERR_OOM;
     } else {
         E->nt_total = (uint64_t)cnt;
-        cudaFree(E->d_pred_test); cudaFree(E->d_pred_sum); E->d_pred_test = nullptr; E->d_pred_sum = nullptr;
+        cudaFreeAsync(E->d_pred_test, E->stream); cudaFreeAsync(E->d_pred_sum, E->stream); E->d_pred_test = nullptr; E->d_pred_sum = nullptr;
         if (dev_alloc(E, &E->d_pred_test, num_cases)) return SVBFM_ERR_OOM;
         if (dev_alloc(E, &E->d_pred_sum, num_cases)) return SVBFM_ERR_OOM;
         SV_CUDA(E, cudaMemsetAsync(E->d_pred_sum, 0, std::max<size_t>(num_cases, 1) * 8, E->stream));
@@ -597,8 +606,8 @@ int svbfm_set_state(svbfm_t* h, double w0_mean, double w0_var, const double* w_m
     SV_CUDA(E, cudaSetDevice(E->dev));
     size_t D = E->D, KD = (size_t)E->K * D;
     double *tm = nullptr, *tv = nullptr;
-    SV_CUDA(E, cudaMalloc((void**)&tm, std::max<size_t>(KD, D) * 8));
-    SV_CUDA(E, cudaMalloc((void**)&tv, std::max<size_t>(KD, D) * 8));
+    SV_CUDA(E, cudaMallocAsync((void**)&tm, std::max<size_t>(KD, D) * 8, E->stream));
+    SV_CUDA(E, cudaMallocAsync((void**)&tv, std::max<size_t>(KD, D) * 8, E->stream));
     cudaStream_t st = E->stream;
     SV_CUDA(E, cudaMemcpyAsync(tm, w_mean, D * 8, cudaMemcpyHostToDevice, st));
     if (w_var) SV_CUDA(E, cudaMemcpyAsync(tv, w_var, D * 8, cudaMemcpyHostToDevice, st));
@@ -610,7 +619,7 @@ int svbfm_set_state(svbfm_t* h, double w0_mean, double w0_var, const double* w_m
         k_pack<<<nblk(KD), 256, 0, st>>>(tm, v_var ? tv : nullptr, KD, E->d_pv);
         SV_CUDA(E, cudaStreamSynchronize(st));
     }
-    cudaFree(tm); cudaFree(tv);
+    cudaFreeAsync(tm, E->stream); cudaFreeAsync(tv, E->stream);
     Scalars sc;
     SV_CUDA(E, copy_sync(E, &sc, E->d_sc, sizeof(sc), cudaMemcpyDeviceToHost));
     sc.w0_mean = w0_mean; sc.w0_var = w0_var;
@@ -633,8 +642,8 @@ int svbfm_get_state(svbfm_t* h, double* w0_mean, double* w0_var, double* w_mean,
     size_t D = E->D, KD = (size_t)E->K * D;
     cudaStream_t st = E->stream;
     double *tm = nullptr, *tv = nullptr;
-    SV_CUDA(E, cudaMalloc((void**)&tm, std::max<size_t>(KD, D) * 8));
-    SV_CUDA(E, cudaMalloc((void**)&tv, std::max<size_t>(KD, D) * 8));
+    SV_CUDA(E, cudaMallocAsync((void**)&tm, std::max<size_t>(KD, D) * 8, E->stream));
+    SV_CUDA(E, cudaMallocAsync((void**)&tv, std::max<size_t>(KD, D) * 8, E->stream));
     k_unpack<<<nblk(D), 256, 0, st>>>(E->d_pw, D, tm, tv);
     if (w_mean) SV_CUDA(E, cudaMemcpyAsync(w_mean, tm, D * 8, cudaMemcpyDeviceToHost, st));
     if (w_var) SV_CUDA(E, cudaMemcpyAsync(w_var, tv, D * 8, cudaMemcpyDeviceToHost, st));
@@ -645,7 +654,7 @@ int svbfm_get_state(svbfm_t* h, double* w0_mean, double* w0_var, double* w_mean,
         if (v_var) SV_CUDA(E, cudaMemcpyAsync(v_var, tv, KD * 8, cudaMemcpyDeviceToHost, st));
         SV_CUDA(E, cudaStreamSynchronize(st));
     }
-    cudaFree(tm); cudaFree(tv);
+    cudaFreeAsync(tm, E->stream); cudaFreeAsync(tv, E->stream);
     Scalars sc;
     SV_CUDA(E, copy_sync(E, &sc, E->d_sc, sizeof(sc), cudaMemcpyDeviceToHost));
     if (w0_mean) *w0_mean = sc.w0_mean;
@@ -720,6 +729,22 @@ int svbfm_begin(svbfm_t* h) {
     return check_launch(E, "begin");
 }
 
+int svbfm_reset(svbfm_t* h) {
+    // back to the state right after svbfm_create (+ comm_init, set_groups): new data and a new initial state may follow.
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E) return SVBFM_ERR_ARG;
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    SV_CUDA(E, cudaStreamSynchronize(E->stream));
+    free_split(E, E->tr); free_split(E, E->te);
+    E->runs.clear();
+    E->begun = false; E->have_state = false; E->rows_reordered = false;
+    SV_CUDA(E, cudaMemsetAsync(E->d_dT, 0, (size_t)E->D * 8, E->stream));
+    SV_CUDA(E, cudaMemsetAsync(E->d_sc, 0, sizeof(Scalars), E->stream));
+    SV_CUDA(E, cudaStreamSynchronize(E->stream));
+    std::vector<uint32_t> g = E->h_group;
+    return svbfm_set_groups(h, g.data(), E->G);     // re-initialises the hyper-parameters (vb.h:707-708 / mcmc.h:1109-1117)
+}
+
 int svbfm_run(svbfm_t* h, uint32_t n_iter, svbfm_iter_stats* out) {
     Engine* E = reinterpret_cast<Engine*>(h);
     if (!E) return SVBFM_ERR_ARG;
@@ -757,13 +782,13 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
         if (dev_alloc(E, &E->d_cnt_col, E->D)) return SVBFM_ERR_OOM;
     }
     if (E->batch_cap < num_batch) {
-        cudaFree(E->d_batch_cnt); cudaFree(E->d_batch_n); E->d_batch_cnt = nullptr; E->d_batch_n = nullptr;
+        cudaFreeAsync(E->d_batch_cnt, E->stream); cudaFreeAsync(E->d_batch_n, E->stream); E->d_batch_cnt = nullptr; E->d_batch_n = nullptr;
         if (dev_alloc(E, &E->d_batch_cnt, num_batch)) return SVBFM_ERR_OOM;
         if (dev_alloc(E, &E->d_batch_n, num_batch)) return SVBFM_ERR_OOM;
         E->batch_cap = num_batch;
     }
     uint32_t* d_boc = nullptr;
-    SV_CUDA(E, cudaMalloc((void**)&d_boc, std::max<size_t>(S.n, 1) * 4));
+    SV_CUDA(E, cudaMallocAsync((void**)&d_boc, std::max<size_t>(S.n, 1) * 4, E->stream));
     SV_CUDA(E, cudaMemcpyAsync(d_boc, batch_of_case, (size_t)S.n * 4, cudaMemcpyHostToDevice, st));
     SV_CUDA(E, cudaMemsetAsync(E->d_batch_cnt, 0, (size_t)num_batch * 8, st));
     if (S.n) {
@@ -808,7 +833,7 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
     DevStats hs;
     cudaError_t ce = cudaMemcpyAsync(&hs, E->d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-    cudaFree(d_boc);
+    cudaFreeAsync(d_boc, E->stream);
     if (ce != cudaSuccess) return fail(E, SVBFM_ERR_CUDA, std::string("vb_online epoch: ") + cudaGetErrorString(ce));
     if (out) {
         memset(out, 0, sizeof(*out));
@@ -847,11 +872,11 @@ int svbfm_get_residuals(svbfm_t* h, double* e) {
     SV_CUDA(E, cudaSetDevice(E->dev));
     uint32_t n = E->tr.n;
     double* tmp = nullptr;
-    SV_CUDA(E, cudaMalloc((void**)&tmp, std::max<size_t>(n, 1) * 8));
+    SV_CUDA(E, cudaMallocAsync((void**)&tmp, std::max<size_t>(n, 1) * 8, E->stream));
     k_unpermute<<<nblk(n), 256, 0, E->stream>>>(E->d_e, E->tr.perm, n, tmp);
     SV_CUDA(E, cudaMemcpyAsync(e, tmp, (size_t)n * 8, cudaMemcpyDeviceToHost, E->stream));
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
-    cudaFree(tmp);
+    cudaFreeAsync(tmp, E->stream);
     return check_launch(E, "get_residuals");
 }
 

@@ -11,6 +11,8 @@
 // sweep.
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include "svbfm_internal.h"
 
@@ -163,25 +165,25 @@ static int bits_for(uint64_t n) {
 // stable sort of (key, value) pairs by key; returns device arrays (caller frees with cudaFree)
 static int sort_pairs(Engine* E, const uint32_t* keys_in, const uint32_t* vals_in, uint64_t n, uint64_t key_range,
                       uint32_t** keys_out, uint32_t** vals_out) {
-    SV_CUDA(E, cudaMalloc((void**)keys_out, std::max<uint64_t>(n, 1) * 4));
-    SV_CUDA(E, cudaMalloc((void**)vals_out, std::max<uint64_t>(n, 1) * 4));
+    SV_CUDA(E, cudaMallocAsync((void**)keys_out, std::max<uint64_t>(n, 1) * 4, E->stream));
+    SV_CUDA(E, cudaMallocAsync((void**)vals_out, std::max<uint64_t>(n, 1) * 4, E->stream));
     if (n == 0) return 0;
     size_t tmp_bytes = 0;
     int end_bit = bits_for(key_range);
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, *keys_out, vals_in, *vals_out, (int64_t)n, 0, end_bit, E->stream);
     void* tmp = nullptr;
-    SV_CUDA(E, cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    SV_CUDA(E, cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, E->stream));
     cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, *keys_out, vals_in, *vals_out, (int64_t)n, 0, end_bit, E->stream);
     cudaError_t e2 = cudaStreamSynchronize(E->stream);
-    cudaFree(tmp);
+    cudaFreeAsync(tmp, E->stream);
     if (e != cudaSuccess || e2 != cudaSuccess) return fail(E, SVBFM_ERR_CUDA, std::string("radix sort: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
     return 0;
 }
 
 void free_split(Engine* E, DevSplit& S) {
     (void)E;
-    cudaFree(S.colptr); cudaFree(S.crow); cudaFree(S.cval); cudaFree(S.rowptr); cudaFree(S.rcol); cudaFree(S.rval);
-    cudaFree(S.y); cudaFree(S.perm); cudaFree(S.cother); cudaFree(S.cother_val);
+    cudaFreeAsync(S.colptr, E->stream); cudaFreeAsync(S.crow, E->stream); cudaFreeAsync(S.cval, E->stream); cudaFreeAsync(S.rowptr, E->stream); cudaFreeAsync(S.rcol, E->stream); cudaFreeAsync(S.rval, E->stream);
+    cudaFreeAsync(S.y, E->stream); cudaFreeAsync(S.perm, E->stream); cudaFreeAsync(S.cother, E->stream); cudaFreeAsync(S.cother_val, E->stream);
     S = DevSplit();
 }
 
@@ -189,6 +191,15 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
                  const float* x, const float* target) {
     cudaStream_t st = E->stream;
     free_split(E, S);
+    const bool timing = getenv("SVBFM_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(st);
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[svbfm ingest %s] %-28s %8.2f ms\n", is_train ? "train" : "test", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     if (ncols > E->D) return fail(E, SVBFM_ERR_ARG, "set_csc: num_cols exceeds num_attribute");
     if (colptr[0] != 0) return fail(E, SVBFM_ERR_ARG, "set_csc: colptr[0] != 0");
     for (uint32_t j = 0; j < ncols; j++)
@@ -206,14 +217,14 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     if (dev_alloc(E, &S.crow, nnz)) return SVBFM_ERR_OOM;
     if (dev_alloc(E, &S.y, n)) return SVBFM_ERR_OOM;
     float* d_x = nullptr;
-    SV_CUDA(E, cudaMalloc((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4));
+    SV_CUDA(E, cudaMallocAsync((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4, E->stream));
     SV_CUDA(E, cudaMemcpyAsync(S.colptr, S.h_colptr.data(), ((size_t)S.ncols_ext + 1) * 8, cudaMemcpyHostToDevice, st));
     SV_CUDA(E, cudaMemcpyAsync(S.crow, case_id, nnz * 4, cudaMemcpyHostToDevice, st));
     SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, st));
     SV_CUDA(E, cudaMemcpyAsync(S.y, target, (size_t)n * 4, cudaMemcpyHostToDevice, st));
 
     uint32_t* d_flags = nullptr;   // [0] any x != 1  [1] case id out of range  [2] duplicate feature in a case  [3] non-uniform  [4] perm not identity
-    SV_CUDA(E, cudaMalloc((void**)&d_flags, 8 * 4));
+    SV_CUDA(E, cudaMallocAsync((void**)&d_flags, 8 * 4, E->stream));
     SV_CUDA(E, cudaMemsetAsync(d_flags, 0, 8 * 4, st));
     if (nnz) {
         k_any_not_one<<<std::min<unsigned>(nblk(nnz), 148 * 16), 256, 0, st>>>(d_x, nnz, d_flags + 0);
@@ -221,8 +232,8 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     }
     // CSC -> CSR: feature id per entry, stable sort by case id
     uint32_t *d_colof = nullptr, *d_idx = nullptr, *d_skeys = nullptr, *d_sidx = nullptr;
-    SV_CUDA(E, cudaMalloc((void**)&d_colof, std::max<uint64_t>(nnz, 1) * 4));
-    SV_CUDA(E, cudaMalloc((void**)&d_idx, std::max<uint64_t>(nnz, 1) * 4));
+    SV_CUDA(E, cudaMallocAsync((void**)&d_colof, std::max<uint64_t>(nnz, 1) * 4, E->stream));
+    SV_CUDA(E, cudaMallocAsync((void**)&d_idx, std::max<uint64_t>(nnz, 1) * 4, E->stream));
     if (nnz) {
         k_col_of_entry<<<nblk(nnz), 256, 0, st>>>(S.colptr, ncols, nnz, d_colof);
         k_iota<<<nblk(nnz), 256, 0, st>>>(d_idx, nnz);
@@ -230,34 +241,36 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     uint32_t h_flags[8];
     SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
     SV_CUDA(E, cudaStreamSynchronize(st));
-    if (h_flags[1]) { cudaFree(d_x); cudaFree(d_flags); cudaFree(d_colof); cudaFree(d_idx); return fail(E, SVBFM_ERR_ARG, "set_csc: case id out of range"); }
+    if (h_flags[1]) { cudaFreeAsync(d_x, E->stream); cudaFreeAsync(d_flags, E->stream); cudaFreeAsync(d_colof, E->stream); cudaFreeAsync(d_idx, E->stream); return fail(E, SVBFM_ERR_ARG, "set_csc: case id out of range"); }
     S.all_ones = (h_flags[0] == 0);
+    mark("validate + H2D + col_of_entry");
     if (int r = sort_pairs(E, S.crow, d_idx, nnz, std::max<uint32_t>(n, 1), &d_skeys, &d_sidx)) return r;
-    cudaFree(d_idx);
+    cudaFreeAsync(d_idx, E->stream);
     uint64_t* d_rowptr = nullptr;
-    SV_CUDA(E, cudaMalloc((void**)&d_rowptr, ((size_t)n + 1) * 8));
+    SV_CUDA(E, cudaMallocAsync((void**)&d_rowptr, ((size_t)n + 1) * 8, E->stream));
     k_rowptr_from_sorted<<<nblk((uint64_t)n + 1), 256, 0, st>>>(d_skeys, nnz, n, d_rowptr);
-    cudaFree(d_skeys);
+    cudaFreeAsync(d_skeys, E->stream);
     uint32_t* d_rcol = nullptr; float* d_rval = nullptr;
-    SV_CUDA(E, cudaMalloc((void**)&d_rcol, std::max<uint64_t>(nnz, 1) * 4));
-    if (!S.all_ones) SV_CUDA(E, cudaMalloc((void**)&d_rval, std::max<uint64_t>(nnz, 1) * 4));
+    SV_CUDA(E, cudaMallocAsync((void**)&d_rcol, std::max<uint64_t>(nnz, 1) * 4, E->stream));
+    if (!S.all_ones) SV_CUDA(E, cudaMallocAsync((void**)&d_rval, std::max<uint64_t>(nnz, 1) * 4, E->stream));
     if (nnz) {
         k_gather_u32<<<nblk(nnz), 256, 0, st>>>(d_colof, d_sidx, nnz, d_rcol);
         if (!S.all_ones) k_gather_f32<<<nblk(nnz), 256, 0, st>>>(d_x, d_sidx, nnz, d_rval);
     }
-    cudaFree(d_sidx); cudaFree(d_colof);
+    cudaFreeAsync(d_sidx, E->stream); cudaFreeAsync(d_colof, E->stream);
+    mark("sort by case + CSR gather");
 
     // per-case scan: duplicates, uniform length, need[]
     uint32_t* d_need = nullptr;
     if (is_train) {
-        SV_CUDA(E, cudaMalloc((void**)&d_need, std::max<uint32_t>(S.ncols_ext, 1) * 4));
+        SV_CUDA(E, cudaMallocAsync((void**)&d_need, std::max<uint32_t>(S.ncols_ext, 1) * 4, E->stream));
         SV_CUDA(E, cudaMemsetAsync(d_need, 0, std::max<uint32_t>(S.ncols_ext, 1) * 4, st));
     }
     if (n) k_scan_rows<<<nblk(n), 256, 0, st>>>(d_rowptr, d_rcol, n, d_need, d_flags + 2);
     SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
     SV_CUDA(E, cudaStreamSynchronize(st));
     if (h_flags[2]) {
-        cudaFree(d_x); cudaFree(d_flags); cudaFree(d_rowptr); cudaFree(d_rcol); cudaFree(d_rval); cudaFree(d_need);
+        cudaFreeAsync(d_x, E->stream); cudaFreeAsync(d_flags, E->stream); cudaFreeAsync(d_rowptr, E->stream); cudaFreeAsync(d_rcol, E->stream); cudaFreeAsync(d_rval, E->stream); cudaFreeAsync(d_need, E->stream);
         return fail(E, SVBFM_ERR_DATA, "set_csc: a feature id occurs twice in one case; not supported");
     }
     bool uniform = (n > 0) && (h_flags[3] == 0);
@@ -271,7 +284,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         std::vector<uint32_t> need(S.ncols_ext);
         SV_CUDA(E, cudaMemcpyAsync(need.data(), d_need, (size_t)S.ncols_ext * 4, cudaMemcpyDeviceToHost, st));
         SV_CUDA(E, cudaStreamSynchronize(st));
-        cudaFree(d_need);
+        cudaFreeAsync(d_need, E->stream);
         E->runs.clear();
         uint32_t run_start = 0;
         for (uint32_t j = 0; j < S.ncols_ext; j++) {
@@ -283,73 +296,75 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         }
         if (S.ncols_ext > 0) { Run r; r.col_begin = run_start; r.col_end = S.ncols_ext; E->runs.push_back(r); }
         for (auto& r : E->runs) r.nnz = S.h_colptr[r.col_end] - S.h_colptr[r.col_begin];
+        mark("row scan + field runs");
 
         // ---- case re-ordering: device order = order of the cases inside run 0 (when run 0 holds every case once)
         bool reorder = !(E->cfg.flags & SVBFM_FLAG_NO_ROW_REORDER) && !E->runs.empty() && E->runs[0].nnz == n && n > 0 && nnz > 0;
         if (reorder) {
             uint32_t *d_perm = nullptr, *d_inv = nullptr;
-            SV_CUDA(E, cudaMalloc((void**)&d_perm, (size_t)n * 4));
-            SV_CUDA(E, cudaMalloc((void**)&d_inv, (size_t)n * 4));
+            SV_CUDA(E, cudaMallocAsync((void**)&d_perm, (size_t)n * 4, E->stream));
+            SV_CUDA(E, cudaMallocAsync((void**)&d_inv, (size_t)n * 4, E->stream));
             SV_CUDA(E, cudaMemcpyAsync(d_perm, S.crow + S.h_colptr[E->runs[0].col_begin], (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
             k_invert_perm<<<nblk(n), 256, 0, st>>>(d_perm, n, d_inv, d_flags + 4);
             SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
             SV_CUDA(E, cudaStreamSynchronize(st));
-            cudaFree(d_inv);
+            cudaFreeAsync(d_inv, E->stream);
             if (h_flags[4]) {
                 // new CSR = cases gathered in device order
                 uint64_t *d_len = nullptr, *d_newptr = nullptr;
-                SV_CUDA(E, cudaMalloc((void**)&d_len, ((size_t)n + 1) * 8));
-                SV_CUDA(E, cudaMalloc((void**)&d_newptr, ((size_t)n + 1) * 8));
+                SV_CUDA(E, cudaMallocAsync((void**)&d_len, ((size_t)n + 1) * 8, E->stream));
+                SV_CUDA(E, cudaMallocAsync((void**)&d_newptr, ((size_t)n + 1) * 8, E->stream));
                 k_row_lengths_perm<<<nblk((uint64_t)n + 1), 256, 0, st>>>(d_rowptr, d_perm, n, d_len);
                 size_t tmp_bytes = 0;
                 cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_newptr, (int64_t)n + 1, st);
                 void* tmp = nullptr;
-                SV_CUDA(E, cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+                SV_CUDA(E, cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, E->stream));
                 cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_len, d_newptr, (int64_t)n + 1, st);
                 uint32_t *d_ncol = nullptr, *d_nrow = nullptr; float* d_nval = nullptr;
-                SV_CUDA(E, cudaMalloc((void**)&d_ncol, nnz * 4));
-                SV_CUDA(E, cudaMalloc((void**)&d_nrow, nnz * 4));
-                if (!S.all_ones) SV_CUDA(E, cudaMalloc((void**)&d_nval, nnz * 4));
+                SV_CUDA(E, cudaMallocAsync((void**)&d_ncol, nnz * 4, E->stream));
+                SV_CUDA(E, cudaMallocAsync((void**)&d_nrow, nnz * 4, E->stream));
+                if (!S.all_ones) SV_CUDA(E, cudaMallocAsync((void**)&d_nval, nnz * 4, E->stream));
                 k_permute_rows<<<nblk(n), 256, 0, st>>>(d_rowptr, d_rcol, d_rval, d_perm, n, d_newptr, d_ncol, d_nval, d_nrow);
                 SV_CUDA(E, cudaStreamSynchronize(st));
-                cudaFree(tmp); cudaFree(d_len);
-                cudaFree(d_rowptr); cudaFree(d_rcol); cudaFree(d_rval);
+                cudaFreeAsync(tmp, E->stream); cudaFreeAsync(d_len, E->stream);
+                cudaFreeAsync(d_rowptr, E->stream); cudaFreeAsync(d_rcol, E->stream); cudaFreeAsync(d_rval, E->stream);
                 d_rowptr = d_newptr; d_rcol = d_ncol; d_rval = d_nval;
                 // new CSC = stable sort of the new CSR entries by feature id (case ids stay ascending per column)
                 uint32_t *d_eidx = nullptr, *d_k2 = nullptr, *d_v2 = nullptr;
-                SV_CUDA(E, cudaMalloc((void**)&d_eidx, nnz * 4));
+                SV_CUDA(E, cudaMallocAsync((void**)&d_eidx, nnz * 4, E->stream));
                 k_iota<<<nblk(nnz), 256, 0, st>>>(d_eidx, nnz);
                 if (int r = sort_pairs(E, d_rcol, d_eidx, nnz, std::max<uint32_t>(ncols, 1), &d_k2, &d_v2)) return r;
-                cudaFree(d_eidx); cudaFree(d_k2);
+                cudaFreeAsync(d_eidx, E->stream); cudaFreeAsync(d_k2, E->stream);
                 k_gather_u32<<<nblk(nnz), 256, 0, st>>>(d_nrow, d_v2, nnz, S.crow);
                 if (!S.all_ones) {
                     float* d_cv = nullptr;
-                    SV_CUDA(E, cudaMalloc((void**)&d_cv, nnz * 4));
+                    SV_CUDA(E, cudaMallocAsync((void**)&d_cv, nnz * 4, E->stream));
                     k_gather_f32<<<nblk(nnz), 256, 0, st>>>(d_rval, d_v2, nnz, d_cv);
                     SV_CUDA(E, cudaStreamSynchronize(st));
-                    cudaFree(d_x); d_x = d_cv;
+                    cudaFreeAsync(d_x, E->stream); d_x = d_cv;
                 }
                 SV_CUDA(E, cudaStreamSynchronize(st));
-                cudaFree(d_v2); cudaFree(d_nrow);
+                cudaFreeAsync(d_v2, E->stream); cudaFreeAsync(d_nrow, E->stream);
                 float* d_y2 = nullptr;
-                SV_CUDA(E, cudaMalloc((void**)&d_y2, (size_t)n * 4));
+                SV_CUDA(E, cudaMallocAsync((void**)&d_y2, (size_t)n * 4, E->stream));
                 k_permute_f32<<<nblk(n), 256, 0, st>>>(S.y, d_perm, n, d_y2);
                 SV_CUDA(E, cudaStreamSynchronize(st));
-                cudaFree(S.y); S.y = d_y2;
+                cudaFreeAsync(S.y, E->stream); S.y = d_y2;
                 S.perm = d_perm; E->dev_bytes += (size_t)n * 4;
                 E->rows_reordered = true;
             } else {
-                cudaFree(d_perm);
+                cudaFreeAsync(d_perm, E->stream);
             }
         }
     }
-    cudaFree(d_flags);
+    mark("case re-ordering + CSC rebuild");
+    cudaFreeAsync(d_flags, E->stream);
     // keep
     S.rcol = d_rcol; E->dev_bytes += nnz * 4;
     S.rval = d_rval; if (d_rval) E->dev_bytes += nnz * 4;
-    if (S.all_ones) { cudaFree(d_x); S.cval = nullptr; } else { S.cval = d_x; E->dev_bytes += nnz * 4; }
+    if (S.all_ones) { cudaFreeAsync(d_x, E->stream); S.cval = nullptr; } else { S.cval = d_x; E->dev_bytes += nnz * 4; }
     S.uniformF = F;
-    if (F > 0) { cudaFree(d_rowptr); S.rowptr = nullptr; } else { S.rowptr = d_rowptr; E->dev_bytes += ((size_t)n + 1) * 8; }
+    if (F > 0) { cudaFreeAsync(d_rowptr, E->stream); S.rowptr = nullptr; } else { S.rowptr = d_rowptr; E->dev_bytes += ((size_t)n + 1) * 8; }
 
     if (is_train && F == 2 && nnz) {
         if (dev_alloc(E, &S.cother, nnz)) return SVBFM_ERR_OOM;
@@ -357,6 +372,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         k_other_of_entry<<<nblk(nnz), 256, 0, st>>>(S.colptr, ncols, nnz, S.crow, S.rcol, S.rval, S.cother, S.cother_val);
         SV_CUDA(E, cudaStreamSynchronize(st));
     }
+    mark("other-feature arrays");
     if (is_train) {
         // ---- warp tiles (host). A tile = <= T consecutive CSC entries of ONE column; a column's tiles are consecutive
         // tile ids (fixed summation order). Runs whose case ids are not sequential ("gather runs") read e_i at random:
@@ -383,15 +399,15 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         std::vector<uint64_t> cuts;   // [cut_cols][NB+1] absolute entry positions
         if (!cut_cols.empty()) {
             uint32_t* d_cc = nullptr; uint64_t* d_cuts = nullptr;
-            SV_CUDA(E, cudaMalloc((void**)&d_cc, cut_cols.size() * 4));
-            SV_CUDA(E, cudaMalloc((void**)&d_cuts, cut_cols.size() * (size_t)(NB + 1) * 8));
+            SV_CUDA(E, cudaMallocAsync((void**)&d_cc, cut_cols.size() * 4, E->stream));
+            SV_CUDA(E, cudaMallocAsync((void**)&d_cuts, cut_cols.size() * (size_t)(NB + 1) * 8, E->stream));
             SV_CUDA(E, cudaMemcpyAsync(d_cc, cut_cols.data(), cut_cols.size() * 4, cudaMemcpyHostToDevice, st));
             dim3 grid((unsigned)cut_cols.size(), (NB + 1 + 63) / 64);
             k_block_cuts<<<grid, 64, 0, st>>>(d_cc, S.colptr, S.crow, block_cases, NB, d_cuts);
             cuts.resize(cut_cols.size() * (size_t)(NB + 1));
             SV_CUDA(E, cudaMemcpyAsync(cuts.data(), d_cuts, cuts.size() * 8, cudaMemcpyDeviceToHost, st));
             SV_CUDA(E, cudaStreamSynchronize(st));
-            cudaFree(d_cc); cudaFree(d_cuts);
+            cudaFreeAsync(d_cc, E->stream); cudaFreeAsync(d_cuts, E->stream);
         }
         size_t cc = 0;
         for (auto& r : E->runs) {
@@ -427,8 +443,8 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         col_tile0[S.ncols_ext] = (uint32_t)tile_col.size();
         E->n_tiles = (uint32_t)tile_col.size();
         E->n_heavy = (uint32_t)heavy.size();
-        cudaFree(E->d_tile_col); cudaFree(E->d_tile_begin); cudaFree(E->d_col_tile0); cudaFree(E->d_heavy_cols);
-        cudaFree(E->d_tile_len); cudaFree(E->d_exec_order);
+        cudaFreeAsync(E->d_tile_col, E->stream); cudaFreeAsync(E->d_tile_begin, E->stream); cudaFreeAsync(E->d_col_tile0, E->stream); cudaFreeAsync(E->d_heavy_cols, E->stream);
+        cudaFreeAsync(E->d_tile_len, E->stream); cudaFreeAsync(E->d_exec_order, E->stream);
         E->d_tile_col = nullptr; E->d_tile_begin = nullptr; E->d_col_tile0 = nullptr; E->d_heavy_cols = nullptr;
         E->d_tile_len = nullptr; E->d_exec_order = nullptr;
         if (dev_alloc(E, &E->d_tile_col, tile_col.size())) return SVBFM_ERR_OOM;
@@ -445,6 +461,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         SV_CUDA(E, cudaMemcpyAsync(E->d_heavy_cols, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice, st));
         SV_CUDA(E, cudaStreamSynchronize(st));
     }
+    mark("tiles + exec order");
     SV_CUDA(E, cudaGetLastError());
     return 0;
 }

@@ -17,6 +17,9 @@
 #include <vector>
 #include "../../include/svbfm.h"
 
+// null-tolerant stream-ordered free (like cudaFree(nullptr))
+#define cudaFreeAsync(p, s) ((p) ? cudaFreeAsync((p), (s)) : cudaSuccess)
+
 namespace svb {
 
 struct ColPack;
@@ -170,7 +173,7 @@ int fail(Engine* E, int code, const std::string& msg);
 template <typename T>
 int dev_alloc(Engine* E, T** p, size_t count) {
     if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    cudaError_t e = cudaMallocAsync((void**)p, count * sizeof(T), E->stream);
     if (e != cudaSuccess) return fail(E, SVBFM_ERR_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     E->dev_bytes += count * sizeof(T);
     return 0;

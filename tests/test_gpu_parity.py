@@ -178,3 +178,15 @@ def test_fused_equals_unfused_schedule(built, monkeypatch):
             assert all(rel(x, y) < 1e-10 for x, y in zip(a, b)), (a, b)
         monkeypatch.delenv("SVBFM_NO_FUSE", raising=False)
         run_vb(tr, te, K=3, iters=4)
+
+
+def test_reset_reuses_handle(built):
+    """svbfm_reset: a second learn() on the same handle (same data, same initial state) repeats the first one."""
+    tr, te = two_field(10000, 1000, 200, 150, seed=81)
+    L = make_learner("vb", tr, te, 3, num_iter=3)
+    h1 = [(s.test_rmse, s.free_energy) for s in L.learn(to_csc(tr), to_csc(te))]
+    E = L.engine
+    E.reset()
+    E.set_csc(sv.TRAIN, to_csc(tr)); E.set_csc(sv.TEST, to_csc(te)); E.set_state(L._state); E.begin()
+    h2 = [(s.test_rmse, s.free_energy) for s in E.run(3)]
+    assert h1 == h2
