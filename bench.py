@@ -330,12 +330,14 @@ def main():
     achieved = (N_global / world) * K * ALGO_BYTES_PER_RATING_K / (sweep_per_step * 1e-3) / 1e9     # per GPU
     n_local = hi - lo
     fused = bool(info0.get("fused_schedule"))
-    # own algorithmic bytes per rating*k: fused = stream (cother 4 + e 8r+8w) + gather pass 1 (crow 4 + cother 4 + e 8)
-    own_bytes = 36.0 if fused else 80.0
-    # per-class model bytes per entry under SURVEY's 216 B accounting: pass 1 = 8 B CSC entry + 40 B state, pass 2 = 40 B state write
-    model_bytes = {"reduce_v": 48.0, "apply_v": 40.0, "fused_stream_v": 128.0, "fused_flush_v": 80.0}
-    kname = {"reduce_v": "k_sweep_reduce<VB_V> (pass 1" + (", gather run" if fused else "") + ")", "apply_v": "k_row_apply<VB_V> (pass 2)",
-             "fused_stream_v": "k_fused_stream<VB_V> (pending pass 2 of both runs + pass 1 of run 0)", "fused_flush_v": "k_fused_stream<flush>"}
+    # own algorithmic bytes per rating*k: stream schedule = per field pass (other-column id 4 + e 8 r + 8 w) x 2 fields
+    own_bytes = 40.0 if fused else 80.0
+    # per-class model bytes per entry under SURVEY's 216 B accounting: pass 1 = 8 B CSC entry + 40 B state, pass 2 = 40 B state write,
+    # one stream pass = one field's share of the 216 B (88 B field sweep + half of the 40 B q-rebuild)
+    model_bytes = {"reduce_v": 48.0, "apply_v": 40.0, "stream_v_field0": 108.0, "stream_v_field1": 108.0}
+    kname = {"reduce_v": "k_sweep_reduce<VB_V> (pass 1)", "apply_v": "k_row_apply<VB_V> (pass 2)",
+             "stream_v_field0": "k_stream<V> over field 0 (pending updates + pass 1, residual copy in case order)",
+             "stream_v_field1": "k_stream<V> over field 1 (pending updates + pass 1, residual copy in field-1 entry order)"}
     dom = max((k for k in model_bytes if prof[k]["launches"]), key=lambda k: prof[k]["ms"], default="reduce_v")
     dk = prof[dom]
     dk_avg = dk["ms"] / max(dk["launches"], 1)

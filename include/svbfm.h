@@ -139,6 +139,9 @@ int svbfm_predict(svbfm_t* h, int32_t split, double* out /*[num_cases]*/);
 int svbfm_get_residuals(svbfm_t* h, double* e /*[num_cases of train]*/);
 /* sum_i T_i (vb.h:207-312 gives T_i; only its sum enters alpha and the free energy) */
 int svbfm_get_sum_t(svbfm_t* h, double* sum_t);
+/* stream schedule self-check: max |e2[p] - e[case of p]| between the two residual copies (0.0 expected: the copies
+ * are updated with identical arithmetic); 0.0 when the schedule is not in use */
+int svbfm_copies_max_diff(svbfm_t* h, double* max_abs_diff);
 
 /* introspection for DESIGN/bench: number of field runs, tiles, kernel launches issued so far */
 typedef struct svbfm_info {
@@ -151,14 +154,15 @@ typedef struct svbfm_info {
     uint64_t train_nnz;
     uint32_t rows_reordered;
     uint32_t world_size;
-    uint32_t fused_schedule;   /* 1 when the two-field fused schedule (pass 2 folded into the next pass 1) is in use */
+    uint32_t fused_schedule;   /* 1 when the two-field stream schedule (two residual copies, k_stream) is in use */
     uint32_t reserved;
 } svbfm_info;
 int svbfm_get_info(svbfm_t* h, svbfm_info* out);
 /* per-kernel-class device time (CUDA events on the launching stream), for bench.py's roofline block.
  * classes: 0 reduce_v (k_sweep_reduce), 1 combine+finalize_v, 2 apply_v, 3 reduce_w, 4 combine+finalize_w, 5 apply_w,
- *          6 fused_stream_v (k_fused_stream: pending pass 2 + pass 1 of run 0), 7 fused_flush_v */
-#define SVBFM_PROFILE_CLASSES 8
+ *          stream schedule (k_stream): 6 stream_v of the first field, 8 stream_v of the second field, 9 stream_w (both fields),
+ *          7 the two flush passes at the end of an iteration */
+#define SVBFM_PROFILE_CLASSES 10
 int svbfm_set_profile(svbfm_t* h, int32_t enabled);
 int svbfm_get_profile(svbfm_t* h, double ms[SVBFM_PROFILE_CLASSES], uint64_t launches[SVBFM_PROFILE_CLASSES]); /* reads and resets */
 /* run on an externally owned CUDA stream (cudaStream_t); NULL restores the handle's own stream */

@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "svbfm_create", "svbfm_destroy", "svbfm_last_error", "svbfm_abi_version", "svbfm_comm_get_unique_id",
     "svbfm_comm_init", "svbfm_set_groups", "svbfm_set_csc", "svbfm_set_state", "svbfm_get_state",
     "svbfm_get_hyper", "svbfm_set_hyper", "svbfm_begin", "svbfm_vb_sweep", "svbfm_mcmc_sweep",
-    "svbfm_vb_online_epoch", "svbfm_run", "svbfm_reset", "svbfm_predict", "svbfm_get_residuals", "svbfm_get_sum_t",
+    "svbfm_vb_online_epoch", "svbfm_run", "svbfm_reset", "svbfm_predict", "svbfm_get_residuals", "svbfm_get_sum_t", "svbfm_copies_max_diff",
     "svbfm_get_info", "svbfm_set_stream", "svbfm_set_profile", "svbfm_get_profile", "svbfm_host_init_state", "svbfm_host_random_shuffle",
 ]
 
@@ -96,6 +96,7 @@ def lib():
         L.svbfm_predict.argtypes = [vp, C.c_int32, vp]
         L.svbfm_get_residuals.argtypes = [vp, vp]
         L.svbfm_get_sum_t.argtypes = [vp, C.POINTER(C.c_double)]
+        L.svbfm_copies_max_diff.argtypes = [vp, C.POINTER(C.c_double)]
         L.svbfm_get_info.argtypes = [vp, C.POINTER(Info)]
         L.svbfm_set_stream.argtypes = [vp, vp]
         L.svbfm_set_profile.argtypes = [vp, C.c_int32]
@@ -213,6 +214,11 @@ class Engine:
     def begin(self):
         self._ck(lib().svbfm_begin(self.h), "svbfm_begin")
 
+    def copies_max_diff(self):
+        d = C.c_double(0.0)
+        self._ck(lib().svbfm_copies_max_diff(self.h, C.byref(d)), "svbfm_copies_max_diff")
+        return d.value
+
     def reset(self):
         self._ck(lib().svbfm_reset(self.h), "svbfm_reset")
 
@@ -252,10 +258,10 @@ class Engine:
         self._ck(lib().svbfm_set_profile(self.h, int(on)), "svbfm_set_profile")
 
     def get_profile(self):
-        ms = np.zeros(8)
-        cnt = np.zeros(8, dtype=np.uint64)
+        names = ["reduce_v", "finalize_v", "apply_v", "reduce_w", "finalize_w", "apply_w", "stream_v_field0", "stream_flush", "stream_v_field1", "stream_w"]
+        ms = np.zeros(len(names))     # SVBFM_PROFILE_CLASSES
+        cnt = np.zeros(len(names), dtype=np.uint64)
         self._ck(lib().svbfm_get_profile(self.h, _p(ms), _p(cnt)), "svbfm_get_profile")
-        names = ["reduce_v", "finalize_v", "apply_v", "reduce_w", "finalize_w", "apply_w", "fused_stream_v", "fused_flush_v"]
         return {n: dict(ms=float(m), launches=int(c)) for n, m, c in zip(names, ms, cnt)}
 
     def info(self):

@@ -52,6 +52,9 @@ int allreduce(Engine* E, void* buf, size_t count, int dtype, int op) {
     return 0;
 }
 }  // namespace svb
+namespace svb {
+int stream_tile_cols(Engine* E);
+}
 static inline int allreduce_sum_f64(Engine* E, double* buf, size_t n) { return allreduce(E, buf, n, 8 /*ncclDouble*/, 0 /*ncclSum*/); }
 
 // ---------------------------------------------------------------------------------------------- helpers
@@ -98,30 +101,53 @@ struct ProfScope {
     }
 };
 
+// stream schedule: what a finalize has to leave behind for the passes that follow (kernels.cuh FinalizeArgs)
+struct RecPlan {
+    int run = -1;                  // 0 / 1: implicit tiles of that run (span layout); -1: explicit tiles
+    int rec_mode = 0;
+    const double2* p_next = nullptr;
+    const double2* p_prev = nullptr;
+};
+
 // tiles -> column sums (-> allreduce when sharded) -> per-column update
 template <int KIND>
-static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, int pack_mode = 0) {
+static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, const RecPlan* rp = nullptr) {
     cudaStream_t st = E->stream;
     constexpr bool IS_V = (KIND == KIND_VB_V || KIND == KIND_MC_V || KIND == KIND_VBO_V);
     double2* pf = IS_V ? E->d_pv + (size_t)f * E->D : E->d_pw;
     (void)batch;
     ProfScope ps(E, (IS_V ? 0 : 3) + 1);
-    uint32_t nheavy = r.heavy_end - r.heavy_begin;
-    if (nheavy) { k_combine_heavy<<<nheavy, 128, 0, st>>>(E->d_heavy_cols, r.heavy_begin, E->d_col_tile0, E->d_partial, E->d_colsum); LAUNCHED(E); }
     uint32_t ncols = r.col_end - r.col_begin;
     bool from_colsum = false;
-    if (E->world > 1) {
-        k_combine_light<<<nblk(ncols), 256, 0, st>>>(r.col_begin, r.col_end, E->d_col_tile0, E->d_partial, E->d_colsum); LAUNCHED(E);
-        if (int rc = allreduce_sum_f64(E, E->d_colsum + (size_t)r.col_begin * 4, (size_t)ncols * 4)) return rc;
-        from_colsum = true;
+    SpanView sp{nullptr, 0, E->ts_shift};
+    const double* partial = E->d_partial;
+    if (rp && rp->run >= 0) {
+        sp.colptr = E->tr.colptr; sp.entry0 = E->tr.h_colptr[r.col_begin];
+        partial = E->d_partial + (rp->run ? (size_t)E->s_ntiles[0] * 8 : 0);
+        uint32_t nh = E->span_heavy_n[rp->run], h0 = rp->run ? E->span_heavy_n[0] : 0;
+        if (nh) { k_combine_span<<<nh, 128, 0, st>>>(E->d_span_heavy, h0, sp, partial, E->d_colsum); LAUNCHED(E); }
+        if (E->world > 1) {
+            k_combine_light_span<<<nblk(ncols), 256, 0, st>>>(r.col_begin, r.col_end, sp, partial, E->d_colsum); LAUNCHED(E);
+            if (int rc = allreduce_sum_f64(E, E->d_colsum + (size_t)r.col_begin * 4, (size_t)ncols * 4)) return rc;
+            from_colsum = true;
+        }
+    } else {
+        uint32_t nheavy = r.heavy_end - r.heavy_begin;
+        if (nheavy) { k_combine_heavy<<<nheavy, 128, 0, st>>>(E->d_heavy_cols, r.heavy_begin, E->d_col_tile0, E->d_partial, E->d_colsum); LAUNCHED(E); }
+        if (E->world > 1) {
+            k_combine_light<<<nblk(ncols), 256, 0, st>>>(r.col_begin, r.col_end, E->d_col_tile0, E->d_partial, E->d_colsum); LAUNCHED(E);
+            if (int rc = allreduce_sum_f64(E, E->d_colsum + (size_t)r.col_begin * 4, (size_t)ncols * 4)) return rc;
+            from_colsum = true;
+        }
     }
     FinalizeArgs fa{};
     fa.c0 = r.col_begin; fa.c1 = r.col_end; fa.f = IS_V ? f : -1; fa.K = E->K;
-    fa.col_tile0 = E->d_col_tile0; fa.partial = E->d_partial; fa.colsum = E->d_colsum; fa.from_colsum = from_colsum;
+    fa.col_tile0 = E->d_col_tile0; fa.partial = partial; fa.colsum = E->d_colsum; fa.from_colsum = from_colsum;
     fa.pf = pf; fa.group = E->d_group; fa.hyper = IS_V ? E->d_hyper_v : E->d_hyper_w;
-    fa.hyper_mu = IS_V ? E->d_mu_v : E->d_mu_w; fa.sc = E->d_sc; fa.delta = E->d_delta; fa.mu_prev = E->d_mu_prev; fa.dT = E->d_dT;
+    fa.hyper_mu = IS_V ? E->d_mu_v : E->d_mu_w; fa.sc = E->d_sc; fa.delta = E->d_delta; fa.dT = E->d_dT;
     fa.seed = E->cfg.seed; fa.do_sample = E->cfg.do_sample;
-    fa.cpack = pack_mode ? E->d_cpack : nullptr; fa.pack_mode = pack_mode; fa.D = E->D;
+    fa.span = sp;
+    if (rp) { fa.cpack = E->d_cpack; fa.opack = E->d_opack; fa.rec_mode = rp->rec_mode; fa.p_next = rp->p_next; fa.p_prev = rp->p_prev; }
     if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V) {
         fa.nat = IS_V ? E->d_nat_v + (size_t)f * E->D : E->d_nat_w;
         fa.t_cnt = IS_V ? E->d_t_v : E->d_t_w;
@@ -191,57 +217,98 @@ static int sweep_run(Engine* E, const Run& r, int f, int batch = -1) {
     return check_launch(E, "sweep_run");
 }
 
-// Fused schedule (two complete one-hot fields, device case order = run 0): see k_fused_stream.
-static bool fused_ok(const Engine* E) {
-    const DevSplit& S = E->tr;
-    return !getenv("SVBFM_NO_FUSE") && E->cfg.method != SVBFM_VB_ONLINE && E->runs.size() == 2 && S.uniformF == 2 && E->rows_reordered &&
-           E->runs[0].nnz == S.n && E->runs[1].nnz == S.n && S.cother && E->d_mu_prev && E->K > 0;
-}
+// Two-copy stream schedule (two complete one-hot fields, device case order = run 0): see k_stream.
+static bool stream_ok(const Engine* E) { return E->streams; }
 
-template <int KIND, bool REDUCE>
-static void launch_fused(Engine* E, int f, bool pending) {
+// one pass over `side` (0: run 0 / e, 1: run 1 / e2). W: a w step (KIND_*_W), else v.
+template <bool MCMC, bool W, bool REDUCE>
+static void launch_stream(Engine* E, int side, bool has_own, bool own_is_w, bool has_oth, bool oth_is_w) {
     const DevSplit& S = E->tr;
-    const Run& r0 = E->runs[0];
-    FusedArgs a{};
-    a.tile_col = E->d_tile_col; a.tile_begin = E->d_tile_begin; a.tile_len = E->d_tile_len; a.exec_order = E->d_exec_order;
-    a.tile0 = r0.tile_begin; a.ntiles = r0.tile_end - r0.tile_begin; a.entry0 = S.h_colptr[r0.col_begin];
-    a.cval = S.cval; a.ov = OtherView{S.cother, S.cother_val}; a.e = E->d_e;
-    a.pf = REDUCE ? E->d_pv + (size_t)f * E->D : nullptr;
-    a.pf_prev = pending ? E->d_pv + (size_t)(f - 1) * E->D : nullptr;
-    a.delta = E->d_delta; a.cpack = E->d_cpack; a.partial = E->d_partial;
+    const Run& r = E->runs[side];
+    StreamArgs a{};
+    a.colptr = S.colptr; a.c0 = r.col_begin; a.c1 = r.col_end; a.entry0 = S.h_colptr[r.col_begin]; a.n = S.n;
+    a.ntiles = E->s_ntiles[side]; a.ts_shift = E->ts_shift; a.tile_col0 = E->d_stile_col0 + (side ? E->s_ntiles[0] : 0);
+    a.oc = S.cother; a.xv = S.cval; a.xo = S.cother_val;
+    a.e = side ? E->d_e2 : E->d_e;
+    a.rec = E->d_cpack; a.own = E->d_opack;
+    a.has_own = has_own; a.own_is_w = own_is_w; a.has_oth = has_oth; a.oth_is_w = oth_is_w;
+    a.colsum = E->d_colsum; a.partial = E->d_partial + (side ? (size_t)E->s_ntiles[0] * 8 : 0);
+    constexpr int KIND = MCMC ? (W ? KIND_MC_W : KIND_MC_V) : (W ? KIND_VB_W : KIND_VB_V);
     unsigned grid = (a.ntiles + 7) / 8;
-    if (S.all_ones) k_fused_stream<KIND, true, REDUCE><<<grid, 256, 0, E->stream>>>(a);
-    else k_fused_stream<KIND, false, REDUCE><<<grid, 256, 0, E->stream>>>(a);
+    if (!a.ntiles) return;
+    if (S.all_ones) k_stream<KIND, true, REDUCE><<<grid, 256, 0, E->stream>>>(a);
+    else k_stream<KIND, false, REDUCE><<<grid, 256, 0, E->stream>>>(a);
     LAUNCHED(E);
 }
 
-template <int KIND>   // KIND_VB_V or KIND_MC_V
-static int sweep_factors_fused(Engine* E) {
-    const DevSplit& S = E->tr;
+// update_w + update_v of one iteration (vb.h:390-440 / mcmc.h:465-623 without the hyper-parameter draws)
+template <bool MCMC>
+static int sweep_streams(Engine* E) {
     const Run &r0 = E->runs[0], &r1 = E->runs[1];
     cudaStream_t st = E->stream;
-    k_pack_cols<<<nblk(r1.col_end - r1.col_begin), 256, 0, st>>>(r1.col_begin, r1.col_end, E->d_pv, E->d_cpack); LAUNCHED(E);
-    for (int f = 0; f < E->K; f++) {
-        { ProfScope ps(E, 6); launch_fused<KIND, true>(E, f, f > 0); }                 // pending pass 2 of factor f-1 + pass 1 of run 0
-        if (int rc = combine_finalize<KIND>(E, r0, f, -1, 1)) return rc;
-        {
-            ProfScope ps(E, 0);                                                        // pass 1 of run 1, run 0's pass 2 added on the fly
-            SweepArgs a{};
-            a.tile_col = E->d_tile_col; a.tile_begin = E->d_tile_begin; a.tile_len = E->d_tile_len; a.exec_order = E->d_exec_order;
-            a.colptr = S.colptr; a.crow = S.crow; a.cval = S.cval; a.rv = row_view(S); a.ov = OtherView{S.cother, S.cother_val};
-            a.e = E->d_e; a.pf = E->d_pv + (size_t)f * E->D; a.partial = E->d_partial; a.delta = E->d_delta; a.cpack = E->d_cpack;
-            a.tile0 = r1.tile_begin; a.ntiles = r1.tile_end - r1.tile_begin; a.tile_entries = E->tile_entries;
-            unsigned grid = (a.ntiles + 7) / 8;
-            if (a.ntiles) {
-                if (S.all_ones) k_sweep_reduce<KIND, 2, true><<<grid, 256, 0, st>>>(a);
-                else k_sweep_reduce<KIND, 2, false><<<grid, 256, 0, st>>>(a);
-                LAUNCHED(E);
-            }
+    std::vector<int> steps;                       // -1 = w, f = v_f
+    if (E->cfg.k1) steps.push_back(-1);
+    for (int f = 0; f < E->K; f++) steps.push_back(f);
+    if (steps.empty()) return 0;
+    auto table = [&](int s) -> double2* { return s < 0 ? E->d_pw : E->d_pv + (size_t)s * E->D; };
+    k_pack_init<<<nblk(r1.col_end - r0.col_begin), 256, 0, st>>>(r0.col_begin, r0.col_end, r1.col_begin, r1.col_end, table(steps[0]), E->d_cpack, E->d_opack);
+    LAUNCHED(E);
+    constexpr int KW = MCMC ? KIND_MC_W : KIND_VB_W, KV = MCMC ? KIND_MC_V : KIND_VB_V;
+    for (size_t k = 0; k < steps.size(); k++) {
+        const int s = steps[k];
+        const bool first = (k == 0), prev_w = (!first && steps[k - 1] < 0), w = (s < 0);
+        RecPlan rp;
+        rp.p_next = (k + 1 < steps.size()) ? table(steps[k + 1]) : nullptr;
+        {   // first field: pending U(s-1), I(s-1) + pass 1
+            ProfScope ps(E, w ? 9 : 6);
+            if (w) launch_stream<MCMC, true, true>(E, 0, !first, prev_w, !first, prev_w);
+            else launch_stream<MCMC, false, true>(E, 0, !first, prev_w, !first, prev_w);
         }
-        if (int rc = combine_finalize<KIND>(E, r1, f, -1, f + 1 < E->K ? 2 : 3)) return rc;
+        rp.run = 0; rp.rec_mode = 1; rp.p_prev = first ? nullptr : table(steps[k - 1]);
+        if (int rc = w ? combine_finalize<KW>(E, r0, s, -1, &rp) : combine_finalize<KV>(E, r0, s, -1, &rp)) return rc;
+        {   // second field: pending I(s-1), U(s) + pass 1
+            ProfScope ps(E, w ? 9 : 8);
+            if (w) launch_stream<MCMC, true, true>(E, 1, !first, prev_w, true, true);
+            else launch_stream<MCMC, false, true>(E, 1, !first, prev_w, true, false);
+        }
+        rp.run = 1; rp.rec_mode = 2; rp.p_prev = nullptr;
+        if (int rc = w ? combine_finalize<KW>(E, r1, s, -1, &rp) : combine_finalize<KV>(E, r1, s, -1, &rp)) return rc;
     }
-    { ProfScope ps(E, 7); launch_fused<KIND, false>(E, E->K, true); }                  // flush the last factor's pass 2
-    return check_launch(E, "sweep_factors_fused");
+    {   // flush the last step's updates into both copies
+        ProfScope ps(E, 7);
+        const bool lw = steps.back() < 0;
+        launch_stream<MCMC, false, false>(E, 0, true, lw, true, lw);
+        k_pack_h4<<<nblk(r0.col_end - r0.col_begin), 256, 0, st>>>(r0.col_begin, r0.col_end, table(steps.back()), E->d_cpack); LAUNCHED(E);
+        launch_stream<MCMC, false, false>(E, 1, true, lw, false, false);
+    }
+    return check_launch(E, "sweep_streams");
+}
+
+namespace svb {
+int stream_tile_cols(Engine* E) {
+    uint32_t off = 0;
+    for (int ri = 0; ri < 2; ri++) {
+        const Run& r = E->runs[ri];
+        uint32_t nt = E->s_ntiles[ri];
+        if (nt) { k_tile_col0<<<(nt + 255) / 256, 256, 0, E->stream>>>(E->tr.colptr, r.col_begin, r.col_end, nt, E->ts_shift, E->d_stile_col0 + off); LAUNCHED(E); }
+        off += nt;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(E, SVBFM_ERR_CUDA, std::string("k_tile_col0: ") + cudaGetErrorString(e));
+    return 0;
+}
+}  // namespace svb
+
+// every e_i += w0_delta, on both copies
+static void shift_e(Engine* E) {
+    k_shift_e<<<SV_RGRID, 256, 0, E->stream>>>(E->d_e, E->tr.n, E->d_sc); LAUNCHED(E);
+    if (E->streams) { k_shift_e<<<SV_RGRID, 256, 0, E->stream>>>(E->d_e2, E->tr.n, E->d_sc); LAUNCHED(E); }
+}
+// (re)build the second copy from the first
+static void sync_e2(Engine* E) {
+    if (!E->streams || !E->tr.n) return;
+    const Run& r1 = E->runs[1];
+    k_gather_e<<<nblk(E->tr.n), 256, 0, E->stream>>>(E->d_e, E->tr.crow + E->tr.h_colptr[r1.col_begin], E->tr.n, E->d_e2); LAUNCHED(E);
 }
 
 // sum e, sum e^2, sum clamp(e)^2 -> red[0..2] (global)
@@ -294,15 +361,15 @@ static int vb_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
     if (E->cfg.k0) {                                               // update_w0 (vb.h:385-387)
         if (int rc = reduce_e(E)) return rc;
         k_vb_w0<<<1, 1, 0, st>>>(E->d_sc); LAUNCHED(E);
-        k_shift_e<<<SV_RGRID, 256, 0, st>>>(E->d_e, E->tr.n, E->d_sc); LAUNCHED(E);
+        shift_e(E);
     }
-    if (E->cfg.k1)                                                 // update_w, all columns (vb.h:390-406)
-        for (const Run& r : E->runs)
-            if (int rc = sweep_run<KIND_VB_W>(E, r, -1)) return rc;
-    if (fused_ok(E)) {                                             // update_v (vb.h:409-440)
-        if (int rc = sweep_factors_fused<KIND_VB_V>(E)) return rc;
+    if (stream_ok(E)) {                                            // update_w + update_v (vb.h:390-440)
+        if (int rc = sweep_streams<false>(E)) return rc;
     } else {
-        for (int f = 0; f < E->K; f++)
+        if (E->cfg.k1)                                             // update_w, all columns (vb.h:390-406)
+            for (const Run& r : E->runs)
+                if (int rc = sweep_run<KIND_VB_W>(E, r, -1)) return rc;
+        for (int f = 0; f < E->K; f++)                             // update_v (vb.h:409-440)
             for (const Run& r : E->runs)
                 if (int rc = sweep_run<KIND_VB_V>(E, r, f)) return rc;
     }
@@ -328,13 +395,13 @@ static int mcmc_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
     if (int rc = group_sums(E, true)) return rc;
     k_mcmc_hyper<<<1, 1, 0, st>>>(E->d_sc, E->d_grp_sums, E->d_n_per_group, E->G, E->K, E->cfg.k0, E->cfg.k1, E->d_hyper_w, E->d_mu_w,
                                   E->d_hyper_v, E->d_mu_v, E->cfg.seed, E->cfg.do_sample, E->cfg.do_multilevel); LAUNCHED(E);
-    if (E->cfg.k0) { k_shift_e<<<SV_RGRID, 256, 0, st>>>(E->d_e, E->tr.n, E->d_sc); LAUNCHED(E); }
-    if (E->cfg.k1)
-        for (const Run& r : E->runs)
-            if (int rc = sweep_run<KIND_MC_W>(E, r, -1)) return rc;
-    if (fused_ok(E)) {
-        if (int rc = sweep_factors_fused<KIND_MC_V>(E)) return rc;
+    if (E->cfg.k0) shift_e(E);
+    if (stream_ok(E)) {
+        if (int rc = sweep_streams<true>(E)) return rc;
     } else {
+        if (E->cfg.k1)
+            for (const Run& r : E->runs)
+                if (int rc = sweep_run<KIND_MC_W>(E, r, -1)) return rc;
         for (int f = 0; f < E->K; f++)
             for (const Run& r : E->runs)
                 if (int rc = sweep_run<KIND_MC_V>(E, r, f)) return rc;
@@ -349,6 +416,7 @@ static int mcmc_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
         if (int rc = allreduce_sum_f64(E, RED(E->d_sc, 5), 1)) return rc;
     } else {
         if (int rc = predict<PRED_MC_TRAIN>(E, E->tr, E->d_e, 5, 1)) return rc;
+        sync_e2(E);
     }
     if (int rc = predict<PRED_MC_TEST>(E, E->te, nullptr, 3, 2)) return rc;
     k_finish_iter<<<1, 1, 0, st>>>(E->d_sc, stp, SVBFM_MCMC); LAUNCHED(E);
@@ -437,6 +505,8 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     Engine* E = new Engine();
     E->cfg = *cfg; E->dev = cfg->device; E->D = cfg->num_attribute; E->K = cfg->num_factor;
     E->tile_entries = cfg->tile_entries ? cfg->tile_entries : 1024;
+    E->ts_shift = 5;
+    while (E->ts_shift < 20 && (2u << E->ts_shift) <= E->tile_entries) E->ts_shift++;
     {   // stream-ordered allocations from the device's default pool, never handed back to the OS between learn() calls:
         // ingest allocates and frees tens of GB of scratch; plain cudaMalloc/cudaFree would dominate set_csc
         cudaMemPool_t pool;
@@ -461,8 +531,8 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     rc |= dev_alloc(E, &E->d_sc, 1);
     rc |= dev_alloc(E, &E->d_colsum, D * 4);
     rc |= dev_alloc(E, &E->d_delta, D);
-    rc |= dev_alloc(E, &E->d_mu_prev, D);
     rc |= dev_alloc(E, &E->d_cpack, D);
+    rc |= dev_alloc(E, &E->d_opack, D);
     rc |= dev_alloc(E, &E->d_dT, D);
     rc |= dev_alloc(E, &E->d_red_partial, SCR_GROUP + (K + 1) * 64 /*max groups*/ * 2 * SV_GGRID);
     if (rc) { g_create_error = E->err; svbfm_destroy(*out); *out = nullptr; return SVBFM_ERR_OOM; }
@@ -488,7 +558,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_mu_prev, E->d_cpack, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) cudaFreeAsync(p, E->stream);
     cudaStreamSynchronize(E->stream);
     if (E->own_stream) cudaStreamDestroy(E->own_stream);
@@ -584,9 +654,13 @@ int svbfm_set_csc(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_co
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
     if (is_train) {
         E->n_total = (uint64_t)cnt;
-        cudaFreeAsync(E->d_e, E->stream); cudaFreeAsync(E->d_partial, E->stream); E->d_e = nullptr; E->d_partial = nullptr;
+        cudaFreeAsync(E->d_e, E->stream); cudaFreeAsync(E->d_partial, E->stream); cudaFreeAsync(E->d_e2, E->stream);
+        E->d_e = nullptr; E->d_partial = nullptr; E->d_e2 = nullptr;
         if (dev_alloc(E, &E->d_e, num_cases)) return SVBFM_ERR_OOM;
-        if (dev_alloc(E, &E->d_partial, (size_t)E->n_tiles * 4)) return SVBFM_ERR_OOM;
+        if (E->streams) {
+            if (dev_alloc(E, &E->d_e2, num_cases)) return SVBFM_ERR_OOM;
+            if (dev_alloc(E, &E->d_partial, ((size_t)E->s_ntiles[0] + E->s_ntiles[1]) * 8)) return SVBFM_ERR_OOM;
+        } else if (dev_alloc(E, &E->d_partial, (size_t)E->n_tiles * 4)) return SVBFM_ERR_OOM;
     } else {
         E->nt_total = (uint64_t)cnt;
         cudaFreeAsync(E->d_pred_test, E->stream); cudaFreeAsync(E->d_pred_sum, E->stream); E->d_pred_test = nullptr; E->d_pred_sum = nullptr;
@@ -709,6 +783,7 @@ int svbfm_begin(svbfm_t* h) {
     } else if (E->cfg.method == SVBFM_MCMC) {
         if (int rc = predict<PRED_MC_TRAIN>(E, E->tr, E->d_e, 6, 1)) return rc;     // e = yhat - y (mcmcs.h:75-80)
     }
+    if (E->cfg.method != SVBFM_VB_ONLINE) sync_e2(E);
     else {   // vb_online: global count of every feature in the training data (vbo.h:704-726) and the natural parameters
         if (!E->d_col_count) {
             if (dev_alloc(E, &E->d_col_count, E->D)) return SVBFM_ERR_OOM;
@@ -737,7 +812,7 @@ int svbfm_reset(svbfm_t* h) {
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
     free_split(E, E->tr); free_split(E, E->te);
     E->runs.clear();
-    E->begun = false; E->have_state = false; E->rows_reordered = false;
+    E->begun = false; E->have_state = false; E->rows_reordered = false; E->run0_sequential = false; E->streams = false;
     SV_CUDA(E, cudaMemsetAsync(E->d_dT, 0, (size_t)E->D * 8, E->stream));
     SV_CUDA(E, cudaMemsetAsync(E->d_sc, 0, sizeof(Scalars), E->stream));
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
@@ -889,6 +964,24 @@ int svbfm_get_sum_t(svbfm_t* h, double* sum_t) {
     return SVBFM_OK;
 }
 
+int svbfm_copies_max_diff(svbfm_t* h, double* max_abs_diff) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E || !max_abs_diff) return SVBFM_ERR_ARG;
+    *max_abs_diff = 0.0;
+    if (!E->streams || !E->d_e2 || !E->tr.n) return SVBFM_OK;
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    unsigned long long* d = nullptr;
+    SV_CUDA(E, cudaMallocAsync((void**)&d, 8, E->stream));
+    SV_CUDA(E, cudaMemsetAsync(d, 0, 8, E->stream));
+    const Run& r1 = E->runs[1];
+    k_copies_max_diff<<<nblk(E->tr.n), 256, 0, E->stream>>>(E->d_e, E->tr.crow + E->tr.h_colptr[r1.col_begin], E->tr.n, E->d_e2, d);
+    unsigned long long bits = 0;
+    SV_CUDA(E, copy_sync(E, &bits, d, 8, cudaMemcpyDeviceToHost));
+    cudaFreeAsync(d, E->stream);
+    memcpy(max_abs_diff, &bits, 8);
+    return check_launch(E, "copies_max_diff");
+}
+
 int svbfm_set_profile(svbfm_t* h, int32_t enabled) {
     Engine* E = reinterpret_cast<Engine*>(h);
     if (!E) return SVBFM_ERR_ARG;
@@ -917,7 +1010,7 @@ int svbfm_get_info(svbfm_t* h, svbfm_info* out) {
     if (!E || !out) return SVBFM_ERR_ARG;
     memset(out, 0, sizeof(*out));
     out->num_runs = (uint32_t)E->runs.size();
-    out->num_tiles = E->n_tiles;
+    out->num_tiles = E->streams ? E->s_ntiles[0] + E->s_ntiles[1] : E->n_tiles;
     out->uniform_row_nnz = E->tr.uniformF;
     out->all_ones = E->tr.all_ones;
     out->kernel_launches = E->launches;
@@ -925,7 +1018,7 @@ int svbfm_get_info(svbfm_t* h, svbfm_info* out) {
     out->train_nnz = E->tr.nnz;
     out->rows_reordered = E->rows_reordered;
     out->world_size = (uint32_t)E->world;
-    out->fused_schedule = fused_ok(E) ? 1u : 0u;
+    out->fused_schedule = stream_ok(E) ? 1u : 0u;
     return SVBFM_OK;
 }
 

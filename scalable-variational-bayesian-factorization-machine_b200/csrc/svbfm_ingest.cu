@@ -353,9 +353,12 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
                 S.perm = d_perm; E->dev_bytes += (size_t)n * 4;
                 E->rows_reordered = true;
             } else {
-                cudaFreeAsync(d_perm, E->stream);
+                cudaFreeAsync(d_perm, E->stream);     // the caller's order already is run 0's order
             }
+            E->run0_sequential = true;
         }
+        E->streams = E->run0_sequential && E->cfg.method != SVBFM_VB_ONLINE && !getenv("SVBFM_NO_FUSE") && E->runs.size() == 2 && F == 2 &&
+                     E->runs[1].nnz == n;
     }
     mark("case re-ordering + CSC rebuild");
     cudaFreeAsync(d_flags, E->stream);
@@ -373,7 +376,33 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         SV_CUDA(E, cudaStreamSynchronize(st));
     }
     mark("other-feature arrays");
-    if (is_train) {
+    if (is_train && E->streams) {
+        // ---- stream schedule: implicit tiles of 2^ts_shift entries per run; only their first column and the list of the
+        // columns that span many tiles are materialised (kernels.cuh k_stream / k_combine_span)
+        const uint64_t TS = 1ull << E->ts_shift;
+        cudaFreeAsync(E->d_stile_col0, st); cudaFreeAsync(E->d_span_heavy, st);
+        E->d_stile_col0 = nullptr; E->d_span_heavy = nullptr;
+        std::vector<uint32_t> heavy;
+        for (int ri = 0; ri < 2; ri++) {
+            Run& r = E->runs[ri];
+            E->s_ntiles[ri] = (uint32_t)((r.nnz + TS - 1) / TS);
+            uint64_t e0 = S.h_colptr[r.col_begin];
+            size_t h0 = heavy.size();
+            for (uint32_t j = r.col_begin; j < r.col_end; j++) {
+                uint64_t b = S.h_colptr[j], e = S.h_colptr[j + 1];
+                if (e > b && (e - 1 - e0) / TS - (b - e0) / TS > 8 /* SV_SPAN_LIGHT */) heavy.push_back(j);
+            }
+            E->span_heavy_n[ri] = (uint32_t)(heavy.size() - h0);
+            r.tile_begin = r.tile_end = 0; r.heavy_begin = r.heavy_end = 0;
+        }
+        if (dev_alloc(E, &E->d_stile_col0, (size_t)E->s_ntiles[0] + E->s_ntiles[1])) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->d_span_heavy, heavy.size())) return SVBFM_ERR_OOM;
+        SV_CUDA(E, cudaMemcpyAsync(E->d_span_heavy, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice, st));
+        if (int r = stream_tile_cols(E)) return r;
+        SV_CUDA(E, cudaStreamSynchronize(st));
+        E->n_tiles = 0; E->n_heavy = 0;
+        mark("implicit tiles");
+    } else if (is_train) {
         // ---- warp tiles (host). A tile = <= T consecutive CSC entries of ONE column; a column's tiles are consecutive
         // tile ids (fixed summation order). Runs whose case ids are not sequential ("gather runs") read e_i at random:
         // every miss moves a 128 B HBM line for 8 useful bytes (profiles/r01_v2_*). For their big columns the entry list

@@ -23,6 +23,7 @@
 namespace svb {
 
 struct ColPack;
+struct OwnPack;
 
 struct DevSplit {
     uint32_t n = 0;          // local cases
@@ -108,6 +109,16 @@ struct Engine {
     uint32_t* d_heavy_cols = nullptr;
     uint32_t n_tiles = 0, n_heavy = 0, tile_entries = 1024;
     bool rows_reordered = false;
+    bool run0_sequential = false;      // device case order = entry order of run 0 (run 0 holds every case exactly once)
+    // two-copy stream schedule (two complete one-hot fields; kernels.cuh k_stream)
+    bool streams = false;
+    uint32_t ts_shift = 10;            // implicit tile = 2^ts_shift entries (largest power of two <= tile_entries, >= 32)
+    uint32_t s_ntiles[2] = {0, 0};     // implicit tiles of run 0 / run 1
+    uint32_t* d_stile_col0 = nullptr;  // [s_ntiles[0] + s_ntiles[1]] first column of every implicit tile
+    uint32_t* d_span_heavy = nullptr;  // columns spanning more than SV_SPAN_LIGHT tiles, run 0 then run 1
+    uint32_t span_heavy_n[2] = {0, 0};
+    double* d_e2 = nullptr;            // [n] residuals in the entry order of run 1
+    struct OwnPack* d_opack = nullptr; // [D] own-side constants of the next pass
     // state
     double2* d_pw = nullptr;          // [D]
     double2* d_pv = nullptr;          // [K][D]
@@ -134,8 +145,7 @@ struct Engine {
     double* d_partial = nullptr;      // [n_tiles][4]
     double* d_colsum = nullptr;       // [D][4]
     double* d_delta = nullptr;        // [D]
-    double* d_mu_prev = nullptr;      // [D] parameter mean before its latest update (fused schedule)
-    struct ColPack* d_cpack = nullptr; // [D] fused schedule: 32-byte per-column records gathered by the sweeps
+    struct ColPack* d_cpack = nullptr; // [D] stream schedule: 32-byte per-column records gathered by the other side's pass
     double* d_dT = nullptr;           // [D]
     double* d_red_partial = nullptr;  // reduction scratch
     double* d_grp_sums = nullptr;     // [(K+1)][G][2]
@@ -159,6 +169,7 @@ struct Engine {
 int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t num_cases, uint32_t num_cols, const uint64_t* colptr,
                  const uint32_t* case_id, const float* x, const float* target);
 void free_split(Engine* E, DevSplit& S);
+int stream_tile_cols(Engine* E);   // svbfm_engine.cu: first column of every implicit tile (k_tile_col0)
 int allreduce(Engine* E, void* buf, size_t count, int dtype /*nccl*/, int op /*nccl*/);
 
 // error helpers

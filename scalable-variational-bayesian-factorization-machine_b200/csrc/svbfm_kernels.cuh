@@ -52,8 +52,10 @@ struct OtherView {            // F == 2 only: for every CSC entry, the feature i
     const float* val;
 };
 
-// fused schedule: everything a case needs from its OTHER column in one 32-byte record (one LDG.E.256 gather)
-struct alignas(32) ColPack { double mu, sg, delta, mu_prev; };
+// two-copy stream schedule: everything an entry needs from its OTHER column in one 32-byte record (one LDG.E.256
+// gather), and the constants of its OWN column for the next pass of its side (k_stream below)
+struct alignas(32) ColPack { double mu, sg, delta, h4; };
+struct alignas(32) OwnPack { double mu_red, h_oth, d_own, pad; };
 
 template <int FT, bool ONES, bool VAR>
 __device__ __forceinline__ void others(const RowView& rv, const OtherView& ov, const double2* __restrict__ pf, uint64_t p, uint32_t i, uint32_t j,
@@ -104,7 +106,6 @@ struct SweepArgs {
     const double2* pf;        // params of this factor ([D]) or the w params
     double* partial;          // [n_tiles][4]
     const double* delta;      // [D]
-    const ColPack* cpack;     // F == 2 fused schedule: {mu, sigma, delta, -} of the other column; delta = pass 2 of the previous run, not yet applied to e
     uint32_t tile0, ntiles, tile_entries;
     const uint16_t* cbatch;   // vb_online: batch id of the case of every CSC entry (null otherwise)
     uint32_t batch;           // vb_online: current batch
@@ -155,32 +156,14 @@ __global__ void __launch_bounds__(256) k_sweep_reduce(SweepArgs a) {
                 B += xx;
             } else if constexpr (KIND == KIND_VB_V || KIND == KIND_VBO_V) {
                 double h, h1, h2;
-                if constexpr (FT == 2) {
-                    if (a.cpack) {           // fused schedule: other column's record; pass 2 of the previous run folded in (vb.h:628, 638)
-                        uint32_t o = __ldcs(&a.ov.col[p]);
-                        float xo = 1.0f;
-                        if constexpr (!ONES) xo = __ldcs(&a.ov.val[p]);
-                        ColPack g = a.cpack[o];
-                        ei += (xo * (mu * xf)) * g.delta;
-                        h = g.mu * xo; h1 = g.sg * xo * xo; h2 = g.mu * g.mu * xo * xo;
-                    } else others<FT, ONES, true>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
-                } else others<FT, ONES, true>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
+                others<FT, ONES, true>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
                 A += xf * h * (ei + xf * mu * h);                      // vb.h:594
                 B += xx * h * h + xx * h1;                             // vb.h:595
                 C1 += xx * h1;                                         // sum of pass-2 h1 (vb.h:629)
                 C2 += xx * h2;                                         // sum of pass-2 h2 (vb.h:630)
             } else {                                                   // KIND_MC_V
                 double h, h1, h2;
-                if constexpr (FT == 2) {
-                    if (a.cpack) {           // mcmc.h:831-833 of the previous run folded in
-                        uint32_t o = __ldcs(&a.ov.col[p]);
-                        float xo = 1.0f;
-                        if constexpr (!ONES) xo = __ldcs(&a.ov.val[p]);
-                        ColPack g = a.cpack[o];
-                        ei += (xo * (mu * xf)) * g.delta;
-                        h = g.mu * xo;
-                    } else others<FT, ONES, false>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
-                } else others<FT, ONES, false>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
+                others<FT, ONES, false>(a.rv, a.ov, a.pf, p, i, j, h, h1, h2);
                 double hh = xf * h;                                    // mcmc.h:789
                 A += hh * ei;                                          // mcmc.h:790
                 B += hh * hh;                                          // mcmc.h:791
@@ -247,6 +230,64 @@ __global__ void k_combine_light(uint32_t c0, uint32_t c1, const uint32_t* __rest
     o[1] = make_double2(C1, C2);
 }
 
+// ---- stream schedule (k_stream): implicit tiles of TS = 2^ts_shift consecutive entries of a run, which may span several
+// columns. A column that lies inside one tile has its sums written straight to colsum[j]; a column that crosses
+// tile borders leaves one piece per tile: partial[T][1] in the tile where it starts, partial[T][0] in the others.
+#define SV_SPAN_LIGHT 8u      // columns spanning more tiles than this are combined by a CTA (k_combine_span)
+
+struct SpanView {
+    const uint64_t* colptr;   // null: the explicit-tile layout (col_tile0 / partial[tile][4]) is in use
+    uint64_t entry0;          // first entry of the run
+    uint32_t ts_shift;        // tile = 2^ts_shift entries (Engine::ts_shift; 1024 by default)
+};
+
+__global__ void __launch_bounds__(128) k_combine_span(const uint32_t* __restrict__ heavy_cols, uint32_t h0, SpanView sp,
+                                                      const double* __restrict__ partial, double* __restrict__ colsum) {
+    __shared__ double sm[4 * 32];
+    uint32_t j = heavy_cols[h0 + blockIdx.x];
+    uint64_t b = sp.colptr[j], e = sp.colptr[j + 1];
+    uint64_t T0 = (b - sp.entry0) >> sp.ts_shift, T1 = (e - 1 - sp.entry0) >> sp.ts_shift;
+    double v[4] = {0, 0, 0, 0};
+    for (uint64_t T = T0 + threadIdx.x; T <= T1; T += blockDim.x) {
+        const double2* p = reinterpret_cast<const double2*>(partial + (T * 2 + (T == T0 ? 1 : 0)) * 4);
+        double2 x = p[0], y = p[1];
+        v[0] += x.x; v[1] += x.y; v[2] += y.x; v[3] += y.y;
+    }
+    block_sum<4>(v, sm);
+    if (threadIdx.x == 0) {
+        double2* o = reinterpret_cast<double2*>(colsum + (size_t)j * 4);
+        o[0] = make_double2(v[0], v[1]);
+        o[1] = make_double2(v[2], v[3]);
+    }
+}
+
+// returns false when colsum[j] already holds the sums (one-tile column, heavy column, or after the allreduce)
+__device__ __forceinline__ bool span_sum(uint32_t j, SpanView sp, const double* __restrict__ partial, double& A, double& B, double& C1, double& C2,
+                                         bool& empty) {
+    uint64_t b = sp.colptr[j], e = sp.colptr[j + 1];
+    A = B = C1 = C2 = 0.0;
+    empty = (e == b);
+    if (empty) return true;
+    uint64_t T0 = (b - sp.entry0) >> sp.ts_shift, T1 = (e - 1 - sp.entry0) >> sp.ts_shift;
+    if (T0 == T1 || T1 - T0 > SV_SPAN_LIGHT) return false;
+    for (uint64_t T = T0; T <= T1; T++) {
+        const double2* p = reinterpret_cast<const double2*>(partial + (T * 2 + (T == T0 ? 1 : 0)) * 4);
+        double2 x = p[0], y = p[1];
+        A += x.x; B += x.y; C1 += y.x; C2 += y.y;
+    }
+    return true;
+}
+
+__global__ void k_combine_light_span(uint32_t c0, uint32_t c1, SpanView sp, const double* __restrict__ partial, double* __restrict__ colsum) {
+    uint32_t j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c1) return;
+    double A, B, C1, C2; bool empty;
+    if (!span_sum(j, sp, partial, A, B, C1, C2, empty)) return;
+    double2* o = reinterpret_cast<double2*>(colsum + (size_t)j * 4);
+    o[0] = make_double2(A, B);
+    o[1] = make_double2(C1, C2);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // counter-based RNG (Philox4x32-10, Salmon et al. 2011) -- replaces the reference's libc rand() stream
 // (src/util/random.h:150-176) for MCMC draws; matched in distribution, identical on every rank.
@@ -284,10 +325,14 @@ struct FinalizeArgs {
     const double* hyper_mu;      // mcmc: mu per group
     Scalars* sc;
     double* delta;               // [D]
-    double* mu_prev;             // [D] mean before this update (fused schedule), may be null
-    ColPack* cpack;              // [D] fused schedule record of this column (null otherwise)
-    int pack_mode;               // 1: {new mu, new sigma} of this factor; 2: {mu, sigma} of the NEXT factor (pf + D); 3: zeros
-    uint32_t D;
+    // stream schedule (null / 0 otherwise): records of this column for the passes that follow (see k_stream)
+    SpanView span;
+    ColPack* cpack;              // [D] gathered by the other side
+    OwnPack* opack;              // [D] read by this side's next pass
+    int rec_mode;                // 1: first field  -> cpack {new mean, new var, delta, p_prev mean}    opack {p_next mean, new mean, delta}
+                                 // 2: second field -> cpack {p_next mean, p_next var, delta, old mean} opack {p_next mean, p_next mean, delta}
+    const double2* p_next;       // parameters of the step that follows ([D]; null after the last one)
+    const double2* p_prev;       // parameters of the step before ([D]; null at the first one)
     double* dT;                  // [D]
     uint64_t seed; int do_sample;
     // vb_online
@@ -304,13 +349,21 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
     uint32_t j = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= a.c1) return;
     double A, B, C1, C2;
-    load_colsum(j, a.col_tile0, a.partial, a.colsum, a.from_colsum, A, B, C1, C2);
+    if (a.span.colptr) {
+        bool empty;
+        if (a.from_colsum || !span_sum(j, a.span, a.partial, A, B, C1, C2, empty)) {
+            const double2* p = reinterpret_cast<const double2*>(a.colsum + (size_t)j * 4);
+            double2 x = p[0], y = p[1];
+            A = x.x; B = x.y; C1 = y.x; C2 = y.y;
+        }
+    } else load_colsum(j, a.col_tile0, a.partial, a.colsum, a.from_colsum, A, B, C1, C2);
     uint32_t g = a.group[j];
     double hy = (a.f < 0) ? a.hyper[g] : a.hyper[(size_t)g * a.K + a.f];
     double alpha = a.sc->alpha;
     double2 P = a.pf[j];
     double mu_old = P.x, sg_old = P.y;
     unsigned bad = 0;
+    double new_mean, new_var, dlt;
     if constexpr (KIND == KIND_VB_W || KIND == KIND_VB_V) {
         double sg = 1.0 / (hy + alpha * B);                 // vb.h:540 / :597
         double mu = sg * alpha * A;                          // vb.h:541 / :598
@@ -318,12 +371,8 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
         bool skip = false;
         if (isnan(mu) || isinf(mu)) { mu = mu_old; bad++; skip = true; }   // vb.h:552-565 / :606-619 (pass 2 skipped)
         a.pf[j] = make_double2(mu, sg);
-        a.delta[j] = skip ? 0.0 : (mu_old - mu);
-        if (a.mu_prev) a.mu_prev[j] = mu_old;
-        if (a.cpack) {
-            double2 Q = a.pack_mode == 1 ? make_double2(mu, sg) : (a.pack_mode == 2 ? a.pf[(size_t)a.D + j] : make_double2(0.0, 0.0));
-            a.cpack[j] = ColPack{Q.x, Q.y, skip ? 0.0 : (mu_old - mu), mu_old};
-        }
+        new_mean = mu; new_var = sg; dlt = skip ? 0.0 : (mu_old - mu);
+        a.delta[j] = dlt;
         if (!skip) {
             if constexpr (KIND == KIND_VB_W) a.dT[j] += B * (sg - sg_old);                                    // vb.h:572
             else a.dT[j] += (C1 + C2) * (sg - sg_old) + C1 * (mu * mu - mu_old * mu_old);                        // vb.h:639-640
@@ -344,11 +393,17 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
         bool skip = false;
         if (isnan(v) || isinf(v)) { v = v_old; bad++; skip = true; }         // mcmc.h:697-710 / :811-824
         a.pf[j] = make_double2(v, 0.0);
-        a.delta[j] = skip ? 0.0 : (v - v_old);                               // e -= h (v_old - v)  (mcmc.h:716 / :833)
-        if (a.mu_prev) a.mu_prev[j] = v_old;
-        if (a.cpack) {
-            double2 Q = a.pack_mode == 1 ? make_double2(v, 0.0) : (a.pack_mode == 2 ? a.pf[(size_t)a.D + j] : make_double2(0.0, 0.0));
-            a.cpack[j] = ColPack{Q.x, Q.y, skip ? 0.0 : (v - v_old), v_old};
+        new_mean = v; new_var = 0.0; dlt = skip ? 0.0 : (v - v_old);         // e -= h (v_old - v)  (mcmc.h:716 / :833)
+        a.delta[j] = dlt;
+    }
+    if (a.rec_mode) {
+        double2 N = a.p_next ? a.p_next[j] : make_double2(0.0, 0.0);
+        if (a.rec_mode == 1) {
+            a.cpack[j] = ColPack{new_mean, new_var, dlt, a.p_prev ? a.p_prev[j].x : 0.0};
+            a.opack[j] = OwnPack{N.x, new_mean, dlt, 0.0};
+        } else {
+            a.cpack[j] = ColPack{N.x, N.y, dlt, mu_old};
+            a.opack[j] = OwnPack{N.x, N.x, dlt, 0.0};
         }
     }
     if (bad) atomicAdd(&a.sc->nan_inf, (unsigned long long)bad);
@@ -421,94 +476,176 @@ __global__ void __launch_bounds__(256) k_sweep_apply(SweepArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Fused schedule for two complete one-hot fields (every case has exactly one feature in run 0 and one in run 1, and
-// the device case order is run 0's order, so case i = p - entry0 for CSC entry p of run 0).
-// One streaming kernel per factor f over run 0:
-//     e_i += pass 2 of run 0, factor f-1        (vb.h:638 with h from the item mean BEFORE its f-1 update: mu_prev)
-//     e_i += pass 2 of run 1, factor f-1        (h from the user mean of factor f-1, already updated)
-//     store e_i ; pass 1 of run 0, factor f     (vb.h:587-596)
-// Run 1's pass 1 adds run 0's pending pass 2 on the fly (k_sweep_reduce, pend_delta) and does not write e. This
-// removes both k_row_apply launches of a factor. REDUCE = false flushes the pending updates after the last factor.
-struct FusedArgs {
-    const uint32_t* tile_col;
-    const uint64_t* tile_begin;
-    const uint32_t* tile_len;
-    const uint32_t* exec_order;
-    uint32_t tile0, ntiles;
-    uint64_t entry0;
-    const float* cval;
-    OtherView ov;
-    double* e;
-    const double2* pf;        // parameters of factor f
-    const double2* pf_prev;   // parameters of factor f-1 (null: nothing pending)
-    const double* delta;      // [D] deltas of factor f-1 (own column of the tile)
-    const ColPack* cpack;     // [D] other column: {mu_f, sigma_f, delta_{f-1}, mean before its f-1 update}
-    double* partial;
+// Two-copy stream schedule for two complete one-hot fields (every case has exactly one feature in run 0 and one in
+// run 1). The residuals are kept TWICE: e[i] in the entry order of run 0 (= device case order) and e2[p] in the entry
+// order of run 1. Every pass over a field then streams its own copy (oc 4 B + e 8 B read + 8 B write per entry, x
+// arrays when not all ones) and gathers one 32-byte record of the OTHER column from L2; there is no random access
+// to the residuals at all. The copies stay bit-identical because each applies the same updates
+//       e += x_j * h * delta_j                 (vb.h:571 / :638, mcmc.h:716 / :833)
+// in the same order with the same operands; an update made by one side is "pending" for a copy until that copy's
+// next pass:
+//   steps s = w, v_0, .., v_{K-1}; per step  U(s): pass over run 0 -> finalize -> I(s): pass over run 1 -> finalize
+//   pass over run 0 at step s : apply U(s-1) [own, h from the record's h4] and I(s-1) [other, h = own mean of s-1]
+//   pass over run 1 at step s : apply I(s-1) [own, h4 = the user's mean of s-1] and U(s) [other, h = own mean of s]
+//   then (REDUCE) the per-entry terms of pass 1 of the step (vb.h:537-538, 587-596 / mcmc.h:677, 785-792) with the
+//   up-to-date residual. After the last step both copies are flushed (REDUCE = false).
+// Tiles are implicit: warp t handles entries [t*TS, (t+1)*TS) of the run (TS = 2^ts_shift, 1024 by default) and walks over the columns inside
+// (a 32-column window of own-column constants lives in the lanes); sums of a column that ends inside the tile are
+// reduced with shuffles and written once. Fixed order everywhere: results are bit-reproducible.
+struct StreamArgs {
+    const uint64_t* colptr;
+    uint32_t c0, c1;          // columns of the run
+    uint64_t entry0;          // colptr[c0]
+    uint32_t n;               // entries of the run (= cases)
+    uint32_t ntiles, ts_shift;
+    const uint32_t* tile_col0;
+    const uint32_t* oc;       // [nnz] other column of every entry
+    const float* xv;          // [nnz] own x, other x (null when all ones)
+    const float* xo;
+    double* e;                // this side's copy of the residuals, index = entry - entry0
+    const ColPack* rec;       // records of the other side's columns
+    const OwnPack* own;       // constants of this side's columns
+    int has_own, own_is_w;    // a pending update of this side (own_is_w: it was a w step, h = 1)
+    int has_oth, oth_is_w;    // a pending update of the other side
+    double* colsum;           // [D][4]
+    double* partial;          // [ntiles of the run][2][4]
 };
 
 template <int KIND, bool ONES, bool REDUCE>
-__global__ void __launch_bounds__(256) k_fused_stream(FusedArgs a) {
-    uint32_t w = (blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5);
-    if (w >= a.ntiles) return;
-    uint32_t t = __ldg(&a.exec_order[a.tile0 + w]), lane = threadIdx.x & 31;
-    uint32_t j = __ldg(&a.tile_col[t]);
-    uint64_t b = __ldg(&a.tile_begin[t]);
-    uint64_t e_ = b + __ldg(&a.tile_len[t]);
-    double mu = 0.0, mu_p = 0.0, dU = 0.0;
-    if constexpr (REDUCE) mu = __ldg(&a.pf[j]).x;
-    const bool pending = a.pf_prev != nullptr;
-    if (pending) { mu_p = __ldg(&a.pf_prev[j]).x; dU = __ldg(&a.delta[j]); }
-    double A = 0.0, B = 0.0, C1 = 0.0, C2 = 0.0;
+__global__ void __launch_bounds__(256) k_stream(StreamArgs a) {
+    constexpr bool IS_V = (KIND == KIND_VB_V || KIND == KIND_MC_V);
+    constexpr bool IS_VB = (KIND == KIND_VB_V || KIND == KIND_VB_W);
+    constexpr unsigned FULL = 0xffffffffu;
     constexpr int U = 4;
-    for (uint64_t p0 = b + lane; p0 < e_; p0 += 32 * U) {
-        bool ok[U]; uint32_t oc[U]; float xs[U], xo[U]; double es[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            uint64_t p = p0 + (uint64_t)u * 32;
-            ok[u] = p < e_;
-            oc[u] = ok[u] ? __ldcs(&a.ov.col[p]) : 0u;
-            xs[u] = 1.0f; xo[u] = 1.0f;
-            if constexpr (!ONES) if (ok[u]) { xs[u] = __ldcs(&a.cval[p]); xo[u] = __ldcs(&a.ov.val[p]); }
-            es[u] = ok[u] ? a.e[p - a.entry0] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (!ok[u]) continue;
-            uint64_t i = p0 + (uint64_t)u * 32 - a.entry0;
-            float xf = xs[u], xof = xo[u];
-            double ei = es[u];
-            ColPack g = a.cpack[oc[u]];
-            if (pending) {
-                ei += (xf * (g.mu_prev * xof)) * dU;                               // run 0, factor f-1
-                ei += (xof * (mu_p * xf)) * g.delta;                               // run 1, factor f-1
-                a.e[i] = ei;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= a.ntiles) return;
+    const uint64_t p_begin = a.entry0 + ((uint64_t)t << a.ts_shift);
+    const uint64_t p_last = a.entry0 + a.n;
+    const uint64_t p_end = (p_begin + (1ull << a.ts_shift) < p_last) ? p_begin + (1ull << a.ts_shift) : p_last;
+
+    // window: lane l holds the constants of column jb + l
+    uint32_t j = __ldg(&a.tile_col0[t]), jb = 0;
+    uint64_t w_next = 0;
+    double w_mu = 0.0, w_h = 0.0, w_d = 0.0;
+    auto load_window = [&](uint32_t base) {
+        jb = base;
+        uint32_t cj = base + lane;
+        if (cj < a.c1) {
+            w_next = __ldg(&a.colptr[cj + 1]);
+            OwnPack o = a.own[cj];
+            w_mu = o.mu_red; w_h = o.h_oth; w_d = o.d_own;
+        } else { w_next = ~0ull; w_mu = w_h = w_d = 0.0; }
+    };
+    uint64_t cur_b = __ldg(&a.colptr[j]), next_b;
+    double mu, h_oth, d_own;
+    auto select = [&]() {
+        int s = (int)(j - jb);
+        next_b = __shfl_sync(FULL, w_next, s);
+        mu = __shfl_sync(FULL, w_mu, s); h_oth = __shfl_sync(FULL, w_h, s); d_own = __shfl_sync(FULL, w_d, s);
+    };
+    // column that holds entry `pos` (the columns between j and it are empty); pos < p_last
+    auto advance = [&](uint64_t pos) {
+        j++;
+        while (true) {
+            if (j >= jb + 32) load_window(j);
+            unsigned m = __ballot_sync(FULL, w_next > pos) & (FULL << (j - jb));
+            if (m) { j = jb + (uint32_t)__ffs(m) - 1; break; }
+            // a whole window of empty columns: binary search for the largest column with colptr[] <= pos
+            uint32_t lo = jb + 31, hi = a.c1;
+            while (hi - lo > 1) {
+                uint32_t mid = lo + (hi - lo) / 2;
+                if (__ldg(&a.colptr[mid]) <= pos) lo = mid; else hi = mid;
             }
-            if constexpr (REDUCE) {
-                double2 P = make_double2(g.mu, g.sg);
-                double xx = (double)(xf * xf);
-                if constexpr (KIND == KIND_VB_V) {
-                    double h = P.x * xof, h1 = P.y * xof * xof, h2 = P.x * P.x * xof * xof;
-                    A += xf * h * (ei + xf * mu * h);
-                    B += xx * h * h + xx * h1;
-                    C1 += xx * h1;
-                    C2 += xx * h2;
-                } else {   // KIND_MC_V
-                    double hh = xf * (P.x * xof);
-                    A += hh * ei;
-                    B += hh * hh;
-                }
-            }
+            j = lo;
+            load_window(j);
         }
-    }
-    if constexpr (REDUCE) {
+        cur_b = pos;
+        select();
+    };
+    load_window(j);
+    select();
+
+    double A = 0.0, B = 0.0, C1 = 0.0, C2 = 0.0;
+    auto emit = [&](uint64_t cb, uint64_t nb) {    // sums of the part of column j inside this tile
         A = warp_sum(A); B = warp_sum(B);
         if constexpr (KIND == KIND_VB_V) { C1 = warp_sum(C1); C2 = warp_sum(C2); }
         if (lane == 0) {
-            double2* out = reinterpret_cast<double2*>(a.partial + (size_t)t * 4);
-            out[0] = make_double2(A, B);
-            out[1] = make_double2(C1, C2);
+            bool whole = (cb >= p_begin) && (nb <= p_end);
+            double* out = whole ? a.colsum + (size_t)j * 4 : a.partial + ((size_t)t * 2 + (cb < p_begin ? 0 : 1)) * 4;
+            reinterpret_cast<double2*>(out)[0] = make_double2(A, B);
+            reinterpret_cast<double2*>(out)[1] = make_double2(C1, C2);
+        }
+        A = B = C1 = C2 = 0.0;
+    };
+    const bool pend = a.has_own | a.has_oth;
+    const bool need_rec = (IS_V && REDUCE) || a.has_oth || (a.has_own && !a.own_is_w);
+    bool done = false;
+
+    for (uint64_t p0 = p_begin; p0 < p_end && !done; p0 += 32 * U) {
+        bool ok[U]; uint32_t oc[U]; float xs[U], xo[U]; double es[U]; ColPack g[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            uint64_t p = p0 + (uint64_t)u * 32 + lane;
+            ok[u] = p < p_end;
+            oc[u] = ok[u] ? __ldcs(&a.oc[p]) : 0u;
+            xs[u] = 1.0f; xo[u] = 1.0f;
+            if constexpr (!ONES) if (ok[u]) { xs[u] = __ldcs(&a.xv[p]); xo[u] = __ldcs(&a.xo[p]); }
+            es[u] = ok[u] ? __ldcs(&a.e[p - a.entry0]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (need_rec && ok[u]) g[u] = a.rec[oc[u]];
+            else g[u] = ColPack{0.0, 0.0, 0.0, 0.0};
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t row_b = p0 + (uint64_t)u * 32;
+            if (row_b >= p_end || done) break;
+            const uint64_t row_e = (row_b + 32 < p_end) ? row_b + 32 : p_end;
+            const uint64_t p = row_b + lane;
+            const float xf = xs[u], xof = xo[u];
+            double ei = es[u];
+            uint64_t seg_b = row_b;
+            while (true) {
+                const uint64_t seg_e = next_b < row_e ? next_b : row_e;
+                if (p >= seg_b && p < seg_e) {
+                    if (a.has_own) ei += (xf * (a.own_is_w ? 1.0 : g[u].h4 * xof)) * d_own;
+                    if (a.has_oth) ei += (xof * (a.oth_is_w ? 1.0 : h_oth * xf)) * g[u].delta;
+                    if constexpr (REDUCE) {
+                        double xx = (double)(xf * xf);     // the reference forms x*x in float (FM_FLOAT), then promotes
+                        if constexpr (KIND == KIND_VB_W) {
+                            A += xf * (ei + xf * mu);                              // vb.h:537
+                            B += xx;                                               // vb.h:538
+                        } else if constexpr (KIND == KIND_MC_W) {
+                            A += xf * (ei - mu * xf);                              // mcmc.h:677
+                            B += xx;
+                        } else if constexpr (KIND == KIND_VB_V) {
+                            double h = g[u].mu * xof, h1 = g[u].sg * xof * xof, h2 = g[u].mu * g[u].mu * xof * xof;
+                            A += xf * h * (ei + xf * mu * h);                      // vb.h:594
+                            B += xx * h * h + xx * h1;                             // vb.h:595
+                            C1 += xx * h1;                                         // sum of pass-2 h1 (vb.h:629)
+                            C2 += xx * h2;                                         // sum of pass-2 h2 (vb.h:630)
+                        } else {                                                   // KIND_MC_V
+                            double hh = xf * (g[u].mu * xof);                      // mcmc.h:789
+                            A += hh * ei;                                          // mcmc.h:790
+                            B += hh * hh;                                          // mcmc.h:791
+                        }
+                    }
+                }
+                if (next_b > row_e) break;
+                // column j ends inside (or at the end of) this row
+                if constexpr (REDUCE) emit(cur_b, next_b);
+                seg_b = next_b;
+                if (seg_b >= p_end) { done = true; break; }
+                advance(seg_b);
+                if (seg_b >= row_e) break;
+            }
+            if (pend && ok[u]) __stcs(&a.e[p - a.entry0], ei);
         }
     }
+    if constexpr (REDUCE) if (!done) emit(cur_b, next_b);   // column j continues in the next tile
+    (void)IS_VB;
 }
 
 // pass 2 in CASE order (streaming): the run's columns are case-disjoint, so every case has at most one feature
@@ -1023,10 +1160,44 @@ __global__ void k_finish_iter(Scalars* sc, DevStats* st, int method) {
     sc->iter += 1;
 }
 
-// fused schedule: records of a column range before the first factor {mu, sigma, 0, 0}
-__global__ void k_pack_cols(uint32_t c0, uint32_t c1, const double2* __restrict__ pf, ColPack* __restrict__ cpack) {
+// stream schedule: records before the first step s0 (parameters p0): second-field columns are gathered by the first
+// pass, every column needs its own constants
+__global__ void k_pack_init(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, const double2* __restrict__ p0, ColPack* __restrict__ cpack,
+                            OwnPack* __restrict__ opack) {
+    uint32_t j = a0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= b1) return;
+    double2 P = p0[j];
+    if (j < a1) { opack[j] = OwnPack{P.x, 0.0, 0.0, 0.0}; cpack[j] = ColPack{0.0, 0.0, 0.0, 0.0}; }
+    else if (j >= b0) { opack[j] = OwnPack{P.x, P.x, 0.0, 0.0}; cpack[j] = ColPack{P.x, P.y, 0.0, 0.0}; }
+}
+// before the second field's flush pass: h4 = the first field's mean of the last step
+__global__ void k_pack_h4(uint32_t c0, uint32_t c1, const double2* __restrict__ p, ColPack* __restrict__ cpack) {
     uint32_t j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < c1) { double2 P = pf[j]; cpack[j] = ColPack{P.x, P.y, 0.0, 0.0}; }
+    if (j < c1) cpack[j].h4 = p[j].x;
+}
+// first column that intersects each implicit tile of a run (largest j in [c0, c1) with colptr[j] <= first entry of the tile)
+__global__ void k_tile_col0(const uint64_t* __restrict__ colptr, uint32_t c0, uint32_t c1, uint32_t ntiles, uint32_t ts_shift, uint32_t* __restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    uint64_t p = colptr[c0] + ((uint64_t)t << ts_shift);
+    uint32_t lo = c0, hi = c1;            // invariant: colptr[lo] <= p < colptr[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (colptr[mid] <= p) lo = mid; else hi = mid;
+    }
+    out[t] = lo;
+}
+// the second copy of the residuals, in the entry order of the second field: e2[p] = e[case of entry p]
+__global__ void k_gather_e(const double* __restrict__ e, const uint32_t* __restrict__ crow, uint32_t n, double* __restrict__ e2) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) e2[p] = e[crow[p]];
+}
+__global__ void __launch_bounds__(256) k_copies_max_diff(const double* __restrict__ e, const uint32_t* __restrict__ crow, uint32_t n,
+                                                         const double* __restrict__ e2, unsigned long long* __restrict__ out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    double d = fabs(e2[p] - e[crow[p]]);
+    if (!(d == 0.0)) atomicMax(out, (unsigned long long)__double_as_longlong(d == d ? d : INFINITY));   // non-negative doubles order like integers
 }
 
 // state pack/unpack

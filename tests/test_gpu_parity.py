@@ -46,6 +46,7 @@ def test_vb_two_field_onehot(built):
     ho, hg = orc.get_hyper(), L.engine.get_hyper()
     assert np.allclose(ho["sigma_v"], hg["sigma_v"], rtol=1e-9) and np.allclose(ho["sigma_w"], hg["sigma_w"], rtol=1e-9)
     assert np.max(np.abs(L.engine.predict() - orc.get_test_pred())) < 1e-9
+    assert L.engine.copies_max_diff() == 0.0     # the two residual copies of the stream schedule are bit-identical
 
 
 def test_vb_values_no_reorder(built):
@@ -150,9 +151,11 @@ def test_vb_block_cut_tiles(built, monkeypatch):
     """Big columns of gather runs are cut at case-block boundaries and executed block-major (L2 blocking):
     only the schedule changes, the sums per column keep their tile order."""
     monkeypatch.setenv("SVBFM_BLOCK_CASES", "1000")
+    monkeypatch.setenv("SVBFM_NO_FUSE", "1")          # two-field data would otherwise take the stream schedule
     tr, te = two_field(20000, 2000, 300, 200, seed=61)
     L, _ = run_vb(tr, te, K=3, iters=4, tile_entries=64)
-    assert L.engine.info()["num_tiles"] > 700
+    assert L.engine.info()["num_tiles"] > 700 and L.engine.info()["fused_schedule"] == 0
+    monkeypatch.delenv("SVBFM_NO_FUSE")
     monkeypatch.setenv("SVBFM_BLOCK_CASES", "700")
     tr, te = ragged(6000, 300, 30, seed=62)
     run_vb(tr, te, K=2, iters=3, tile_entries=32)
@@ -178,6 +181,39 @@ def test_fused_equals_unfused_schedule(built, monkeypatch):
             assert all(rel(x, y) < 1e-10 for x, y in zip(a, b)), (a, b)
         monkeypatch.delenv("SVBFM_NO_FUSE", raising=False)
         run_vb(tr, te, K=3, iters=4)
+
+
+@pytest.mark.parametrize("tile_entries", [32, 64, 256])
+def test_stream_schedule_small_tiles(built, tile_entries):
+    """Stream schedule with tiny implicit tiles: columns inside one tile, columns crossing tile borders (light spans) and
+    columns spanning many tiles (k_combine_span), empty columns in both fields, x != 1; both residual copies stay identical."""
+    for values, method in ((False, "vb"), (True, "vb"), (False, "mcmc")):
+        tr, te = two_field(30000, 3000, 400, 300, seed=91 + tile_entries, values=values)
+        if method == "vb":
+            L, _ = run_vb(tr, te, K=3, iters=4, tile_entries=tile_entries)
+        else:
+            orc = ob.Oracle("mcmc", tr, te, K=3, seed=42, do_sample=False, do_multilevel=False)
+            L = make_learner("mcmc", tr, te, 3, num_iter=4, do_sample=False, do_multilevel=False, tile_entries=tile_entries)
+            L.fm.reg0, L.fm.regw, L.fm.regv = 0.0, 0.0, 0.0
+            for s in L.learn(to_csc(tr), to_csc(te)):
+                o = orc.iterate()
+                assert rel(s.test_rmse, o.test_rmse) < 1e-7 and rel(s.train_stat, o.train_stat) < 1e-7
+        info = L.engine.info()
+        assert info["fused_schedule"] == 1 and info["num_tiles"] >= 2 * (30000 // tile_entries)
+        assert L.engine.copies_max_diff() == 0.0
+        L.engine.close()
+
+
+def test_stream_schedule_sorted_input(built):
+    """Cases already sorted by the first field (no re-ordering needed) still take the stream schedule."""
+    tr, te = two_field(12000, 1200, 200, 150, seed=95)
+    order = np.argsort(tr.col[0::2], kind="stable")
+    idx = np.stack([2 * order, 2 * order + 1], axis=1).ravel()
+    tr2 = ob.Csr(tr.rowptr.copy(), tr.col[idx].copy(), tr.val[idx].copy(), tr.y[order].copy())
+    L, _ = run_vb(tr2, te, K=3, iters=3)
+    info = L.engine.info()
+    assert info["fused_schedule"] == 1 and info["rows_reordered"] == 0
+    assert L.engine.copies_max_diff() == 0.0
 
 
 def test_reset_reuses_handle(built):
