@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvbfm.so")
+LIB_PATH = os.environ.get("SVBFM_LIB") or os.path.join(_HERE, "libsvbfm.so")   # SVBFM_LIB: another build of the same ABI
 
 VB, VB_ONLINE, MCMC = 0, 1, 2
 TRAIN, TEST = 0, 1

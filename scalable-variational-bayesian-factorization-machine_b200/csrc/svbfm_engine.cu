@@ -236,8 +236,14 @@ static void launch_stream(Engine* E, int side, bool has_own, bool own_is_w, bool
     constexpr int KIND = MCMC ? (W ? KIND_MC_W : KIND_MC_V) : (W ? KIND_VB_W : KIND_VB_V);
     unsigned grid = (a.ntiles + 7) / 8;
     if (!a.ntiles) return;
-    if (S.all_ones) k_stream<KIND, true, REDUCE><<<grid, 256, 0, E->stream>>>(a);
-    else k_stream<KIND, false, REDUCE><<<grid, 256, 0, E->stream>>>(a);
+    const bool steady = !W && has_own && !own_is_w && has_oth && !oth_is_w;
+    if (steady) {
+        if (S.all_ones) k_stream<KIND, true, REDUCE, true><<<grid, 256, 0, E->stream>>>(a);
+        else k_stream<KIND, false, REDUCE, true><<<grid, 256, 0, E->stream>>>(a);
+    } else {
+        if (S.all_ones) k_stream<KIND, true, REDUCE, false><<<grid, 256, 0, E->stream>>>(a);
+        else k_stream<KIND, false, REDUCE, false><<<grid, 256, 0, E->stream>>>(a);
+    }
     LAUNCHED(E);
 }
 
@@ -505,8 +511,11 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     Engine* E = new Engine();
     E->cfg = *cfg; E->dev = cfg->device; E->D = cfg->num_attribute; E->K = cfg->num_factor;
     E->tile_entries = cfg->tile_entries ? cfg->tile_entries : 1024;
+    if (const char* te = getenv("SVBFM_TILE_ENTRIES")) if (atoi(te) >= 32) E->tile_entries = (uint32_t)atoi(te);   // tuning knob
+    // implicit tiles of the stream schedule: 4096 entries unless the caller (or the knob) says otherwise
+    uint32_t ts = (cfg->tile_entries || getenv("SVBFM_TILE_ENTRIES")) ? E->tile_entries : 4096u;
     E->ts_shift = 5;
-    while (E->ts_shift < 20 && (2u << E->ts_shift) <= E->tile_entries) E->ts_shift++;
+    while (E->ts_shift < 20 && (2u << E->ts_shift) <= ts) E->ts_shift++;
     {   // stream-ordered allocations from the device's default pool, never handed back to the OS between learn() calls:
         // ingest allocates and frees tens of GB of scratch; plain cudaMalloc/cudaFree would dominate set_csc
         cudaMemPool_t pool;

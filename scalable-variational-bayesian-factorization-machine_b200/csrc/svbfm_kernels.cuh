@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
             double2 x = p[0], y = p[1];
             A = x.x; B = x.y; C1 = y.x; C2 = y.y;
         }
+        if constexpr (KIND == KIND_VB_V) B = C1 + C2;      // vb.h:595 (k_stream leaves the B slot empty)
     } else load_colsum(j, a.col_tile0, a.partial, a.colsum, a.from_colsum, A, B, C1, C2);
     uint32_t g = a.group[j];
     double hy = (a.f < 0) ? a.hyper[g] : a.hyper[(size_t)g * a.K + a.f];
@@ -511,41 +512,147 @@ struct StreamArgs {
     double* partial;          // [ntiles of the run][2][4]
 };
 
-template <int KIND, bool ONES, bool REDUCE>
-__global__ void __launch_bounds__(256) k_stream(StreamArgs a) {
+// four sums over the warp with 6 shuffle steps instead of 20: the lanes first split the values among themselves
+// (xor 16: two each, xor 8: one each), then reduce their own. Result: lane 0 -> v0, lane 8 -> v1, lane 16 -> v2,
+// lane 24 -> v3 (returned in every lane's `k`; lanes with (lane & 7) == 0 hold totals). Fixed order: deterministic.
+__device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, double v3, uint32_t lane) {
+    const bool up16 = lane & 16, up8 = lane & 8;
+    double k0 = up16 ? v2 : v0, k1 = up16 ? v3 : v1;
+    k0 += __shfl_xor_sync(0xffffffffu, up16 ? v0 : v2, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, up16 ? v1 : v3, 16);
+    double k = up8 ? k1 : k0;
+    k += __shfl_xor_sync(0xffffffffu, up8 ? k0 : k1, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;
+}
+// two sums: lane 0 -> v0, lane 16 -> v1
+__device__ __forceinline__ double warp_sum2(double v0, double v1, uint32_t lane) {
+    const bool up16 = lane & 16;
+    double k = up16 ? v1 : v0;
+    k += __shfl_xor_sync(0xffffffffu, up16 ? v0 : v1, 16);
+    k += __shfl_xor_sync(0xffffffffu, k, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;
+}
+
+// the pending updates of one entry. Written with explicit intrinsics: both residual copies must round identically
+// whichever code path (fast / general, first / second field) applies them.
+template <bool ONES>
+__device__ __forceinline__ double apply_pending(double ei, float xf, float xof, const ColPack& g, double h_oth, double d_own,
+                                                bool has_own, bool own_is_w, bool has_oth, bool oth_is_w) {
+    if (has_own) {
+        double H = own_is_w ? 1.0 : (ONES ? g.h4 : __dmul_rn(g.h4, (double)xof));
+        ei = __fma_rn(ONES ? H : __dmul_rn((double)xf, H), d_own, ei);
+    }
+    if (has_oth) {
+        double H = oth_is_w ? 1.0 : (ONES ? h_oth : __dmul_rn(h_oth, (double)xf));
+        ei = __fma_rn(ONES ? H : __dmul_rn((double)xof, H), g.delta, ei);
+    }
+    return ei;
+}
+
+// per-entry terms of pass 1 (vb.h:537-538, 587-596 / mcmc.h:677, 785-792)
+template <int KIND>
+__device__ __forceinline__ void entry_terms(double ei, float xf, float xof, const ColPack& g, double mu, double& A, double& B, double& C1, double& C2) {
+    double xx = (double)(xf * xf);     // the reference forms x*x in float (FM_FLOAT), then promotes
+    if constexpr (KIND == KIND_VB_W) {
+        A += xf * (ei + xf * mu);                              // vb.h:537
+        B += xx;                                               // vb.h:538
+    } else if constexpr (KIND == KIND_MC_W) {
+        A += xf * (ei - mu * xf);                              // mcmc.h:677
+        B += xx;
+    } else if constexpr (KIND == KIND_VB_V) {
+        double h = g.mu * xof, h1 = g.sg * xof * xof, h2 = g.mu * g.mu * xof * xof;
+        A += xf * h * (ei + xf * mu * h);                      // vb.h:594
+        C1 += xx * h1;                                         // sum of pass-2 h1 (vb.h:629)
+        C2 += xx * h2;                                         // sum of pass-2 h2 (vb.h:630)
+        (void)B;                                               // vb.h:595: B = sum x^2 h^2 + x^2 h1 = C2 + C1, formed in k_finalize
+    } else {                                                   // KIND_MC_V
+        double hh = xf * (g.mu * xof);                         // mcmc.h:789
+        A += hh * ei;                                          // mcmc.h:790
+        B += hh * hh;                                          // mcmc.h:791
+    }
+}
+
+// STEADY: both sides have a pending v update (every pass of the factor loop but the first ones): no runtime flags
+#ifndef SV_STREAM_U
+#define SV_STREAM_U 2        // rows of 32 entries per batch (measured: 2 x 4 CTAs/SM beats 4 x 2, gpurun_out/tune_*)
+#endif
+#ifndef SV_STREAM_MINB
+#define SV_STREAM_MINB 3     // resident CTAs per SM the register allocation aims at (72 registers, no spills)
+#endif
+template <int KIND, bool ONES, bool REDUCE, bool STEADY>
+__global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
     constexpr bool IS_V = (KIND == KIND_VB_V || KIND == KIND_MC_V);
-    constexpr bool IS_VB = (KIND == KIND_VB_V || KIND == KIND_VB_W);
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int U = 4;
+    constexpr int U = SV_STREAM_U;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= a.ntiles) return;
-    const uint64_t p_begin = a.entry0 + ((uint64_t)t << a.ts_shift);
-    const uint64_t p_last = a.entry0 + a.n;
-    const uint64_t p_end = (p_begin + (1ull << a.ts_shift) < p_last) ? p_begin + (1ull << a.ts_shift) : p_last;
+    // entry positions relative to the run (32 bit)
+    const uint32_t q_begin = t << a.ts_shift;
+    const uint32_t q_end = (a.n - q_begin > (1u << a.ts_shift)) ? q_begin + (1u << a.ts_shift) : a.n;
+    const uint32_t* __restrict__ ocp = a.oc + a.entry0;
+    const float* __restrict__ xvp = ONES ? nullptr : a.xv + a.entry0;
+    const float* __restrict__ xop = ONES ? nullptr : a.xo + a.entry0;
+    double* __restrict__ ep = a.e;
+    const bool has_own = STEADY ? true : (a.has_own != 0), own_is_w = STEADY ? false : (a.own_is_w != 0);
+    const bool has_oth = STEADY ? true : (a.has_oth != 0), oth_is_w = STEADY ? false : (a.oth_is_w != 0);
+    const bool pend = has_own | has_oth;
+    const bool need_rec = (IS_V && REDUCE) || has_oth || (has_own && !own_is_w);
+
+    // next batch of the streams (issued one batch ahead)
+    uint32_t oc_n[U]; float xs_n[U], xo_n[U]; double e_n[U];
+    auto load_batch = [&](uint32_t q) {
+        if (q_end - q >= 32 * U) {          // a whole batch: no predicates
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                uint32_t k = q + u * 32 + lane;
+                oc_n[u] = __ldcs(ocp + k);
+                xs_n[u] = 1.0f; xo_n[u] = 1.0f;
+                if constexpr (!ONES) { xs_n[u] = __ldcs(xvp + k); xo_n[u] = __ldcs(xop + k); }
+                e_n[u] = __ldcs(ep + k);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                uint32_t k = q + u * 32 + lane;
+                bool ok = k < q_end;
+                oc_n[u] = ok ? __ldcs(ocp + k) : 0u;
+                xs_n[u] = 1.0f; xo_n[u] = 1.0f;
+                if constexpr (!ONES) if (ok) { xs_n[u] = __ldcs(xvp + k); xo_n[u] = __ldcs(xop + k); }
+                e_n[u] = ok ? __ldcs(ep + k) : 0.0;
+            }
+        }
+    };
+    load_batch(q_begin);
 
     // window: lane l holds the constants of column jb + l
     uint32_t j = __ldg(&a.tile_col0[t]), jb = 0;
-    uint64_t w_next = 0;
+    uint32_t w_next = 0;                     // relative end of the column (clamped: ~0u beyond the run)
     double w_mu = 0.0, w_h = 0.0, w_d = 0.0;
     auto load_window = [&](uint32_t base) {
         jb = base;
         uint32_t cj = base + lane;
         if (cj < a.c1) {
-            w_next = __ldg(&a.colptr[cj + 1]);
+            w_next = (uint32_t)(__ldg(&a.colptr[cj + 1]) - a.entry0);
             OwnPack o = a.own[cj];
             w_mu = o.mu_red; w_h = o.h_oth; w_d = o.d_own;
-        } else { w_next = ~0ull; w_mu = w_h = w_d = 0.0; }
+        } else { w_next = ~0u; w_mu = w_h = w_d = 0.0; }
     };
-    uint64_t cur_b = __ldg(&a.colptr[j]), next_b;
+    uint32_t cur_b = (uint32_t)(__ldg(&a.colptr[j]) - a.entry0), next_b;
     double mu, h_oth, d_own;
     auto select = [&]() {
         int s = (int)(j - jb);
         next_b = __shfl_sync(FULL, w_next, s);
         mu = __shfl_sync(FULL, w_mu, s); h_oth = __shfl_sync(FULL, w_h, s); d_own = __shfl_sync(FULL, w_d, s);
     };
-    // column that holds entry `pos` (the columns between j and it are empty); pos < p_last
-    auto advance = [&](uint64_t pos) {
+    // column that holds entry `pos` (the columns between j and it are empty); pos < n
+    auto advance = [&](uint32_t pos) {
         j++;
         while (true) {
             if (j >= jb + 32) load_window(j);
@@ -555,7 +662,7 @@ __global__ void __launch_bounds__(256) k_stream(StreamArgs a) {
             uint32_t lo = jb + 31, hi = a.c1;
             while (hi - lo > 1) {
                 uint32_t mid = lo + (hi - lo) / 2;
-                if (__ldg(&a.colptr[mid]) <= pos) lo = mid; else hi = mid;
+                if (__ldg(&a.colptr[mid]) - a.entry0 <= (uint64_t)pos) lo = mid; else hi = mid;
             }
             j = lo;
             load_window(j);
@@ -567,85 +674,77 @@ __global__ void __launch_bounds__(256) k_stream(StreamArgs a) {
     select();
 
     double A = 0.0, B = 0.0, C1 = 0.0, C2 = 0.0;
-    auto emit = [&](uint64_t cb, uint64_t nb) {    // sums of the part of column j inside this tile
-        A = warp_sum(A); B = warp_sum(B);
-        if constexpr (KIND == KIND_VB_V) { C1 = warp_sum(C1); C2 = warp_sum(C2); }
-        if (lane == 0) {
-            bool whole = (cb >= p_begin) && (nb <= p_end);
-            double* out = whole ? a.colsum + (size_t)j * 4 : a.partial + ((size_t)t * 2 + (cb < p_begin ? 0 : 1)) * 4;
-            reinterpret_cast<double2*>(out)[0] = make_double2(A, B);
-            reinterpret_cast<double2*>(out)[1] = make_double2(C1, C2);
+    auto emit = [&](uint32_t cb, uint32_t nb) {    // sums of the part of column j inside this tile -> {A, B, C1, C2}
+        bool whole = (cb >= q_begin) && (nb <= q_end);
+        double* out = whole ? a.colsum + (size_t)j * 4 : a.partial + ((size_t)t * 2 + (cb < q_begin ? 0 : 1)) * 4;
+        if constexpr (KIND == KIND_VB_V) {          // slot B stays 0: B = C1 + C2 (k_finalize)
+            double k = warp_sum4(A, 0.0, C1, C2, lane);
+            if ((lane & 7) == 0) out[lane >> 3] = k;
+        } else {
+            double k = warp_sum2(A, B, lane);
+            if ((lane & 15) == 0) out[lane >> 4] = k;
         }
         A = B = C1 = C2 = 0.0;
     };
-    const bool pend = a.has_own | a.has_oth;
-    const bool need_rec = (IS_V && REDUCE) || a.has_oth || (a.has_own && !a.own_is_w);
     bool done = false;
 
-    for (uint64_t p0 = p_begin; p0 < p_end && !done; p0 += 32 * U) {
-        bool ok[U]; uint32_t oc[U]; float xs[U], xo[U]; double es[U]; ColPack g[U];
+    for (uint32_t q0 = q_begin; q0 < q_end && !done; q0 += 32 * U) {
+        uint32_t oc[U]; float xs[U], xo[U]; double es[U]; ColPack g[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            uint64_t p = p0 + (uint64_t)u * 32 + lane;
-            ok[u] = p < p_end;
-            oc[u] = ok[u] ? __ldcs(&a.oc[p]) : 0u;
-            xs[u] = 1.0f; xo[u] = 1.0f;
-            if constexpr (!ONES) if (ok[u]) { xs[u] = __ldcs(&a.xv[p]); xo[u] = __ldcs(&a.xo[p]); }
-            es[u] = ok[u] ? __ldcs(&a.e[p - a.entry0]) : 0.0;
+        for (int u = 0; u < U; u++) { oc[u] = oc_n[u]; xs[u] = xs_n[u]; xo[u] = xo_n[u]; es[u] = e_n[u]; }
+        const bool full = (q_end - q0 >= 32 * U);
+        if ((STEADY || need_rec) && full) {
+#pragma unroll
+            for (int u = 0; u < U; u++) g[u] = a.rec[oc[u]];
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (need_rec && q0 + u * 32 + lane < q_end) g[u] = a.rec[oc[u]];
+                else g[u] = ColPack{0.0, 0.0, 0.0, 0.0};
+            }
+        }
+        if (q_end - q0 > 32 * U) load_batch(q0 + 32 * U);
+        if (full && next_b >= q0 + 32 * U) {
+            // the whole batch lies inside column j: no per-lane predicates
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                double ei = apply_pending<ONES>(es[u], xs[u], xo[u], g[u], h_oth, d_own, has_own, own_is_w, has_oth, oth_is_w);
+                if (pend) __stcs(ep + q0 + u * 32 + lane, ei);
+                if constexpr (REDUCE) entry_terms<KIND>(ei, xs[u], xo[u], g[u], mu, A, B, C1, C2);
+            }
+            if (next_b == q0 + 32 * U) {             // column j ends exactly with the batch
+                if constexpr (REDUCE) emit(cur_b, next_b);
+                if (next_b >= q_end) done = true;
+                else advance(next_b);
+            }
+            continue;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            if (need_rec && ok[u]) g[u] = a.rec[oc[u]];
-            else g[u] = ColPack{0.0, 0.0, 0.0, 0.0};
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint64_t row_b = p0 + (uint64_t)u * 32;
-            if (row_b >= p_end || done) break;
-            const uint64_t row_e = (row_b + 32 < p_end) ? row_b + 32 : p_end;
-            const uint64_t p = row_b + lane;
-            const float xf = xs[u], xof = xo[u];
+            const uint32_t row_b = q0 + u * 32;
+            if (row_b >= q_end || done) break;
+            const uint32_t row_e = (q_end - row_b > 32) ? row_b + 32 : q_end;
+            const uint32_t k = row_b + lane;
             double ei = es[u];
-            uint64_t seg_b = row_b;
+            uint32_t seg_b = row_b;
             while (true) {
-                const uint64_t seg_e = next_b < row_e ? next_b : row_e;
-                if (p >= seg_b && p < seg_e) {
-                    if (a.has_own) ei += (xf * (a.own_is_w ? 1.0 : g[u].h4 * xof)) * d_own;
-                    if (a.has_oth) ei += (xof * (a.oth_is_w ? 1.0 : h_oth * xf)) * g[u].delta;
-                    if constexpr (REDUCE) {
-                        double xx = (double)(xf * xf);     // the reference forms x*x in float (FM_FLOAT), then promotes
-                        if constexpr (KIND == KIND_VB_W) {
-                            A += xf * (ei + xf * mu);                              // vb.h:537
-                            B += xx;                                               // vb.h:538
-                        } else if constexpr (KIND == KIND_MC_W) {
-                            A += xf * (ei - mu * xf);                              // mcmc.h:677
-                            B += xx;
-                        } else if constexpr (KIND == KIND_VB_V) {
-                            double h = g[u].mu * xof, h1 = g[u].sg * xof * xof, h2 = g[u].mu * g[u].mu * xof * xof;
-                            A += xf * h * (ei + xf * mu * h);                      // vb.h:594
-                            B += xx * h * h + xx * h1;                             // vb.h:595
-                            C1 += xx * h1;                                         // sum of pass-2 h1 (vb.h:629)
-                            C2 += xx * h2;                                         // sum of pass-2 h2 (vb.h:630)
-                        } else {                                                   // KIND_MC_V
-                            double hh = xf * (g[u].mu * xof);                      // mcmc.h:789
-                            A += hh * ei;                                          // mcmc.h:790
-                            B += hh * hh;                                          // mcmc.h:791
-                        }
-                    }
+                const uint32_t seg_e = next_b < row_e ? next_b : row_e;
+                if (k >= seg_b && k < seg_e) {
+                    ei = apply_pending<ONES>(ei, xs[u], xo[u], g[u], h_oth, d_own, has_own, own_is_w, has_oth, oth_is_w);
+                    if constexpr (REDUCE) entry_terms<KIND>(ei, xs[u], xo[u], g[u], mu, A, B, C1, C2);
                 }
                 if (next_b > row_e) break;
                 // column j ends inside (or at the end of) this row
                 if constexpr (REDUCE) emit(cur_b, next_b);
                 seg_b = next_b;
-                if (seg_b >= p_end) { done = true; break; }
+                if (seg_b >= q_end) { done = true; break; }
                 advance(seg_b);
                 if (seg_b >= row_e) break;
             }
-            if (pend && ok[u]) __stcs(&a.e[p - a.entry0], ei);
+            if (pend && k < row_e) __stcs(ep + k, ei);
         }
     }
     if constexpr (REDUCE) if (!done) emit(cur_b, next_b);   // column j continues in the next tile
-    (void)IS_VB;
 }
 
 // pass 2 in CASE order (streaming): the run's columns are case-disjoint, so every case has at most one feature
