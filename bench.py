@@ -41,7 +41,11 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=400_000, help="ratings in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+    ap.add_argument("--shard-by", default="user_block", choices=["user_block", "case_range"],
+                    help="strong scaling: how the ratings are split over the GPUs")
+    ap.add_argument("--col-cost", type=float, default=90.0,
+                    help="user-block shards are balanced by ratings + col_cost x users (a column costs the stream pass about as much as 90 entries)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU holds its own N ratings (global N x gpus); strong: the N ratings are split over the GPUs")
     return ap.parse_args()
 
@@ -176,13 +180,52 @@ def main():
     # ---- synthetic data on the device. strong: the same N ratings on every rank, this rank keeps a contiguous shard;
     #      weak: every rank draws its own N ratings (same planted model, different seed): the global data set has N x world cases
     weak = (a.scaling == "weak") and world > 1
-    u, it, y = synth.ratings_torch(N, U, I, 20261018 + (1000 * rank if weak else 0), dev)
-    ut, itt, yt = synth.ratings_torch(Nt, U, I, 20261019 + (1000 * rank if weak else 0), dev)
+    block = a.shard_by == "user_block"
     D = U + I + (0 if a.method == "vb_online" else 1)     # libfm.cpp:215: max(train, test num_feature) + 1 (vb_online: max id + 1)
+    if weak and block:
+        # the global data set is `world` draws of N ratings (seeds s, s+1000, ..); this rank keeps the ratings of its user block,
+        # cut where the expected (Zipf) mass is rank/world, so every GPU holds about N ratings and owns its users exclusively
+        exp_n = synth.user_mass_torch(U, I, dev) * float(N * world)          # expected ratings per user
+        cum = torch.cumsum(exp_n + a.col_cost * (1.0 - torch.exp(-exp_n)), 0)  # a column costs about as much as col_cost entries
+        cuts = torch.searchsorted(cum, torch.tensor([float(cum[-1]) * r / world for r in range(1, world)], device=dev, dtype=cum.dtype))
+        bnd = [0] + [int(x) for x in cuts.cpu()] + [U]
+        parts = [synth.ratings_torch(N, U, I, 20261018 + 1000 * c, dev, user_range=(bnd[rank], bnd[rank + 1])) for c in range(world)]
+        u, it, y = (torch.cat([p_[k] for p_ in parts]) for k in range(3))
+        del parts, cum
+    else:
+        u, it, y = synth.ratings_torch(N, U, I, 20261018 + (1000 * rank if weak else 0), dev)
+    ut, itt, yt = synth.ratings_torch(Nt, U, I, 20261019 + (1000 * rank if weak else 0), dev)
+    ymin, ymax = 1.0, 5.0                                  # the synthetic targets span {1..5} on every shard
     N_global, Nt_global = (N * world, Nt * world) if weak else (N, Nt)
 
     def shard(n):
         return (0, n) if weak else ((n * rank) // world, (n * (rank + 1)) // world)
+
+    shard_mode = "single GPU"
+    if world > 1 and not weak:
+        if a.shard_by == "user_block":
+            # partition the ratings by user block, balanced by number of ratings: this rank keeps the ratings of the
+            # users [b_rank, b_rank+1); the engine detects the disjoint blocks and needs no exchange for the user field
+            cnt = torch.bincount(u, minlength=U).to(torch.float64)
+            cum = torch.cumsum(cnt + a.col_cost * (cnt > 0), 0)                # a column costs about as much as col_cost entries
+            cuts = torch.searchsorted(cum, torch.tensor([float(cum[-1]) * r / world for r in range(1, world)], device=dev, dtype=cum.dtype))
+            b = [0] + [int(x) for x in cuts.cpu()] + [U]
+            keep = torch.nonzero((u >= b[rank]) & (u < b[rank + 1])).squeeze(1)
+            u, it, y = u[keep].contiguous(), it[keep].contiguous(), y[keep].contiguous()
+            del keep, cum, cnt
+            shard_mode = f"{world} shards by user block (balanced by ratings), NCCL allreduce of the item column sums per factor, user blocks broadcast once per iteration"
+        else:
+            lo_, hi_ = shard(N)
+            u, it, y = u[lo_:hi_].contiguous(), it[lo_:hi_].contiguous(), y[lo_:hi_].contiguous()
+            shard_mode = f"{world} contiguous case shards, NCCL allreduce of the column sums of both fields per factor"
+        tlo_, thi_ = shard(Nt)
+        ut, itt, yt = ut[tlo_:thi_].contiguous(), itt[tlo_:thi_].contiguous(), yt[tlo_:thi_].contiguous()
+    elif weak and block:
+        shard_mode = (f"{world} GPUs x ~{N} ratings each (weak scaling: {world} x {N} ratings globally, sharded by user block), NCCL allreduce of the item "
+                      "column sums per factor, user blocks broadcast once per iteration")
+    elif weak:
+        shard_mode = f"{world} GPUs x {N} ratings each (weak scaling), NCCL allreduce of the column sums of both fields per factor"
+    n_mine, nt_mine = int(u.numel()), int(ut.numel())      # the arrays now hold this rank's cases only
 
     def host_csc(uu, ii, yy, lo, hi):
         colptr, case_id = synth.csc_two_field_torch(uu[lo:hi], ii[lo:hi], U, I)
@@ -196,18 +239,18 @@ def main():
         d._keep = (cp, ci, x, ty)
         return d
 
-    lo, hi = shard(N)
-    tlo, thi = shard(Nt)
+    lo, hi = 0, n_mine
+    tlo, thi = 0, nt_mine
     train = host_csc(u, it, y, lo, hi)
     test = host_csc(ut, itt, yt, tlo, thi)
-    ymin, ymax = float(y.min()), float(y.max())
     del u, it, y, ut, itt, yt
     torch.cuda.empty_cache()
     g = torch.Generator(device=dev); g.manual_seed(42)
     state = dict(w0_mean=0.0, w0_var=0.0 if a.method == "mcmc" else 0.02,
                  w_mean=(0.1 * torch.randn(D, generator=g, device=dev, dtype=torch.float64)).cpu().pin_memory().numpy(),
-                 w_var=np.full(D, 0.02), v_mean=(0.1 * torch.randn(K, D, generator=g, device=dev, dtype=torch.float64)).cpu().pin_memory().numpy(),
-                 v_var=np.full((K, D), 0.02))
+                 w_var=torch.full((D,), 0.02, dtype=torch.float64).pin_memory().numpy(),
+                 v_mean=(0.1 * torch.randn(K, D, generator=g, device=dev, dtype=torch.float64)).cpu().pin_memory().numpy(),
+                 v_var=torch.full((K, D), 0.02, dtype=torch.float64).pin_memory().numpy())
     torch.cuda.empty_cache()
 
     def new_uid():
@@ -280,6 +323,12 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dev_ms, sweep_ms, wall_ms = [float(x) for x in tt.cpu()]
+    mine = torch.tensor([sum(v["ms"] for k, v in prof.items() if k.startswith("stream")) / a.steps, float(hi - lo)], dtype=torch.float64, device=dev)
+    per_rank = [mine.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine)
+    rank_stream_ms = [round(float(x[0]), 2) for x in per_rank]
+    rank_ratings = [int(x[1]) for x in per_rank]
     ms_per_step = dev_ms / a.steps
     value = N_global * K / (ms_per_step * 1e-3)
     last = hist[-1]
@@ -295,7 +344,7 @@ def main():
         E2 = sv.Engine(a.method, D, K, 1, 1, ymin, ymax, device=local, seed=42)    # long-lived handle (device context + communicator)
         if world > 1:
             E2.comm_init(new_uid(), rank, world)
-        for s in range(max(1, min(a.steps, 3)) + 1):
+        for s in range(5):
             phase_ms.clear()
             barrier()
             t0 = time.perf_counter()
@@ -306,13 +355,14 @@ def main():
             barrier()
             ts.append(time.perf_counter() - t0)
         E2.close()
-        t_e2e = sum(ts[1:]) / len(ts[1:])          # first pass warms allocator / module load
+        t_e2e = float(np.median(ts[1:]))           # first pass warms the allocator; median of the other four (H2D / allocator hiccups)
         tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_e2e = float(tt.cpu()[0])
         e2e = {"value": N_global * K / t_e2e, "unit": "ratings*k/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 64,
-               "ms_per_step": t_e2e * 1e3, "last_step_phases_ms": dict(phase_ms), "step": "reset + set_csc(train,test) from pinned host + set_state + begin + 1 iteration + stats readback, on a long-lived handle"}
+               "ms_per_step": t_e2e * 1e3, "last_step_phases_ms": dict(phase_ms), "passes_ms": [t * 1e3 for t in ts],
+               "step": "reset + set_csc(train,test) from pinned host + set_state + begin + 1 iteration + stats readback, on a long-lived handle; median of 4 passes after 1 warm-up"}
 
     if rank != 0:
         if world > 1:
@@ -370,7 +420,7 @@ def main():
     out = {"metric": a.method + "_sweep_ratings_x_k_per_sec", "value": value, "unit": "ratings*k/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload, "global_ratings": N_global,
-                      "sharding": (f"{world} case shards of {hi - lo} ratings each ({a.scaling} scaling), NCCL allreduce of the column sums per field run" if world > 1 else "single GPU"),
+                      "sharding": shard_mode, "ratings_per_rank": rank_ratings, "stream_ms_per_rank": rank_stream_ms, "exclusive_blocks": info0.get("exclusive_blocks", 0),
                       "l2": "inputs (residuals + design matrix) are far larger than the 126 MB L2; no flush needed",
                       "field_runs": info0["num_runs"], "tiles": info0["num_tiles"], "rows_reordered": info0["rows_reordered"],
                       "fused_schedule": info0.get("fused_schedule", 0)},

@@ -155,14 +155,15 @@ typedef struct svbfm_info {
     uint32_t rows_reordered;
     uint32_t world_size;
     uint32_t fused_schedule;   /* 1 when the two-field stream schedule (two residual copies, k_stream) is in use */
-    uint32_t reserved;
+    uint32_t exclusive_blocks; /* multi-GPU: 1 when the ranks hold disjoint column blocks of the first field (no exchange for it inside the sweep) */
 } svbfm_info;
 int svbfm_get_info(svbfm_t* h, svbfm_info* out);
 /* per-kernel-class device time (CUDA events on the launching stream), for bench.py's roofline block.
  * classes: 0 reduce_v (k_sweep_reduce), 1 combine+finalize_v, 2 apply_v, 3 reduce_w, 4 combine+finalize_w, 5 apply_w,
  *          stream schedule (k_stream): 6 stream_v of the first field, 8 stream_v of the second field, 9 stream_w (both fields),
- *          7 the two flush passes at the end of an iteration */
-#define SVBFM_PROFILE_CLASSES 10
+ *          7 the two flush passes at the end of an iteration; 10 NCCL collectives of the sharded stream schedule (inside the
+ *          classes 1 / 4 spans; includes the wait for the slowest rank); 11 the block exchange after the sweep */
+#define SVBFM_PROFILE_CLASSES 12
 int svbfm_set_profile(svbfm_t* h, int32_t enabled);
 int svbfm_get_profile(svbfm_t* h, double ms[SVBFM_PROFILE_CLASSES], uint64_t launches[SVBFM_PROFILE_CLASSES]); /* reads and resets */
 /* run on an externally owned CUDA stream (cudaStream_t); NULL restores the handle's own stream */

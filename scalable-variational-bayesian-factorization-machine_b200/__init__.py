@@ -51,7 +51,7 @@ class Info(C.Structure):
     _fields_ = [("num_runs", C.c_uint32), ("num_tiles", C.c_uint32), ("uniform_row_nnz", C.c_uint32),
                 ("all_ones", C.c_uint32), ("kernel_launches", C.c_uint64), ("device_bytes", C.c_uint64),
                 ("train_nnz", C.c_uint64), ("rows_reordered", C.c_uint32), ("world_size", C.c_uint32),
-                ("fused_schedule", C.c_uint32), ("reserved", C.c_uint32)]
+                ("fused_schedule", C.c_uint32), ("exclusive_blocks", C.c_uint32)]
 
 
 # every symbol include/svbfm.h declares (tests/test_abi.py checks the library exports exactly these)
@@ -258,7 +258,7 @@ class Engine:
         self._ck(lib().svbfm_set_profile(self.h, int(on)), "svbfm_set_profile")
 
     def get_profile(self):
-        names = ["reduce_v", "finalize_v", "apply_v", "reduce_w", "finalize_w", "apply_w", "stream_v_field0", "stream_flush", "stream_v_field1", "stream_w"]
+        names = ["reduce_v", "finalize_v", "apply_v", "reduce_w", "finalize_w", "apply_w", "stream_v_field0", "stream_flush", "stream_v_field1", "stream_w", "collectives", "block_exchange"]
         ms = np.zeros(len(names))     # SVBFM_PROFILE_CLASSES
         cnt = np.zeros(len(names), dtype=np.uint64)
         self._ck(lib().svbfm_get_profile(self.h, _p(ms), _p(cnt)), "svbfm_get_profile")

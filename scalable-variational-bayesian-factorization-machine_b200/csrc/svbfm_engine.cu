@@ -24,6 +24,10 @@ struct Nccl {
     int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Id128, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 }  // namespace
@@ -39,9 +43,14 @@ static bool nccl_load() {
         g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
         g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
         g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+        g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclBroadcast");
+        g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
+        g_nccl.GroupStart = (int (*)())dlsym(g_nccl.lib, "ncclGroupStart");
+        g_nccl.GroupEnd = (int (*)())dlsym(g_nccl.lib, "ncclGroupEnd");
         g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
     });
-    return g_nccl.lib && g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
+    return g_nccl.lib && g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy && g_nccl.Broadcast &&
+           g_nccl.AllGather && g_nccl.GroupStart && g_nccl.GroupEnd;
 }
 
 namespace svb {
@@ -101,6 +110,74 @@ struct ProfScope {
     }
 };
 
+namespace svb {
+// Do the ranks hold disjoint, rank-ordered ranges of run 0's columns? (cases sharded by blocks of the first field)
+int detect_exclusive_blocks(Engine* E) {
+    E->excl0 = false;
+    if (E->world <= 1 || E->runs.size() != 2 || getenv("SVBFM_NO_EXCL")) return 0;
+    const Run& r0 = E->runs[0];
+    const std::vector<uint64_t>& cp = E->tr.h_colptr;
+    uint32_t lo = r0.col_end, hi = r0.col_begin;            // first / one past the last non-empty column of this rank
+    for (uint32_t j = r0.col_begin; j < r0.col_end; j++)
+        if (cp[j + 1] > cp[j]) { if (lo == r0.col_end) lo = j; hi = j + 1; }
+    std::vector<uint32_t> v((size_t)E->world * 2, 0u);
+    v[(size_t)E->rank * 2] = lo; v[(size_t)E->rank * 2 + 1] = hi;
+    uint32_t* d = nullptr;
+    SV_CUDA(E, cudaMallocAsync((void**)&d, v.size() * 4, E->stream));
+    SV_CUDA(E, cudaMemcpyAsync(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice, E->stream));
+    if (int rc = allreduce(E, d, v.size(), 3 /*ncclUint32*/, 0 /*ncclSum*/)) return rc;
+    SV_CUDA(E, cudaMemcpyAsync(v.data(), d, v.size() * 4, cudaMemcpyDeviceToHost, E->stream));
+    SV_CUDA(E, cudaStreamSynchronize(E->stream));
+    cudaFreeAsync(d, E->stream);
+    bool ok = true;
+    uint32_t prev_hi = r0.col_begin;
+    for (int r = 0; r < E->world; r++) {
+        uint32_t l = v[(size_t)r * 2], h = v[(size_t)r * 2 + 1];
+        if (h <= l) continue;                              // no cases on that rank
+        if (l < prev_hi) ok = false;
+        prev_hi = h;
+    }
+    if (!ok) return 0;
+    E->blk.assign((size_t)E->world + 1, r0.col_end);
+    for (int r = E->world - 1; r >= 1; r--) {
+        uint32_t l = v[(size_t)r * 2], h = v[(size_t)r * 2 + 1];
+        E->blk[r] = (h > l) ? l : E->blk[r + 1];
+    }
+    E->blk[0] = r0.col_begin;
+    E->excl0 = true;
+    return 0;
+}
+}  // namespace svb
+
+// stream schedule, exclusive blocks: after the sweep every rank hands the parameters of its block of run 0 (w and every
+// factor) to the others: pack [rows][maxcnt] -> one ncclAllGather -> unpack the other ranks' blocks
+static int exchange_blocks(Engine* E) {
+    if (!E->excl0) return 0;
+    ProfScope pc(E, 11);
+    cudaStream_t st = E->stream;
+    const uint32_t rows = (E->cfg.k1 ? 1u : 0u) + (uint32_t)E->K;
+    uint32_t maxcnt = 0;
+    for (int r = 0; r < E->world; r++) maxcnt = std::max(maxcnt, E->blk[r + 1] - E->blk[r]);
+    if (!rows || !maxcnt) return 0;
+    const size_t per_rank = (size_t)rows * maxcnt;                         // double2 elements
+    if (E->xchg_cap < per_rank * (size_t)(E->world + 1)) {
+        cudaFreeAsync(E->d_xchg, st); E->d_xchg = nullptr;
+        if (dev_alloc(E, &E->d_xchg, per_rank * (size_t)(E->world + 1))) return SVBFM_ERR_OOM;
+        E->xchg_cap = per_rank * (size_t)(E->world + 1);
+    }
+    double2* send = E->d_xchg;                                             // [rows][maxcnt]
+    double2* recv = E->d_xchg + per_rank;                                  // [world][rows][maxcnt]
+    BlockXchg bx{};
+    bx.pw = E->cfg.k1 ? E->d_pw : nullptr; bx.pv = E->d_pv; bx.D = E->D; bx.rows = rows; bx.maxcnt = maxcnt; bx.world = E->world; bx.rank = E->rank;
+    for (int r = 0; r <= E->world && r <= 16; r++) bx.blk[r] = E->blk[r];
+    const uint32_t own = E->blk[E->rank + 1] - E->blk[E->rank];
+    if (own) { k_xchg_pack<<<dim3(nblk(own), rows), 256, 0, st>>>(bx, send); LAUNCHED(E); }
+    int r = g_nccl.AllGather(send, recv, per_rank * 2, 8 /*ncclDouble*/, E->nccl_comm, st);
+    if (r != 0) return fail(E, SVBFM_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    k_xchg_unpack<<<dim3(nblk(maxcnt), rows, E->world), 256, 0, st>>>(bx, recv); LAUNCHED(E);
+    return check_launch(E, "exchange_blocks");
+}
+
 // stream schedule: what a finalize has to leave behind for the passes that follow (kernels.cuh FinalizeArgs)
 struct RecPlan {
     int run = -1;                  // 0 / 1: implicit tiles of that run (span layout); -1: explicit tiles
@@ -118,7 +195,7 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
     (void)batch;
     ProfScope ps(E, (IS_V ? 0 : 3) + 1);
     uint32_t ncols = r.col_end - r.col_begin;
-    bool from_colsum = false;
+    bool from_colsum = false, use_ab = false;
     SpanView sp{nullptr, 0, E->ts_shift};
     const double* partial = E->d_partial;
     if (rp && rp->run >= 0) {
@@ -126,10 +203,11 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
         partial = E->d_partial + (rp->run ? (size_t)E->s_ntiles[0] * 8 : 0);
         uint32_t nh = E->span_heavy_n[rp->run], h0 = rp->run ? E->span_heavy_n[0] : 0;
         if (nh) { k_combine_span<<<nh, 128, 0, st>>>(E->d_span_heavy, h0, sp, partial, E->d_colsum); LAUNCHED(E); }
-        if (E->world > 1) {
-            k_combine_light_span<<<nblk(ncols), 256, 0, st>>>(r.col_begin, r.col_end, sp, partial, E->d_colsum); LAUNCHED(E);
-            if (int rc = allreduce_sum_f64(E, E->d_colsum + (size_t)r.col_begin * 4, (size_t)ncols * 4)) return rc;
-            from_colsum = true;
+        if (E->world > 1 && !(rp->run == 0 && E->excl0)) {
+            k_combine_light_span<KIND == KIND_VB_V><<<nblk(ncols), 256, 0, st>>>(r.col_begin, r.col_end, sp, partial, E->d_colsum, E->d_ab); LAUNCHED(E);
+            ProfScope pc(E, 10);      // includes the wait for the slowest rank
+            if (int rc = allreduce_sum_f64(E, reinterpret_cast<double*>(E->d_ab + r.col_begin), (size_t)ncols * 2)) return rc;
+            from_colsum = true; use_ab = true;
         }
     } else {
         uint32_t nheavy = r.heavy_end - r.heavy_begin;
@@ -142,11 +220,15 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
     }
     FinalizeArgs fa{};
     fa.c0 = r.col_begin; fa.c1 = r.col_end; fa.f = IS_V ? f : -1; fa.K = E->K;
+    if (rp && rp->run == 0 && E->excl0) {      // only the columns of this rank's block (their sums are complete locally)
+        fa.c0 = E->blk[E->rank]; fa.c1 = E->blk[E->rank + 1];
+        ncols = fa.c1 - fa.c0;
+    }
     fa.col_tile0 = E->d_col_tile0; fa.partial = partial; fa.colsum = E->d_colsum; fa.from_colsum = from_colsum;
     fa.pf = pf; fa.group = E->d_group; fa.hyper = IS_V ? E->d_hyper_v : E->d_hyper_w;
     fa.hyper_mu = IS_V ? E->d_mu_v : E->d_mu_w; fa.sc = E->d_sc; fa.delta = E->d_delta; fa.dT = E->d_dT;
     fa.seed = E->cfg.seed; fa.do_sample = E->cfg.do_sample;
-    fa.span = sp;
+    fa.span = sp; fa.ab = use_ab ? E->d_ab : nullptr;
     if (rp) { fa.cpack = E->d_cpack; fa.opack = E->d_opack; fa.rec_mode = rp->rec_mode; fa.p_next = rp->p_next; fa.p_prev = rp->p_prev; }
     if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V) {
         fa.nat = IS_V ? E->d_nat_v + (size_t)f * E->D : E->d_nat_w;
@@ -156,7 +238,7 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
         int update_params = IS_V ? 1 : (E->cfg.k1 != 0);   // with k1 = 0 the w pass only counts the batch entries per column
         k_finalize_vbo<KIND><<<nblk(ncols), 256, 0, st>>>(fa, E->d_cnt_col, 0.5, 1u, update_params);
     } else {
-        k_finalize<KIND><<<nblk(ncols), 256, 0, st>>>(fa);
+        if (ncols) k_finalize<KIND><<<nblk(ncols), 256, 0, st>>>(fa);
     }
     LAUNCHED(E);
     return check_launch(E, "combine_finalize");
@@ -371,6 +453,7 @@ static int vb_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
     }
     if (stream_ok(E)) {                                            // update_w + update_v (vb.h:390-440)
         if (int rc = sweep_streams<false>(E)) return rc;
+        if (int rc = exchange_blocks(E)) return rc;
     } else {
         if (E->cfg.k1)                                             // update_w, all columns (vb.h:390-406)
             for (const Run& r : E->runs)
@@ -382,7 +465,14 @@ static int vb_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
     // hyper-parameters + free energy (vb.h:446-500)
     if (int rc = reduce_e(E)) return rc;
     k_reduce_dT<<<SV_GGRID, 256, 0, st>>>(E->d_dT, E->D, E->d_red_partial); LAUNCHED(E);
-    k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_GGRID, 1, &E->d_sc->sum_t, 1); LAUNCHED(E);
+    if (E->streams && E->world > 1) {
+        // sharded stream schedule: every rank holds its own share of d(sum T) (columns of its block; local C1, C2 elsewhere)
+        k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_GGRID, 1, RED(E->d_sc, 6), 0); LAUNCHED(E);
+        if (int rc = allreduce_sum_f64(E, RED(E->d_sc, 6), 1)) return rc;
+        k_add_scalar<<<1, 1, 0, st>>>(&E->d_sc->sum_t, RED(E->d_sc, 6)); LAUNCHED(E);
+    } else {
+        k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_GGRID, 1, &E->d_sc->sum_t, 1); LAUNCHED(E);
+    }
     if (int rc = group_sums(E, false)) return rc;
     k_vb_hyper<<<1, 1, 0, st>>>(E->d_sc, E->d_grp_sums, E->d_n_per_group, E->G, E->K, E->d_hyper_w, E->d_hyper_v, stp); LAUNCHED(E);
     if (ev) cudaEventRecord(ev->t1, st);
@@ -404,6 +494,7 @@ static int mcmc_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
     if (E->cfg.k0) shift_e(E);
     if (stream_ok(E)) {
         if (int rc = sweep_streams<true>(E)) return rc;
+        if (int rc = exchange_blocks(E)) return rc;
     } else {
         if (E->cfg.k1)
             for (const Run& r : E->runs)
@@ -542,6 +633,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     rc |= dev_alloc(E, &E->d_delta, D);
     rc |= dev_alloc(E, &E->d_cpack, D);
     rc |= dev_alloc(E, &E->d_opack, D);
+    rc |= dev_alloc(E, &E->d_ab, D);
     rc |= dev_alloc(E, &E->d_dT, D);
     rc |= dev_alloc(E, &E->d_red_partial, SCR_GROUP + (K + 1) * 64 /*max groups*/ * 2 * SV_GGRID);
     if (rc) { g_create_error = E->err; svbfm_destroy(*out); *out = nullptr; return SVBFM_ERR_OOM; }
@@ -567,7 +659,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) cudaFreeAsync(p, E->stream);
     cudaStreamSynchronize(E->stream);
     if (E->own_stream) cudaStreamDestroy(E->own_stream);
@@ -594,6 +686,7 @@ int svbfm_comm_init(svbfm_t* h, const uint8_t id[SVBFM_COMM_ID_BYTES], int32_t r
     if (!E || !id || world_size < 1 || rank < 0 || rank >= world_size) return fail(E, SVBFM_ERR_ARG, "svbfm_comm_init: bad arguments");
     if (E->tr.n || E->te.n) return fail(E, SVBFM_ERR_ARG, "svbfm_comm_init must precede svbfm_set_csc");
     if (world_size == 1) { E->rank = 0; E->world = 1; return SVBFM_OK; }
+    if (world_size > 16) return fail(E, SVBFM_ERR_ARG, "svbfm_comm_init: at most 16 ranks (one node)");
     if (!nccl_load()) return fail(E, SVBFM_ERR_NCCL, "NCCL (libnccl.so.2) could not be loaded");
     SV_CUDA(E, cudaSetDevice(E->dev));
     Id128 uid;
@@ -821,7 +914,7 @@ int svbfm_reset(svbfm_t* h) {
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
     free_split(E, E->tr); free_split(E, E->te);
     E->runs.clear();
-    E->begun = false; E->have_state = false; E->rows_reordered = false; E->run0_sequential = false; E->streams = false;
+    E->begun = false; E->have_state = false; E->rows_reordered = false; E->run0_sequential = false; E->streams = false; E->excl0 = false;
     SV_CUDA(E, cudaMemsetAsync(E->d_dT, 0, (size_t)E->D * 8, E->stream));
     SV_CUDA(E, cudaMemsetAsync(E->d_sc, 0, sizeof(Scalars), E->stream));
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
@@ -1028,6 +1121,7 @@ int svbfm_get_info(svbfm_t* h, svbfm_info* out) {
     out->rows_reordered = E->rows_reordered;
     out->world_size = (uint32_t)E->world;
     out->fused_schedule = stream_ok(E) ? 1u : 0u;
+    out->exclusive_blocks = E->excl0 ? 1u : 0u;
     return SVBFM_OK;
 }
 

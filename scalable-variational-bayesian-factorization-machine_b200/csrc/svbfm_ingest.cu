@@ -245,10 +245,12 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     S.all_ones = (h_flags[0] == 0);
     mark("validate + H2D + col_of_entry");
     if (int r = sort_pairs(E, S.crow, d_idx, nnz, std::max<uint32_t>(n, 1), &d_skeys, &d_sidx)) return r;
+    mark("  sort pairs by case");
     cudaFreeAsync(d_idx, E->stream);
     uint64_t* d_rowptr = nullptr;
     SV_CUDA(E, cudaMallocAsync((void**)&d_rowptr, ((size_t)n + 1) * 8, E->stream));
     k_rowptr_from_sorted<<<nblk((uint64_t)n + 1), 256, 0, st>>>(d_skeys, nnz, n, d_rowptr);
+    mark("  rowptr");
     cudaFreeAsync(d_skeys, E->stream);
     uint32_t* d_rcol = nullptr; float* d_rval = nullptr;
     SV_CUDA(E, cudaMallocAsync((void**)&d_rcol, std::max<uint64_t>(nnz, 1) * 4, E->stream));
@@ -359,6 +361,17 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         }
         E->streams = E->run0_sequential && E->cfg.method != SVBFM_VB_ONLINE && !getenv("SVBFM_NO_FUSE") && E->runs.size() == 2 && F == 2 &&
                      E->runs[1].nnz == n;
+        E->excl0 = false;
+        if (E->world > 1) {      // one schedule for all ranks
+            uint32_t* d_ok = d_flags + 6;
+            uint32_t ok = E->streams ? 1u : 0u;
+            SV_CUDA(E, cudaMemcpyAsync(d_ok, &ok, 4, cudaMemcpyHostToDevice, st));
+            if (int r = allreduce(E, d_ok, 1, 3 /*ncclUint32*/, 3 /*ncclMin*/)) return r;
+            SV_CUDA(E, cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, st));
+            SV_CUDA(E, cudaStreamSynchronize(st));
+            E->streams = ok != 0;
+            if (E->streams) if (int r = detect_exclusive_blocks(E)) return r;
+        }
     }
     mark("case re-ordering + CSC rebuild");
     cudaFreeAsync(d_flags, E->stream);

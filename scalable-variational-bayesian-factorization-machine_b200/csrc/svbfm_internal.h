@@ -119,6 +119,7 @@ struct Engine {
     uint32_t span_heavy_n[2] = {0, 0};
     double* d_e2 = nullptr;            // [n] residuals in the entry order of run 1
     struct OwnPack* d_opack = nullptr; // [D] own-side constants of the next pass
+    double2* d_ab = nullptr;           // [D] sharded: {A, B} of every column, the allreduce buffer
     // state
     double2* d_pw = nullptr;          // [D]
     double2* d_pv = nullptr;          // [K][D]
@@ -163,6 +164,13 @@ struct Engine {
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
     uint64_t n_total = 0, nt_total = 0;
+    // stream schedule on several GPUs: when every rank's cases cover a disjoint, rank-ordered range of run 0's columns
+    // (cases sharded by blocks of the first field), run 0 needs no exchange inside the sweep: each rank updates the
+    // columns of its block [blk[rank], blk[rank+1]) and the blocks are broadcast once after the sweep.
+    bool excl0 = false;
+    std::vector<uint32_t> blk;        // [world + 1]
+    double2* d_xchg = nullptr;        // staging of the block exchange: send [rows][maxcnt] + recv [world][rows][maxcnt]
+    size_t xchg_cap = 0;
 };
 
 // svbfm_ingest.cu
@@ -171,6 +179,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t num_cases, uint
 void free_split(Engine* E, DevSplit& S);
 int stream_tile_cols(Engine* E);   // svbfm_engine.cu: first column of every implicit tile (k_tile_col0)
 int allreduce(Engine* E, void* buf, size_t count, int dtype /*nccl*/, int op /*nccl*/);
+int detect_exclusive_blocks(Engine* E);   // svbfm_engine.cu; collective (every rank calls it after the train split is in)
 
 // error helpers
 int fail(Engine* E, int code, const std::string& msg);

@@ -278,14 +278,24 @@ __device__ __forceinline__ bool span_sum(uint32_t j, SpanView sp, const double* 
     return true;
 }
 
-__global__ void k_combine_light_span(uint32_t c0, uint32_t c1, SpanView sp, const double* __restrict__ partial, double* __restrict__ colsum) {
+// sharded stream schedule: complete colsum[j] for every column of the run and pack what travels through the
+// allreduce: ab[j] = {A, B} (VB_V: B = C1 + C2). C1, C2 stay local: d(sum T) is linear in them, so every rank adds
+// its own share and the shares are summed once per iteration.
+template <bool VB_V>
+__global__ void k_combine_light_span(uint32_t c0, uint32_t c1, SpanView sp, const double* __restrict__ partial, double* __restrict__ colsum,
+                                     double2* __restrict__ ab) {
     uint32_t j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= c1) return;
     double A, B, C1, C2; bool empty;
-    if (!span_sum(j, sp, partial, A, B, C1, C2, empty)) return;
     double2* o = reinterpret_cast<double2*>(colsum + (size_t)j * 4);
-    o[0] = make_double2(A, B);
-    o[1] = make_double2(C1, C2);
+    if (span_sum(j, sp, partial, A, B, C1, C2, empty)) {
+        o[0] = make_double2(A, B);
+        o[1] = make_double2(C1, C2);
+    } else {
+        double2 x = o[0], y = o[1];
+        A = x.x; B = x.y; C1 = y.x; C2 = y.y;
+    }
+    ab[j] = make_double2(A, VB_V ? C1 + C2 : B);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -327,6 +337,7 @@ struct FinalizeArgs {
     double* delta;               // [D]
     // stream schedule (null / 0 otherwise): records of this column for the passes that follow (see k_stream)
     SpanView span;
+    const double2* ab;           // sharded: global {A, B} of every column after the allreduce (colsum keeps the local sums)
     ColPack* cpack;              // [D] gathered by the other side
     OwnPack* opack;              // [D] read by this side's next pass
     int rec_mode;                // 1: first field  -> cpack {new mean, new var, delta, p_prev mean}    opack {p_next mean, new mean, delta}
@@ -358,6 +369,8 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
         }
         if constexpr (KIND == KIND_VB_V) B = C1 + C2;      // vb.h:595 (k_stream leaves the B slot empty)
     } else load_colsum(j, a.col_tile0, a.partial, a.colsum, a.from_colsum, A, B, C1, C2);
+    const double B_local = B;                              // this rank's share (d(sum T) of a w column, vb.h:572)
+    if (a.ab) { double2 g2 = a.ab[j]; A = g2.x; B = g2.y; }
     uint32_t g = a.group[j];
     double hy = (a.f < 0) ? a.hyper[g] : a.hyper[(size_t)g * a.K + a.f];
     double alpha = a.sc->alpha;
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
         new_mean = mu; new_var = sg; dlt = skip ? 0.0 : (mu_old - mu);
         a.delta[j] = dlt;
         if (!skip) {
-            if constexpr (KIND == KIND_VB_W) a.dT[j] += B * (sg - sg_old);                                    // vb.h:572
+            if constexpr (KIND == KIND_VB_W) a.dT[j] += B_local * (sg - sg_old);                              // vb.h:572
             else a.dT[j] += (C1 + C2) * (sg - sg_old) + C1 * (mu * mu - mu_old * mu_old);                        // vb.h:639-640
         }
     } else if constexpr (KIND == KIND_MC_W || KIND == KIND_MC_V) {
@@ -853,6 +866,33 @@ __global__ void __launch_bounds__(256) k_reduce_dT(double* __restrict__ dT, uint
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { v[0] += dT[i]; dT[i] = 0.0; }
     block_sum<1>(v, sm);
     if (threadIdx.x == 0) partial[blockIdx.x] = v[0];
+}
+
+__global__ void k_add_scalar(double* dst, const double* src) { *dst += *src; }
+
+// sharded stream schedule: block exchange of run 0's parameters. row 0 = w (when present), then one row per factor.
+struct BlockXchg {
+    double2* pw;              // null: no w row
+    double2* pv;
+    uint32_t D, rows, maxcnt;
+    int world, rank;
+    uint32_t blk[17];
+};
+__device__ __forceinline__ double2* xchg_table(const BlockXchg& b, uint32_t row) {
+    if (b.pw) return row == 0 ? b.pw : b.pv + (size_t)(row - 1) * b.D;
+    return b.pv + (size_t)row * b.D;
+}
+__global__ void k_xchg_pack(BlockXchg b, double2* __restrict__ send) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+    uint32_t lo = b.blk[b.rank], cnt = b.blk[b.rank + 1] - lo;
+    if (i < cnt) send[(size_t)row * b.maxcnt + i] = xchg_table(b, row)[lo + i];
+}
+__global__ void k_xchg_unpack(BlockXchg b, const double2* __restrict__ recv) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+    int r = blockIdx.z;
+    if (r == b.rank) return;
+    uint32_t lo = b.blk[r], cnt = b.blk[r + 1] - lo;
+    if (i < cnt) xchg_table(b, row)[lo + i] = recv[((size_t)r * b.rows + row) * b.maxcnt + i];
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -22,6 +22,36 @@ def shard_csc(data, rank, world):
     return CscData(colptr, (data.case_id[keep] - lo).astype(np.uint32), data.x[keep], data.target[lo:hi])
 
 
+def block_bounds(colptr, first_field_cols, world):
+    """Column boundaries [world + 1] that split the first field's columns into rank-ordered blocks with about the same
+    number of entries each ('partition rows by user block')."""
+    cum = np.asarray(colptr[:first_field_cols + 1], dtype=np.int64)
+    total = int(cum[-1])
+    b = [0]
+    for r in range(1, world):
+        b.append(int(np.searchsorted(cum, total * r // world, side="left")))
+    b.append(first_field_cols)
+    return [min(max(x, 0), first_field_cols) for x in b]
+
+
+def shard_csc_by_block(data, rank, world, first_field_cols):
+    """Cases whose first-field feature lies in this rank's column block (block_bounds), local case ids in ascending
+    original order. The engine detects the disjoint blocks and updates the first field without any exchange.
+    Returns (CscData, original case ids of the shard)."""
+    import sys
+    CscData = sys.modules[__name__.rsplit('.', 1)[0]].CscData
+    b = block_bounds(data.colptr, first_field_cols, world)
+    cp = data.colptr.astype(np.int64)
+    mine = np.sort(data.case_id[cp[b[rank]]:cp[b[rank + 1]]].astype(np.int64))     # one first-field entry per case
+    local = np.full(data.num_cases, -1, dtype=np.int64)
+    local[mine] = np.arange(len(mine))
+    keep = local[data.case_id] >= 0
+    col_of = np.repeat(np.arange(data.num_feature, dtype=np.int64), np.diff(cp))
+    colptr = np.zeros(data.num_feature + 1, dtype=np.uint64)
+    np.cumsum(np.bincount(col_of[keep], minlength=data.num_feature), out=colptr[1:])
+    return CscData(colptr, local[data.case_id[keep]].astype(np.uint32), data.x[keep], data.target[mine]), mine
+
+
 def broadcast_unique_id(get_id, rank, device=None):
     """Rank 0 calls get_id() -> bytes; every rank returns the same bytes (torch.distributed broadcast; gloo or nccl)."""
     import torch

@@ -63,8 +63,7 @@ def csc_two_field(u, i, y, U, I, num_cols=None):
 
 
 # ---- torch generator for the large configs (runs on the GPU; same distributions as above) -----------------
-def ratings_torch(n, U, I, seed, device, chunk=25_000_000, model_seed=20261017):
-    """Returns (user int32[n], item int32[n], y float32[n]) on `device`; deterministic for a given seed."""
+def _model_torch(U, I, device, model_seed):
     import torch
     gm = torch.Generator(device=device)
     gm.manual_seed(model_seed)
@@ -74,25 +73,43 @@ def ratings_torch(n, U, I, seed, device, chunk=25_000_000, model_seed=20261017):
     Q = torch.randn(I, 8, generator=gm, device=device) * 0.3
     perm_u = torch.randperm(U, generator=gm, device=device)
     perm_i = torch.randperm(I, generator=gm, device=device)
+    return bu, bi, P, Q, perm_u, perm_i
+
+
+def user_mass_torch(U, I, device, model_seed=20261017):
+    """Expected share of the ratings of every user id under ratings_torch (Zipf(1) over the planted permutation)."""
+    import torch
+    perm_u = _model_torch(U, I, device, model_seed)[4]
+    p = 1.0 / torch.arange(1, U + 1, device=device, dtype=torch.float64)
+    mass = torch.empty(U, device=device, dtype=torch.float64)
+    mass[perm_u] = p / p.sum()
+    return mass
+
+
+def ratings_torch(n, U, I, seed, device, chunk=25_000_000, model_seed=20261017, user_range=None):
+    """Returns (user int32[m], item int32[m], y float32[m]) on `device`; deterministic for a given seed. m = n, or, with
+    user_range = (lo, hi), the subset of the same n draws whose user id lies in [lo, hi) (a user-block shard)."""
+    import torch
+    bu, bi, P, Q, perm_u, perm_i = _model_torch(U, I, device, model_seed)
     cdf_u = torch.cumsum(1.0 / torch.arange(1, U + 1, device=device, dtype=torch.float64), 0)
     cdf_u /= cdf_u[-1].clone()
     cdf_i = torch.cumsum(1.0 / torch.arange(1, I + 1, device=device, dtype=torch.float64), 0)
     cdf_i /= cdf_i[-1].clone()
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    u = torch.empty(n, dtype=torch.int32, device=device)
-    it = torch.empty(n, dtype=torch.int32, device=device)
-    y = torch.empty(n, dtype=torch.float32, device=device)
+    us, its, ys = [], [], []
     for a in range(0, n, chunk):
         b = min(n, a + chunk)
         ru = torch.searchsorted(cdf_u, torch.rand(b - a, generator=g, device=device, dtype=torch.float64)).clamp_(max=U - 1)
         ri = torch.searchsorted(cdf_i, torch.rand(b - a, generator=g, device=device, dtype=torch.float64)).clamp_(max=I - 1)
         uu, ii = perm_u[ru], perm_i[ri]
         s = 3.5 + bu[uu] + bi[ii] + (P[uu] * Q[ii]).sum(1) + 0.8 * torch.randn(b - a, generator=g, device=device)
-        u[a:b] = uu.to(torch.int32)
-        it[a:b] = ii.to(torch.int32)
-        y[a:b] = s.round_().clamp_(1, 5)
-    return u, it, y
+        yy = s.round_().clamp_(1, 5)
+        if user_range is not None:
+            keep = (uu >= user_range[0]) & (uu < user_range[1])
+            uu, ii, yy = uu[keep], ii[keep], yy[keep]
+        us.append(uu.to(torch.int32)); its.append(ii.to(torch.int32)); ys.append(yy.to(torch.float32))
+    return torch.cat(us), torch.cat(its), torch.cat(ys)
 
 
 def csc_two_field_torch(u, it, U, I, num_cols=None):

@@ -31,15 +31,22 @@ def main():
 
     ok = True
     for name, (tr, te), method, K, iters in (("two_field_vb", two_field(30000, 3000, 400, 300, seed=51), "vb", 4, 5),
+                                             ("two_field_vb_blocks", two_field(30000, 3000, 400, 300, seed=54), "vb", 4, 5),
                                              ("ragged_vb", ragged(4000, 500, 60, seed=52), "vb", 3, 4),
-                                             ("two_field_als", two_field(20000, 2000, 300, 200, seed=53), "mcmc", 3, 4)):
+                                             ("two_field_als", two_field(20000, 2000, 300, 200, seed=53), "mcmc", 3, 4),
+                                             ("two_field_als_blocks", two_field(20000, 2000, 300, 200, seed=55), "mcmc", 3, 4)):
         uid = d.broadcast_unique_id(get_id, rank, device=torch.device("cuda", local))
         D = max(tr.n_feat, te.n_feat) + 1
         kw = dict(do_sample=False, do_multilevel=False) if method == "mcmc" else {}
         E = sv.Engine(method, D, K, 1, 1, float(tr.y.min()), float(tr.y.max()), device=local, seed=42, **kw)
         E.comm_init(uid, rank, world)
-        E.set_csc(sv.TRAIN, d.shard_csc(to_csc(tr), rank, world))
+        blocks = name.endswith("_blocks")       # cases sharded by blocks of the first field (users): no exchange for that field
+        nu = 400 if "vb" in name else 300
+        E.set_csc(sv.TRAIN, d.shard_csc_by_block(to_csc(tr), rank, world, nu)[0] if blocks else d.shard_csc(to_csc(tr), rank, world))
         E.set_csc(sv.TEST, d.shard_csc(to_csc(te), rank, world))
+        assert E.info()["exclusive_blocks"] == (1 if blocks else 0), (name, E.info())
+        if name.startswith("two_field"):
+            assert E.info()["fused_schedule"] == 1
         E.set_state(sv.host_init_state(42, D, K, 0.1, sv.METHODS[method]))
         E.begin()
         hist = E.run(iters)
@@ -61,6 +68,7 @@ def main():
         dist.all_reduce(mn, op=dist.ReduceOp.MIN)
         ok = ok and bool(torch.equal(mx, mn))
         assert E.info()["world_size"] == world
+        ok = ok and E.copies_max_diff() == 0.0
         E.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
