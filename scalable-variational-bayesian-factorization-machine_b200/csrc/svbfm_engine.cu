@@ -8,12 +8,14 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include "svbfm_kernels.cuh"
 
 using namespace svb;
 
 static thread_local std::string g_create_error;
+static std::atomic<int> g_handles{0};
 
 // ---------------------------------------------------------------------------------------------- NCCL (dlopen)
 struct Id128 { char b[SVBFM_COMM_ID_BYTES]; };
@@ -439,6 +441,33 @@ static int predict(Engine* E, const DevSplit& S, double* e_out, int red_slot, in
     return check_launch(E, "predict");
 }
 
+// train prediction, two complete fields: transposed parameters + warp per case (k_predict2). Falls back to k_predict.
+template <int MODE>   // PRED_VB_TRAIN or PRED_MC_TRAIN
+static int predict_train(Engine* E, int red_slot) {
+    const DevSplit& S = E->tr;
+    if (!E->streams || E->K < 1 || E->K > 256 || getenv("SVBFM_NO_PREDICT2")) return predict<MODE>(E, S, E->d_e, red_slot, 1);
+    cudaStream_t st = E->stream;
+    if (!E->d_pvT && dev_alloc(E, &E->d_pvT, (size_t)E->K * E->D)) return SVBFM_ERR_OOM;
+    k_transpose_params<<<dim3((E->D + 31) / 32, (E->K + 31) / 32), dim3(32, 8), 0, st>>>(E->d_pv, E->D, E->K, E->d_pvT); LAUNCHED(E);
+    Predict2Args a{};
+    a.rcol = S.rcol; a.rval = S.rval; a.y = S.y; a.n = S.n; a.pw = E->d_pw; a.pvT = E->d_pvT; a.K = E->K; a.k0 = E->cfg.k0; a.k1 = E->cfg.k1;
+    a.sc = E->d_sc; a.e = E->d_e; a.partial = E->d_red_partial;
+    const unsigned grid = std::max(1u, std::min<unsigned>((S.n + 255) / 256, SV_RGRID / 2));   // partial[] holds grid * 8 <= SV_RGRID * 4 sums
+    constexpr bool MC = (MODE == PRED_MC_TRAIN);
+    const int ns = E->K <= 32 ? 1 : (E->K <= 64 ? 2 : (E->K <= 128 ? 4 : 8));
+#define CALL_P2(NS)                                                                                  \
+    do {                                                                                             \
+        if (S.all_ones) k_predict2<MC, true, NS><<<grid, 256, 0, st>>>(a);                           \
+        else k_predict2<MC, false, NS><<<grid, 256, 0, st>>>(a);                                     \
+    } while (0)
+    if (ns == 1) CALL_P2(1); else if (ns == 2) CALL_P2(2); else if (ns == 4) CALL_P2(4); else CALL_P2(8);
+#undef CALL_P2
+    LAUNCHED(E);
+    k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, grid * 8, 1, RED(E->d_sc, red_slot), 0); LAUNCHED(E);
+    if (int rc = allreduce_sum_f64(E, RED(E->d_sc, red_slot), 1)) return rc;
+    return check_launch(E, "predict_train");
+}
+
 // ---------------------------------------------------------------------------------------------- iterations
 struct IterEvents { cudaEvent_t t0, t1, t2; };
 
@@ -512,7 +541,7 @@ static int mcmc_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
         SV_CUDA(E, cudaMemcpyAsync(RED(E->d_sc, 5), E->d_red_partial + SCR_FINAL, sizeof(double), cudaMemcpyDeviceToDevice, st));
         if (int rc = allreduce_sum_f64(E, RED(E->d_sc, 5), 1)) return rc;
     } else {
-        if (int rc = predict<PRED_MC_TRAIN>(E, E->tr, E->d_e, 5, 1)) return rc;
+        if (int rc = predict_train<PRED_MC_TRAIN>(E, 5)) return rc;
         sync_e2(E);
     }
     if (int rc = predict<PRED_MC_TEST>(E, E->te, nullptr, 3, 2)) return rc;
@@ -600,6 +629,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
         if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
     }
     Engine* E = new Engine();
+    ++g_handles;
     E->cfg = *cfg; E->dev = cfg->device; E->D = cfg->num_attribute; E->K = cfg->num_factor;
     E->tile_entries = cfg->tile_entries ? cfg->tile_entries : 1024;
     if (const char* te = getenv("SVBFM_TILE_ENTRIES")) if (atoi(te) >= 32) E->tile_entries = (uint32_t)atoi(te);   // tuning knob
@@ -607,16 +637,8 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     uint32_t ts = (cfg->tile_entries || getenv("SVBFM_TILE_ENTRIES")) ? E->tile_entries : 4096u;
     E->ts_shift = 5;
     while (E->ts_shift < 20 && (2u << E->ts_shift) <= ts) E->ts_shift++;
-    {   // stream-ordered allocations from the device's default pool, never handed back to the OS between learn() calls:
-        // ingest allocates and frees tens of GB of scratch; plain cudaMalloc/cudaFree would dominate set_csc
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
-            uint64_t thr = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-    }
     ce = cudaStreamCreateWithFlags(&E->own_stream, cudaStreamNonBlocking);
-    if (ce != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(ce); delete E; return SVBFM_ERR_CUDA; }
+    if (ce != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(ce); delete E; --g_handles; return SVBFM_ERR_CUDA; }
     E->stream = E->own_stream;
     E->G = 1;
     E->h_group.assign(E->D, 0);
@@ -659,11 +681,12 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) cudaFreeAsync(p, E->stream);
     cudaStreamSynchronize(E->stream);
     if (E->own_stream) cudaStreamDestroy(E->own_stream);
     delete E;
+    if (--g_handles == 0) sv_cache_release();      // the last handle gives the cached device blocks back to the driver
 }
 
 int svbfm_set_stream(svbfm_t* h, void* cuda_stream) {
@@ -880,10 +903,10 @@ int svbfm_begin(svbfm_t* h) {
     if (int rc = ensure_stats(E, 16)) return rc;
     if (E->cfg.method == SVBFM_VB) {
         // initial y-hat and T over train (vbs.h:37-44): e_i = y_i - yhat_i ; sum_t = sum_i T_i
-        if (int rc = predict<PRED_VB_TRAIN>(E, E->tr, E->d_e, 6, 1)) return rc;
+        if (int rc = predict_train<PRED_VB_TRAIN>(E, 6)) return rc;
         SV_CUDA(E, cudaMemcpyAsync(&E->d_sc->sum_t, RED(E->d_sc, 6), 8, cudaMemcpyDeviceToDevice, st));
     } else if (E->cfg.method == SVBFM_MCMC) {
-        if (int rc = predict<PRED_MC_TRAIN>(E, E->tr, E->d_e, 6, 1)) return rc;     // e = yhat - y (mcmcs.h:75-80)
+        if (int rc = predict_train<PRED_MC_TRAIN>(E, 6)) return rc;                 // e = yhat - y (mcmcs.h:75-80)
     }
     if (E->cfg.method != SVBFM_VB_ONLINE) sync_e2(E);
     else {   // vb_online: global count of every feature in the training data (vbo.h:704-726) and the natural parameters

@@ -16,7 +16,69 @@
 #include <cstring>
 #include "svbfm_internal.h"
 
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
 namespace svb {
+
+// ---- size-keyed block cache (see svbfm_internal.h) -----------------------------------------------------------------
+namespace {
+struct BlockCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> free_blocks;          // (device, bytes) -> block
+    std::unordered_map<void*, std::pair<int, size_t>> live;            // block -> (device, bytes)
+};
+BlockCache& cache() { static BlockCache c; return c; }
+}  // namespace
+
+#undef cudaMallocAsync
+#undef cudaFreeAsync
+cudaError_t sv_malloc(void** p, size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    BlockCache& c = cache();
+    std::lock_guard<std::mutex> g(c.mu);
+    auto it = c.free_blocks.find({dev, bytes});
+    if (it != c.free_blocks.end()) {
+        *p = it->second;
+        c.free_blocks.erase(it);
+        c.live[*p] = {dev, bytes};
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {                      // memory pressure: give the cached blocks of this device back and retry once
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        for (auto f = c.free_blocks.begin(); f != c.free_blocks.end();)
+            if (f->first.first == dev) { cudaFree(f->second); f = c.free_blocks.erase(f); } else ++f;
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) c.live[*p] = {dev, bytes};
+    return e;
+}
+cudaError_t sv_free(void* p) {
+    if (!p) return cudaSuccess;
+    BlockCache& c = cache();
+    std::lock_guard<std::mutex> g(c.mu);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) return cudaFree(p);
+    c.free_blocks.insert({it->second, p});
+    c.live.erase(it);
+    return cudaSuccess;
+}
+void sv_cache_release() {
+    BlockCache& c = cache();
+    std::lock_guard<std::mutex> g(c.mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& f : c.free_blocks) { cudaSetDevice(f.first.first); cudaFree(f.second); }
+    c.free_blocks.clear();
+    cudaSetDevice(cur);
+}
+#define cudaMallocAsync(p, bytes, stream) svb::sv_malloc((void**)(p), (bytes))
+#define cudaFreeAsync(p, s) svb::sv_free((void*)(p))
 
 int fail(Engine* E, int code, const std::string& msg) {
     if (E) E->err = msg;

@@ -17,8 +17,20 @@
 #include <vector>
 #include "../../include/svbfm.h"
 
-// null-tolerant stream-ordered free (like cudaFree(nullptr))
-#define cudaFreeAsync(p, s) ((p) ? cudaFreeAsync((p), (s)) : cudaSuccess)
+// Device memory goes through a size-keyed block cache (svbfm_ingest.cu): a freed block is kept and handed out again
+// to the next request of exactly the same size on the same device. A learn() on data of the same shape repeats the same
+// sequence of sizes, so after the first pass neither ingest nor the sweeps call the driver's allocator at all (plain
+// cudaMalloc/cudaFree of tens of GB cost more than the ingest kernels; the stream-ordered pool showed stalls of up to
+// seconds when its free list was fragmented: DESIGN.md section 7). All work of a handle is ordered on one stream, so
+// reusing a block right after its release is safe. Blocks return to the driver when the last handle is destroyed or when
+// an allocation fails.
+namespace svb {
+cudaError_t sv_malloc(void** p, size_t bytes);
+cudaError_t sv_free(void* p);          // null-tolerant
+void sv_cache_release();               // hand every cached block back to the driver
+}
+#define cudaMallocAsync(p, bytes, stream) svb::sv_malloc((void**)(p), (bytes))
+#define cudaFreeAsync(p, s) svb::sv_free((void*)(p))
 
 namespace svb {
 
@@ -120,6 +132,7 @@ struct Engine {
     double* d_e2 = nullptr;            // [n] residuals in the entry order of run 1
     struct OwnPack* d_opack = nullptr; // [D] own-side constants of the next pass
     double2* d_ab = nullptr;           // [D] sharded: {A, B} of every column, the allreduce buffer
+    double2* d_pvT = nullptr;          // [D][K] transposed factor parameters for the two-field train prediction (k_predict2)
     // state
     double2* d_pw = nullptr;          // [D]
     double2* d_pv = nullptr;          // [K][D]

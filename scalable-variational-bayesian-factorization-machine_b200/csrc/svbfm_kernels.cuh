@@ -998,6 +998,120 @@ __global__ void __launch_bounds__(256) k_predict(PredictArgs a) {
         for (int k = 0; k < 4; k++) a.partial[blockIdx.x * 4 + k] = acc[k];
 }
 
+// ---- train prediction for two complete fields (the stream schedule's data shape) ------------------------------------
+// k_predict walks the K factor rows of the [K][D] parameter matrix per case: K*F sector gathers from 1.3 GB (68 ms for
+// 200 M cases, K = 50). Here the parameters are first transposed to [D][K] (k_transpose_params, 1 ms); a warp then takes
+// one case at a time with its lanes over the factors: two coalesced K*16 B rows per case (the user's row is kept while
+// the user does not change: device case order is sorted by user), two butterfly sums, and the 32 results of a block of
+// cases are written coalesced. Same formulas as k_predict (vb.h:70-312 / mcmc.h:117-348), factor sums in lane order.
+__global__ void k_transpose_params(const double2* __restrict__ pv, uint32_t D, int K, double2* __restrict__ pvT) {
+    __shared__ double2 tile[32][33];
+    uint32_t j0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        uint32_t f = f0 + r, j = j0 + threadIdx.x;
+        if (f < (uint32_t)K && j < D) tile[r][threadIdx.x] = pv[(size_t)f * D + j];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        uint32_t j = j0 + r, f = f0 + threadIdx.x;
+        if (f < (uint32_t)K && j < D) pvT[(size_t)j * K + f] = tile[threadIdx.x][r];
+    }
+}
+
+struct Predict2Args {
+    const uint32_t* rcol;     // [2n] CSR of the two-field cases
+    const float* rval;        // [2n] or null
+    const float* y;
+    uint32_t n;
+    const double2* pw;
+    const double2* pvT;       // [D][K]
+    int K, k0, k1;
+    const Scalars* sc;
+    double* e;
+    double* partial;          // [warps] sum T (vb) / sum of squared clamped errors (mcmc)
+};
+
+template <bool MCMC, bool ONES, int NS>
+__global__ void __launch_bounds__(256) k_predict2(Predict2Args a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
+    const uint32_t blocks = (a.n + 31) / 32;                       // blocks of 32 consecutive cases, dealt out contiguously
+    const uint32_t b0 = (uint32_t)((uint64_t)blocks * w / nw), b1 = (uint32_t)((uint64_t)blocks * (w + 1) / nw);
+    const double w0 = a.sc->w0_mean, w0v = a.sc->w0_var, lo = a.sc->min_target, hi = a.sc->max_target;
+    double acc = 0.0;
+    uint32_t u_prev = 0xffffffffu;
+    double2 Pu[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) Pu[s] = make_double2(0.0, 0.0);
+    for (uint32_t b = b0; b < b1; b++) {
+        const uint32_t i = b * 32 + lane;
+        const bool ok = i < a.n;
+        uint2 c = ok ? __ldcs(reinterpret_cast<const uint2*>(a.rcol) + i) : make_uint2(0u, 0u);
+        float2 xv = make_float2(1.0f, 1.0f);
+        if constexpr (!ONES) if (ok) xv = __ldcs(reinterpret_cast<const float2*>(a.rval) + i);
+        const double yi = ok ? (double)__ldcs(a.y + i) : 0.0;
+        double lin = 0.0, tw = 0.0;
+        if (ok) {
+            double2 A = __ldg(&a.pw[c.x]), B = __ldg(&a.pw[c.y]);
+            lin = A.x * xv.x + B.x * xv.y;                                  // vb.h:184
+            tw = A.y * xv.x * xv.x + B.y * xv.y * xv.y;                     // vb.h:298
+        }
+        double res = 0.0;
+        const uint32_t cnt = (a.n - b * 32 < 32u) ? a.n - b * 32 : 32u;
+        for (uint32_t k = 0; k < cnt; k++) {
+            const uint32_t u = __shfl_sync(0xffffffffu, c.x, k), j = __shfl_sync(0xffffffffu, c.y, k);
+            float xu = 1.0f, xj = 1.0f;
+            if constexpr (!ONES) { xu = __shfl_sync(0xffffffffu, xv.x, k); xj = __shfl_sync(0xffffffffu, xv.y, k); }
+            if (u != u_prev) {
+#pragma unroll
+                for (int s = 0; s < NS; s++) {
+                    int f = (int)lane + 32 * s;
+                    Pu[s] = f < a.K ? __ldg(&a.pvT[(size_t)u * a.K + f]) : make_double2(0.0, 0.0);
+                }
+                u_prev = u;
+            }
+            double yv = 0.0, tv = 0.0;
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                int f = (int)lane + 32 * s;
+                double2 Pj = f < a.K ? __ldg(&a.pvT[(size_t)j * a.K + f]) : make_double2(0.0, 0.0);
+                double mu_u = Pu[s].x * xu, mu_j = Pj.x * xj;
+                double sm = mu_u + mu_j;                                    // vb.h:115
+                double q = mu_u * mu_u + mu_j * mu_j;                       // vb.h:159 / :241
+                yv += 0.5 * sm * sm - 0.5 * q;                              // vb.h:128, 159
+                if constexpr (!MCMC) {
+                    double xu2 = (double)xu * xu, xj2 = (double)xj * xj;
+                    double z = Pu[s].y * xu2 + Pj.y * xj2;                  // vb.h:242
+                    tv += 0.5 * z * z + z * q                               // vb.h:250
+                          - (mu_u * mu_u * xu2 * Pu[s].y + 0.5 * xu2 * xu2 * Pu[s].y * Pu[s].y)   // vb.h:277-278
+                          - (mu_j * mu_j * xj2 * Pj.y + 0.5 * xj2 * xj2 * Pj.y * Pj.y);
+                }
+            }
+            yv = warp_sum(yv);
+            if constexpr (!MCMC) tv = warp_sum(tv);
+            if (lane == k) {
+                double yhat = yv;
+                if (a.k1) yhat += lin;
+                if (a.k0) yhat += w0;                                       // vb.h:196-199
+                if constexpr (MCMC) {
+                    double p = fmax(lo, fmin(hi, yhat));                    // mcmcs.h:167-171
+                    acc += (p - yi) * (p - yi);
+                    res = yhat - yi;                                        // mcmcs.h:172
+                } else {
+                    double T = tv;
+                    if (a.k1) T += tw;
+                    if (a.k0) T += w0v;                                     // vb.h:306-309
+                    acc += T;
+                    res = yi - yhat;                                        // vbs.h:43
+                }
+            }
+        }
+        if (ok) a.e[i] = res;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) a.partial[w] = acc;
+}
+
 // mcmc without re-prediction: Train= from the cached residuals (yhat = e + y)
 __global__ void __launch_bounds__(256) k_train_sse_from_e(const double* __restrict__ e, const float* __restrict__ y, uint32_t n, const Scalars* sc,
                                                           double* __restrict__ partial) {

@@ -216,6 +216,30 @@ def test_stream_schedule_sorted_input(built):
     assert L.engine.copies_max_diff() == 0.0
 
 
+@pytest.mark.parametrize("K", [40, 70, 130])
+def test_two_field_train_prediction_wide_k(built, K, monkeypatch):
+    """k_predict2 (transposed parameters, warp per case) with 2, 4 and 8 factor slots per lane, one-hot and real values, vb and
+    mcmc/als; the residuals it produces equal those of the general case-wise kernel (k_predict) to rounding."""
+    for values in (False, True):
+        tr, te = two_field(6000, 600, 90, 70, seed=97, values=values)
+        L, _ = run_vb(tr, te, K=K, iters=2)
+        e_fast = L.engine.get_residuals()
+        L.engine.close()
+        monkeypatch.setenv("SVBFM_NO_PREDICT2", "1")
+        L2 = make_learner("vb", tr, te, K, num_iter=2)
+        L2.learn(to_csc(tr), to_csc(te))
+        assert np.max(np.abs(L2.engine.get_residuals() - e_fast)) < 1e-9
+        L2.engine.close()
+        monkeypatch.delenv("SVBFM_NO_PREDICT2")
+    tr, te = two_field(6000, 600, 90, 70, seed=98)
+    orc = ob.Oracle("mcmc", tr, te, K=K, seed=42, do_sample=False, do_multilevel=False)
+    L = make_learner("mcmc", tr, te, K, num_iter=3, do_sample=False, do_multilevel=False)
+    L.fm.reg0, L.fm.regw, L.fm.regv = 0.0, 0.0, 0.0
+    for s in L.learn(to_csc(tr), to_csc(te)):
+        o = orc.iterate()
+        assert rel(s.test_rmse, o.test_rmse) < 1e-7 and rel(s.train_stat, o.train_stat) < 1e-7
+
+
 def test_reset_reuses_handle(built):
     """svbfm_reset: a second learn() on the same handle (same data, same initial state) repeats the first one."""
     tr, te = two_field(10000, 1000, 200, 150, seed=81)
