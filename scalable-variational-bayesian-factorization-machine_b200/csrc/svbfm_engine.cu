@@ -198,9 +198,12 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
     ProfScope ps(E, (IS_V ? 0 : 3) + 1);
     uint32_t ncols = r.col_end - r.col_begin;
     bool from_colsum = false, use_ab = false;
-    SpanView sp{nullptr, 0, E->ts_shift};
+    SpanView sp{nullptr, 0, E->ts_shift, SV_SPAN_LIGHT};
     const double* partial = E->d_partial;
-    if (rp && rp->run >= 0) {
+    if (rp && rp->run >= 0 && E->bv.on) {        // one vb_online batch: its own column pointer; any span is summed in k_finalize_vbo
+        sp.colptr = E->bv.colptr[rp->run]; sp.entry0 = E->bv.entry0; sp.light_limit = ~0u; sp.ts_shift = E->vbo_ts_shift;
+        partial = E->d_vbo_partial + (rp->run ? (size_t)E->vbo_max_tiles * 8 : 0);
+    } else if (rp && rp->run >= 0) {
         sp.colptr = E->tr.colptr; sp.entry0 = E->tr.h_colptr[r.col_begin];
         partial = E->d_partial + (rp->run ? (size_t)E->s_ntiles[0] * 8 : 0);
         uint32_t nh = E->span_heavy_n[rp->run], h0 = rp->run ? E->span_heavy_n[0] : 0;
@@ -304,36 +307,47 @@ static int sweep_run(Engine* E, const Run& r, int f, int batch = -1) {
 // Two-copy stream schedule (two complete one-hot fields, device case order = run 0): see k_stream.
 static bool stream_ok(const Engine* E) { return E->streams; }
 
-// one pass over `side` (0: run 0 / e, 1: run 1 / e2). W: a w step (KIND_*_W), else v.
+// one pass over `side` (0: run 0 / e, 1: run 1 / e2). W: a w step (KIND_*_W), else v. vb_online shares vb's pass arithmetic.
 template <bool MCMC, bool W, bool REDUCE>
 static void launch_stream(Engine* E, int side, bool has_own, bool own_is_w, bool has_oth, bool oth_is_w) {
     const DevSplit& S = E->tr;
     const Run& r = E->runs[side];
     StreamArgs a{};
-    a.colptr = S.colptr; a.c0 = r.col_begin; a.c1 = r.col_end; a.entry0 = S.h_colptr[r.col_begin]; a.n = S.n;
-    a.ntiles = E->s_ntiles[side]; a.ts_shift = E->ts_shift; a.tile_col0 = E->d_stile_col0 + (side ? E->s_ntiles[0] : 0);
+    a.c0 = r.col_begin; a.c1 = r.col_end; a.real0 = S.h_colptr[r.col_begin]; a.ts_shift = E->ts_shift;
+    if (E->bv.on) {
+        a.colptr = E->bv.colptr[side]; a.entry0 = E->bv.entry0; a.n = E->bv.n; a.ntiles = E->bv.ntiles; a.ts_shift = E->vbo_ts_shift;
+        a.tile_col0 = E->d_vbo_tile_col0 + (side ? E->vbo_max_tiles : 0); a.idx = E->d_vbo_idx[side];
+        a.partial = E->d_vbo_partial + (side ? (size_t)E->vbo_max_tiles * 8 : 0);
+    } else {
+        a.colptr = S.colptr; a.entry0 = a.real0; a.n = S.n; a.ntiles = E->s_ntiles[side];
+        a.tile_col0 = E->d_stile_col0 + (side ? E->s_ntiles[0] : 0); a.idx = nullptr;
+        a.partial = E->d_partial + (side ? (size_t)E->s_ntiles[0] * 8 : 0);
+    }
     a.oc = S.cother; a.xv = S.cval; a.xo = S.cother_val;
     a.e = side ? E->d_e2 : E->d_e;
     a.rec = E->d_cpack; a.own = E->d_opack;
     a.has_own = has_own; a.own_is_w = own_is_w; a.has_oth = has_oth; a.oth_is_w = oth_is_w;
-    a.colsum = E->d_colsum; a.partial = E->d_partial + (side ? (size_t)E->s_ntiles[0] * 8 : 0);
+    a.colsum = E->d_colsum;
     constexpr int KIND = MCMC ? (W ? KIND_MC_W : KIND_MC_V) : (W ? KIND_VB_W : KIND_VB_V);
     unsigned grid = (a.ntiles + 7) / 8;
     if (!a.ntiles) return;
     const bool steady = !W && has_own && !own_is_w && has_oth && !oth_is_w;
-    if (steady) {
-        if (S.all_ones) k_stream<KIND, true, REDUCE, true><<<grid, 256, 0, E->stream>>>(a);
-        else k_stream<KIND, false, REDUCE, true><<<grid, 256, 0, E->stream>>>(a);
-    } else {
-        if (S.all_ones) k_stream<KIND, true, REDUCE, false><<<grid, 256, 0, E->stream>>>(a);
-        else k_stream<KIND, false, REDUCE, false><<<grid, 256, 0, E->stream>>>(a);
-    }
+#define CALL_S(ONES, STEADY)                                                                                         \
+    do {                                                                                                             \
+        if (a.idx) { if constexpr (!MCMC) k_stream<KIND, ONES, REDUCE, STEADY, true><<<grid, 256, 0, E->stream>>>(a); } \
+        else k_stream<KIND, ONES, REDUCE, STEADY, false><<<grid, 256, 0, E->stream>>>(a);                           \
+    } while (0)
+    if (steady) { if (S.all_ones) CALL_S(true, true); else CALL_S(false, true); }
+    else { if (S.all_ones) CALL_S(true, false); else CALL_S(false, false); }
+#undef CALL_S
     LAUNCHED(E);
 }
 
-// update_w + update_v of one iteration (vb.h:390-440 / mcmc.h:465-623 without the hyper-parameter draws)
-template <bool MCMC>
+// update_w + update_v of one iteration (vb.h:390-440 / mcmc.h:465-623 without the hyper-parameter draws), or of one
+// vb_online batch (vbo.h:360-408; E->bv set). FLAVOR: 0 vb, 1 mcmc, 2 vb_online
+template <int FLAVOR>
 static int sweep_streams(Engine* E) {
+    constexpr bool MCMC = (FLAVOR == 1);
     const Run &r0 = E->runs[0], &r1 = E->runs[1];
     cudaStream_t st = E->stream;
     std::vector<int> steps;                       // -1 = w, f = v_f
@@ -343,7 +357,9 @@ static int sweep_streams(Engine* E) {
     auto table = [&](int s) -> double2* { return s < 0 ? E->d_pw : E->d_pv + (size_t)s * E->D; };
     k_pack_init<<<nblk(r1.col_end - r0.col_begin), 256, 0, st>>>(r0.col_begin, r0.col_end, r1.col_begin, r1.col_end, table(steps[0]), E->d_cpack, E->d_opack);
     LAUNCHED(E);
-    constexpr int KW = MCMC ? KIND_MC_W : KIND_VB_W, KV = MCMC ? KIND_MC_V : KIND_VB_V;
+    constexpr int KW = FLAVOR == 1 ? KIND_MC_W : (FLAVOR == 2 ? KIND_VBO_W : KIND_VB_W);
+    constexpr int KV = FLAVOR == 1 ? KIND_MC_V : (FLAVOR == 2 ? KIND_VBO_V : KIND_VB_V);
+    const int batch = E->bv.on ? 0 : -1;
     for (size_t k = 0; k < steps.size(); k++) {
         const int s = steps[k];
         const bool first = (k == 0), prev_w = (!first && steps[k - 1] < 0), w = (s < 0);
@@ -355,14 +371,14 @@ static int sweep_streams(Engine* E) {
             else launch_stream<MCMC, false, true>(E, 0, !first, prev_w, !first, prev_w);
         }
         rp.run = 0; rp.rec_mode = 1; rp.p_prev = first ? nullptr : table(steps[k - 1]);
-        if (int rc = w ? combine_finalize<KW>(E, r0, s, -1, &rp) : combine_finalize<KV>(E, r0, s, -1, &rp)) return rc;
+        if (int rc = w ? combine_finalize<KW>(E, r0, s, batch, &rp) : combine_finalize<KV>(E, r0, s, batch, &rp)) return rc;
         {   // second field: pending I(s-1), U(s) + pass 1
             ProfScope ps(E, w ? 9 : 8);
             if (w) launch_stream<MCMC, true, true>(E, 1, !first, prev_w, true, true);
             else launch_stream<MCMC, false, true>(E, 1, !first, prev_w, true, false);
         }
         rp.run = 1; rp.rec_mode = 2; rp.p_prev = nullptr;
-        if (int rc = w ? combine_finalize<KW>(E, r1, s, -1, &rp) : combine_finalize<KV>(E, r1, s, -1, &rp)) return rc;
+        if (int rc = w ? combine_finalize<KW>(E, r1, s, batch, &rp) : combine_finalize<KV>(E, r1, s, batch, &rp)) return rc;
     }
     {   // flush the last step's updates into both copies
         ProfScope ps(E, 7);
@@ -392,7 +408,7 @@ int stream_tile_cols(Engine* E) {
 // every e_i += w0_delta, on both copies
 static void shift_e(Engine* E) {
     k_shift_e<<<SV_RGRID, 256, 0, E->stream>>>(E->d_e, E->tr.n, E->d_sc); LAUNCHED(E);
-    if (E->streams) { k_shift_e<<<SV_RGRID, 256, 0, E->stream>>>(E->d_e2, E->tr.n, E->d_sc); LAUNCHED(E); }
+    if (E->d_e2) { k_shift_e<<<SV_RGRID, 256, 0, E->stream>>>(E->d_e2, E->tr.n, E->d_sc); LAUNCHED(E); }
 }
 // (re)build the second copy from the first
 static void sync_e2(Engine* E) {
@@ -481,7 +497,7 @@ static int vb_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
         shift_e(E);
     }
     if (stream_ok(E)) {                                            // update_w + update_v (vb.h:390-440)
-        if (int rc = sweep_streams<false>(E)) return rc;
+        if (int rc = sweep_streams<0>(E)) return rc;
         if (int rc = exchange_blocks(E)) return rc;
     } else {
         if (E->cfg.k1)                                             // update_w, all columns (vb.h:390-406)
@@ -522,7 +538,7 @@ static int mcmc_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
                                   E->d_hyper_v, E->d_mu_v, E->cfg.seed, E->cfg.do_sample, E->cfg.do_multilevel); LAUNCHED(E);
     if (E->cfg.k0) shift_e(E);
     if (stream_ok(E)) {
-        if (int rc = sweep_streams<true>(E)) return rc;
+        if (int rc = sweep_streams<1>(E)) return rc;
         if (int rc = exchange_blocks(E)) return rc;
     } else {
         if (E->cfg.k1)
@@ -681,7 +697,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) cudaFreeAsync(p, E->stream);
     cudaStreamSynchronize(E->stream);
     if (E->own_stream) cudaStreamDestroy(E->own_stream);
@@ -937,7 +953,7 @@ int svbfm_reset(svbfm_t* h) {
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
     free_split(E, E->tr); free_split(E, E->te);
     E->runs.clear();
-    E->begun = false; E->have_state = false; E->rows_reordered = false; E->run0_sequential = false; E->streams = false; E->excl0 = false;
+    E->begun = false; E->have_state = false; E->rows_reordered = false; E->run0_sequential = false; E->streams = false; E->excl0 = false; E->vbo_streams = false; E->bv.on = false;
     SV_CUDA(E, cudaMemsetAsync(E->d_dT, 0, (size_t)E->D * 8, E->stream));
     SV_CUDA(E, cudaMemsetAsync(E->d_sc, 0, sizeof(Scalars), E->stream));
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
@@ -1000,6 +1016,14 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
     if (int rc = allreduce_sum_f64(E, E->d_batch_n, num_batch)) return rc;
     if (int rc = ensure_stats(E, 1)) return rc;
     SV_CUDA(E, cudaMemsetAsync(E->d_stats, 0, sizeof(DevStats), st));
+    // two complete fields on one GPU: every batch is swept by the stream schedule on its own entries (batch index lists built once
+    // per epoch) instead of scanning the whole design matrix with a batch mask per (batch, factor, field)
+    const bool use_streams = E->vbo_streams && S.n > 0 &&
+                             (uint64_t)num_batch * std::max(E->runs[0].col_end - E->runs[0].col_begin, E->runs[1].col_end - E->runs[1].col_begin) < (1ull << 31);
+    if (use_streams) {
+        if (!E->d_e2 && dev_alloc(E, &E->d_e2, S.n)) return SVBFM_ERR_OOM;
+        if (int rc = vbo_stream_prepare(E, num_batch)) return rc;
+    }
     cudaEvent_t t0, t1, t2;
     cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
     cudaEventRecord(t0, st);
@@ -1008,16 +1032,37 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
         // fresh y-hat, T for the cases of the batch (vbos.h:120-127)
         if (int rc = predict<PRED_VB_TRAIN>(E, S, E->d_e, 6, 1, (int)b)) return rc;
         SV_CUDA(E, cudaMemcpyAsync(&E->d_sc->sum_t, RED(E->d_sc, 6), 8, cudaMemcpyDeviceToDevice, st));
+        const uint32_t nb_cases = use_streams ? (uint32_t)(E->vbo_off[b + 1] - E->vbo_off[b]) : 0u;
+        if (use_streams && nb_cases) {
+            const Run &r0 = E->runs[0], &r1 = E->runs[1];
+            E->bv.on = true; E->bv.entry0 = E->vbo_off[b]; E->bv.n = nb_cases;
+            E->bv.ntiles = (uint32_t)(((uint64_t)nb_cases + (1ull << E->vbo_ts_shift) - 1) >> E->vbo_ts_shift);
+            for (int ri = 0; ri < 2; ri++) {
+                const Run& r = ri ? r1 : r0;
+                const uint32_t nc = r.col_end - r.col_begin;
+                // view indexed by global column id: view[j] = first position in idx of column j of batch b
+                E->bv.colptr[ri] = reinterpret_cast<const uint64_t*>(E->d_vbo_colptr[ri]) + (size_t)b * nc - r.col_begin;
+                k_tile_col0<<<nblk(E->bv.ntiles), 256, 0, st>>>(E->bv.colptr[ri], r.col_begin, r.col_end, E->bv.ntiles, E->vbo_ts_shift,
+                                                               E->d_vbo_tile_col0 + (ri ? E->vbo_max_tiles : 0)); LAUNCHED(E);
+            }
+            // second residual copy for the entries of the batch
+            k_gather_e_idx<<<nblk(nb_cases), 256, 0, st>>>(E->d_e, S.crow + S.h_colptr[r1.col_begin], E->d_vbo_idx[1], (uint32_t)E->vbo_off[b],
+                                                            (uint32_t)E->vbo_off[b + 1], E->d_e2); LAUNCHED(E);
+        }
         if (E->cfg.k0) {                                           // update_w0 (vbo.h:356-358)
             if (int rc = reduce_e(E, (int)b)) return rc;
             k_vbo_w0<<<1, 1, 0, st>>>(E->d_sc); LAUNCHED(E);
-            k_shift_e<<<SV_RGRID, 256, 0, st>>>(E->d_e, S.n, E->d_sc); LAUNCHED(E);
+            shift_e(E);
         }
-        for (const Run& r : E->runs)                               // update_w; also counts |Omega_j^b| (vbo.h:360-373)
-            if (int rc = sweep_run<KIND_VBO_W>(E, r, -1, (int)b)) return rc;
-        for (int f = 0; f < E->K; f++)                             // update_v (vbo.h:375-408)
-            for (const Run& r : E->runs)
-                if (int rc = sweep_run<KIND_VBO_V>(E, r, f, (int)b)) return rc;
+        if (use_streams) {
+            if (nb_cases) { int rc = sweep_streams<2>(E); E->bv.on = false; if (rc) return rc; }
+        } else {
+            for (const Run& r : E->runs)                           // update_w; also counts |Omega_j^b| (vbo.h:360-373)
+                if (int rc = sweep_run<KIND_VBO_W>(E, r, -1, (int)b)) return rc;
+            for (int f = 0; f < E->K; f++)                         // update_v (vbo.h:375-408)
+                for (const Run& r : E->runs)
+                    if (int rc = sweep_run<KIND_VBO_V>(E, r, f, (int)b)) return rc;
+        }
         if (int rc = reduce_e(E, (int)b)) return rc;
         k_reduce_dT<<<SV_GGRID, 256, 0, st>>>(E->d_dT, E->D, E->d_red_partial); LAUNCHED(E);
         k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_GGRID, 1, &E->d_sc->sum_t, 1); LAUNCHED(E);
@@ -1143,7 +1188,7 @@ int svbfm_get_info(svbfm_t* h, svbfm_info* out) {
     out->train_nnz = E->tr.nnz;
     out->rows_reordered = E->rows_reordered;
     out->world_size = (uint32_t)E->world;
-    out->fused_schedule = stream_ok(E) ? 1u : 0u;
+    out->fused_schedule = (stream_ok(E) || E->vbo_streams) ? 1u : 0u;
     out->exclusive_blocks = E->excl0 ? 1u : 0u;
     return SVBFM_OK;
 }

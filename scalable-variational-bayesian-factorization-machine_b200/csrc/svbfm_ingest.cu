@@ -421,8 +421,9 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
             }
             E->run0_sequential = true;
         }
-        E->streams = E->run0_sequential && E->cfg.method != SVBFM_VB_ONLINE && !getenv("SVBFM_NO_FUSE") && E->runs.size() == 2 && F == 2 &&
-                     E->runs[1].nnz == n;
+        const bool two_fields = E->run0_sequential && !getenv("SVBFM_NO_FUSE") && E->runs.size() == 2 && F == 2 && E->runs[1].nnz == n;
+        E->streams = two_fields && E->cfg.method != SVBFM_VB_ONLINE;
+        E->vbo_streams = two_fields && E->cfg.method == SVBFM_VB_ONLINE && E->world == 1 && !getenv("SVBFM_NO_VBO_STREAM");
         E->excl0 = false;
         if (E->world > 1) {      // one schedule for all ranks
             uint32_t* d_ok = d_flags + 6;
@@ -566,6 +567,86 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         SV_CUDA(E, cudaStreamSynchronize(st));
     }
     mark("tiles + exec order");
+    SV_CUDA(E, cudaGetLastError());
+    return 0;
+}
+
+// ---- vb_online on the stream schedule: batch index lists of one epoch ------------------------------------------------
+// keys for the stable sort by batch: run 0 entry q is case q; run 1 entry p is case crow1[p]
+static __global__ void k_vbo_keys(const uint16_t* __restrict__ rbatch, const uint32_t* __restrict__ crow1 /*null: run 0*/, uint32_t n,
+                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    keys[q] = rbatch[crow1 ? crow1[q] : q];
+    vals[q] = q;
+}
+// cnt[b * nc + (column of the case in the run - c0)] += 1; `which` selects the case's feature (0: first field, 1: second)
+static __global__ void k_vbo_hist(const uint16_t* __restrict__ rbatch, const uint32_t* __restrict__ rcol, uint32_t n, int which, uint32_t c0, uint32_t nc,
+                                  unsigned long long* __restrict__ cnt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t j = rcol[2 * (size_t)i + which];
+    atomicAdd(&cnt[(size_t)rbatch[i] * nc + (j - c0)], 1ull);          // integer atomics: order-independent
+}
+
+// For each field: idx = the run's entries stably sorted by batch (inside a batch they keep the run's column order), and
+// colptr[b * nc + c] = first position in idx of column c0 + c of batch b (histogram + exclusive scan; the flattened scan
+// makes colptr[(b + 1) * nc] the end of batch b). Stale after the next call.
+int vbo_stream_prepare(Engine* E, uint32_t num_batch) {
+    cudaStream_t st = E->stream;
+    const DevSplit& S = E->tr;
+    const uint32_t n = S.n;
+    E->vbo_off.assign((size_t)num_batch + 1, 0);
+    {
+        std::vector<unsigned long long> cnt(num_batch);
+        SV_CUDA(E, cudaMemcpyAsync(cnt.data(), E->d_batch_cnt, (size_t)num_batch * 8, cudaMemcpyDeviceToHost, st));
+        SV_CUDA(E, cudaStreamSynchronize(st));
+        for (uint32_t b = 0; b < num_batch; b++) E->vbo_off[b + 1] = E->vbo_off[b] + cnt[b];
+    }
+    // tiles of a batch pass: about 4 warps per scheduler on 148 SMs, between 64 and the regular tile size (or what the caller asked for)
+    if (E->cfg.tile_entries || getenv("SVBFM_TILE_ENTRIES")) E->vbo_ts_shift = E->ts_shift;
+    else {
+        uint64_t want = (n / std::max<uint32_t>(num_batch, 1)) / (148 * 32);
+        E->vbo_ts_shift = 6;
+        while (E->vbo_ts_shift < E->ts_shift && (2ull << E->vbo_ts_shift) <= want) E->vbo_ts_shift++;
+    }
+    uint32_t max_tiles = 1;
+    for (uint32_t b = 0; b < num_batch; b++)
+        max_tiles = std::max<uint32_t>(max_tiles, (uint32_t)(((E->vbo_off[b + 1] - E->vbo_off[b]) >> E->vbo_ts_shift) + 1));
+    if (max_tiles > E->vbo_max_tiles) {
+        cudaFreeAsync(E->d_vbo_tile_col0, st); cudaFreeAsync(E->d_vbo_partial, st);
+        E->d_vbo_tile_col0 = nullptr; E->d_vbo_partial = nullptr;
+        if (dev_alloc(E, &E->d_vbo_tile_col0, (size_t)max_tiles * 2)) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->d_vbo_partial, (size_t)max_tiles * 2 * 8)) return SVBFM_ERR_OOM;
+        E->vbo_max_tiles = max_tiles;
+    }
+    uint32_t *d_keys = nullptr, *d_vals = nullptr, *d_skeys = nullptr;
+    SV_CUDA(E, cudaMallocAsync((void**)&d_keys, std::max<size_t>(n, 1) * 4, st));
+    SV_CUDA(E, cudaMallocAsync((void**)&d_vals, std::max<size_t>(n, 1) * 4, st));
+    for (int ri = 0; ri < 2; ri++) {
+        const Run& r = E->runs[ri];
+        const uint32_t nc = r.col_end - r.col_begin;
+        const size_t ncp = (size_t)num_batch * nc + 1;
+        cudaFreeAsync(E->d_vbo_idx[ri], st); cudaFreeAsync(E->d_vbo_colptr[ri], st);
+        E->d_vbo_idx[ri] = nullptr; E->d_vbo_colptr[ri] = nullptr;
+        if (dev_alloc(E, &E->d_vbo_colptr[ri], ncp)) return SVBFM_ERR_OOM;
+        SV_CUDA(E, cudaMemsetAsync(E->d_vbo_colptr[ri], 0, ncp * 8, st));
+        if (n) {
+            k_vbo_keys<<<nblk(n), 256, 0, st>>>(E->d_rbatch, ri ? S.crow + S.h_colptr[r.col_begin] : nullptr, n, d_keys, d_vals);
+            if (int rc = sort_pairs(E, d_keys, d_vals, n, std::max<uint32_t>(num_batch, 1), &d_skeys, &E->d_vbo_idx[ri])) return rc;
+            cudaFreeAsync(d_skeys, st);
+            E->dev_bytes += (size_t)n * 4;
+            k_vbo_hist<<<nblk(n), 256, 0, st>>>(E->d_rbatch, S.rcol, n, ri, r.col_begin, nc, E->d_vbo_colptr[ri]);
+        } else if (dev_alloc(E, &E->d_vbo_idx[ri], 1)) return SVBFM_ERR_OOM;
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, E->d_vbo_colptr[ri], E->d_vbo_colptr[ri], (int64_t)ncp, st);
+        void* tmp = nullptr;
+        SV_CUDA(E, cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, st));
+        cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, E->d_vbo_colptr[ri], E->d_vbo_colptr[ri], (int64_t)ncp, st);
+        cudaFreeAsync(tmp, st);
+        if (e != cudaSuccess) return fail(E, SVBFM_ERR_CUDA, std::string("vb_online scan: ") + cudaGetErrorString(e));
+    }
+    cudaFreeAsync(d_keys, st); cudaFreeAsync(d_vals, st);
     SV_CUDA(E, cudaGetLastError());
     return 0;
 }

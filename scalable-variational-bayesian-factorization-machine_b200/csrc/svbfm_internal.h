@@ -133,6 +133,22 @@ struct Engine {
     struct OwnPack* d_opack = nullptr; // [D] own-side constants of the next pass
     double2* d_ab = nullptr;           // [D] sharded: {A, B} of every column, the allreduce buffer
     double2* d_pvT = nullptr;          // [D][K] transposed factor parameters for the two-field train prediction (k_predict2)
+    // vb_online on the stream schedule (single GPU, two complete fields): per epoch, for each field the entries of every
+    // batch in column order (idx: positions inside the run) and the batches' own column pointers into idx
+    bool vbo_streams = false;
+    uint32_t* d_vbo_idx[2] = {nullptr, nullptr};           // [n] each
+    unsigned long long* d_vbo_colptr[2] = {nullptr, nullptr};   // [num_batch * ncols(run) + 1] each
+    uint32_t* d_vbo_tile_col0 = nullptr;                   // [2][vbo_max_tiles]
+    double* d_vbo_partial = nullptr;                       // [2][vbo_max_tiles][2][4]
+    uint32_t vbo_max_tiles = 0;
+    std::vector<uint64_t> vbo_off;                         // [num_batch + 1] first entry of every batch in idx
+    struct BatchView {                                      // what launch_stream / combine_finalize use instead of the whole run
+        bool on = false;
+        const uint64_t* colptr[2] = {nullptr, nullptr};
+        uint64_t entry0 = 0;
+        uint32_t n = 0, ntiles = 0;
+    } bv;
+    uint32_t vbo_ts_shift = 9;          // tile size of the batch passes: small enough that one batch fills the GPU with warps
     // state
     double2* d_pw = nullptr;          // [D]
     double2* d_pv = nullptr;          // [K][D]
@@ -193,6 +209,7 @@ void free_split(Engine* E, DevSplit& S);
 int stream_tile_cols(Engine* E);   // svbfm_engine.cu: first column of every implicit tile (k_tile_col0)
 int allreduce(Engine* E, void* buf, size_t count, int dtype /*nccl*/, int op /*nccl*/);
 int detect_exclusive_blocks(Engine* E);   // svbfm_engine.cu; collective (every rank calls it after the train split is in)
+int vbo_stream_prepare(Engine* E, uint32_t num_batch);   // svbfm_ingest.cu: per-epoch batch index lists (needs d_rbatch, d_cbatch, d_batch_cnt)
 
 // error helpers
 int fail(Engine* E, int code, const std::string& msg);

@@ -238,7 +238,8 @@ __global__ void k_combine_light(uint32_t c0, uint32_t c1, const uint32_t* __rest
 struct SpanView {
     const uint64_t* colptr;   // null: the explicit-tile layout (col_tile0 / partial[tile][4]) is in use
     uint64_t entry0;          // first entry of the run
-    uint32_t ts_shift;        // tile = 2^ts_shift entries (Engine::ts_shift; 1024 by default)
+    uint32_t ts_shift;        // tile = 2^ts_shift entries (Engine::ts_shift)
+    uint32_t light_limit;     // columns spanning more tiles than this have their sums in colsum[j] (k_combine_span); ~0u: none
 };
 
 __global__ void __launch_bounds__(128) k_combine_span(const uint32_t* __restrict__ heavy_cols, uint32_t h0, SpanView sp,
@@ -269,7 +270,7 @@ __device__ __forceinline__ bool span_sum(uint32_t j, SpanView sp, const double* 
     empty = (e == b);
     if (empty) return true;
     uint64_t T0 = (b - sp.entry0) >> sp.ts_shift, T1 = (e - 1 - sp.entry0) >> sp.ts_shift;
-    if (T0 == T1 || T1 - T0 > SV_SPAN_LIGHT) return false;
+    if (T0 == T1 || T1 - T0 > (uint64_t)sp.light_limit) return false;
     for (uint64_t T = T0; T <= T1; T++) {
         const double2* p = reinterpret_cast<const double2*>(partial + (T * 2 + (T == T0 ? 1 : 0)) * 4);
         double2 x = p[0], y = p[1];
@@ -354,6 +355,19 @@ struct FinalizeArgs {
     int update_t;                // vb_online: 1 when this sweep advances t_cnt (w: always; v: f == 0)
 };
 
+// stream schedule: the records of column j for the passes that follow its update (see k_stream)
+__device__ __forceinline__ void write_records(const FinalizeArgs& a, uint32_t j, double new_mean, double new_var, double dlt, double mu_old) {
+    if (!a.rec_mode) return;
+    double2 N = a.p_next ? a.p_next[j] : make_double2(0.0, 0.0);
+    if (a.rec_mode == 1) {
+        a.cpack[j] = ColPack{new_mean, new_var, dlt, a.p_prev ? a.p_prev[j].x : 0.0};
+        a.opack[j] = OwnPack{N.x, new_mean, dlt, 0.0};
+    } else {
+        a.cpack[j] = ColPack{N.x, N.y, dlt, mu_old};
+        a.opack[j] = OwnPack{N.x, N.x, dlt, 0.0};
+    }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
     static_assert(KIND <= KIND_MC_V, "vb_online uses k_finalize_vbo");
@@ -410,16 +424,7 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
         new_mean = v; new_var = 0.0; dlt = skip ? 0.0 : (v - v_old);         // e -= h (v_old - v)  (mcmc.h:716 / :833)
         a.delta[j] = dlt;
     }
-    if (a.rec_mode) {
-        double2 N = a.p_next ? a.p_next[j] : make_double2(0.0, 0.0);
-        if (a.rec_mode == 1) {
-            a.cpack[j] = ColPack{new_mean, new_var, dlt, a.p_prev ? a.p_prev[j].x : 0.0};
-            a.opack[j] = OwnPack{N.x, new_mean, dlt, 0.0};
-        } else {
-            a.cpack[j] = ColPack{N.x, N.y, dlt, mu_old};
-            a.opack[j] = OwnPack{N.x, N.x, dlt, 0.0};
-        }
-    }
+    write_records(a, j, new_mean, new_var, dlt, mu_old);
     if (bad) atomicAdd(&a.sc->nan_inf, (unsigned long long)bad);
 }
 
@@ -431,11 +436,25 @@ __global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __
     uint32_t j = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= a.c1) return;
     double A, B, C1, C2;
-    load_colsum(j, a.col_tile0, a.partial, a.colsum, a.from_colsum, A, B, C1, C2);
     double cnt;
-    if constexpr (KIND == KIND_VBO_W) { cnt = C1; cnt_arr[j] = cnt; }   // the w pass also counts the batch entries of the column
-    else cnt = cnt_arr[j];
-    if (cnt == 0.0 || !update_params) { a.delta[j] = 0.0; return; }     // empty columns are skipped (vbo.h:367, 394)
+    if (a.span.colptr) {
+        // stream schedule: colptr is the batch's own column pointer, so the column's batch entries are counted directly.
+        // Records of a skipped column are not written: no entry of the batch refers to it.
+        cnt = (double)(a.span.colptr[j + 1] - a.span.colptr[j]);
+        if (cnt == 0.0 || !update_params) { a.delta[j] = 0.0; return; }
+        bool empty;
+        if (!span_sum(j, a.span, a.partial, A, B, C1, C2, empty)) {
+            const double2* p = reinterpret_cast<const double2*>(a.colsum + (size_t)j * 4);
+            double2 x = p[0], y = p[1];
+            A = x.x; B = x.y; C1 = y.x; C2 = y.y;
+        }
+        if constexpr (KIND == KIND_VBO_V) B = C1 + C2;
+    } else {
+        load_colsum(j, a.col_tile0, a.partial, a.colsum, a.from_colsum, A, B, C1, C2);
+        if constexpr (KIND == KIND_VBO_W) { cnt = C1; cnt_arr[j] = cnt; }   // the w pass also counts the batch entries of the column
+        else cnt = cnt_arr[j];
+        if (cnt == 0.0 || !update_params) { a.delta[j] = 0.0; return; }     // empty columns are skipped (vbo.h:367, 394)
+    }
     uint32_t g = a.group[j];
     double hy = (a.f < 0) ? a.hyper[g] : a.hyper[(size_t)g * a.K + a.f];
     double alpha = a.sc->alpha;
@@ -460,6 +479,7 @@ __global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __
         if constexpr (KIND == KIND_VBO_W) a.dT[j] += B * (sg - sg_dash);
         else a.dT[j] += (C1 + C2) * (sg - sg_dash) + C1 * (mu * mu - mu_dash * mu_dash);
     }
+    write_records(a, j, mu, sg, skip ? 0.0 : (mu_dash - mu), mu_dash);
     if (bad) atomicAdd(&a.sc->nan_inf, (unsigned long long)bad);
 }
 
@@ -510,7 +530,10 @@ struct StreamArgs {
     const uint64_t* colptr;
     uint32_t c0, c1;          // columns of the run
     uint64_t entry0;          // colptr[c0]
-    uint32_t n;               // entries of the run (= cases)
+    uint64_t real0;           // first entry of the run in oc / xv / xo (= entry0 unless idx is set)
+    const uint32_t* idx;      // IDX: entry k of this pass is the run's entry idx[entry0 + k] (vb_online: the entries of one batch,
+                              // in column order; colptr then is the batch's own column pointer into idx)
+    uint32_t n;               // entries of the pass
     uint32_t ntiles, ts_shift;
     const uint32_t* tile_col0;
     const uint32_t* oc;       // [nnz] other column of every entry
@@ -598,7 +621,7 @@ __device__ __forceinline__ void entry_terms(double ei, float xf, float xof, cons
 #ifndef SV_STREAM_MINB
 #define SV_STREAM_MINB 3     // resident CTAs per SM the register allocation aims at (72 registers, no spills)
 #endif
-template <int KIND, bool ONES, bool REDUCE, bool STEADY>
+template <int KIND, bool ONES, bool REDUCE, bool STEADY, bool IDX = false>
 __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
     constexpr bool IS_V = (KIND == KIND_VB_V || KIND == KIND_MC_V);
     constexpr unsigned FULL = 0xffffffffu;
@@ -609,9 +632,10 @@ __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
     // entry positions relative to the run (32 bit)
     const uint32_t q_begin = t << a.ts_shift;
     const uint32_t q_end = (a.n - q_begin > (1u << a.ts_shift)) ? q_begin + (1u << a.ts_shift) : a.n;
-    const uint32_t* __restrict__ ocp = a.oc + a.entry0;
-    const float* __restrict__ xvp = ONES ? nullptr : a.xv + a.entry0;
-    const float* __restrict__ xop = ONES ? nullptr : a.xo + a.entry0;
+    const uint32_t* __restrict__ ocp = a.oc + a.real0;
+    const float* __restrict__ xvp = ONES ? nullptr : a.xv + a.real0;
+    const float* __restrict__ xop = ONES ? nullptr : a.xo + a.real0;
+    const uint32_t* __restrict__ idxp = IDX ? a.idx + a.entry0 : nullptr;
     double* __restrict__ ep = a.e;
     const bool has_own = STEADY ? true : (a.has_own != 0), own_is_w = STEADY ? false : (a.own_is_w != 0);
     const bool has_oth = STEADY ? true : (a.has_oth != 0), oth_is_w = STEADY ? false : (a.oth_is_w != 0);
@@ -620,11 +644,13 @@ __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
 
     // next batch of the streams (issued one batch ahead)
     uint32_t oc_n[U]; float xs_n[U], xo_n[U]; double e_n[U];
+    uint32_t r_n[IDX ? U : 1];              // IDX: the real positions of the batch (needed again for the store)
     auto load_batch = [&](uint32_t q) {
         if (q_end - q >= 32 * U) {          // a whole batch: no predicates
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 uint32_t k = q + u * 32 + lane;
+                if constexpr (IDX) { k = __ldcs(idxp + k); r_n[u] = k; }
                 oc_n[u] = __ldcs(ocp + k);
                 xs_n[u] = 1.0f; xo_n[u] = 1.0f;
                 if constexpr (!ONES) { xs_n[u] = __ldcs(xvp + k); xo_n[u] = __ldcs(xop + k); }
@@ -635,6 +661,7 @@ __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
             for (int u = 0; u < U; u++) {
                 uint32_t k = q + u * 32 + lane;
                 bool ok = k < q_end;
+                if constexpr (IDX) { k = ok ? __ldcs(idxp + k) : 0u; r_n[u] = k; }
                 oc_n[u] = ok ? __ldcs(ocp + k) : 0u;
                 xs_n[u] = 1.0f; xo_n[u] = 1.0f;
                 if constexpr (!ONES) if (ok) { xs_n[u] = __ldcs(xvp + k); xo_n[u] = __ldcs(xop + k); }
@@ -703,8 +730,9 @@ __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
 
     for (uint32_t q0 = q_begin; q0 < q_end && !done; q0 += 32 * U) {
         uint32_t oc[U]; float xs[U], xo[U]; double es[U]; ColPack g[U];
+        uint32_t rr[IDX ? U : 1];
 #pragma unroll
-        for (int u = 0; u < U; u++) { oc[u] = oc_n[u]; xs[u] = xs_n[u]; xo[u] = xo_n[u]; es[u] = e_n[u]; }
+        for (int u = 0; u < U; u++) { oc[u] = oc_n[u]; xs[u] = xs_n[u]; xo[u] = xo_n[u]; es[u] = e_n[u]; if constexpr (IDX) rr[u] = r_n[u]; }
         const bool full = (q_end - q0 >= 32 * U);
         if ((STEADY || need_rec) && full) {
 #pragma unroll
@@ -722,7 +750,7 @@ __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 double ei = apply_pending<ONES>(es[u], xs[u], xo[u], g[u], h_oth, d_own, has_own, own_is_w, has_oth, oth_is_w);
-                if (pend) __stcs(ep + q0 + u * 32 + lane, ei);
+                if (pend) { uint32_t k = q0 + u * 32 + lane; if constexpr (IDX) k = rr[u]; __stcs(ep + k, ei); }
                 if constexpr (REDUCE) entry_terms<KIND>(ei, xs[u], xo[u], g[u], mu, A, B, C1, C2);
             }
             if (next_b == q0 + 32 * U) {             // column j ends exactly with the batch
@@ -754,7 +782,7 @@ __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
                 advance(seg_b);
                 if (seg_b >= row_e) break;
             }
-            if (pend && k < row_e) __stcs(ep + k, ei);
+            if (pend && k < row_e) { uint32_t kr = k; if constexpr (IDX) kr = rr[u]; __stcs(ep + kr, ei); }
         }
     }
     if constexpr (REDUCE) if (!done) emit(cur_b, next_b);   // column j continues in the next tile
@@ -869,6 +897,16 @@ __global__ void __launch_bounds__(256) k_reduce_dT(double* __restrict__ dT, uint
 }
 
 __global__ void k_add_scalar(double* dst, const double* src) { *dst += *src; }
+
+// ---- vb_online on the stream schedule: per epoch, the entries of every batch in column order ------------------------
+// second residual copy for the entries of one batch: e2[p] = e[crow1[p]] for p in idx1[lo, hi)
+__global__ void k_gather_e_idx(const double* __restrict__ e, const uint32_t* __restrict__ crow1, const uint32_t* __restrict__ idx, uint32_t lo,
+                               uint32_t hi, double* __restrict__ e2) {
+    uint32_t k = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= hi) return;
+    uint32_t p = idx[k];
+    e2[p] = e[crow1[p]];
+}
 
 // sharded stream schedule: block exchange of run 0's parameters. row 0 = w (when present), then one row per factor.
 struct BlockXchg {
@@ -1429,7 +1467,7 @@ __global__ void k_pack_h4(uint32_t c0, uint32_t c1, const double2* __restrict__ 
     if (j < c1) cpack[j].h4 = p[j].x;
 }
 // first column that intersects each implicit tile of a run (largest j in [c0, c1) with colptr[j] <= first entry of the tile)
-__global__ void k_tile_col0(const uint64_t* __restrict__ colptr, uint32_t c0, uint32_t c1, uint32_t ntiles, uint32_t ts_shift, uint32_t* __restrict__ out) {
+__global__ void k_tile_col0(const uint64_t* colptr, uint32_t c0, uint32_t c1, uint32_t ntiles, uint32_t ts_shift, uint32_t* __restrict__ out) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
     uint64_t p = colptr[c0] + ((uint64_t)t << ts_shift);

@@ -131,6 +131,27 @@ def test_vb_online_vs_oracle(built):
         assert np.max(np.abs(so[k] - sg[k])) < 1e-9, k
 
 
+@pytest.mark.parametrize("values,k1,tile_entries", [(False, 1, 32), (True, 1, 64), (False, 0, 0), (True, 0, 256)])
+def test_vb_online_stream_equals_general(built, monkeypatch, values, k1, tile_entries):
+    """vb_online on two complete fields sweeps every batch with the stream schedule on the batch's own entries (per-epoch index
+    lists); the masked general schedule (validated against the oracle above and below) must give the same statistics."""
+    tr, te = two_field(9000, 900, 140, 110, seed=33, values=values)
+    out = []
+    for general in (False, True):
+        if general:
+            monkeypatch.setenv("SVBFM_NO_VBO_STREAM", "1")
+        L = make_learner("vb_online", tr, te, 3, num_iter=3, num_batch=7, k1=k1, tile_entries=tile_entries)
+        hist = L.learn(to_csc(tr), to_csc(te))
+        assert L.engine.info()["fused_schedule"] == (0 if general else 1)
+        out.append(([(s.test_rmse, s.free_energy, s.alpha) for s in hist], L.engine.get_state()))
+        L.engine.close()
+        monkeypatch.delenv("SVBFM_NO_VBO_STREAM", raising=False)
+    for a, b in zip(out[0][0], out[1][0]):
+        assert all(rel(x, y) < 1e-9 for x, y in zip(a, b)), (a, b)
+    for k in ("w_mean", "w_var", "v_mean", "v_var"):
+        assert np.max(np.abs(out[0][1][k] - out[1][1][k])) < 1e-10, k
+
+
 def test_vb_online_ragged_groups(built):
     tr, te = ragged(2500, 300, 40, seed=41)
     D = max(tr.n_feat, te.n_feat)
