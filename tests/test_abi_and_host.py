@@ -89,3 +89,24 @@ def test_cmdline_semantics(built):
     assert "already specified" in p.stderr
     p = subprocess.run([exe, "-help"], capture_output=True, text=True)
     assert "-method" in p.stdout and "-dim" in p.stdout
+
+
+def test_balanced_user_block_cuts():
+    """bench.py's contiguous partition of a heavy-tailed cost vector: covers everything, ordered, and the heaviest part stays close to the
+    unavoidable bound max(total / parts, heaviest element) where plain quantile cuts are off by half the heaviest element."""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    g = torch.Generator().manual_seed(3)
+    U = 50_000
+    p = 1.0 / torch.arange(1, U + 1, dtype=torch.float64)
+    cost = torch.empty(U, dtype=torch.float64)
+    cost[torch.randperm(U, generator=g)] = p / p.sum() * 1e9
+    for parts in (1, 2, 3, 8):
+        b = bench.balanced_cuts(cost, parts)
+        assert len(b) == parts + 1 and b[0] == 0 and b[-1] == U and all(x <= y for x, y in zip(b, b[1:]))
+        loads = [float(cost[b[i]:b[i + 1]].sum()) for i in range(parts)]
+        bound = max(float(cost.sum()) / parts, float(cost.max()))
+        assert max(loads) <= 1.15 * bound, (parts, max(loads) / bound)
