@@ -618,6 +618,9 @@ __device__ __forceinline__ void entry_terms(double ei, float xf, float xof, cons
 #ifndef SV_STREAM_U
 #define SV_STREAM_U 2        // rows of 32 entries per batch (measured: 2 x 4 CTAs/SM beats 4 x 2, gpurun_out/tune_*)
 #endif
+#ifndef SV_STREAM_GPIPE
+#define SV_STREAM_GPIPE 0    // 1: records gathered one batch ahead of the arithmetic (more registers)
+#endif
 #ifndef SV_STREAM_MINB
 #define SV_STREAM_MINB 3     // resident CTAs per SM the register allocation aims at (72 registers, no spills)
 #endif
@@ -728,23 +731,10 @@ __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
     };
     bool done = false;
 
-    for (uint32_t q0 = q_begin; q0 < q_end && !done; q0 += 32 * U) {
-        uint32_t oc[U]; float xs[U], xo[U]; double es[U]; ColPack g[U];
-        uint32_t rr[IDX ? U : 1];
-#pragma unroll
-        for (int u = 0; u < U; u++) { oc[u] = oc_n[u]; xs[u] = xs_n[u]; xo[u] = xo_n[u]; es[u] = e_n[u]; if constexpr (IDX) rr[u] = r_n[u]; }
+    // arithmetic of one batch (entries q0 .. q0 + 32 U) once its streams and records are in registers
+    auto process = [&](uint32_t q0, const float (&xs)[U], const float (&xo)[U], const double (&es)[U], const uint32_t (&rr)[IDX ? U : 1],
+                       const ColPack (&g)[U]) {
         const bool full = (q_end - q0 >= 32 * U);
-        if ((STEADY || need_rec) && full) {
-#pragma unroll
-            for (int u = 0; u < U; u++) g[u] = a.rec[oc[u]];
-        } else {
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                if (need_rec && q0 + u * 32 + lane < q_end) g[u] = a.rec[oc[u]];
-                else g[u] = ColPack{0.0, 0.0, 0.0, 0.0};
-            }
-        }
-        if (q_end - q0 > 32 * U) load_batch(q0 + 32 * U);
         if (full && next_b >= q0 + 32 * U) {
             // the whole batch lies inside column j: no per-lane predicates
 #pragma unroll
@@ -758,7 +748,7 @@ __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
                 if (next_b >= q_end) done = true;
                 else advance(next_b);
             }
-            continue;
+            return;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -784,7 +774,54 @@ __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
             }
             if (pend && k < row_e) { uint32_t kr = k; if constexpr (IDX) kr = rr[u]; __stcs(ep + kr, ei); }
         }
+    };
+    auto gather = [&](uint32_t q0, const uint32_t (&oc)[U], ColPack (&g)[U]) {
+        if ((STEADY || need_rec) && q_end - q0 >= 32 * U) {
+#pragma unroll
+            for (int u = 0; u < U; u++) g[u] = a.rec[oc[u]];
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (need_rec && q0 + u * 32 + lane < q_end) g[u] = a.rec[oc[u]];
+                else g[u] = ColPack{0.0, 0.0, 0.0, 0.0};
+            }
+        }
+    };
+#if SV_STREAM_GPIPE
+    // records gathered one batch ahead of the arithmetic, streams two batches ahead
+    {
+        float xs[U], xo[U]; double es[U]; uint32_t rr[IDX ? U : 1]; ColPack g[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { xs[u] = xs_n[u]; xo[u] = xo_n[u]; es[u] = e_n[u]; if constexpr (IDX) rr[u] = r_n[u]; }
+        gather(q_begin, oc_n, g);
+        if (q_end - q_begin > 32 * U) load_batch(q_begin + 32 * U);
+        for (uint32_t q0 = q_begin; q0 < q_end && !done; q0 += 32 * U) {
+            float xs1[U], xo1[U]; double es1[U]; uint32_t rr1[IDX ? U : 1]; ColPack g1[U];
+            const bool more = q_end - q0 > 32 * U;
+            if (more) {
+                gather(q0 + 32 * U, oc_n, g1);
+#pragma unroll
+                for (int u = 0; u < U; u++) { xs1[u] = xs_n[u]; xo1[u] = xo_n[u]; es1[u] = e_n[u]; if constexpr (IDX) rr1[u] = r_n[u]; }
+                if (q_end - q0 > 64 * U) load_batch(q0 + 64 * U);
+            }
+            process(q0, xs, xo, es, rr, g);
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < U; u++) { xs[u] = xs1[u]; xo[u] = xo1[u]; es[u] = es1[u]; g[u] = g1[u]; if constexpr (IDX) rr[u] = rr1[u]; }
+            }
+        }
     }
+#else
+    for (uint32_t q0 = q_begin; q0 < q_end && !done; q0 += 32 * U) {
+        float xs[U], xo[U]; double es[U]; ColPack g[U];
+        uint32_t rr[IDX ? U : 1];
+#pragma unroll
+        for (int u = 0; u < U; u++) { xs[u] = xs_n[u]; xo[u] = xo_n[u]; es[u] = e_n[u]; if constexpr (IDX) rr[u] = r_n[u]; }
+        gather(q0, oc_n, g);
+        if (q_end - q0 > 32 * U) load_batch(q0 + 32 * U);
+        process(q0, xs, xo, es, rr, g);
+    }
+#endif
     if constexpr (REDUCE) if (!done) emit(cur_b, next_b);   // column j continues in the next tile
 }
 
