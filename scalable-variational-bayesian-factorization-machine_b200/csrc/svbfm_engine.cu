@@ -656,6 +656,9 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     ce = cudaStreamCreateWithFlags(&E->own_stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(ce); delete E; --g_handles; return SVBFM_ERR_CUDA; }
     E->stream = E->own_stream;
+    if (!getenv("SVBFM_NO_COPY_STREAM") && cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking) == cudaSuccess) {
+        if (cudaEventCreateWithFlags(&E->copy_event, cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(E->copy_stream); E->copy_stream = nullptr; }
+    } else E->copy_stream = nullptr;
     E->G = 1;
     E->h_group.assign(E->D, 0);
     E->h_n_per_group.assign(1, E->D);
@@ -700,6 +703,8 @@ void svbfm_destroy(svbfm_t* h) {
                     E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) cudaFreeAsync(p, E->stream);
     cudaStreamSynchronize(E->stream);
+    if (E->copy_stream) { cudaStreamSynchronize(E->copy_stream); cudaStreamDestroy(E->copy_stream); }
+    if (E->copy_event) cudaEventDestroy(E->copy_event);
     if (E->own_stream) cudaStreamDestroy(E->own_stream);
     delete E;
     if (--g_handles == 0) sv_cache_release();      // the last handle gives the cached device blocks back to the driver

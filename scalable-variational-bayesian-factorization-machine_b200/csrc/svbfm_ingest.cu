@@ -280,18 +280,22 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     if (dev_alloc(E, &S.y, n)) return SVBFM_ERR_OOM;
     float* d_x = nullptr;
     SV_CUDA(E, cudaMallocAsync((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4, E->stream));
-    SV_CUDA(E, cudaMemcpyAsync(S.colptr, S.h_colptr.data(), ((size_t)S.ncols_ext + 1) * 8, cudaMemcpyHostToDevice, st));
-    SV_CUDA(E, cudaMemcpyAsync(S.crow, case_id, nnz * 4, cudaMemcpyHostToDevice, st));
-    SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, st));
-    SV_CUDA(E, cudaMemcpyAsync(S.y, target, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-
+    // The values and the targets are not needed before the CSR gather / the case re-ordering: they travel on a second stream
+    // while the main stream sorts the case ids (pinned host buffers; with pageable memory the copies serialise anyway).
+    cudaStream_t cs = E->copy_stream ? E->copy_stream : st;
     uint32_t* d_flags = nullptr;   // [0] any x != 1  [1] case id out of range  [2] duplicate feature in a case  [3] non-uniform  [4] perm not identity
     SV_CUDA(E, cudaMallocAsync((void**)&d_flags, 8 * 4, E->stream));
     SV_CUDA(E, cudaMemsetAsync(d_flags, 0, 8 * 4, st));
-    if (nnz) {
-        k_any_not_one<<<std::min<unsigned>(nblk(nnz), 148 * 16), 256, 0, st>>>(d_x, nnz, d_flags + 0);
-        k_check_case_ids<<<nblk(nnz), 256, 0, st>>>(S.crow, nnz, n, d_flags + 1);
+    if (cs != st) {                // everything queued on the main stream so far (earlier users of the recycled blocks, the memset) first
+        SV_CUDA(E, cudaEventRecord(E->copy_event, st));
+        SV_CUDA(E, cudaStreamWaitEvent(cs, E->copy_event, 0));
     }
+    SV_CUDA(E, cudaMemcpyAsync(S.colptr, S.h_colptr.data(), ((size_t)S.ncols_ext + 1) * 8, cudaMemcpyHostToDevice, st));
+    SV_CUDA(E, cudaMemcpyAsync(S.crow, case_id, nnz * 4, cudaMemcpyHostToDevice, st));
+    SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, cs));
+    if (nnz) k_any_not_one<<<std::min<unsigned>(nblk(nnz), 148 * 16), 256, 0, cs>>>(d_x, nnz, d_flags + 0);
+    SV_CUDA(E, cudaMemcpyAsync(S.y, target, (size_t)n * 4, cudaMemcpyHostToDevice, cs));
+    if (nnz) k_check_case_ids<<<nblk(nnz), 256, 0, st>>>(S.crow, nnz, n, d_flags + 1);
     // CSC -> CSR: feature id per entry, stable sort by case id
     uint32_t *d_colof = nullptr, *d_idx = nullptr, *d_skeys = nullptr, *d_sidx = nullptr;
     SV_CUDA(E, cudaMallocAsync((void**)&d_colof, std::max<uint64_t>(nnz, 1) * 4, E->stream));
@@ -301,12 +305,15 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         k_iota<<<nblk(nnz), 256, 0, st>>>(d_idx, nnz);
     }
     uint32_t h_flags[8];
-    SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
+    SV_CUDA(E, cudaMemcpyAsync(h_flags + 1, d_flags + 1, 4, cudaMemcpyDeviceToHost, st));
     SV_CUDA(E, cudaStreamSynchronize(st));
-    if (h_flags[1]) { cudaFreeAsync(d_x, E->stream); cudaFreeAsync(d_flags, E->stream); cudaFreeAsync(d_colof, E->stream); cudaFreeAsync(d_idx, E->stream); return fail(E, SVBFM_ERR_ARG, "set_csc: case id out of range"); }
-    S.all_ones = (h_flags[0] == 0);
-    mark("validate + H2D + col_of_entry");
-    if (int r = sort_pairs(E, S.crow, d_idx, nnz, std::max<uint32_t>(n, 1), &d_skeys, &d_sidx)) return r;
+    if (h_flags[1]) {
+        cudaStreamSynchronize(cs);
+        cudaFreeAsync(d_x, E->stream); cudaFreeAsync(d_flags, E->stream); cudaFreeAsync(d_colof, E->stream); cudaFreeAsync(d_idx, E->stream);
+        return fail(E, SVBFM_ERR_ARG, "set_csc: case id out of range");
+    }
+    mark("H2D of the case ids + col_of_entry");
+    if (int r = sort_pairs(E, S.crow, d_idx, nnz, std::max<uint32_t>(n, 1), &d_skeys, &d_sidx)) { cudaStreamSynchronize(cs); return r; }
     mark("  sort pairs by case");
     cudaFreeAsync(d_idx, E->stream);
     uint64_t* d_rowptr = nullptr;
@@ -316,12 +323,8 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     cudaFreeAsync(d_skeys, E->stream);
     uint32_t* d_rcol = nullptr; float* d_rval = nullptr;
     SV_CUDA(E, cudaMallocAsync((void**)&d_rcol, std::max<uint64_t>(nnz, 1) * 4, E->stream));
-    if (!S.all_ones) SV_CUDA(E, cudaMallocAsync((void**)&d_rval, std::max<uint64_t>(nnz, 1) * 4, E->stream));
-    if (nnz) {
-        k_gather_u32<<<nblk(nnz), 256, 0, st>>>(d_colof, d_sidx, nnz, d_rcol);
-        if (!S.all_ones) k_gather_f32<<<nblk(nnz), 256, 0, st>>>(d_x, d_sidx, nnz, d_rval);
-    }
-    cudaFreeAsync(d_sidx, E->stream); cudaFreeAsync(d_colof, E->stream);
+    if (nnz) k_gather_u32<<<nblk(nnz), 256, 0, st>>>(d_colof, d_sidx, nnz, d_rcol);
+    cudaFreeAsync(d_colof, E->stream);
     mark("sort by case + CSR gather");
 
     // per-case scan: duplicates, uniform length, need[]
@@ -331,6 +334,16 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         SV_CUDA(E, cudaMemsetAsync(d_need, 0, std::max<uint32_t>(S.ncols_ext, 1) * 4, st));
     }
     if (n) k_scan_rows<<<nblk(n), 256, 0, st>>>(d_rowptr, d_rcol, n, d_need, d_flags + 2);
+    // the values and targets have had the sort, the CSR gather and the row scan to arrive
+    SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 4, cudaMemcpyDeviceToHost, cs));
+    SV_CUDA(E, cudaStreamSynchronize(cs));
+    S.all_ones = (h_flags[0] == 0);
+    if (!S.all_ones) {
+        SV_CUDA(E, cudaMallocAsync((void**)&d_rval, std::max<uint64_t>(nnz, 1) * 4, E->stream));
+        if (nnz) k_gather_f32<<<nblk(nnz), 256, 0, st>>>(d_x, d_sidx, nnz, d_rval);
+    }
+    cudaFreeAsync(d_sidx, E->stream);
+    mark("  H2D of values and targets (overlapped) + row scan");
     SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
     SV_CUDA(E, cudaStreamSynchronize(st));
     if (h_flags[2]) {

@@ -104,6 +104,8 @@ struct Engine {
     std::string err;
     int dev = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // second stream of the ingest (H2D of values / targets overlaps the sort of the case ids)
+    cudaEvent_t copy_event = nullptr;
     uint32_t D = 0, G = 1;
     int K = 0;
     // groups
