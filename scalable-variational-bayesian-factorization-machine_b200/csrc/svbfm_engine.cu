@@ -470,11 +470,20 @@ static int predict_train(Engine* E, int red_slot) {
     a.sc = E->d_sc; a.e = E->d_e; a.partial = E->d_red_partial;
     const unsigned grid = std::max(1u, std::min<unsigned>((S.n + 255) / 256, SV_RGRID / 2));   // partial[] holds grid * 8 <= SV_RGRID * 4 sums
     constexpr bool MC = (MODE == PRED_MC_TRAIN);
-    const int ns = E->K <= 32 ? 1 : (E->K <= 64 ? 2 : (E->K <= 128 ? 4 : 8));
+    // a warp per case. Half a warp per case (two cases share the fixed cost of a warp step) is built too, but measured slower
+    // (begin 57 ms instead of 40 ms at 200 M cases, K = 50): opt-in for experiments
+    const bool half = E->K <= 128 && getenv("SVBFM_PREDICT2_HALFWARP");
+    const int per = half ? 16 : 32;
+    const int ns = E->K <= per ? 1 : (E->K <= 2 * per ? 2 : (E->K <= 4 * per ? 4 : 8));
 #define CALL_P2(NS)                                                                                  \
     do {                                                                                             \
-        if (S.all_ones) k_predict2<MC, true, NS><<<grid, 256, 0, st>>>(a);                           \
-        else k_predict2<MC, false, NS><<<grid, 256, 0, st>>>(a);                                     \
+        if (half) {                                                                                  \
+            if (S.all_ones) k_predict2<MC, true, NS, 16><<<grid, 256, 0, st>>>(a);                   \
+            else k_predict2<MC, false, NS, 16><<<grid, 256, 0, st>>>(a);                             \
+        } else {                                                                                     \
+            if (S.all_ones) k_predict2<MC, true, NS, 32><<<grid, 256, 0, st>>>(a);                   \
+            else k_predict2<MC, false, NS, 32><<<grid, 256, 0, st>>>(a);                             \
+        }                                                                                            \
     } while (0)
     if (ns == 1) CALL_P2(1); else if (ns == 2) CALL_P2(2); else if (ns == 4) CALL_P2(4); else CALL_P2(8);
 #undef CALL_P2

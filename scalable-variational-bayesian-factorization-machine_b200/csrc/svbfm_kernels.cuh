@@ -1106,9 +1106,12 @@ struct Predict2Args {
     double* partial;          // [warps] sum T (vb) / sum of squared clamped errors (mcmc)
 };
 
-template <bool MCMC, bool ONES, int NS>
+// G = lanes per case: 32 (one case per warp step) or 16 (two cases per warp step, one per half-warp: the fixed cost of a
+// step -- shuffles of the case's columns, reduction, bookkeeping -- is shared by two cases)
+template <bool MCMC, bool ONES, int NS, int G>
 __global__ void __launch_bounds__(256) k_predict2(Predict2Args a) {
-    const uint32_t lane = threadIdx.x & 31;
+    static_assert(G == 32 || G == 16, "lanes per case");
+    const uint32_t lane = threadIdx.x & 31, gl = lane & (G - 1), gbase = lane & ~(uint32_t)(G - 1);
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = gridDim.x * (blockDim.x >> 5);
     const uint32_t blocks = (a.n + 31) / 32;                       // blocks of 32 consecutive cases, dealt out contiguously
     const uint32_t b0 = (uint32_t)((uint64_t)blocks * w / nw), b1 = (uint32_t)((uint64_t)blocks * (w + 1) / nw);
@@ -1132,15 +1135,16 @@ __global__ void __launch_bounds__(256) k_predict2(Predict2Args a) {
             tw = A.y * xv.x * xv.x + B.y * xv.y * xv.y;                     // vb.h:298
         }
         double res = 0.0;
-        const uint32_t cnt = (a.n - b * 32 < 32u) ? a.n - b * 32 : 32u;
-        for (uint32_t k = 0; k < cnt; k++) {
-            const uint32_t u = __shfl_sync(0xffffffffu, c.x, k), j = __shfl_sync(0xffffffffu, c.y, k);
+        for (uint32_t k = 0; k < (uint32_t)G; k++) {
+            const uint32_t kk = gbase + k;                                  // the case this group works on: held by lane kk
+            const bool valid = b * 32 + kk < a.n;
+            const uint32_t u = __shfl_sync(0xffffffffu, c.x, kk), j = __shfl_sync(0xffffffffu, c.y, kk);
             float xu = 1.0f, xj = 1.0f;
-            if constexpr (!ONES) { xu = __shfl_sync(0xffffffffu, xv.x, k); xj = __shfl_sync(0xffffffffu, xv.y, k); }
-            if (u != u_prev) {
+            if constexpr (!ONES) { xu = __shfl_sync(0xffffffffu, xv.x, kk); xj = __shfl_sync(0xffffffffu, xv.y, kk); }
+            if (valid && u != u_prev) {
 #pragma unroll
                 for (int s = 0; s < NS; s++) {
-                    int f = (int)lane + 32 * s;
+                    int f = (int)gl + G * s;
                     Pu[s] = f < a.K ? __ldg(&a.pvT[(size_t)u * a.K + f]) : make_double2(0.0, 0.0);
                 }
                 u_prev = u;
@@ -1148,8 +1152,8 @@ __global__ void __launch_bounds__(256) k_predict2(Predict2Args a) {
             double yv = 0.0, tv = 0.0;
 #pragma unroll
             for (int s = 0; s < NS; s++) {
-                int f = (int)lane + 32 * s;
-                double2 Pj = f < a.K ? __ldg(&a.pvT[(size_t)j * a.K + f]) : make_double2(0.0, 0.0);
+                int f = (int)gl + G * s;
+                double2 Pj = (valid && f < a.K) ? __ldg(&a.pvT[(size_t)j * a.K + f]) : make_double2(0.0, 0.0);
                 double mu_u = Pu[s].x * xu, mu_j = Pj.x * xj;
                 double sm = mu_u + mu_j;                                    // vb.h:115
                 double q = mu_u * mu_u + mu_j * mu_j;                       // vb.h:159 / :241
@@ -1162,9 +1166,12 @@ __global__ void __launch_bounds__(256) k_predict2(Predict2Args a) {
                           - (mu_j * mu_j * xj2 * Pj.y + 0.5 * xj2 * xj2 * Pj.y * Pj.y);
                 }
             }
-            yv = warp_sum(yv);
-            if constexpr (!MCMC) tv = warp_sum(tv);
-            if (lane == k) {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {                           // sum over the lanes of the group
+                yv += __shfl_xor_sync(0xffffffffu, yv, o);
+                if constexpr (!MCMC) tv += __shfl_xor_sync(0xffffffffu, tv, o);
+            }
+            if (valid && gl == k) {                                         // lane kk keeps the result of its own case
                 double yhat = yv;
                 if (a.k1) yhat += lin;
                 if (a.k0) yhat += w0;                                       // vb.h:196-199
