@@ -2,7 +2,8 @@
 //
 // Device layout (DESIGN.md "Data layout in HBM"):
 //   * residuals e_i: fp64 SoA, one per train case, in DEVICE case order (cases are re-ordered so that the
-//     first field run streams; perm[] maps device order -> caller order).
+//     first field run streams; perm[] maps device order -> caller order). Two complete fields: a second copy e2 in
+//     the entry order of the second field, kept bit-identical by the stream schedule (no residual gathers at all).
 //   * design matrix twice: CSC per column (colptr u64, case id u32, x f32) for the column sweeps and CSR per
 //     case (rowptr u64 or implicit i*F, feature id u32, x f32) for "the other fields of this case".
 //     x arrays are elided when every x == 1.0f (one-hot data).

@@ -1,5 +1,10 @@
 // csrc/svbfm_kernels.cuh -- hand-written sm_100a kernels of the VB / MCMC coordinate sweep.
 //
+// Two schedules:
+//   * two complete one-hot fields (user x item data, the headline shape): the TWO-COPY STREAM schedule, k_stream below:
+//     one streaming pass per (step, field) over that field's own copy of the residuals + k_finalize.
+//   * anything else (ragged / multi-hot rows, more fields, sharded vb_online): the general per-run schedule:
+//
 // One FIELD RUN (consecutive, case-disjoint columns) of one factor is swept by
 //     k_sweep_reduce   warp per tile (<= tile_entries CSC entries of one column): per-entry terms -> warp
 //                      shuffle reduction -> one partial {A,B,C1,C2} per tile          (gather e_i, other-field params)
