@@ -88,6 +88,21 @@ def main():
         dict(name="g2_mcmc_112_meta", data="g2", method="mcmc", dim="1,1,2", iters=6, seed=9, meta=True),
         dict(name="g3_vbo_112", data="g3", method="vb_online", dim="1,1,2", iters=3, seed=3, extra=["-batch", "4"]),
     ]
+    # second set, consumed by the CPU oracle test only (tests/test_oracle_golden.py): longer runs and more switch combinations
+    extra_cases = [
+        dict(name="g1_vb_118_100it", data="g1", method="vb", dim="1,1,8", iters=100, seed=42),        # BASELINE config 1: -dim '1,1,8' -iter 100
+        dict(name="g1_mcmc_013", data="g1", method="mcmc", dim="0,1,3", iters=8, seed=11),
+        dict(name="g1_als_114_noreg", data="g1", method="als", dim="1,1,4", iters=8, seed=13),
+        dict(name="g1_vbo_012_b7", data="g1", method="vb_online", dim="0,1,2", iters=5, seed=17, extra=["-batch", "7"]),
+        dict(name="g2_vb_101_meta", data="g2", method="vb", dim="1,0,1", iters=8, seed=19, meta=True),
+        dict(name="g3_vb_114", data="g3", method="vb", dim="1,1,4", iters=12, seed=23),
+    ]
+    for out_name, case_list in (("golden.json", cases), ("golden_extra.json", extra_cases)):
+        run_cases(case_list, out_name)
+    write_formats()
+
+
+def run_cases(cases, out_name):
     golden = {"cases": []}
     for c in cases:
         with tempfile.TemporaryDirectory() as td:
@@ -109,6 +124,12 @@ def main():
             assert len(rec["test_rmse"]) == c["iters"], (c["name"], rec["test_rmse"], out[-2000:])
             golden["cases"].append(rec)
             print(c["name"], rec["test_rmse"][-1], rec["neg_free_energy"][-1:] )
+    with open(os.path.join(HERE, out_name), "w") as f:
+        json.dump(golden, f, indent=1)
+    print("wrote", os.path.join(HERE, out_name))
+
+
+def write_formats():
     # formats: reference convert / transpose outputs for both data sets (committed bytes)
     for d in ("g1", "g2"):
         with tempfile.TemporaryDirectory() as td:
@@ -121,9 +142,6 @@ def main():
                 shutil.copy(os.path.join(td, f"a.{ext}"), os.path.join(HERE, f"{d}_train.{ext}"))
     # RNG known answers: first draws of the reference's generators after srand(42), via its own binary is not
     # possible (no CLI for it), so they are pinned indirectly by the vb/mcmc runs above (initial state).
-    with open(os.path.join(HERE, "golden.json"), "w") as f:
-        json.dump(golden, f, indent=1)
-    print("wrote", os.path.join(HERE, "golden.json"))
 
 
 if __name__ == "__main__":

@@ -13,6 +13,9 @@ import oracle_binding as ob
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLD = json.load(open(os.path.join(G, "golden.json")))["cases"]
+# second set, CPU only: 100 iterations of the BASELINE config 1 switches (-dim '1,1,8'), mcmc without w0, als without -regular,
+# vb_online with k0 = 0 and 7 batches, vb with groups and K = 1, vb on the ragged set
+GOLD = GOLD + json.load(open(os.path.join(G, "golden_extra.json")))["cases"]
 TOL = 1e-5
 
 
@@ -31,7 +34,7 @@ def load_case(c):
         kw["reg"] = [float(x) for x in extra[extra.index("-regular") + 1].split(",")]
     if c.get("meta"):
         kw["groups"] = np.loadtxt(os.path.join(G, "g2_meta.txt"), dtype=np.uint32)
-    return tr, te, method, k0, k1, K, kw
+    return tr, te, method, int(k0 != 0), int(k1 != 0), K, kw
 
 
 @pytest.mark.parametrize("c", GOLD, ids=[c["name"] for c in GOLD])
