@@ -125,12 +125,12 @@ int detect_exclusive_blocks(Engine* E) {
     std::vector<uint32_t> v((size_t)E->world * 2, 0u);
     v[(size_t)E->rank * 2] = lo; v[(size_t)E->rank * 2 + 1] = hi;
     uint32_t* d = nullptr;
-    SV_CUDA(E, cudaMallocAsync((void**)&d, v.size() * 4, E->stream));
+    SV_CUDA(E, sv_malloc((void**)&d, v.size() * 4));
     SV_CUDA(E, cudaMemcpyAsync(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice, E->stream));
     if (int rc = allreduce(E, d, v.size(), 3 /*ncclUint32*/, 0 /*ncclSum*/)) return rc;
     SV_CUDA(E, cudaMemcpyAsync(v.data(), d, v.size() * 4, cudaMemcpyDeviceToHost, E->stream));
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
-    cudaFreeAsync(d, E->stream);
+    sv_free(d);
     bool ok = true;
     uint32_t prev_hi = r0.col_begin;
     for (int r = 0; r < E->world; r++) {
@@ -163,7 +163,7 @@ static int exchange_blocks(Engine* E) {
     if (!rows || !maxcnt) return 0;
     const size_t per_rank = (size_t)rows * maxcnt;                         // double2 elements
     if (E->xchg_cap < per_rank * (size_t)(E->world + 1)) {
-        cudaFreeAsync(E->d_xchg, st); E->d_xchg = nullptr;
+        sv_free(E->d_xchg); E->d_xchg = nullptr;
         if (dev_alloc(E, &E->d_xchg, per_rank * (size_t)(E->world + 1))) return SVBFM_ERR_OOM;
         E->xchg_cap = per_rank * (size_t)(E->world + 1);
     }
@@ -577,7 +577,7 @@ static int mcmc_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
 
 static int ensure_stats(Engine* E, uint32_t n) {
     if (E->stats_cap >= n) return 0;
-    cudaFreeAsync(E->d_stats, E->stream); E->d_stats = nullptr;
+    sv_free(E->d_stats); E->d_stats = nullptr;
     if (dev_alloc(E, &E->d_stats, n)) return SVBFM_ERR_OOM;
     E->stats_cap = n;
     return 0;
@@ -710,7 +710,7 @@ void svbfm_destroy(svbfm_t* h) {
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
                     E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
-    for (void* p : ptrs) cudaFreeAsync(p, E->stream);
+    for (void* p : ptrs) sv_free(p);
     cudaStreamSynchronize(E->stream);
     if (E->copy_stream) { cudaStreamSynchronize(E->copy_stream); cudaStreamDestroy(E->copy_stream); }
     if (E->copy_event) cudaEventDestroy(E->copy_event);
@@ -767,7 +767,7 @@ int svbfm_set_groups(svbfm_t* h, const uint32_t* attr_group, uint32_t num_groups
     for (uint32_t g = 0; g < num_groups; g++) E->h_n_per_group[g] = (uint32_t)npg[g];
     SV_CUDA(E, copy_sync(E, E->d_group, attr_group, (size_t)E->D * 4, cudaMemcpyHostToDevice));
     void* old[] = {E->d_n_per_group, E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_grp_sums};
-    for (void* p : old) cudaFreeAsync(p, E->stream);
+    for (void* p : old) sv_free(p);
     E->d_n_per_group = E->d_hyper_w = E->d_hyper_v = E->d_mu_w = E->d_mu_v = E->d_grp_sums = nullptr;
     size_t G = num_groups, K = (size_t)E->K;
     int rc = 0;
@@ -809,7 +809,7 @@ int svbfm_set_csc(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_co
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
     if (is_train) {
         E->n_total = (uint64_t)cnt;
-        cudaFreeAsync(E->d_e, E->stream); cudaFreeAsync(E->d_partial, E->stream); cudaFreeAsync(E->d_e2, E->stream);
+        sv_free(E->d_e); sv_free(E->d_partial); sv_free(E->d_e2);
         E->d_e = nullptr; E->d_partial = nullptr; E->d_e2 = nullptr;
         if (dev_alloc(E, &E->d_e, num_cases)) return SVBFM_ERR_OOM;
         if (E->streams) {
@@ -818,7 +818,7 @@ int svbfm_set_csc(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_co
         } else if (dev_alloc(E, &E->d_partial, (size_t)E->n_tiles * 4)) return SVBFM_ERR_OOM;
     } else {
         E->nt_total = (uint64_t)cnt;
-        cudaFreeAsync(E->d_pred_test, E->stream); cudaFreeAsync(E->d_pred_sum, E->stream); E->d_pred_test = nullptr; E->d_pred_sum = nullptr;
+        sv_free(E->d_pred_test); sv_free(E->d_pred_sum); E->d_pred_test = nullptr; E->d_pred_sum = nullptr;
         if (dev_alloc(E, &E->d_pred_test, num_cases)) return SVBFM_ERR_OOM;
         if (dev_alloc(E, &E->d_pred_sum, num_cases)) return SVBFM_ERR_OOM;
         SV_CUDA(E, cudaMemsetAsync(E->d_pred_sum, 0, std::max<size_t>(num_cases, 1) * 8, E->stream));
@@ -835,8 +835,8 @@ int svbfm_set_state(svbfm_t* h, double w0_mean, double w0_var, const double* w_m
     SV_CUDA(E, cudaSetDevice(E->dev));
     size_t D = E->D, KD = (size_t)E->K * D;
     double *tm = nullptr, *tv = nullptr;
-    SV_CUDA(E, cudaMallocAsync((void**)&tm, std::max<size_t>(KD, D) * 8, E->stream));
-    SV_CUDA(E, cudaMallocAsync((void**)&tv, std::max<size_t>(KD, D) * 8, E->stream));
+    SV_CUDA(E, sv_malloc((void**)&tm, std::max<size_t>(KD, D) * 8));
+    SV_CUDA(E, sv_malloc((void**)&tv, std::max<size_t>(KD, D) * 8));
     cudaStream_t st = E->stream;
     SV_CUDA(E, cudaMemcpyAsync(tm, w_mean, D * 8, cudaMemcpyHostToDevice, st));
     if (w_var) SV_CUDA(E, cudaMemcpyAsync(tv, w_var, D * 8, cudaMemcpyHostToDevice, st));
@@ -848,7 +848,7 @@ int svbfm_set_state(svbfm_t* h, double w0_mean, double w0_var, const double* w_m
         k_pack<<<nblk(KD), 256, 0, st>>>(tm, v_var ? tv : nullptr, KD, E->d_pv);
         SV_CUDA(E, cudaStreamSynchronize(st));
     }
-    cudaFreeAsync(tm, E->stream); cudaFreeAsync(tv, E->stream);
+    sv_free(tm); sv_free(tv);
     Scalars sc;
     SV_CUDA(E, copy_sync(E, &sc, E->d_sc, sizeof(sc), cudaMemcpyDeviceToHost));
     sc.w0_mean = w0_mean; sc.w0_var = w0_var;
@@ -871,8 +871,8 @@ int svbfm_get_state(svbfm_t* h, double* w0_mean, double* w0_var, double* w_mean,
     size_t D = E->D, KD = (size_t)E->K * D;
     cudaStream_t st = E->stream;
     double *tm = nullptr, *tv = nullptr;
-    SV_CUDA(E, cudaMallocAsync((void**)&tm, std::max<size_t>(KD, D) * 8, E->stream));
-    SV_CUDA(E, cudaMallocAsync((void**)&tv, std::max<size_t>(KD, D) * 8, E->stream));
+    SV_CUDA(E, sv_malloc((void**)&tm, std::max<size_t>(KD, D) * 8));
+    SV_CUDA(E, sv_malloc((void**)&tv, std::max<size_t>(KD, D) * 8));
     k_unpack<<<nblk(D), 256, 0, st>>>(E->d_pw, D, tm, tv);
     if (w_mean) SV_CUDA(E, cudaMemcpyAsync(w_mean, tm, D * 8, cudaMemcpyDeviceToHost, st));
     if (w_var) SV_CUDA(E, cudaMemcpyAsync(w_var, tv, D * 8, cudaMemcpyDeviceToHost, st));
@@ -883,7 +883,7 @@ int svbfm_get_state(svbfm_t* h, double* w0_mean, double* w0_var, double* w_mean,
         if (v_var) SV_CUDA(E, cudaMemcpyAsync(v_var, tv, KD * 8, cudaMemcpyDeviceToHost, st));
         SV_CUDA(E, cudaStreamSynchronize(st));
     }
-    cudaFreeAsync(tm, E->stream); cudaFreeAsync(tv, E->stream);
+    sv_free(tm); sv_free(tv);
     Scalars sc;
     SV_CUDA(E, copy_sync(E, &sc, E->d_sc, sizeof(sc), cudaMemcpyDeviceToHost));
     if (w0_mean) *w0_mean = sc.w0_mean;
@@ -1012,13 +1012,13 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
         if (dev_alloc(E, &E->d_cnt_col, E->D)) return SVBFM_ERR_OOM;
     }
     if (E->batch_cap < num_batch) {
-        cudaFreeAsync(E->d_batch_cnt, E->stream); cudaFreeAsync(E->d_batch_n, E->stream); E->d_batch_cnt = nullptr; E->d_batch_n = nullptr;
+        sv_free(E->d_batch_cnt); sv_free(E->d_batch_n); E->d_batch_cnt = nullptr; E->d_batch_n = nullptr;
         if (dev_alloc(E, &E->d_batch_cnt, num_batch)) return SVBFM_ERR_OOM;
         if (dev_alloc(E, &E->d_batch_n, num_batch)) return SVBFM_ERR_OOM;
         E->batch_cap = num_batch;
     }
     uint32_t* d_boc = nullptr;
-    SV_CUDA(E, cudaMallocAsync((void**)&d_boc, std::max<size_t>(S.n, 1) * 4, E->stream));
+    SV_CUDA(E, sv_malloc((void**)&d_boc, std::max<size_t>(S.n, 1) * 4));
     SV_CUDA(E, cudaMemcpyAsync(d_boc, batch_of_case, (size_t)S.n * 4, cudaMemcpyHostToDevice, st));
     SV_CUDA(E, cudaMemsetAsync(E->d_batch_cnt, 0, (size_t)num_batch * 8, st));
     if (S.n) {
@@ -1092,7 +1092,7 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
     DevStats hs;
     cudaError_t ce = cudaMemcpyAsync(&hs, E->d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-    cudaFreeAsync(d_boc, E->stream);
+    sv_free(d_boc);
     if (ce != cudaSuccess) return fail(E, SVBFM_ERR_CUDA, std::string("vb_online epoch: ") + cudaGetErrorString(ce));
     if (out) {
         memset(out, 0, sizeof(*out));
@@ -1131,11 +1131,11 @@ int svbfm_get_residuals(svbfm_t* h, double* e) {
     SV_CUDA(E, cudaSetDevice(E->dev));
     uint32_t n = E->tr.n;
     double* tmp = nullptr;
-    SV_CUDA(E, cudaMallocAsync((void**)&tmp, std::max<size_t>(n, 1) * 8, E->stream));
+    SV_CUDA(E, sv_malloc((void**)&tmp, std::max<size_t>(n, 1) * 8));
     k_unpermute<<<nblk(n), 256, 0, E->stream>>>(E->d_e, E->tr.perm, n, tmp);
     SV_CUDA(E, cudaMemcpyAsync(e, tmp, (size_t)n * 8, cudaMemcpyDeviceToHost, E->stream));
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
-    cudaFreeAsync(tmp, E->stream);
+    sv_free(tmp);
     return check_launch(E, "get_residuals");
 }
 
@@ -1155,13 +1155,13 @@ int svbfm_copies_max_diff(svbfm_t* h, double* max_abs_diff) {
     if (!E->streams || !E->d_e2 || !E->tr.n) return SVBFM_OK;
     SV_CUDA(E, cudaSetDevice(E->dev));
     unsigned long long* d = nullptr;
-    SV_CUDA(E, cudaMallocAsync((void**)&d, 8, E->stream));
+    SV_CUDA(E, sv_malloc((void**)&d, 8));
     SV_CUDA(E, cudaMemsetAsync(d, 0, 8, E->stream));
     const Run& r1 = E->runs[1];
     k_copies_max_diff<<<nblk(E->tr.n), 256, 0, E->stream>>>(E->d_e, E->tr.crow + E->tr.h_colptr[r1.col_begin], E->tr.n, E->d_e2, d);
     unsigned long long bits = 0;
     SV_CUDA(E, copy_sync(E, &bits, d, 8, cudaMemcpyDeviceToHost));
-    cudaFreeAsync(d, E->stream);
+    sv_free(d);
     memcpy(max_abs_diff, &bits, 8);
     return check_launch(E, "copies_max_diff");
 }

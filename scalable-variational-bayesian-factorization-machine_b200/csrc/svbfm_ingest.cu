@@ -32,8 +32,6 @@ struct BlockCache {
 BlockCache& cache() { static BlockCache c; return c; }
 }  // namespace
 
-#undef cudaMallocAsync
-#undef cudaFreeAsync
 cudaError_t sv_malloc(void** p, size_t bytes) {
     bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
     int dev = 0;
@@ -77,8 +75,6 @@ void sv_cache_release() {
     c.free_blocks.clear();
     cudaSetDevice(cur);
 }
-#define cudaMallocAsync(p, bytes, stream) svb::sv_malloc((void**)(p), (bytes))
-#define cudaFreeAsync(p, s) svb::sv_free((void*)(p))
 
 int fail(Engine* E, int code, const std::string& msg) {
     if (E) E->err = msg;
@@ -227,25 +223,25 @@ static int bits_for(uint64_t n) {
 // stable sort of (key, value) pairs by key; returns device arrays (caller frees with cudaFree)
 static int sort_pairs(Engine* E, const uint32_t* keys_in, const uint32_t* vals_in, uint64_t n, uint64_t key_range,
                       uint32_t** keys_out, uint32_t** vals_out) {
-    SV_CUDA(E, cudaMallocAsync((void**)keys_out, std::max<uint64_t>(n, 1) * 4, E->stream));
-    SV_CUDA(E, cudaMallocAsync((void**)vals_out, std::max<uint64_t>(n, 1) * 4, E->stream));
+    SV_CUDA(E, sv_malloc((void**)keys_out, std::max<uint64_t>(n, 1) * 4));
+    SV_CUDA(E, sv_malloc((void**)vals_out, std::max<uint64_t>(n, 1) * 4));
     if (n == 0) return 0;
     size_t tmp_bytes = 0;
     int end_bit = bits_for(key_range);
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, *keys_out, vals_in, *vals_out, (int64_t)n, 0, end_bit, E->stream);
     void* tmp = nullptr;
-    SV_CUDA(E, cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, E->stream));
+    SV_CUDA(E, sv_malloc(&tmp, tmp_bytes ? tmp_bytes : 1));
     cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, *keys_out, vals_in, *vals_out, (int64_t)n, 0, end_bit, E->stream);
     cudaError_t e2 = cudaStreamSynchronize(E->stream);
-    cudaFreeAsync(tmp, E->stream);
+    sv_free(tmp);
     if (e != cudaSuccess || e2 != cudaSuccess) return fail(E, SVBFM_ERR_CUDA, std::string("radix sort: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
     return 0;
 }
 
 void free_split(Engine* E, DevSplit& S) {
     (void)E;
-    cudaFreeAsync(S.colptr, E->stream); cudaFreeAsync(S.crow, E->stream); cudaFreeAsync(S.cval, E->stream); cudaFreeAsync(S.rowptr, E->stream); cudaFreeAsync(S.rcol, E->stream); cudaFreeAsync(S.rval, E->stream);
-    cudaFreeAsync(S.y, E->stream); cudaFreeAsync(S.perm, E->stream); cudaFreeAsync(S.cother, E->stream); cudaFreeAsync(S.cother_val, E->stream);
+    sv_free(S.colptr); sv_free(S.crow); sv_free(S.cval); sv_free(S.rowptr); sv_free(S.rcol); sv_free(S.rval);
+    sv_free(S.y); sv_free(S.perm); sv_free(S.cother); sv_free(S.cother_val);
     S = DevSplit();
 }
 
@@ -279,12 +275,12 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     if (dev_alloc(E, &S.crow, nnz)) return SVBFM_ERR_OOM;
     if (dev_alloc(E, &S.y, n)) return SVBFM_ERR_OOM;
     float* d_x = nullptr;
-    SV_CUDA(E, cudaMallocAsync((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4, E->stream));
+    SV_CUDA(E, sv_malloc((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4));
     // The values and the targets are not needed before the CSR gather / the case re-ordering: they travel on a second stream
     // while the main stream sorts the case ids (pinned host buffers; with pageable memory the copies serialise anyway).
     cudaStream_t cs = E->copy_stream ? E->copy_stream : st;
     uint32_t* d_flags = nullptr;   // [0] any x != 1  [1] case id out of range  [2] duplicate feature in a case  [3] non-uniform  [4] perm not identity
-    SV_CUDA(E, cudaMallocAsync((void**)&d_flags, 8 * 4, E->stream));
+    SV_CUDA(E, sv_malloc((void**)&d_flags, 8 * 4));
     SV_CUDA(E, cudaMemsetAsync(d_flags, 0, 8 * 4, st));
     if (cs != st) {                // everything queued on the main stream so far (earlier users of the recycled blocks, the memset) first
         SV_CUDA(E, cudaEventRecord(E->copy_event, st));
@@ -298,8 +294,8 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     if (nnz) k_check_case_ids<<<nblk(nnz), 256, 0, st>>>(S.crow, nnz, n, d_flags + 1);
     // CSC -> CSR: feature id per entry, stable sort by case id
     uint32_t *d_colof = nullptr, *d_idx = nullptr, *d_skeys = nullptr, *d_sidx = nullptr;
-    SV_CUDA(E, cudaMallocAsync((void**)&d_colof, std::max<uint64_t>(nnz, 1) * 4, E->stream));
-    SV_CUDA(E, cudaMallocAsync((void**)&d_idx, std::max<uint64_t>(nnz, 1) * 4, E->stream));
+    SV_CUDA(E, sv_malloc((void**)&d_colof, std::max<uint64_t>(nnz, 1) * 4));
+    SV_CUDA(E, sv_malloc((void**)&d_idx, std::max<uint64_t>(nnz, 1) * 4));
     if (nnz) {
         k_col_of_entry<<<nblk(nnz), 256, 0, st>>>(S.colptr, ncols, nnz, d_colof);
         k_iota<<<nblk(nnz), 256, 0, st>>>(d_idx, nnz);
@@ -309,28 +305,28 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     SV_CUDA(E, cudaStreamSynchronize(st));
     if (h_flags[1]) {
         cudaStreamSynchronize(cs);
-        cudaFreeAsync(d_x, E->stream); cudaFreeAsync(d_flags, E->stream); cudaFreeAsync(d_colof, E->stream); cudaFreeAsync(d_idx, E->stream);
+        sv_free(d_x); sv_free(d_flags); sv_free(d_colof); sv_free(d_idx);
         return fail(E, SVBFM_ERR_ARG, "set_csc: case id out of range");
     }
     mark("H2D of the case ids + col_of_entry");
     if (int r = sort_pairs(E, S.crow, d_idx, nnz, std::max<uint32_t>(n, 1), &d_skeys, &d_sidx)) { cudaStreamSynchronize(cs); return r; }
     mark("  sort pairs by case");
-    cudaFreeAsync(d_idx, E->stream);
+    sv_free(d_idx);
     uint64_t* d_rowptr = nullptr;
-    SV_CUDA(E, cudaMallocAsync((void**)&d_rowptr, ((size_t)n + 1) * 8, E->stream));
+    SV_CUDA(E, sv_malloc((void**)&d_rowptr, ((size_t)n + 1) * 8));
     k_rowptr_from_sorted<<<nblk((uint64_t)n + 1), 256, 0, st>>>(d_skeys, nnz, n, d_rowptr);
     mark("  rowptr");
-    cudaFreeAsync(d_skeys, E->stream);
+    sv_free(d_skeys);
     uint32_t* d_rcol = nullptr; float* d_rval = nullptr;
-    SV_CUDA(E, cudaMallocAsync((void**)&d_rcol, std::max<uint64_t>(nnz, 1) * 4, E->stream));
+    SV_CUDA(E, sv_malloc((void**)&d_rcol, std::max<uint64_t>(nnz, 1) * 4));
     if (nnz) k_gather_u32<<<nblk(nnz), 256, 0, st>>>(d_colof, d_sidx, nnz, d_rcol);
-    cudaFreeAsync(d_colof, E->stream);
+    sv_free(d_colof);
     mark("sort by case + CSR gather");
 
     // per-case scan: duplicates, uniform length, need[]
     uint32_t* d_need = nullptr;
     if (is_train) {
-        SV_CUDA(E, cudaMallocAsync((void**)&d_need, std::max<uint32_t>(S.ncols_ext, 1) * 4, E->stream));
+        SV_CUDA(E, sv_malloc((void**)&d_need, std::max<uint32_t>(S.ncols_ext, 1) * 4));
         SV_CUDA(E, cudaMemsetAsync(d_need, 0, std::max<uint32_t>(S.ncols_ext, 1) * 4, st));
     }
     if (n) k_scan_rows<<<nblk(n), 256, 0, st>>>(d_rowptr, d_rcol, n, d_need, d_flags + 2);
@@ -339,15 +335,15 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     SV_CUDA(E, cudaStreamSynchronize(cs));
     S.all_ones = (h_flags[0] == 0);
     if (!S.all_ones) {
-        SV_CUDA(E, cudaMallocAsync((void**)&d_rval, std::max<uint64_t>(nnz, 1) * 4, E->stream));
+        SV_CUDA(E, sv_malloc((void**)&d_rval, std::max<uint64_t>(nnz, 1) * 4));
         if (nnz) k_gather_f32<<<nblk(nnz), 256, 0, st>>>(d_x, d_sidx, nnz, d_rval);
     }
-    cudaFreeAsync(d_sidx, E->stream);
+    sv_free(d_sidx);
     mark("  H2D of values and targets (overlapped) + row scan");
     SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
     SV_CUDA(E, cudaStreamSynchronize(st));
     if (h_flags[2]) {
-        cudaFreeAsync(d_x, E->stream); cudaFreeAsync(d_flags, E->stream); cudaFreeAsync(d_rowptr, E->stream); cudaFreeAsync(d_rcol, E->stream); cudaFreeAsync(d_rval, E->stream); cudaFreeAsync(d_need, E->stream);
+        sv_free(d_x); sv_free(d_flags); sv_free(d_rowptr); sv_free(d_rcol); sv_free(d_rval); sv_free(d_need);
         return fail(E, SVBFM_ERR_DATA, "set_csc: a feature id occurs twice in one case; not supported");
     }
     bool uniform = (n > 0) && (h_flags[3] == 0);
@@ -361,7 +357,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         std::vector<uint32_t> need(S.ncols_ext);
         SV_CUDA(E, cudaMemcpyAsync(need.data(), d_need, (size_t)S.ncols_ext * 4, cudaMemcpyDeviceToHost, st));
         SV_CUDA(E, cudaStreamSynchronize(st));
-        cudaFreeAsync(d_need, E->stream);
+        sv_free(d_need);
         E->runs.clear();
         uint32_t run_start = 0;
         for (uint32_t j = 0; j < S.ncols_ext; j++) {
@@ -379,58 +375,58 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         bool reorder = !(E->cfg.flags & SVBFM_FLAG_NO_ROW_REORDER) && !E->runs.empty() && E->runs[0].nnz == n && n > 0 && nnz > 0;
         if (reorder) {
             uint32_t *d_perm = nullptr, *d_inv = nullptr;
-            SV_CUDA(E, cudaMallocAsync((void**)&d_perm, (size_t)n * 4, E->stream));
-            SV_CUDA(E, cudaMallocAsync((void**)&d_inv, (size_t)n * 4, E->stream));
+            SV_CUDA(E, sv_malloc((void**)&d_perm, (size_t)n * 4));
+            SV_CUDA(E, sv_malloc((void**)&d_inv, (size_t)n * 4));
             SV_CUDA(E, cudaMemcpyAsync(d_perm, S.crow + S.h_colptr[E->runs[0].col_begin], (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
             k_invert_perm<<<nblk(n), 256, 0, st>>>(d_perm, n, d_inv, d_flags + 4);
             SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
             SV_CUDA(E, cudaStreamSynchronize(st));
-            cudaFreeAsync(d_inv, E->stream);
+            sv_free(d_inv);
             if (h_flags[4]) {
                 // new CSR = cases gathered in device order
                 uint64_t *d_len = nullptr, *d_newptr = nullptr;
-                SV_CUDA(E, cudaMallocAsync((void**)&d_len, ((size_t)n + 1) * 8, E->stream));
-                SV_CUDA(E, cudaMallocAsync((void**)&d_newptr, ((size_t)n + 1) * 8, E->stream));
+                SV_CUDA(E, sv_malloc((void**)&d_len, ((size_t)n + 1) * 8));
+                SV_CUDA(E, sv_malloc((void**)&d_newptr, ((size_t)n + 1) * 8));
                 k_row_lengths_perm<<<nblk((uint64_t)n + 1), 256, 0, st>>>(d_rowptr, d_perm, n, d_len);
                 size_t tmp_bytes = 0;
                 cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_newptr, (int64_t)n + 1, st);
                 void* tmp = nullptr;
-                SV_CUDA(E, cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, E->stream));
+                SV_CUDA(E, sv_malloc(&tmp, tmp_bytes ? tmp_bytes : 1));
                 cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_len, d_newptr, (int64_t)n + 1, st);
                 uint32_t *d_ncol = nullptr, *d_nrow = nullptr; float* d_nval = nullptr;
-                SV_CUDA(E, cudaMallocAsync((void**)&d_ncol, nnz * 4, E->stream));
-                SV_CUDA(E, cudaMallocAsync((void**)&d_nrow, nnz * 4, E->stream));
-                if (!S.all_ones) SV_CUDA(E, cudaMallocAsync((void**)&d_nval, nnz * 4, E->stream));
+                SV_CUDA(E, sv_malloc((void**)&d_ncol, nnz * 4));
+                SV_CUDA(E, sv_malloc((void**)&d_nrow, nnz * 4));
+                if (!S.all_ones) SV_CUDA(E, sv_malloc((void**)&d_nval, nnz * 4));
                 k_permute_rows<<<nblk(n), 256, 0, st>>>(d_rowptr, d_rcol, d_rval, d_perm, n, d_newptr, d_ncol, d_nval, d_nrow);
                 SV_CUDA(E, cudaStreamSynchronize(st));
-                cudaFreeAsync(tmp, E->stream); cudaFreeAsync(d_len, E->stream);
-                cudaFreeAsync(d_rowptr, E->stream); cudaFreeAsync(d_rcol, E->stream); cudaFreeAsync(d_rval, E->stream);
+                sv_free(tmp); sv_free(d_len);
+                sv_free(d_rowptr); sv_free(d_rcol); sv_free(d_rval);
                 d_rowptr = d_newptr; d_rcol = d_ncol; d_rval = d_nval;
                 // new CSC = stable sort of the new CSR entries by feature id (case ids stay ascending per column)
                 uint32_t *d_eidx = nullptr, *d_k2 = nullptr, *d_v2 = nullptr;
-                SV_CUDA(E, cudaMallocAsync((void**)&d_eidx, nnz * 4, E->stream));
+                SV_CUDA(E, sv_malloc((void**)&d_eidx, nnz * 4));
                 k_iota<<<nblk(nnz), 256, 0, st>>>(d_eidx, nnz);
                 if (int r = sort_pairs(E, d_rcol, d_eidx, nnz, std::max<uint32_t>(ncols, 1), &d_k2, &d_v2)) return r;
-                cudaFreeAsync(d_eidx, E->stream); cudaFreeAsync(d_k2, E->stream);
+                sv_free(d_eidx); sv_free(d_k2);
                 k_gather_u32<<<nblk(nnz), 256, 0, st>>>(d_nrow, d_v2, nnz, S.crow);
                 if (!S.all_ones) {
                     float* d_cv = nullptr;
-                    SV_CUDA(E, cudaMallocAsync((void**)&d_cv, nnz * 4, E->stream));
+                    SV_CUDA(E, sv_malloc((void**)&d_cv, nnz * 4));
                     k_gather_f32<<<nblk(nnz), 256, 0, st>>>(d_rval, d_v2, nnz, d_cv);
                     SV_CUDA(E, cudaStreamSynchronize(st));
-                    cudaFreeAsync(d_x, E->stream); d_x = d_cv;
+                    sv_free(d_x); d_x = d_cv;
                 }
                 SV_CUDA(E, cudaStreamSynchronize(st));
-                cudaFreeAsync(d_v2, E->stream); cudaFreeAsync(d_nrow, E->stream);
+                sv_free(d_v2); sv_free(d_nrow);
                 float* d_y2 = nullptr;
-                SV_CUDA(E, cudaMallocAsync((void**)&d_y2, (size_t)n * 4, E->stream));
+                SV_CUDA(E, sv_malloc((void**)&d_y2, (size_t)n * 4));
                 k_permute_f32<<<nblk(n), 256, 0, st>>>(S.y, d_perm, n, d_y2);
                 SV_CUDA(E, cudaStreamSynchronize(st));
-                cudaFreeAsync(S.y, E->stream); S.y = d_y2;
+                sv_free(S.y); S.y = d_y2;
                 S.perm = d_perm; E->dev_bytes += (size_t)n * 4;
                 E->rows_reordered = true;
             } else {
-                cudaFreeAsync(d_perm, E->stream);     // the caller's order already is run 0's order
+                sv_free(d_perm);     // the caller's order already is run 0's order
             }
             E->run0_sequential = true;
         }
@@ -450,13 +446,13 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         }
     }
     mark("case re-ordering + CSC rebuild");
-    cudaFreeAsync(d_flags, E->stream);
+    sv_free(d_flags);
     // keep
     S.rcol = d_rcol; E->dev_bytes += nnz * 4;
     S.rval = d_rval; if (d_rval) E->dev_bytes += nnz * 4;
-    if (S.all_ones) { cudaFreeAsync(d_x, E->stream); S.cval = nullptr; } else { S.cval = d_x; E->dev_bytes += nnz * 4; }
+    if (S.all_ones) { sv_free(d_x); S.cval = nullptr; } else { S.cval = d_x; E->dev_bytes += nnz * 4; }
     S.uniformF = F;
-    if (F > 0) { cudaFreeAsync(d_rowptr, E->stream); S.rowptr = nullptr; } else { S.rowptr = d_rowptr; E->dev_bytes += ((size_t)n + 1) * 8; }
+    if (F > 0) { sv_free(d_rowptr); S.rowptr = nullptr; } else { S.rowptr = d_rowptr; E->dev_bytes += ((size_t)n + 1) * 8; }
 
     if (is_train && F == 2 && nnz) {
         if (dev_alloc(E, &S.cother, nnz)) return SVBFM_ERR_OOM;
@@ -469,7 +465,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         // ---- stream schedule: implicit tiles of 2^ts_shift entries per run; only their first column and the list of the
         // columns that span many tiles are materialised (kernels.cuh k_stream / k_combine_span)
         const uint64_t TS = 1ull << E->ts_shift;
-        cudaFreeAsync(E->d_stile_col0, st); cudaFreeAsync(E->d_span_heavy, st);
+        sv_free(E->d_stile_col0); sv_free(E->d_span_heavy);
         E->d_stile_col0 = nullptr; E->d_span_heavy = nullptr;
         std::vector<uint32_t> heavy;
         for (int ri = 0; ri < 2; ri++) {
@@ -517,15 +513,15 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         std::vector<uint64_t> cuts;   // [cut_cols][NB+1] absolute entry positions
         if (!cut_cols.empty()) {
             uint32_t* d_cc = nullptr; uint64_t* d_cuts = nullptr;
-            SV_CUDA(E, cudaMallocAsync((void**)&d_cc, cut_cols.size() * 4, E->stream));
-            SV_CUDA(E, cudaMallocAsync((void**)&d_cuts, cut_cols.size() * (size_t)(NB + 1) * 8, E->stream));
+            SV_CUDA(E, sv_malloc((void**)&d_cc, cut_cols.size() * 4));
+            SV_CUDA(E, sv_malloc((void**)&d_cuts, cut_cols.size() * (size_t)(NB + 1) * 8));
             SV_CUDA(E, cudaMemcpyAsync(d_cc, cut_cols.data(), cut_cols.size() * 4, cudaMemcpyHostToDevice, st));
             dim3 grid((unsigned)cut_cols.size(), (NB + 1 + 63) / 64);
             k_block_cuts<<<grid, 64, 0, st>>>(d_cc, S.colptr, S.crow, block_cases, NB, d_cuts);
             cuts.resize(cut_cols.size() * (size_t)(NB + 1));
             SV_CUDA(E, cudaMemcpyAsync(cuts.data(), d_cuts, cuts.size() * 8, cudaMemcpyDeviceToHost, st));
             SV_CUDA(E, cudaStreamSynchronize(st));
-            cudaFreeAsync(d_cc, E->stream); cudaFreeAsync(d_cuts, E->stream);
+            sv_free(d_cc); sv_free(d_cuts);
         }
         size_t cc = 0;
         for (auto& r : E->runs) {
@@ -561,8 +557,8 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         col_tile0[S.ncols_ext] = (uint32_t)tile_col.size();
         E->n_tiles = (uint32_t)tile_col.size();
         E->n_heavy = (uint32_t)heavy.size();
-        cudaFreeAsync(E->d_tile_col, E->stream); cudaFreeAsync(E->d_tile_begin, E->stream); cudaFreeAsync(E->d_col_tile0, E->stream); cudaFreeAsync(E->d_heavy_cols, E->stream);
-        cudaFreeAsync(E->d_tile_len, E->stream); cudaFreeAsync(E->d_exec_order, E->stream);
+        sv_free(E->d_tile_col); sv_free(E->d_tile_begin); sv_free(E->d_col_tile0); sv_free(E->d_heavy_cols);
+        sv_free(E->d_tile_len); sv_free(E->d_exec_order);
         E->d_tile_col = nullptr; E->d_tile_begin = nullptr; E->d_col_tile0 = nullptr; E->d_heavy_cols = nullptr;
         E->d_tile_len = nullptr; E->d_exec_order = nullptr;
         if (dev_alloc(E, &E->d_tile_col, tile_col.size())) return SVBFM_ERR_OOM;
@@ -627,39 +623,39 @@ int vbo_stream_prepare(Engine* E, uint32_t num_batch) {
     for (uint32_t b = 0; b < num_batch; b++)
         max_tiles = std::max<uint32_t>(max_tiles, (uint32_t)(((E->vbo_off[b + 1] - E->vbo_off[b]) >> E->vbo_ts_shift) + 1));
     if (max_tiles > E->vbo_max_tiles) {
-        cudaFreeAsync(E->d_vbo_tile_col0, st); cudaFreeAsync(E->d_vbo_partial, st);
+        sv_free(E->d_vbo_tile_col0); sv_free(E->d_vbo_partial);
         E->d_vbo_tile_col0 = nullptr; E->d_vbo_partial = nullptr;
         if (dev_alloc(E, &E->d_vbo_tile_col0, (size_t)max_tiles * 2)) return SVBFM_ERR_OOM;
         if (dev_alloc(E, &E->d_vbo_partial, (size_t)max_tiles * 2 * 8)) return SVBFM_ERR_OOM;
         E->vbo_max_tiles = max_tiles;
     }
     uint32_t *d_keys = nullptr, *d_vals = nullptr, *d_skeys = nullptr;
-    SV_CUDA(E, cudaMallocAsync((void**)&d_keys, std::max<size_t>(n, 1) * 4, st));
-    SV_CUDA(E, cudaMallocAsync((void**)&d_vals, std::max<size_t>(n, 1) * 4, st));
+    SV_CUDA(E, sv_malloc((void**)&d_keys, std::max<size_t>(n, 1) * 4));
+    SV_CUDA(E, sv_malloc((void**)&d_vals, std::max<size_t>(n, 1) * 4));
     for (int ri = 0; ri < 2; ri++) {
         const Run& r = E->runs[ri];
         const uint32_t nc = r.col_end - r.col_begin;
         const size_t ncp = (size_t)num_batch * nc + 1;
-        cudaFreeAsync(E->d_vbo_idx[ri], st); cudaFreeAsync(E->d_vbo_colptr[ri], st);
+        sv_free(E->d_vbo_idx[ri]); sv_free(E->d_vbo_colptr[ri]);
         E->d_vbo_idx[ri] = nullptr; E->d_vbo_colptr[ri] = nullptr;
         if (dev_alloc(E, &E->d_vbo_colptr[ri], ncp)) return SVBFM_ERR_OOM;
         SV_CUDA(E, cudaMemsetAsync(E->d_vbo_colptr[ri], 0, ncp * 8, st));
         if (n) {
             k_vbo_keys<<<nblk(n), 256, 0, st>>>(E->d_rbatch, ri ? S.crow + S.h_colptr[r.col_begin] : nullptr, n, d_keys, d_vals);
             if (int rc = sort_pairs(E, d_keys, d_vals, n, std::max<uint32_t>(num_batch, 1), &d_skeys, &E->d_vbo_idx[ri])) return rc;
-            cudaFreeAsync(d_skeys, st);
+            sv_free(d_skeys);
             E->dev_bytes += (size_t)n * 4;
             k_vbo_hist<<<nblk(n), 256, 0, st>>>(E->d_rbatch, S.rcol, n, ri, r.col_begin, nc, E->d_vbo_colptr[ri]);
         } else if (dev_alloc(E, &E->d_vbo_idx[ri], 1)) return SVBFM_ERR_OOM;
         size_t tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, E->d_vbo_colptr[ri], E->d_vbo_colptr[ri], (int64_t)ncp, st);
         void* tmp = nullptr;
-        SV_CUDA(E, cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, st));
+        SV_CUDA(E, sv_malloc(&tmp, tmp_bytes ? tmp_bytes : 1));
         cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, E->d_vbo_colptr[ri], E->d_vbo_colptr[ri], (int64_t)ncp, st);
-        cudaFreeAsync(tmp, st);
+        sv_free(tmp);
         if (e != cudaSuccess) return fail(E, SVBFM_ERR_CUDA, std::string("vb_online scan: ") + cudaGetErrorString(e));
     }
-    cudaFreeAsync(d_keys, st); cudaFreeAsync(d_vals, st);
+    sv_free(d_keys); sv_free(d_vals);
     SV_CUDA(E, cudaGetLastError());
     return 0;
 }

@@ -30,8 +30,6 @@ cudaError_t sv_malloc(void** p, size_t bytes);
 cudaError_t sv_free(void* p);          // null-tolerant
 void sv_cache_release();               // hand every cached block back to the driver
 }
-#define cudaMallocAsync(p, bytes, stream) svb::sv_malloc((void**)(p), (bytes))
-#define cudaFreeAsync(p, s) svb::sv_free((void*)(p))
 
 namespace svb {
 
@@ -226,7 +224,7 @@ int fail(Engine* E, int code, const std::string& msg);
 template <typename T>
 int dev_alloc(Engine* E, T** p, size_t count) {
     if (count == 0) count = 1;
-    cudaError_t e = cudaMallocAsync((void**)p, count * sizeof(T), E->stream);
+    cudaError_t e = sv_malloc((void**)p, count * sizeof(T));
     if (e != cudaSuccess) return fail(E, SVBFM_ERR_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     E->dev_bytes += count * sizeof(T);
     return 0;
