@@ -182,9 +182,9 @@ def test_vb_block_cut_tiles(built, monkeypatch):
     run_vb(tr, te, K=2, iters=3, tile_entries=32)
 
 
-def test_fused_equals_unfused_schedule(built, monkeypatch):
-    """The fused two-field schedule and the general per-run schedule are the same algorithm: identical statistics
-    to rounding, on one-hot data and on two-field data with real values."""
+def test_stream_equals_general_schedule(built, monkeypatch):
+    """The two-copy stream schedule (info: fused_schedule = 1) and the general per-run schedule are the same algorithm:
+    identical statistics to rounding, on one-hot data and on two-field data with real values."""
     for values in (False, True):
         tr, te = two_field(15000, 1500, 250, 180, seed=71, values=values)
         out = []
