@@ -406,7 +406,9 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     sweep_per_step = sweep_ms / a.steps
-    achieved = (N_global / world) * K * ALGO_BYTES_PER_RATING_K / (sweep_per_step * 1e-3) / 1e9     # per GPU
+    # 216 B per rating*k for the cached-state VB algorithm (vb, vb_online), 104 B for MCMC (e and q only)
+    algo_bytes = 104.0 if a.method == "mcmc" else ALGO_BYTES_PER_RATING_K
+    achieved = (N_global / world) * K * algo_bytes / (sweep_per_step * 1e-3) / 1e9     # per GPU
     n_local = hi - lo
     fused = bool(info0.get("fused_schedule"))
     # own algorithmic bytes per rating*k: stream schedule = per field pass (other-column id 4 + e 8 r + 8 w) x 2 fields
@@ -414,6 +416,8 @@ def main():
     # per-class model bytes per entry under SURVEY's 216 B accounting: pass 1 = 8 B CSC entry + 40 B state, pass 2 = 40 B state write,
     # one stream pass = one field's share of the 216 B (88 B field sweep + half of the 40 B q-rebuild)
     model_bytes = {"reduce_v": 48.0, "apply_v": 40.0, "stream_v_field0": 108.0, "stream_v_field1": 108.0}
+    if a.method == "mcmc":      # 48F + 8 = 104 B: pass 1 = 8 B entry + 16 B {e, q}, pass 2 = 16 B, a field pass = half of the 104 B
+        model_bytes = {"reduce_v": 24.0, "apply_v": 16.0, "stream_v_field0": 52.0, "stream_v_field1": 52.0}
     kname = {"reduce_v": "k_sweep_reduce<VB_V> (pass 1)", "apply_v": "k_row_apply<VB_V> (pass 2)",
              "stream_v_field0": "k_stream<V> over field 0 (pending updates + pass 1, residual copy in case order)",
              "stream_v_field1": "k_stream<V> over field 1 (pending updates + pass 1, residual copy in field-1 entry order)"}
@@ -443,7 +447,7 @@ def main():
                 "own_algorithmic_bytes_per_launch": own_launch,
                 "own_achieved": own_launch / (dk_avg * 1e-3) / 1e9 if dk["launches"] else None,
                 "own_frac": own_launch / (dk_avg * 1e-3) / 1e9 / peak if dk["launches"] else None,
-                "sweep": {"achieved_216B": achieved, "frac_216B": achieved / peak, "own_bytes_per_rating_k": own_bytes,
+                "sweep": {"survey_bytes_per_rating_k": algo_bytes, "achieved_216B": achieved, "frac_216B": achieved / peak, "own_bytes_per_rating_k": own_bytes,
                           "own_achieved": (N_global / world) * K * own_bytes / (sweep_per_step * 1e-3) / 1e9,
                           "own_frac": (N_global / world) * K * own_bytes / (sweep_per_step * 1e-3) / 1e9 / peak},
                 "kernel_classes_ms": {k: v["ms"] for k, v in prof.items()}}
