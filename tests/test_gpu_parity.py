@@ -9,7 +9,7 @@ import pytest
 
 import oracle_binding as ob
 import svbfm_b200 as sv
-from helpers import make_learner, ragged, rel, to_csc, two_field
+from helpers import make_learner, ragged, rel, synth, to_csc, two_field
 
 pytestmark = pytest.mark.gpu
 
@@ -223,6 +223,42 @@ def test_stream_schedule_small_tiles(built, tile_entries):
         assert info["fused_schedule"] == 1 and info["num_tiles"] >= 2 * (30000 // tile_entries)
         assert L.engine.copies_max_diff() == 0.0
         L.engine.close()
+
+
+def test_stream_schedule_id_gaps(built):
+    """Long stretches of never-used feature ids inside both fields (more than a 32-column window, so the column walk of
+    k_stream has to skip whole windows by binary search), for vb, als and vb_online, with small tiles."""
+    r = np.random.default_rng(5)
+    U, I, N, Nt = 400, 300, 8000, 800
+    users = np.concatenate([np.arange(0, 30), np.arange(130, 160), np.arange(395, 400)])       # gaps of 100 and 235 ids
+    items = np.concatenate([np.arange(2, 12), np.arange(120, 170), np.arange(290, 300)])       # gaps of 108 and 120 ids
+
+    def make(n, seed):
+        rr = np.random.default_rng(seed)
+        u, i = rr.choice(users, n), rr.choice(items, n)
+        y = np.clip(np.round(3.5 + 0.01 * (u % 7) - 0.02 * (i % 5) + rr.normal(0, 0.8, n)), 1, 5).astype(np.float32)
+        return ob.Csr(*synth.to_csr(u.astype(np.uint32), i.astype(np.uint32), y, U))
+    tr, te = make(N, 1), make(Nt, 2)
+    for te_ in (32, 256):
+        L, _ = run_vb(tr, te, K=3, iters=3, tile_entries=te_)
+        assert L.engine.info()["fused_schedule"] == 1 and L.engine.copies_max_diff() == 0.0
+        L.engine.close()
+    orc = ob.Oracle("mcmc", tr, te, K=2, seed=42, do_sample=False, do_multilevel=False)
+    L = make_learner("mcmc", tr, te, 2, num_iter=3, do_sample=False, do_multilevel=False, tile_entries=64)
+    L.fm.reg0, L.fm.regw, L.fm.regv = 0.0, 0.0, 0.0
+    for s in L.learn(to_csc(tr), to_csc(te)):
+        o = orc.iterate()
+        assert rel(s.test_rmse, o.test_rmse) < 1e-7 and rel(s.train_stat, o.train_stat) < 1e-7
+    L.engine.close()
+    want = []
+    orc = ob.Oracle("vb_online", tr, te, K=2, seed=42, num_batch=6)
+    for _ in range(3):
+        s = orc.iterate()
+        want.append((s.test_rmse, s.free_energy))
+    L = make_learner("vb_online", tr, te, 2, num_iter=3, num_batch=6, tile_entries=32)
+    for it, s in enumerate(L.learn(to_csc(tr), to_csc(te))):
+        assert rel(s.test_rmse, want[it][0]) < VB_TOL and rel(s.free_energy, want[it][1]) < VB_TOL
+    assert L.engine.info()["fused_schedule"] == 1
 
 
 def test_stream_schedule_sorted_input(built):
