@@ -1,0 +1,239 @@
+// tests/emu/emu_runtime.cpp -- TEST INFRASTRUCTURE (see include/cuda_runtime.h).
+// Fiber scheduler of the lockstep emulator + the handful of runtime calls the engine makes. One OS thread; the CUDA
+// threads of a CTA are fibers that run until they return or reach a warp / block primitive; CTAs run one at a time.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <vector>
+
+uint3 threadIdx, blockIdx;
+dim3 blockDim, gridDim;
+
+namespace {
+
+#if defined(__x86_64__)
+// void emu_switch(void** save_sp, void* load_sp): callee-saved registers on the stack, swap stack pointers
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+#else
+#error "the emulator's context switch is written for x86-64"
+#endif
+
+constexpr size_t STACK_BYTES = 256 * 1024;
+
+struct Warp {
+    uint64_t slot[2][32];
+    unsigned arrived = 0, exited = 0, gen = 0;
+};
+
+struct Fiber {
+    void* sp = nullptr;
+    char* stack = nullptr;
+    bool done = false;
+    uint3 tid;
+    int lane = 0, warp = 0;
+};
+
+struct Block {
+    std::vector<Fiber> fibers;
+    std::vector<Warp> warps;
+    const std::function<void()>* body = nullptr;
+    void* sched_sp = nullptr;
+    int cur = -1;
+    unsigned n = 0, exited = 0, bar_arrived = 0, bar_gen = 0;
+} B;
+
+std::vector<char*> g_stacks;     // reused between launches
+
+void yield_to_scheduler() {
+    Fiber& f = B.fibers[B.cur];
+    emu_switch(&f.sp, B.sched_sp);
+}
+
+void release_warp_if_complete(Warp& w, unsigned mask) {
+    if (w.arrived && ((w.arrived | w.exited) & mask) == mask) { w.arrived = 0; w.gen++; }
+}
+void release_block_if_complete() {
+    if (B.bar_arrived && B.bar_arrived + B.exited == B.n) { B.bar_arrived = 0; B.bar_gen++; }
+}
+
+void fiber_main() {
+    (*B.body)();
+    Fiber& f = B.fibers[B.cur];
+    f.done = true;
+    B.exited++;
+    Warp& w = B.warps[f.warp];
+    w.exited |= 1u << f.lane;
+    release_warp_if_complete(w, 0xffffffffu);    // every mask in csrc is the full mask
+    release_block_if_complete();
+    emu_switch(&f.sp, B.sched_sp);
+    abort();   // never resumed
+}
+
+void run_block() {
+    const unsigned n = blockDim.x * blockDim.y * blockDim.z;
+    B.n = n; B.exited = 0; B.bar_arrived = 0; B.bar_gen = 0;
+    B.fibers.assign(n, Fiber());
+    B.warps.assign((n + 31) / 32, Warp());
+    while (g_stacks.size() < n) g_stacks.push_back((char*)aligned_alloc(64, STACK_BYTES));
+    for (unsigned t = 0; t < n; t++) {
+        Fiber& f = B.fibers[t];
+        f.tid.x = t % blockDim.x; f.tid.y = (t / blockDim.x) % blockDim.y; f.tid.z = t / (blockDim.x * blockDim.y);
+        f.lane = t & 31; f.warp = t >> 5;
+        f.stack = g_stacks[t];
+        // initial frame: six callee-saved registers, then the "return address" fiber_main; on entry rsp % 16 == 8
+        uintptr_t top = ((uintptr_t)f.stack + STACK_BYTES) & ~(uintptr_t)15;
+        uint64_t* sp = (uint64_t*)(top - 8);      // slot a caller's `call` would have used
+        *--sp = (uint64_t)(uintptr_t)&fiber_main; // popped by `ret`
+        for (int r = 0; r < 6; r++) *--sp = 0;
+        f.sp = sp;
+    }
+    // lanes a partial last warp does not have count as exited
+    if (n & 31) B.warps.back().exited = ~0u << (n & 31);
+    unsigned live = n;
+    unsigned stuck_rounds = 0;
+    while (live) {
+        unsigned progressed = 0;
+        for (unsigned t = 0; t < n; t++) {
+            Fiber& f = B.fibers[t];
+            if (f.done) continue;
+            B.cur = (int)t;
+            threadIdx = f.tid;
+            const unsigned g0 = B.warps[f.warp].gen, b0 = B.bar_gen;
+            emu_switch(&B.sched_sp, f.sp);
+            if (f.done) { live--; progressed++; }
+            else if (B.warps[f.warp].gen != g0 || B.bar_gen != b0) progressed++;
+            else progressed += 0;
+        }
+        // a full round in which nothing arrived anywhere new cannot happen unless the kernel deadlocks (divergent barrier)
+        if (!progressed) { if (++stuck_rounds > 4) { fprintf(stderr, "[emu] deadlock: a warp or block barrier was not reached by every thread\n"); abort(); } }
+        else stuck_rounds = 0;
+    }
+    B.cur = -1;
+}
+
+}  // namespace
+
+namespace emu {
+
+int lane_id() { return B.fibers[B.cur].lane; }
+
+static void warp_wait(Warp& w, unsigned mask, int lane) {
+    const unsigned gen = w.gen;
+    w.arrived |= 1u << lane;
+    release_warp_if_complete(w, mask);
+    while (w.gen == gen) yield_to_scheduler();
+}
+
+uint64_t warp_exchange(unsigned mask, uint64_t mine, int src_lane) {
+    Fiber& f = B.fibers[B.cur];
+    Warp& w = B.warps[f.warp];
+    const unsigned buf = w.gen & 1;
+    w.slot[buf][f.lane] = mine;
+    warp_wait(w, mask, f.lane);
+    return w.slot[buf][src_lane & 31];
+}
+
+unsigned warp_ballot(unsigned mask, bool pred) {
+    Fiber& f = B.fibers[B.cur];
+    Warp& w = B.warps[f.warp];
+    const unsigned buf = w.gen & 1;
+    const unsigned exited = w.exited;
+    w.slot[buf][f.lane] = pred ? 1 : 0;
+    warp_wait(w, mask, f.lane);
+    unsigned r = 0;
+    for (int l = 0; l < 32; l++)
+        if ((mask >> l & 1) && !(exited >> l & 1) && w.slot[buf][l]) r |= 1u << l;
+    return r;
+}
+
+void block_barrier() {
+    const unsigned gen = B.bar_gen;
+    B.bar_arrived++;
+    release_block_if_complete();
+    while (B.bar_gen == gen) yield_to_scheduler();
+}
+
+void launch(dim3 grid, dim3 block, size_t, cudaStream_t, const std::function<void()>& body) {
+    if (B.cur != -1) { fprintf(stderr, "[emu] nested launch\n"); abort(); }
+    if (grid.x == 0 || grid.y == 0 || grid.z == 0 || block.x * block.y * block.z == 0 || block.x * block.y * block.z > 1024) {
+        fprintf(stderr, "[emu] invalid launch configuration grid (%u,%u,%u) block (%u,%u,%u)\n", grid.x, grid.y, grid.z, block.x, block.y, block.z);
+        abort();     // the real runtime reports cudaErrorInvalidConfiguration: a bug either way
+    }
+    gridDim = grid; blockDim = block;
+    B.body = &body;
+    for (uint32_t z = 0; z < grid.z; z++)
+        for (uint32_t y = 0; y < grid.y; y++)
+            for (uint32_t x = 0; x < grid.x; x++) {
+                blockIdx.x = x; blockIdx.y = y; blockIdx.z = z;
+                run_block();
+            }
+    B.body = nullptr;
+}
+
+}  // namespace emu
+
+// ------------------------------------------------------------------------------------------------ runtime calls
+struct emuStream { int id; };
+struct emuEvent { std::chrono::steady_clock::time_point t; };
+
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : e == cudaErrorMemoryAllocation ? "out of memory" : "invalid value"; }
+cudaError_t cudaGetLastError() { return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
+    memset(p, 0, sizeof(*p));
+    snprintf(p->name, sizeof(p->name), "lockstep CPU emulator of sm_100 (tests/emu)");
+    p->major = 10; p->minor = 0; p->multiProcessorCount = 148; p->totalGlobalMem = (size_t)8 << 30;
+    return cudaSuccess;
+}
+cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+cudaError_t cudaMalloc(void** p, size_t n) {
+    *p = aligned_alloc(256, (n + 255) / 256 * 256 + 256);
+    if (!*p) return cudaErrorMemoryAllocation;
+    memset(*p, 0xcd, n);       // "device memory" starts out as garbage, not zeros
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { if (n) memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = new emuStream{1}; return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new emuStream{1}; return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emuEvent{std::chrono::steady_clock::now()}; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+    return cudaSuccess;
+}
