@@ -235,6 +235,7 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
     fa.seed = E->cfg.seed; fa.do_sample = E->cfg.do_sample;
     fa.span = sp; fa.ab = use_ab ? E->d_ab : nullptr;
     if (rp) { fa.cpack = E->d_cpack; fa.opack = E->d_opack; fa.rec_mode = rp->rec_mode; fa.p_next = rp->p_next; fa.p_prev = rp->p_prev; }
+    fa.rec_slot = E->rec_rank ? E->d_rec_slot : nullptr;
     if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V) {
         fa.nat = IS_V ? E->d_nat_v + (size_t)f * E->D : E->d_nat_w;
         fa.t_cnt = IS_V ? E->d_t_v : E->d_t_w;
@@ -355,7 +356,8 @@ static int sweep_streams(Engine* E) {
     for (int f = 0; f < E->K; f++) steps.push_back(f);
     if (steps.empty()) return 0;
     auto table = [&](int s) -> double2* { return s < 0 ? E->d_pw : E->d_pv + (size_t)s * E->D; };
-    k_pack_init<<<nblk(r1.col_end - r0.col_begin), 256, 0, st>>>(r0.col_begin, r0.col_end, r1.col_begin, r1.col_end, table(steps[0]), E->d_cpack, E->d_opack);
+    k_pack_init<<<nblk(r1.col_end - r0.col_begin), 256, 0, st>>>(r0.col_begin, r0.col_end, r1.col_begin, r1.col_end, table(steps[0]), E->d_cpack, E->d_opack,
+                                                                          E->rec_rank ? E->d_rec_slot : nullptr);
     LAUNCHED(E);
     constexpr int KW = FLAVOR == 1 ? KIND_MC_W : (FLAVOR == 2 ? KIND_VBO_W : KIND_VB_W);
     constexpr int KV = FLAVOR == 1 ? KIND_MC_V : (FLAVOR == 2 ? KIND_VBO_V : KIND_VB_V);
@@ -709,7 +711,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) sv_free(p);
     cudaStreamSynchronize(E->stream);
     if (E->copy_stream) { cudaStreamSynchronize(E->copy_stream); cudaStreamDestroy(E->copy_stream); }
@@ -1202,7 +1204,7 @@ int svbfm_get_info(svbfm_t* h, svbfm_info* out) {
     out->train_nnz = E->tr.nnz;
     out->rows_reordered = E->rows_reordered;
     out->world_size = (uint32_t)E->world;
-    out->fused_schedule = (stream_ok(E) || E->vbo_streams) ? 1u : 0u;
+    out->fused_schedule = ((stream_ok(E) || E->vbo_streams) ? 1u : 0u) | (E->rec_rank ? 2u : 0u);
     out->exclusive_blocks = E->excl0 ? 1u : 0u;
     return SVBFM_OK;
 }

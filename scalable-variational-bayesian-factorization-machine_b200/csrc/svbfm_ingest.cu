@@ -212,6 +212,32 @@ static __global__ void k_block_cuts(const uint32_t* __restrict__ cols, const uin
     cuts[(size_t)c * (NB + 1) + k] = lo;
 }
 
+// ---- SVBFM_REC_RANK (experiment): record slots of the second field's columns by popularity rank
+// key = descending column length, value = column id (sorted by key: rank order)
+static __global__ void k_slot_keys(const uint64_t* __restrict__ colptr, uint32_t c0, uint32_t nc, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nc) return;
+    uint64_t len = colptr[c0 + r + 1] - colptr[c0 + r];
+    keys[r] = 0xffffffffu - (uint32_t)(len > 0xffffffffull ? 0xffffffffull : len);
+    vals[r] = c0 + r;
+}
+static __global__ void k_slot_scatter(const uint32_t* __restrict__ cols_by_rank, uint32_t c0, uint32_t nc, uint32_t* __restrict__ slot) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nc) slot[cols_by_rank[r]] = c0 + r;
+}
+// sort key of the case at position k of `cases`: which = 1 -> slot rank of its second-field column, 0 -> its first-field column
+static __global__ void k_case_keys(const uint32_t* __restrict__ cases, const uint32_t* __restrict__ rcol, const uint32_t* __restrict__ slot, uint32_t base,
+                                   uint32_t n, int which, uint32_t* __restrict__ keys) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint2 c = reinterpret_cast<const uint2*>(rcol)[cases[k]];
+    keys[k] = (which ? slot[c.y] : c.x) - base;
+}
+static __global__ void k_map_slots(uint32_t* __restrict__ oc, uint64_t n, const uint32_t* __restrict__ slot) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) oc[p] = slot[oc[p]];
+}
+
 static inline unsigned nblk(uint64_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t); }
 
 static int bits_for(uint64_t n) {
@@ -373,11 +399,41 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
 
         // ---- case re-ordering: device order = order of the cases inside run 0 (when run 0 holds every case once)
         bool reorder = !(E->cfg.flags & SVBFM_FLAG_NO_ROW_REORDER) && !E->runs.empty() && E->runs[0].nnz == n && n > 0 && nnz > 0;
+        // SVBFM_REC_RANK=1 (experiment, two complete fields only): record slots of the second field by popularity rank
+        sv_free(E->d_rec_slot); E->d_rec_slot = nullptr; E->rec_rank = false;
+        const bool want_rank = reorder && getenv("SVBFM_REC_RANK") && atoi(getenv("SVBFM_REC_RANK")) != 0 && E->runs.size() == 2 && uniform && F == 2 &&
+                               E->runs[1].nnz == n;
+        if (want_rank) {
+            const Run& r1 = E->runs[1];
+            const uint32_t nc1 = r1.col_end - r1.col_begin;
+            uint32_t *d_k = nullptr, *d_v = nullptr, *d_ks = nullptr, *d_vs = nullptr;
+            SV_CUDA(E, sv_malloc((void**)&d_k, (size_t)nc1 * 4));
+            SV_CUDA(E, sv_malloc((void**)&d_v, (size_t)nc1 * 4));
+            if (dev_alloc(E, &E->d_rec_slot, E->D)) return SVBFM_ERR_OOM;
+            k_iota<<<nblk(E->D), 256, 0, st>>>(E->d_rec_slot, E->D);
+            k_slot_keys<<<nblk(nc1), 256, 0, st>>>(S.colptr, r1.col_begin, nc1, d_k, d_v);
+            if (int r = sort_pairs(E, d_k, d_v, nc1, 1ull << 32, &d_ks, &d_vs)) return r;
+            k_slot_scatter<<<nblk(nc1), 256, 0, st>>>(d_vs, r1.col_begin, nc1, E->d_rec_slot);
+            SV_CUDA(E, cudaStreamSynchronize(st));
+            sv_free(d_k); sv_free(d_v); sv_free(d_ks); sv_free(d_vs);
+        }
         if (reorder) {
             uint32_t *d_perm = nullptr, *d_inv = nullptr;
             SV_CUDA(E, sv_malloc((void**)&d_perm, (size_t)n * 4));
             SV_CUDA(E, sv_malloc((void**)&d_inv, (size_t)n * 4));
             SV_CUDA(E, cudaMemcpyAsync(d_perm, S.crow + S.h_colptr[E->runs[0].col_begin], (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+            if (want_rank) {
+                // cases of one first-field column in the rank order of their second-field column: stable sort by rank, then by column
+                const Run &r0 = E->runs[0], &r1 = E->runs[1];
+                for (int which = 1; which >= 0; which--) {
+                    uint32_t *d_k = nullptr, *d_ks = nullptr, *d_vs = nullptr;
+                    SV_CUDA(E, sv_malloc((void**)&d_k, (size_t)n * 4));
+                    k_case_keys<<<nblk(n), 256, 0, st>>>(d_perm, d_rcol, E->d_rec_slot, which ? r1.col_begin : r0.col_begin, n, which, d_k);
+                    if (int r = sort_pairs(E, d_k, d_perm, n, std::max<uint32_t>(which ? r1.col_end - r1.col_begin : r0.col_end - r0.col_begin, 1), &d_ks, &d_vs)) return r;
+                    sv_free(d_k); sv_free(d_ks); sv_free(d_perm);
+                    d_perm = d_vs;
+                }
+            }
             k_invert_perm<<<nblk(n), 256, 0, st>>>(d_perm, n, d_inv, d_flags + 4);
             SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
             SV_CUDA(E, cudaStreamSynchronize(st));
@@ -458,8 +514,14 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         if (dev_alloc(E, &S.cother, nnz)) return SVBFM_ERR_OOM;
         if (!S.all_ones && dev_alloc(E, &S.cother_val, nnz)) return SVBFM_ERR_OOM;
         k_other_of_entry<<<nblk(nnz), 256, 0, st>>>(S.colptr, ncols, nnz, S.crow, S.rcol, S.rval, S.cother, S.cother_val);
+        if (E->d_rec_slot && (E->streams || E->vbo_streams)) {      // the first field's entries gather by record slot
+            const Run& r0 = E->runs[0];
+            k_map_slots<<<nblk(r0.nnz), 256, 0, st>>>(S.cother + S.h_colptr[r0.col_begin], r0.nnz, E->d_rec_slot);
+            E->rec_rank = true;
+        }
         SV_CUDA(E, cudaStreamSynchronize(st));
     }
+    if (is_train && !E->rec_rank) { sv_free(E->d_rec_slot); E->d_rec_slot = nullptr; }
     mark("other-feature arrays");
     if (is_train && E->streams) {
         // ---- stream schedule: implicit tiles of 2^ts_shift entries per run; only their first column and the list of the

@@ -177,6 +177,12 @@ struct Engine {
     double* d_colsum = nullptr;       // [D][4]
     double* d_delta = nullptr;        // [D]
     struct ColPack* d_cpack = nullptr; // [D] stream schedule: 32-byte per-column records gathered by the other side's pass
+    // SVBFM_REC_RANK=1 (experiment, off by default): the records of the second field's columns are laid out by popularity
+    // rank (slot = rank by descending column length) and the cases of every first-field column are ordered by that rank, so
+    // that neighbouring lanes of the first field's pass gather neighbouring records. d_rec_slot[j] = record slot of column j
+    // (identity outside the second field); the first field's `cother` entries then hold slots, not column ids.
+    uint32_t* d_rec_slot = nullptr;    // [D]
+    bool rec_rank = false;
     double* d_dT = nullptr;           // [D]
     double* d_red_partial = nullptr;  // reduction scratch
     double* d_grp_sums = nullptr;     // [(K+1)][G][2]

@@ -345,6 +345,7 @@ struct FinalizeArgs {
     SpanView span;
     const double2* ab;           // sharded: global {A, B} of every column after the allreduce (colsum keeps the local sums)
     ColPack* cpack;              // [D] gathered by the other side
+    const uint32_t* rec_slot;    // record slot of every column (null: the column id; Engine::d_rec_slot)
     OwnPack* opack;              // [D] read by this side's next pass
     int rec_mode;                // 1: first field  -> cpack {new mean, new var, delta, p_prev mean}    opack {p_next mean, new mean, delta}
                                  // 2: second field -> cpack {p_next mean, p_next var, delta, old mean} opack {p_next mean, p_next mean, delta}
@@ -364,11 +365,12 @@ struct FinalizeArgs {
 __device__ __forceinline__ void write_records(const FinalizeArgs& a, uint32_t j, double new_mean, double new_var, double dlt, double mu_old) {
     if (!a.rec_mode) return;
     double2 N = a.p_next ? a.p_next[j] : make_double2(0.0, 0.0);
+    const uint32_t sj = a.rec_slot ? a.rec_slot[j] : j;
     if (a.rec_mode == 1) {
-        a.cpack[j] = ColPack{new_mean, new_var, dlt, a.p_prev ? a.p_prev[j].x : 0.0};
+        a.cpack[sj] = ColPack{new_mean, new_var, dlt, a.p_prev ? a.p_prev[j].x : 0.0};
         a.opack[j] = OwnPack{N.x, new_mean, dlt, 0.0};
     } else {
-        a.cpack[j] = ColPack{N.x, N.y, dlt, mu_old};
+        a.cpack[sj] = ColPack{N.x, N.y, dlt, mu_old};
         a.opack[j] = OwnPack{N.x, N.x, dlt, 0.0};
     }
 }
@@ -1503,12 +1505,13 @@ __global__ void k_finish_iter(Scalars* sc, DevStats* st, int method) {
 // stream schedule: records before the first step s0 (parameters p0): second-field columns are gathered by the first
 // pass, every column needs its own constants
 __global__ void k_pack_init(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, const double2* __restrict__ p0, ColPack* __restrict__ cpack,
-                            OwnPack* __restrict__ opack) {
+                            OwnPack* __restrict__ opack, const uint32_t* __restrict__ rec_slot) {
     uint32_t j = a0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= b1) return;
     double2 P = p0[j];
-    if (j < a1) { opack[j] = OwnPack{P.x, 0.0, 0.0, 0.0}; cpack[j] = ColPack{0.0, 0.0, 0.0, 0.0}; }
-    else if (j >= b0) { opack[j] = OwnPack{P.x, P.x, 0.0, 0.0}; cpack[j] = ColPack{P.x, P.y, 0.0, 0.0}; }
+    const uint32_t sj = rec_slot ? rec_slot[j] : j;
+    if (j < a1) { opack[j] = OwnPack{P.x, 0.0, 0.0, 0.0}; cpack[sj] = ColPack{0.0, 0.0, 0.0, 0.0}; }
+    else if (j >= b0) { opack[j] = OwnPack{P.x, P.x, 0.0, 0.0}; cpack[sj] = ColPack{P.x, P.y, 0.0, 0.0}; }
 }
 // before the second field's flush pass: h4 = the first field's mean of the last step
 __global__ void k_pack_h4(uint32_t c0, uint32_t c1, const double2* __restrict__ p, ColPack* __restrict__ cpack) {

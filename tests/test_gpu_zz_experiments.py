@@ -1,0 +1,49 @@
+"""Opt-in variants of the hot path (environment knobs, off by default) against the oracle. Kept in a file that sorts last:
+these paths are experiments for the next measurement round, the default path's parity tests come first."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from helpers import make_learner, rel, to_csc, two_field
+
+pytestmark = pytest.mark.gpu
+VB_TOL = 1e-7
+
+
+@pytest.mark.parametrize("tile_entries", [0, 64])
+def test_rec_rank_layout(built, monkeypatch, tile_entries):
+    """SVBFM_REC_RANK=1: second-field records by popularity rank, cases of a first-field column ordered by that rank.
+    Same algorithm, another case order: statistics, parameters and residuals (caller order) equal the oracle's."""
+    monkeypatch.setenv("SVBFM_REC_RANK", "1")
+    for values in (False, True):
+        tr, te = two_field(20000, 2000, 300, 200, seed=11, values=values)
+        orc = ob.Oracle("vb", tr, te, K=3, seed=42)
+        L = make_learner("vb", tr, te, 3, num_iter=4, tile_entries=tile_entries)
+        for it, s in enumerate(L.learn(to_csc(tr), to_csc(te))):
+            o = orc.iterate()
+            assert rel(s.test_rmse, o.test_rmse) < VB_TOL and rel(s.free_energy, o.free_energy) < VB_TOL and rel(s.alpha, o.alpha) < VB_TOL, it
+        assert L.engine.info()["fused_schedule"] == 3
+        assert L.engine.copies_max_diff() == 0.0
+        e_o, t_o = orc.get_train_cache()
+        assert np.max(np.abs(L.engine.get_residuals() - e_o)) < (1e-7 if values else 1e-9)   # x != 1: float products round differently
+        so, sg = orc.get_state(), L.engine.get_state()
+        for k in ("w_mean", "w_var", "v_mean", "v_var"):
+            assert np.max(np.abs(so[k] - sg[k])) < (1e-7 if values else 1e-9), k
+        L.engine.close()
+    # als and vb_online on the same layout
+    tr, te = two_field(12000, 1200, 200, 150, seed=12)
+    orc = ob.Oracle("mcmc", tr, te, K=2, seed=42, do_sample=False, do_multilevel=False)
+    L = make_learner("mcmc", tr, te, 2, num_iter=3, do_sample=False, do_multilevel=False, tile_entries=tile_entries)
+    L.fm.reg0, L.fm.regw, L.fm.regv = 0.0, 0.0, 0.0
+    for s in L.learn(to_csc(tr), to_csc(te)):
+        o = orc.iterate()
+        assert rel(s.test_rmse, o.test_rmse) < VB_TOL and rel(s.train_stat, o.train_stat) < VB_TOL
+    assert L.engine.info()["fused_schedule"] == 3
+    L.engine.close()
+    orc = ob.Oracle("vb_online", tr, te, K=2, seed=42, num_batch=5)
+    want = [orc.iterate() for _ in range(2)]
+    L = make_learner("vb_online", tr, te, 2, num_iter=2, num_batch=5, tile_entries=tile_entries)
+    for it, s in enumerate(L.learn(to_csc(tr), to_csc(te))):
+        assert rel(s.test_rmse, want[it].test_rmse) < VB_TOL and rel(s.free_energy, want[it].free_energy) < VB_TOL
+    assert L.engine.info()["fused_schedule"] == 3
+    L.engine.close()
