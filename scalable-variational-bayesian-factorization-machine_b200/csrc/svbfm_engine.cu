@@ -409,6 +409,12 @@ int stream_tile_cols(Engine* E) {
 
 // every e_i += w0_delta, on both copies
 static void shift_e(Engine* E) {
+    if (E->bv.on && E->bv.lists) {      // vb_online batch on the stream schedule: only the entries of the batch are live
+        const uint32_t n = E->bv.n, grid = std::max(1u, std::min<unsigned>(nblk(n), SV_RGRID));
+        k_shift_e_list<<<grid, 256, 0, E->stream>>>(E->d_e, E->d_vbo_idx[0] + E->bv.entry0, n, E->d_sc); LAUNCHED(E);
+        k_shift_e_list<<<grid, 256, 0, E->stream>>>(E->d_e2, E->d_vbo_idx[1] + E->bv.entry0, n, E->d_sc); LAUNCHED(E);
+        return;
+    }
     k_shift_e<<<SV_RGRID, 256, 0, E->stream>>>(E->d_e, E->tr.n, E->d_sc); LAUNCHED(E);
     if (E->d_e2) { k_shift_e<<<SV_RGRID, 256, 0, E->stream>>>(E->d_e2, E->tr.n, E->d_sc); LAUNCHED(E); }
 }
@@ -422,6 +428,12 @@ static void sync_e2(Engine* E) {
 // sum e, sum e^2, sum clamp(e)^2 -> red[0..2] (global)
 static int reduce_e(Engine* E, int batch = -1) {
     cudaStream_t st = E->stream;
+    if (E->bv.on && E->bv.lists) {      // vb_online batch on the stream schedule: the batch's own case list (positions in e = device case ids)
+        const uint32_t n = E->bv.n, grid = std::max(1u, std::min<unsigned>(nblk(n), SV_RGRID));
+        k_reduce_e_list<<<grid, 256, 0, st>>>(E->d_e, E->d_vbo_idx[0] + E->bv.entry0, n, E->d_sc, E->d_red_partial); LAUNCHED(E);
+        k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, grid, 3, RED(E->d_sc, 0), 0); LAUNCHED(E);
+        return allreduce_sum_f64(E, RED(E->d_sc, 0), 3);
+    }
     k_reduce_e<<<SV_RGRID, 256, 0, st>>>(E->d_e, E->tr.n, E->d_sc, E->d_red_partial, batch >= 0 ? E->d_rbatch : nullptr, batch >= 0 ? (uint32_t)batch : 0u); LAUNCHED(E);
     k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_RGRID, 3, RED(E->d_sc, 0), 0); LAUNCHED(E);
     return allreduce_sum_f64(E, RED(E->d_sc, 0), 3);
@@ -448,9 +460,17 @@ static int predict(Engine* E, const DevSplit& S, double* e_out, int red_slot, in
     a.partial = E->d_red_partial;
     a.rbatch = batch >= 0 ? E->d_rbatch : nullptr; a.batch = batch >= 0 ? (uint32_t)batch : 0u;
     unsigned grid = std::max(1u, std::min<unsigned>(nblk(S.n), SV_RGRID));
+    if (MODE == PRED_VB_TRAIN && E->bv.on && E->bv.lists) {     // vb_online batch on the stream schedule: walk the batch's own case list
+        a.list = E->d_vbo_idx[0] + E->bv.entry0; a.nlist = E->bv.n;
+        grid = std::max(1u, std::min<unsigned>(nblk(a.nlist), SV_RGRID));
+#define CALL_PL(FT, ONES) k_predict<MODE, FT, ONES, true><<<grid, 256, 0, st>>>(a)
+        DISPATCH_FMT(S, CALL_PL);
+#undef CALL_PL
+    } else {
 #define CALL_P(FT, ONES) k_predict<MODE, FT, ONES><<<grid, 256, 0, st>>>(a)
-    DISPATCH_FMT(S, CALL_P);
+        DISPATCH_FMT(S, CALL_P);
 #undef CALL_P
+    }
     LAUNCHED(E);
     k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, grid, 4, E->d_red_partial + SCR_FINAL, 0); LAUNCHED(E);
     // move the first nred sums into red[red_slot..]
@@ -1045,13 +1065,17 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
     cudaEventRecord(t0, st);
     for (uint32_t b = 0; b < num_batch; b++) {
         k_vbo_batch_begin<<<1, 1, 0, st>>>(E->d_sc, E->d_batch_n, b); LAUNCHED(E);
+        const uint32_t nb_cases = use_streams ? (uint32_t)(E->vbo_off[b + 1] - E->vbo_off[b]) : 0u;
+        // on the stream schedule the prediction, the reductions and the w0 shift of a batch walk the batch's own case list
+        // (E->bv) instead of masking the whole arrays; SVBFM_VBO_FULL_PASSES=1 keeps the masked passes (for comparison)
+        const bool full_passes = getenv("SVBFM_VBO_FULL_PASSES") != nullptr;
+        struct BvGuard { Engine* E; ~BvGuard() { E->bv.on = false; } } bv_guard{E};      // every exit leaves the whole-run views in force
+        if (use_streams && nb_cases) { E->bv.on = true; E->bv.lists = !full_passes; E->bv.entry0 = E->vbo_off[b]; E->bv.n = nb_cases; }
         // fresh y-hat, T for the cases of the batch (vbos.h:120-127)
         if (int rc = predict<PRED_VB_TRAIN>(E, S, E->d_e, 6, 1, (int)b)) return rc;
         SV_CUDA(E, cudaMemcpyAsync(&E->d_sc->sum_t, RED(E->d_sc, 6), 8, cudaMemcpyDeviceToDevice, st));
-        const uint32_t nb_cases = use_streams ? (uint32_t)(E->vbo_off[b + 1] - E->vbo_off[b]) : 0u;
         if (use_streams && nb_cases) {
             const Run &r0 = E->runs[0], &r1 = E->runs[1];
-            E->bv.on = true; E->bv.entry0 = E->vbo_off[b]; E->bv.n = nb_cases;
             E->bv.ntiles = (uint32_t)(((uint64_t)nb_cases + (1ull << E->vbo_ts_shift) - 1) >> E->vbo_ts_shift);
             for (int ri = 0; ri < 2; ri++) {
                 const Run& r = ri ? r1 : r0;
@@ -1071,7 +1095,7 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
             shift_e(E);
         }
         if (use_streams) {
-            if (nb_cases) { int rc = sweep_streams<2>(E); E->bv.on = false; if (rc) return rc; }
+            if (nb_cases) if (int rc = sweep_streams<2>(E)) return rc;
         } else {
             for (const Run& r : E->runs)                           // update_w; also counts |Omega_j^b| (vbo.h:360-373)
                 if (int rc = sweep_run<KIND_VBO_W>(E, r, -1, (int)b)) return rc;

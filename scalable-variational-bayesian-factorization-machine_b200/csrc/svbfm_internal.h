@@ -145,6 +145,7 @@ struct Engine {
     std::vector<uint64_t> vbo_off;                         // [num_batch + 1] first entry of every batch in idx
     struct BatchView {                                      // what launch_stream / combine_finalize use instead of the whole run
         bool on = false;
+        bool lists = false;                                 // prediction / reductions / w0 shift of the batch walk its case list too
         const uint64_t* colptr[2] = {nullptr, nullptr};
         uint64_t entry0 = 0;
         uint32_t n = 0, ntiles = 0;

@@ -931,6 +931,26 @@ __global__ void __launch_bounds__(256) k_shift_e(double* __restrict__ e, uint32_
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) e[i] += d;
 }
 
+// vb_online on the stream schedule: the same two passes over the entries of one batch only (list = their positions in e)
+__global__ void __launch_bounds__(256) k_reduce_e_list(const double* __restrict__ e, const uint32_t* __restrict__ list, uint32_t n, const Scalars* sc,
+                                                       double* __restrict__ partial) {
+    __shared__ double sm[3 * 32];
+    double lo = sc->min_target, hi = sc->max_target;
+    double v[3] = {0, 0, 0};
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        double x = e[__ldcs(&list[k])];
+        v[0] += x; v[1] += x * x;
+        double p = fmax(lo, fmin(hi, x));
+        v[2] += p * p;
+    }
+    block_sum<3>(v, sm);
+    if (threadIdx.x == 0) { partial[blockIdx.x * 3 + 0] = v[0]; partial[blockIdx.x * 3 + 1] = v[1]; partial[blockIdx.x * 3 + 2] = v[2]; }
+}
+__global__ void __launch_bounds__(256) k_shift_e_list(double* __restrict__ e, const uint32_t* __restrict__ list, uint32_t n, const Scalars* sc) {
+    double d = sc->w0_delta;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) e[__ldcs(&list[k])] += d;
+}
+
 // sum over columns of dT[j]; zeroes dT
 __global__ void __launch_bounds__(256) k_reduce_dT(double* __restrict__ dT, uint32_t n, double* __restrict__ partial) {
     __shared__ double sm[32];
@@ -996,17 +1016,22 @@ struct PredictArgs {
     double* partial;      // [grid][4]
     const uint16_t* rbatch;    // vb_online: restrict to the cases of the current batch
     uint32_t batch;
+    const uint32_t* list;      // LIST: the cases to predict (vb_online on the stream schedule: the batch's own case list)
+    uint32_t nlist;
 };
 
-template <int MODE, int FT, bool ONES>
+template <int MODE, int FT, bool ONES, bool LIST = false>
 __global__ void __launch_bounds__(256) k_predict(PredictArgs a) {
     __shared__ double sm[4 * 32];
     double acc[4] = {0, 0, 0, 0};
     const double w0 = a.sc->w0_mean, w0v = a.sc->w0_var;
     const double lo = a.sc->min_target, hi = a.sc->max_target;
     const double inv_it = 1.0 / (double)(a.sc->iter + 1);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
-        if (MODE == PRED_VB_TRAIN && a.rbatch && __ldg(&a.rbatch[i]) != a.batch) continue;
+    const uint32_t count = LIST ? a.nlist : a.n;
+    for (uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x; k0 < count; k0 += gridDim.x * blockDim.x) {
+        uint32_t i = k0;
+        if constexpr (LIST) i = __ldcs(&a.list[k0]);
+        else if (MODE == PRED_VB_TRAIN && a.rbatch && __ldg(&a.rbatch[i]) != a.batch) continue;
         uint64_t b, e_;
         uint32_t c2[2] = {0, 0}; float x2[2] = {1.0f, 1.0f};
         if constexpr (FT == 2) {

@@ -47,3 +47,21 @@ def test_rec_rank_layout(built, monkeypatch, tile_entries):
         assert rel(s.test_rmse, want[it].test_rmse) < VB_TOL and rel(s.free_energy, want[it].free_energy) < VB_TOL
     assert L.engine.info()["fused_schedule"] == 3
     L.engine.close()
+
+
+def test_vb_online_batch_lists_equal_masked_passes(built, monkeypatch):
+    """vb_online on the stream schedule: prediction / reductions / w0 shift over the batch's own case list (default) against
+    the masked passes over the whole arrays (SVBFM_VBO_FULL_PASSES=1): same numbers up to the order of the sums."""
+    tr, te = two_field(16000, 1600, 260, 190, seed=21)
+    out = []
+    for full in (False, True):
+        if full:
+            monkeypatch.setenv("SVBFM_VBO_FULL_PASSES", "1")
+        else:
+            monkeypatch.delenv("SVBFM_VBO_FULL_PASSES", raising=False)
+        L = make_learner("vb_online", tr, te, 3, num_iter=3, num_batch=7, tile_entries=64)
+        out.append([(s.test_rmse, s.free_energy, s.alpha) for s in L.learn(to_csc(tr), to_csc(te))])
+        assert L.engine.info()["fused_schedule"] == 1
+        L.engine.close()
+    for a, b in zip(*out):
+        assert all(rel(x, y) < 1e-10 for x, y in zip(a, b)), (a, b)
