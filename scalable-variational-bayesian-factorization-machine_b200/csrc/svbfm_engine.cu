@@ -460,13 +460,18 @@ static int predict(Engine* E, const DevSplit& S, double* e_out, int red_slot, in
     a.partial = E->d_red_partial;
     a.rbatch = batch >= 0 ? E->d_rbatch : nullptr; a.batch = batch >= 0 ? (uint32_t)batch : 0u;
     unsigned grid = std::max(1u, std::min<unsigned>(nblk(S.n), SV_RGRID));
-    if (MODE == PRED_VB_TRAIN && E->bv.on && E->bv.lists) {     // vb_online batch on the stream schedule: walk the batch's own case list
-        a.list = E->d_vbo_idx[0] + E->bv.entry0; a.nlist = E->bv.n;
-        grid = std::max(1u, std::min<unsigned>(nblk(a.nlist), SV_RGRID));
+    bool listed = false;
+    if constexpr (MODE == PRED_VB_TRAIN) {
+        if (E->bv.on && E->bv.lists) {     // vb_online batch on the stream schedule: walk the batch's own case list
+            listed = true;
+            a.list = E->d_vbo_idx[0] + E->bv.entry0; a.nlist = E->bv.n;
+            grid = std::max(1u, std::min<unsigned>(nblk(a.nlist), SV_RGRID));
 #define CALL_PL(FT, ONES) k_predict<MODE, FT, ONES, true><<<grid, 256, 0, st>>>(a)
-        DISPATCH_FMT(S, CALL_PL);
+            DISPATCH_FMT(S, CALL_PL);
 #undef CALL_PL
-    } else {
+        }
+    }
+    if (!listed) {
 #define CALL_P(FT, ONES) k_predict<MODE, FT, ONES><<<grid, 256, 0, st>>>(a)
         DISPATCH_FMT(S, CALL_P);
 #undef CALL_P
