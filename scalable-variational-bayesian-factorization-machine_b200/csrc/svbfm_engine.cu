@@ -338,7 +338,13 @@ static void launch_stream(Engine* E, int side, bool has_own, bool own_is_w, bool
         if (a.idx) { if constexpr (!MCMC) k_stream<KIND, ONES, REDUCE, STEADY, true><<<grid, 256, 0, E->stream>>>(a); } \
         else k_stream<KIND, ONES, REDUCE, STEADY, false><<<grid, 256, 0, E->stream>>>(a);                           \
     } while (0)
-    if (steady) { if (S.all_ones) CALL_S(true, true); else CALL_S(false, true); }
+    // SVBFM_STREAM_TMA=1 (experiment): streams staged through shared memory by bulk copies; needs 16-byte aligned stream starts
+    const bool tma = E->stream_tma && S.all_ones && !a.idx && (a.real0 % 4 == 0);
+    if (tma) {
+        if (steady) k_stream<KIND, true, REDUCE, true, false, true><<<grid, 256, 0, E->stream>>>(a);
+        else k_stream<KIND, true, REDUCE, false, false, true><<<grid, 256, 0, E->stream>>>(a);
+    }
+    else if (steady) { if (S.all_ones) CALL_S(true, true); else CALL_S(false, true); }
     else { if (S.all_ones) CALL_S(true, false); else CALL_S(false, false); }
 #undef CALL_S
     LAUNCHED(E);
@@ -684,6 +690,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     ++g_handles;
     E->cfg = *cfg; E->dev = cfg->device; E->D = cfg->num_attribute; E->K = cfg->num_factor;
     E->tile_entries = cfg->tile_entries ? cfg->tile_entries : 1024;
+    if (const char* tm = getenv("SVBFM_STREAM_TMA")) E->stream_tma = atoi(tm) != 0;
     if (const char* te = getenv("SVBFM_TILE_ENTRIES")) if (atoi(te) >= 32) E->tile_entries = (uint32_t)atoi(te);   // tuning knob
     // implicit tiles of the stream schedule: 4096 entries unless the caller (or the knob) says otherwise
     uint32_t ts = (cfg->tile_entries || getenv("SVBFM_TILE_ENTRIES")) ? E->tile_entries : 4096u;
@@ -1233,7 +1240,7 @@ int svbfm_get_info(svbfm_t* h, svbfm_info* out) {
     out->train_nnz = E->tr.nnz;
     out->rows_reordered = E->rows_reordered;
     out->world_size = (uint32_t)E->world;
-    out->fused_schedule = ((stream_ok(E) || E->vbo_streams) ? 1u : 0u) | (E->rec_rank ? 2u : 0u);
+    out->fused_schedule = ((stream_ok(E) || E->vbo_streams) ? 1u : 0u) | (E->rec_rank ? 2u : 0u) | ((E->stream_tma && stream_ok(E)) ? 4u : 0u);
     out->exclusive_blocks = E->excl0 ? 1u : 0u;
     return SVBFM_OK;
 }

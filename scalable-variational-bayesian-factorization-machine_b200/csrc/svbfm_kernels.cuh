@@ -621,6 +621,57 @@ __device__ __forceinline__ void entry_terms(double ei, float xf, float xof, cons
     }
 }
 
+// ---- 1-D bulk copies global -> shared, completion on an mbarrier (TMA unit: no LSU wavefronts, no registers in flight).
+// Used by the TMA variant of k_stream. Under tests/emu the copy happens at issue and the barrier keeps the same
+// phase / transaction arithmetic, so that a wait on a stage that was never armed shows up as a deadlock.
+#if defined(SVBFM_EMULATED)
+struct SvMbar { uint32_t phase, pending, init; int64_t tx; };
+static inline void sv_mbar_init(SvMbar* b, uint32_t count) { b->phase = 0; b->pending = count; b->init = count; b->tx = 0; }
+static inline void sv_mbar_flip(SvMbar* b) { if (b->pending == 0 && b->tx == 0) { b->phase ^= 1; b->pending = b->init; } }
+static inline void sv_mbar_arrive_expect_tx(SvMbar* b, uint32_t bytes) { b->tx += bytes; b->pending--; sv_mbar_flip(b); }
+static inline void sv_bulk_g2s(void* dst, const void* src, uint32_t bytes, SvMbar* b) {
+    if (((uintptr_t)dst & 15) || ((uintptr_t)src & 15) || (bytes & 15)) { fprintf(stderr, "[emu] misaligned bulk copy\n"); abort(); }
+    static long n_copies = 0;
+    if (++n_copies == 1 && getenv("SVBFM_EMU_VERBOSE")) fprintf(stderr, "[emu] bulk copies in use\n");
+    memcpy(dst, src, bytes); b->tx -= bytes; sv_mbar_flip(b);
+}
+static inline void sv_mbar_wait(SvMbar* b, uint32_t parity) {
+    if (b->phase == parity) { fprintf(stderr, "[emu] mbarrier wait on a phase that will never complete\n"); abort(); }
+}
+static inline void sv_fence_mbar_init() {}
+#else
+typedef unsigned long long SvMbar;
+__device__ __forceinline__ uint32_t sv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sv_mbar_init(SvMbar* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sv_smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sv_fence_mbar_init() {      // make the initialised barriers visible to the async proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void sv_mbar_arrive_expect_tx(SvMbar* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sv_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sv_bulk_g2s(void* dst, const void* src, uint32_t bytes, SvMbar* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sv_smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(sv_smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void sv_mbar_wait(SvMbar* b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SV_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SV_DONE_%=;\n"
+        "bra SV_WAIT_%=;\n"
+        "SV_DONE_%=:\n"
+        "}\n" ::"r"(sv_smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+#endif
+
 // STEADY: both sides have a pending v update (every pass of the factor loop but the first ones): no runtime flags
 #ifndef SV_STREAM_U
 #define SV_STREAM_U 2        // rows of 32 entries per batch (measured: 2 x 4 CTAs/SM beats 4 x 2, gpurun_out/tune_*)
@@ -631,8 +682,33 @@ __device__ __forceinline__ void entry_terms(double ei, float xf, float xof, cons
 #ifndef SV_STREAM_MINB
 #define SV_STREAM_MINB 3     // resident CTAs per SM the register allocation aims at (72 registers, no spills)
 #endif
-template <int KIND, bool ONES, bool REDUCE, bool STEADY, bool IDX = false>
+// per-warp ring + barriers of the TMA variant (8 warps per CTA); the plain variant declares no shared memory at all
+template <bool TMA, int NST, uint32_t BYTES>
+struct StreamRing {
+    static __device__ __forceinline__ unsigned char* ring(uint32_t) { return nullptr; }
+    static __device__ __forceinline__ SvMbar* bars(uint32_t) { return nullptr; }
+};
+template <int NST, uint32_t BYTES>
+struct StreamRing<true, NST, BYTES> {
+    static __device__ __forceinline__ unsigned char* ring(uint32_t w) {
+        alignas(128) __shared__ unsigned char s_ring[8][NST][BYTES];
+        return &s_ring[w][0][0];
+    }
+    static __device__ __forceinline__ SvMbar* bars(uint32_t w) {
+        alignas(8) __shared__ SvMbar s_bar[8][NST];
+        return &s_bar[w][0];
+    }
+};
+#ifndef SV_TMA_STAGES
+#define SV_TMA_STAGES 6      // ring slots per warp (one slot = one batch: 32 U residuals + 32 U column ids); SV_TMA_STAGES - 2 batches in flight
+#endif
+// TMA (experiment, SVBFM_STREAM_TMA=1; all-ones data, no index list): the two streams of a warp's tile (residuals, other-column
+// ids) are staged through a per-warp shared-memory ring by 1-D bulk copies that lane 0 issues SV_TMA_STAGES - 2 batches
+// ahead; the lanes read their entries with LDS once the slot's mbarrier completes. Deeper prefetch than the register batch
+// (bytes in flight per SM: 24 warps x 4 x 768 B instead of 24 x 768 B) at no register cost. The stores stay STG.
+template <int KIND, bool ONES, bool REDUCE, bool STEADY, bool IDX = false, bool TMA = false>
 __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
+    static_assert(!TMA || (ONES && !IDX && SV_STREAM_GPIPE == 0), "the TMA variant covers the all-ones streams without an index list");
     constexpr bool IS_V = (KIND == KIND_VB_V || KIND == KIND_MC_V);
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int U = SV_STREAM_U;
@@ -655,8 +731,46 @@ __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
     // next batch of the streams (issued one batch ahead)
     uint32_t oc_n[U]; float xs_n[U], xo_n[U]; double e_n[U];
     uint32_t r_n[IDX ? U : 1];              // IDX: the real positions of the batch (needed again for the store)
+    // TMA: per-warp ring of SV_TMA_STAGES slots {32 U doubles, 32 U ids}; batch b of the tile lives in slot b % SV_TMA_STAGES
+    constexpr int NST = SV_TMA_STAGES;
+    constexpr uint32_t SLOT_E = 32 * U * 8, SLOT_BYTES = 32 * U * 12;
+    unsigned char* const my_ring = StreamRing<TMA, NST, SLOT_BYTES>::ring(threadIdx.x >> 5);   // null unless TMA (no shared memory then)
+    SvMbar* const my_bar = StreamRing<TMA, NST, SLOT_BYTES>::bars(threadIdx.x >> 5);
+    auto tma_issue = [&](uint32_t bn) {     // lane 0: arm the slot of batch bn and start its two copies (whole batches only)
+        const uint32_t qn = q_begin + bn * (32 * U);
+        if (qn >= q_end || q_end - qn < 32 * U) return;
+        SvMbar* bar = my_bar + bn % NST;
+        unsigned char* dst = my_ring + (size_t)(bn % NST) * SLOT_BYTES;
+        sv_mbar_arrive_expect_tx(bar, SLOT_BYTES);
+        sv_bulk_g2s(dst, ep + qn, SLOT_E, bar);
+        sv_bulk_g2s(dst + SLOT_E, ocp + qn, SLOT_BYTES - SLOT_E, bar);
+    };
+    if constexpr (TMA) {
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NST; k++) sv_mbar_init(my_bar + k, 1);
+            sv_fence_mbar_init();
+#pragma unroll
+            for (int k = 0; k < NST; k++) tma_issue((uint32_t)k);
+        }
+        __syncwarp();
+    }
     auto load_batch = [&](uint32_t q) {
-        if (q_end - q >= 32 * U) {          // a whole batch: no predicates
+        if (TMA && q_end - q >= 32 * U) {   // a whole batch out of the ring
+            const uint32_t bi = (q - q_begin) / (32 * U), slot = bi % NST;
+            sv_mbar_wait(my_bar + slot, (bi / NST) & 1u);
+            const double* se = reinterpret_cast<const double*>(my_ring + (size_t)slot * SLOT_BYTES);
+            const uint32_t* so = reinterpret_cast<const uint32_t*>(my_ring + (size_t)slot * SLOT_BYTES + SLOT_E);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                oc_n[u] = so[u * 32 + lane];
+                xs_n[u] = 1.0f; xo_n[u] = 1.0f;
+                e_n[u] = se[u * 32 + lane];
+            }
+            // the slot of batch bi - 2 is free: every lane has used its values (process() of that batch lies behind us)
+            __syncwarp();
+            if (bi >= 2 && lane == 0) tma_issue(bi - 2 + NST);
+        } else if (q_end - q >= 32 * U) {          // a whole batch: no predicates
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 uint32_t k = q + u * 32 + lane;
