@@ -1,0 +1,27 @@
+#!/bin/bash
+# First gpurun call of the next measurement round: validates and times everything that was built without a GPU
+# (DESIGN.md section 7a). Every step runs under its own timeout so that a hang in an experimental kernel cannot hold the box;
+# results land in gpurun_out/next_*.  Usage:
+#   gpurun --timeout 1500 -- 'bash tools/next_gpu_call.sh'
+set -u
+mkdir -p gpurun_out
+out=gpurun_out
+py=python
+
+# 1. the default path: full GPU suite (includes the vb_online batch lists, now the default)
+timeout 600 $py -m pytest tests -m gpu -x -q > $out/next_pytest_gpu.log 2>&1; echo "pytest -m gpu rc=$?" | tee $out/next_summary.txt
+
+# 2. the experiments, each alone (a hang or a wrong result in one must not hide the others)
+SVBFM_REC_RANK=1 timeout 300 $py -m pytest tests/test_gpu_zz_experiments.py -m gpu -q -k rec_rank > $out/next_pytest_rec_rank.log 2>&1; echo "rec_rank tests rc=$?" | tee -a $out/next_summary.txt
+SVBFM_STREAM_TMA=1 timeout 300 $py -m pytest tests/test_gpu_zz_experiments.py -m gpu -q -k tma > $out/next_pytest_tma.log 2>&1; echo "tma tests rc=$?" | tee -a $out/next_summary.txt
+
+# 3. bench lines: default, each experiment, both (device-resident value only where e2e is not the question)
+timeout 600 $py bench.py --steps 5 --warmup 3 > $out/next_bench_default.json 2> $out/next_bench_default.err; echo "bench default rc=$?" | tee -a $out/next_summary.txt
+SVBFM_REC_RANK=1 timeout 600 $py bench.py --steps 5 --warmup 3 --no-cpu-baseline > $out/next_bench_rec_rank.json 2> $out/next_bench_rec_rank.err; echo "bench rec_rank rc=$?" | tee -a $out/next_summary.txt
+SVBFM_STREAM_TMA=1 timeout 600 $py bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > $out/next_bench_tma.json 2> $out/next_bench_tma.err; echo "bench tma rc=$?" | tee -a $out/next_summary.txt
+SVBFM_REC_RANK=1 SVBFM_STREAM_TMA=1 timeout 600 $py bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > $out/next_bench_rec_rank_tma.json 2> $out/next_bench_rec_rank_tma.err; echo "bench rec_rank+tma rc=$?" | tee -a $out/next_summary.txt
+timeout 900 $py bench.py --method vb_online --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $out/next_bench_vbo.json 2> $out/next_bench_vbo.err; echo "bench vb_online rc=$?" | tee -a $out/next_summary.txt
+SVBFM_VBO_FULL_PASSES=1 timeout 900 $py bench.py --method vb_online --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $out/next_bench_vbo_full_passes.json 2> $out/next_bench_vbo_full_passes.err; echo "bench vb_online (masked passes) rc=$?" | tee -a $out/next_summary.txt
+
+grep -h -o '"ms_per_step": [0-9.]*' $out/next_bench_*.json | paste -d' ' - - - - - - 2>/dev/null | tee -a $out/next_summary.txt
+for f in $out/next_bench_*.json; do echo "$f $(grep -o '"ms_per_step": [0-9.]*' $f | head -1)"; done | tee -a $out/next_summary.txt
