@@ -52,6 +52,13 @@ def lib():
         L.orc_init.argtypes = [C.c_void_p, C.c_long, C.c_double]
         L.orc_set_mcmc_options.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_set_num_batch.argtypes = [C.c_void_p, C.c_uint32]
+        L.orc_set_task.argtypes = [C.c_void_p, C.c_int32]
+        L.orc_cdf_gaussian.argtypes = [C.c_double]
+        L.orc_cdf_gaussian.restype = C.c_double
+        L.orc_ran_left_tgaussian.argtypes = [C.c_double] * 3
+        L.orc_ran_left_tgaussian.restype = C.c_double
+        L.orc_ran_right_tgaussian.argtypes = [C.c_double] * 3
+        L.orc_ran_right_tgaussian.restype = C.c_double
         L.orc_set_regular.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
         L.orc_begin.argtypes = [C.c_void_p]
         L.orc_iterate.argtypes = [C.c_void_p, C.POINTER(Stats)]
@@ -154,7 +161,7 @@ class Oracle:
     """One learner instance of the CPU restatement (vb | vb_online | mcmc)."""
 
     def __init__(self, method, train, test, K, k0=1, k1=1, D=None, seed=42, init_stdev=0.1,
-                 groups=None, num_batch=None, do_sample=True, do_multilevel=True, reg=None):
+                 groups=None, num_batch=None, do_sample=True, do_multilevel=True, reg=None, task=0):
         L = lib()
         self.method = METHODS[method] if isinstance(method, str) else method
         if D is None:
@@ -177,6 +184,8 @@ class Oracle:
         if num_batch is not None:
             L.orc_set_num_batch(self.h, int(num_batch))
         L.orc_set_mcmc_options(self.h, int(do_sample), int(do_multilevel))
+        if task:
+            assert L.orc_set_task(self.h, int(task)) == 0
         assert L.orc_init(self.h, int(seed), float(init_stdev)) == 0
         if reg is not None:
             assert L.orc_set_regular(self.h, float(reg[0]), float(reg[1]), float(reg[2])) == 0

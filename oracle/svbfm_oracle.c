@@ -60,6 +60,32 @@ double orc_ran_gamma(double alpha) {                                            
 }
 static double ran_gamma_ab(double alpha, double beta) { return orc_ran_gamma(alpha) / beta; } /* random.h:146-148 */
 
+/* ---- classification (-task c): the reference's own erf approximation, cdf and truncated normals */
+double orc_erf(double x) {                                                        /* random.h:47-61 (Abramowitz-Stegun 7.1.26) */
+    double t = (x >= 0) ? 1.0 / (1.0 + 0.3275911 * x) : 1.0 / (1.0 - 0.3275911 * x);
+    double result = 1.0 - (t * (0.254829592 + t * (-0.284496736 + t * (1.421413741 + t * (-1.453152027 + t * 1.061405429))))) * exp(-x * x);
+    return (x >= 0) ? result : -result;
+}
+double orc_cdf_gaussian(double x) { return 0.5 + 0.5 * orc_erf(0.707106781 * x); }   /* random.h:67-69 */
+static double ran_exp(void) { return -log(1 - orc_ran_uniform()); }               /* random.h:178-180 */
+static double ran_left_tgaussian0(double left) {                                  /* random.h:72-102 */
+    if (left <= 0.0) {                                                            /* naive: acceptance probability > 0.5 */
+        double result;
+        do { result = orc_ran_gaussian(); } while (result < left);
+        return result;
+    }
+    double alpha_star = 0.5 * (left + sqrt(left * left + 4.0));                   /* Robert: translated exponential proposal */
+    for (;;) {
+        double z = ran_exp() / alpha_star + left;
+        double d = z - alpha_star;
+        d = exp(-(d * d) / 2);
+        double u = orc_ran_uniform();
+        if (u < d) return z;
+    }
+}
+double orc_ran_left_tgaussian(double left, double mean, double stdev) { return mean + stdev * ran_left_tgaussian0((left - mean) / stdev); }   /* random.h:104-106 */
+double orc_ran_right_tgaussian(double right, double mean, double stdev) { return mean + stdev * (-ran_left_tgaussian0(-((right - mean) / stdev))); } /* random.h:108-114 */
+
 /* ------------------------------------------------------------------ sparse containers */
 typedef struct spm {          /* sparse_row[] + sparse_entry[] (fmatrix.h:36-44) */
     uint32_t n;               /* number of rows of THIS matrix (cases for CSR, features for CSC) */
@@ -118,6 +144,7 @@ typedef struct split {
 /* ------------------------------------------------------------------ handle */
 struct orc {
     int method, K, k0, k1;
+    int task;                                /* 0 regression, 1 binary classification (fm_learn.h:67-68; mcmc only) */
     uint32_t D, G;
     uint32_t *attr_group, *n_per_group;      /* DataMetaInfo (Data.h:35-69) */
     split sp[2];
@@ -211,6 +238,7 @@ int orc_set_mcmc_options(orc_t *h, int do_sample, int do_multilevel) {
     h->do_sample = do_sample; h->do_multilevel = do_multilevel; return 0;
 }
 int orc_set_num_batch(orc_t *h, uint32_t nb) { h->num_batch = nb; return 0; }
+int orc_set_task(orc_t *h, int task) { if (task != 0 && (task != 1 || h->method != ORC_MCMC)) return -1; h->task = task; return 0; }
 /* -regular r0,r1,r2 for mcmc/als (libfm.cpp:367-405): call after orc_init */
 int orc_set_regular(orc_t *h, double r0, double rw, double rv) {
     if (h->method != ORC_MCMC || !h->w_lambda) return -1;
@@ -872,6 +900,54 @@ int orc_iterate(orc_t *h, orc_stats *out) {
         mcmc_draw_all(h);
         predict_eterms(h, tr, h->v, h->w, h->w0, h->e, h->q);
         predict_eterms(h, te, h->v, h->w, h->w0, h->e_test, h->q_test);
+        if (h->task == 1) {                                          /* mcmcs.h:176-221, 262-275, 326-398 */
+            for (uint32_t c = 0; c < nt; c++) {
+                double p = orc_cdf_gaussian(h->e_test[c]);
+                h->pred_this[c] = p;
+                h->pred_sum_all[c] += p;
+            }
+            uint32_t acc_train = 0;
+            for (uint32_t c = 0; c < n; c++) {
+                double p = orc_cdf_gaussian(h->e[c]);
+                if (((p >= 0.5) && (tr->y[c] > 0.0)) || ((p < 0.5) && (tr->y[c] < 0.0))) acc_train++;
+                double sampled_target, mu = h->e[c];
+                if (tr->y[c] >= 0.0) {
+                    if (h->do_sample) sampled_target = orc_ran_left_tgaussian(0.0, mu, 1.0);
+                    else {                                                       /* expected value of the truncated normal (3.141: the reference's pi) */
+                        double phi_minus_mu = exp(-mu * mu / 2.0) / sqrt(3.141 * 2);
+                        double Phi_minus_mu = orc_cdf_gaussian(-mu);
+                        sampled_target = mu + phi_minus_mu / (1 - Phi_minus_mu);
+                    }
+                } else {
+                    if (h->do_sample) sampled_target = orc_ran_right_tgaussian(0.0, mu, 1.0);
+                    else {
+                        double phi_minus_mu = exp(-mu * mu / 2.0) / sqrt(3.141 * 2);
+                        double Phi_minus_mu = orc_cdf_gaussian(-mu);
+                        sampled_target = mu - phi_minus_mu / Phi_minus_mu;
+                    }
+                }
+                h->e[c] = h->e[c] - sampled_target;
+            }
+            out->train_stat = (double)acc_train / n;                 /* "Train=" */
+            uint32_t a_this = 0, a_all = 0;
+            double ll = 0.0;
+            for (uint32_t c = 0; c < nt; c++) {                      /* _evaluate_class (this draw) and the accuracy part of _evaluate_class_map (running mean) */
+                double p = h->pred_this[c], pa = h->pred_sum_all[c] * (1.0 / (h->iter + 1));
+                if (((p >= 0.5) && (te->y[c] > 0.0)) || ((p < 0.5) && (te->y[c] < 0.0))) a_this++;
+                if (((pa >= 0.5) && (te->y[c] > 0.0)) || ((pa < 0.5) && (te->y[c] < 0.0))) a_all++;
+                double m = (te->y[c] + 1.0) * 0.5, pll = p;
+                if (pll > 0.99) pll = 0.99;
+                if (pll < 0.01) pll = 0.01;
+                ll -= m * log10(pll) + (1 - m) * log10(1 - pll);
+            }
+            out->rmse_this = (double)a_this / nt;                    /* acc_mcmc_this */
+            out->test_rmse = (double)a_all / nt;                     /* "Test=" (acc_mcmc_all) */
+            out->free_energy = ll / nt;                              /* ll_mcmc_this, carried in the free-energy slot */
+            out->alpha = h->alpha;
+            out->nan_inf_count = h->nan_inf;
+            h->iter++;
+            return 0;
+        }
         for (uint32_t c = 0; c < nt; c++) {                          /* mcmcs.h:154-163 */
             double p = h->e_test[c];
             h->pred_this[c] = p;

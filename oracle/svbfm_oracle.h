@@ -50,6 +50,7 @@ int    orc_begin(orc_t* h);
  * vb_online -> one epoch over num_batch batches */
 int    orc_iterate(orc_t* h, orc_stats* out);
 int    orc_set_num_batch(orc_t* h, uint32_t num_batch);
+int    orc_set_task(orc_t* h, int task);   /* 1 = binary classification, targets already mapped to -1 / +1 (libfm.cpp:337-343); mcmc only */
 int    orc_set_regular(orc_t* h, double r0, double rw, double rv);   /* mcmc/als -regular (libfm.cpp:367-405); after orc_init */
 
 /* state access (row-major [K][D] for the matrices, like DMatrix::value[f][j]) */
@@ -79,6 +80,10 @@ int  orc_read_y(const char* path, float** y, uint32_t* n);               /* matr
 double orc_ran_uniform(void);
 double orc_ran_gaussian(void);
 double orc_ran_gamma(double alpha);
+double orc_erf(double x);                  /* random.h:47-61 */
+double orc_cdf_gaussian(double x);         /* random.h:67-69 */
+double orc_ran_left_tgaussian(double left, double mean, double stdev);    /* random.h:72-106 */
+double orc_ran_right_tgaussian(double right, double mean, double stdev);  /* random.h:108-114 */
 
 #ifdef __cplusplus
 }

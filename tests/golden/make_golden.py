@@ -36,6 +36,19 @@ def write_two_field(path, n, U, I, seed):
             f.write(f"{a} {b}:1 {U + c}:1\n")
 
 
+def write_two_field_binary(path, n, U, I, seed, zero_for_negative=False):
+    """two one-hot fields with a binary target (+1 / -1, or 1 / 0: the reference maps every target <= 0 to -1, libfm.cpp:339)"""
+    r = np.random.default_rng(seed)
+    bu, bi = r.normal(0, 0.6, U), r.normal(0, 0.6, I)
+    P, Q = r.normal(0, 0.5, (U, 3)), r.normal(0, 0.5, (I, 3))
+    rr = np.random.default_rng(seed + 1000)
+    u, i = rr.integers(0, U, n), rr.integers(0, I, n)
+    s = bu[u] + bi[i] + (P[u] * Q[i]).sum(1) + rr.normal(0, 1.0, n)
+    with open(path, "w") as f:
+        for a, b, c in zip(s, u, i):
+            f.write(f"{1 if a > 0 else (0 if zero_for_negative else -1)} {b}:1 {U + c}:1\n")
+
+
 def write_ragged(path, n, D, seed, comments=False):
     r = np.random.default_rng(seed)
     with open(path, "w") as f:
@@ -97,7 +110,15 @@ def main():
         dict(name="g2_vb_101_meta", data="g2", method="vb", dim="1,0,1", iters=8, seed=19, meta=True),
         dict(name="g3_vb_114", data="g3", method="vb", dim="1,1,4", iters=12, seed=23),
     ]
-    for out_name, case_list in (("golden.json", cases), ("golden_extra.json", extra_cases)):
+    # third set: binary classification (-task c, mcmc / als only), CPU oracle test + GPU parity test
+    write_two_field_binary(os.path.join(HERE, "g4_train.libfm"), 2500, 80, 60, 41)
+    write_two_field_binary(os.path.join(HERE, "g4_test.libfm"), 400, 80, 60, 42, zero_for_negative=True)
+    class_cases = [
+        dict(name="g4_mcmc_c_113", data="g4", method="mcmc", dim="1,1,3", iters=10, seed=42, task="c"),
+        dict(name="g4_als_c_112", data="g4", method="als", dim="1,1,2", iters=8, seed=7, task="c", extra=["-regular", "0.1,0.5,1"]),
+        dict(name="g4_mcmc_c_012", data="g4", method="mcmc", dim="0,1,2", iters=6, seed=9, task="c"),
+    ]
+    for out_name, case_list in (("golden.json", cases), ("golden_extra.json", extra_cases), ("golden_class.json", class_cases)):
         run_cases(case_list, out_name)
     write_formats()
 
@@ -108,7 +129,7 @@ def run_cases(cases, out_name):
         with tempfile.TemporaryDirectory() as td:
             for s in ("train", "test"):
                 shutil.copy(os.path.join(HERE, f"{c['data']}_{s}.libfm"), os.path.join(td, s))
-            args = ["-task", "r", "-train", "train", "-test", "test", "-dim", c["dim"], "-method", c["method"], "-iter", str(c["iters"])]
+            args = ["-task", c.get("task", "r"), "-train", "train", "-test", "test", "-dim", c["dim"], "-method", c["method"], "-iter", str(c["iters"])]
             if c.get("meta"):
                 shutil.copy(os.path.join(HERE, "g2_meta.txt"), os.path.join(td, "meta"))
                 args += ["-meta", "meta"]
@@ -121,6 +142,12 @@ def run_cases(cases, out_name):
             rec["test_rmse"] = read_floats(os.path.join(td, f"test_rmse_{tag}_{m}"))
             rec["neg_free_energy"] = read_floats(os.path.join(td, f"free_energy_{tag}_vb"))   # vb_online also appends here (vbo.h:637)
             rec["train_stat"] = [float(l.split("Train=")[1].split("\t")[0]) for l in out.splitlines() if l.startswith("#Iter=") and "Train=" in l]
+            if c.get("task") == "c":     # nothing is appended to test_rmse_* for classification (mcmcs.h:262-275): the accuracies are on stdout only
+                rec["test_acc"] = [float(l.split("Test=")[1].split("\t")[0]) for l in out.splitlines() if l.startswith("#Iter=") and "Test=" in l]
+                assert len(rec["test_acc"]) == c["iters"] and not rec["test_rmse"], (c["name"], out[-2000:])
+                golden["cases"].append(rec)
+                print(c["name"], rec["train_stat"][-1], rec["test_acc"][-1])
+                continue
             assert len(rec["test_rmse"]) == c["iters"], (c["name"], rec["test_rmse"], out[-2000:])
             golden["cases"].append(rec)
             print(c["name"], rec["test_rmse"][-1], rec["neg_free_energy"][-1:] )

@@ -84,3 +84,25 @@ def test_sa_fixture_when_reference_present():
         s = orc.iterate()
         assert abs(s.test_rmse - want[it]) <= TOL * want[it]
         assert abs(-s.free_energy - want_fe[it]) <= TOL * abs(want_fe[it])
+
+
+GOLD_CLASS = json.load(open(os.path.join(G, "golden_class.json")))["cases"]
+
+
+def load_class_case(c):
+    tr, te, method, k0, k1, K, kw = load_case(c)
+    for s in (tr, te):          # libfm.cpp:339-340: every target <= 0 becomes -1, the others +1
+        s.y[:] = np.where(s.y <= 0.0, -1.0, 1.0).astype(np.float32)
+    return tr, te, method, k0, k1, K, kw
+
+
+@pytest.mark.parametrize("c", GOLD_CLASS, ids=[c["name"] for c in GOLD_CLASS])
+def test_oracle_classification_matches_reference_binary(c):
+    """-task c (mcmc / als): train and test accuracy per iteration as the unmodified reference binary prints them, including
+    the truncated-normal target draws on the libc stream (util/random.h:72-114) and the reference's own erf."""
+    tr, te, method, k0, k1, K, kw = load_class_case(c)
+    orc = ob.Oracle(method, tr, te, K=K, k0=k0, k1=k1, seed=c["seed"], task=1, **kw)
+    for it in range(c["iters"]):
+        s = orc.iterate()
+        assert abs(s.train_stat - c["train_stat"][it]) <= TOL * c["train_stat"][it], (it, s.train_stat, c["train_stat"][it])
+        assert abs(s.test_rmse - c["test_acc"][it]) <= TOL * c["test_acc"][it], (it, s.test_rmse, c["test_acc"][it])
