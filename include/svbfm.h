@@ -45,7 +45,11 @@ typedef struct svbfm_config {
     uint32_t num_attribute;    /* D  = fm.num_attribute (libfm.cpp:215,261) */
     int32_t  num_factor;       /* K  = fm.num_factor   (libfm.cpp:270) */
     int32_t  k0, k1;           /* fm.k0, fm.k1         (libfm.cpp:268-269) */
-    int32_t  task;             /* 0 = regression (only task on this path; classification is out of scope) */
+    int32_t  task;             /* 0 = regression; 1 = binary classification (fm_learn.h:67-68), SVBFM_MCMC only: targets are -1 / +1
+                                * (the caller maps them like libfm.cpp:337-343); the iteration statistics then carry accuracies:
+                                * train_stat = "Train=", test_rmse = "Test=" (running mean), rmse_this = acc_mcmc_this
+                                * (fm_learn_mcmc_simultaneous.h:176-221, 262-275); svbfm_predict returns probabilities in [0, 1].
+                                * SVBFM_FLAG_MCMC_NO_REPREDICT is ignored (e = yhat - latent target). MAP@k is not computed. */
     double   min_target;       /* fml->min_target / max_target: taken from TRAIN (libfm.cpp:332-333) */
     double   max_target;
     int32_t  device;           /* CUDA device ordinal */

@@ -1031,7 +1031,8 @@ int orc_get_test_pred(orc_t *h, double *p) {
     if (h->method == ORC_MCMC) {                                     /* mcmc.h:355-379: running mean, clamped */
         for (uint32_t c = 0; c < h->sp[1].n_cases; c++) {
             double v = h->pred_sum_all[c] / (h->iter ? h->iter : 1);
-            v = fmin(h->max_target, v); v = fmax(h->min_target, v);
+            if (h->task == 1) { v = fmin(1.0, v); v = fmax(0.0, v); }     /* mcmc.h:372-374 */
+            else { v = fmin(h->max_target, v); v = fmax(h->min_target, v); }
             p[c] = v;
         }
     } else memcpy(p, h->pred_this, h->sp[1].n_cases * sizeof(double));

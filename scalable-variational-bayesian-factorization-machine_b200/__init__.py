@@ -153,9 +153,9 @@ class Engine:
     """Thin RAII wrapper of one C-ABI handle."""
 
     def __init__(self, method, num_attribute, num_factor, k0=1, k1=1, min_target=0.0, max_target=0.0, device=0,
-                 seed=42, do_sample=True, do_multilevel=True, reg=(0.0, 0.0, 0.0), tile_entries=0, flags=0):
+                 seed=42, do_sample=True, do_multilevel=True, reg=(0.0, 0.0, 0.0), tile_entries=0, flags=0, task=0):
         self.method = METHODS[method] if isinstance(method, str) else int(method)
-        cfg = Config(C.sizeof(Config), self.method, int(num_attribute), int(num_factor), int(bool(k0)), int(bool(k1)), 0,
+        cfg = Config(C.sizeof(Config), self.method, int(num_attribute), int(num_factor), int(bool(k0)), int(bool(k1)), int(task),
                      float(min_target), float(max_target), int(device), int(do_sample), int(do_multilevel), int(seed),
                      float(reg[0]), float(reg[1]), float(reg[2]), int(tile_entries), int(flags))
         self.D, self.K, self.G = int(num_attribute), int(num_factor), 1
@@ -312,8 +312,10 @@ class FmLearn:
         self.comm = None                # (unique_id, rank, world_size)
 
     def init(self):
-        if self.task != 0:
-            raise SvbfmError("unknown task")         # only regression is on this path
+        if self.task not in (0, 1):
+            raise SvbfmError("unknown task")         # fm_learn.h:87, 111
+        if self.task == 1 and self.method != "mcmc":
+            raise SvbfmError("classification (task 1) is on the CUDA path for mcmc / als only")
         m = METHODS[self.method]
         self._state = host_init_state(self.seed, self.fm.num_attribute, self.fm.num_factor, self.fm.init_stdev, m)
 
@@ -321,7 +323,7 @@ class FmLearn:
         fm = self.fm
         self.engine = Engine(self.method, fm.num_attribute, fm.num_factor, fm.k0, fm.k1, self.min_target, self.max_target,
                              device=self.device, seed=self.seed, reg=(fm.reg0, fm.regw, fm.regv), flags=self.flags,
-                             tile_entries=self.tile_entries, **kw)
+                             tile_entries=self.tile_entries, task=self.task, **kw)
         if self.comm is not None:
             self.engine.comm_init(*self.comm)
         if self.attr_group is not None:
@@ -347,7 +349,10 @@ class FmLearnVB(FmLearn):
 
 
 class FmLearnMCMC(FmLearn):
-    """fm_learn_mcmc_simultaneous (fm_learn_mcmc_simultaneous.h:47-305)."""
+    """fm_learn_mcmc_simultaneous (fm_learn_mcmc_simultaneous.h:47-305). task = 1: binary classification; the caller maps the
+    targets to -1 / +1 first, as the reference's main() does (libfm.cpp:337-343). The iteration statistics then hold accuracies:
+    train_stat = "Train=", test_rmse = "Test=" (running mean), rmse_this = acc_mcmc_this; MAP@k needs the reference's
+    hard-coded side file (fm_learn.h:124) and is not computed."""
     method = "mcmc"
 
     def __init__(self):

@@ -592,7 +592,18 @@ static int mcmc_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
     }
     if (ev) cudaEventRecord(ev->t1, st);
     // re-prediction of train and test (mcmcs.h:134-174)
-    if (E->cfg.flags & SVBFM_FLAG_MCMC_NO_REPREDICT) {
+    const bool classify = E->cfg.task == 1;
+    if (classify) {
+        // classification: e = yhat - latent target, so yhat cannot be recovered from e: always re-predict (the NO_REPREDICT flag
+        // is ignored), then train accuracy + new latent targets in one more streaming pass (mcmcs.h:188-221)
+        if (int rc = predict_train<PRED_MC_TRAIN>(E, 5)) return rc;
+        unsigned grid = std::max(1u, std::min<unsigned>(nblk(E->tr.n), SV_RGRID));
+        k_mc_class_targets<<<grid, 256, 0, st>>>(E->d_e, E->tr.y, E->tr.perm, E->tr.n, E->cfg.seed, (uint32_t)E->rank, E->cfg.do_sample, E->d_sc,
+                                                 E->d_red_partial); LAUNCHED(E);
+        k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, grid, 1, RED(E->d_sc, 5), 0); LAUNCHED(E);
+        if (int rc = allreduce_sum_f64(E, RED(E->d_sc, 5), 1)) return rc;
+        sync_e2(E);
+    } else if (E->cfg.flags & SVBFM_FLAG_MCMC_NO_REPREDICT) {
         unsigned grid = std::max(1u, std::min<unsigned>(nblk(E->tr.n), SV_RGRID));
         k_train_sse_from_e<<<grid, 256, 0, st>>>(E->d_e, E->tr.y, E->tr.n, E->d_sc, E->d_red_partial); LAUNCHED(E);
         k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, grid, 4, E->d_red_partial + SCR_FINAL, 0); LAUNCHED(E);
@@ -602,8 +613,9 @@ static int mcmc_iteration(Engine* E, uint32_t slot, IterEvents* ev) {
         if (int rc = predict_train<PRED_MC_TRAIN>(E, 5)) return rc;
         sync_e2(E);
     }
-    if (int rc = predict<PRED_MC_TEST>(E, E->te, nullptr, 3, 2)) return rc;
-    k_finish_iter<<<1, 1, 0, st>>>(E->d_sc, stp, SVBFM_MCMC); LAUNCHED(E);
+    if (classify) { if (int rc = predict<PRED_MC_TEST_CLASS>(E, E->te, nullptr, 3, 2)) return rc; }
+    else if (int rc = predict<PRED_MC_TEST>(E, E->te, nullptr, 3, 2)) return rc;
+    k_finish_iter<<<1, 1, 0, st>>>(E->d_sc, stp, SVBFM_MCMC, E->cfg.task); LAUNCHED(E);
     if (ev) cudaEventRecord(ev->t2, st);
     return check_launch(E, "mcmc_iteration");
 }
@@ -662,7 +674,10 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     *out = nullptr;
     if (cfg->struct_size != sizeof(svbfm_config)) { g_create_error = "svbfm_create: struct_size mismatch (ABI)"; return SVBFM_ERR_ARG; }
     if (cfg->method < SVBFM_VB || cfg->method > SVBFM_MCMC) { g_create_error = "svbfm_create: unknown method"; return SVBFM_ERR_ARG; }
-    if (cfg->task != 0) { g_create_error = "svbfm_create: only regression (task 0) is implemented on this path"; return SVBFM_ERR_ARG; }
+    if (cfg->task != 0 && !(cfg->task == 1 && cfg->method == SVBFM_MCMC)) {
+        g_create_error = "svbfm_create: task 0 (regression), or task 1 (binary classification, targets -1 / +1) with the mcmc method";
+        return SVBFM_ERR_ARG;
+    }
     if (cfg->num_factor < 0 || cfg->num_attribute == 0) { g_create_error = "svbfm_create: bad dimensions"; return SVBFM_ERR_ARG; }
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -1156,7 +1171,8 @@ int svbfm_predict(svbfm_t* h, int32_t split, double* out) {
         Scalars sc;
         SV_CUDA(E, copy_sync(E, &sc, E->d_sc, sizeof(sc), cudaMemcpyDeviceToHost));
         double it = sc.iter ? (double)sc.iter : 1.0;
-        for (size_t i = 0; i < n; i++) out[i] = std::fmax(sc.min_target, std::fmin(sc.max_target, s[i] / it));   // mcmc.h:355-379
+        const double lo = E->cfg.task == 1 ? 0.0 : sc.min_target, hi = E->cfg.task == 1 ? 1.0 : sc.max_target;    // classification: a probability
+        for (size_t i = 0; i < n; i++) out[i] = std::fmax(lo, std::fmin(hi, s[i] / it));   // mcmc.h:355-379
     } else {
         SV_CUDA(E, copy_sync(E, out, E->d_pred_test, n * 8, cudaMemcpyDeviceToHost));
     }

@@ -1114,7 +1114,17 @@ __global__ void k_xchg_unpack(BlockXchg b, const double2* __restrict__ recv) {
 // ---------------------------------------------------------------------------------------------------------
 // case-wise prediction (replaces the 2K+1 CSC scatter passes of predict_data_and_write_to_eterms,
 // fm_learn_vb.h:70-203 / fm_learn_mcmc.h:117-348, and of predict_t_and_write_to_qterms, vb.h:207-312)
-enum { PRED_VB_TRAIN = 0, PRED_VB_TEST = 1, PRED_MC_TRAIN = 2, PRED_MC_TEST = 3 };
+enum { PRED_VB_TRAIN = 0, PRED_VB_TEST = 1, PRED_MC_TRAIN = 2, PRED_MC_TEST = 3, PRED_MC_TEST_CLASS = 4 };
+
+// ---- binary classification (-task c, mcmc / als): the reference's own erf approximation (Abramowitz-Stegun 7.1.26,
+// util/random.h:47-61) and probit link (random.h:67-69), restated so that the deterministic (als) path agrees to rounding
+__device__ __forceinline__ double ref_erf(double x) {
+    double t = (x >= 0) ? 1.0 / (1.0 + 0.3275911 * x) : 1.0 / (1.0 - 0.3275911 * x);
+    double result = 1.0 - (t * (0.254829592 + t * (-0.284496736 + t * (1.421413741 + t * (-1.453152027 + t * 1.061405429))))) * exp(-x * x);
+    return (x >= 0) ? result : -result;
+}
+__device__ __forceinline__ double ref_cdf_gaussian(double x) { return 0.5 + 0.5 * ref_erf(0.707106781 * x); }
+__device__ __forceinline__ bool class_hit(double p, double y) { return ((p >= 0.5) && (y > 0.0)) || ((p < 0.5) && (y < 0.0)); }   // mcmcs.h:193, 333
 
 struct PredictArgs {
     RowView rv;
@@ -1203,6 +1213,13 @@ __global__ void __launch_bounds__(256) k_predict(PredictArgs a) {
             double err = p - y;
             acc[0] += err * err;
             a.e[i] = yhat - y;                                  // mcmcs.h:172
+        } else if constexpr (MODE == PRED_MC_TEST_CLASS) {
+            double p = ref_cdf_gaussian(yhat);                  // mcmcs.h:178-180
+            a.pred[i] = p;
+            double s = a.pred_sum[i] + p;                       // mcmcs.h:181
+            a.pred_sum[i] = s;
+            if (class_hit(p, y)) acc[0] += 1.0;                 // acc_mcmc_this (_evaluate_class, mcmcs.h:379-397)
+            if (class_hit(s * inv_it, y)) acc[1] += 1.0;        // acc_mcmc_all  (_evaluate_class_map without the MAP part, mcmcs.h:331-338)
         } else {
             a.pred[i] = yhat;                                   // mcmcs.h:156
             double p = fmax(lo, fmin(hi, yhat));
@@ -1354,6 +1371,54 @@ __global__ void __launch_bounds__(256) k_train_sse_from_e(const double* __restri
     block_sum<4>(acc, sm);
     if (threadIdx.x == 0)
         for (int k = 0; k < 4; k++) partial[blockIdx.x * 4 + k] = acc[k];
+}
+
+// classification, after the re-prediction of train (e = yhat - y with y = -1 / +1): train accuracy, then the new latent
+// target of every case -- a draw from the normal around yhat truncated to the side of the class (or, without sampling, its
+// expected value) -- and e = yhat - target (mcmcs.h:188-221). Draws: Philox keyed by (seed, iteration, caller case id, rank),
+// so they do not depend on the device case order.
+struct CaseRng {
+    uint64_t seed; uint32_t id, iter, salt, n;
+    __device__ double uniform() { uint4 r = philox4x32_10(make_uint4(n++, id, iter, salt), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))); return u01(r.x, r.y); }
+    __device__ double normal() { return philox_normal(seed, n++, id, iter, salt ^ 0x00010000u); }
+    // standard normal truncated to [left, inf) (util/random.h:72-102: naive rejection for left <= 0, Robert's translated exponential else)
+    __device__ double left_tgaussian(double left) {
+        if (left <= 0.0) {
+            double r;
+            do { r = normal(); } while (r < left);
+            return r;
+        }
+        const double alpha_star = 0.5 * (left + sqrt(left * left + 4.0));
+        while (true) {
+            double z = -log(1.0 - uniform()) / alpha_star + left;
+            double d = z - alpha_star;
+            d = exp(-(d * d) / 2);
+            if (uniform() < d) return z;
+        }
+    }
+};
+__global__ void __launch_bounds__(256) k_mc_class_targets(double* __restrict__ e, const float* __restrict__ y, const uint32_t* __restrict__ perm, uint32_t n,
+                                                          uint64_t seed, uint32_t rank, int do_sample, const Scalars* sc, double* __restrict__ partial) {
+    __shared__ double sm[32];
+    double acc[1] = {0.0};
+    const uint32_t iter = sc->iter;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double yy = (double)y[i];
+        const double mu = e[i] + yy;                               // yhat
+        if (class_hit(ref_cdf_gaussian(mu), yy)) acc[0] += 1.0;    // mcmcs.h:191-195
+        double r;                                                  // e = yhat - target
+        if (do_sample) {
+            CaseRng rng{seed, perm ? perm[i] : i, iter, 0x5eed0004u ^ (rank << 20), 0u};
+            r = (yy >= 0.0) ? -rng.left_tgaussian(-mu) : rng.left_tgaussian(mu);   // random.h:104-114 with mean mu, stdev 1
+        } else {
+            double phi_minus_mu = exp(-mu * mu / 2.0) / sqrt(3.141 * 2);            // 3.141: the reference's pi (mcmcs.h:203, 213)
+            double Phi_minus_mu = ref_cdf_gaussian(-mu);
+            r = (yy >= 0.0) ? -(phi_minus_mu / (1 - Phi_minus_mu)) : phi_minus_mu / Phi_minus_mu;
+        }
+        e[i] = r;
+    }
+    block_sum<1>(acc, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc[0];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1625,9 +1690,14 @@ __global__ void k_nat_from_params(const double2* __restrict__ p, size_t n, doubl
 
 // end of an iteration: evaluation numbers -> stats slot. red[3] = test sse (this), red[4] = test sse (running mean),
 // red[5] = train sse (mcmc)
-__global__ void k_finish_iter(Scalars* sc, DevStats* st, int method) {
+__global__ void k_finish_iter(Scalars* sc, DevStats* st, int method, int task = 0) {
     double nt = sc->nt_total, N = sc->n_total;
-    if (method == SVBFM_MCMC) {
+    if (method == SVBFM_MCMC && task == 1) {     // classification: accuracies instead of RMSEs (mcmcs.h:262-275)
+        st->rmse_this = sc->red[3] / nt;         // acc_mcmc_this
+        st->test_rmse = sc->red[4] / nt;         // "Test=" (accuracy of the running mean)
+        st->train_stat = sc->red[5] / N;         // "Train="
+        st->alpha = sc->alpha; st->has_fe = 0.0; st->free_energy = 0.0;
+    } else if (method == SVBFM_MCMC) {
         st->rmse_this = sqrt(sc->red[3] / nt);
         st->test_rmse = sqrt(sc->red[4] / nt);
         st->train_stat = sqrt(sc->red[5] / N);

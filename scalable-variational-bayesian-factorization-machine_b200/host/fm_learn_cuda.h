@@ -44,7 +44,7 @@ public:
     MetaInfo* meta = nullptr;
     fm_model* fm = nullptr;
     double min_target = 0, max_target = 0;
-    int task = 0;                    // 0 = regression, 1 = classification (not on this path)
+    int task = 0;                    // 0 = regression, 1 = binary classification (mcmc / als only on this path; targets -1 / +1)
     DataSet* validation = nullptr;
     RLog* log = nullptr;
     unsigned num_iter = 100, num_eval_cases = 0;
@@ -80,7 +80,8 @@ public:
 
     void init() override {
         fm_learn::init();
-        if (task != 0) throw std::string("task not supported on the CUDA path (regression only)");
+        if (task != 0 && !(task == 1 && method == SVBFM_MCMC))
+            throw std::string("task not supported on the CUDA path (regression; binary classification with mcmc / als)");
         init_state(seed, fm->num_attribute, fm->num_factor, fm->init_stdev, method, state_);   // host/init_state.h
         if (log) {                   // fm_learn_vb::init / fm_learn_mcmc::init log fields (vb.h:714-742, mcmc.h:1120-1150)
             log->addField("alpha", nan_());
@@ -120,7 +121,7 @@ protected:
         svbfm_config c;
         memset(&c, 0, sizeof(c));
         c.struct_size = sizeof(c); c.method = method; c.num_attribute = fm->num_attribute; c.num_factor = fm->num_factor;
-        c.k0 = fm->k0; c.k1 = fm->k1; c.task = 0; c.min_target = min_target; c.max_target = max_target; c.device = device;
+        c.k0 = fm->k0; c.k1 = fm->k1; c.task = task; c.min_target = min_target; c.max_target = max_target; c.device = device;
         c.do_sample = do_sample; c.do_multilevel = do_multilevel; c.seed = (uint64_t)seed; c.reg0 = fm->reg0; c.regw = fm->regw; c.regv = fm->regv;
         int rc = svbfm_create(&h_, &c);
         if (rc != 0) throw std::string("svbfm_create: ") + svbfm_last_error(nullptr);
@@ -202,6 +203,21 @@ public:
             svbfm_iter_stats s;
             ck(svbfm_mcmc_sweep(h_, &s), "svbfm_mcmc_sweep");
             if (s.nan_inf_count > 0 && root()) std::cout << "#nans/infs reverted:\t" << s.nan_inf_count << std::endl;
+            if (task == 1) {
+                // classification: accuracies on stdout only, nothing goes to test_rmse_* (mcmcs.h:262-275). MAP@5 comes from a side
+                // file with a hard-coded path (fm_learn.h:124); without that file the reference prints 0, and so does this line.
+                if (root())
+                    std::cout << "#Iter=" << std::setw(3) << i << "\tTrain=" << s.train_stat << "\tTest=" << s.test_rmse << "\tMAP@5= " << 0 << std::endl;
+                if (log && root()) {
+                    log->log("time_learn", user_time() - t0);
+                    log->log("time_learn2", (double)(clock() - c0) / CLOCKS_PER_SEC);
+                    log->log("time_learn4", (double)(time(nullptr) - w0));
+                    log->log("alpha", s.alpha);
+                    log->log("accuracy", s.test_rmse);
+                    log->newLine();
+                }
+                continue;
+            }
             if (root())
                 std::cout << "#Iter=" << std::setw(3) << i << "\tTrain=" << s.train_stat << "\tTest=" << s.test_rmse << std::endl;   // mcmcs.h:244
             append_value("test_rmse_" + tag_ + "_mcmc", s.test_rmse);                                  // mcmcs.h:245

@@ -169,7 +169,12 @@ int main(int argc, char** argv) {
         fml->seed = seed; fml->device = device; fml->shard = sh;
         const std::string task = cmd.get(p_task);
         if (task == "r") fml->task = 0;
-        else if (task == "c") throw std::string("classification (-task c) is out of scope of the CUDA path");
+        else if (task == "c") {                                   // libfm.cpp:337-343: every target <= 0 becomes -1, the others +1
+            if (method != "mcmc") throw std::string("classification (-task c) is on the CUDA path for -method mcmc / als only");
+            fml->task = 1;
+            for (float& t : train.target) t = (t <= 0.0f) ? -1.0f : 1.0f;
+            for (float& t : test.target) t = (t <= 0.0f) ? -1.0f : 1.0f;
+        }
         else throw std::string("unknown task");
         {                                                         // regularisation (libfm.cpp:367-427)
             std::vector<double> reg = cmd.get_doubles(p_reg);

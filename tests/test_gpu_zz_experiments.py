@@ -98,3 +98,97 @@ def test_stream_tma_ring(built, monkeypatch, tile_entries, n):
         assert rel(s.test_rmse, o.test_rmse) < VB_TOL and rel(s.train_stat, o.train_stat) < VB_TOL
     assert L.engine.copies_max_diff() == 0.0
     L.engine.close()
+
+
+# ---- binary classification (-task c) for mcmc / als: SURVEY section 8(f) rank 4. Built and emulator-checked without a GPU.
+def _binary_two_field(n, nt, U, I, seed, values=False):
+    tr, te = two_field(n, nt, U, I, seed=seed, values=values)
+    for s in (tr, te):
+        s.y[:] = np.where(s.y >= 4, 1.0, -1.0).astype(np.float32)     # libfm.cpp:339-340 maps to -1 / +1
+    return tr, te
+
+
+@pytest.mark.parametrize("values,tile_entries", [(False, 0), (True, 64)])
+def test_classification_als_equals_oracle(built, values, tile_entries):
+    """do_sample = 0: the latent targets are the expected values of the truncated normals (mcmcs.h:199-216): deterministic,
+    so accuracies, residuals (yhat - latent target) and the averaged test probabilities equal the oracle's."""
+    tr, te = _binary_two_field(12000, 1500, 200, 150, seed=51, values=values)
+    orc = ob.Oracle("mcmc", tr, te, K=3, seed=42, do_sample=False, do_multilevel=False, reg=(0.0, 0.5, 1.0), task=1)
+    L = make_learner("mcmc", tr, te, 3, num_iter=6, do_sample=False, do_multilevel=False, tile_entries=tile_entries, task=1)
+    L.fm.reg0, L.fm.regw, L.fm.regv = 0.0, 0.5, 1.0
+    for it, s in enumerate(L.learn(to_csc(tr), to_csc(te))):
+        o = orc.iterate()
+        assert abs(s.train_stat - o.train_stat) < 2.0 / tr.n_rows, (it, s.train_stat, o.train_stat)     # at most a borderline case or two
+        assert abs(s.test_rmse - o.test_rmse) < 2.0 / te.n_rows and abs(s.rmse_this - o.rmse_this) < 2.0 / te.n_rows
+    e_o, _ = orc.get_train_cache(want_t=False)
+    assert np.max(np.abs(L.engine.get_residuals() - e_o)) < 1e-6
+    assert np.max(np.abs(L.engine.predict() - orc.get_test_pred())) < 1e-6
+    if not values:
+        assert L.engine.info()["fused_schedule"] & 1 and L.engine.copies_max_diff() == 0.0
+    L.engine.close()
+
+
+def test_classification_golden_als(built):
+    """The als run of the reference binary on tests/golden/g4_* (-task c): same accuracies as printed by the reference."""
+    import json
+    import os
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    c = [c for c in json.load(open(os.path.join(G, "golden_class.json")))["cases"] if c["name"] == "g4_als_c_112"][0]
+    tr, te = ob.parse_text(os.path.join(G, "g4_train.libfm")), ob.parse_text(os.path.join(G, "g4_test.libfm"))
+    lo, hi = float(tr.y.min()), float(tr.y.max())
+    for s in (tr, te):
+        s.y[:] = np.where(s.y <= 0.0, -1.0, 1.0).astype(np.float32)
+    reg = [float(x) for x in c["extra"][1].split(",")]
+    L = make_learner("mcmc", tr, te, 2, seed=c["seed"], num_iter=c["iters"], do_sample=False, do_multilevel=False, task=1)
+    L.min_target, L.max_target = lo, hi
+    L.fm.reg0, L.fm.regw, L.fm.regv = reg
+    for it, s in enumerate(L.learn(to_csc(tr), to_csc(te))):
+        assert abs(s.train_stat - c["train_stat"][it]) < 1e-5 + 1.0 / tr.n_rows, (it, s.train_stat, c["train_stat"][it])
+        assert abs(s.test_rmse - c["test_acc"][it]) < 1e-5 + 1.0 / te.n_rows, (it, s.test_rmse, c["test_acc"][it])
+    L.engine.close()
+
+
+def test_classification_sampling_distribution(built):
+    """do_sample = 1: Philox draws instead of the libc stream, so only the distribution can match: train / test accuracy of
+    the running mean after 12 sweeps within 2 points of the mean over three oracle seeds."""
+    tr, te = _binary_two_field(20000, 4000, 150, 100, seed=52)
+    want_tr, want_te = [], []
+    for seed in (1, 2, 3):
+        orc = ob.Oracle("mcmc", tr, te, K=3, seed=seed, task=1)
+        for _ in range(12):
+            o = orc.iterate()
+        want_tr.append(o.train_stat); want_te.append(o.test_rmse)
+    L = make_learner("mcmc", tr, te, 3, num_iter=12, task=1)
+    s = L.learn(to_csc(tr), to_csc(te))[-1]
+    assert abs(s.train_stat - np.mean(want_tr)) < 0.02, (s.train_stat, want_tr)
+    assert abs(s.test_rmse - np.mean(want_te)) < 0.02, (s.test_rmse, want_te)
+    assert 0.5 < s.test_rmse <= 1.0
+    p = L.engine.predict()
+    assert p.min() >= 0.0 and p.max() <= 1.0
+    L.engine.close()
+
+
+def test_cli_classification_reproduces_reference_stdout(built, tmp_path):
+    """libFM-compatible CLI with -task c -method als on tests/golden/g4_*: the '#Iter= .. Train= .. Test= .. MAP@5= 0' lines of
+    the unmodified reference binary (nothing is written to test_rmse_* for classification), and -out probabilities in [0, 1]."""
+    import json
+    import os
+    import shutil
+    import subprocess
+    import svbfm_b200 as sv
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    c = [c for c in json.load(open(os.path.join(G, "golden_class.json")))["cases"] if c["name"] == "g4_als_c_112"][0]
+    for s in ("train", "test"):
+        shutil.copy(os.path.join(G, f"g4_{s}.libfm"), tmp_path / s)
+    args = [os.path.join(sv.PKG_DIR, "bin", "libFM"), "-task", "c", "-train", "train", "-test", "test", "-dim", c["dim"], "-method", "als",
+            "-iter", str(c["iters"]), "-seed", str(c["seed"]), "-out", "pred.txt"] + c["extra"]
+    p = subprocess.run(args, cwd=tmp_path, capture_output=True, text=True)
+    assert "ERROR" not in p.stderr, p.stderr
+    lines = [l for l in p.stdout.splitlines() if l.startswith("#Iter=")]
+    assert len(lines) == c["iters"] and all(l.endswith("MAP@5= 0") for l in lines)
+    for it, l in enumerate(lines):
+        tr_acc, te_acc = float(l.split("Train=")[1].split("\t")[0]), float(l.split("Test=")[1].split("\t")[0])
+        assert abs(tr_acc - c["train_stat"][it]) < 1e-4 + 1.0 / 2500 and abs(te_acc - c["test_acc"][it]) < 1e-4 + 1.0 / 400, (it, l)
+    assert open(tmp_path / "test_rmse_112_mcmc").read() == ""
+    pred = [float(x) for x in open(tmp_path / "pred.txt").read().split()]
+    assert len(pred) == 400 and min(pred) >= 0.0 and max(pred) <= 1.0
