@@ -39,3 +39,24 @@ def test_parity_subset_on_the_emulator(emu_lib):
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
+
+
+def test_two_ranks_on_the_emulator(emu_lib, tmp_path):
+    """The sharded launch order (allreduce of the column sums, exclusive user blocks + block exchange, agreement on the schedule,
+    sharded vb_online) with two PROCESSES: the host build of the kernels + tests/emu/fake_nccl.c (the nine NCCL entry points the
+    engine binds, over shared memory). Same cases as the 2-GPU test (tests/mgpu_worker.py); rank 0 compares with the oracle."""
+    build_dir = os.path.dirname(emu_lib)
+    env = dict(os.environ, SVBFM_LIB=emu_lib, LD_LIBRARY_PATH=build_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    worker = os.path.join(ROOT, "tests", "emu", "mrank_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(tmp_path)], env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = []
+    for p in procs:
+        try:
+            outs.append(p.communicate(timeout=900)[0])
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[-2000:] for o in outs)
+    assert "MRANK_OK" in outs[0], outs[0][-3000:]
