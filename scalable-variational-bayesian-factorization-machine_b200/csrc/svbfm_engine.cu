@@ -203,6 +203,12 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
     if (rp && rp->run >= 0 && E->bv.on) {        // one vb_online batch: its own column pointer; any span is summed in k_finalize_vbo
         sp.colptr = E->bv.colptr[rp->run]; sp.entry0 = E->bv.entry0; sp.light_limit = ~0u; sp.ts_shift = E->vbo_ts_shift;
         partial = E->d_vbo_partial + (rp->run ? (size_t)E->vbo_max_tiles * 8 : 0);
+        if (E->world > 1) {       // sharded: complete local sums of every column -> {A, B} through the allreduce (C1, C2 stay local)
+            k_combine_light_span<KIND == KIND_VBO_V><<<nblk(ncols), 256, 0, st>>>(r.col_begin, r.col_end, sp, partial, E->d_colsum, E->d_ab); LAUNCHED(E);
+            ProfScope pc(E, 10);
+            if (int rc = allreduce_sum_f64(E, reinterpret_cast<double*>(E->d_ab + r.col_begin), (size_t)ncols * 2)) return rc;
+            from_colsum = true; use_ab = true;
+        }
     } else if (rp && rp->run >= 0) {
         sp.colptr = E->tr.colptr; sp.entry0 = E->tr.h_colptr[r.col_begin];
         partial = E->d_partial + (rp->run ? (size_t)E->s_ntiles[0] * 8 : 0);
@@ -236,6 +242,7 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
     fa.span = sp; fa.ab = use_ab ? E->d_ab : nullptr;
     if (rp) { fa.cpack = E->d_cpack; fa.opack = E->d_opack; fa.rec_mode = rp->rec_mode; fa.p_next = rp->p_next; fa.p_prev = rp->p_prev; }
     fa.rec_slot = E->rec_rank ? E->d_rec_slot : nullptr;
+    if (rp && rp->run >= 0 && E->bv.on) fa.gcnt = E->bv.gcnt[rp->run];
     if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V) {
         fa.nat = IS_V ? E->d_nat_v + (size_t)f * E->D : E->d_nat_w;
         fa.t_cnt = IS_V ? E->d_t_v : E->d_t_w;
@@ -758,7 +765,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_gcnt[0], E->d_vbo_gcnt[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) sv_free(p);
     cudaStreamSynchronize(E->stream);
     if (E->copy_stream) { cudaStreamSynchronize(E->copy_stream); cudaStreamDestroy(E->copy_stream); }
@@ -1097,11 +1104,12 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
         // (E->bv) instead of masking the whole arrays; SVBFM_VBO_FULL_PASSES=1 keeps the masked passes (for comparison)
         const bool full_passes = getenv("SVBFM_VBO_FULL_PASSES") != nullptr;
         struct BvGuard { Engine* E; ~BvGuard() { E->bv.on = false; } } bv_guard{E};      // every exit leaves the whole-run views in force
-        if (use_streams && nb_cases) { E->bv.on = true; E->bv.lists = !full_passes; E->bv.entry0 = E->vbo_off[b]; E->bv.n = nb_cases; }
+        const bool batch_streams = use_streams && (nb_cases || E->world > 1);      // sharded: a rank without cases in the batch still takes part in the collectives
+        if (batch_streams) { E->bv.on = true; E->bv.lists = !full_passes; E->bv.entry0 = E->vbo_off[b]; E->bv.n = nb_cases; }
         // fresh y-hat, T for the cases of the batch (vbos.h:120-127)
         if (int rc = predict<PRED_VB_TRAIN>(E, S, E->d_e, 6, 1, (int)b)) return rc;
         SV_CUDA(E, cudaMemcpyAsync(&E->d_sc->sum_t, RED(E->d_sc, 6), 8, cudaMemcpyDeviceToDevice, st));
-        if (use_streams && nb_cases) {
+        if (batch_streams) {
             const Run &r0 = E->runs[0], &r1 = E->runs[1];
             E->bv.ntiles = (uint32_t)(((uint64_t)nb_cases + (1ull << E->vbo_ts_shift) - 1) >> E->vbo_ts_shift);
             for (int ri = 0; ri < 2; ri++) {
@@ -1109,12 +1117,17 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
                 const uint32_t nc = r.col_end - r.col_begin;
                 // view indexed by global column id: view[j] = first position in idx of column j of batch b
                 E->bv.colptr[ri] = reinterpret_cast<const uint64_t*>(E->d_vbo_colptr[ri]) + (size_t)b * nc - r.col_begin;
-                k_tile_col0<<<nblk(E->bv.ntiles), 256, 0, st>>>(E->bv.colptr[ri], r.col_begin, r.col_end, E->bv.ntiles, E->vbo_ts_shift,
-                                                               E->d_vbo_tile_col0 + (ri ? E->vbo_max_tiles : 0)); LAUNCHED(E);
+                E->bv.gcnt[ri] = E->d_vbo_gcnt[ri] ? E->d_vbo_gcnt[ri] + (size_t)b * nc - r.col_begin : nullptr;
+                if (E->bv.ntiles) {
+                    k_tile_col0<<<nblk(E->bv.ntiles), 256, 0, st>>>(E->bv.colptr[ri], r.col_begin, r.col_end, E->bv.ntiles, E->vbo_ts_shift,
+                                                                   E->d_vbo_tile_col0 + (ri ? E->vbo_max_tiles : 0)); LAUNCHED(E);
+                }
             }
             // second residual copy for the entries of the batch
-            k_gather_e_idx<<<nblk(nb_cases), 256, 0, st>>>(E->d_e, S.crow + S.h_colptr[r1.col_begin], E->d_vbo_idx[1], (uint32_t)E->vbo_off[b],
-                                                            (uint32_t)E->vbo_off[b + 1], E->d_e2); LAUNCHED(E);
+            if (nb_cases) {
+                k_gather_e_idx<<<nblk(nb_cases), 256, 0, st>>>(E->d_e, S.crow + S.h_colptr[r1.col_begin], E->d_vbo_idx[1], (uint32_t)E->vbo_off[b],
+                                                                (uint32_t)E->vbo_off[b + 1], E->d_e2); LAUNCHED(E);
+            }
         }
         if (E->cfg.k0) {                                           // update_w0 (vbo.h:356-358)
             if (int rc = reduce_e(E, (int)b)) return rc;
@@ -1122,7 +1135,7 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
             shift_e(E);
         }
         if (use_streams) {
-            if (nb_cases) if (int rc = sweep_streams<2>(E)) return rc;
+            if (batch_streams) if (int rc = sweep_streams<2>(E)) return rc;
         } else {
             for (const Run& r : E->runs)                           // update_w; also counts |Omega_j^b| (vbo.h:360-373)
                 if (int rc = sweep_run<KIND_VBO_W>(E, r, -1, (int)b)) return rc;
@@ -1132,7 +1145,13 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
         }
         if (int rc = reduce_e(E, (int)b)) return rc;
         k_reduce_dT<<<SV_GGRID, 256, 0, st>>>(E->d_dT, E->D, E->d_red_partial); LAUNCHED(E);
-        k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_GGRID, 1, &E->d_sc->sum_t, 1); LAUNCHED(E);
+        if (use_streams && E->world > 1) {       // sharded stream schedule: every rank holds its own share of d(sum T)
+            k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_GGRID, 1, RED(E->d_sc, 6), 0); LAUNCHED(E);
+            if (int rc = allreduce_sum_f64(E, RED(E->d_sc, 6), 1)) return rc;
+            k_add_scalar<<<1, 1, 0, st>>>(&E->d_sc->sum_t, RED(E->d_sc, 6)); LAUNCHED(E);
+        } else {
+            k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_GGRID, 1, &E->d_sc->sum_t, 1); LAUNCHED(E);
+        }
         if (int rc = group_sums(E, false)) return rc;
         int want_fe = (b == 0 || b + 1 == num_batch);              // vbos.h:143-146
         k_vbo_hyper<<<1, 1, 0, st>>>(E->d_sc, E->d_grp_sums, E->d_n_per_group, E->G, E->K, E->d_hyper_w, E->d_hyper_v, E->d_stats, want_fe, b == 0, 0.5);

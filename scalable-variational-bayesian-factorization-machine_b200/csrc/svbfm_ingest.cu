@@ -488,16 +488,18 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         }
         const bool two_fields = E->run0_sequential && !getenv("SVBFM_NO_FUSE") && E->runs.size() == 2 && F == 2 && E->runs[1].nnz == n;
         E->streams = two_fields && E->cfg.method != SVBFM_VB_ONLINE;
-        E->vbo_streams = two_fields && E->cfg.method == SVBFM_VB_ONLINE && E->world == 1 && !getenv("SVBFM_NO_VBO_STREAM");
+        E->vbo_streams = two_fields && E->cfg.method == SVBFM_VB_ONLINE && !getenv("SVBFM_NO_VBO_STREAM") && (E->world == 1 || !getenv("SVBFM_NO_VBO_STREAM_SHARDED"));
         E->excl0 = false;
         if (E->world > 1) {      // one schedule for all ranks
             uint32_t* d_ok = d_flags + 6;
-            uint32_t ok = E->streams ? 1u : 0u;
-            SV_CUDA(E, cudaMemcpyAsync(d_ok, &ok, 4, cudaMemcpyHostToDevice, st));
-            if (int r = allreduce(E, d_ok, 1, 3 /*ncclUint32*/, 3 /*ncclMin*/)) return r;
-            SV_CUDA(E, cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, st));
+            uint32_t ok = (E->streams ? 1u : 0u) | (E->vbo_streams ? 2u : 0u);
+            uint32_t ok2[2] = {ok & 1u, (ok >> 1) & 1u};
+            SV_CUDA(E, cudaMemcpyAsync(d_ok, ok2, 8, cudaMemcpyHostToDevice, st));
+            if (int r = allreduce(E, d_ok, 2, 3 /*ncclUint32*/, 3 /*ncclMin*/)) return r;
+            SV_CUDA(E, cudaMemcpyAsync(ok2, d_ok, 8, cudaMemcpyDeviceToHost, st));
             SV_CUDA(E, cudaStreamSynchronize(st));
-            E->streams = ok != 0;
+            E->streams = ok2[0] != 0;
+            E->vbo_streams = ok2[1] != 0;
             if (E->streams) if (int r = detect_exclusive_blocks(E)) return r;
         }
     }
@@ -660,6 +662,11 @@ static __global__ void k_vbo_hist(const uint16_t* __restrict__ rbatch, const uin
     atomicAdd(&cnt[(size_t)rbatch[i] * nc + (j - c0)], 1ull);          // integer atomics: order-independent
 }
 
+static __global__ void k_u64_to_u32(const unsigned long long* __restrict__ in, size_t n, uint32_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)in[i];
+}
+
 // For each field: idx = the run's entries stably sorted by batch (inside a batch they keep the run's column order), and
 // colptr[b * nc + c] = first position in idx of column c0 + c of batch b (histogram + exclusive scan; the flattened scan
 // makes colptr[(b + 1) * nc] the end of batch b). Stale after the next call.
@@ -709,6 +716,12 @@ int vbo_stream_prepare(Engine* E, uint32_t num_batch) {
             E->dev_bytes += (size_t)n * 4;
             k_vbo_hist<<<nblk(n), 256, 0, st>>>(E->d_rbatch, S.rcol, n, ri, r.col_begin, nc, E->d_vbo_colptr[ri]);
         } else if (dev_alloc(E, &E->d_vbo_idx[ri], 1)) return SVBFM_ERR_OOM;
+        if (E->world > 1) {       // global number of batch entries of every column: the histogram summed over the ranks (before the scan)
+            sv_free(E->d_vbo_gcnt[ri]); E->d_vbo_gcnt[ri] = nullptr;
+            if (dev_alloc(E, &E->d_vbo_gcnt[ri], ncp)) return SVBFM_ERR_OOM;
+            k_u64_to_u32<<<nblk(ncp - 1), 256, 0, st>>>(E->d_vbo_colptr[ri], ncp - 1, E->d_vbo_gcnt[ri]);
+            if (int rc = allreduce(E, E->d_vbo_gcnt[ri], ncp - 1, 3 /*ncclUint32*/, 0 /*ncclSum*/)) return rc;
+        }
         size_t tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, E->d_vbo_colptr[ri], E->d_vbo_colptr[ri], (int64_t)ncp, st);
         void* tmp = nullptr;

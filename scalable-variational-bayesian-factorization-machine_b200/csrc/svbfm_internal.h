@@ -139,6 +139,7 @@ struct Engine {
     bool vbo_streams = false;
     uint32_t* d_vbo_idx[2] = {nullptr, nullptr};           // [n] each
     unsigned long long* d_vbo_colptr[2] = {nullptr, nullptr};   // [num_batch * ncols(run) + 1] each
+    uint32_t* d_vbo_gcnt[2] = {nullptr, nullptr};          // sharded: [num_batch * ncols(run)] GLOBAL number of batch entries per column
     uint32_t* d_vbo_tile_col0 = nullptr;                   // [2][vbo_max_tiles]
     double* d_vbo_partial = nullptr;                       // [2][vbo_max_tiles][2][4]
     uint32_t vbo_max_tiles = 0;
@@ -147,6 +148,7 @@ struct Engine {
         bool on = false;
         bool lists = false;                                 // prediction / reductions / w0 shift of the batch walk its case list too
         const uint64_t* colptr[2] = {nullptr, nullptr};
+        const uint32_t* gcnt[2] = {nullptr, nullptr};       // sharded: global batch entries per column (same indexing as colptr)
         uint64_t entry0 = 0;
         uint32_t n = 0, ntiles = 0;
     } bv;

@@ -358,6 +358,7 @@ struct FinalizeArgs {
     uint32_t* t_cnt;             // [D] t_wj (w) or t_vj (v)
     const double* col_count;     // [D]
     const uint64_t* colptr;      // batch column sizes come from colsum C-slot instead (see engine)
+    const uint32_t* gcnt;        // vb_online on the sharded stream schedule: global batch entries of every column (indexed like span.colptr)
     int update_t;                // vb_online: 1 when this sweep advances t_cnt (w: always; v: f == 0)
 };
 
@@ -447,10 +448,10 @@ __global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __
     if (a.span.colptr) {
         // stream schedule: colptr is the batch's own column pointer, so the column's batch entries are counted directly.
         // Records of a skipped column are not written: no entry of the batch refers to it.
-        cnt = (double)(a.span.colptr[j + 1] - a.span.colptr[j]);
+        cnt = a.gcnt ? (double)a.gcnt[j] : (double)(a.span.colptr[j + 1] - a.span.colptr[j]);
         if (cnt == 0.0 || !update_params) { a.delta[j] = 0.0; return; }
         bool empty;
-        if (!span_sum(j, a.span, a.partial, A, B, C1, C2, empty)) {
+        if (a.from_colsum || !span_sum(j, a.span, a.partial, A, B, C1, C2, empty)) {
             const double2* p = reinterpret_cast<const double2*>(a.colsum + (size_t)j * 4);
             double2 x = p[0], y = p[1];
             A = x.x; B = x.y; C1 = y.x; C2 = y.y;
@@ -462,6 +463,8 @@ __global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __
         else cnt = cnt_arr[j];
         if (cnt == 0.0 || !update_params) { a.delta[j] = 0.0; return; }     // empty columns are skipped (vbo.h:367, 394)
     }
+    const double B_local = B;                                 // this rank's share (d(sum T) of a w column)
+    if (a.ab) { double2 g2 = a.ab[j]; A = g2.x; B = g2.y; }   // sharded: global sums after the allreduce
     uint32_t g = a.group[j];
     double hy = (a.f < 0) ? a.hyper[g] : a.hyper[(size_t)g * a.K + a.f];
     double alpha = a.sc->alpha;
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __
     a.pf[j] = make_double2(mu, sg);
     a.delta[j] = skip ? 0.0 : (mu_dash - mu);
     if (!skip) {
-        if constexpr (KIND == KIND_VBO_W) a.dT[j] += B * (sg - sg_dash);
+        if constexpr (KIND == KIND_VBO_W) a.dT[j] += B_local * (sg - sg_dash);
         else a.dT[j] += (C1 + C2) * (sg - sg_dash) + C1 * (mu * mu - mu_dash * mu_dash);
     }
     write_records(a, j, mu, sg, skip ? 0.0 : (mu_dash - mu), mu_dash);

@@ -41,7 +41,9 @@ def main():
              ("ragged_vb", ragged(3000, 400, 60, seed=52), "vb", 2, 3, {}),
              ("two_field_als", two_field(10000, 1000, 160, 120, seed=53), "mcmc", 2, 3, {}),
              ("two_field_als_blocks", two_field(10000, 1000, 160, 120, seed=55), "mcmc", 2, 3, {}),
-             ("two_field_vbo", two_field(10000, 1000, 160, 120, seed=56), "vb_online", 2, 2, dict(num_batch=4)))
+             ("two_field_vbo", two_field(10000, 1000, 160, 120, seed=56), "vb_online", 2, 2, dict(num_batch=4)),
+             # three cases per batch: some ranks have no case of a batch and still have to take part in its collectives
+             ("two_field_vbo_tiny_batches", two_field(300, 100, 20, 15, seed=57), "vb_online", 2, 2, dict(num_batch=100)))
     for name, (tr, te), method, K, iters, extra in cases:
         if only and only not in name:
             continue
@@ -54,7 +56,7 @@ def main():
         E = sv.Engine(method, D, K, 1, 1, float(tr.y.min()), float(tr.y.max()), seed=42, tile_entries=64, **kw)
         E.comm_init(uid, rank, world)
         blocks = name.endswith("_blocks")
-        nu = 200 if "vb" in name else 160
+        nu = 200 if name.startswith("two_field_vb") else 160
         if blocks:
             shard, mine = d.shard_csc_by_block(to_csc(tr), rank, world, nu)
         else:
