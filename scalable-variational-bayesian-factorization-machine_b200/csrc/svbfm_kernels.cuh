@@ -1013,7 +1013,9 @@ __global__ void __launch_bounds__(256) k_row_apply(RowApplyArgs a) {
 
 // ---------------------------------------------------------------------------------------------------------
 // dense passes over the residuals
-#define SV_RGRID 1184   // 148 SMs x 8
+#ifndef SV_RGRID
+#define SV_RGRID 1184   // 148 SMs x 8 (tests/emu builds with a smaller grid: every CUDA thread is a fiber there)
+#endif
 
 // partial[b*3 + {0,1,2}] = sum e, sum e^2, sum clamp(e)^2  (vb.h:513, :451, vbs.h:153-162)
 __global__ void __launch_bounds__(256) k_reduce_e(const double* __restrict__ e, uint32_t n, const Scalars* sc, double* __restrict__ partial,

@@ -3,8 +3,11 @@
 // threads of a CTA are fibers that run until they return or reach a warp / block primitive; CTAs run one at a time.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <map>
+#include <string>
 #include <vector>
 
 uint3 threadIdx, blockIdx;
@@ -176,7 +179,22 @@ void block_barrier() {
     while (B.bar_gen == gen) yield_to_scheduler();
 }
 
-void launch(dim3 grid, dim3 block, size_t, cudaStream_t, const std::function<void()>& body) {
+// SVBFM_EMU_PROFILE=1: host time and launch / thread counts per kernel name, printed at exit (where does an emulated test spend its time)
+struct KernelStat { double seconds = 0; uint64_t launches = 0, threads = 0; };
+static std::map<std::string, KernelStat>& kernel_stats() { static auto* m = new std::map<std::string, KernelStat>(); return *m; }   // never destroyed: read at exit
+static void print_kernel_stats() {
+    std::vector<std::pair<double, std::string>> v;
+    for (auto& kv : kernel_stats()) v.push_back({kv.second.seconds, kv.first});
+    std::sort(v.rbegin(), v.rend());
+    fprintf(stderr, "[emu] %-28s %10s %10s %14s\n", "kernel", "seconds", "launches", "threads");
+    for (auto& p : v) { const KernelStat& k = kernel_stats()[p.second]; fprintf(stderr, "[emu] %-28s %10.3f %10llu %14llu\n", p.second.c_str(), k.seconds, (unsigned long long)k.launches, (unsigned long long)k.threads); }
+}
+
+void launch(dim3 grid, dim3 block, size_t, cudaStream_t, const std::function<void()>& body, const char* name) {
+    static const bool profile = getenv("SVBFM_EMU_PROFILE") != nullptr;
+    static bool registered = false;
+    if (profile && !registered) { registered = true; atexit(print_kernel_stats); }
+    const auto t_begin = std::chrono::steady_clock::now();
     if (B.cur != -1) { fprintf(stderr, "[emu] nested launch\n"); abort(); }
     if (grid.x == 0 || grid.y == 0 || grid.z == 0 || block.x * block.y * block.z == 0 || block.x * block.y * block.z > 1024) {
         fprintf(stderr, "[emu] invalid launch configuration grid (%u,%u,%u) block (%u,%u,%u)\n", grid.x, grid.y, grid.z, block.x, block.y, block.z);
@@ -191,6 +209,12 @@ void launch(dim3 grid, dim3 block, size_t, cudaStream_t, const std::function<voi
                 run_block();
             }
     B.body = nullptr;
+    if (profile) {
+        KernelStat& k = kernel_stats()[name];
+        k.seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+        k.launches++;
+        k.threads += (uint64_t)grid.x * grid.y * grid.z * block.x * block.y * block.z;
+    }
 }
 
 }  // namespace emu

@@ -89,7 +89,7 @@ cudaError_t cudaEventElapsedTime(float*, cudaEvent_t, cudaEvent_t);
 
 // ---- the scheduler (emu_runtime.cpp)
 namespace emu {
-void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, const std::function<void()>& body);
+void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t st, const std::function<void()>& body, const char* name = "");
 uint64_t warp_exchange(unsigned mask, uint64_t mine, int src_lane);   // every lane deposits `mine`, returns the deposit of src_lane
 unsigned warp_ballot(unsigned mask, bool pred);
 void block_barrier();
