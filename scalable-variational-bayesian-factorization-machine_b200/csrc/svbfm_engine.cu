@@ -716,6 +716,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     if (const char* te = getenv("SVBFM_TILE_ENTRIES")) if (atoi(te) >= 32) E->tile_entries = (uint32_t)atoi(te);   // tuning knob
     // implicit tiles of the stream schedule: 4096 entries unless the caller (or the knob) says otherwise
     uint32_t ts = (cfg->tile_entries || getenv("SVBFM_TILE_ENTRIES")) ? E->tile_entries : 4096u;
+    E->ts_auto = !(cfg->tile_entries || getenv("SVBFM_TILE_ENTRIES"));     // ingest may shrink the tiles of a small train split (stream_tile_shift)
     E->ts_shift = 5;
     while (E->ts_shift < 20 && (2u << E->ts_shift) <= ts) E->ts_shift++;
     ce = cudaStreamCreateWithFlags(&E->own_stream, cudaStreamNonBlocking);

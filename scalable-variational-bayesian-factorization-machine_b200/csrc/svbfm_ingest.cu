@@ -528,6 +528,14 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     if (is_train && E->streams) {
         // ---- stream schedule: implicit tiles of 2^ts_shift entries per run; only their first column and the list of the
         // columns that span many tiles are materialised (kernels.cuh k_stream / k_combine_span)
+        if (E->ts_auto) {
+            // A pass is one warp per tile: 148 SMs x 3 CTAs x 8 warps = 3552 warps are resident at a time. 4096-entry tiles (the best
+            // size at 200 M entries) leave most SMs idle below ~15 M entries per field (1 M ratings: 244 warps on
+            // 31 SMs). Aim at four waves of warps, with tiles between 256 and 4096 entries.
+            const uint64_t want = (uint64_t)n / (3552ull * 4);
+            E->ts_shift = 8;
+            while (E->ts_shift < 12 && (2ull << E->ts_shift) <= want) E->ts_shift++;
+        }
         const uint64_t TS = 1ull << E->ts_shift;
         sv_free(E->d_stile_col0); sv_free(E->d_span_heavy);
         E->d_stile_col0 = nullptr; E->d_span_heavy = nullptr;

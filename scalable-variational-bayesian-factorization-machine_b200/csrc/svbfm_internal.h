@@ -126,6 +126,7 @@ struct Engine {
     // two-copy stream schedule (two complete one-hot fields; kernels.cuh k_stream)
     bool streams = false;
     uint32_t ts_shift = 10;            // implicit tile = 2^ts_shift entries (largest power of two <= tile_entries, >= 32)
+    bool ts_auto = false;              // no tile size was asked for: small train splits get smaller tiles (svbfm_ingest.cu)
     uint32_t s_ntiles[2] = {0, 0};     // implicit tiles of run 0 / run 1
     uint32_t* d_stile_col0 = nullptr;  // [s_ntiles[0] + s_ntiles[1]] first column of every implicit tile
     uint32_t* d_span_heavy = nullptr;  // columns spanning more than SV_SPAN_LIGHT tiles, run 0 then run 1

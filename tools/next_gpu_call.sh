@@ -23,5 +23,9 @@ SVBFM_REC_RANK=1 SVBFM_STREAM_TMA=1 timeout 600 $py bench.py --steps 5 --warmup 
 timeout 900 $py bench.py --method vb_online --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $out/next_bench_vbo.json 2> $out/next_bench_vbo.err; echo "bench vb_online rc=$?" | tee -a $out/next_summary.txt
 SVBFM_VBO_FULL_PASSES=1 timeout 900 $py bench.py --method vb_online --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $out/next_bench_vbo_full_passes.json 2> $out/next_bench_vbo_full_passes.err; echo "bench vb_online (masked passes) rc=$?" | tee -a $out/next_summary.txt
 
+for w in ml1m ml10m; do
+  timeout 600 $py bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline > $out/next_bench_$w.json 2> $out/next_bench_$w.err; echo "bench $w rc=$?" | tee -a $out/next_summary.txt
+  SVBFM_TILE_ENTRIES=4096 timeout 600 $py bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > $out/next_bench_${w}_tiles4096.json 2> $out/next_bench_${w}_tiles4096.err; echo "bench $w (4096-entry tiles) rc=$?" | tee -a $out/next_summary.txt
+done
 grep -h -o '"ms_per_step": [0-9.]*' $out/next_bench_*.json | paste -d' ' - - - - - - 2>/dev/null | tee -a $out/next_summary.txt
 for f in $out/next_bench_*.json; do echo "$f $(grep -o '"ms_per_step": [0-9.]*' $f | head -1)"; done | tee -a $out/next_summary.txt
