@@ -464,7 +464,8 @@ def main():
                       "sharding": shard_mode, "ratings_per_rank": rank_ratings, "stream_ms_per_rank": rank_stream_ms, "exclusive_blocks": info0.get("exclusive_blocks", 0),
                       "l2": "inputs (residuals + design matrix) are far larger than the 126 MB L2; no flush needed",
                       "field_runs": info0["num_runs"], "tiles": info0["num_tiles"], "rows_reordered": info0["rows_reordered"],
-                      "fused_schedule": info0.get("fused_schedule", 0)},
+                      "fused_schedule": info0.get("fused_schedule", 0),
+                      "knobs": {k: v for k, v in sorted(os.environ.items()) if k.startswith("SVBFM_") and k != "SVBFM_LIB"}},
            "sweep_only_ms_per_step": sweep_per_step, "wall_ms_per_step": wall_ms / a.steps,
            "test_rmse_last": last.test_rmse, "free_energy_last": last.free_energy,
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
