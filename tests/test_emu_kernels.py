@@ -60,3 +60,14 @@ def test_two_ranks_on_the_emulator(emu_lib, tmp_path):
             raise
     assert all(p.returncode == 0 for p in procs), "\n".join(o[-2000:] for o in outs)
     assert "MRANK_OK" in outs[0], outs[0][-3000:]
+
+
+def test_experimental_variants_on_the_emulator(emu_lib):
+    """One case each of the opt-in kernel variants that have not run on a B200 yet: the bulk-copy ring of
+    k_stream (bit-identical to the plain kernel; misaligned second field, partial last batch) and the rank-ordered records."""
+    env = dict(os.environ, SVBFM_LIB=emu_lib)
+    cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider",
+           os.path.join(ROOT, "tests", "test_gpu_zzz_tma_ring.py") + "::test_stream_tma_ring[256-20002]",
+           os.path.join(ROOT, "tests", "test_gpu_zz_experiments.py") + "::test_rec_rank_layout[64]"]
+    r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]

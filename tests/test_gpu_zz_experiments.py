@@ -67,39 +67,6 @@ def test_vb_online_batch_lists_equal_masked_passes(built, monkeypatch):
         assert all(rel(x, y) < 1e-10 for x, y in zip(a, b)), (a, b)
 
 
-@pytest.mark.parametrize("tile_entries,n", [(0, 20000), (64, 20000), (256, 20002), (1024, 30001)])
-def test_stream_tma_ring(built, monkeypatch, tile_entries, n):
-    """SVBFM_STREAM_TMA=1: the streams of k_stream staged through a per-warp shared-memory ring of bulk copies. Same
-    arithmetic in the same order as the plain kernel: identical statistics (bit for bit) and identical residual copies.
-    n = 20002 / 30001: the second field's streams do not start on a 16-byte boundary (plain kernel for that side), partial
-    last batches and tiles."""
-    tr, te = two_field(n, 2000, 300, 200, seed=31)
-    out = []
-    for tma in ("0", "1"):
-        monkeypatch.setenv("SVBFM_STREAM_TMA", tma)
-        L = make_learner("vb", tr, te, 3, num_iter=3, tile_entries=tile_entries)
-        out.append([(s.test_rmse, s.free_energy, s.alpha, s.train_stat) for s in L.learn(to_csc(tr), to_csc(te))])
-        assert L.engine.info()["fused_schedule"] == (5 if tma == "1" else 1)
-        assert L.engine.copies_max_diff() == 0.0
-        out.append(L.engine.get_residuals())
-        L.engine.close()
-    assert out[0] == out[2]
-    assert np.array_equal(out[1], out[3])
-    orc = ob.Oracle("vb", tr, te, K=3, seed=42)
-    for a in out[2]:
-        o = orc.iterate()
-        assert rel(a[0], o.test_rmse) < VB_TOL and rel(a[1], o.free_energy) < VB_TOL
-    # als through the same ring
-    orc = ob.Oracle("mcmc", tr, te, K=2, seed=42, do_sample=False, do_multilevel=False)
-    L = make_learner("mcmc", tr, te, 2, num_iter=3, do_sample=False, do_multilevel=False, tile_entries=tile_entries)
-    L.fm.reg0, L.fm.regw, L.fm.regv = 0.0, 0.0, 0.0
-    for s in L.learn(to_csc(tr), to_csc(te)):
-        o = orc.iterate()
-        assert rel(s.test_rmse, o.test_rmse) < VB_TOL and rel(s.train_stat, o.train_stat) < VB_TOL
-    assert L.engine.copies_max_diff() == 0.0
-    L.engine.close()
-
-
 # ---- binary classification (-task c) for mcmc / als: SURVEY section 8(f) rank 4. Built and emulator-checked without a GPU.
 def _binary_two_field(n, nt, U, I, seed, values=False):
     tr, te = two_field(n, nt, U, I, seed=seed, values=values)

@@ -12,8 +12,8 @@ py=python
 timeout 600 $py -m pytest tests -m gpu -x -q > $out/next_pytest_gpu.log 2>&1; echo "pytest -m gpu rc=$?" | tee $out/next_summary.txt
 
 # 2. the experiments, each alone (a hang or a wrong result in one must not hide the others)
-SVBFM_REC_RANK=1 timeout 300 $py -m pytest tests/test_gpu_zz_experiments.py -m gpu -q -k rec_rank > $out/next_pytest_rec_rank.log 2>&1; echo "rec_rank tests rc=$?" | tee -a $out/next_summary.txt
-SVBFM_STREAM_TMA=1 timeout 300 $py -m pytest tests/test_gpu_zz_experiments.py -m gpu -q -k tma > $out/next_pytest_tma.log 2>&1; echo "tma tests rc=$?" | tee -a $out/next_summary.txt
+timeout 300 $py -m pytest tests/test_gpu_zz_experiments.py -m gpu -q -k rec_rank > $out/next_pytest_rec_rank.log 2>&1; echo "rec_rank tests rc=$?" | tee -a $out/next_summary.txt
+SVBFM_RUN_EXPERIMENTS=1 timeout 900 $py -m pytest tests/test_gpu_zzz_tma_ring.py -m gpu -q > $out/next_pytest_tma.log 2>&1; echo "tma tests rc=$?" | tee -a $out/next_summary.txt
 
 # 3. bench lines: default, each experiment, both (device-resident value only where e2e is not the question)
 timeout 600 $py bench.py --steps 5 --warmup 3 > $out/next_bench_default.json 2> $out/next_bench_default.err; echo "bench default rc=$?" | tee -a $out/next_summary.txt
