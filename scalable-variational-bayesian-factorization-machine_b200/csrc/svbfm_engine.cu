@@ -716,7 +716,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     if (const char* te = getenv("SVBFM_TILE_ENTRIES")) if (atoi(te) >= 32) E->tile_entries = (uint32_t)atoi(te);   // tuning knob
     // implicit tiles of the stream schedule: 4096 entries unless the caller (or the knob) says otherwise
     uint32_t ts = (cfg->tile_entries || getenv("SVBFM_TILE_ENTRIES")) ? E->tile_entries : 4096u;
-    E->ts_auto = !(cfg->tile_entries || getenv("SVBFM_TILE_ENTRIES"));     // ingest may shrink the tiles of a small train split (stream_tile_shift)
+    E->ts_auto = !(cfg->tile_entries || getenv("SVBFM_TILE_ENTRIES"));     // ingest may shrink the tiles of a small train split
     E->ts_shift = 5;
     while (E->ts_shift < 20 && (2u << E->ts_shift) <= ts) E->ts_shift++;
     ce = cudaStreamCreateWithFlags(&E->own_stream, cudaStreamNonBlocking);
@@ -1089,7 +1089,7 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
     SV_CUDA(E, cudaMemsetAsync(E->d_stats, 0, sizeof(DevStats), st));
     // two complete fields on one GPU: every batch is swept by the stream schedule on its own entries (batch index lists built once
     // per epoch) instead of scanning the whole design matrix with a batch mask per (batch, factor, field)
-    const bool use_streams = E->vbo_streams && S.n > 0 &&
+    const bool use_streams = E->vbo_streams && (S.n > 0 || E->world > 1) &&      // sharded: the same decision on every rank, cases or not
                              (uint64_t)num_batch * std::max(E->runs[0].col_end - E->runs[0].col_begin, E->runs[1].col_end - E->runs[1].col_begin) < (1ull << 31);
     if (use_streams) {
         if (!E->d_e2 && dev_alloc(E, &E->d_e2, S.n)) return SVBFM_ERR_OOM;
