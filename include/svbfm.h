@@ -161,7 +161,8 @@ typedef struct svbfm_info {
     uint32_t world_size;
     uint32_t fused_schedule;   /* bit 0: the two-field stream schedule (two residual copies, k_stream) is in use;
                                 * bit 1: its records are laid out by popularity rank (SVBFM_REC_RANK=1, experiment);
-                                * bit 2: its streams are staged by bulk copies (SVBFM_STREAM_TMA=1, experiment) */
+                                * bit 2: its streams are staged by bulk copies (SVBFM_STREAM_TMA=1, experiment);
+                                * bit 3: iterations were replayed from a CUDA graph (SVBFM_GRAPH=1, experiment) */
     uint32_t exclusive_blocks; /* multi-GPU: 1 when the ranks hold disjoint column blocks of the first field (no exchange for it inside the sweep) */
 } svbfm_info;
 int svbfm_get_info(svbfm_t* h, svbfm_info* out);

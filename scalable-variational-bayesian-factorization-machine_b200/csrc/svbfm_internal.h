@@ -186,6 +186,8 @@ struct Engine {
     // that neighbouring lanes of the first field's pass gather neighbouring records. d_rec_slot[j] = record slot of column j
     // (identity outside the second field); the first field's `cother` entries then hold slots, not column ids.
     uint32_t* d_rec_slot = nullptr;    // [D]
+    bool use_graph = false;            // SVBFM_GRAPH=1 (experiment): iterations 1.. of svbfm_run replay a CUDA graph of one iteration
+    uint64_t graph_replays = 0;
     bool stream_tma = false;           // SVBFM_STREAM_TMA=1 (experiment): k_stream's streams through a shared-memory ring of bulk copies
     bool rec_rank = false;
     double* d_dT = nullptr;           // [D]

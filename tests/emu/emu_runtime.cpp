@@ -139,6 +139,11 @@ void run_block() {
 
 }  // namespace
 
+// stream capture (cudaStreamBeginCapture .. EndCapture): launches and async copies are recorded into a graph instead of executed
+struct emuGraph { std::vector<std::function<void()>> nodes; };
+static emuGraph* g_capture = nullptr;      // non-null while a capture is open (the engine keeps one stream of work at a time)
+static bool g_capture_broken = false;      // a call that is illegal during capture was made
+
 namespace emu {
 
 int lane_id() { return B.fibers[B.cur].lane; }
@@ -200,6 +205,12 @@ void launch(dim3 grid, dim3 block, size_t, cudaStream_t, const std::function<voi
         fprintf(stderr, "[emu] invalid launch configuration grid (%u,%u,%u) block (%u,%u,%u)\n", grid.x, grid.y, grid.z, block.x, block.y, block.z);
         abort();     // the real runtime reports cudaErrorInvalidConfiguration: a bug either way
     }
+    if (g_capture) {        // recorded, not executed; the body holds its arguments by value ([=] in the rewritten launch)
+        std::function<void()> copy = body;
+        std::string nm = name;
+        g_capture->nodes.push_back([grid, block, copy, nm] { emu::launch(grid, block, 0, nullptr, copy, nm.c_str()); });
+        return;
+    }
     gridDim = grid; blockDim = block;
     B.body = &body;
     for (uint32_t z = 0; z < grid.z; z++)
@@ -221,6 +232,7 @@ void launch(dim3 grid, dim3 block, size_t, cudaStream_t, const std::function<voi
 
 // ------------------------------------------------------------------------------------------------ runtime calls
 struct emuStream { int id; };
+
 struct emuEvent { std::chrono::steady_clock::time_point t; };
 
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : e == cudaErrorMemoryAllocation ? "out of memory" : "invalid value"; }
@@ -237,6 +249,7 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
 cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 cudaError_t cudaMalloc(void** p, size_t n) {
+    if (g_capture) g_capture_broken = true;     // not allowed while capturing
     *p = aligned_alloc(256, (n + 255) / 256 * 256 + 256);
     if (!*p) return cudaErrorMemoryAllocation;
     memset(*p, 0xcd, n);       // "device memory" starts out as garbage, not zeros
@@ -244,13 +257,24 @@ cudaError_t cudaMalloc(void** p, size_t n) {
 }
 cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+    if (g_capture) { g_capture->nodes.push_back([d, s, n] { if (n) memmove(d, s, n); }); return cudaSuccess; }
+    if (n) memmove(d, s, n);
+    return cudaSuccess;
+}
 cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { if (n) memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) {
+    if (g_capture) { g_capture->nodes.push_back([d, v, n] { if (n) memset(d, v, n); }); return cudaSuccess; }
+    if (n) memset(d, v, n);
+    return cudaSuccess;
+}
 cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = new emuStream{1}; return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new emuStream{1}; return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) {
+    if (g_capture) { g_capture_broken = true; return cudaErrorStreamCaptureUnsupported; }     // illegal while capturing, as on the GPU
+    return cudaSuccess;
+}
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emuEvent{std::chrono::steady_clock::now()}; return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
@@ -261,3 +285,26 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
     *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
     return cudaSuccess;
 }
+
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) {
+    if (g_capture) return cudaErrorInvalidValue;
+    g_capture = new emuGraph();
+    g_capture_broken = false;
+    return cudaSuccess;
+}
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* out) {
+    if (!g_capture) { *out = nullptr; return cudaErrorInvalidValue; }
+    emuGraph* g = g_capture;
+    g_capture = nullptr;
+    if (g_capture_broken) { delete g; *out = nullptr; return cudaErrorStreamCaptureUnsupported; }
+    *out = g;
+    return cudaSuccess;
+}
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t* ex, cudaGraph_t g, unsigned long long) { *ex = new emuGraph(*g); return cudaSuccess; }
+cudaError_t cudaGraphLaunch(cudaGraphExec_t ex, cudaStream_t) {
+    if (g_capture) return cudaErrorInvalidValue;
+    for (auto& n : ex->nodes) n();
+    return cudaSuccess;
+}
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t ex) { delete ex; return cudaSuccess; }
+cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }

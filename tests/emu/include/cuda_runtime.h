@@ -52,7 +52,7 @@ extern dim3 blockDim, gridDim;
 
 // ---- runtime API (synchronous; "device memory" is host memory)
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorStreamCaptureUnsupported = 900 };
 typedef struct emuStream* cudaStream_t;
 typedef struct emuEvent* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
@@ -86,6 +86,16 @@ cudaError_t cudaEventDestroy(cudaEvent_t);
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr);
 cudaError_t cudaEventSynchronize(cudaEvent_t);
 cudaError_t cudaEventElapsedTime(float*, cudaEvent_t, cudaEvent_t);
+// stream capture / graphs: while a capture is open, launches and async copies are recorded (not executed), like on the GPU
+typedef struct emuGraph* cudaGraph_t;
+typedef struct emuGraph* cudaGraphExec_t;
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureModeThreadLocal = 1, cudaStreamCaptureModeRelaxed = 2 };
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode);
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t*);
+cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, unsigned long long = 0);
+cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t);
+cudaError_t cudaGraphExecDestroy(cudaGraphExec_t);
+cudaError_t cudaGraphDestroy(cudaGraph_t);
 
 // ---- the scheduler (emu_runtime.cpp)
 namespace emu {

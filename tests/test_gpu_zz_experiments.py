@@ -159,3 +159,26 @@ def test_cli_classification_reproduces_reference_stdout(built, tmp_path):
     assert open(tmp_path / "test_rmse_112_mcmc").read() == ""
     pred = [float(x) for x in open(tmp_path / "pred.txt").read().split()]
     assert len(pred) == 400 and min(pred) >= 0.0 and max(pred) <= 1.0
+
+
+@pytest.mark.parametrize("method", ["vb", "mcmc"])
+def test_graph_replay_equals_plain_launches(built, monkeypatch, method):
+    """SVBFM_GRAPH=1: iterations 1.. of svbfm_run are replays of a CUDA graph captured from one iteration. Same launches with
+    the same arguments in the same order: every statistic is bit-identical to the plain run, and so are the parameters."""
+    tr, te = two_field(15000, 1500, 250, 180, seed=61)
+    kw = dict(do_sample=True, do_multilevel=True) if method == "mcmc" else {}
+    out = []
+    for graph in ("0", "1"):
+        monkeypatch.setenv("SVBFM_GRAPH", graph)
+        L = make_learner(method, tr, te, 3, num_iter=5, **kw)
+        hist = L.learn(to_csc(tr), to_csc(te))
+        out.append([(s.test_rmse, s.train_stat, s.free_energy, s.alpha, s.rmse_this, s.nan_inf_count) for s in hist])
+        st = L.engine.get_state()
+        out.append(np.concatenate([st["w_mean"], st["v_mean"].ravel(), st["v_var"].ravel()]))
+        assert bool(L.engine.info()["fused_schedule"] & 8) == (graph == "1")
+        assert L.engine.info()["kernel_launches"] > 0
+        out.append(L.engine.info()["kernel_launches"])
+        L.engine.close()
+    assert out[0] == out[3]
+    assert np.array_equal(out[1], out[4])
+    assert out[2] == out[5]          # the launch counter counts the replayed kernels too

@@ -12,7 +12,7 @@ py=python
 timeout 600 $py -m pytest tests -m gpu -x -q > $out/next_pytest_gpu.log 2>&1; echo "pytest -m gpu rc=$?" | tee $out/next_summary.txt
 
 # 2. the experiments, each alone (a hang or a wrong result in one must not hide the others)
-timeout 300 $py -m pytest tests/test_gpu_zz_experiments.py -m gpu -q -k rec_rank > $out/next_pytest_rec_rank.log 2>&1; echo "rec_rank tests rc=$?" | tee -a $out/next_summary.txt
+timeout 600 $py -m pytest tests/test_gpu_zz_experiments.py -m gpu -q -k 'rec_rank or graph' > $out/next_pytest_rec_rank.log 2>&1; echo "rec_rank tests rc=$?" | tee -a $out/next_summary.txt
 SVBFM_RUN_EXPERIMENTS=1 timeout 900 $py -m pytest tests/test_gpu_zzz_tma_ring.py -m gpu -q > $out/next_pytest_tma.log 2>&1; echo "tma tests rc=$?" | tee -a $out/next_summary.txt
 
 # 3. bench lines: default, each experiment, both (device-resident value only where e2e is not the question)
@@ -24,6 +24,7 @@ timeout 900 $py bench.py --method vb_online --steps 2 --warmup 1 --no-cpu-baseli
 SVBFM_VBO_FULL_PASSES=1 timeout 900 $py bench.py --method vb_online --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $out/next_bench_vbo_full_passes.json 2> $out/next_bench_vbo_full_passes.err; echo "bench vb_online (masked passes) rc=$?" | tee -a $out/next_summary.txt
 
 for w in ml1m ml10m; do
+  SVBFM_GRAPH=1 timeout 600 $py bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $out/next_bench_${w}_graph.json 2> $out/next_bench_${w}_graph.err; echo "bench $w (graph replay) rc=$?" | tee -a $out/next_summary.txt
   timeout 600 $py bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline > $out/next_bench_$w.json 2> $out/next_bench_$w.err; echo "bench $w rc=$?" | tee -a $out/next_summary.txt
   SVBFM_TILE_ENTRIES=4096 timeout 600 $py bench.py --workload $w --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > $out/next_bench_${w}_tiles4096.json 2> $out/next_bench_${w}_tiles4096.err; echo "bench $w (4096-entry tiles) rc=$?" | tee -a $out/next_summary.txt
 done
