@@ -275,6 +275,19 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
                  const float* x, const float* target) {
     cudaStream_t st = E->stream;
     free_split(E, S);
+    // temporaries of this function: whatever is still owned when it returns (early, on an error) goes back to the block cache
+    struct Temps {
+        std::vector<void**> slots;
+        cudaStream_t side = nullptr;       // the copy stream: its transfers into these blocks must have landed before they are recycled
+        void own(void** p) { slots.push_back(p); }
+        ~Temps() {
+            bool any = false;
+            for (void** s : slots) any = any || (*s != nullptr);
+            if (any && side) cudaStreamSynchronize(side);
+            for (void** s : slots) { sv_free(*s); *s = nullptr; }
+        }
+    } temps;
+    auto drop = [](auto*& p) { sv_free(p); p = nullptr; };
     const bool timing = getenv("SVBFM_TIMING") != nullptr;
     auto t_last = std::chrono::steady_clock::now();
     auto mark = [&](const char* what) {
@@ -301,11 +314,14 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     if (dev_alloc(E, &S.crow, nnz)) return SVBFM_ERR_OOM;
     if (dev_alloc(E, &S.y, n)) return SVBFM_ERR_OOM;
     float* d_x = nullptr;
+    temps.own((void**)&d_x);
     SV_CUDA(E, sv_malloc((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4));
     // The values and the targets are not needed before the CSR gather / the case re-ordering: they travel on a second stream
     // while the main stream sorts the case ids (pinned host buffers; with pageable memory the copies serialise anyway).
     cudaStream_t cs = E->copy_stream ? E->copy_stream : st;
+    temps.side = (cs != st) ? cs : nullptr;
     uint32_t* d_flags = nullptr;   // [0] any x != 1  [1] case id out of range  [2] duplicate feature in a case  [3] non-uniform  [4] perm not identity
+    temps.own((void**)&d_flags);
     SV_CUDA(E, sv_malloc((void**)&d_flags, 8 * 4));
     SV_CUDA(E, cudaMemsetAsync(d_flags, 0, 8 * 4, st));
     if (cs != st) {                // everything queued on the main stream so far (earlier users of the recycled blocks, the memset) first
@@ -320,6 +336,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     if (nnz) k_check_case_ids<<<nblk(nnz), 256, 0, st>>>(S.crow, nnz, n, d_flags + 1);
     // CSC -> CSR: feature id per entry, stable sort by case id
     uint32_t *d_colof = nullptr, *d_idx = nullptr, *d_skeys = nullptr, *d_sidx = nullptr;
+    temps.own((void**)&d_colof); temps.own((void**)&d_idx); temps.own((void**)&d_skeys); temps.own((void**)&d_sidx);
     SV_CUDA(E, sv_malloc((void**)&d_colof, std::max<uint64_t>(nnz, 1) * 4));
     SV_CUDA(E, sv_malloc((void**)&d_idx, std::max<uint64_t>(nnz, 1) * 4));
     if (nnz) {
@@ -331,26 +348,29 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     SV_CUDA(E, cudaStreamSynchronize(st));
     if (h_flags[1]) {
         cudaStreamSynchronize(cs);
-        sv_free(d_x); sv_free(d_flags); sv_free(d_colof); sv_free(d_idx);
+        drop(d_x); drop(d_flags); drop(d_colof); drop(d_idx);
         return fail(E, SVBFM_ERR_ARG, "set_csc: case id out of range");
     }
     mark("H2D of the case ids + col_of_entry");
     if (int r = sort_pairs(E, S.crow, d_idx, nnz, std::max<uint32_t>(n, 1), &d_skeys, &d_sidx)) { cudaStreamSynchronize(cs); return r; }
     mark("  sort pairs by case");
-    sv_free(d_idx);
+    drop(d_idx);
     uint64_t* d_rowptr = nullptr;
+    temps.own((void**)&d_rowptr);
     SV_CUDA(E, sv_malloc((void**)&d_rowptr, ((size_t)n + 1) * 8));
     k_rowptr_from_sorted<<<nblk((uint64_t)n + 1), 256, 0, st>>>(d_skeys, nnz, n, d_rowptr);
     mark("  rowptr");
-    sv_free(d_skeys);
+    drop(d_skeys);
     uint32_t* d_rcol = nullptr; float* d_rval = nullptr;
+    temps.own((void**)&d_rcol); temps.own((void**)&d_rval);
     SV_CUDA(E, sv_malloc((void**)&d_rcol, std::max<uint64_t>(nnz, 1) * 4));
     if (nnz) k_gather_u32<<<nblk(nnz), 256, 0, st>>>(d_colof, d_sidx, nnz, d_rcol);
-    sv_free(d_colof);
+    drop(d_colof);
     mark("sort by case + CSR gather");
 
     // per-case scan: duplicates, uniform length, need[]
     uint32_t* d_need = nullptr;
+    temps.own((void**)&d_need);
     if (is_train) {
         SV_CUDA(E, sv_malloc((void**)&d_need, std::max<uint32_t>(S.ncols_ext, 1) * 4));
         SV_CUDA(E, cudaMemsetAsync(d_need, 0, std::max<uint32_t>(S.ncols_ext, 1) * 4, st));
@@ -364,12 +384,12 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         SV_CUDA(E, sv_malloc((void**)&d_rval, std::max<uint64_t>(nnz, 1) * 4));
         if (nnz) k_gather_f32<<<nblk(nnz), 256, 0, st>>>(d_x, d_sidx, nnz, d_rval);
     }
-    sv_free(d_sidx);
+    drop(d_sidx);
     mark("  H2D of values and targets (overlapped) + row scan");
     SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
     SV_CUDA(E, cudaStreamSynchronize(st));
     if (h_flags[2]) {
-        sv_free(d_x); sv_free(d_flags); sv_free(d_rowptr); sv_free(d_rcol); sv_free(d_rval); sv_free(d_need);
+        drop(d_x); drop(d_flags); drop(d_rowptr); drop(d_rcol); drop(d_rval); drop(d_need);
         return fail(E, SVBFM_ERR_DATA, "set_csc: a feature id occurs twice in one case; not supported");
     }
     bool uniform = (n > 0) && (h_flags[3] == 0);
@@ -383,7 +403,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         std::vector<uint32_t> need(S.ncols_ext);
         SV_CUDA(E, cudaMemcpyAsync(need.data(), d_need, (size_t)S.ncols_ext * 4, cudaMemcpyDeviceToHost, st));
         SV_CUDA(E, cudaStreamSynchronize(st));
-        sv_free(d_need);
+        drop(d_need);
         E->runs.clear();
         uint32_t run_start = 0;
         for (uint32_t j = 0; j < S.ncols_ext; j++) {
@@ -456,7 +476,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
                 k_permute_rows<<<nblk(n), 256, 0, st>>>(d_rowptr, d_rcol, d_rval, d_perm, n, d_newptr, d_ncol, d_nval, d_nrow);
                 SV_CUDA(E, cudaStreamSynchronize(st));
                 sv_free(tmp); sv_free(d_len);
-                sv_free(d_rowptr); sv_free(d_rcol); sv_free(d_rval);
+                drop(d_rowptr); drop(d_rcol); drop(d_rval);
                 d_rowptr = d_newptr; d_rcol = d_ncol; d_rval = d_nval;
                 // new CSC = stable sort of the new CSR entries by feature id (case ids stay ascending per column)
                 uint32_t *d_eidx = nullptr, *d_k2 = nullptr, *d_v2 = nullptr;
@@ -470,7 +490,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
                     SV_CUDA(E, sv_malloc((void**)&d_cv, nnz * 4));
                     k_gather_f32<<<nblk(nnz), 256, 0, st>>>(d_rval, d_v2, nnz, d_cv);
                     SV_CUDA(E, cudaStreamSynchronize(st));
-                    sv_free(d_x); d_x = d_cv;
+                    drop(d_x); d_x = d_cv;
                 }
                 SV_CUDA(E, cudaStreamSynchronize(st));
                 sv_free(d_v2); sv_free(d_nrow);
@@ -504,13 +524,13 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         }
     }
     mark("case re-ordering + CSC rebuild");
-    sv_free(d_flags);
+    drop(d_flags);
     // keep
-    S.rcol = d_rcol; E->dev_bytes += nnz * 4;
-    S.rval = d_rval; if (d_rval) E->dev_bytes += nnz * 4;
-    if (S.all_ones) { sv_free(d_x); S.cval = nullptr; } else { S.cval = d_x; E->dev_bytes += nnz * 4; }
+    S.rcol = d_rcol; d_rcol = nullptr; E->dev_bytes += nnz * 4;
+    S.rval = d_rval; d_rval = nullptr; if (S.rval) E->dev_bytes += nnz * 4;
+    if (S.all_ones) { drop(d_x); S.cval = nullptr; } else { S.cval = d_x; d_x = nullptr; E->dev_bytes += nnz * 4; }
     S.uniformF = F;
-    if (F > 0) { sv_free(d_rowptr); S.rowptr = nullptr; } else { S.rowptr = d_rowptr; E->dev_bytes += ((size_t)n + 1) * 8; }
+    if (F > 0) { drop(d_rowptr); S.rowptr = nullptr; } else { S.rowptr = d_rowptr; d_rowptr = nullptr; E->dev_bytes += ((size_t)n + 1) * 8; }
 
     if (is_train && F == 2 && nnz) {
         if (dev_alloc(E, &S.cother, nnz)) return SVBFM_ERR_OOM;

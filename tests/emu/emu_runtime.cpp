@@ -13,6 +13,23 @@
 uint3 threadIdx, blockIdx;
 dim3 blockDim, gridDim;
 
+// SVBFM_EMU_BACKTRACE=1: print a native backtrace when an emulated kernel (or the engine) faults
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void emu_fault_handler(int sig) {
+    void* frames[64];
+    int n = backtrace(frames, 64);
+    const char msg[] = "[emu] fatal signal, native backtrace:\n";
+    (void)!write(2, msg, sizeof(msg) - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+__attribute__((constructor)) static void emu_install_fault_handler() {
+    if (getenv("SVBFM_EMU_BACKTRACE")) { signal(SIGSEGV, emu_fault_handler); signal(SIGBUS, emu_fault_handler); signal(SIGABRT, emu_fault_handler); }
+}
+
 namespace {
 
 #if defined(__x86_64__)
