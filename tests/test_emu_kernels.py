@@ -72,3 +72,15 @@ def test_experimental_variants_on_the_emulator(emu_lib):
            os.path.join(ROOT, "tests", "test_gpu_zy_errors.py")]           # and the error convention of the C-ABI
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "4 passed" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+def test_full_size_properties_on_divided_shapes(emu_lib):
+    """tests/test_gpu_zzzz_full_size.py (first-principles checks of the handed-back state at BASELINE's full sizes) on shapes divided
+    down to a few thousand ratings: proves the test's own arithmetic (torch fp64 restatement of y-hat, T, the hyper-parameters and the
+    free energy) against the engine before it meets 200 M ratings on a B200."""
+    env = dict(os.environ, SVBFM_LIB=emu_lib)
+    f = os.path.join(ROOT, "tests", "test_gpu_zzzz_full_size.py")
+    cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider",
+           f + "::test_vb_full_size_state_is_consistent[ml1m]", f + "::test_mcmc_full_size_state_is_consistent[1]"]
+    r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]

@@ -1,0 +1,231 @@
+"""-m gpu: BASELINE.json's configurations at their FULL sizes (1 M ... 200 M ratings), where the oracle cannot follow.
+What is checked are size-independent properties of the state the engine hands back through the C-ABI, each recomputed
+here from first principles with torch fp64 on the same device (plain gathers; nothing of the engine, nothing of the oracle):
+
+  * the cached residuals, kept incrementally through every column update of every step (vb.h:571, 638; mcmc.h:716, 833),
+    equal  y - yhat(parameters)  (mcmc: yhat - y)  recomputed from the final parameters;
+  * the running scalar  sum_i T_i  equals the case-wise T_i formula (vb.h:207-312) summed over the final parameters;
+  * alpha = N / sum(e^2 + T) (vb.h:450-454), sigma_0, sigma_w, sigma_v (vb.h:473-498) and the free energy (vb.h:646-681,
+    with the reference's 3.14) follow from that state;
+  * test RMSE (vbs.h:261-279) and svbfm_predict equal the clamped prediction of the final parameters;
+  * the two residual copies of the stream schedule are bit-identical (svbfm_copies_max_diff == 0.0);
+  * a second learn() on the same handle reproduces every statistic bit for bit (fixed summation orders, no fp atomics);
+  * vb_online: the cases of the epoch's last batch carry residuals consistent with the final parameters.
+
+Data: the bench's generator (synth.ratings_torch: Zipf(1) users and items, planted rank-8 model), same seeds as bench.py.
+On the emulator (SVBFM_LIB = tests/emu build; CPU suite runs one case) the same code runs on shapes divided down to a few
+thousand ratings, which checks the test itself; SVBFM_FULL_SIZE_DIV=<n> divides the shapes on a GPU too."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import svbfm_b200 as sv
+
+pytestmark = pytest.mark.gpu
+synth = sv.submodule("synth")
+
+
+def _emulated():
+    return "emu" in os.path.basename(os.environ.get("SVBFM_LIB", ""))
+
+
+def _shape(name):
+    U, I, N, Nt, K = synth.SHAPES[name]
+    div = int(os.environ.get("SVBFM_FULL_SIZE_DIV", "0")) or (max(1, N // 3000) if _emulated() else 1)
+    if div > 1:
+        U, I, N, Nt = max(24, U // div), max(16, I // div), max(600, N // div), max(100, Nt // div)
+        if _emulated():
+            K = min(K, 3)
+    return U, I, N, Nt, K
+
+
+def _data(name):
+    import torch
+    dev = "cpu" if _emulated() else "cuda:0"
+    U, I, N, Nt, K = _shape(name)
+    out = {}
+    for split, n, seed in (("train", N, 20261018), ("test", Nt, 20261019)):
+        u, it, y = synth.ratings_torch(n, U, I, seed, dev)
+        colptr, case_id = synth.csc_two_field_torch(u, it, U, I)
+        d = sv.CscData.__new__(sv.CscData)
+        d.colptr = colptr.cpu().numpy().view(np.uint64)
+        d.case_id = case_id.cpu().numpy().view(np.uint32)
+        d.x = np.ones(2 * n, dtype=np.float32)
+        d.target = y.cpu().numpy()
+        d.num_cases, d.num_feature = n, U + I
+        out[split] = (d, u.long(), it.long() + U, y.double())
+        del colptr, case_id
+    return dev, (U, I, N, Nt, K), out
+
+
+def _init_state(D, K, method, dev):
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(42)
+    var = 0.0 if method == "mcmc" else 0.02
+    return dict(w0_mean=0.0, w0_var=var,
+                w_mean=(0.1 * torch.randn(D, generator=g, device=dev, dtype=torch.float64)).cpu().numpy(),
+                w_var=np.full(D, var),
+                v_mean=(0.1 * torch.randn(K, D, generator=g, device=dev, dtype=torch.float64)).cpu().numpy(),
+                v_var=np.full((K, D), var))
+
+
+class _State:
+    """Final parameters of the engine as torch fp64 tensors + the case-wise quantities recomputed from them."""
+
+    def __init__(self, E, dev):
+        import torch
+        s = E.get_state()
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.w0, self.w0_var = s["w0_mean"], s["w0_var"]
+        self.w, self.w_var, self.v, self.v_var = t(s["w_mean"]), t(s["w_var"]), t(s["v_mean"]), t(s["v_var"])
+        self.K = self.v.shape[0]
+
+    def yhat(self, cu, ci):           # vb.h:70-203 for x = 1 and two features per case
+        acc = self.w0 + self.w[cu] + self.w[ci]
+        for f in range(self.K):
+            acc += self.v[f][cu] * self.v[f][ci]
+        return acc
+
+    def sum_t(self, cu, ci):          # vb.h:207-312: per factor (1/2 Z^2 + Z Q) - sum_j (mu^2 sigma + 1/2 sigma^2) = su si + su mi^2 + si mu^2
+        acc = self.w0_var + self.w_var[cu] + self.w_var[ci]
+        for f in range(self.K):
+            mu, mi, su, si = self.v[f][cu], self.v[f][ci], self.v_var[f][cu], self.v_var[f][ci]
+            acc += su * si + su * mi * mi + si * mu * mu
+        return float(acc.sum())
+
+
+def _rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+def _rmse_clamped(pred, y, lo=1.0, hi=5.0):
+    d = pred.clamp(lo, hi) - y
+    return math.sqrt(float((d * d).sum()) / y.numel())
+
+
+def _stats_bits(stats):
+    return [(s.test_rmse, s.train_stat, s.free_energy, s.alpha, s.rmse_this, s.nan_inf_count) for s in stats]
+
+
+VB_CASES = ["ml1m", "ml10m", "netflix", "kdd200m"]       # BASELINE.json configs[1..4]: K = 20, 50, 100, 50
+
+
+@pytest.mark.parametrize("name", VB_CASES)
+def test_vb_full_size_state_is_consistent(built, name):
+    import torch
+    dev, (U, I, N, Nt, K), data = _data(name)
+    D = U + I + 1                                         # libfm.cpp:215: the phantom attribute
+    (tr, cu, ci, y), (te, tu, ti, yt) = data["train"], data["test"]
+    state = _init_state(D, K, "vb", dev)
+    E = sv.Engine("vb", D, K, 1, 1, 1.0, 5.0, device=0, seed=42)
+    try:
+        runs = []
+        for rep in range(2):
+            if rep:
+                E.reset()
+            E.set_csc(sv.TRAIN, tr)
+            E.set_csc(sv.TEST, te)
+            E.set_state(state)
+            E.begin()
+            runs.append(E.run(2))
+        assert _stats_bits(runs[0]) == _stats_bits(runs[1]), "a second learn() on the same data must reproduce every bit"
+        last = runs[1][-1]
+        assert last.has_free_energy and last.nan_inf_count == 0
+        info = E.info()
+        if U * I > 0:
+            assert info["fused_schedule"] & 1, "two complete one-hot fields must take the stream schedule"
+        assert E.copies_max_diff() == 0.0
+
+        S = _State(E, dev)
+        e = torch.from_numpy(E.get_residuals()).to(dev)
+        e_ref = y - S.yhat(cu, ci)
+        assert float((e - e_ref).abs().max()) < 1e-9
+        sum_t = E.get_sum_t()
+        assert _rel(sum_t, S.sum_t(cu, ci)) < 1e-10
+        sse = float((e * e).sum())
+        hy = E.get_hyper()
+        assert _rel(hy["alpha"], N / (sse + sum_t)) < 1e-10 and hy["alpha"] == last.alpha
+        assert _rel(hy["sigma_0"], 1.0 / (S.w0 * S.w0 + S.w0_var)) < 1e-12
+        sw = D / float((S.w * S.w + S.w_var).sum())
+        assert _rel(float(hy["sigma_w"][0]), sw) < 1e-10
+        sv_ref = D / (S.v * S.v + S.v_var).sum(1)
+        got = torch.from_numpy(np.ascontiguousarray(hy["sigma_v"][0])).to(dev)
+        assert float(((got - sv_ref).abs() / sv_ref).max()) < 1e-10
+        # free energy of that state (vb.h:646-681)
+        a = hy["alpha"]
+        fe = -0.5 * a * (sse + sum_t) - 0.5 * N * math.log(2 * 3.14 / a)
+        fe += -0.5 * hy["sigma_0"] * (S.w0 * S.w0 + S.w0_var) + 0.5 * math.log(S.w0_var * hy["sigma_0"]) + 0.5
+        fe += float((-0.5 * sw * (S.w * S.w + S.w_var) + 0.5 * torch.log(S.w_var * sw) + 0.5).sum())
+        fe += float((-0.5 * sv_ref[:, None] * (S.v * S.v + S.v_var) + 0.5 * torch.log(S.v_var * sv_ref[:, None]) + 0.5).sum())
+        assert _rel(last.free_energy, fe) < 1e-9, (last.free_energy, fe)
+        # test split
+        pt = S.yhat(tu, ti)
+        assert _rel(last.test_rmse, _rmse_clamped(pt, yt)) < 1e-10
+        got = torch.from_numpy(E.predict(sv.TEST)).to(dev)
+        assert float((got - pt.clamp(1.0, 5.0)).abs().max()) < 1e-10
+    finally:
+        E.close()
+
+
+@pytest.mark.parametrize("do_sample", [1, 0])
+def test_mcmc_full_size_state_is_consistent(built, do_sample):
+    """BASELINE.json configs[2]: ML-10M shape, K = 50, mcmc (and als = mcmc without sampling)."""
+    import torch
+    dev, (U, I, N, Nt, K), data = _data("ml10m")
+    D = U + I + 1
+    (tr, cu, ci, y), (te, tu, ti, yt) = data["train"], data["test"]
+    state = _init_state(D, K, "mcmc", dev)
+    E = sv.Engine("mcmc", D, K, 1, 1, 1.0, 5.0, device=0, seed=42, do_sample=do_sample, reg=(0.0, 0.0, 0.0) if do_sample else (0.0, 1.0, 5.0))
+    try:
+        runs = []
+        for rep in range(2):
+            if rep:
+                E.reset()
+            E.set_csc(sv.TRAIN, tr)
+            E.set_csc(sv.TEST, te)
+            E.set_state(state)
+            E.begin()
+            runs.append(E.run(2))
+        assert _stats_bits(runs[0]) == _stats_bits(runs[1]), "the Philox draws are keyed by (seed, iteration, factor, column): same run, same bits"
+        last = runs[1][-1]
+        assert last.nan_inf_count == 0 and math.isfinite(last.test_rmse)
+        assert E.copies_max_diff() == 0.0
+        S = _State(E, dev)
+        e = torch.from_numpy(E.get_residuals()).to(dev)
+        assert float((e - (S.yhat(cu, ci) - y)).abs().max()) < 1e-9          # mcmc: e = yhat - y (mcmc.h:52-55)
+        assert _rel(last.rmse_this, _rmse_clamped(S.yhat(tu, ti), yt)) < 1e-10   # rmse of this draw (mcmcs.h:226-233)
+        assert last.test_rmse <= max(s.rmse_this for s in runs[1]) + 1e-12    # the running mean cannot be worse than its worst draw
+    finally:
+        E.close()
+
+
+def test_vb_online_full_size_last_batch_is_consistent(built):
+    """BASELINE.json configs[4]: 200 M ratings, K = 50, vb_online with 100 batches per epoch (one epoch)."""
+    import torch
+    dev, (U, I, N, Nt, K), data = _data("kdd200m")
+    D = U + I                                             # vb_online: max id + 1 (libfm.cpp:160-171)
+    B = 100
+    (tr, cu, ci, y), (te, tu, ti, yt) = data["train"], data["test"]
+    state = _init_state(D, K, "vb_online", dev)
+    size = -(-N // B)
+    batch_of_case = (np.random.default_rng(7).permutation(N) // size).astype(np.uint32)     # a shuffled balanced split (vbos.h:74-95)
+    E = sv.Engine("vb_online", D, K, 1, 1, 1.0, 5.0, device=0, seed=42)
+    try:
+        E.set_csc(sv.TRAIN, tr)
+        E.set_csc(sv.TEST, te)
+        E.set_state(state)
+        E.begin()
+        s = E.vb_online_epoch(batch_of_case, B)
+        assert math.isfinite(s.test_rmse) and math.isfinite(s.free_energy) and math.isfinite(s.free_energy_first) and s.nan_inf_count == 0
+        assert E.copies_max_diff() == 0.0
+        S = _State(E, dev)
+        assert _rel(s.test_rmse, _rmse_clamped(S.yhat(tu, ti), yt)) < 1e-10
+        # the cases of the last batch were predicted afresh at the start of their batch and updated incrementally since
+        sel = torch.from_numpy(np.nonzero(batch_of_case == B - 1)[0]).to(dev)
+        e = torch.from_numpy(E.get_residuals()).to(dev)[sel]
+        assert sel.numel() > 0 and float((e - (y[sel] - S.yhat(cu[sel], ci[sel]))).abs().max()) < 1e-9
+    finally:
+        E.close()

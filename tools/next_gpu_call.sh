@@ -9,7 +9,10 @@ out=gpurun_out
 py=python
 
 # 1. the default path: full GPU suite (includes the vb_online batch lists, now the default)
-timeout 600 $py -m pytest tests -m gpu -x -q > $out/next_pytest_gpu.log 2>&1; echo "pytest -m gpu rc=$?" | tee $out/next_summary.txt
+timeout 600 $py -m pytest tests -m gpu -x -q --deselect tests/test_gpu_zzzz_full_size.py > $out/next_pytest_gpu.log 2>&1; echo "pytest -m gpu rc=$?" | tee $out/next_summary.txt
+
+# 1b. BASELINE's full sizes (first-principles checks of the handed-back state; written without a GPU)
+timeout 900 $py -m pytest tests/test_gpu_zzzz_full_size.py -m gpu -q --durations=0 > $out/next_pytest_full_size.log 2>&1; echo "full-size properties rc=$?" | tee -a $out/next_summary.txt
 
 # 2. the experiments, each alone (a hang or a wrong result in one must not hide the others)
 timeout 600 $py -m pytest tests/test_gpu_zz_experiments.py -m gpu -q -k 'rec_rank or graph' > $out/next_pytest_rec_rank.log 2>&1; echo "rec_rank tests rc=$?" | tee -a $out/next_summary.txt
