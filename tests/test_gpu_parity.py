@@ -307,3 +307,27 @@ def test_reset_reuses_handle(built):
     E.set_csc(sv.TRAIN, to_csc(tr)); E.set_csc(sv.TEST, to_csc(te)); E.set_state(L._state); E.begin()
     h2 = [(s.test_rmse, s.free_energy) for s in E.run(3)]
     assert h1 == h2
+
+
+@pytest.mark.parametrize("method", ["vb", "mcmc", "vb_online"])
+def test_degenerate_splits(built, method):
+    """An empty test split (the reference divides by zero cases and prints `Test=nan`, vbs.h:261-279 / mcmcs.h:226-233), a single
+    train case (one tile, one entry per column, every other column empty) and a train split that is smaller than one warp."""
+    kw = dict(do_sample=False, do_multilevel=False) if method == "mcmc" else dict(num_batch=2) if method == "vb_online" else {}
+    tr, te = two_field(500, 50, 20, 15, seed=5)
+    empty = ob.Csr(np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint32), np.zeros(0, dtype=np.float32), np.zeros(0, dtype=np.float32))
+    one, _ = two_field(1, 5, 20, 15, seed=6)
+    few, _ = two_field(7, 5, 20, 15, seed=7)
+    cases = [(tr, empty), (few, te)] + ([(one, te)] if method != "vb_online" else [])      # vb_online: one case in two batches leaves a batch empty (DESIGN section 2)
+    for a, b in cases:
+        orc = ob.Oracle(method, a, b, K=2, seed=42, **kw)
+        want = [orc.iterate() for _ in range(3)]          # the oracle first: vb_online replays the process-global libc rand() stream on both sides
+        L = make_learner(method, a, b, 2, num_iter=3, **kw)
+        same = lambda x, y: (np.isnan(x) and np.isnan(y)) or (x == 0.0 and y == 0.0) or rel(x, y) < VB_TOL
+        for it, (s, o) in enumerate(zip(L.learn(to_csc(a), to_csc(b)), want)):
+            assert np.isnan(o.test_rmse) == (b.n_rows == 0)
+            assert same(s.test_rmse, o.test_rmse), (method, a.n_rows, it, s.test_rmse, o.test_rmse)
+            assert same(s.train_stat, o.train_stat), (method, a.n_rows, it, s.train_stat, o.train_stat)
+            if method != "mcmc":
+                assert same(s.free_energy, o.free_energy), (method, a.n_rows, it, s.free_energy, o.free_energy)
+        L.engine.close()
