@@ -19,20 +19,12 @@ using namespace svbfm_host;
 
 // pre-scan for the online method (libfm.cpp:528-599): number of cases, largest feature id (NOT +1), target range
 static void find_max_feature(DataSet& d, const std::string& file) {
-    std::ifstream in(file.c_str());
-    d.num_cases = 0; d.num_feature = 0; d.min_target = +FLT_MAX; d.max_target = -FLT_MAX;
-    std::string line;
-    while (std::getline(in, line)) {
-        const char* p = line.c_str();
-        if (LineParser::skip_line(p)) continue;
-        float t;
-        if (!LineParser::scan_float(p, t)) throw "cannot parse line \"" + line + "\" at character " + p[0];
-        d.min_target = std::min(t, d.min_target); d.max_target = std::max(t, d.max_target);
-        long id; float v;
-        while (LineParser::scan_pair(p, id, v)) d.num_feature = std::max<int>((int)id, d.num_feature);
-        LineParser::finish(p, line);
-        d.num_cases++;
-    }
+    ParsedText t;
+    parse_text_file(file, t, false);              // targets + largest id only (data.h: the parallel text parser)
+    d.num_cases = (uint32_t)t.target.size();
+    d.num_feature = (int)t.max_id;
+    d.min_target = +FLT_MAX; d.max_target = -FLT_MAX;
+    for (float v : t.target) { d.min_target = std::min(v, d.min_target); d.max_target = std::max(v, d.max_target); }
 }
 
 static void exchange_comm_id(ShardInfo& sh) {
