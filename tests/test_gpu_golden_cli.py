@@ -18,6 +18,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "tests", "golden")
 GOLD = json.load(open(os.path.join(G, "golden.json")))["cases"]
+# six more runs of the reference binary, among them 100 iterations of `-method vb -dim '1,1,8'` (the switches of BASELINE config 1)
+GOLD = GOLD + json.load(open(os.path.join(G, "golden_extra.json")))["cases"]
 EXE = os.path.join(sv.PKG_DIR, "bin", "libFM")
 TOL = 1e-4
 
