@@ -127,7 +127,8 @@ int svbfm_mcmc_sweep(svbfm_t* h, svbfm_iter_stats* out);
 /* replaces: one epoch of the vb_online loop (vbos.h:66-288; vbo.h:354-468). batch_of_case[i] in [0,num_batch)
  * is the batch of local train case i (the host replays std::random_shuffle, vbos.h:74-95). Batches are case
  * subsets of the resident design matrix (the reference writes and re-parses batch files); on two complete fields
- * (one GPU) every batch is swept on its own entries through per-epoch index lists, otherwise with a batch mask. */
+ * every batch is swept on its own entries through per-epoch index lists (sharded: per-batch column counts and {A, B}
+ * sums are allreduced), otherwise with a batch mask. */
 int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t num_batch, svbfm_iter_stats* out);
 /* forget data + state of a handle but keep the device context, communicator and groups (a long-lived service handle:
  * the next learn() starts again at svbfm_set_csc). No reference counterpart: the reference builds a new learner per process. */

@@ -229,3 +229,24 @@ def test_vb_online_full_size_last_batch_is_consistent(built):
         assert sel.numel() > 0 and float((e - (y[sel] - S.yhat(cu[sel], ci[sel]))).abs().max()) < 1e-9
     finally:
         E.close()
+
+
+def test_mcmc_one_million_ratings_within_half_percent(built):
+    """north_star's MCMC bar, literally: test RMSE of the running mean within 0.5 % of the reference's after a fixed number of sweeps
+    under a stated seed, on >= 1 M ratings (below that the reference's own seed-to-seed spread is larger than the bound).
+    ML-1M shape (6040 users x 3952 items, 1 M train / 100 k test ratings), K = 8, 10 sweeps, sampling on, seed 42 on both sides
+    (different generators: libc rand() in the oracle, Philox in the engine). The oracle needs ~7 s of CPU for this.
+    On the emulator (4 minutes, run once by hand): 0.836526 against the oracle's 0.836438, 1.0e-4 relative."""
+    if _emulated() and not os.environ.get("SVBFM_RUN_SLOW"):
+        pytest.skip("4 minutes on the emulator: set SVBFM_RUN_SLOW=1")
+    import oracle_binding as ob
+    from helpers import make_learner, to_csc, two_field
+    tr, te = two_field(1_000_000, 100_000, 6040, 3952, seed=61)
+    orc = ob.Oracle("mcmc", tr, te, K=8, seed=42)
+    for _ in range(10):
+        o = orc.iterate()
+    L = make_learner("mcmc", tr, te, 8, num_iter=10)
+    hist = L.learn(to_csc(tr), to_csc(te))
+    assert abs(hist[-1].test_rmse - o.test_rmse) < 0.005 * o.test_rmse, (hist[-1].test_rmse, o.test_rmse)
+    assert all(a.test_rmse > b.test_rmse for a, b in zip(hist, hist[1:])), "the running mean keeps improving over the first sweeps on this data"
+    L.engine.close()
