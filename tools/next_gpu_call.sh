@@ -33,3 +33,14 @@ for w in ml1m ml10m; do
 done
 grep -h -o '"ms_per_step": [0-9.]*' $out/next_bench_*.json | paste -d' ' - - - - - - 2>/dev/null | tee -a $out/next_summary.txt
 for f in $out/next_bench_*.json; do echo "$f $(grep -o '"ms_per_step": [0-9.]*' $f | head -1)"; done | tee -a $out/next_summary.txt
+
+# 4. ncu (only after the plain runs above): launch list of one iteration and a full capture of two steady k_stream launches
+#    (field 0 + field 1), default layout and rank-ordered records; read here with `ncu -i ... --page raw --csv`
+if grep -q '"ms_per_step"' $out/next_bench_default.json 2>/dev/null; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/next_launches_default.csv \
+    $py bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $out/next_ncu_launches.log 2>&1; echo "ncu launch list rc=$?" | tee -a $out/next_summary.txt
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stream -s 12 -c 2 -f -o $out/next_ncu_k_stream_default \
+    $py bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $out/next_ncu_default.log 2>&1; echo "ncu k_stream (default) rc=$?" | tee -a $out/next_summary.txt
+  SVBFM_REC_RANK=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stream -s 12 -c 2 -f -o $out/next_ncu_k_stream_rec_rank \
+    $py bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $out/next_ncu_rec_rank.log 2>&1; echo "ncu k_stream (rec_rank) rc=$?" | tee -a $out/next_summary.txt
+fi
