@@ -1100,8 +1100,6 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
     SV_CUDA(E, cudaSetDevice(E->dev));
     cudaStream_t st = E->stream;
     const DevSplit& S = E->tr;
-    for (uint32_t i = 0; i < S.n; i++)
-        if (batch_of_case[i] >= num_batch) return fail(E, SVBFM_ERR_ARG, "svbfm_vb_online_epoch: batch id out of range");
     if (!E->d_rbatch) {
         if (dev_alloc(E, &E->d_rbatch, S.n)) return SVBFM_ERR_OOM;
         if (dev_alloc(E, &E->d_cbatch, S.nnz)) return SVBFM_ERR_OOM;
@@ -1116,6 +1114,18 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
     uint32_t* d_boc = nullptr;
     SV_CUDA(E, sv_malloc((void**)&d_boc, std::max<size_t>(S.n, 1) * 4));
     SV_CUDA(E, cudaMemcpyAsync(d_boc, batch_of_case, (size_t)S.n * 4, cudaMemcpyHostToDevice, st));
+    if (S.n) {      // ids out of range are rejected before anything is indexed by them
+        uint32_t* d_bad = nullptr;
+        uint32_t h_bad = 0;
+        cudaError_t ce = sv_malloc((void**)&d_bad, 4);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(d_bad, 0, 4, st);
+        if (ce == cudaSuccess) { k_vbo_check_batch_ids<<<nblk(S.n), 256, 0, st>>>(d_boc, S.n, num_batch, d_bad); LAUNCHED(E); ce = cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, st); }
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        sv_free(d_bad);
+        if (ce != cudaSuccess || h_bad) sv_free(d_boc);
+        SV_CUDA(E, ce);
+        if (h_bad) return fail(E, SVBFM_ERR_ARG, "svbfm_vb_online_epoch: batch id out of range");
+    }
     SV_CUDA(E, cudaMemsetAsync(E->d_batch_cnt, 0, (size_t)num_batch * 8, st));
     if (S.n) {
         k_vbo_set_rbatch<<<nblk(S.n), 256, 0, st>>>(d_boc, S.perm, S.n, E->d_rbatch); LAUNCHED(E);

@@ -1667,6 +1667,11 @@ __global__ void k_vbo_hyper(Scalars* sc, const double* __restrict__ grp, const d
     st->alpha = sc->alpha;
 }
 
+// vb_online: the caller's batch ids are checked on the device (the copy is needed anyway; a host loop over 2*10^8 ids is not)
+__global__ void k_vbo_check_batch_ids(const uint32_t* __restrict__ batch_of_case, uint32_t n, uint32_t num_batch, uint32_t* __restrict__ flag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && batch_of_case[i] >= num_batch) *flag = 1u;
+}
 // vb_online: batch id of every case in device order, and of the case of every CSC entry
 __global__ void k_vbo_set_rbatch(const uint32_t* __restrict__ batch_of_case, const uint32_t* __restrict__ perm, uint32_t n, uint16_t* __restrict__ rbatch) {
     uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
