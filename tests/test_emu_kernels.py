@@ -84,3 +84,12 @@ def test_full_size_properties_on_divided_shapes(emu_lib):
            f + "::test_vb_full_size_state_is_consistent[ml1m]", f + "::test_mcmc_full_size_state_is_consistent[1]"]
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+def test_randomised_differential_run(emu_lib):
+    """tools/fuzz_parity.py: random data shapes (one-hot, real values, ragged, three fields), methods, switches, groups and tile
+    sizes against the oracle, statistics of every iteration and the final parameters; 60 cases here, thousands when run by hand."""
+    env = dict(os.environ, SVBFM_LIB=emu_lib)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "--cases", "60", "--seed", "5", "--seconds", "600"],
+                       env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "60 cases, no mismatch" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -1,0 +1,115 @@
+"""Randomised differential run of the engine against the CPU oracle (test infrastructure; not part of the product).
+Draws data shapes (two one-hot fields with or without values, ragged multi-hot, three fields), methods (vb, als, vb_online),
+switches (k0, k1, K, groups, tile size) and compares every iteration's statistics and the final parameters.
+  SVBFM_LIB=tests/emu/_build/libsvbfm_emu.so python tools/fuzz_parity.py --seconds 600 --seed 1     # on the emulator
+  python tools/fuzz_parity.py --seconds 120                                                          # on a B200
+Prints one line per case and exits non-zero at the first mismatch (the line holds everything needed to replay it)."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import oracle_binding as ob      # noqa: E402  (the checker)
+import svbfm_b200 as sv          # noqa: E402
+from helpers import make_learner, ragged, rel, to_csc, two_field      # noqa: E402
+
+
+def three_fields(N, Nt, sizes, seed):
+    """Three one-hot fields, the third one optional per case (ragged rows, three field runs)."""
+    def make(n, s):
+        r = np.random.default_rng(s)
+        cols, ptr = [], [0]
+        off = np.concatenate([[0], np.cumsum(sizes)])
+        for _ in range(n):
+            row = [off[0] + r.integers(sizes[0]), off[1] + r.integers(sizes[1])]
+            if r.random() < 0.7:
+                row.append(off[2] + r.integers(sizes[2]))
+            cols += row
+            ptr.append(len(cols))
+        val = np.ones(len(cols), dtype=np.float32)
+        return ob.Csr(np.array(ptr, dtype=np.uint64), np.array(cols, dtype=np.uint32), val, r.integers(1, 6, n).astype(np.float32))
+    return make(N, seed), make(Nt, seed + 1)
+
+
+def one_case(r, case_id):
+    kind = r.choice(["two", "two_values", "ragged", "three"])
+    method = r.choice(["vb", "vb", "als", "vb_online"])
+    N = int(r.choice([1, 7, 33, 300, 2500, 9000]))
+    Nt = int(r.choice([0, 5, 200]))
+    K = int(r.choice([0, 1, 2, 3, 5]))
+    k0, k1 = int(r.random() < 0.8), int(r.random() < 0.8)
+    tile = int(r.choice([0, 0, 32, 64, 256]))
+    seed = int(r.integers(1, 10_000))
+    if kind in ("two", "two_values"):
+        U, I = int(r.choice([3, 20, 150])), int(r.choice([2, 15, 120]))
+        tr, te = two_field(N, max(Nt, 1), U, I, seed=seed, values=(kind == "two_values"))
+    elif kind == "ragged":
+        tr, te = ragged(N, max(Nt, 1), int(r.choice([6, 40])), seed=seed, max_nnz=int(r.choice([2, 5])))
+    else:
+        tr, te = three_fields(N, max(Nt, 1), [int(r.choice([4, 30])), int(r.choice([3, 25])), int(r.choice([2, 9]))], seed)
+    if Nt == 0:
+        te = ob.Csr(np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint32), np.zeros(0, dtype=np.float32), np.zeros(0, dtype=np.float32))
+    D = max(tr.n_feat, te.n_feat) + (0 if method == "vb_online" else 1)
+    if D == 0 or (method != "vb_online" and D == 1):      # no feature at all: svbfm_create rejects the dimensions
+        return f"case {case_id}: no features, skipped", None
+    groups = None
+    if r.random() < 0.4 and D >= 2:
+        groups = (np.arange(D) * int(r.choice([2, 3])) // D).astype(np.uint32)
+    kw, okw = {}, {}
+    if method == "als":
+        kw = okw = dict(do_sample=False, do_multilevel=False)
+    if method == "vb_online":
+        nb = int(r.choice([1, 2, 5]))
+        if -(-N // nb) * (nb - 1) >= N:        # an empty batch: the reference prints NaN and stops
+            nb = 1
+        kw = okw = dict(num_batch=nb)
+    iters = int(r.choice([1, 3]))
+    desc = f"case {case_id}: {kind} {method} N={N} Nt={Nt} K={K} k0={k0} k1={k1} tile={tile} seed={seed} groups={None if groups is None else int(groups.max()) + 1} {kw}"
+    m = "mcmc" if method == "als" else method
+    orc = ob.Oracle(m, tr, te, K=K, seed=42, k0=k0, k1=k1, groups=groups, **okw)
+    want = [orc.iterate() for _ in range(iters)]
+    so = orc.get_state()
+    L = make_learner(m, tr, te, K, num_iter=iters, k0=k0, k1=k1, groups=groups, tile_entries=tile, **kw)
+    hist = L.learn(to_csc(tr), to_csc(te))
+    stol = 1e-7 if kind in ("two", "three") else 2e-6         # real values: see the note on the parameters below
+    same = lambda x, y: (np.isnan(x) and np.isnan(y)) or (abs(x) < 1e-8 and abs(y) < 1e-8) or rel(x, y) < stol
+    for it, (s, o) in enumerate(zip(hist, want)):
+        for name in ("test_rmse", "train_stat") + (("free_energy", "alpha") if m != "mcmc" else ()):
+            a, b = getattr(s, name), getattr(o, name)
+            if not same(a, b):
+                return desc, f"iteration {it}: {name} {a!r} != {b!r}"
+    sg = L.engine.get_state()
+    # x = 1: only the summation order differs (1e-9). Real values: the reference's cached S2 / S3 keep a float-rounding residue of the
+    # entry's own column (added as sigma*x*x in double, subtracted as (x*x in float)*sigma, vb.h:372-373 against :591, 629-630), which a
+    # sum over the OTHER features does not have: 6e-8 relative per term
+    tol = 1e-9 if kind in ("two", "three") else 2e-6
+    for k in ("w_mean", "w_var", "v_mean", "v_var"):
+        if so[k].size and not np.allclose(so[k], sg[k], rtol=tol, atol=tol, equal_nan=True):
+            return desc, f"final {k}: max diff {np.nanmax(np.abs(so[k] - sg[k]))}"
+    L.engine.close()
+    return desc, None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=300)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cases", type=int, default=10**9)
+    a = ap.parse_args()
+    r = np.random.default_rng(a.seed)
+    t0, n = time.time(), 0
+    while time.time() - t0 < a.seconds and n < a.cases:
+        desc, err = one_case(r, n)
+        print(desc, "OK" if err is None else "MISMATCH " + err, flush=True)
+        if err is not None:
+            sys.exit(1)
+        n += 1
+    print(f"{n} cases, no mismatch")
+
+
+if __name__ == "__main__":
+    main()
