@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <functional>
+#include <tuple>
 
 #define SVBFM_EMULATED 1
 

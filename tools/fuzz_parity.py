@@ -35,7 +35,7 @@ def three_fields(N, Nt, sizes, seed):
     return make(N, seed), make(Nt, seed + 1)
 
 
-def one_case(r, case_id):
+def one_case(r, case_id, run=True):
     kind = r.choice(["two", "two_values", "ragged", "three"])
     method = r.choice(["vb", "vb", "als", "vb_online"])
     N = int(r.choice([1, 7, 33, 300, 2500, 9000]))
@@ -69,6 +69,8 @@ def one_case(r, case_id):
         kw = okw = dict(num_batch=nb)
     iters = int(r.choice([1, 3]))
     desc = f"case {case_id}: {kind} {method} N={N} Nt={Nt} K={K} k0={k0} k1={k1} tile={tile} seed={seed} groups={None if groups is None else int(groups.max()) + 1} {kw}"
+    if not run:
+        return desc + " (skipped)", None
     m = "mcmc" if method == "als" else method
     orc = ob.Oracle(m, tr, te, K=K, seed=42, k0=k0, k1=k1, groups=groups, **okw)
     want = [orc.iterate() for _ in range(iters)]
@@ -99,11 +101,13 @@ def main():
     ap.add_argument("--seconds", type=float, default=300)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cases", type=int, default=10**9)
+    ap.add_argument("--only", type=str, default="", help="replay: run only these cases of the sequence (comma-separated)")
     a = ap.parse_args()
+    only = {int(x) for x in a.only.split(",") if x}
     r = np.random.default_rng(a.seed)
     t0, n = time.time(), 0
     while time.time() - t0 < a.seconds and n < a.cases:
-        desc, err = one_case(r, n)
+        desc, err = one_case(r, n, run=(not only or n in only))
         print(desc, "OK" if err is None else "MISMATCH " + err, flush=True)
         if err is not None:
             sys.exit(1)
