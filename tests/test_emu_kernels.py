@@ -93,3 +93,11 @@ def test_randomised_differential_run(emu_lib):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "--cases", "60", "--seed", "5", "--seconds", "600"],
                        env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "60 cases, no mismatch" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_randomised_sharded_run(emu_lib):
+    """tools/fuzz_sharded.py: three PROCESSES (fake NCCL), random shapes / methods / switches / shard modes (contiguous case ranges,
+    user blocks, ranks without a case) against the single-process oracle; parameters bit-identical on every rank. 40 cases here."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_sharded.py"), "--world", "3", "--cases", "40", "--seed", "7", "--seconds", "600"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0 and "40 cases, no mismatch" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
