@@ -60,15 +60,22 @@ def one_case(r, case_id, run=True):
     if r.random() < 0.4 and D >= 2:
         groups = (np.arange(D) * int(r.choice([2, 3])) // D).astype(np.uint32)
     kw, okw = {}, {}
+    task = 0
     if method == "als":
         kw = okw = dict(do_sample=False, do_multilevel=False)
+        if r.random() < 0.35:                  # binary classification (-task c): targets -1 / +1, regularised like a libFM run with -regular
+            task = 1
+            for d in (tr, te):
+                d.y[:] = np.where(d.y >= 4, 1.0, -1.0).astype(np.float32)
+            kw = dict(kw, task=1)
+            okw = dict(okw, task=1, reg=(0.0, 0.5, 1.0))
     if method == "vb_online":
         nb = int(r.choice([1, 2, 5]))
         if -(-N // nb) * (nb - 1) >= N:        # an empty batch: the reference prints NaN and stops
             nb = 1
         kw = okw = dict(num_batch=nb)
     iters = int(r.choice([1, 3]))
-    desc = f"case {case_id}: {kind} {method} N={N} Nt={Nt} K={K} k0={k0} k1={k1} tile={tile} seed={seed} groups={None if groups is None else int(groups.max()) + 1} {kw}"
+    desc = f"case {case_id}: {kind} {method}{" -task c" if task else ""} N={N} Nt={Nt} K={K} k0={k0} k1={k1} tile={tile} seed={seed} groups={None if groups is None else int(groups.max()) + 1} {kw}"
     if not run:
         return desc + " (skipped)", None
     m = "mcmc" if method == "als" else method
@@ -76,7 +83,18 @@ def one_case(r, case_id, run=True):
     want = [orc.iterate() for _ in range(iters)]
     so = orc.get_state()
     L = make_learner(m, tr, te, K, num_iter=iters, k0=k0, k1=k1, groups=groups, tile_entries=tile, **kw)
+    if task:
+        L.fm.reg0, L.fm.regw, L.fm.regv = 0.0, 0.5, 1.0
     hist = L.learn(to_csc(tr), to_csc(te))
+    if task:                                   # accuracies: at most a borderline case or two; residuals against the latent targets
+        for it, (s, o) in enumerate(zip(hist, want)):
+            if abs(s.train_stat - o.train_stat) > 2.0 / max(tr.n_rows, 1) or (te.n_rows and abs(s.test_rmse - o.test_rmse) > 2.0 / te.n_rows):
+                return desc + " task=c", f"iteration {it}: accuracies {s.train_stat!r}, {s.test_rmse!r} != {o.train_stat!r}, {o.test_rmse!r}"
+        e_o, _ = orc.get_train_cache(want_t=False)
+        if tr.n_rows and np.max(np.abs(L.engine.get_residuals() - e_o)) > (1e-6 if kind in ("two", "three") else 1e-4):
+            return desc + " task=c", f"residuals differ by {np.max(np.abs(L.engine.get_residuals() - e_o))}"
+        L.engine.close()
+        return desc + " task=c", None
     stol = 1e-7 if kind in ("two", "three") else 2e-6         # real values: see the note on the parameters below
     same = lambda x, y: (np.isnan(x) and np.isnan(y)) or (abs(x) < 1e-8 and abs(y) < 1e-8) or rel(x, y) < stol
     for it, (s, o) in enumerate(zip(hist, want)):
