@@ -101,3 +101,13 @@ def test_randomised_sharded_run(emu_lib):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_sharded.py"), "--world", "3", "--cases", "40", "--seed", "7", "--seconds", "600"],
                        cwd=ROOT, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0 and "40 cases, no mismatch" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_randomised_cli_against_the_reference_binary(emu_lib):
+    """tools/fuzz_cli.py: random small data sets and command lines through the UNMODIFIED reference binary (oracle/_ref/libFM) and
+    through bin/libFM (engine = the emulated build), files in the CWD and `Train=` lines compared at 1e-4. 30 cases here."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libFM")):
+        pytest.skip("oracle/_ref/libFM not built")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_cli.py"), "--cases", "30", "--seed", "9", "--seconds", "600"],
+                       env=dict(os.environ, SVBFM_EMU="1"), cwd=ROOT, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0 and "30 cases, no mismatch" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
