@@ -6,8 +6,8 @@ with the same arguments in two scratch directories, and the files they leave in 
 free_energy_<tag>_vb) and the `Train=` values on stdout are compared at north_star's 1e-4 (the files carry 6 digits).
 vb / als / vb_online, -dim, -iter, -meta groups, -regular, -batch, -task c for als.
 
-  SVBFM_EMU=1 python tools/fuzz_cli.py --seconds 300 --seed 1      # engine = tests/emu build (LD_PRELOAD), no GPU needed
-  python tools/fuzz_cli.py --seconds 120                            # on a B200 (oracle/_ref travels with the snapshot)
+  SVBFM_EMU=1 python tests/fuzz_cli.py --seconds 300 --seed 1      # engine = tests/emu build (LD_PRELOAD), no GPU needed
+  python tests/fuzz_cli.py --seconds 120                            # on a B200 (oracle/_ref travels with the snapshot)
 """
 import argparse
 import os

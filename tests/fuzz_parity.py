@@ -1,8 +1,8 @@
 """Randomised differential run of the engine against the CPU oracle (test infrastructure; not part of the product).
 Draws data shapes (two one-hot fields with or without values, ragged multi-hot, three fields), methods (vb, als, vb_online),
 switches (k0, k1, K, groups, tile size) and compares every iteration's statistics and the final parameters.
-  SVBFM_LIB=tests/emu/_build/libsvbfm_emu.so python tools/fuzz_parity.py --seconds 600 --seed 1     # on the emulator
-  python tools/fuzz_parity.py --seconds 120                                                          # on a B200
+  SVBFM_LIB=tests/emu/_build/libsvbfm_emu.so python tests/fuzz_parity.py --seconds 600 --seed 1     # on the emulator
+  python tests/fuzz_parity.py --seconds 120                                                          # on a B200
 Prints one line per case and exits non-zero at the first mismatch (the line holds everything needed to replay it)."""
 import argparse
 import os

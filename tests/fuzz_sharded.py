@@ -4,7 +4,7 @@ Every rank draws the same list of cases from the seed: two one-hot fields (with 
 data; vb / als / vb_online; K, k0, k1, tile size; contiguous case ranges or user blocks; more ranks than cases. Rank 0 compares
 every iteration's statistics with the oracle; the replicated parameters must be bit-identical on every rank.
 
-  python tools/fuzz_sharded.py --world 3 --seconds 300 --seed 1        # launcher: builds / finds the emulator, spawns the ranks
+  python tests/fuzz_sharded.py --world 3 --seconds 300 --seed 1        # launcher: builds / finds the emulator, spawns the ranks
 """
 import argparse
 import hashlib

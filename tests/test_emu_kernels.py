@@ -87,27 +87,27 @@ def test_full_size_properties_on_divided_shapes(emu_lib):
 
 
 def test_randomised_differential_run(emu_lib):
-    """tools/fuzz_parity.py: random data shapes (one-hot, real values, ragged, three fields), methods, switches, groups and tile
+    """tests/fuzz_parity.py: random data shapes (one-hot, real values, ragged, three fields), methods, switches, groups and tile
     sizes against the oracle, statistics of every iteration and the final parameters; 60 cases here, thousands when run by hand."""
     env = dict(os.environ, SVBFM_LIB=emu_lib)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "--cases", "60", "--seed", "5", "--seconds", "600"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fuzz_parity.py"), "--cases", "60", "--seed", "5", "--seconds", "600"],
                        env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "60 cases, no mismatch" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_randomised_sharded_run(emu_lib):
-    """tools/fuzz_sharded.py: three PROCESSES (fake NCCL), random shapes / methods / switches / shard modes (contiguous case ranges,
+    """tests/fuzz_sharded.py: three PROCESSES (fake NCCL), random shapes / methods / switches / shard modes (contiguous case ranges,
     user blocks, ranks without a case) against the single-process oracle; parameters bit-identical on every rank. 40 cases here."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_sharded.py"), "--world", "3", "--cases", "40", "--seed", "7", "--seconds", "600"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fuzz_sharded.py"), "--world", "3", "--cases", "40", "--seed", "7", "--seconds", "600"],
                        cwd=ROOT, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0 and "40 cases, no mismatch" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_randomised_cli_against_the_reference_binary(emu_lib):
-    """tools/fuzz_cli.py: random small data sets and command lines through the UNMODIFIED reference binary (oracle/_ref/libFM) and
+    """tests/fuzz_cli.py: random small data sets and command lines through the UNMODIFIED reference binary (oracle/_ref/libFM) and
     through bin/libFM (engine = the emulated build), files in the CWD and `Train=` lines compared at 1e-4. 30 cases here."""
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libFM")):
         pytest.skip("oracle/_ref/libFM not built")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_cli.py"), "--cases", "30", "--seed", "9", "--seconds", "600"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fuzz_cli.py"), "--cases", "30", "--seed", "9", "--seconds", "600"],
                        env=dict(os.environ, SVBFM_EMU="1"), cwd=ROOT, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0 and "30 cases, no mismatch" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -15,9 +15,9 @@ timeout 600 $py -m pytest tests -m gpu -x -q --deselect tests/test_gpu_zzzz_full
 timeout 900 $py -m pytest tests/test_gpu_zzzz_full_size.py -m gpu -q --durations=0 > $out/next_pytest_full_size.log 2>&1; echo "full-size properties rc=$?" | tee -a $out/next_summary.txt
 
 # 1c. the randomised differential runs on the real engine (oracle and reference binary as checkers), default and experiments
-timeout 200 $py tools/fuzz_parity.py --seconds 90 --seed 101 > $out/next_fuzz_parity.log 2>&1; echo "fuzz parity rc=$?" | tee -a $out/next_summary.txt
-timeout 200 $py tools/fuzz_cli.py --seconds 90 --seed 102 > $out/next_fuzz_cli.log 2>&1; echo "fuzz cli rc=$?" | tee -a $out/next_summary.txt
-SVBFM_REC_RANK=1 SVBFM_GRAPH=1 timeout 200 $py tools/fuzz_parity.py --seconds 60 --seed 103 > $out/next_fuzz_parity_rank_graph.log 2>&1; echo "fuzz parity (rec_rank + graph) rc=$?" | tee -a $out/next_summary.txt
+timeout 200 $py tests/fuzz_parity.py --seconds 90 --seed 101 > $out/next_fuzz_parity.log 2>&1; echo "fuzz parity rc=$?" | tee -a $out/next_summary.txt
+timeout 200 $py tests/fuzz_cli.py --seconds 90 --seed 102 > $out/next_fuzz_cli.log 2>&1; echo "fuzz cli rc=$?" | tee -a $out/next_summary.txt
+SVBFM_REC_RANK=1 SVBFM_GRAPH=1 timeout 200 $py tests/fuzz_parity.py --seconds 60 --seed 103 > $out/next_fuzz_parity_rank_graph.log 2>&1; echo "fuzz parity (rec_rank + graph) rc=$?" | tee -a $out/next_summary.txt
 
 # 2. the experiments, each alone (a hang or a wrong result in one must not hide the others)
 timeout 600 $py -m pytest tests/test_gpu_zz_experiments.py -m gpu -q -k 'rec_rank or graph' > $out/next_pytest_rec_rank.log 2>&1; echo "rec_rank tests rc=$?" | tee -a $out/next_summary.txt
