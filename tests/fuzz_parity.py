@@ -87,8 +87,10 @@ def one_case(r, case_id, run=True):
         L.fm.reg0, L.fm.regw, L.fm.regv = 0.0, 0.5, 1.0
     hist = L.learn(to_csc(tr), to_csc(te))
     if task:                                   # accuracies: at most a borderline case or two; residuals against the latent targets
+        # a probability within 1e-6 of 0.5 (a case of never-observed attributes: y-hat = 0 up to rounding) falls on either side
+        ties = int(np.sum(np.abs(orc.get_test_pred() - 0.5) < 1e-6)) if te.n_rows else 0
         for it, (s, o) in enumerate(zip(hist, want)):
-            if abs(s.train_stat - o.train_stat) > 2.0 / max(tr.n_rows, 1) or (te.n_rows and abs(s.test_rmse - o.test_rmse) > 2.0 / te.n_rows):
+            if abs(s.train_stat - o.train_stat) > 2.0 / max(tr.n_rows, 1) + 1e-12 or (te.n_rows and abs(s.test_rmse - o.test_rmse) > (2.0 + ties) / te.n_rows + 1e-12):
                 return desc + " task=c", f"iteration {it}: accuracies {s.train_stat!r}, {s.test_rmse!r} != {o.train_stat!r}, {o.test_rmse!r}"
         e_o, _ = orc.get_train_cache(want_t=False)
         if tr.n_rows and np.max(np.abs(L.engine.get_residuals() - e_o)) > (1e-6 if kind in ("two", "three") else 1e-4):
