@@ -2,7 +2,7 @@
 # First gpurun call of the next measurement round: validates and times everything that was built without a GPU
 # (DESIGN.md section 7a). Every step runs under its own timeout so that a hang in an experimental kernel cannot hold the box;
 # results land in gpurun_out/next_*.  Usage:
-#   gpurun --timeout 1500 -- 'bash tools/next_gpu_call.sh'
+#   gpurun --timeout 3000 -- 'bash tools/next_gpu_call.sh'      (about 40 minutes of box time)
 set -u
 mkdir -p gpurun_out
 out=gpurun_out
