@@ -1235,13 +1235,14 @@ int svbfm_predict(svbfm_t* h, int32_t split, double* out) {
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
     size_t n = E->te.n;
     if (E->cfg.method == SVBFM_MCMC) {
+        // mcmc.h:355-379: the mean of the draws when sampling, the last prediction otherwise (als), clamped either way
         std::vector<double> s(n);
-        SV_CUDA(E, copy_sync(E, s.data(), E->d_pred_sum, n * 8, cudaMemcpyDeviceToHost));
+        SV_CUDA(E, copy_sync(E, s.data(), E->cfg.do_sample ? E->d_pred_sum : E->d_pred_test, n * 8, cudaMemcpyDeviceToHost));
         Scalars sc;
         SV_CUDA(E, copy_sync(E, &sc, E->d_sc, sizeof(sc), cudaMemcpyDeviceToHost));
-        double it = sc.iter ? (double)sc.iter : 1.0;
+        double it = (E->cfg.do_sample && sc.iter) ? (double)sc.iter : 1.0;
         const double lo = E->cfg.task == 1 ? 0.0 : sc.min_target, hi = E->cfg.task == 1 ? 1.0 : sc.max_target;    // classification: a probability
-        for (size_t i = 0; i < n; i++) out[i] = std::fmax(lo, std::fmin(hi, s[i] / it));   // mcmc.h:355-379
+        for (size_t i = 0; i < n; i++) out[i] = std::fmax(lo, std::fmin(hi, s[i] / it));
     } else {
         SV_CUDA(E, copy_sync(E, out, E->d_pred_test, n * 8, cudaMemcpyDeviceToHost));
     }

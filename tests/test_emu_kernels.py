@@ -111,3 +111,15 @@ def test_randomised_cli_against_the_reference_binary(emu_lib):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fuzz_cli.py"), "--cases", "30", "--seed", "9", "--seconds", "600"],
                        env=dict(os.environ, SVBFM_EMU="1"), cwd=ROOT, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0 and "30 cases, no mismatch" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_reference_tree_binding_on_the_emulator(emu_lib):
+    """oracle/_ref/libFM_cuda (the reference's own libfm.cpp + host/reference_tree/*.h, recipe oracle/make_ref_cuda.py) with the
+    emulated engine preloaded: `-method vb_cuda` against `-method vb` and `als_cuda` against `als` from the one binary."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libFM_cuda")):
+        pytest.skip("oracle/_ref/libFM_cuda not built")
+    f = os.path.join(ROOT, "tests", "test_gpu_ref_tree_binding.py")
+    cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider",
+           f + "::test_vb_cuda_equals_vb_in_the_reference_binary[g1-1,1,4]", f + "::test_als_cuda_equals_als_in_the_reference_binary"]
+    r = subprocess.run(cmd, env=dict(os.environ, SVBFM_EMU_PRELOAD=emu_lib), cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
