@@ -1028,9 +1028,9 @@ int orc_get_train_cache(orc_t *h, double *e, double *t) {
     return 0;
 }
 int orc_get_test_pred(orc_t *h, double *p) {
-    if (h->method == ORC_MCMC) {                                     /* mcmc.h:355-379: running mean, clamped */
+    if (h->method == ORC_MCMC) {                                     /* mcmc.h:355-379: mean of the draws (sampling) or the last prediction (als), clamped */
         for (uint32_t c = 0; c < h->sp[1].n_cases; c++) {
-            double v = h->pred_sum_all[c] / (h->iter ? h->iter : 1);
+            double v = h->do_sample ? h->pred_sum_all[c] / (h->iter ? h->iter : 1) : h->pred_this[c];
             if (h->task == 1) { v = fmin(1.0, v); v = fmax(0.0, v); }     /* mcmc.h:372-374 */
             else { v = fmin(h->max_target, v); v = fmax(h->min_target, v); }
             p[c] = v;

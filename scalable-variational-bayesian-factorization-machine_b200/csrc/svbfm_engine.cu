@@ -337,19 +337,20 @@ static void launch_stream(Engine* E, int side, bool has_own, bool own_is_w, bool
     a.has_own = has_own; a.own_is_w = own_is_w; a.has_oth = has_oth; a.oth_is_w = oth_is_w;
     a.colsum = E->d_colsum;
     constexpr int KIND = MCMC ? (W ? KIND_MC_W : KIND_MC_V) : (W ? KIND_VB_W : KIND_VB_V);
-    unsigned grid = (a.ntiles + 7) / 8;
+    constexpr unsigned SW = SV_STREAM_WARPS, ST = 32 * SV_STREAM_WARPS;
+    unsigned grid = (a.ntiles + SW - 1) / SW;
     if (!a.ntiles) return;
     const bool steady = !W && has_own && !own_is_w && has_oth && !oth_is_w;
 #define CALL_S(ONES, STEADY)                                                                                         \
     do {                                                                                                             \
-        if (a.idx) { if constexpr (!MCMC) k_stream<KIND, ONES, REDUCE, STEADY, true><<<grid, 256, 0, E->stream>>>(a); } \
-        else k_stream<KIND, ONES, REDUCE, STEADY, false><<<grid, 256, 0, E->stream>>>(a);                           \
+        if (a.idx) { if constexpr (!MCMC) k_stream<KIND, ONES, REDUCE, STEADY, true><<<grid, ST, 0, E->stream>>>(a); } \
+        else k_stream<KIND, ONES, REDUCE, STEADY, false><<<grid, ST, 0, E->stream>>>(a);                           \
     } while (0)
-    // SVBFM_STREAM_TMA=1 (experiment): streams staged through shared memory by bulk copies; needs 16-byte aligned stream starts
+    // all-ones streams are staged through shared memory by bulk copies (SVBFM_STREAM_TMA=0: plain loads); needs 16-byte aligned stream starts
     const bool tma = E->stream_tma && S.all_ones && !a.idx && (a.real0 % 4 == 0);
     if (tma) {
-        if (steady) k_stream<KIND, true, REDUCE, true, false, true><<<grid, 256, 0, E->stream>>>(a);
-        else k_stream<KIND, true, REDUCE, false, false, true><<<grid, 256, 0, E->stream>>>(a);
+        if (steady) k_stream<KIND, true, REDUCE, true, false, true><<<grid, ST, 0, E->stream>>>(a);
+        else k_stream<KIND, true, REDUCE, false, false, true><<<grid, ST, 0, E->stream>>>(a);
     }
     else if (steady) { if (S.all_ones) CALL_S(true, true); else CALL_S(false, true); }
     else { if (S.all_ones) CALL_S(true, false); else CALL_S(false, false); }
@@ -750,7 +751,8 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     ++g_handles;
     E->cfg = *cfg; E->dev = cfg->device; E->D = cfg->num_attribute; E->K = cfg->num_factor;
     E->tile_entries = cfg->tile_entries ? cfg->tile_entries : 1024;
-    if (const char* tm = getenv("SVBFM_STREAM_TMA")) E->stream_tma = atoi(tm) != 0;
+    if (const char* tm = getenv("SVBFM_STREAM_TMA")) E->stream_tma = atoi(tm) != 0;      // default on; 0: plain loads (A/B runs, tests)
+    if (const char* rr = getenv("SVBFM_REC_RANK")) E->want_rec_rank = atoi(rr) != 0;    // default on; 0: records in column order
     if (const char* gr = getenv("SVBFM_GRAPH")) E->use_graph = atoi(gr) != 0;
     if (const char* te = getenv("SVBFM_TILE_ENTRIES")) if (atoi(te) >= 32) E->tile_entries = (uint32_t)atoi(te);   // tuning knob
     // implicit tiles of the stream schedule: 4096 entries unless the caller (or the knob) says otherwise

@@ -419,10 +419,9 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
 
         // ---- case re-ordering: device order = order of the cases inside run 0 (when run 0 holds every case once)
         bool reorder = !(E->cfg.flags & SVBFM_FLAG_NO_ROW_REORDER) && !E->runs.empty() && E->runs[0].nnz == n && n > 0 && nnz > 0;
-        // SVBFM_REC_RANK=1 (experiment, two complete fields only): record slots of the second field by popularity rank
+        // two complete fields: record slots of the second field by popularity rank (Engine::d_rec_slot)
         sv_free(E->d_rec_slot); E->d_rec_slot = nullptr; E->rec_rank = false;
-        const bool want_rank = reorder && getenv("SVBFM_REC_RANK") && atoi(getenv("SVBFM_REC_RANK")) != 0 && E->runs.size() == 2 && uniform && F == 2 &&
-                               E->runs[1].nnz == n;
+        const bool want_rank = reorder && E->want_rec_rank && !getenv("SVBFM_NO_FUSE") && E->runs.size() == 2 && uniform && F == 2 && E->runs[1].nnz == n;
         if (want_rank) {
             const Run& r1 = E->runs[1];
             const uint32_t nc1 = r1.col_end - r1.col_begin;
@@ -549,10 +548,10 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         // ---- stream schedule: implicit tiles of 2^ts_shift entries per run; only their first column and the list of the
         // columns that span many tiles are materialised (kernels.cuh k_stream / k_combine_span)
         if (E->ts_auto) {
-            // A pass is one warp per tile: 148 SMs x 3 CTAs x 8 warps = 3552 warps are resident at a time. 4096-entry tiles (the best
+            // A pass is one warp per tile: 148 SMs x 7 CTAs x 4 warps = 4144 warps are resident at a time. 4096-entry tiles (the best
             // size at 200 M entries) leave most SMs idle below ~15 M entries per field (1 M ratings: 244 warps on
             // 31 SMs). Aim at four waves of warps, with tiles between 256 and 4096 entries.
-            const uint64_t want = (uint64_t)n / (3552ull * 4);
+            const uint64_t want = (uint64_t)n / (4144ull * 4);
             E->ts_shift = 8;
             while (E->ts_shift < 12 && (2ull << E->ts_shift) <= want) E->ts_shift++;
         }

@@ -679,13 +679,19 @@ __device__ __forceinline__ void sv_mbar_wait(SvMbar* b, uint32_t parity) {
 #ifndef SV_STREAM_U
 #define SV_STREAM_U 2        // rows of 32 entries per batch (measured: 2 x 4 CTAs/SM beats 4 x 2, gpurun_out/tune_*)
 #endif
-#ifndef SV_STREAM_GPIPE
-#define SV_STREAM_GPIPE 0    // 1: records gathered one batch ahead of the arithmetic (more registers)
+// The warps of a CTA do not cooperate, so the CTA size only sets the granularity of the occupancy: 4 warps x 7 CTAs = 28 warps per
+// SM at 72 registers (8 x 3 = 24 before). Measured at 200 M ratings, K = 50 (gpurun_out/r2b_*, profiles/r02_kstream_variants.txt):
+// 8 x 3 109.3 ms per iteration, 4 x 7 106.2 ms. Tried and dropped in round 2: the records of batch b + 1 gathered into a second
+// register set while batch b is processed (80 registers: 127 ms), prefetch.global.L1 / .L2 of the next batch's records (153 ms),
+// 32-entry batches at 4 x 8 warps (119 ms): whatever adds L1TEX requests or keeps more of them in flight loses, the pass is
+// bound by the 128-byte lines the record gathers touch.
+#ifndef SV_STREAM_WARPS
+#define SV_STREAM_WARPS 4
 #endif
 #ifndef SV_STREAM_MINB
-#define SV_STREAM_MINB 3     // resident CTAs per SM the register allocation aims at (72 registers, no spills)
+#define SV_STREAM_MINB 7     // resident CTAs per SM the register allocation aims at (<= 73 registers, no spills)
 #endif
-// per-warp ring + barriers of the TMA variant (8 warps per CTA); the plain variant declares no shared memory at all
+// per-warp ring + barriers of the TMA variant; the plain variant declares no shared memory at all
 template <bool TMA, int NST, uint32_t BYTES>
 struct StreamRing {
     static __device__ __forceinline__ unsigned char* ring(uint32_t) { return nullptr; }
@@ -694,11 +700,11 @@ struct StreamRing {
 template <int NST, uint32_t BYTES>
 struct StreamRing<true, NST, BYTES> {
     static __device__ __forceinline__ unsigned char* ring(uint32_t w) {
-        alignas(128) __shared__ unsigned char s_ring[8][NST][BYTES];
+        alignas(128) __shared__ unsigned char s_ring[SV_STREAM_WARPS][NST][BYTES];
         return &s_ring[w][0][0];
     }
     static __device__ __forceinline__ SvMbar* bars(uint32_t w) {
-        alignas(8) __shared__ SvMbar s_bar[8][NST];
+        alignas(8) __shared__ SvMbar s_bar[SV_STREAM_WARPS][NST];
         return &s_bar[w][0];
     }
 };
@@ -710,8 +716,8 @@ struct StreamRing<true, NST, BYTES> {
 // ahead; the lanes read their entries with LDS once the slot's mbarrier completes. Deeper prefetch than the register batch
 // (bytes in flight per SM: 24 warps x 4 x 768 B instead of 24 x 768 B) at no register cost. The stores stay STG.
 template <int KIND, bool ONES, bool REDUCE, bool STEADY, bool IDX = false, bool TMA = false>
-__global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
-    static_assert(!TMA || (ONES && !IDX && SV_STREAM_GPIPE == 0), "the TMA variant covers the all-ones streams without an index list");
+__global__ void __launch_bounds__(32 * SV_STREAM_WARPS, ONES ? SV_STREAM_MINB : SV_STREAM_MINB - 1) k_stream(StreamArgs a) {      // x != 1: two more streams
+    static_assert(!TMA || (ONES && !IDX), "the TMA variant covers the all-ones streams without an index list");
     constexpr bool IS_V = (KIND == KIND_VB_V || KIND == KIND_MC_V);
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int U = SV_STREAM_U;
@@ -911,31 +917,6 @@ __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
             }
         }
     };
-#if SV_STREAM_GPIPE
-    // records gathered one batch ahead of the arithmetic, streams two batches ahead
-    {
-        float xs[U], xo[U]; double es[U]; uint32_t rr[IDX ? U : 1]; ColPack g[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) { xs[u] = xs_n[u]; xo[u] = xo_n[u]; es[u] = e_n[u]; if constexpr (IDX) rr[u] = r_n[u]; }
-        gather(q_begin, oc_n, g);
-        if (q_end - q_begin > 32 * U) load_batch(q_begin + 32 * U);
-        for (uint32_t q0 = q_begin; q0 < q_end && !done; q0 += 32 * U) {
-            float xs1[U], xo1[U]; double es1[U]; uint32_t rr1[IDX ? U : 1]; ColPack g1[U];
-            const bool more = q_end - q0 > 32 * U;
-            if (more) {
-                gather(q0 + 32 * U, oc_n, g1);
-#pragma unroll
-                for (int u = 0; u < U; u++) { xs1[u] = xs_n[u]; xo1[u] = xo_n[u]; es1[u] = e_n[u]; if constexpr (IDX) rr1[u] = r_n[u]; }
-                if (q_end - q0 > 64 * U) load_batch(q0 + 64 * U);
-            }
-            process(q0, xs, xo, es, rr, g);
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < U; u++) { xs[u] = xs1[u]; xo[u] = xo1[u]; es[u] = es1[u]; g[u] = g1[u]; if constexpr (IDX) rr[u] = rr1[u]; }
-            }
-        }
-    }
-#else
     for (uint32_t q0 = q_begin; q0 < q_end && !done; q0 += 32 * U) {
         float xs[U], xo[U]; double es[U]; ColPack g[U];
         uint32_t rr[IDX ? U : 1];
@@ -945,7 +926,6 @@ __global__ void __launch_bounds__(256, SV_STREAM_MINB) k_stream(StreamArgs a) {
         if (q_end - q0 > 32 * U) load_batch(q0 + 32 * U);
         process(q0, xs, xo, es, rr, g);
     }
-#endif
     if constexpr (REDUCE) if (!done) emit(cur_b, next_b);   // column j continues in the next tile
 }
 

@@ -63,12 +63,12 @@ def test_two_ranks_on_the_emulator(emu_lib, tmp_path):
 
 
 def test_experimental_variants_on_the_emulator(emu_lib):
-    """One case each of the opt-in kernel variants that have not run on a B200 yet: the bulk-copy ring of
-    k_stream (bit-identical to the plain kernel; misaligned second field, partial last batch) and the rank-ordered records."""
+    """One case each of the kernel variants behind knobs: the bulk-copy ring of k_stream against plain loads (bit-identical; misaligned
+    second field, partial last batch) and the records in column order (SVBFM_REC_RANK=0)."""
     env = dict(os.environ, SVBFM_LIB=emu_lib)
     cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider",
            os.path.join(ROOT, "tests", "test_gpu_zzz_tma_ring.py") + "::test_stream_tma_ring[256-20002]",
-           os.path.join(ROOT, "tests", "test_gpu_zz_experiments.py") + "::test_rec_rank_layout[64]",
+           os.path.join(ROOT, "tests", "test_gpu_zz_experiments.py") + "::test_rec_rank_layout[0-64]",
            os.path.join(ROOT, "tests", "test_gpu_zy_errors.py")]           # and the error convention of the C-ABI
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "4 passed" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
