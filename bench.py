@@ -69,9 +69,10 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=400_000, help="ratings in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--shard-by", default="auto", choices=["auto", "user_block", "case_range"],
-                    help="how the ratings are split over the GPUs. auto: weak -> case_range (every GPU draws its own N ratings: perfectly balanced, "
-                         "both fields exchanged), strong -> user_block (no exchange for the user field; balance limited by the heaviest users)")
+    ap.add_argument("--shard-by", default="auto", choices=["auto", "cross", "user_block", "case_range"],
+                    help="how the ratings are split over the GPUs. auto: strong -> cross (first residual copy by user block, second copy by item block: no "
+                         "column sums cross the ranks, the updated columns' records do), weak -> case_range (every GPU draws its own N ratings, both "
+                         "fields allreduced). user_block: both copies by user block, item sums allreduced")
     ap.add_argument("--col-cost", type=float, default=20.0,
                     help="user-block shards are balanced by ratings + col_cost x users: a column costs the stream passes about as much as 15-20 "
                          "entries (fitted on the per-rank stream times of 2-GPU runs: 90 over-corrects, 107 M vs 93 M ratings -> 64.6 vs 59.8 ms)")
@@ -222,8 +223,9 @@ class Problem:
         #      weak: every rank draws its own N ratings (same planted model, different seed): the global data set has N x world cases
         weak = (scaling == "weak") and world > 1
         if shard_by == "auto":
-            shard_by = "case_range" if weak else "user_block"
-        block = shard_by == "user_block"
+            shard_by = "case_range" if weak else "cross"
+        cross = shard_by == "cross" and world > 1 and not weak and method != "vb_online"
+        block = shard_by in ("user_block", "cross")
         self.D = D = U + I + (0 if method == "vb_online" else 1)     # libfm.cpp:215: max(train, test num_feature) + 1 (vb_online: max id + 1)
         if weak and block:
             # the global data set is `world` draws of N ratings (seeds s, s+1000, ..); this rank keeps the ratings of its user block,
@@ -243,7 +245,14 @@ class Problem:
             return (0, n) if weak else ((n * rank) // world, (n * (rank + 1)) // world)
 
         self.shard_mode = "single GPU"
+        u2 = it2 = y2 = None
         if world > 1 and not weak:
+            if cross:      # the second residual copy's shard: the ratings of this rank's block of items (balanced like the user blocks)
+                cnt_i = torch.bincount(it, minlength=I).to(torch.float64)
+                b1 = balanced_cuts(cnt_i + col_cost * (cnt_i > 0), world)
+                keep2 = torch.nonzero((it >= b1[rank]) & (it < b1[rank + 1])).squeeze(1)
+                u2, it2, y2 = u[keep2].contiguous(), it[keep2].contiguous(), y[keep2].contiguous()
+                del keep2, cnt_i
             if block:
                 # partition the ratings by user block, balanced by number of ratings: this rank keeps the ratings of the
                 # users [b_rank, b_rank+1); the engine detects the disjoint blocks and needs no exchange for the user field
@@ -254,6 +263,10 @@ class Problem:
                 del keep, cnt
                 self.shard_mode = (f"strong scaling: the {N} ratings in {world} shards by user block (balanced by ratings + {col_cost:g} x users), NCCL allreduce of "
                                    "the item column sums per factor, user blocks exchanged once per iteration")
+                if cross:
+                    self.shard_mode = (f"strong scaling, cross shards: the {N} ratings by user block for the first residual copy and by item block for the second "
+                                       f"(both balanced by ratings + {col_cost:g} x columns); no column sums cross the ranks: NCCL allgather of the updated columns' "
+                                       "32-byte records per factor and field, parameter blocks exchanged once per iteration")
             else:
                 lo_, hi_ = shard(N)
                 u, it, y = u[lo_:hi_].contiguous(), it[lo_:hi_].contiguous(), y[lo_:hi_].contiguous()
@@ -280,8 +293,10 @@ class Problem:
             return d
 
         self.train = host_csc(u, it, y)
+        self.train2 = host_csc(u2, it2, y2) if u2 is not None else None
+        self.n_second = int(u2.numel()) if u2 is not None else 0
         self.test = host_csc(ut, itt, yt)
-        del u, it, y, ut, itt, yt
+        del u, it, y, ut, itt, yt, u2, it2, y2
         torch.cuda.empty_cache()
         g = torch.Generator(device=dev); g.manual_seed(42)
         self.state = dict(w0_mean=0.0, w0_var=0.0 if method == "mcmc" else 0.02,
@@ -298,7 +313,9 @@ class Problem:
 
     def h2d_bytes(self):
         tr, te, st = self.train, self.test, self.state
+        t2 = self.train2
         return (sum(x.nbytes for x in (tr.colptr, tr.case_id, tr.x, tr.target, te.colptr, te.case_id, te.x, te.target)) +
+                (sum(x.nbytes for x in (t2.colptr, t2.case_id, t2.x, t2.target)) if t2 is not None else 0) +
                 st["w_mean"].nbytes + st["w_var"].nbytes + st["v_mean"].nbytes + st["v_var"].nbytes)
 
     def _tick(self, name, t0):
@@ -310,6 +327,9 @@ class Problem:
         t0 = time.perf_counter()
         E.set_csc(sv.TRAIN, self.train)
         self._tick("set_csc_train", t0); t0 = time.perf_counter()
+        if self.train2 is not None:
+            E.set_csc(sv.TRAIN_SECOND, self.train2)
+            self._tick("set_csc_train_second", t0); t0 = time.perf_counter()
         E.set_csc(sv.TEST, self.test)
         self._tick("set_csc_test", t0); t0 = time.perf_counter()
         E.set_state(self.state)
@@ -365,7 +385,7 @@ def device_resident(P, steps, warmup, sample_clocks=True):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dev_ms, sweep_ms, wall_ms = [float(x) for x in tt.cpu()]
     mine = torch.tensor([sum(v["ms"] for k, v in prof.items() if k.startswith("stream")) / max(steps, 1), float(P.n_mine),
-                         prof.get("collectives", {"ms": 0.0})["ms"] / max(steps, 1)], dtype=torch.float64, device=cx.dev)
+                         prof.get("collectives", {"ms": 0.0})["ms"] / max(steps, 1), float(P.n_second)], dtype=torch.float64, device=cx.dev)
     per_rank = [mine.clone() for _ in range(world)]
     if world > 1:
         dist.all_gather(per_rank, mine)
@@ -374,7 +394,7 @@ def device_resident(P, steps, warmup, sample_clocks=True):
     return dict(info0=info0, warm_hist=warm_hist, hist=hist, launches=int(launches), prof=prof, clocks=clocks, ms_per_step=dev_ms / max(steps, 1),
                 sweep_ms_per_step=sweep_ms / max(steps, 1), wall_ms_per_step=wall_ms / max(steps, 1),
                 rank_stream_ms=[round(float(x[0]), 2) for x in per_rank], rank_ratings=[int(x[1]) for x in per_rank],
-                rank_collective_ms=[round(float(x[2]), 2) for x in per_rank])
+                rank_collective_ms=[round(float(x[2]), 2) for x in per_rank], rank_second=[int(x[3]) for x in per_rank])
 
 
 def end_to_end(P):
@@ -506,7 +526,7 @@ def main():
     parity = None
     if world > 1 and a.scaling == "strong" and not a.no_parity and a.method != "vb_online":     # vb_online: the batches are drawn per shard
         n_mine = P.n_mine
-        del P.train, P.test
+        del P.train, P.test, P.train2
         cx.torch.cuda.empty_cache()
         parity = parity_vs_single_gpu(cx, a, r["warm_hist"], hist)
     else:
@@ -586,6 +606,7 @@ def main():
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": P.workload, "global_ratings": N_global,
                       "sharding": P.shard_mode, "ratings_per_rank": r["rank_ratings"], "stream_ms_per_rank": r["rank_stream_ms"],
+                      "second_copy_ratings_per_rank": r["rank_second"] if any(r["rank_second"]) else None,
                       "collective_ms_per_rank": r["rank_collective_ms"], "exclusive_blocks": info0.get("exclusive_blocks", 0),
                       "l2": "inputs (residuals + design matrix) are far larger than the 126 MB L2; no flush needed",
                       "field_runs": info0["num_runs"], "tiles": info0["num_tiles"], "rows_reordered": info0["rows_reordered"],

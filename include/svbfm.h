@@ -36,7 +36,8 @@ typedef enum svbfm_status {
 } svbfm_status;
 
 enum { SVBFM_VB = 0, SVBFM_VB_ONLINE = 1, SVBFM_MCMC = 2 };   /* -method vb | vb_online | mcmc (libfm.cpp:297-320) */
-enum { SVBFM_TRAIN = 0, SVBFM_TEST = 1 };
+enum { SVBFM_TRAIN = 0, SVBFM_TEST = 1,
+       SVBFM_TRAIN_SECOND = 2   /* several GPUs only: the shard of the SECOND residual copy (see svbfm_set_csc) */ };
 
 /* What main() wires into the learner before init() (libfm.cpp:259-274, 301-320, 331-336). */
 typedef struct svbfm_config {
@@ -104,6 +105,15 @@ int svbfm_set_groups(svbfm_t* h, const uint32_t* attr_group /*[D]*/, uint32_t nu
 int svbfm_set_csc(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_cols,
                   const uint64_t* colptr /*[num_cols+1]*/, const uint32_t* case_id /*[nnz]*/,
                   const float* x /*[nnz]*/, const float* target /*[num_cases]*/);
+/* Cross shards (optional, several GPUs, two complete one-hot fields with x = 1, vb / mcmc regression): after SVBFM_TRAIN
+ * -- which must then be a shard by blocks of the FIRST field's columns (rank r holds every case of its users; blocks disjoint and
+ * ordered by rank) -- the caller hands over, as split SVBFM_TRAIN_SECOND in the same CSC format, the cases of the same global train
+ * set that fall into this rank's block of the SECOND field's columns (every case of its items). The engine then keeps its second
+ * residual copy on that shard: every column of either field has all of its entries on one rank, so no column sums are reduced
+ * between the ranks; the records of the updated columns travel instead (one allgather per factor and field). Results equal the
+ * single-GPU run up to summation order. Every rank must make the call (it is collective); SVBFM_ERR_ARG when the data does not
+ * qualify (all ranks fail together). No reference counterpart (the reference is single-process). */
+
 
 /* replaces: the variational state set up by fm_learn_vb::init (vb.h:693-712) / fm_model (fm_model.h:92-101).
  * vb / vb_online: (mean, var) = (mu', sigma'); mcmc: mean = the parameter, var ignored.

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SVBFM_LIB") or os.path.join(_HERE, "libsvbfm.so")   # SVBFM_LIB: another build of the same ABI
 
 VB, VB_ONLINE, MCMC = 0, 1, 2
-TRAIN, TEST = 0, 1
+TRAIN, TEST, TRAIN_SECOND = 0, 1, 2     # TRAIN_SECOND: the second residual copy's shard (several GPUs; include/svbfm.h)
 METHODS = {"vb": VB, "vb_online": VB_ONLINE, "mcmc": MCMC}
 FLAG_NO_ROW_REORDER = 1
 FLAG_MCMC_NO_REPREDICT = 2
@@ -187,7 +187,7 @@ class Engine:
                                      _p(data.x), _p(data.target)), "svbfm_set_csc")
         if split == TRAIN:
             self.n_train = data.num_cases
-        else:
+        elif split == TEST:
             self.n_test = data.num_cases
 
     def set_state(self, s):

@@ -113,12 +113,9 @@ struct ProfScope {
 };
 
 namespace svb {
-// Do the ranks hold disjoint, rank-ordered ranges of run 0's columns? (cases sharded by blocks of the first field)
-int detect_exclusive_blocks(Engine* E) {
-    E->excl0 = false;
-    if (E->world <= 1 || E->runs.size() != 2 || getenv("SVBFM_NO_EXCL")) return 0;
-    const Run& r0 = E->runs[0];
-    const std::vector<uint64_t>& cp = E->tr.h_colptr;
+// Do the ranks hold disjoint, rank-ordered ranges of the run's columns? (cases sharded by blocks of that field). Collective.
+int detect_blocks(Engine* E, const Run& r0, const std::vector<uint64_t>& cp, std::vector<uint32_t>& blk, bool& exclusive) {
+    exclusive = false;
     uint32_t lo = r0.col_end, hi = r0.col_begin;            // first / one past the last non-empty column of this rank
     for (uint32_t j = r0.col_begin; j < r0.col_end; j++)
         if (cp[j + 1] > cp[j]) { if (lo == r0.col_end) lo = j; hi = j + 1; }
@@ -140,26 +137,29 @@ int detect_exclusive_blocks(Engine* E) {
         prev_hi = h;
     }
     if (!ok) return 0;
-    E->blk.assign((size_t)E->world + 1, r0.col_end);
+    blk.assign((size_t)E->world + 1, r0.col_end);
     for (int r = E->world - 1; r >= 1; r--) {
         uint32_t l = v[(size_t)r * 2], h = v[(size_t)r * 2 + 1];
-        E->blk[r] = (h > l) ? l : E->blk[r + 1];
+        blk[r] = (h > l) ? l : blk[r + 1];
     }
-    E->blk[0] = r0.col_begin;
-    E->excl0 = true;
+    blk[0] = r0.col_begin;
+    exclusive = true;
     return 0;
+}
+int detect_exclusive_blocks(Engine* E) {
+    E->excl0 = false;
+    if (E->world <= 1 || E->runs.size() != 2 || getenv("SVBFM_NO_EXCL")) return 0;
+    return detect_blocks(E, E->runs[0], E->tr.h_colptr, E->blk, E->excl0);
 }
 }  // namespace svb
 
 // stream schedule, exclusive blocks: after the sweep every rank hands the parameters of its block of run 0 (w and every
 // factor) to the others: pack [rows][maxcnt] -> one ncclAllGather -> unpack the other ranks' blocks
-static int exchange_blocks(Engine* E) {
-    if (!E->excl0) return 0;
-    ProfScope pc(E, 11);
+static int exchange_blocks_of(Engine* E, const std::vector<uint32_t>& blk) {
     cudaStream_t st = E->stream;
     const uint32_t rows = (E->cfg.k1 ? 1u : 0u) + (uint32_t)E->K;
     uint32_t maxcnt = 0;
-    for (int r = 0; r < E->world; r++) maxcnt = std::max(maxcnt, E->blk[r + 1] - E->blk[r]);
+    for (int r = 0; r < E->world; r++) maxcnt = std::max(maxcnt, blk[r + 1] - blk[r]);
     if (!rows || !maxcnt) return 0;
     const size_t per_rank = (size_t)rows * maxcnt;                         // double2 elements
     if (E->xchg_cap < per_rank * (size_t)(E->world + 1)) {
@@ -171,13 +171,32 @@ static int exchange_blocks(Engine* E) {
     double2* recv = E->d_xchg + per_rank;                                  // [world][rows][maxcnt]
     BlockXchg bx{};
     bx.pw = E->cfg.k1 ? E->d_pw : nullptr; bx.pv = E->d_pv; bx.D = E->D; bx.rows = rows; bx.maxcnt = maxcnt; bx.world = E->world; bx.rank = E->rank;
-    for (int r = 0; r <= E->world && r <= 16; r++) bx.blk[r] = E->blk[r];
-    const uint32_t own = E->blk[E->rank + 1] - E->blk[E->rank];
+    for (int r = 0; r <= E->world && r <= 16; r++) bx.blk[r] = blk[r];
+    const uint32_t own = blk[E->rank + 1] - blk[E->rank];
     if (own) { k_xchg_pack<<<dim3(nblk(own), rows), 256, 0, st>>>(bx, send); LAUNCHED(E); }
     int r = g_nccl.AllGather(send, recv, per_rank * 2, 8 /*ncclDouble*/, E->nccl_comm, st);
     if (r != 0) return fail(E, SVBFM_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
     k_xchg_unpack<<<dim3(nblk(maxcnt), rows, E->world), 256, 0, st>>>(bx, recv); LAUNCHED(E);
     return check_launch(E, "exchange_blocks");
+}
+static int exchange_blocks(Engine* E) {
+    if (!E->excl0) return 0;
+    ProfScope pc(E, 11);
+    if (int rc = exchange_blocks_of(E, E->blk)) return rc;
+    if (E->xs) return exchange_blocks_of(E, E->blk1);      // cross shards: the second field's columns are updated by their owners only, too
+    return 0;
+}
+
+// cross shards: the records of the columns a rank has just finalized travel to every rank: slot-contiguous, equally sized blocks
+// of cpack, one in-place allgather (send block = this rank's part of the receive buffer)
+static int exchange_records(Engine* E, int run) {
+    if (!E->xs) return 0;
+    ProfScope pc(E, 10);
+    const size_t per = (size_t)E->slot_max[run] * 4;                       // doubles per rank
+    double* base = reinterpret_cast<double*>(E->d_cpack + E->slot_base[run]);
+    int r = g_nccl.AllGather(base + per * (size_t)E->rank, base, per, 8 /*ncclDouble*/, E->nccl_comm, E->stream);
+    if (r != 0) return fail(E, SVBFM_ERR_NCCL, std::string("ncclAllGather (records): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    return 0;
 }
 
 // stream schedule: what a finalize has to leave behind for the passes that follow (kernels.cuh FinalizeArgs)
@@ -210,11 +229,11 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
             from_colsum = true; use_ab = true;
         }
     } else if (rp && rp->run >= 0) {
-        sp.colptr = E->tr.colptr; sp.entry0 = E->tr.h_colptr[r.col_begin];
+        sp.colptr = E->side[rp->run].colptr; sp.entry0 = E->side[rp->run].entry0;
         partial = E->d_partial + (rp->run ? (size_t)E->s_ntiles[0] * 8 : 0);
         uint32_t nh = E->span_heavy_n[rp->run], h0 = rp->run ? E->span_heavy_n[0] : 0;
         if (nh) { k_combine_span<<<nh, 128, 0, st>>>(E->d_span_heavy, h0, sp, partial, E->d_colsum); LAUNCHED(E); }
-        if (E->world > 1 && !(rp->run == 0 && E->excl0)) {
+        if (E->world > 1 && !(rp->run == 0 && E->excl0) && !E->xs) {
             k_combine_light_span<KIND == KIND_VB_V><<<nblk(ncols), 256, 0, st>>>(r.col_begin, r.col_end, sp, partial, E->d_colsum, E->d_ab); LAUNCHED(E);
             ProfScope pc(E, 10);      // includes the wait for the slowest rank
             if (int rc = allreduce_sum_f64(E, reinterpret_cast<double*>(E->d_ab + r.col_begin), (size_t)ncols * 2)) return rc;
@@ -233,6 +252,9 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
     fa.c0 = r.col_begin; fa.c1 = r.col_end; fa.f = IS_V ? f : -1; fa.K = E->K;
     if (rp && rp->run == 0 && E->excl0) {      // only the columns of this rank's block (their sums are complete locally)
         fa.c0 = E->blk[E->rank]; fa.c1 = E->blk[E->rank + 1];
+        ncols = fa.c1 - fa.c0;
+    } else if (rp && rp->run == 1 && E->xs) {  // cross shards: the same for the second field
+        fa.c0 = E->blk1[E->rank]; fa.c1 = E->blk1[E->rank + 1];
         ncols = fa.c1 - fa.c0;
     }
     fa.col_tile0 = E->d_col_tile0; fa.partial = partial; fa.colsum = E->d_colsum; fa.from_colsum = from_colsum;
@@ -254,6 +276,7 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
         if (ncols) k_finalize<KIND><<<nblk(ncols), 256, 0, st>>>(fa);
     }
     LAUNCHED(E);
+    if (rp && rp->run >= 0 && E->xs) if (int rc = exchange_records(E, rp->run)) return rc;
     return check_launch(E, "combine_finalize");
 }
 
@@ -321,17 +344,18 @@ static void launch_stream(Engine* E, int side, bool has_own, bool own_is_w, bool
     const DevSplit& S = E->tr;
     const Run& r = E->runs[side];
     StreamArgs a{};
-    a.c0 = r.col_begin; a.c1 = r.col_end; a.real0 = S.h_colptr[r.col_begin]; a.ts_shift = E->ts_shift;
+    const Engine::SideView& sv = E->side[side];
+    a.c0 = r.col_begin; a.c1 = r.col_end; a.real0 = sv.entry0; a.ts_shift = E->ts_shift;
     if (E->bv.on) {
         a.colptr = E->bv.colptr[side]; a.entry0 = E->bv.entry0; a.n = E->bv.n; a.ntiles = E->bv.ntiles; a.ts_shift = E->vbo_ts_shift;
         a.tile_col0 = E->d_vbo_tile_col0 + (side ? E->vbo_max_tiles : 0); a.idx = E->d_vbo_idx[side];
         a.partial = E->d_vbo_partial + (side ? (size_t)E->vbo_max_tiles * 8 : 0);
     } else {
-        a.colptr = S.colptr; a.entry0 = a.real0; a.n = S.n; a.ntiles = E->s_ntiles[side];
+        a.colptr = sv.colptr; a.entry0 = a.real0; a.n = sv.n; a.ntiles = E->s_ntiles[side];
         a.tile_col0 = E->d_stile_col0 + (side ? E->s_ntiles[0] : 0); a.idx = nullptr;
         a.partial = E->d_partial + (side ? (size_t)E->s_ntiles[0] * 8 : 0);
     }
-    a.oc = S.cother; a.xv = S.cval; a.xo = S.cother_val;
+    a.oc = sv.oc; a.xv = sv.xv; a.xo = sv.xo;
     a.e = side ? E->d_e2 : E->d_e;
     a.rec = E->d_cpack; a.own = E->d_opack;
     a.has_own = has_own; a.own_is_w = own_is_w; a.has_oth = has_oth; a.oth_is_w = oth_is_w;
@@ -400,7 +424,10 @@ static int sweep_streams(Engine* E) {
         ProfScope ps(E, 7);
         const bool lw = steps.back() < 0;
         launch_stream<MCMC, false, false>(E, 0, true, lw, true, lw);
-        k_pack_h4<<<nblk(r0.col_end - r0.col_begin), 256, 0, st>>>(r0.col_begin, r0.col_end, table(steps.back()), E->d_cpack); LAUNCHED(E);
+        if (E->xs) {      // the first field's final means of the other ranks' blocks are not in the parameter tables yet: they are the records' own means
+            const uint32_t ns = (uint32_t)E->world * E->slot_max[0];
+            k_pack_h4_self<<<nblk(ns), 256, 0, st>>>(E->slot_base[0], E->slot_base[0] + ns, E->d_cpack); LAUNCHED(E);
+        } else { k_pack_h4<<<nblk(r0.col_end - r0.col_begin), 256, 0, st>>>(r0.col_begin, r0.col_end, table(steps.back()), E->d_cpack); LAUNCHED(E); }
         launch_stream<MCMC, false, false>(E, 1, true, lw, false, false);
     }
     return check_launch(E, "sweep_streams");
@@ -412,7 +439,7 @@ int stream_tile_cols(Engine* E) {
     for (int ri = 0; ri < 2; ri++) {
         const Run& r = E->runs[ri];
         uint32_t nt = E->s_ntiles[ri];
-        if (nt) { k_tile_col0<<<(nt + 255) / 256, 256, 0, E->stream>>>(E->tr.colptr, r.col_begin, r.col_end, nt, E->ts_shift, E->d_stile_col0 + off); LAUNCHED(E); }
+        if (nt) { k_tile_col0<<<(nt + 255) / 256, 256, 0, E->stream>>>(E->side[ri].colptr, r.col_begin, r.col_end, nt, E->ts_shift, E->d_stile_col0 + off); LAUNCHED(E); }
         off += nt;
     }
     cudaError_t e = cudaGetLastError();
@@ -430,10 +457,12 @@ static void shift_e(Engine* E) {
         return;
     }
     k_shift_e<<<SV_RGRID, 256, 0, E->stream>>>(E->d_e, E->tr.n, E->d_sc); LAUNCHED(E);
-    if (E->d_e2) { k_shift_e<<<SV_RGRID, 256, 0, E->stream>>>(E->d_e2, E->tr.n, E->d_sc); LAUNCHED(E); }
+    if (E->d_e2) { k_shift_e<<<SV_RGRID, 256, 0, E->stream>>>(E->d_e2, E->xs ? E->sec.n : E->tr.n, E->d_sc); LAUNCHED(E); }
 }
 // (re)build the second copy from the first
+static int predict_second(Engine* E);
 static void sync_e2(Engine* E) {
+    if (E->xs) { predict_second(E); return; }      // cross shards: the second copy lives on other cases: predicted from the parameters
     if (!E->streams || !E->tr.n) return;
     const Run& r1 = E->runs[1];
     k_gather_e<<<nblk(E->tr.n), 256, 0, E->stream>>>(E->d_e, E->tr.crow + E->tr.h_colptr[r1.col_begin], E->tr.n, E->d_e2); LAUNCHED(E);
@@ -502,14 +531,17 @@ static int predict(Engine* E, const DevSplit& S, double* e_out, int red_slot, in
 template <int MODE>   // PRED_VB_TRAIN or PRED_MC_TRAIN
 static int predict_train(Engine* E, int red_slot) {
     const DevSplit& S = E->tr;
-    if (!E->streams || E->K < 1 || E->K > 256 || getenv("SVBFM_NO_PREDICT2")) return predict<MODE>(E, S, E->d_e, red_slot, 1);
+    if (red_slot >= 0 && (!E->streams || E->K < 1 || E->K > 256 || getenv("SVBFM_NO_PREDICT2"))) return predict<MODE>(E, S, E->d_e, red_slot, 1);
     cudaStream_t st = E->stream;
     if (!E->d_pvT && dev_alloc(E, &E->d_pvT, (size_t)E->K * E->D)) return SVBFM_ERR_OOM;
     k_transpose_params<<<dim3((E->D + 31) / 32, (E->K + 31) / 32), dim3(32, 8), 0, st>>>(E->d_pv, E->D, E->K, E->d_pvT); LAUNCHED(E);
     Predict2Args a{};
     a.rcol = S.rcol; a.rval = S.rval; a.y = S.y; a.n = S.n; a.pw = E->d_pw; a.pvT = E->d_pvT; a.K = E->K; a.k0 = E->cfg.k0; a.k1 = E->cfg.k1;
     a.sc = E->d_sc; a.e = E->d_e; a.partial = E->d_red_partial;
-    const unsigned grid = std::max(1u, std::min<unsigned>((S.n + 255) / 256, SV_RGRID / 2));   // partial[] holds grid * 8 <= SV_RGRID * 4 sums
+    if (red_slot < 0) {      // cross shards: the residuals of the second copy's cases; their sums are not used (the first copy holds every case once)
+        a.rcol = E->sec.rcol; a.rval = nullptr; a.y = E->sec.y; a.n = E->sec.n; a.e = E->d_e2;
+    }
+    const unsigned grid = std::max(1u, std::min<unsigned>((a.n + 255) / 256, SV_RGRID / 2));   // partial[] holds grid * 8 <= SV_RGRID * 4 sums
     constexpr bool MC = (MODE == PRED_MC_TRAIN);
     // a warp per case. Half a warp per case (two cases share the fixed cost of a warp step) is built too, but measured slower
     // (begin 57 ms instead of 40 ms at 200 M cases, K = 50): opt-in for experiments
@@ -529,9 +561,20 @@ static int predict_train(Engine* E, int red_slot) {
     if (ns == 1) CALL_P2(1); else if (ns == 2) CALL_P2(2); else if (ns == 4) CALL_P2(4); else CALL_P2(8);
 #undef CALL_P2
     LAUNCHED(E);
+    if (red_slot < 0) return check_launch(E, "predict_second");
     k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, grid * 8, 1, RED(E->d_sc, red_slot), 0); LAUNCHED(E);
     if (int rc = allreduce_sum_f64(E, RED(E->d_sc, red_slot), 1)) return rc;
     return check_launch(E, "predict_train");
+}
+static int predict_second(Engine* E) {
+    const bool mc = E->cfg.method == SVBFM_MCMC;
+    if (E->K < 1 || E->K > 256 || getenv("SVBFM_NO_PREDICT2")) {      // the case-wise kernel on a view of the shard (its sums go to a scratch slot)
+        DevSplit V;
+        V.n = E->sec.n; V.nnz = 2ull * E->sec.n; V.rcol = E->sec.rcol; V.uniformF = 2; V.all_ones = true; V.y = E->sec.y;
+        return mc ? predict<PRED_MC_TRAIN>(E, V, E->d_e2, 7, 1) : predict<PRED_VB_TRAIN>(E, V, E->d_e2, 7, 1);
+    }
+    if (!E->sec.n) return 0;
+    return mc ? predict_train<PRED_MC_TRAIN>(E, -1) : predict_train<PRED_VB_TRAIN>(E, -1);
 }
 
 // ---------------------------------------------------------------------------------------------- iterations
@@ -779,7 +822,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     rc |= dev_alloc(E, &E->d_sc, 1);
     rc |= dev_alloc(E, &E->d_colsum, D * 4);
     rc |= dev_alloc(E, &E->d_delta, D);
-    rc |= dev_alloc(E, &E->d_cpack, D);
+    rc |= dev_alloc(E, &E->d_cpack, D); E->cpack_cap = D;
     rc |= dev_alloc(E, &E->d_opack, D);
     rc |= dev_alloc(E, &E->d_ab, D);
     rc |= dev_alloc(E, &E->d_dT, D);
@@ -803,7 +846,7 @@ void svbfm_destroy(svbfm_t* h) {
     cudaSetDevice(E->dev);
     cudaStreamSynchronize(E->stream);
     if (E->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(E->nccl_comm);
-    free_split(E, E->tr); free_split(E, E->te);
+    free_split(E, E->tr); free_split(E, E->te); free_second(E);
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
@@ -890,11 +933,12 @@ int svbfm_set_groups(svbfm_t* h, const uint32_t* attr_group, uint32_t num_groups
 int svbfm_set_csc(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_cols, const uint64_t* colptr, const uint32_t* case_id,
                   const float* x, const float* target) {
     Engine* E = reinterpret_cast<Engine*>(h);
-    if (!E || !colptr || (split != SVBFM_TRAIN && split != SVBFM_TEST)) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc: bad arguments");
-    if (colptr[num_cols] > 0 && (!case_id || !x)) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc: null entry arrays");
-    if (num_cases > 0 && !target) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc: null target");
+    if (!E || !colptr || (split != SVBFM_TRAIN && split != SVBFM_TEST && split != SVBFM_TRAIN_SECOND)) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc: bad arguments");
     if (E->begun) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc after svbfm_begin");
     SV_CUDA(E, cudaSetDevice(E->dev));
+    if (split == SVBFM_TRAIN_SECOND) return ingest_second(E, num_cases, num_cols, colptr, case_id, x, target);      // validates its arguments collectively
+    if (colptr[num_cols] > 0 && (!case_id || !x)) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc: null entry arrays");
+    if (num_cases > 0 && !target) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc: null target");
     bool is_train = split == SVBFM_TRAIN;
     DevSplit& S = is_train ? E->tr : E->te;
     int rc = ingest_split(E, S, is_train, num_cases, num_cols, colptr, case_id, x, target);
@@ -1063,7 +1107,7 @@ int svbfm_reset(svbfm_t* h) {
     if (!E) return SVBFM_ERR_ARG;
     SV_CUDA(E, cudaSetDevice(E->dev));
     SV_CUDA(E, cudaStreamSynchronize(E->stream));
-    free_split(E, E->tr); free_split(E, E->te);
+    free_split(E, E->tr); free_split(E, E->te); free_second(E);
     E->runs.clear();
     E->begun = false; E->have_state = false; E->rows_reordered = false; E->run0_sequential = false; E->streams = false; E->excl0 = false; E->vbo_streams = false; E->bv.on = false;
     SV_CUDA(E, cudaMemsetAsync(E->d_dT, 0, (size_t)E->D * 8, E->stream));
@@ -1278,7 +1322,7 @@ int svbfm_copies_max_diff(svbfm_t* h, double* max_abs_diff) {
     Engine* E = reinterpret_cast<Engine*>(h);
     if (!E || !max_abs_diff) return SVBFM_ERR_ARG;
     *max_abs_diff = 0.0;
-    if (!E->streams || !E->d_e2 || !E->tr.n) return SVBFM_OK;
+    if (!E->streams || !E->d_e2 || !E->tr.n || E->xs) return SVBFM_OK;      // cross shards: the two copies hold different cases on a rank
     SV_CUDA(E, cudaSetDevice(E->dev));
     unsigned long long* d = nullptr;
     SV_CUDA(E, sv_malloc((void**)&d, 8));
@@ -1330,7 +1374,7 @@ int svbfm_get_info(svbfm_t* h, svbfm_info* out) {
     out->world_size = (uint32_t)E->world;
     out->fused_schedule = ((stream_ok(E) || E->vbo_streams) ? 1u : 0u) | (E->rec_rank ? 2u : 0u) | ((E->stream_tma && stream_ok(E)) ? 4u : 0u) |
                           (E->graph_replays ? 8u : 0u);
-    out->exclusive_blocks = E->excl0 ? 1u : 0u;
+    out->exclusive_blocks = (E->excl0 ? 1u : 0u) | (E->xs ? 2u : 0u);
     return SVBFM_OK;
 }
 

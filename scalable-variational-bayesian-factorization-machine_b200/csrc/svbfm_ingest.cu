@@ -275,6 +275,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
                  const float* x, const float* target) {
     cudaStream_t st = E->stream;
     free_split(E, S);
+    if (is_train) free_second(E);
     // temporaries of this function: whatever is still owned when it returns (early, on an error) goes back to the block cache
     struct Temps {
         std::vector<void**> slots;
@@ -543,6 +544,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         SV_CUDA(E, cudaStreamSynchronize(st));
     }
     if (is_train && !E->rec_rank) { sv_free(E->d_rec_slot); E->d_rec_slot = nullptr; }
+    if (is_train) set_side_views(E);
     mark("other-feature arrays");
     if (is_train && E->streams) {
         // ---- stream schedule: implicit tiles of 2^ts_shift entries per run; only their first column and the list of the
@@ -574,6 +576,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         if (dev_alloc(E, &E->d_stile_col0, (size_t)E->s_ntiles[0] + E->s_ntiles[1])) return SVBFM_ERR_OOM;
         if (dev_alloc(E, &E->d_span_heavy, heavy.size())) return SVBFM_ERR_OOM;
         SV_CUDA(E, cudaMemcpyAsync(E->d_span_heavy, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice, st));
+        set_side_views(E);
         if (int r = stream_tile_cols(E)) return r;
         SV_CUDA(E, cudaStreamSynchronize(st));
         E->n_tiles = 0; E->n_heavy = 0;
@@ -667,6 +670,263 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         SV_CUDA(E, cudaStreamSynchronize(st));
     }
     mark("tiles + exec order");
+    SV_CUDA(E, cudaGetLastError());
+    return 0;
+}
+
+// ---- cross shards: the second residual copy on its own shard (svbfm_set_csc(SVBFM_TRAIN_SECOND); svbfm_internal.h Engine::xs) ----
+void set_side_views(Engine* E) {
+    const DevSplit& S = E->tr;
+    for (int side = 0; side < 2; side++) {
+        Engine::SideView& v = E->side[side];
+        v = Engine::SideView();
+        if (E->runs.size() != 2) continue;
+        const Run& r = E->runs[side];
+        const uint64_t e0 = S.h_colptr.empty() ? 0 : S.h_colptr[r.col_begin];
+        if (side == 1 && E->xs) {
+            v.colptr = E->sec.colptr; v.entry0 = 0; v.n = E->sec.n; v.oc = E->sec.oc;
+        } else {
+            v.colptr = S.colptr; v.entry0 = e0; v.n = (uint32_t)r.nnz;
+            v.oc = S.cother; v.xv = S.cval; v.xo = S.cother_val;
+        }
+    }
+}
+
+void free_second(Engine* E) {
+    sv_free(E->sec.colptr); sv_free(E->sec.oc); sv_free(E->sec.rcol); sv_free(E->sec.y);
+    E->sec = Engine::SecondShard();
+    E->xs = false;
+    E->blk1.clear();
+}
+
+struct BlockTable { uint32_t blk[17]; int world; };
+// common record slots of the cross-shard layout: field f, block r, position k inside the block -> base[f] + r * max[f] + k.
+// First field: k = column - block start. Second field: the same, unless `ranked` (then only the columns OUTSIDE this
+// rank's block are zeroed here; the own block is filled by k_slot_scatter and the ranks' pieces are summed)
+static __global__ void k_xs_slots(uint32_t c0, uint32_t c1, BlockTable bt, uint32_t base, uint32_t mx, int zero_only, uint32_t* __restrict__ slot) {
+    uint32_t j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c1) return;
+    if (zero_only) { slot[j] = 0; return; }
+    int r = 0;
+    while (r + 1 < bt.world && j >= bt.blk[r + 1]) r++;
+    slot[j] = base + (uint32_t)r * mx + (j - bt.blk[r]);
+}
+static __global__ void k_invert_slots(const uint32_t* __restrict__ slot, uint32_t c0, uint32_t c1, uint32_t* __restrict__ col_of_slot) {
+    uint32_t j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < c1) col_of_slot[slot[j]] = j;
+}
+// oc[p] <- new_slot[column of oc[p]] (old: the entries hold old slots when col_of_old is set, column ids otherwise)
+static __global__ void k_remap_oc(uint32_t* __restrict__ oc, uint64_t n, const uint32_t* __restrict__ col_of_old, const uint32_t* __restrict__ new_slot) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t c = oc[p];
+    if (col_of_old) c = col_of_old[c];
+    oc[p] = new_slot[c];
+}
+// first-field entries of the second shard: user_of_case[case] = column
+static __global__ void k_sec_users(const uint32_t* __restrict__ case_id, const uint32_t* __restrict__ colof, uint32_t n, uint32_t* __restrict__ user_of_case,
+                                   uint32_t* flags) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t c = case_id[p];
+    if (c >= n) { flags[1] = 1; return; }
+    if (atomicExch(&user_of_case[c], colof[p]) != 0xffffffffu) flags[2] = 1;      // a case twice in the first field
+}
+// second-field entries (the shard's entry order): other column, target, {user, item} pair of every entry
+static __global__ void k_sec_entries(const uint32_t* __restrict__ case_id, const uint32_t* __restrict__ colof, uint32_t n, const uint32_t* __restrict__ user_of_case,
+                                     uint32_t* __restrict__ seen, const float* __restrict__ target, uint32_t* __restrict__ oc, uint32_t* __restrict__ rcol,
+                                     float* __restrict__ y, uint32_t* flags) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    uint32_t c = case_id[q];
+    if (c >= n) { flags[1] = 1; return; }
+    if (atomicExch(&seen[c], 1u) != 0u) flags[2] = 1;                               // a case twice in the second field
+    uint32_t u = user_of_case[c];
+    if (u == 0xffffffffu) { flags[2] = 1; u = 0; }
+    oc[q] = u;
+    rcol[2 * (size_t)q] = u; rcol[2 * (size_t)q + 1] = colof[q];
+    y[q] = target[c];
+}
+
+int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr, const uint32_t* case_id, const float* x, const float* target) {
+    cudaStream_t st = E->stream;
+    DevSplit& S = E->tr;
+    free_second(E);
+    // ---- what must hold on every rank alike (no data-dependent exits before the first collective)
+    if (E->world <= 1) return fail(E, SVBFM_ERR_ARG, "set_csc(TRAIN_SECOND): needs a communicator (svbfm_comm_init)");
+    if (!E->d_e) return fail(E, SVBFM_ERR_ARG, "set_csc(TRAIN_SECOND): the train split must be set first");
+    if (E->cfg.method == SVBFM_VB_ONLINE || E->cfg.task != 0) return fail(E, SVBFM_ERR_ARG, "set_csc(TRAIN_SECOND): vb and mcmc regression only");
+    if (!E->streams || !E->excl0 || E->runs.size() != 2)
+        return fail(E, SVBFM_ERR_ARG, "set_csc(TRAIN_SECOND): the train split must be two complete one-hot fields sharded by blocks of the first field");
+    const Run r0 = E->runs[0], r1 = E->runs[1];
+    // ---- local validation; the verdict is agreed on by all ranks before anything else is exchanged
+    std::string why;
+    if (ncols > E->D || ncols < r1.col_begin) why = "num_cols out of range";
+    else if (colptr[0] != 0) why = "colptr[0] != 0";
+    else {
+        for (uint32_t j = 0; j < ncols && why.empty(); j++) if (colptr[j + 1] < colptr[j]) why = "colptr not monotone";
+    }
+    const uint32_t nc_ext = S.ncols_ext;
+    uint64_t off1 = 0;
+    if (why.empty()) {
+        const uint64_t nnz = colptr[ncols];
+        off1 = colptr[std::min(r1.col_begin, ncols)];
+        if (nnz != 2ull * n || off1 != n) why = "every case needs exactly one entry in each of the two fields";
+        else if (n && (!case_id || !x || !target)) why = "null entry arrays";
+        else if (ncols > nc_ext) why = "more columns than the train split";
+    }
+    uint32_t* d_flags = nullptr;      // [0] x != 1   [1] case id out of range   [2] not one entry per case and field
+    uint32_t *d_case = nullptr, *d_colof = nullptr, *d_user = nullptr, *d_seen = nullptr;
+    uint64_t* d_cp = nullptr;
+    float *d_x = nullptr, *d_t = nullptr;
+    struct Temps { std::vector<void**> v; ~Temps() { for (void** p : v) { sv_free(*p); *p = nullptr; } } } temps;
+    for (void** p : {(void**)&d_flags, (void**)&d_case, (void**)&d_colof, (void**)&d_user, (void**)&d_seen, (void**)&d_cp, (void**)&d_x, (void**)&d_t}) temps.v.push_back(p);
+    SV_CUDA(E, sv_malloc((void**)&d_flags, 8 * 4));
+    SV_CUDA(E, cudaMemsetAsync(d_flags, 0, 8 * 4, st));
+    uint32_t h_flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (why.empty() && n) {
+        const uint64_t nnz = 2ull * n;
+        SV_CUDA(E, sv_malloc((void**)&d_case, nnz * 4));
+        SV_CUDA(E, sv_malloc((void**)&d_colof, nnz * 4));
+        SV_CUDA(E, sv_malloc((void**)&d_x, nnz * 4));
+        SV_CUDA(E, sv_malloc((void**)&d_t, (size_t)n * 4));
+        SV_CUDA(E, sv_malloc((void**)&d_cp, ((size_t)ncols + 1) * 8));
+        SV_CUDA(E, sv_malloc((void**)&d_user, (size_t)n * 4));
+        SV_CUDA(E, sv_malloc((void**)&d_seen, (size_t)n * 4));
+        SV_CUDA(E, cudaMemcpyAsync(d_cp, colptr, ((size_t)ncols + 1) * 8, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemcpyAsync(d_case, case_id, nnz * 4, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemcpyAsync(d_t, target, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemsetAsync(d_user, 0xff, (size_t)n * 4, st));
+        SV_CUDA(E, cudaMemsetAsync(d_seen, 0, (size_t)n * 4, st));
+        k_any_not_one<<<std::min<unsigned>(nblk(nnz), 148 * 16), 256, 0, st>>>(d_x, nnz, d_flags + 0);
+        k_col_of_entry<<<nblk(nnz), 256, 0, st>>>(d_cp, ncols, nnz, d_colof);
+        if (dev_alloc(E, &E->sec.oc, n)) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->sec.rcol, (size_t)n * 2)) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->sec.y, n)) return SVBFM_ERR_OOM;
+        k_sec_users<<<nblk(n), 256, 0, st>>>(d_case, d_colof, n, d_user, d_flags);
+        k_sec_entries<<<nblk(n), 256, 0, st>>>(d_case + off1, d_colof + off1, n, d_user, d_seen, d_t, E->sec.oc, E->sec.rcol, E->sec.y, d_flags);
+        SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
+        SV_CUDA(E, cudaStreamSynchronize(st));
+        if (h_flags[0]) why = "x != 1";
+        else if (h_flags[1]) why = "case id out of range";
+        else if (h_flags[2]) why = "every case needs exactly one entry in each of the two fields";
+    }
+    // entry pointers of the second field's columns inside the shard, indexed by global column id
+    E->sec.n = why.empty() ? n : 0;
+    E->sec.h_colptr.assign((size_t)nc_ext + 1, 0);
+    if (why.empty())
+        for (uint32_t j = r1.col_begin; j <= nc_ext; j++) E->sec.h_colptr[j] = colptr[std::min(j, ncols)] - off1;
+    // ---- the ranks' verdicts, the blocks of the second field and the global number of cases: collectives from here on
+    {
+        uint32_t bad = why.empty() ? 0u : 1u;
+        SV_CUDA(E, cudaMemcpyAsync(d_flags + 4, &bad, 4, cudaMemcpyHostToDevice, st));
+        if (int rc = allreduce(E, d_flags + 4, 1, 3 /*ncclUint32*/, 2 /*ncclMax*/)) return rc;
+        SV_CUDA(E, cudaMemcpyAsync(&bad, d_flags + 4, 4, cudaMemcpyDeviceToHost, st));
+        SV_CUDA(E, cudaStreamSynchronize(st));
+        if (bad) { free_second(E); return fail(E, SVBFM_ERR_ARG, "set_csc(TRAIN_SECOND): " + (why.empty() ? std::string("another rank rejected its shard") : why)); }
+    }
+    bool excl1 = false;
+    if (int rc = detect_blocks(E, r1, E->sec.h_colptr, E->blk1, excl1)) return rc;
+    double tot = (double)n, *d_tot = nullptr;
+    temps.v.push_back((void**)&d_tot);
+    SV_CUDA(E, sv_malloc((void**)&d_tot, 8));
+    SV_CUDA(E, cudaMemcpyAsync(d_tot, &tot, 8, cudaMemcpyHostToDevice, st));
+    if (int rc = allreduce(E, d_tot, 1, 8 /*ncclDouble*/, 0 /*ncclSum*/)) return rc;
+    SV_CUDA(E, cudaMemcpyAsync(&tot, d_tot, 8, cudaMemcpyDeviceToHost, st));
+    SV_CUDA(E, cudaStreamSynchronize(st));
+    if (!excl1 || (uint64_t)tot != E->n_total) {
+        free_second(E);
+        return fail(E, SVBFM_ERR_ARG, !excl1 ? "set_csc(TRAIN_SECOND): the ranks' shards must cover disjoint, rank-ordered blocks of the second field's columns"
+                                             : "set_csc(TRAIN_SECOND): the second shards do not hold the same number of cases as the train split");
+    }
+    if (dev_alloc(E, &E->sec.colptr, (size_t)nc_ext + 1)) return SVBFM_ERR_OOM;
+    SV_CUDA(E, cudaMemcpyAsync(E->sec.colptr, E->sec.h_colptr.data(), ((size_t)nc_ext + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (!E->sec.oc) {      // a rank without cases
+        if (dev_alloc(E, &E->sec.oc, 1)) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->sec.rcol, 2)) return SVBFM_ERR_OOM;
+        if (dev_alloc(E, &E->sec.y, 1)) return SVBFM_ERR_OOM;
+    }
+
+    // ---- common record slots: slot-contiguous blocks, padded to the largest block, so that the records of a field travel by
+    // one in-place allgather. Second field: inside a block by popularity (descending column length, known to the block's owner)
+    BlockTable b0{}, b1{};
+    b0.world = b1.world = E->world;
+    uint32_t mx0 = 1, mx1 = 1;
+    for (int r = 0; r <= E->world; r++) { b0.blk[r] = E->blk[r]; b1.blk[r] = E->blk1[r]; }
+    for (int r = 0; r < E->world; r++) { mx0 = std::max(mx0, E->blk[r + 1] - E->blk[r]); mx1 = std::max(mx1, E->blk1[r + 1] - E->blk1[r]); }
+    E->slot_base[0] = 0; E->slot_max[0] = mx0;
+    E->slot_base[1] = (uint32_t)E->world * mx0; E->slot_max[1] = mx1;
+    const size_t total_slots = (size_t)E->world * ((size_t)mx0 + mx1);
+    if (total_slots >= (1ull << 32)) { free_second(E); return fail(E, SVBFM_ERR_ARG, "set_csc(TRAIN_SECOND): too many record slots"); }
+    uint32_t* d_new = nullptr;
+    temps.v.push_back((void**)&d_new);
+    SV_CUDA(E, sv_malloc((void**)&d_new, (size_t)E->D * 4));
+    SV_CUDA(E, cudaMemsetAsync(d_new, 0, (size_t)E->D * 4, st));
+    const uint32_t nc0 = r0.col_end - r0.col_begin, nc1 = r1.col_end - r1.col_begin;
+    if (nc0) k_xs_slots<<<nblk(nc0), 256, 0, st>>>(r0.col_begin, r0.col_end, b0, E->slot_base[0], mx0, 0, d_new);
+    const bool ranked = E->want_rec_rank;
+    if (nc1) k_xs_slots<<<nblk(nc1), 256, 0, st>>>(r1.col_begin, r1.col_end, b1, E->slot_base[1], mx1, ranked ? 1 : 0, d_new);
+    if (ranked) {
+        const uint32_t c0 = E->blk1[E->rank], nb = E->blk1[E->rank + 1] - c0;
+        if (nb) {
+            uint32_t *d_k = nullptr, *d_v = nullptr, *d_ks = nullptr, *d_vs = nullptr;
+            SV_CUDA(E, sv_malloc((void**)&d_k, (size_t)nb * 4));
+            SV_CUDA(E, sv_malloc((void**)&d_v, (size_t)nb * 4));
+            k_slot_keys<<<nblk(nb), 256, 0, st>>>(E->sec.colptr, c0, nb, d_k, d_v);
+            int rc = sort_pairs(E, d_k, d_v, nb, 1ull << 32, &d_ks, &d_vs);
+            if (!rc) { k_slot_scatter<<<nblk(nb), 256, 0, st>>>(d_vs, E->slot_base[1] + (uint32_t)E->rank * mx1, nb, d_new); cudaStreamSynchronize(st); }
+            sv_free(d_k); sv_free(d_v); sv_free(d_ks); sv_free(d_vs);
+            if (rc) return rc;
+        }
+        if (int rc = allreduce(E, d_new + r1.col_begin, nc1, 3 /*ncclUint32*/, 0 /*ncclSum*/)) return rc;
+    }
+    // the first copy's entries gather second-field records: old slots (or column ids) -> common slots
+    {
+        uint32_t* d_inv = nullptr;
+        if (E->rec_rank) {
+            SV_CUDA(E, sv_malloc((void**)&d_inv, (size_t)E->D * 4));
+            k_invert_slots<<<nblk(nc1), 256, 0, st>>>(E->d_rec_slot, r1.col_begin, r1.col_end, d_inv);
+        }
+        if (r0.nnz) k_remap_oc<<<nblk(r0.nnz), 256, 0, st>>>(S.cother + S.h_colptr[r0.col_begin], r0.nnz, d_inv, d_new);
+        if (n) k_remap_oc<<<nblk(n), 256, 0, st>>>(E->sec.oc, n, nullptr, d_new);
+        SV_CUDA(E, cudaStreamSynchronize(st));
+        sv_free(d_inv);
+    }
+    sv_free(E->d_rec_slot);
+    E->d_rec_slot = d_new; d_new = nullptr;
+    E->rec_rank = true;
+    if (E->cpack_cap < total_slots) {
+        sv_free(E->d_cpack); E->d_cpack = nullptr;
+        if (sv_malloc((void**)&E->d_cpack, total_slots * 32 /* sizeof(ColPack) */) != cudaSuccess) return fail(E, SVBFM_ERR_OOM, "cudaMalloc: record slots");
+        E->cpack_cap = total_slots;
+    }
+    // ---- tiles of the second side on the new shard (the first side keeps its own), second residual copy, tile sums
+    const uint64_t TS = 1ull << E->ts_shift;
+    std::vector<uint32_t> heavy;
+    for (int ri = 0; ri < 2; ri++) {
+        const Run& r = E->runs[ri];
+        const std::vector<uint64_t>& cp = ri ? E->sec.h_colptr : S.h_colptr;
+        const uint64_t e0 = cp[r.col_begin], nn = cp[r.col_end] - e0;
+        E->s_ntiles[ri] = (uint32_t)((nn + TS - 1) / TS);
+        const size_t h0 = heavy.size();
+        for (uint32_t j = r.col_begin; j < r.col_end; j++) {
+            uint64_t b = cp[j], e = cp[j + 1];
+            if (e > b && (e - 1 - e0) / TS - (b - e0) / TS > 8 /* SV_SPAN_LIGHT */) heavy.push_back(j);
+        }
+        E->span_heavy_n[ri] = (uint32_t)(heavy.size() - h0);
+    }
+    sv_free(E->d_stile_col0); sv_free(E->d_span_heavy); sv_free(E->d_e2); sv_free(E->d_partial);
+    E->d_stile_col0 = nullptr; E->d_span_heavy = nullptr; E->d_e2 = nullptr; E->d_partial = nullptr;
+    if (dev_alloc(E, &E->d_stile_col0, (size_t)E->s_ntiles[0] + E->s_ntiles[1])) return SVBFM_ERR_OOM;
+    if (dev_alloc(E, &E->d_span_heavy, heavy.size())) return SVBFM_ERR_OOM;
+    if (dev_alloc(E, &E->d_e2, n)) return SVBFM_ERR_OOM;
+    if (dev_alloc(E, &E->d_partial, ((size_t)E->s_ntiles[0] + E->s_ntiles[1]) * 8)) return SVBFM_ERR_OOM;
+    SV_CUDA(E, cudaMemcpyAsync(E->d_span_heavy, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice, st));
+    E->xs = true;
+    set_side_views(E);
+    if (int rc = stream_tile_cols(E)) return rc;
+    SV_CUDA(E, cudaStreamSynchronize(st));
     SV_CUDA(E, cudaGetLastError());
     return 0;
 }

@@ -216,7 +216,37 @@ struct Engine {
     std::vector<uint32_t> blk;        // [world + 1]
     double2* d_xchg = nullptr;        // staging of the block exchange: send [rows][maxcnt] + recv [world][rows][maxcnt]
     size_t xchg_cap = 0;
+    // Cross shards (several GPUs, stream schedule; svbfm_set_csc(SVBFM_TRAIN_SECOND)): the two residual copies are sharded
+    // DIFFERENTLY. Copy 1 (e, entry order of the first field) holds the cases of this rank's block of first-field columns
+    // (excl0), copy 2 (e2, entry order of the second field) the cases of this rank's block of SECOND-field columns, handed
+    // over as a second shard of the same global train set. Every column of either field then has all of its entries on one
+    // rank: no sums are reduced between the ranks and no column is updated twice; what travels is the 32-byte record of
+    // every updated column (one in-place ncclAllGather per (step, field) over slot-contiguous blocks of `cpack`) and, once
+    // per iteration, the parameter blocks (exchange_blocks). Per-rank work per pass: n / world entries and |field| / world
+    // columns, against n / world entries and ALL columns of the second field with the allreduce scheme.
+    bool xs = false;
+    std::vector<uint32_t> blk1;       // [world + 1] blocks of the second field's columns
+    struct SecondShard {
+        uint32_t n = 0;                    // cases of the second copy on this rank
+        uint64_t* colptr = nullptr;        // [tr.ncols_ext + 1], indexed by global column id: entry pointer into the shard (0 below run 1)
+        std::vector<uint64_t> h_colptr;    // host copy of the same
+        uint32_t* oc = nullptr;            // [n] record slot of the first-field column of every entry
+        uint32_t* rcol = nullptr;          // [n][2] {first-field column, second-field column} of every entry (re-prediction)
+        float* y = nullptr;                // [n] targets in entry order
+    } sec;
+    uint32_t slot_base[2] = {0, 0}, slot_max[2] = {0, 0};   // record slots of field f: [slot_base[f] + r * slot_max[f], + block size) for rank r
+    size_t cpack_cap = 0;             // records allocated in d_cpack
+    // what a pass over side 0 / 1 of the stream schedule reads (set_side_views)
+    struct SideView {
+        const uint64_t* colptr = nullptr;  // indexed by global column id
+        uint64_t entry0 = 0;               // colptr[first column of the run]
+        uint32_t n = 0;                    // entries of the side
+        const uint32_t* oc = nullptr;      // other-column record slot / id per entry; the side's first entry is oc[entry0]
+        const float* xv = nullptr;         // x of the entry / of the other entry, indexed like oc (null: all ones)
+        const float* xo = nullptr;
+    } side[2];
 };
+void set_side_views(Engine* E);
 
 // svbfm_ingest.cu
 int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t num_cases, uint32_t num_cols, const uint64_t* colptr,
@@ -225,6 +255,10 @@ void free_split(Engine* E, DevSplit& S);
 int stream_tile_cols(Engine* E);   // svbfm_engine.cu: first column of every implicit tile (k_tile_col0)
 int allreduce(Engine* E, void* buf, size_t count, int dtype /*nccl*/, int op /*nccl*/);
 int detect_exclusive_blocks(Engine* E);   // svbfm_engine.cu; collective (every rank calls it after the train split is in)
+int ingest_second(Engine* E, uint32_t num_cases, uint32_t num_cols, const uint64_t* colptr, const uint32_t* case_id, const float* x,
+                  const float* target);       // svbfm_ingest.cu: the second residual copy's shard (cross shards)
+void free_second(Engine* E);
+int detect_blocks(Engine* E, const Run& r, const std::vector<uint64_t>& h_colptr, std::vector<uint32_t>& blk, bool& exclusive);   // collective
 int vbo_stream_prepare(Engine* E, uint32_t num_batch);   // svbfm_ingest.cu: per-epoch batch index lists (needs d_rbatch, d_cbatch, d_batch_cnt)
 
 // error helpers

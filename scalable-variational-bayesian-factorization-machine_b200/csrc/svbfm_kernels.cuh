@@ -684,7 +684,11 @@ __device__ __forceinline__ void sv_mbar_wait(SvMbar* b, uint32_t parity) {
 // 8 x 3 109.3 ms per iteration, 4 x 7 106.2 ms. Tried and dropped in round 2: the records of batch b + 1 gathered into a second
 // register set while batch b is processed (80 registers: 127 ms), prefetch.global.L1 / .L2 of the next batch's records (153 ms),
 // 32-entry batches at 4 x 8 warps (119 ms): whatever adds L1TEX requests or keeps more of them in flight loses, the pass is
-// bound by the 128-byte lines the record gathers touch.
+// bound by the 128-byte lines the record gathers touch. Also tried (profiles/r02_d_*): the ring loop
+// rewritten for instruction count (shared addresses formed once, slots of two batches, no register double buffer): 586 M -> 427 M
+// warp instructions per pass, but 113.9 ms instead of 107.2: issue-active fell from 61 % to 43 % while the long-scoreboard stall
+// (the record gather) grew from 1.6 to 6.3 warps per issue -- the pass waits on L1TEX (data-pipe wavefronts 76 % either way),
+// not on the issue slots. Ring depth 4 x 768 B instead of 6 x 768 B: 106.0 vs 107.6 ms, inside the noise of the power cap.
 #ifndef SV_STREAM_WARPS
 #define SV_STREAM_WARPS 4
 #endif
@@ -1716,6 +1720,11 @@ __global__ void k_pack_init(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, 
 __global__ void k_pack_h4(uint32_t c0, uint32_t c1, const double2* __restrict__ p, ColPack* __restrict__ cpack) {
     uint32_t j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (j < c1) cpack[j].h4 = p[j].x;
+}
+// the same in slot space (cross shards): after the first field's last finalize the mean of a record is that final mean
+__global__ void k_pack_h4_self(uint32_t s0, uint32_t s1, ColPack* __restrict__ cpack) {
+    uint32_t sl = s0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (sl < s1) cpack[sl].h4 = cpack[sl].mu;
 }
 // first column that intersects each implicit tile of a run (largest j in [c0, c1) with colptr[j] <= first entry of the tile)
 __global__ void k_tile_col0(const uint64_t* colptr, uint32_t c0, uint32_t c1, uint32_t ntiles, uint32_t ts_shift, uint32_t* __restrict__ out) {

@@ -52,6 +52,35 @@ def shard_csc_by_block(data, rank, world, first_field_cols):
     return CscData(colptr, local[data.case_id[keep]].astype(np.uint32), data.x[keep], data.target[mine]), mine
 
 
+def second_block_bounds(colptr, first_field_cols, num_cols, world):
+    """Column boundaries [world + 1] that split the SECOND field's columns [first_field_cols, num_cols) into rank-ordered blocks
+    with about the same number of entries each (cross shards: the second residual copy is sharded by these blocks)."""
+    cum = np.asarray(colptr[first_field_cols:num_cols + 1], dtype=np.int64) - int(colptr[first_field_cols])
+    total = int(cum[-1])
+    b = [0]
+    for r in range(1, world):
+        b.append(int(np.searchsorted(cum, total * r // world, side="left")))
+    b.append(num_cols - first_field_cols)
+    return [first_field_cols + min(max(x, 0), num_cols - first_field_cols) for x in b]
+
+
+def shard_csc_by_second_block(data, rank, world, first_field_cols):
+    """Cases whose second-field feature lies in this rank's block of the second field's columns: the shard a rank hands over as
+    split TRAIN_SECOND after its first-field block (shard_csc_by_block) went in as TRAIN. Returns (CscData, original case ids)."""
+    import sys
+    CscData = sys.modules[__name__.rsplit('.', 1)[0]].CscData
+    b = second_block_bounds(data.colptr, first_field_cols, data.num_feature, world)
+    cp = data.colptr.astype(np.int64)
+    mine = np.sort(data.case_id[cp[b[rank]]:cp[b[rank + 1]]].astype(np.int64))     # one second-field entry per case
+    local = np.full(data.num_cases, -1, dtype=np.int64)
+    local[mine] = np.arange(len(mine))
+    keep = local[data.case_id] >= 0
+    col_of = np.repeat(np.arange(data.num_feature, dtype=np.int64), np.diff(cp))
+    colptr = np.zeros(data.num_feature + 1, dtype=np.uint64)
+    np.cumsum(np.bincount(col_of[keep], minlength=data.num_feature), out=colptr[1:])
+    return CscData(colptr, local[data.case_id[keep]].astype(np.uint32), data.x[keep], data.target[mine]), mine
+
+
 def broadcast_unique_id(get_id, rank, device=None):
     """Rank 0 calls get_id() -> bytes; every rank returns the same bytes (torch.distributed broadcast; gloo or nccl)."""
     import torch

@@ -41,6 +41,9 @@ def main():
              ("ragged_vb", ragged(3000, 400, 60, seed=52), "vb", 2, 3, {}),
              ("two_field_als", two_field(10000, 1000, 160, 120, seed=53), "mcmc", 2, 3, {}),
              ("two_field_als_blocks", two_field(10000, 1000, 160, 120, seed=55), "mcmc", 2, 3, {}),
+             # cross shards: first copy by user block, second copy by item block (svbfm_set_csc(TRAIN_SECOND))
+             ("two_field_vb_cross", two_field(12000, 1200, 200, 150, seed=58), "vb", 3, 3, {}),
+             ("two_field_als_cross", two_field(10000, 1000, 160, 120, seed=59), "mcmc", 2, 3, {}),
              ("two_field_vbo", two_field(10000, 1000, 160, 120, seed=56), "vb_online", 2, 2, dict(num_batch=4)),
              # three cases per batch: some ranks have no case of a batch and still have to take part in its collectives
              ("two_field_vbo_tiny_batches", two_field(300, 100, 20, 15, seed=57), "vb_online", 2, 2, dict(num_batch=100)))
@@ -55,7 +58,8 @@ def main():
         kw = dict(do_sample=False, do_multilevel=False) if method == "mcmc" else {}
         E = sv.Engine(method, D, K, 1, 1, float(tr.y.min()), float(tr.y.max()), seed=42, tile_entries=64, **kw)
         E.comm_init(uid, rank, world)
-        blocks = name.endswith("_blocks")
+        cross = name.endswith("_cross")
+        blocks = name.endswith("_blocks") or cross
         nu = 200 if name.startswith("two_field_vb") else 160
         if blocks:
             shard, mine = d.shard_csc_by_block(to_csc(tr), rank, world, nu)
@@ -64,9 +68,11 @@ def main():
             lo, hi = d.shard_bounds(tr.n_rows, rank, world)
             mine = np.arange(lo, hi)
         E.set_csc(sv.TRAIN, shard)
+        if cross:
+            E.set_csc(sv.TRAIN_SECOND, d.shard_csc_by_second_block(to_csc(tr), rank, world, nu)[0])
         E.set_csc(sv.TEST, d.shard_csc(to_csc(te), rank, world))
         info = E.info()
-        assert info["exclusive_blocks"] == (1 if blocks else 0), (name, info)
+        assert info["exclusive_blocks"] == (3 if cross else 1 if blocks else 0), (name, info)
         assert info["world_size"] == world
         E.set_state(sv.host_init_state(42, D, K, 0.1, sv.METHODS[method]))
         E.begin()

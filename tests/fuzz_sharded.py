@@ -54,7 +54,8 @@ def worker(a):
         tile = int(r.choice([0, 32, 64]))
         seed = int(r.integers(1, 10_000))
         U, I = int(r.choice([3, 20, 150])), int(r.choice([2, 15, 120]))
-        blocks = bool(r.random() < 0.4) and kind != "ragged"
+        blocks = bool(r.random() < 0.5) and kind != "ragged"
+        cross = blocks and bool(r.random() < 0.6)       # cross shards: the second residual copy on a shard by item block (may be refused: every rank alike)
         nb = int(r.choice([1, 3, 8]))
         iters = int(r.choice([1, 2, 3]))
         if kind == "ragged":
@@ -65,7 +66,7 @@ def worker(a):
             nb = 1
         m = "mcmc" if method == "als" else method
         D = max(tr.n_feat, te.n_feat) + (0 if m == "vb_online" else 1)
-        desc = f"case {n_done}: {kind} {method} N={N} K={K} k0={k0} k1={k1} tile={tile} seed={seed} U={U} I={I} blocks={blocks} nb={nb} iters={iters}"
+        desc = f"case {n_done}: {kind} {method} N={N} K={K} k0={k0} k1={k1} tile={tile} seed={seed} U={U} I={I} blocks={blocks} cross={cross} nb={nb} iters={iters}"
         n_done += 1
         if D == 0 or (m != "vb_online" and D == 1):
             continue
@@ -84,6 +85,11 @@ def worker(a):
             lo, hi = d.shard_bounds(tr.n_rows, rank, world)
             mine = np.arange(lo, hi)
         E.set_csc(sv.TRAIN, shard)
+        if cross:
+            try:
+                E.set_csc(sv.TRAIN_SECOND, d.shard_csc_by_second_block(to_csc(tr), rank, world, U)[0])
+            except sv.SvbfmError as ex:      # data that does not qualify (x != 1, vb_online, no stream schedule): the handle carries on without it
+                assert "TRAIN_SECOND" in str(ex), ex
         E.set_csc(sv.TEST, d.shard_csc(to_csc(te), rank, world))
         info = E.info()
         E.set_state(sv.host_init_state(42, D, K, 0.1, sv.METHODS[m]))

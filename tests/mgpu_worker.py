@@ -35,17 +35,23 @@ def main():
                                              ("ragged_vb", ragged(4000, 500, 60, seed=52), "vb", 3, 4),
                                              ("two_field_als", two_field(20000, 2000, 300, 200, seed=53), "mcmc", 3, 4),
                                              ("two_field_als_blocks", two_field(20000, 2000, 300, 200, seed=55), "mcmc", 3, 4),
+                                             # cross shards: first residual copy by user block, second copy by item block (records allgathered)
+                                             ("two_field_vb_cross", two_field(30000, 3000, 400, 300, seed=58), "vb", 4, 5),
+                                             ("two_field_als_cross", two_field(20000, 2000, 300, 200, seed=59), "mcmc", 3, 4),
                                              ("two_field_vbo", two_field(20000, 2000, 300, 200, seed=56), "vb_online", 3, 3)):
         uid = d.broadcast_unique_id(get_id, rank, device=torch.device("cuda", local))
         D = max(tr.n_feat, te.n_feat) + (0 if method == "vb_online" else 1)
         kw = dict(do_sample=False, do_multilevel=False) if method == "mcmc" else {}
         E = sv.Engine(method, D, K, 1, 1, float(tr.y.min()), float(tr.y.max()), device=local, seed=42, **kw)
         E.comm_init(uid, rank, world)
-        blocks = name.endswith("_blocks")       # cases sharded by blocks of the first field (users): no exchange for that field
+        cross = name.endswith("_cross")
+        blocks = name.endswith("_blocks") or cross       # cases sharded by blocks of the first field (users): no exchange for that field
         nu = 400 if "vb" in name else 300
         E.set_csc(sv.TRAIN, d.shard_csc_by_block(to_csc(tr), rank, world, nu)[0] if blocks else d.shard_csc(to_csc(tr), rank, world))
+        if cross:
+            E.set_csc(sv.TRAIN_SECOND, d.shard_csc_by_second_block(to_csc(tr), rank, world, nu)[0])
         E.set_csc(sv.TEST, d.shard_csc(to_csc(te), rank, world))
-        assert E.info()["exclusive_blocks"] == (1 if blocks else 0), (name, E.info())
+        assert E.info()["exclusive_blocks"] == (3 if cross else 1 if blocks else 0), (name, E.info())
         if name.startswith("two_field"):
             assert E.info()["fused_schedule"] & 1
         E.set_state(sv.host_init_state(42, D, K, 0.1, sv.METHODS[method]))

@@ -18,7 +18,7 @@ from helpers import make_learner, rel, to_csc, two_field
 
 pytestmark = pytest.mark.gpu
 VB_TOL = 1e-7
-CASES = [(0, 20000), (64, 20000), (256, 20002), (1024, 30001)]
+CASES = [(0, 20000), (64, 20000), (128, 20000), (256, 20002), (512, 20002), (1024, 30001)]
 
 
 def _emulated():
