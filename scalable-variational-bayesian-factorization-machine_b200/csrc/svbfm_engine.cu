@@ -182,22 +182,15 @@ static int exchange_blocks_of(Engine* E, const std::vector<uint32_t>& blk) {
 static int exchange_blocks(Engine* E) {
     if (!E->excl0) return 0;
     ProfScope pc(E, 11);
-    if (int rc = exchange_blocks_of(E, E->blk)) return rc;
-    if (E->xs) return exchange_blocks_of(E, E->blk1);      // cross shards: the second field's columns are updated by their owners only, too
-    return 0;
+    if (E->xs) return 0;      // cross shards: every rank already followed every column's update (k_records_remote)
+    return exchange_blocks_of(E, E->blk);
 }
 
-// cross shards: the records of the columns a rank has just finalized travel to every rank: slot-contiguous, equally sized blocks
-// of cpack, one in-place allgather (send block = this rank's part of the receive buffer)
-static int exchange_records(Engine* E, int run) {
-    if (!E->xs) return 0;
-    ProfScope pc(E, 10);
-    const size_t per = (size_t)E->slot_max[run] * 4;                       // doubles per rank
-    double* base = reinterpret_cast<double*>(E->d_cpack + E->slot_base[run]);
-    int r = g_nccl.AllGather(base + per * (size_t)E->rank, base, per, 8 /*ncclDouble*/, E->nccl_comm, E->stream);
-    if (r != 0) return fail(E, SVBFM_ERR_NCCL, std::string("ncclAllGather (records): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
-    return 0;
-}
+// cross shards: what a rank has just finalized travels to every rank: {new mean, new var} of its block of columns, 16 bytes per
+// column in slot order (equally sized, padded blocks: one in-place allgather, send block = this rank's part of the receive buffer).
+// Every rank then forms the other blocks' records itself and updates its parameter table (k_records_remote).
+struct RecPlan;
+static int exchange_records(Engine* E, int run, const Run& r, double2* pf, const RecPlan* rp, bool mcmc);
 
 // stream schedule: what a finalize has to leave behind for the passes that follow (kernels.cuh FinalizeArgs)
 struct RecPlan {
@@ -264,6 +257,7 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
     fa.span = sp; fa.ab = use_ab ? E->d_ab : nullptr;
     if (rp) { fa.cpack = E->d_cpack; fa.opack = E->d_opack; fa.rec_mode = rp->rec_mode; fa.p_next = rp->p_next; fa.p_prev = rp->p_prev; }
     fa.rec_slot = E->rec_rank ? E->d_rec_slot : nullptr;
+    if (rp && rp->run >= 0 && E->xs) { fa.stage = E->d_xstage; fa.stage_base = E->slot_base[rp->run]; }
     if (rp && rp->run >= 0 && E->bv.on) fa.gcnt = E->bv.gcnt[rp->run];
     if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V) {
         fa.nat = IS_V ? E->d_nat_v + (size_t)f * E->D : E->d_nat_w;
@@ -276,8 +270,27 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
         if (ncols) k_finalize<KIND><<<nblk(ncols), 256, 0, st>>>(fa);
     }
     LAUNCHED(E);
-    if (rp && rp->run >= 0 && E->xs) if (int rc = exchange_records(E, rp->run)) return rc;
+    if (rp && rp->run >= 0 && E->xs) if (int rc = exchange_records(E, rp->run, r, pf, rp, KIND == KIND_MC_W || KIND == KIND_MC_V)) return rc;
     return check_launch(E, "combine_finalize");
+}
+
+static int exchange_records(Engine* E, int run, const Run& r, double2* pf, const RecPlan* rp, bool mcmc) {
+    cudaStream_t st = E->stream;
+    {
+        ProfScope pc(E, 10);
+        const size_t per = (size_t)E->slot_max[run] * 2;                       // doubles per rank
+        double* base = reinterpret_cast<double*>(E->d_xstage);
+        int rc = g_nccl.AllGather(base + per * (size_t)E->rank, base, per, 8 /*ncclDouble*/, E->nccl_comm, st);
+        if (rc != 0) return fail(E, SVBFM_ERR_NCCL, std::string("ncclAllGather (columns): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    }
+    RemoteRecArgs a{};
+    const std::vector<uint32_t>& blk = run ? E->blk1 : E->blk;
+    a.c0 = r.col_begin; a.c1 = r.col_end; a.own0 = blk[E->rank]; a.own1 = blk[E->rank + 1];
+    a.rec_slot = E->d_rec_slot; a.stage = E->d_xstage; a.stage_base = E->slot_base[run];
+    a.pf = pf; a.p_next = rp->p_next; a.p_prev = rp->p_prev; a.rec_mode = rp->rec_mode; a.mcmc = mcmc ? 1 : 0; a.cpack = E->d_cpack;
+    const uint32_t nc = r.col_end - r.col_begin;
+    if (nc) { k_records_remote<<<nblk(nc), 256, 0, st>>>(a); LAUNCHED(E); }
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------- one run sweep
@@ -850,7 +863,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_gcnt[0], E->d_vbo_gcnt[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_xstage, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_gcnt[0], E->d_vbo_gcnt[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) sv_free(p);
     cudaStreamSynchronize(E->stream);
     if (E->copy_stream) { cudaStreamSynchronize(E->copy_stream); cudaStreamDestroy(E->copy_stream); }

@@ -275,7 +275,13 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
                  const float* x, const float* target) {
     cudaStream_t st = E->stream;
     free_split(E, S);
-    if (is_train) free_second(E);
+    if (is_train) {
+        free_second(E);
+        // per-case / per-entry buffers of vb_online are sized by the train split: a new split (svbfm_reset + svbfm_set_csc on a
+        // long-lived handle) must not inherit the old ones
+        sv_free(E->d_rbatch); sv_free(E->d_cbatch); sv_free(E->d_cnt_col);
+        E->d_rbatch = nullptr; E->d_cbatch = nullptr; E->d_cnt_col = nullptr;
+    }
     // temporaries of this function: whatever is still owned when it returns (early, on an error) goes back to the block cache
     struct Temps {
         std::vector<void**> slots;
@@ -298,12 +304,33 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         fprintf(stderr, "[svbfm ingest %s] %-28s %8.2f ms\n", is_train ? "train" : "test", what, std::chrono::duration<double, std::milli>(now - t_last).count());
         t_last = now;
     };
-    if (ncols > E->D) return fail(E, SVBFM_ERR_ARG, "set_csc: num_cols exceeds num_attribute");
-    if (colptr[0] != 0) return fail(E, SVBFM_ERR_ARG, "set_csc: colptr[0] != 0");
-    for (uint32_t j = 0; j < ncols; j++)
-        if (colptr[j + 1] < colptr[j]) return fail(E, SVBFM_ERR_ARG, "set_csc: colptr not monotone");
+    // Several ranks: a rank that rejects its shard must not leave the others waiting in the collectives below, and the allreduce
+    // counts of the train ingest follow num_cols: the ranks first agree on {any rank failed, min and max of num_cols} (agree()).
+    auto agree = [&](const std::string& why) -> int {
+        if (E->world <= 1) return why.empty() ? 0 : fail(E, SVBFM_ERR_ARG, why);
+        uint32_t h[3] = {why.empty() ? 0u : 1u, ncols, ~ncols};           // max-reduced: [1] = max num_cols, ~[2] = min num_cols
+        uint32_t* d = nullptr;
+        if (sv_malloc((void**)&d, 12) != cudaSuccess) return fail(E, SVBFM_ERR_OOM, "cudaMalloc");
+        cudaMemcpyAsync(d, h, 12, cudaMemcpyHostToDevice, st);
+        int rc = allreduce(E, d, 3, 3 /*ncclUint32*/, 2 /*ncclMax*/);
+        if (!rc) { cudaMemcpyAsync(h, d, 12, cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st); }
+        sv_free(d);
+        if (rc) return rc;
+        if (!why.empty()) return fail(E, SVBFM_ERR_ARG, why);
+        if (h[0]) return fail(E, SVBFM_ERR_ARG, "set_csc: another rank rejected its shard");
+        if (is_train && h[1] != ~h[2]) return fail(E, SVBFM_ERR_ARG, "set_csc: num_cols of the train split differs between the ranks");
+        return 0;
+    };
+    std::string why;
+    if (ncols > E->D) why = "set_csc: num_cols exceeds num_attribute";
+    else if (colptr[0] != 0) why = "set_csc: colptr[0] != 0";
+    else {
+        for (uint32_t j = 0; j < ncols && why.empty(); j++)
+            if (colptr[j + 1] < colptr[j]) why = "set_csc: colptr not monotone";
+        if (why.empty() && colptr[ncols] >= (1ull << 32)) why = "set_csc: more than 2^32-1 entries per rank are not supported";
+    }
+    if (int rc = agree(why)) return rc;
     uint64_t nnz = colptr[ncols];
-    if (nnz >= (1ull << 32)) return fail(E, SVBFM_ERR_ARG, "set_csc: more than 2^32-1 entries per rank are not supported");
     S.n = n; S.n_cols = ncols; S.nnz = nnz;
     // mcmc also draws the attributes that never occur in train (reference fm_learn_mcmc.h:449-457, 568-577):
     // they become empty trailing columns of the last run.
@@ -347,10 +374,10 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     uint32_t h_flags[8];
     SV_CUDA(E, cudaMemcpyAsync(h_flags + 1, d_flags + 1, 4, cudaMemcpyDeviceToHost, st));
     SV_CUDA(E, cudaStreamSynchronize(st));
-    if (h_flags[1]) {
+    if (int rc = agree(h_flags[1] ? "set_csc: case id out of range" : "")) {
         cudaStreamSynchronize(cs);
         drop(d_x); drop(d_flags); drop(d_colof); drop(d_idx);
-        return fail(E, SVBFM_ERR_ARG, "set_csc: case id out of range");
+        return rc;
     }
     mark("H2D of the case ids + col_of_entry");
     if (int r = sort_pairs(E, S.crow, d_idx, nnz, std::max<uint32_t>(n, 1), &d_skeys, &d_sidx)) { cudaStreamSynchronize(cs); return r; }
@@ -389,9 +416,10 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     mark("  H2D of values and targets (overlapped) + row scan");
     SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
     SV_CUDA(E, cudaStreamSynchronize(st));
-    if (h_flags[2]) {
+    if (int rc = agree(h_flags[2] ? "set_csc: a feature id occurs twice in one case; not supported" : "")) {
         drop(d_x); drop(d_flags); drop(d_rowptr); drop(d_rcol); drop(d_rval); drop(d_need);
-        return fail(E, SVBFM_ERR_DATA, "set_csc: a feature id occurs twice in one case; not supported");
+        if (h_flags[2]) return fail(E, SVBFM_ERR_DATA, "set_csc: a feature id occurs twice in one case; not supported");
+        return rc;
     }
     bool uniform = (n > 0) && (h_flags[3] == 0);
     uint32_t F = uniform ? (uint32_t)(nnz / n) : 0;
@@ -732,20 +760,30 @@ static __global__ void k_sec_users(const uint32_t* __restrict__ case_id, const u
     if (c >= n) { flags[1] = 1; return; }
     if (atomicExch(&user_of_case[c], colof[p]) != 0xffffffffu) flags[2] = 1;      // a case twice in the first field
 }
-// second-field entries (the shard's entry order): other column, target, {user, item} pair of every entry
-static __global__ void k_sec_entries(const uint32_t* __restrict__ case_id, const uint32_t* __restrict__ colof, uint32_t n, const uint32_t* __restrict__ user_of_case,
-                                     uint32_t* __restrict__ seen, const float* __restrict__ target, uint32_t* __restrict__ oc, uint32_t* __restrict__ rcol,
-                                     float* __restrict__ y, uint32_t* flags) {
+// second-field entries in the caller's order: first-field column of every entry (sort key) + the checks
+static __global__ void k_sec_keys(const uint32_t* __restrict__ case_id, uint32_t n, const uint32_t* __restrict__ user_of_case, uint32_t* __restrict__ seen,
+                                  uint32_t c0, uint32_t* __restrict__ key, uint32_t* __restrict__ val, uint32_t* flags) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     uint32_t c = case_id[q];
+    key[q] = 0; val[q] = q;
     if (c >= n) { flags[1] = 1; return; }
     if (atomicExch(&seen[c], 1u) != 0u) flags[2] = 1;                               // a case twice in the second field
     uint32_t u = user_of_case[c];
-    if (u == 0xffffffffu) { flags[2] = 1; u = 0; }
-    oc[q] = u;
-    rcol[2 * (size_t)q] = u; rcol[2 * (size_t)q + 1] = colof[q];
-    y[q] = target[c];
+    if (u == 0xffffffffu) { flags[2] = 1; u = c0; }
+    key[q] = u - c0;
+}
+// the shard's entry order: entry p is the caller's entry perm[p]: other column, target, {user, item} pair
+static __global__ void k_sec_entries(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ case_id, const uint32_t* __restrict__ colof, uint32_t n,
+                                     const uint32_t* __restrict__ user_of_case, const float* __restrict__ target, uint32_t* __restrict__ oc,
+                                     uint32_t* __restrict__ rcol, float* __restrict__ y) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t q = perm[p], c = case_id[q];
+    const uint32_t u = user_of_case[c];
+    oc[p] = u;
+    rcol[2 * (size_t)p] = u; rcol[2 * (size_t)p + 1] = colof[q];
+    y[p] = target[c];
 }
 
 int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr, const uint32_t* case_id, const float* x, const float* target) {
@@ -780,7 +818,11 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
     uint64_t* d_cp = nullptr;
     float *d_x = nullptr, *d_t = nullptr;
     struct Temps { std::vector<void**> v; ~Temps() { for (void** p : v) { sv_free(*p); *p = nullptr; } } } temps;
-    for (void** p : {(void**)&d_flags, (void**)&d_case, (void**)&d_colof, (void**)&d_user, (void**)&d_seen, (void**)&d_cp, (void**)&d_x, (void**)&d_t}) temps.v.push_back(p);
+    uint32_t *d_k = nullptr, *d_v = nullptr, *d_k1 = nullptr, *d_v1 = nullptr, *d_k2 = nullptr, *d_v2 = nullptr;      // sort scratch
+    uint32_t* d_new = nullptr;
+    double* d_tot = nullptr;
+    for (void** p : {(void**)&d_flags, (void**)&d_case, (void**)&d_colof, (void**)&d_user, (void**)&d_seen, (void**)&d_cp, (void**)&d_x, (void**)&d_t,
+                     (void**)&d_k, (void**)&d_v, (void**)&d_k1, (void**)&d_v1, (void**)&d_k2, (void**)&d_v2, (void**)&d_new, (void**)&d_tot}) temps.v.push_back(p);
     SV_CUDA(E, sv_malloc((void**)&d_flags, 8 * 4));
     SV_CUDA(E, cudaMemsetAsync(d_flags, 0, 8 * 4, st));
     uint32_t h_flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -805,12 +847,25 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
         if (dev_alloc(E, &E->sec.rcol, (size_t)n * 2)) return SVBFM_ERR_OOM;
         if (dev_alloc(E, &E->sec.y, n)) return SVBFM_ERR_OOM;
         k_sec_users<<<nblk(n), 256, 0, st>>>(d_case, d_colof, n, d_user, d_flags);
-        k_sec_entries<<<nblk(n), 256, 0, st>>>(d_case + off1, d_colof + off1, n, d_user, d_seen, d_t, E->sec.oc, E->sec.rcol, E->sec.y, d_flags);
+        // The copy's entry order: by second-field column (as handed over), inside a column ascending by FIRST-field column, so that
+        // neighbouring lanes of the second field's pass gather neighbouring records (the caller's case order inside a column is
+        // arbitrary; the single-GPU layout gets the same from its case re-ordering). Two stable sorts: by first-field column, then
+        // by second-field column.
+        SV_CUDA(E, sv_malloc((void**)&d_k, (size_t)n * 4));
+        SV_CUDA(E, sv_malloc((void**)&d_v, (size_t)n * 4));
+        k_sec_keys<<<nblk(n), 256, 0, st>>>(d_case + off1, n, d_user, d_seen, r0.col_begin, d_k, d_v, d_flags);
         SV_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 8 * 4, cudaMemcpyDeviceToHost, st));
         SV_CUDA(E, cudaStreamSynchronize(st));
         if (h_flags[0]) why = "x != 1";
         else if (h_flags[1]) why = "case id out of range";
         else if (h_flags[2]) why = "every case needs exactly one entry in each of the two fields";
+        if (why.empty()) {
+            if (int rc = sort_pairs(E, d_k, d_v, n, std::max<uint32_t>(r0.col_end - r0.col_begin, 1), &d_k1, &d_v1)) return rc;
+            k_gather_u32<<<nblk(n), 256, 0, st>>>(d_colof + off1, d_v1, n, d_k);          // second-field column of the entries in that order
+            if (int rc = sort_pairs(E, d_k, d_v1, n, std::max<uint32_t>(ncols, 1), &d_k2, &d_v2)) return rc;
+            k_sec_entries<<<nblk(n), 256, 0, st>>>(d_v2, d_case + off1, d_colof + off1, n, d_user, d_t, E->sec.oc, E->sec.rcol, E->sec.y);
+            SV_CUDA(E, cudaStreamSynchronize(st));
+        }
     }
     // entry pointers of the second field's columns inside the shard, indexed by global column id
     E->sec.n = why.empty() ? n : 0;
@@ -828,8 +883,7 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
     }
     bool excl1 = false;
     if (int rc = detect_blocks(E, r1, E->sec.h_colptr, E->blk1, excl1)) return rc;
-    double tot = (double)n, *d_tot = nullptr;
-    temps.v.push_back((void**)&d_tot);
+    double tot = (double)n;
     SV_CUDA(E, sv_malloc((void**)&d_tot, 8));
     SV_CUDA(E, cudaMemcpyAsync(d_tot, &tot, 8, cudaMemcpyHostToDevice, st));
     if (int rc = allreduce(E, d_tot, 1, 8 /*ncclDouble*/, 0 /*ncclSum*/)) return rc;
@@ -859,8 +913,6 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
     E->slot_base[1] = (uint32_t)E->world * mx0; E->slot_max[1] = mx1;
     const size_t total_slots = (size_t)E->world * ((size_t)mx0 + mx1);
     if (total_slots >= (1ull << 32)) { free_second(E); return fail(E, SVBFM_ERR_ARG, "set_csc(TRAIN_SECOND): too many record slots"); }
-    uint32_t* d_new = nullptr;
-    temps.v.push_back((void**)&d_new);
     SV_CUDA(E, sv_malloc((void**)&d_new, (size_t)E->D * 4));
     SV_CUDA(E, cudaMemsetAsync(d_new, 0, (size_t)E->D * 4, st));
     const uint32_t nc0 = r0.col_end - r0.col_begin, nc1 = r1.col_end - r1.col_begin;
@@ -870,13 +922,13 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
     if (ranked) {
         const uint32_t c0 = E->blk1[E->rank], nb = E->blk1[E->rank + 1] - c0;
         if (nb) {
-            uint32_t *d_k = nullptr, *d_v = nullptr, *d_ks = nullptr, *d_vs = nullptr;
-            SV_CUDA(E, sv_malloc((void**)&d_k, (size_t)nb * 4));
-            SV_CUDA(E, sv_malloc((void**)&d_v, (size_t)nb * 4));
-            k_slot_keys<<<nblk(nb), 256, 0, st>>>(E->sec.colptr, c0, nb, d_k, d_v);
-            int rc = sort_pairs(E, d_k, d_v, nb, 1ull << 32, &d_ks, &d_vs);
+            uint32_t *d_sk = nullptr, *d_sv = nullptr, *d_ks = nullptr, *d_vs = nullptr;
+            SV_CUDA(E, sv_malloc((void**)&d_sk, (size_t)nb * 4));
+            SV_CUDA(E, sv_malloc((void**)&d_sv, (size_t)nb * 4));
+            k_slot_keys<<<nblk(nb), 256, 0, st>>>(E->sec.colptr, c0, nb, d_sk, d_sv);
+            int rc = sort_pairs(E, d_sk, d_sv, nb, 1ull << 32, &d_ks, &d_vs);
             if (!rc) { k_slot_scatter<<<nblk(nb), 256, 0, st>>>(d_vs, E->slot_base[1] + (uint32_t)E->rank * mx1, nb, d_new); cudaStreamSynchronize(st); }
-            sv_free(d_k); sv_free(d_v); sv_free(d_ks); sv_free(d_vs);
+            sv_free(d_sk); sv_free(d_sv); sv_free(d_ks); sv_free(d_vs);
             if (rc) return rc;
         }
         if (int rc = allreduce(E, d_new + r1.col_begin, nc1, 3 /*ncclUint32*/, 0 /*ncclSum*/)) return rc;
@@ -900,6 +952,14 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
         sv_free(E->d_cpack); E->d_cpack = nullptr;
         if (sv_malloc((void**)&E->d_cpack, total_slots * 32 /* sizeof(ColPack) */) != cudaSuccess) return fail(E, SVBFM_ERR_OOM, "cudaMalloc: record slots");
         E->cpack_cap = total_slots;
+    }
+    {
+        const size_t need = (size_t)E->world * std::max(mx0, mx1);
+        if (E->xstage_cap < need) {
+            sv_free(E->d_xstage); E->d_xstage = nullptr;
+            if (dev_alloc(E, &E->d_xstage, need)) return SVBFM_ERR_OOM;
+            E->xstage_cap = need;
+        }
     }
     // ---- tiles of the second side on the new shard (the first side keeps its own), second residual copy, tile sums
     const uint64_t TS = 1ull << E->ts_shift;

@@ -236,6 +236,8 @@ struct Engine {
     } sec;
     uint32_t slot_base[2] = {0, 0}, slot_max[2] = {0, 0};   // record slots of field f: [slot_base[f] + r * slot_max[f], + block size) for rank r
     size_t cpack_cap = 0;             // records allocated in d_cpack
+    double2* d_xstage = nullptr;      // [world * max(slot_max)] {new mean, new var} of the columns finalized in this step, slot order: the allgather buffer
+    size_t xstage_cap = 0;
     // what a pass over side 0 / 1 of the stream schedule reads (set_side_views)
     struct SideView {
         const uint64_t* colptr = nullptr;  // indexed by global column id

@@ -352,6 +352,8 @@ struct FinalizeArgs {
     const double2* p_next;       // parameters of the step that follows ([D]; null after the last one)
     const double2* p_prev;       // parameters of the step before ([D]; null at the first one)
     double* dT;                  // [D]
+    double2* stage;              // cross shards: {new mean, new var} of the column at stage[slot - stage_base]: what travels to the other ranks
+    uint32_t stage_base;
     uint64_t seed; int do_sample;
     // vb_online
     double2* nat;                // [D] natural params of this factor
@@ -367,6 +369,7 @@ __device__ __forceinline__ void write_records(const FinalizeArgs& a, uint32_t j,
     if (!a.rec_mode) return;
     double2 N = a.p_next ? a.p_next[j] : make_double2(0.0, 0.0);
     const uint32_t sj = a.rec_slot ? a.rec_slot[j] : j;
+    if (a.stage) a.stage[sj - a.stage_base] = make_double2(new_mean, new_var);
     if (a.rec_mode == 1) {
         a.cpack[sj] = ColPack{new_mean, new_var, dlt, a.p_prev ? a.p_prev[j].x : 0.0};
         a.opack[j] = OwnPack{N.x, new_mean, dlt, 0.0};
@@ -1720,6 +1723,32 @@ __global__ void k_pack_init(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, 
 __global__ void k_pack_h4(uint32_t c0, uint32_t c1, const double2* __restrict__ p, ColPack* __restrict__ cpack) {
     uint32_t j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (j < c1) cpack[j].h4 = p[j].x;
+}
+// Cross shards: the columns of a field that OTHER ranks have just updated. Their new {mean, var} arrived in `stage` (slot order);
+// this rank still holds the old values, so it forms what the owner's k_finalize formed -- delta from the same two operands, the
+// record of the column for the passes that follow (write_records) -- and brings its parameter table up to date. The tables stay
+// complete and bit-identical on every rank without a block exchange at the end of the iteration.
+struct RemoteRecArgs {
+    uint32_t c0, c1;             // columns of the field
+    uint32_t own0, own1;         // this rank's block (already finalized here)
+    const uint32_t* rec_slot;
+    const double2* stage; uint32_t stage_base;
+    double2* pf;                 // parameters of this step ([D])
+    const double2* p_next;
+    const double2* p_prev;
+    int rec_mode, mcmc;
+    ColPack* cpack;
+};
+__global__ void __launch_bounds__(256) k_records_remote(RemoteRecArgs a) {
+    uint32_t j = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.c1 || (j >= a.own0 && j < a.own1)) return;
+    const uint32_t sj = a.rec_slot[j];
+    const double2 nw = a.stage[sj - a.stage_base], old = a.pf[j];
+    const double dlt = a.mcmc ? (nw.x - old.x) : (old.x - nw.x);      // k_finalize: skip <=> the mean did not move <=> 0
+    a.pf[j] = nw;
+    const double2 N = a.p_next ? a.p_next[j] : make_double2(0.0, 0.0);
+    if (a.rec_mode == 1) a.cpack[sj] = ColPack{nw.x, nw.y, dlt, a.p_prev ? a.p_prev[j].x : 0.0};
+    else a.cpack[sj] = ColPack{N.x, N.y, dlt, old.x};
 }
 // the same in slot space (cross shards): after the first field's last finalize the mean of a record is that final mean
 __global__ void k_pack_h4_self(uint32_t s0, uint32_t s1, ColPack* __restrict__ cpack) {

@@ -4,6 +4,7 @@
 // the host around the sweep: the libc-rand() initial state, the per-iteration files in the CWD
 // (test_rmse_<k0k1K>_<method>, free_energy_<k0k1K>_vb), the "#Iter=" lines and the -rlog fields.
 #pragma once
+#include <unistd.h>
 #include <sys/resource.h>
 #include <cmath>
 #include <ctime>
@@ -125,7 +126,11 @@ protected:
         c.do_sample = do_sample; c.do_multilevel = do_multilevel; c.seed = (uint64_t)seed; c.reg0 = fm->reg0; c.regw = fm->regw; c.regv = fm->regv;
         int rc = svbfm_create(&h_, &c);
         if (rc != 0) throw std::string("svbfm_create: ") + svbfm_last_error(nullptr);
-        if (shard.world > 1) ck(svbfm_comm_init(h_, shard.comm_id, shard.rank, shard.world), "svbfm_comm_init");
+        if (shard.world > 1) {
+            ck(svbfm_comm_init(h_, shard.comm_id, shard.rank, shard.world), "svbfm_comm_init");
+            // the communicator stands on every rank: the id record must not outlive the launch (libfm.cpp exchange_comm_id)
+            if (shard.rank == 0) if (const char* path = getenv("SVBFM_COMM_FILE")) unlink(path);
+        }
         ck(svbfm_set_groups(h_, meta->attr_group.data(), meta->num_attr_groups), "svbfm_set_groups");
         push(SVBFM_TRAIN, train);
         push(SVBFM_TEST, test);

@@ -7,9 +7,12 @@
 //   * v_file.txt (fm_model.h:98) is only written when SVBFM_WRITE_V_FILE=1
 //   * multi-GPU: one process per GPU, RANK / WORLD_SIZE / LOCAL_RANK from the environment, id exchange through
 //     the file named by SVBFM_COMM_FILE
+#include <sys/stat.h>
 #include <unistd.h>
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
+#include <fstream>
 #include <ctime>
 #include <iostream>
 #include "cmdline.h"
@@ -27,24 +30,53 @@ static void find_max_feature(DataSet& d, const std::string& file) {
     for (float v : t.target) { d.min_target = std::min(v, d.min_target); d.max_target = std::max(v, d.max_target); }
 }
 
+// The NCCL unique id travels from rank 0 to the others through a file every rank can read. A file left behind by an earlier launch
+// must not be taken for this one's: the record carries a nonce every rank of ONE launch derives alike (SVBFM_COMM_NONCE, else
+// MASTER_PORT / TORCHELASTIC_RUN_ID of the launcher and the parent's pid), rank 0 removes any old file before it asks for the id,
+// records older than two minutes at the start of this process are ignored, and rank 0 removes the file once the communicator
+// stands (svbfm_comm_init is collective: every rank has read the record by then; fm_learn_cuda.h open_engine).
+static uint64_t launch_nonce() {
+    std::string key;
+    for (const char* name : {"SVBFM_COMM_NONCE", "TORCHELASTIC_RUN_ID", "MASTER_PORT", "SLURM_JOB_ID"})
+        if (const char* v = getenv(name)) { key += name; key += '='; key += v; key += ';'; }
+    key += "ppid=" + std::to_string((long)getppid());
+    uint64_t h = 1469598103934665603ull;              // FNV-1a
+    for (unsigned char c : key) { h ^= c; h *= 1099511628211ull; }
+    return h;
+}
+struct CommRecord { char magic[8]; uint64_t nonce; uint8_t id[SVBFM_COMM_ID_BYTES]; };
 static void exchange_comm_id(ShardInfo& sh) {
     const char* path = getenv("SVBFM_COMM_FILE");
     if (!path) throw std::string("WORLD_SIZE > 1 needs SVBFM_COMM_FILE (a path every rank can read)");
+    const time_t started = time(nullptr);
+    const uint64_t nonce = launch_nonce();
     std::string tmp = std::string(path) + ".tmp";
     if (sh.rank == 0) {
+        unlink(path);
         if (svbfm_comm_get_unique_id(sh.comm_id) != 0) throw std::string("svbfm_comm_get_unique_id: ") + svbfm_last_error(nullptr);
-        { std::ofstream f(tmp.c_str(), std::ios::binary); f.write(reinterpret_cast<const char*>(sh.comm_id), SVBFM_COMM_ID_BYTES); }
+        CommRecord rec;
+        memcpy(rec.magic, "SVBFMID1", 8); rec.nonce = nonce; memcpy(rec.id, sh.comm_id, SVBFM_COMM_ID_BYTES);
+        { std::ofstream f(tmp.c_str(), std::ios::binary); f.write(reinterpret_cast<const char*>(&rec), sizeof(rec)); }
         rename(tmp.c_str(), path);
     } else {
-        for (int tries = 0; tries < 6000; tries++) {
-            std::ifstream f(path, std::ios::binary);
-            if (f.is_open()) { f.read(reinterpret_cast<char*>(sh.comm_id), SVBFM_COMM_ID_BYTES); if (f.gcount() == SVBFM_COMM_ID_BYTES) return; }
+        for (int tries = 0; tries < 12000; tries++) {
+            struct stat st;
+            if (stat(path, &st) == 0 && st.st_mtime + 120 >= started) {
+                std::ifstream f(path, std::ios::binary);
+                CommRecord rec;
+                if (f.is_open()) {
+                    f.read(reinterpret_cast<char*>(&rec), sizeof(rec));
+                    if (f.gcount() == (std::streamsize)sizeof(rec) && memcmp(rec.magic, "SVBFMID1", 8) == 0 && rec.nonce == nonce) {
+                        memcpy(sh.comm_id, rec.id, SVBFM_COMM_ID_BYTES);
+                        return;
+                    }
+                }
+            }
             usleep(10000);
         }
-        throw std::string("timed out waiting for ") + path;
+        throw std::string("timed out waiting for this launch's record in ") + path;
     }
 }
-
 int main(int argc, char** argv) {
     try {
         CmdLine cmd(argc, argv);

@@ -310,6 +310,33 @@ def test_reset_reuses_handle(built):
     assert h1 == h2
 
 
+def test_reset_onto_a_larger_split_vb_online(built):
+    """A long-lived vb_online handle that is reset onto a LARGER train split: the per-case / per-entry batch buffers follow the new
+    split (they used to keep the first split's size). Same statistics as a fresh handle on the larger split, bit for bit."""
+    small, te_s = two_field(3000, 300, 120, 90, seed=83)
+    big, te = two_field(12000, 800, 120, 90, seed=84)
+    D = max(big.n_feat, te.n_feat, small.n_feat, te_s.n_feat)
+    nb = 4
+
+    def epochs(E, tr, k):
+        batch = (np.random.default_rng(5).permutation(tr.n_rows) % nb).astype(np.uint32)
+        return [(s.test_rmse, s.free_energy) for s in (E.vb_online_epoch(batch, nb) for _ in range(k))]
+
+    state = sv.host_init_state(42, D, 3, 0.1, sv.VB_ONLINE)
+    E = sv.Engine("vb_online", D, 3, 1, 1, 1.0, 5.0, seed=42)
+    E.set_csc(sv.TRAIN, to_csc(small)); E.set_csc(sv.TEST, to_csc(te_s)); E.set_state(state); E.begin()
+    epochs(E, small, 1)
+    E.reset()
+    E.set_csc(sv.TRAIN, to_csc(big)); E.set_csc(sv.TEST, to_csc(te)); E.set_state(state); E.begin()
+    again = epochs(E, big, 2)
+    E.close()
+    F = sv.Engine("vb_online", D, 3, 1, 1, 1.0, 5.0, seed=42)
+    F.set_csc(sv.TRAIN, to_csc(big)); F.set_csc(sv.TEST, to_csc(te)); F.set_state(state); F.begin()
+    fresh = epochs(F, big, 2)
+    F.close()
+    assert again == fresh
+
+
 @pytest.mark.parametrize("method", ["vb", "mcmc", "vb_online"])
 def test_degenerate_splits(built, method):
     """An empty test split (the reference divides by zero cases and prints `Test=nan`, vbs.h:261-279 / mcmcs.h:226-233), a single
