@@ -155,6 +155,10 @@ int svbfm_predict(svbfm_t* h, int32_t split, double* out /*[num_cases]*/);
 int svbfm_get_residuals(svbfm_t* h, double* e /*[num_cases of train]*/);
 /* sum_i T_i (vb.h:207-312 gives T_i; only its sum enters alpha and the free energy) */
 int svbfm_get_sum_t(svbfm_t* h, double* sum_t);
+/* checkpoint restore (after svbfm_begin, one GPU): the cached residuals in caller case order and sum_i T_i as svbfm_get_residuals /
+ * svbfm_get_sum_t handed them out. Together with svbfm_set_state / svbfm_set_hyper a vb run continues bit for bit where the saved one
+ * stopped (the CLI's -save_model / -load_model). No reference counterpart: the fork has no model files. */
+int svbfm_set_residuals(svbfm_t* h, const double* e /*[num_cases of train]*/, double sum_t);
 /* stream schedule self-check: max |e2[p] - e[case of p]| between the two residual copies (0.0 expected: the copies
  * are updated with identical arithmetic); 0.0 when the schedule is not in use */
 int svbfm_copies_max_diff(svbfm_t* h, double* max_abs_diff);

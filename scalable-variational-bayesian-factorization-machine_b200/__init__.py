@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "svbfm_create", "svbfm_destroy", "svbfm_last_error", "svbfm_abi_version", "svbfm_comm_get_unique_id",
     "svbfm_comm_init", "svbfm_set_groups", "svbfm_set_csc", "svbfm_set_state", "svbfm_get_state",
     "svbfm_get_hyper", "svbfm_set_hyper", "svbfm_begin", "svbfm_vb_sweep", "svbfm_mcmc_sweep",
-    "svbfm_vb_online_epoch", "svbfm_run", "svbfm_reset", "svbfm_predict", "svbfm_get_residuals", "svbfm_get_sum_t", "svbfm_copies_max_diff",
+    "svbfm_vb_online_epoch", "svbfm_run", "svbfm_reset", "svbfm_predict", "svbfm_get_residuals", "svbfm_get_sum_t", "svbfm_set_residuals", "svbfm_copies_max_diff",
     "svbfm_get_info", "svbfm_set_stream", "svbfm_set_profile", "svbfm_get_profile", "svbfm_host_init_state", "svbfm_host_random_shuffle",
 ]
 
@@ -96,6 +96,7 @@ def lib():
         L.svbfm_predict.argtypes = [vp, C.c_int32, vp]
         L.svbfm_get_residuals.argtypes = [vp, vp]
         L.svbfm_get_sum_t.argtypes = [vp, C.POINTER(C.c_double)]
+        L.svbfm_set_residuals.argtypes = [vp, vp, C.c_double]
         L.svbfm_copies_max_diff.argtypes = [vp, C.POINTER(C.c_double)]
         L.svbfm_get_info.argtypes = [vp, C.POINTER(Info)]
         L.svbfm_set_stream.argtypes = [vp, vp]
@@ -248,6 +249,15 @@ class Engine:
         e = np.zeros(self.n_train)
         self._ck(lib().svbfm_get_residuals(self.h, _p(e)), "svbfm_get_residuals")
         return e
+
+    def set_residuals(self, e, sum_t):
+        e = np.ascontiguousarray(e, dtype=np.float64)
+        self._ck(lib().svbfm_set_residuals(self.h, _p(e), float(sum_t)), "svbfm_set_residuals")
+
+    def set_hyper(self, alpha, sigma_0, sigma_w=None, sigma_v=None):
+        sw = np.ascontiguousarray(sigma_w, dtype=np.float64) if sigma_w is not None else None
+        sv_ = np.ascontiguousarray(sigma_v, dtype=np.float64) if sigma_v is not None else None
+        self._ck(lib().svbfm_set_hyper(self.h, float(alpha), float(sigma_0), _p(sw), _p(sv_)), "svbfm_set_hyper")
 
     def get_sum_t(self):
         v = C.c_double()

@@ -1322,6 +1322,24 @@ int svbfm_get_residuals(svbfm_t* h, double* e) {
     return check_launch(E, "get_residuals");
 }
 
+int svbfm_set_residuals(svbfm_t* h, const double* e, double sum_t) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E || !e) return fail(E, SVBFM_ERR_ARG, "svbfm_set_residuals: null argument");
+    if (!E->begun || !E->d_e) return fail(E, SVBFM_ERR_ARG, "svbfm_set_residuals: svbfm_begin must be called first");
+    if (E->world > 1) return fail(E, SVBFM_ERR_ARG, "svbfm_set_residuals: one GPU only");
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    const uint32_t n = E->tr.n;
+    double* tmp = nullptr;
+    SV_CUDA(E, sv_malloc((void**)&tmp, std::max<size_t>(n, 1) * 8));
+    SV_CUDA(E, cudaMemcpyAsync(tmp, e, (size_t)n * 8, cudaMemcpyHostToDevice, E->stream));
+    if (n) { k_permute<<<nblk(n), 256, 0, E->stream>>>(tmp, E->tr.perm, n, E->d_e); LAUNCHED(E); }
+    if (E->cfg.method != SVBFM_VB_ONLINE) sync_e2(E);
+    SV_CUDA(E, cudaMemcpyAsync(&E->d_sc->sum_t, &sum_t, 8, cudaMemcpyHostToDevice, E->stream));
+    SV_CUDA(E, cudaStreamSynchronize(E->stream));
+    sv_free(tmp);
+    return check_launch(E, "set_residuals");
+}
+
 int svbfm_get_sum_t(svbfm_t* h, double* sum_t) {
     Engine* E = reinterpret_cast<Engine*>(h);
     if (!E || !sum_t) return SVBFM_ERR_ARG;

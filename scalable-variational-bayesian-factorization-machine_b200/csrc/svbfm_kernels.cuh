@@ -1793,6 +1793,10 @@ __global__ void k_fill_f64(double* a, size_t n, double v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = v;
 }
+__global__ void k_permute(const double* __restrict__ src, const uint32_t* __restrict__ perm, uint32_t n, double* __restrict__ dst) {
+    uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n) dst[d] = src[perm ? perm[d] : d];
+}
 __global__ void k_unpermute(const double* __restrict__ src, const uint32_t* __restrict__ perm, uint32_t n, double* __restrict__ dst) {
     uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d < n) dst[perm ? perm[d] : d] = src[d];

@@ -77,6 +77,10 @@ class fm_learn_cuda : public fm_learn {
 public:
     int method = SVBFM_VB;
     bool do_sample = true, do_multilevel = true;
+    // -save_model / -load_model (the fork itself has no model files): parameters (means and variances
+    // of w0, w, v), hyper-parameters and -- one GPU -- the cached residuals + sum_i T_i, raw doubles. A vb run that loads what
+    // another vb run saved continues bit for bit; mcmc / vb_online take the parameters and hyper-parameters as a warm start.
+    std::string save_model, load_model;
     ~fm_learn_cuda() override { if (h_) svbfm_destroy(h_); }
 
     void init() override {
@@ -134,11 +138,70 @@ protected:
         ck(svbfm_set_groups(h_, meta->attr_group.data(), meta->num_attr_groups), "svbfm_set_groups");
         push(SVBFM_TRAIN, train);
         push(SVBFM_TEST, test);
+        if (!load_model.empty()) read_model();          // replaces the random initial state
         ck(svbfm_set_state(h_, state_.w0_mean, state_.w0_var, state_.w_mean.data(), state_.w_var.data(), state_.v_mean.data(), state_.v_var.data()),
            "svbfm_set_state");
+        if (!load_model.empty())
+            ck(svbfm_set_hyper(h_, model_.alpha, model_.sigma_0, model_.sigma_w.data(), model_.sigma_v.empty() ? nullptr : model_.sigma_v.data()), "svbfm_set_hyper");
         std::ostringstream t;
         t << fm->k0 << fm->k1 << fm->num_factor;
         tag_ = t.str();
+    }
+
+    struct ModelHeader { char magic[8]; uint32_t method, D; int32_t K; uint32_t G, has_resid, n_resid, reserved[2]; };
+    struct ModelExtra { double alpha = 1.0, sigma_0 = 1.0, sum_t = 0.0; std::vector<double> sigma_w, sigma_v, resid; bool has_resid = false; } model_;
+
+    void read_model() {
+        std::ifstream f(load_model.c_str(), std::ios::binary);
+        if (!f.is_open()) throw "Unable to open file " + load_model;
+        ModelHeader hd;
+        f.read(reinterpret_cast<char*>(&hd), sizeof(hd));
+        if (f.gcount() != (std::streamsize)sizeof(hd) || memcmp(hd.magic, "SVBFMMD1", 8) != 0) throw load_model + " is not a model file of this program";
+        const uint32_t D = fm->num_attribute, G = meta->num_attr_groups;
+        const int K = fm->num_factor;
+        if (hd.D != D || hd.K != K || hd.G != G) throw "model file " + load_model + " was saved with other dimensions (attributes, factors or groups)";
+        auto rd = [&](double* p, size_t n) {
+            f.read(reinterpret_cast<char*>(p), (std::streamsize)(n * 8));
+            if ((size_t)f.gcount() != n * 8) throw "model file " + load_model + " is truncated";
+        };
+        double sc[5];
+        rd(sc, 5);
+        state_.w0_mean = sc[0]; state_.w0_var = sc[1]; model_.alpha = sc[2]; model_.sigma_0 = sc[3]; model_.sum_t = sc[4];
+        state_.w_mean.resize(D); state_.w_var.resize(D); state_.v_mean.resize((size_t)K * D); state_.v_var.resize((size_t)K * D);
+        rd(state_.w_mean.data(), D); rd(state_.w_var.data(), D); rd(state_.v_mean.data(), (size_t)K * D); rd(state_.v_var.data(), (size_t)K * D);
+        model_.sigma_w.resize(G); model_.sigma_v.resize((size_t)G * K);
+        rd(model_.sigma_w.data(), G); rd(model_.sigma_v.data(), (size_t)G * K);
+        model_.has_resid = hd.has_resid != 0 && (int)hd.method == method;
+        if (hd.has_resid) { model_.resid.resize(hd.n_resid); rd(model_.resid.data(), hd.n_resid); }
+    }
+    // after svbfm_begin: the saved residuals replace the freshly predicted ones (same run, same train split, one GPU)
+    void restore_residuals(uint32_t num_train_cases) {
+        if (method != SVBFM_VB || load_model.empty() || !model_.has_resid || shard.world > 1 || model_.resid.size() != num_train_cases) return;
+        ck(svbfm_set_residuals(h_, model_.resid.data(), model_.sum_t), "svbfm_set_residuals");
+    }
+    void write_model(uint32_t num_train_cases) {
+        if (save_model.empty()) return;
+        const uint32_t D = fm->num_attribute, G = meta->num_attr_groups;
+        const int K = fm->num_factor;
+        std::vector<double> wm(D), wv(D), vm((size_t)K * D), vv((size_t)K * D), sw(G), sv((size_t)G * std::max(K, 1)), resid;
+        double sc[5] = {0, 0, 0, 0, 0};
+        ck(svbfm_get_state(h_, &sc[0], &sc[1], wm.data(), wv.data(), vm.data(), vv.data()), "svbfm_get_state");
+        ck(svbfm_get_hyper(h_, &sc[2], &sc[3], sw.data(), sv.data()), "svbfm_get_hyper");
+        ck(svbfm_get_sum_t(h_, &sc[4]), "svbfm_get_sum_t");
+        const bool with_resid = shard.world <= 1;
+        if (with_resid) { resid.resize(num_train_cases); ck(svbfm_get_residuals(h_, resid.data()), "svbfm_get_residuals"); }
+        if (!root()) return;
+        ModelHeader hd;
+        memset(&hd, 0, sizeof(hd));
+        memcpy(hd.magic, "SVBFMMD1", 8);
+        hd.method = (uint32_t)method; hd.D = D; hd.K = K; hd.G = G; hd.has_resid = with_resid ? 1u : 0u; hd.n_resid = with_resid ? num_train_cases : 0u;
+        std::ofstream f(save_model.c_str(), std::ios::binary);
+        if (!f.is_open()) throw "Unable to open file " + save_model;
+        auto wr = [&](const double* p, size_t n) { f.write(reinterpret_cast<const char*>(p), (std::streamsize)(n * 8)); };
+        f.write(reinterpret_cast<const char*>(&hd), sizeof(hd));
+        wr(sc, 5); wr(wm.data(), D); wr(wv.data(), D); wr(vm.data(), (size_t)K * D); wr(vv.data(), (size_t)K * D); wr(sw.data(), G); wr(sv.data(), (size_t)G * K);
+        if (with_resid) wr(resid.data(), resid.size());
+        if (!f.good()) throw "could not write " + save_model;
     }
 
     // hands data_t + target of this rank's shard of cases to the engine
@@ -169,6 +232,7 @@ public:
     void learn(DataSet& train, DataSet& test) override {
         open_engine(train, test);
         ck(svbfm_begin(h_), "svbfm_begin");
+        restore_residuals(train.num_cases);
         truncate_file("test_rmse_" + tag_ + "_vb");                 // vbs.h:66-73
         truncate_file("free_energy_" + tag_ + "_vb");
         for (unsigned i = 0; i < num_iter; i++) {
@@ -192,6 +256,7 @@ public:
                 log->newLine();
             }
         }
+        write_model(train.num_cases);
     }
 };
 
@@ -237,6 +302,7 @@ public:
                 log->newLine();
             }
         }
+        write_model(train.num_cases);
     }
 };
 
@@ -280,6 +346,7 @@ public:
                 log->newLine();
             }
         }
+        write_model(train.num_cases);
     }
 };
 

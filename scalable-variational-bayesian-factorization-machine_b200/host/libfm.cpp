@@ -104,6 +104,8 @@ int main(int argc, char** argv) {
         const std::string p_rel = cmd.reg("relation", "BS: filenames for the relations, default=''");
         const std::string p_cache = cmd.reg("cache_size", "cache size for data storage (accepted; data is held in memory)");
         const std::string p_batch = cmd.reg("batch", "How many batches for online algorithm");
+        const std::string p_save = cmd.reg("save_model", "filename for writing the model (parameters, hyper-parameters, residuals) after learning");
+        const std::string p_load = cmd.reg("load_model", "filename of a saved model to continue from instead of the random initial state");
         const std::string p_sampling = "do_sampling", p_multilevel = "do_multilevel", p_evalcases = "num_eval_cases";
         cmd.reg(p_sampling, "hidden"); cmd.reg(p_multilevel, "hidden"); cmd.reg(p_evalcases, "hidden");
         cmd.reg("device", "CUDA device ordinal (default: LOCAL_RANK or 0)");
@@ -191,6 +193,8 @@ int main(int argc, char** argv) {
         fml->fm = &fm; fml->meta = &meta;
         fml->max_target = train.max_target; fml->min_target = train.min_target;     // libfm.cpp:332-333
         fml->seed = seed; fml->device = device; fml->shard = sh;
+        if (cmd.has(p_save)) fml->save_model = cmd.get(p_save);
+        if (cmd.has(p_load)) fml->load_model = cmd.get(p_load);
         const std::string task = cmd.get(p_task);
         if (task == "r") fml->task = 0;
         else if (task == "c") {                                   // libfm.cpp:337-343: every target <= 0 becomes -1, the others +1

@@ -80,3 +80,50 @@ def test_cli_binary_input_equals_text_input(built, tmp_path):
     rmse = floats(tmp_path / "test_rmse_114_vb")
     for a, b in zip(rmse, c["test_rmse"][:3]):
         assert abs(a - b) <= TOL * b
+
+
+def test_cli_baseline_config_1_on_the_reference_data(built, tmp_path):
+    """BASELINE config 1: the reference's own data (data/sa.test_libfm, committed gzipped; 90 000 / 10 000 split), `-method vb -dim
+    '1,1,8' -iter 100`: every iteration's test RMSE, train RMSE and free energy against the files the unmodified reference binary wrote
+    (tests/golden/make_golden_sa.py), 1e-4 relative."""
+    import gzip
+    c = json.load(open(os.path.join(G, "golden_sa.json")))
+    lines = gzip.open(os.path.join(G, "sa.test_libfm.gz"), "rt").read().splitlines(True)
+    assert len(lines) == 100000
+    open(tmp_path / "tr", "w").writelines(lines[:90000])
+    open(tmp_path / "te", "w").writelines(lines[90000:])
+    p = subprocess.run([EXE, "-task", "r", "-train", "tr", "-test", "te", "-dim", "1,1,8", "-method", "vb", "-iter", str(c["iters"]), "-seed", str(c["seed"])],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert "ERROR" not in p.stderr, p.stderr
+    rmse, fe = floats(tmp_path / "test_rmse_118_vb"), floats(tmp_path / "free_energy_118_vb")
+    train = [float(l.split("Train=")[1].split("\t")[0]) for l in p.stdout.splitlines() if l.startswith("#Iter=")]
+    assert len(rmse) == len(fe) == len(train) == c["iters"]
+    for it in range(c["iters"]):
+        assert abs(rmse[it] - c["test_rmse"][it]) <= TOL * c["test_rmse"][it], (it, rmse[it], c["test_rmse"][it])
+        assert abs(train[it] - c["train_stat"][it]) <= TOL * c["train_stat"][it], (it, train[it], c["train_stat"][it])
+        assert abs(fe[it] - c["neg_free_energy"][it]) <= TOL * abs(c["neg_free_energy"][it]), (it, fe[it], c["neg_free_energy"][it])
+
+
+def test_cli_save_and_load_model_resume_bit_for_bit(built, tmp_path):
+    """-save_model / -load_model: 5 iterations, save, load, 5 more iterations write the same lines into
+    test_rmse_* and free_energy_* as 10 iterations in one go: parameters, hyper-parameters, residuals and sum T travel as raw doubles."""
+    c = GOLD[0]
+    for s in ("train", "test"):
+        shutil.copy(os.path.join(G, f"{c['data']}_{s}.libfm"), tmp_path / s)
+    base = [EXE, "-task", "r", "-train", "train", "-test", "test", "-dim", c["dim"], "-method", "vb", "-seed", str(c["seed"])]
+    k = c["dim"].split(",")
+    tag = f"{int(k[0] != '0')}{int(k[1] != '0')}{k[2]}"
+
+    def run(extra):
+        p = subprocess.run(base + extra, cwd=tmp_path, capture_output=True, text=True)
+        assert "ERROR" not in p.stderr, p.stderr
+        return open(tmp_path / f"test_rmse_{tag}_vb").read().split(), open(tmp_path / f"free_energy_{tag}_vb").read().split()
+
+    full_r, full_f = run(["-iter", "10"])
+    a_r, a_f = run(["-iter", "5", "-save_model", "model.bin"])
+    b_r, b_f = run(["-iter", "5", "-load_model", "model.bin", "-out", "pred.txt"])
+    assert len(full_r) == 10 and a_r + b_r == full_r and a_f + b_f == full_f
+    # a model of other dimensions is refused the way the reference reports errors
+    other = [EXE, "-task", "r", "-train", "train", "-test", "test", "-dim", "1,1,2", "-method", "vb", "-iter", "1", "-load_model", "model.bin"]
+    p = subprocess.run(other, cwd=tmp_path, capture_output=True, text=True)
+    assert "ERROR" in p.stderr and "dimensions" in p.stderr
