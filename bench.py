@@ -73,9 +73,10 @@ def parse_args():
                     help="how the ratings are split over the GPUs. auto: strong -> cross (first residual copy by user block, second copy by item block: no "
                          "column sums cross the ranks, the updated columns' records do), weak -> case_range (every GPU draws its own N ratings, both "
                          "fields allreduced). user_block: both copies by user block, item sums allreduced")
-    ap.add_argument("--col-cost", type=float, default=20.0,
-                    help="user-block shards are balanced by ratings + col_cost x users: a column costs the stream passes about as much as 15-20 "
-                         "entries (fitted on the per-rank stream times of 2-GPU runs: 90 over-corrects, 107 M vs 93 M ratings -> 64.6 vs 59.8 ms)")
+    ap.add_argument("--col-cost", type=float, default=8.0,
+                    help="block shards are balanced by ratings + col_cost x columns. Fitted on the per-rank pass times of the 8-GPU run of round 2 "
+                         "(profiles/r02_f_bench_n8_cross.json: 26.7 M ratings + 50 k users 7.8 ms, 13.0 M ratings + 650 k users 4.8 ms per iteration: "
+                         "a column costs a pass about 5 entries; the finalize adds a little per column)")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="strong (default): the workload's N ratings are split over the GPUs (BASELINE's metric: the 200 M sweep at 1/2/4/8 GPUs); "
                          "weak: every GPU holds its own N ratings (global N x gpus)")

@@ -191,6 +191,61 @@ static int exchange_blocks(Engine* E) {
 // Every rank then forms the other blocks' records itself and updates its parameter table (k_records_remote).
 struct RecPlan;
 static int exchange_records(Engine* E, int run, const Run& r, double2* pf, const RecPlan* rp, bool mcmc);
+static double2* stage_of(Engine* E, unsigned char* base, int run) {      // p2p: one stage per field (a fast rank may already fill the next one)
+    return reinterpret_cast<double2*>(base + 256) + (E->p2p && run ? E->xstage_cap : 0);
+}
+
+namespace svb {
+// cross shards: the allocation [flags | stage 0 | stage 1] and, when CUDA IPC works between the ranks, the other ranks' mappings of it
+int setup_exchange(Engine* E, size_t cap) {
+    cudaStream_t st = E->stream;
+    const size_t bytes = std::max<size_t>(65536, 256 + 2 * cap * sizeof(double2));
+    if (cudaMalloc((void**)&E->d_xipc, bytes) != cudaSuccess) { cudaGetLastError(); E->d_xipc = nullptr; return fail(E, SVBFM_ERR_OOM, "cudaMalloc: column stages"); }
+    SV_CUDA(E, cudaMemsetAsync(E->d_xipc, 0, 256, st));
+    E->d_xstage = reinterpret_cast<double2*>(E->d_xipc + 256);
+    E->xstage_cap = cap; E->xs_epoch = 0; E->p2p = false;
+    for (int r = 0; r < 16; r++) E->peer_base[r] = nullptr;
+    E->peer_base[E->rank] = E->d_xipc;
+    // every rank publishes the handle of its allocation; any failure anywhere leaves all ranks on the collective
+    const int W = E->world;
+    constexpr int HW = (int)(sizeof(cudaIpcMemHandle_t) / 4);
+    std::vector<uint32_t> hbuf((size_t)W * (HW + 1), 0u);
+    cudaIpcMemHandle_t mine;
+    bool ok = !getenv("SVBFM_NO_P2P") && cudaIpcGetMemHandle(&mine, E->d_xipc) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    if (ok) { memcpy(&hbuf[(size_t)E->rank * (HW + 1)], &mine, sizeof(mine)); hbuf[(size_t)E->rank * (HW + 1) + HW] = 1u; }
+    uint32_t* d = nullptr;
+    SV_CUDA(E, sv_malloc((void**)&d, hbuf.size() * 4));
+    SV_CUDA(E, cudaMemcpyAsync(d, hbuf.data(), hbuf.size() * 4, cudaMemcpyHostToDevice, st));
+    int rc = allreduce(E, d, hbuf.size(), 3 /*ncclUint32*/, 0 /*ncclSum*/);
+    if (!rc) { cudaMemcpyAsync(hbuf.data(), d, hbuf.size() * 4, cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st); }
+    if (rc) { sv_free(d); return rc; }
+    bool all = true;
+    for (int r = 0; r < W; r++) all = all && hbuf[(size_t)r * (HW + 1) + HW] == 1u;
+    uint32_t opened = 1u;
+    if (all) {
+        for (int r = 0; r < W && opened; r++) {
+            if (r == E->rank) continue;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, &hbuf[(size_t)r * (HW + 1)], sizeof(h));
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0u; }
+            else E->peer_base[r] = reinterpret_cast<unsigned char*>(p);
+        }
+    } else opened = 0u;
+    cudaMemcpyAsync(d, &opened, 4, cudaMemcpyHostToDevice, st);
+    rc = allreduce(E, d, 1, 3 /*ncclUint32*/, 3 /*ncclMin*/);
+    if (!rc) { cudaMemcpyAsync(&opened, d, 4, cudaMemcpyDeviceToHost, st); cudaStreamSynchronize(st); }
+    sv_free(d);
+    if (rc) return rc;
+    if (!opened) {
+        for (int r = 0; r < W; r++) if (r != E->rank && E->peer_base[r]) { cudaIpcCloseMemHandle(E->peer_base[r]); E->peer_base[r] = nullptr; }
+        return 0;
+    }
+    E->p2p = true;
+    return 0;
+}
+}  // namespace svb
 
 // stream schedule: what a finalize has to leave behind for the passes that follow (kernels.cuh FinalizeArgs)
 struct RecPlan {
@@ -257,7 +312,10 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
     fa.span = sp; fa.ab = use_ab ? E->d_ab : nullptr;
     if (rp) { fa.cpack = E->d_cpack; fa.opack = E->d_opack; fa.rec_mode = rp->rec_mode; fa.p_next = rp->p_next; fa.p_prev = rp->p_prev; }
     fa.rec_slot = E->rec_rank ? E->d_rec_slot : nullptr;
-    if (rp && rp->run >= 0 && E->xs) { fa.stage = E->d_xstage; fa.stage_base = E->slot_base[rp->run]; }
+    if (rp && rp->run >= 0 && E->xs) {
+        fa.stage = E->d_xstage; fa.stage_base = E->slot_base[rp->run];
+        if (E->p2p) { fa.peer.n = E->world; for (int q = 0; q < E->world; q++) fa.peer.p[q] = stage_of(E, E->peer_base[q], rp->run); }
+    }
     if (rp && rp->run >= 0 && E->bv.on) fa.gcnt = E->bv.gcnt[rp->run];
     if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V) {
         fa.nat = IS_V ? E->d_nat_v + (size_t)f * E->D : E->d_nat_w;
@@ -276,17 +334,22 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
 
 static int exchange_records(Engine* E, int run, const Run& r, double2* pf, const RecPlan* rp, bool mcmc) {
     cudaStream_t st = E->stream;
-    {
+    RemoteRecArgs a{};
+    if (E->p2p) {
+        a.flags.n = E->world; a.flags.me = E->rank;
+        for (int q = 0; q < E->world; q++) a.flags.p[q] = reinterpret_cast<unsigned long long*>(E->peer_base[q]);
+        a.epoch = ++E->xs_epoch;
+    } else {
         ProfScope pc(E, 10);
         const size_t per = (size_t)E->slot_max[run] * 2;                       // doubles per rank
         double* base = reinterpret_cast<double*>(E->d_xstage);
         int rc = g_nccl.AllGather(base + per * (size_t)E->rank, base, per, 8 /*ncclDouble*/, E->nccl_comm, st);
         if (rc != 0) return fail(E, SVBFM_ERR_NCCL, std::string("ncclAllGather (columns): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
     }
-    RemoteRecArgs a{};
+    ProfScope pc(E, E->p2p ? 10 : 1);       // p2p: the wait for the other ranks' flags is the exchange
     const std::vector<uint32_t>& blk = run ? E->blk1 : E->blk;
     a.c0 = r.col_begin; a.c1 = r.col_end; a.own0 = blk[E->rank]; a.own1 = blk[E->rank + 1];
-    a.rec_slot = E->d_rec_slot; a.stage = E->d_xstage; a.stage_base = E->slot_base[run];
+    a.rec_slot = E->d_rec_slot; a.stage = stage_of(E, E->d_xipc, run); a.stage_base = E->slot_base[run];
     a.pf = pf; a.p_next = rp->p_next; a.p_prev = rp->p_prev; a.rec_mode = rp->rec_mode; a.mcmc = mcmc ? 1 : 0; a.cpack = E->d_cpack;
     const uint32_t nc = r.col_end - r.col_begin;
     if (nc) { k_records_remote<<<nblk(nc), 256, 0, st>>>(a); LAUNCHED(E); }
@@ -863,7 +926,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_xstage, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_gcnt[0], E->d_vbo_gcnt[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_gcnt[0], E->d_vbo_gcnt[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) sv_free(p);
     cudaStreamSynchronize(E->stream);
     if (E->copy_stream) { cudaStreamSynchronize(E->copy_stream); cudaStreamDestroy(E->copy_stream); }
@@ -1405,7 +1468,7 @@ int svbfm_get_info(svbfm_t* h, svbfm_info* out) {
     out->world_size = (uint32_t)E->world;
     out->fused_schedule = ((stream_ok(E) || E->vbo_streams) ? 1u : 0u) | (E->rec_rank ? 2u : 0u) | ((E->stream_tma && stream_ok(E)) ? 4u : 0u) |
                           (E->graph_replays ? 8u : 0u);
-    out->exclusive_blocks = (E->excl0 ? 1u : 0u) | (E->xs ? 2u : 0u);
+    out->exclusive_blocks = (E->excl0 ? 1u : 0u) | (E->xs ? 2u : 0u) | (E->p2p ? 4u : 0u);
     return SVBFM_OK;
 }
 

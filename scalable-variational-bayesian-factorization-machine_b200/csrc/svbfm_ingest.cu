@@ -721,6 +721,12 @@ void set_side_views(Engine* E) {
 }
 
 void free_second(Engine* E) {
+    for (int r = 0; r < 16; r++) {
+        if (E->peer_base[r] && E->peer_base[r] != E->d_xipc) cudaIpcCloseMemHandle(E->peer_base[r]);
+        E->peer_base[r] = nullptr;
+    }
+    if (E->d_xipc) { cudaStreamSynchronize(E->stream); cudaFree(E->d_xipc); }
+    E->d_xipc = nullptr; E->d_xstage = nullptr; E->xstage_cap = 0; E->p2p = false; E->xs_epoch = 0;
     sv_free(E->sec.colptr); sv_free(E->sec.oc); sv_free(E->sec.rcol); sv_free(E->sec.y);
     E->sec = Engine::SecondShard();
     E->xs = false;
@@ -953,14 +959,7 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
         if (sv_malloc((void**)&E->d_cpack, total_slots * 32 /* sizeof(ColPack) */) != cudaSuccess) return fail(E, SVBFM_ERR_OOM, "cudaMalloc: record slots");
         E->cpack_cap = total_slots;
     }
-    {
-        const size_t need = (size_t)E->world * std::max(mx0, mx1);
-        if (E->xstage_cap < need) {
-            sv_free(E->d_xstage); E->d_xstage = nullptr;
-            if (dev_alloc(E, &E->d_xstage, need)) return SVBFM_ERR_OOM;
-            E->xstage_cap = need;
-        }
-    }
+    if (int rc = setup_exchange(E, (size_t)E->world * std::max(mx0, mx1))) return rc;
     // ---- tiles of the second side on the new shard (the first side keeps its own), second residual copy, tile sums
     const uint64_t TS = 1ull << E->ts_shift;
     std::vector<uint32_t> heavy;

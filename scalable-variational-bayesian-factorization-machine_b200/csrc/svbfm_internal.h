@@ -236,8 +236,16 @@ struct Engine {
     } sec;
     uint32_t slot_base[2] = {0, 0}, slot_max[2] = {0, 0};   // record slots of field f: [slot_base[f] + r * slot_max[f], + block size) for rank r
     size_t cpack_cap = 0;             // records allocated in d_cpack
-    double2* d_xstage = nullptr;      // [world * max(slot_max)] {new mean, new var} of the columns finalized in this step, slot order: the allgather buffer
-    size_t xstage_cap = 0;
+    // {new mean, new var} of the columns finalized in a step, slot order. One device allocation holds 16 flag words and two such
+    // stages (one per field); when the ranks can map each other's allocation (CUDA IPC over NVLink: p2p) the owner's k_finalize
+    // stores its columns straight into every rank's stage and k_records_remote exchanges flag words instead of a collective;
+    // otherwise stage 0 is the buffer of an in-place ncclAllGather.
+    unsigned char* d_xipc = nullptr;  // [256 B flags | stage 0 | stage 1]
+    double2* d_xstage = nullptr;      // stage 0 (inside d_xipc)
+    size_t xstage_cap = 0;            // columns per stage: world * max(slot_max)
+    bool p2p = false;
+    unsigned char* peer_base[16] = {nullptr};   // [world] rank r's allocation as mapped here (own: d_xipc)
+    uint64_t xs_epoch = 0;            // exchanges done: the value a rank writes into the others' flag words when its stores of an exchange are out
     // what a pass over side 0 / 1 of the stream schedule reads (set_side_views)
     struct SideView {
         const uint64_t* colptr = nullptr;  // indexed by global column id
@@ -260,6 +268,7 @@ int detect_exclusive_blocks(Engine* E);   // svbfm_engine.cu; collective (every 
 int ingest_second(Engine* E, uint32_t num_cases, uint32_t num_cols, const uint64_t* colptr, const uint32_t* case_id, const float* x,
                   const float* target);       // svbfm_ingest.cu: the second residual copy's shard (cross shards)
 void free_second(Engine* E);
+int setup_exchange(Engine* E, size_t columns_per_stage);      // svbfm_engine.cu; collective
 int detect_blocks(Engine* E, const Run& r, const std::vector<uint64_t>& h_colptr, std::vector<uint32_t>& blk, bool& exclusive);   // collective
 int vbo_stream_prepare(Engine* E, uint32_t num_batch);   // svbfm_ingest.cu: per-epoch batch index lists (needs d_rbatch, d_cbatch, d_batch_cnt)
 

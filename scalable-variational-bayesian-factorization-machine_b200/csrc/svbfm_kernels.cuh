@@ -327,6 +327,9 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t c0, uint
     return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
 
+struct PeerStages { double2* p[16]; int n; };
+struct PeerFlags { unsigned long long* p[16]; int n, me; };      // p[r]: rank r's 16 flag words; a rank writes word `me` of every other rank
+
 struct FinalizeArgs {
     uint32_t c0, c1;             // column range of the run
     int f;                       // factor (or -1 for w)
@@ -354,6 +357,7 @@ struct FinalizeArgs {
     double* dT;                  // [D]
     double2* stage;              // cross shards: {new mean, new var} of the column at stage[slot - stage_base]: what travels to the other ranks
     uint32_t stage_base;
+    PeerStages peer;             // p2p: the same stage of EVERY rank (own included), stored to directly over NVLink
     uint64_t seed; int do_sample;
     // vb_online
     double2* nat;                // [D] natural params of this factor
@@ -369,7 +373,11 @@ __device__ __forceinline__ void write_records(const FinalizeArgs& a, uint32_t j,
     if (!a.rec_mode) return;
     double2 N = a.p_next ? a.p_next[j] : make_double2(0.0, 0.0);
     const uint32_t sj = a.rec_slot ? a.rec_slot[j] : j;
-    if (a.stage) a.stage[sj - a.stage_base] = make_double2(new_mean, new_var);
+    if (a.peer.n) {      // fused finalize + all-gather: one 16-byte store per rank; system-scope fence before this rank raises its flag
+        const double2 v = make_double2(new_mean, new_var);
+        for (int r = 0; r < a.peer.n; r++) a.peer.p[r][sj - a.stage_base] = v;
+        __threadfence_system();
+    } else if (a.stage) a.stage[sj - a.stage_base] = make_double2(new_mean, new_var);
     if (a.rec_mode == 1) {
         a.cpack[sj] = ColPack{new_mean, new_var, dlt, a.p_prev ? a.p_prev[j].x : 0.0};
         a.opack[j] = OwnPack{N.x, new_mean, dlt, 0.0};
@@ -1738,12 +1746,29 @@ struct RemoteRecArgs {
     const double2* p_prev;
     int rec_mode, mcmc;
     ColPack* cpack;
+    PeerFlags flags;             // p2p: flag words of every rank (n = 0: the stage was filled by a collective)
+    unsigned long long epoch;    // number of this exchange
 };
 __global__ void __launch_bounds__(256) k_records_remote(RemoteRecArgs a) {
+    if (a.flags.n) {
+        // this rank's k_finalize (earlier on the stream, fenced) has stored its columns into every stage: say so, then wait until every
+        // other rank has said the same. Block 0 is dispatched first; the waiting blocks depend on other GPUs only.
+        const int t = (int)threadIdx.x;
+        if (blockIdx.x == 0 && t < a.flags.n && t != a.flags.me) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(a.flags.p[t] + a.flags.me) = a.epoch;
+        }
+        if (t < a.flags.n && t != a.flags.me) {
+            volatile unsigned long long* f = a.flags.p[a.flags.me] + t;
+            while (*f < a.epoch) {}
+        }
+        __syncthreads();
+        __threadfence_system();
+    }
     uint32_t j = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= a.c1 || (j >= a.own0 && j < a.own1)) return;
     const uint32_t sj = a.rec_slot[j];
-    const double2 nw = a.stage[sj - a.stage_base], old = a.pf[j];
+    const double2 nw = __ldcg(&a.stage[sj - a.stage_base]), old = a.pf[j];      // written by another GPU: not through L1
     const double dlt = a.mcmc ? (nw.x - old.x) : (old.x - nw.x);      // k_finalize: skip <=> the mean did not move <=> 0
     a.pf[j] = nw;
     const double2 N = a.p_next ? a.p_next[j] : make_double2(0.0, 0.0);

@@ -1,6 +1,10 @@
 // tests/emu/emu_runtime.cpp -- TEST INFRASTRUCTURE (see include/cuda_runtime.h).
 // Fiber scheduler of the lockstep emulator + the handful of runtime calls the engine makes. One OS thread; the CUDA
 // threads of a CTA are fibers that run until they return or reach a warp / block primitive; CTAs run one at a time.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+#include <map>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -265,14 +269,69 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
 }
 cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+// allocations of 64 KB and more live in a memfd so that another emulator process can map them (cudaIpc*)
+namespace {
+struct SharedBlock { int fd; size_t bytes; bool opened; };
+std::map<void*, SharedBlock>& shared_blocks() { static std::map<void*, SharedBlock> m; return m; }
+struct IpcRecord { char magic[8]; int pid, fd; size_t bytes; };
+}  // namespace
 cudaError_t cudaMalloc(void** p, size_t n) {
     if (g_capture) g_capture_broken = true;     // not allowed while capturing
+    if (n >= 65536) {
+        const size_t bytes = (n + 4095) / 4096 * 4096;
+        int fd = memfd_create("svbfm_emu", 0);
+        if (fd >= 0 && ftruncate(fd, (off_t)bytes) == 0) {
+            void* m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+            if (m != MAP_FAILED) {
+                memset(m, 0xcd, n);
+                shared_blocks()[m] = SharedBlock{fd, bytes, false};
+                *p = m;
+                return cudaSuccess;
+            }
+        }
+        if (fd >= 0) close(fd);
+    }
     *p = aligned_alloc(256, (n + 255) / 256 * 256 + 256);
     if (!*p) return cudaErrorMemoryAllocation;
     memset(*p, 0xcd, n);       // "device memory" starts out as garbage, not zeros
     return cudaSuccess;
 }
-cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaFree(void* p) {
+    auto it = shared_blocks().find(p);
+    if (it != shared_blocks().end()) { munmap(p, it->second.bytes); close(it->second.fd); shared_blocks().erase(it); return cudaSuccess; }
+    free(p);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+    auto it = shared_blocks().find(p);
+    if (it == shared_blocks().end() || it->second.opened) return cudaErrorInvalidValue;
+    IpcRecord r;
+    memset(&r, 0, sizeof(r));
+    memcpy(r.magic, "EMUIPC01", 8); r.pid = (int)getpid(); r.fd = it->second.fd; r.bytes = it->second.bytes;
+    memset(h, 0, sizeof(*h));
+    memcpy(h->reserved, &r, sizeof(r));
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+    IpcRecord r;
+    memcpy(&r, h.reserved, sizeof(r));
+    if (memcmp(r.magic, "EMUIPC01", 8) != 0) return cudaErrorInvalidValue;
+    char path[64];
+    snprintf(path, sizeof(path), "/proc/%d/fd/%d", r.pid, r.fd);
+    int fd = open(path, O_RDWR);
+    if (fd < 0) return cudaErrorInvalidValue;
+    void* m = mmap(nullptr, r.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (m == MAP_FAILED) { close(fd); return cudaErrorInvalidValue; }
+    shared_blocks()[m] = SharedBlock{fd, r.bytes, true};
+    *p = m;
+    return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void* p) {
+    auto it = shared_blocks().find(p);
+    if (it == shared_blocks().end() || !it->second.opened) return cudaErrorInvalidValue;
+    munmap(p, it->second.bytes); close(it->second.fd); shared_blocks().erase(it);
+    return cudaSuccess;
+}
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
     if (g_capture) { g_capture->nodes.push_back([d, s, n] { if (n) memmove(d, s, n); }); return cudaSuccess; }

@@ -72,6 +72,13 @@ cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaMalloc(void**, size_t);
 template <typename T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
 cudaError_t cudaFree(void*);
+// CUDA IPC between emulator PROCESSES: allocations of 64 KB and more are backed by a memfd, a handle names (pid, fd, size) and
+// the opening process maps /proc/<pid>/fd/<fd>: peer stores and flag words behave like memory shared over NVLink
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*);
+cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned);
+cudaError_t cudaIpcCloseMemHandle(void*);
 cudaError_t cudaMemcpy(void*, const void*, size_t, cudaMemcpyKind);
 cudaError_t cudaMemcpyAsync(void*, const void*, size_t, cudaMemcpyKind, cudaStream_t = nullptr);
 cudaError_t cudaMemset(void*, int, size_t);
@@ -137,7 +144,8 @@ static inline void __syncthreads() { emu::block_barrier(); }
 // ---- loads / stores with cache hints: plain accesses
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __ldcs(const T* p) { return *p; }
-template <typename T> static inline T __ldcg(const T* p) { return *p; }
+template <typename T> static inline T __ldcg(const T* p) { __sync_synchronize(); T v; memcpy(&v, p, sizeof(T)); return v; }
+static inline void __threadfence_system() { __sync_synchronize(); }
 template <typename T> static inline void __stcs(T* p, T v) { *p = v; }
 template <typename T> static inline void __stcg(T* p, T v) { *p = v; }
 

@@ -72,7 +72,7 @@ def main():
             E.set_csc(sv.TRAIN_SECOND, d.shard_csc_by_second_block(to_csc(tr), rank, world, nu)[0])
         E.set_csc(sv.TEST, d.shard_csc(to_csc(te), rank, world))
         info = E.info()
-        assert info["exclusive_blocks"] == (3 if cross else 1 if blocks else 0), (name, info)
+        assert info["exclusive_blocks"] & 3 == (3 if cross else 1 if blocks else 0), (name, info)
         assert info["world_size"] == world
         E.set_state(sv.host_init_state(42, D, K, 0.1, sv.METHODS[method]))
         E.begin()
