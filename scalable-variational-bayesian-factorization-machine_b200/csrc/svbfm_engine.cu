@@ -313,8 +313,7 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
     if (rp) { fa.cpack = E->d_cpack; fa.opack = E->d_opack; fa.rec_mode = rp->rec_mode; fa.p_next = rp->p_next; fa.p_prev = rp->p_prev; }
     fa.rec_slot = E->rec_rank ? E->d_rec_slot : nullptr;
     if (rp && rp->run >= 0 && E->xs) {
-        fa.stage = E->d_xstage; fa.stage_base = E->slot_base[rp->run];
-        if (E->p2p) { fa.peer.n = E->world; for (int q = 0; q < E->world; q++) fa.peer.p[q] = stage_of(E, E->peer_base[q], rp->run); }
+        fa.stage = stage_of(E, E->d_xipc, rp->run); fa.stage_base = E->slot_base[rp->run];
     }
     if (rp && rp->run >= 0 && E->bv.on) fa.gcnt = E->bv.gcnt[rp->run];
     if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V) {
@@ -334,10 +333,11 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
 
 static int exchange_records(Engine* E, int run, const Run& r, double2* pf, const RecPlan* rp, bool mcmc) {
     cudaStream_t st = E->stream;
+    (void)r;
     RemoteRecArgs a{};
     if (E->p2p) {
         a.flags.n = E->world; a.flags.me = E->rank;
-        for (int q = 0; q < E->world; q++) a.flags.p[q] = reinterpret_cast<unsigned long long*>(E->peer_base[q]);
+        for (int q = 0; q < E->world; q++) { a.flags.p[q] = reinterpret_cast<unsigned long long*>(E->peer_base[q]); a.src[q] = stage_of(E, E->peer_base[q], run); }
         a.epoch = ++E->xs_epoch;
     } else {
         ProfScope pc(E, 10);
@@ -345,14 +345,16 @@ static int exchange_records(Engine* E, int run, const Run& r, double2* pf, const
         double* base = reinterpret_cast<double*>(E->d_xstage);
         int rc = g_nccl.AllGather(base + per * (size_t)E->rank, base, per, 8 /*ncclDouble*/, E->nccl_comm, st);
         if (rc != 0) return fail(E, SVBFM_ERR_NCCL, std::string("ncclAllGather (columns): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+        for (int q = 0; q < E->world; q++) a.src[q] = E->d_xstage;
     }
-    ProfScope pc(E, E->p2p ? 10 : 1);       // p2p: the wait for the other ranks' flags is the exchange
+    ProfScope pc(E, E->p2p ? 10 : 1);       // p2p: flags + fetch from the peers are the exchange
     const std::vector<uint32_t>& blk = run ? E->blk1 : E->blk;
-    a.c0 = r.col_begin; a.c1 = r.col_end; a.own0 = blk[E->rank]; a.own1 = blk[E->rank + 1];
-    a.rec_slot = E->d_rec_slot; a.stage = stage_of(E, E->d_xipc, run); a.stage_base = E->slot_base[run];
+    a.slot_max = E->slot_max[run]; a.world = E->world; a.me = E->rank;
+    for (int q = 0; q < E->world; q++) a.cnt[q] = blk[q + 1] - blk[q];
+    a.col_of_slot = E->d_col_of_slot; a.stage_base = E->slot_base[run];
     a.pf = pf; a.p_next = rp->p_next; a.p_prev = rp->p_prev; a.rec_mode = rp->rec_mode; a.mcmc = mcmc ? 1 : 0; a.cpack = E->d_cpack;
-    const uint32_t nc = r.col_end - r.col_begin;
-    if (nc) { k_records_remote<<<nblk(nc), 256, 0, st>>>(a); LAUNCHED(E); }
+    const uint64_t nthreads = (uint64_t)E->world * E->slot_max[run];
+    if (nthreads) { k_records_remote<<<nblk(nthreads), 256, 0, st>>>(a); LAUNCHED(E); }
     return 0;
 }
 

@@ -727,6 +727,7 @@ void free_second(Engine* E) {
     }
     if (E->d_xipc) { cudaStreamSynchronize(E->stream); cudaFree(E->d_xipc); }
     E->d_xipc = nullptr; E->d_xstage = nullptr; E->xstage_cap = 0; E->p2p = false; E->xs_epoch = 0;
+    sv_free(E->d_col_of_slot); E->d_col_of_slot = nullptr;
     sv_free(E->sec.colptr); sv_free(E->sec.oc); sv_free(E->sec.rcol); sv_free(E->sec.y);
     E->sec = Engine::SecondShard();
     E->xs = false;
@@ -954,6 +955,11 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
     sv_free(E->d_rec_slot);
     E->d_rec_slot = d_new; d_new = nullptr;
     E->rec_rank = true;
+    sv_free(E->d_col_of_slot); E->d_col_of_slot = nullptr;
+    if (dev_alloc(E, &E->d_col_of_slot, total_slots)) return SVBFM_ERR_OOM;
+    SV_CUDA(E, cudaMemsetAsync(E->d_col_of_slot, 0xff, total_slots * 4, st));
+    if (nc0) k_invert_slots<<<nblk(nc0), 256, 0, st>>>(E->d_rec_slot, r0.col_begin, r0.col_end, E->d_col_of_slot);
+    if (nc1) k_invert_slots<<<nblk(nc1), 256, 0, st>>>(E->d_rec_slot, r1.col_begin, r1.col_end, E->d_col_of_slot);
     if (E->cpack_cap < total_slots) {
         sv_free(E->d_cpack); E->d_cpack = nullptr;
         if (sv_malloc((void**)&E->d_cpack, total_slots * 32 /* sizeof(ColPack) */) != cudaSuccess) return fail(E, SVBFM_ERR_OOM, "cudaMalloc: record slots");

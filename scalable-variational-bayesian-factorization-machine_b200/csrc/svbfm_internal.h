@@ -237,9 +237,11 @@ struct Engine {
     uint32_t slot_base[2] = {0, 0}, slot_max[2] = {0, 0};   // record slots of field f: [slot_base[f] + r * slot_max[f], + block size) for rank r
     size_t cpack_cap = 0;             // records allocated in d_cpack
     // {new mean, new var} of the columns finalized in a step, slot order. One device allocation holds 16 flag words and two such
-    // stages (one per field); when the ranks can map each other's allocation (CUDA IPC over NVLink: p2p) the owner's k_finalize
-    // stores its columns straight into every rank's stage and k_records_remote exchanges flag words instead of a collective;
-    // otherwise stage 0 is the buffer of an in-place ncclAllGather.
+    // stages (one per field). A rank's k_finalize leaves its block in its own stage; when the ranks can map each other's
+    // allocation (CUDA IPC over NVLink: p2p) k_records_remote raises / waits on flag words and FETCHES the other ranks' blocks
+    // from their memory, coalesced in slot order (fused exchange + record build, no collective); otherwise stage 0 is the buffer
+    // of an in-place ncclAllGather and the same kernel reads it locally.
+    uint32_t* d_col_of_slot = nullptr; // [slots of both fields] column of every record slot (padding: unused)
     unsigned char* d_xipc = nullptr;  // [256 B flags | stage 0 | stage 1]
     double2* d_xstage = nullptr;      // stage 0 (inside d_xipc)
     size_t xstage_cap = 0;            // columns per stage: world * max(slot_max)

@@ -327,7 +327,6 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t c0, uint
     return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
 
-struct PeerStages { double2* p[16]; int n; };
 struct PeerFlags { unsigned long long* p[16]; int n, me; };      // p[r]: rank r's 16 flag words; a rank writes word `me` of every other rank
 
 struct FinalizeArgs {
@@ -355,9 +354,8 @@ struct FinalizeArgs {
     const double2* p_next;       // parameters of the step that follows ([D]; null after the last one)
     const double2* p_prev;       // parameters of the step before ([D]; null at the first one)
     double* dT;                  // [D]
-    double2* stage;              // cross shards: {new mean, new var} of the column at stage[slot - stage_base]: what travels to the other ranks
+    double2* stage;              // cross shards: {new mean, new var} of the column at stage[slot - stage_base]: what the other ranks fetch
     uint32_t stage_base;
-    PeerStages peer;             // p2p: the same stage of EVERY rank (own included), stored to directly over NVLink
     uint64_t seed; int do_sample;
     // vb_online
     double2* nat;                // [D] natural params of this factor
@@ -373,11 +371,7 @@ __device__ __forceinline__ void write_records(const FinalizeArgs& a, uint32_t j,
     if (!a.rec_mode) return;
     double2 N = a.p_next ? a.p_next[j] : make_double2(0.0, 0.0);
     const uint32_t sj = a.rec_slot ? a.rec_slot[j] : j;
-    if (a.peer.n) {      // fused finalize + all-gather: one 16-byte store per rank; system-scope fence before this rank raises its flag
-        const double2 v = make_double2(new_mean, new_var);
-        for (int r = 0; r < a.peer.n; r++) a.peer.p[r][sj - a.stage_base] = v;
-        __threadfence_system();
-    } else if (a.stage) a.stage[sj - a.stage_base] = make_double2(new_mean, new_var);
+    if (a.stage) a.stage[sj - a.stage_base] = make_double2(new_mean, new_var);
     if (a.rec_mode == 1) {
         a.cpack[sj] = ColPack{new_mean, new_var, dlt, a.p_prev ? a.p_prev[j].x : 0.0};
         a.opack[j] = OwnPack{N.x, new_mean, dlt, 0.0};
@@ -1737,10 +1731,12 @@ __global__ void k_pack_h4(uint32_t c0, uint32_t c1, const double2* __restrict__ 
 // record of the column for the passes that follow (write_records) -- and brings its parameter table up to date. The tables stay
 // complete and bit-identical on every rank without a block exchange at the end of the iteration.
 struct RemoteRecArgs {
-    uint32_t c0, c1;             // columns of the field
-    uint32_t own0, own1;         // this rank's block (already finalized here)
-    const uint32_t* rec_slot;
-    const double2* stage; uint32_t stage_base;
+    uint32_t slot_max;           // slots per block; the field's stage is [world][slot_max]
+    uint32_t cnt[16];            // columns in rank q's block
+    int world, me;
+    const uint32_t* col_of_slot; // [slots of both fields] column of every record slot
+    const double2* src[16];      // rank q's stage: its own block is current there (p2p: the peer's memory; else the local allgather buffer)
+    uint32_t stage_base;         // first record slot of the field
     double2* pf;                 // parameters of this step ([D])
     const double2* p_next;
     const double2* p_prev;
@@ -1751,7 +1747,7 @@ struct RemoteRecArgs {
 };
 __global__ void __launch_bounds__(256) k_records_remote(RemoteRecArgs a) {
     if (a.flags.n) {
-        // this rank's k_finalize (earlier on the stream, fenced) has stored its columns into every stage: say so, then wait until every
+        // this rank's k_finalize (earlier on the stream) has left its block in its stage: say so to every rank, then wait until every
         // other rank has said the same. Block 0 is dispatched first; the waiting blocks depend on other GPUs only.
         const int t = (int)threadIdx.x;
         if (blockIdx.x == 0 && t < a.flags.n && t != a.flags.me) {
@@ -1765,10 +1761,13 @@ __global__ void __launch_bounds__(256) k_records_remote(RemoteRecArgs a) {
         __syncthreads();
         __threadfence_system();
     }
-    uint32_t j = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= a.c1 || (j >= a.own0 && j < a.own1)) return;
-    const uint32_t sj = a.rec_slot[j];
-    const double2 nw = __ldcg(&a.stage[sj - a.stage_base]), old = a.pf[j];      // written by another GPU: not through L1
+    // one thread per slot of the OTHER ranks' blocks, in slot order: the fetch from a peer's memory is coalesced
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q = t / a.slot_max, k = t - q * a.slot_max;
+    if (q >= (uint32_t)a.world || q == (uint32_t)a.me || k >= a.cnt[q]) return;
+    const uint32_t sj = a.stage_base + t;
+    const uint32_t j = a.col_of_slot[sj];
+    const double2 nw = __ldcg(a.src[q] + t), old = a.pf[j];          // written by another GPU: not through L1
     const double dlt = a.mcmc ? (nw.x - old.x) : (old.x - nw.x);      // k_finalize: skip <=> the mean did not move <=> 0
     a.pf[j] = nw;
     const double2 N = a.p_next ? a.p_next[j] : make_double2(0.0, 0.0);
