@@ -105,6 +105,18 @@ int svbfm_set_groups(svbfm_t* h, const uint32_t* attr_group /*[D]*/, uint32_t nu
 int svbfm_set_csc(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_cols,
                   const uint64_t* colptr /*[num_cols+1]*/, const uint32_t* case_id /*[nnz]*/,
                   const float* x /*[nnz]*/, const float* target /*[num_cases]*/);
+/* The same split handed over ROW-wise: CSR of this rank's cases as the reference's `data` holds it (DataSubset::data, Data.h:87;
+ * the rows of a binary .x file or of a parsed text file), features in any order inside a case. The transposed matrix the sweeps
+ * run on is built on the device (replaces Data::create_data_t, Data.h:457-509, and tools/transpose.cpp:91-162 for this path): the
+ * caller neither transposes nor ships the data twice. Same results as svbfm_set_csc on the transposed data. */
+int svbfm_set_csr(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_cols,
+                  const uint64_t* rowptr /*[num_cases+1]*/, const uint32_t* feature_id /*[nnz]*/,
+                  const float* x /*[nnz]*/, const float* target /*[num_cases]*/);
+/* The device transpose by itself (no handle): CSR in, CSC out into caller-allocated host arrays; what bin/transpose --device writes
+ * as .xt, byte for byte the reference tool's output. Returns SVBFM_ERR_ARG for a feature id >= num_cols. */
+int svbfm_transpose_csr(int32_t device, uint32_t num_cases, uint32_t num_cols, const uint64_t* rowptr, const uint32_t* feature_id,
+                        const float* x, uint64_t* out_colptr /*[num_cols+1]*/, uint32_t* out_case_id /*[nnz]*/, float* out_x /*[nnz]*/);
+
 /* Cross shards (optional, several GPUs, two complete one-hot fields with x = 1, vb / mcmc regression): after SVBFM_TRAIN
  * -- which must then be a shard by blocks of the FIRST field's columns (rank r holds every case of its users; blocks disjoint and
  * ordered by rank) -- the caller hands over, as split SVBFM_TRAIN_SECOND in the same CSC format, the cases of the same global train

@@ -57,7 +57,7 @@ class Info(C.Structure):
 # every symbol include/svbfm.h declares (tests/test_abi.py checks the library exports exactly these)
 ABI_SYMBOLS = [
     "svbfm_create", "svbfm_destroy", "svbfm_last_error", "svbfm_abi_version", "svbfm_comm_get_unique_id",
-    "svbfm_comm_init", "svbfm_set_groups", "svbfm_set_csc", "svbfm_set_state", "svbfm_get_state",
+    "svbfm_comm_init", "svbfm_set_groups", "svbfm_set_csc", "svbfm_set_csr", "svbfm_transpose_csr", "svbfm_set_state", "svbfm_get_state",
     "svbfm_get_hyper", "svbfm_set_hyper", "svbfm_begin", "svbfm_vb_sweep", "svbfm_mcmc_sweep",
     "svbfm_vb_online_epoch", "svbfm_run", "svbfm_reset", "svbfm_predict", "svbfm_get_residuals", "svbfm_get_sum_t", "svbfm_set_residuals", "svbfm_copies_max_diff",
     "svbfm_get_info", "svbfm_set_stream", "svbfm_set_profile", "svbfm_get_profile", "svbfm_host_init_state", "svbfm_host_random_shuffle",
@@ -83,6 +83,8 @@ def lib():
         L.svbfm_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
         L.svbfm_set_groups.argtypes = [vp, u32p, C.c_uint32]
         L.svbfm_set_csc.argtypes = [vp, C.c_int32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+        L.svbfm_set_csr.argtypes = [vp, C.c_int32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+        L.svbfm_transpose_csr.argtypes = [C.c_int32, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp]
         L.svbfm_set_state.argtypes = [vp, C.c_double, C.c_double, vp, vp, vp, vp]
         L.svbfm_get_state.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), vp, vp, vp, vp]
         L.svbfm_get_hyper.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), vp, vp]
@@ -111,6 +113,19 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def transpose_csr(rowptr, feature_id, x, num_feature, device=0):
+    """Device transpose CSR -> CSC (colptr uint64[num_feature + 1], case_id uint32[nnz], x float32[nnz]): the .xt of a .x."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.uint64); feature_id = np.ascontiguousarray(feature_id, dtype=np.uint32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n, nnz = len(rowptr) - 1, int(rowptr[-1])
+    colptr, case_id, xt = np.zeros(int(num_feature) + 1, dtype=np.uint64), np.zeros(nnz, dtype=np.uint32), np.zeros(nnz, dtype=np.float32)
+    rc = lib().svbfm_transpose_csr(int(device), n, int(num_feature), _p(rowptr), _p(feature_id), _p(x), _p(colptr), _p(case_id), _p(xt))
+    if rc != 0:
+        msg = lib().svbfm_last_error(None)
+        raise SvbfmError(f"svbfm_transpose_csr failed ({rc}): {msg.decode() if msg else ''}")
+    return colptr, case_id, xt
 
 
 def host_init_state(seed, D, K, init_stdev=0.1, method=VB):
@@ -190,6 +205,17 @@ class Engine:
             self.n_train = data.num_cases
         elif split == TEST:
             self.n_test = data.num_cases
+
+    def set_csr(self, split, rowptr, feature_id, x, target, num_feature):
+        """The split row-wise (CSR of the cases, like a parsed text file or a binary .x file): the device builds the transposed matrix."""
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.uint64); feature_id = np.ascontiguousarray(feature_id, dtype=np.uint32)
+        x = np.ascontiguousarray(x, dtype=np.float32); target = np.ascontiguousarray(target, dtype=np.float32)
+        n = len(rowptr) - 1
+        self._ck(lib().svbfm_set_csr(self.h, split, n, int(num_feature), _p(rowptr), _p(feature_id), _p(x), _p(target)), "svbfm_set_csr")
+        if split == TRAIN:
+            self.n_train = n
+        elif split == TEST:
+            self.n_test = n
 
     def set_state(self, s):
         wm = np.ascontiguousarray(s["w_mean"], dtype=np.float64)

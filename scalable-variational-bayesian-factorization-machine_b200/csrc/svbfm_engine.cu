@@ -333,28 +333,32 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
 
 static int exchange_records(Engine* E, int run, const Run& r, double2* pf, const RecPlan* rp, bool mcmc) {
     cudaStream_t st = E->stream;
-    (void)r;
+    const std::vector<uint32_t>& blk = run ? E->blk1 : E->blk;
     RemoteRecArgs a{};
     if (E->p2p) {
         a.flags.n = E->world; a.flags.me = E->rank;
         for (int q = 0; q < E->world; q++) { a.flags.p[q] = reinterpret_cast<unsigned long long*>(E->peer_base[q]); a.src[q] = stage_of(E, E->peer_base[q], run); }
         a.epoch = ++E->xs_epoch;
     } else {
+        // no peer mappings: every rank broadcasts its block of the stage (blocks differ in size: one grouped collective)
         ProfScope pc(E, 10);
-        const size_t per = (size_t)E->slot_max[run] * 2;                       // doubles per rank
         double* base = reinterpret_cast<double*>(E->d_xstage);
-        int rc = g_nccl.AllGather(base + per * (size_t)E->rank, base, per, 8 /*ncclDouble*/, E->nccl_comm, st);
-        if (rc != 0) return fail(E, SVBFM_ERR_NCCL, std::string("ncclAllGather (columns): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+        int rc = g_nccl.GroupStart();
+        for (int q = 0; q < E->world && rc == 0; q++) {
+            const size_t off = (size_t)(blk[q] - r.col_begin) * 2, cnt = (size_t)(blk[q + 1] - blk[q]) * 2;      // doubles
+            if (cnt) rc = g_nccl.Broadcast(base + off, base + off, cnt, 8 /*ncclDouble*/, q, E->nccl_comm, st);
+        }
+        const int rc2 = g_nccl.GroupEnd();
+        if (rc == 0) rc = rc2;
+        if (rc != 0) return fail(E, SVBFM_ERR_NCCL, std::string("ncclBroadcast (columns): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
         for (int q = 0; q < E->world; q++) a.src[q] = E->d_xstage;
     }
     ProfScope pc(E, E->p2p ? 10 : 1);       // p2p: flags + fetch from the peers are the exchange
-    const std::vector<uint32_t>& blk = run ? E->blk1 : E->blk;
-    a.slot_max = E->slot_max[run]; a.world = E->world; a.me = E->rank;
-    for (int q = 0; q < E->world; q++) a.cnt[q] = blk[q + 1] - blk[q];
+    a.n = r.col_end - r.col_begin; a.world = E->world; a.me = E->rank;
+    for (int q = 0; q <= E->world; q++) a.bnd[q] = blk[q] - r.col_begin;
     a.col_of_slot = E->d_col_of_slot; a.stage_base = E->slot_base[run];
     a.pf = pf; a.p_next = rp->p_next; a.p_prev = rp->p_prev; a.rec_mode = rp->rec_mode; a.mcmc = mcmc ? 1 : 0; a.cpack = E->d_cpack;
-    const uint64_t nthreads = (uint64_t)E->world * E->slot_max[run];
-    if (nthreads) { k_records_remote<<<nblk(nthreads), 256, 0, st>>>(a); LAUNCHED(E); }
+    if (a.n) { k_records_remote<<<nblk(a.n), 256, 0, st>>>(a); LAUNCHED(E); }
     return 0;
 }
 
@@ -503,7 +507,7 @@ static int sweep_streams(Engine* E) {
         const bool lw = steps.back() < 0;
         launch_stream<MCMC, false, false>(E, 0, true, lw, true, lw);
         if (E->xs) {      // the first field's final means of the other ranks' blocks are not in the parameter tables yet: they are the records' own means
-            const uint32_t ns = (uint32_t)E->world * E->slot_max[0];
+            const uint32_t ns = E->slot_max[0];
             k_pack_h4_self<<<nblk(ns), 256, 0, st>>>(E->slot_base[0], E->slot_base[0] + ns, E->d_cpack); LAUNCHED(E);
         } else { k_pack_h4<<<nblk(r0.col_end - r0.col_begin), 256, 0, st>>>(r0.col_begin, r0.col_end, table(steps.back()), E->d_cpack); LAUNCHED(E); }
         launch_stream<MCMC, false, false>(E, 1, true, lw, false, false);
@@ -806,8 +810,11 @@ static int run_iterations(Engine* E, uint32_t n_iter, svbfm_iter_stats* out) {
     std::vector<DevStats> hs(n_iter);
     if (!rc) {
         cudaError_t e = cudaMemcpyAsync(hs.data(), E->d_stats, sizeof(DevStats) * n_iter, cudaMemcpyDeviceToHost, E->stream);
+        unsigned long long timeouts = 0;
+        if (e == cudaSuccess && E->p2p) e = cudaMemcpyAsync(&timeouts, E->d_xipc + 16 * 8, 8, cudaMemcpyDeviceToHost, E->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(E->stream);
         if (e != cudaSuccess) rc = fail(E, SVBFM_ERR_CUDA, std::string("iteration: ") + cudaGetErrorString(e));
+        else if (timeouts) rc = fail(E, SVBFM_ERR_NCCL, "peer exchange: a rank did not raise its flag (timed out); the results of this run are invalid");
     }
     if (!rc && out)
         for (uint32_t it = 0; it < n_iter; it++) {
@@ -1046,6 +1053,96 @@ int svbfm_set_csc(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_co
         SV_CUDA(E, cudaStreamSynchronize(E->stream));
     }
     return SVBFM_OK;
+}
+
+int svbfm_set_csr(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_cols, const uint64_t* rowptr, const uint32_t* feature_id, const float* x,
+                  const float* target) {
+    Engine* E = reinterpret_cast<Engine*>(h);
+    if (!E || !rowptr || (split != SVBFM_TRAIN && split != SVBFM_TEST && split != SVBFM_TRAIN_SECOND)) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csr: bad arguments");
+    if (E->begun) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csr after svbfm_begin");
+    const uint64_t nnz = rowptr[num_cases];
+    // local argument errors would leave the other ranks waiting in set_csc's collectives: hand an impossible shard on instead
+    std::string why;
+    if (rowptr[0] != 0) why = "svbfm_set_csr: rowptr[0] != 0";
+    else if (nnz >= (1ull << 32)) why = "svbfm_set_csr: more than 2^32-1 entries per rank are not supported";
+    else if (nnz > 0 && (!feature_id || !x)) why = "svbfm_set_csr: null entry arrays";
+    else if (num_cases > 0 && !target) why = "svbfm_set_csr: null target";
+    else for (uint32_t i = 0; i < num_cases && why.empty(); i++) if (rowptr[i + 1] < rowptr[i]) why = "svbfm_set_csr: rowptr not monotone";
+    if (!why.empty() && E->world <= 1) return fail(E, SVBFM_ERR_ARG, why);
+    SV_CUDA(E, cudaSetDevice(E->dev));
+    cudaStream_t st = E->stream;
+    uint64_t *d_rowptr = nullptr, *d_colptr = nullptr;
+    uint32_t *d_col = nullptr, *d_case = nullptr;
+    float *d_x = nullptr, *d_xt = nullptr, *d_y = nullptr;
+    struct Temps { std::vector<void**> v; ~Temps() { for (void** p : v) { sv_free(*p); *p = nullptr; } } } temps;
+    for (void** p : {(void**)&d_rowptr, (void**)&d_colptr, (void**)&d_col, (void**)&d_case, (void**)&d_x, (void**)&d_xt, (void**)&d_y}) temps.v.push_back(p);
+    std::vector<uint64_t> h_colptr((size_t)num_cols + 1, 0);
+    int rc = 0;
+    if (why.empty()) {
+        SV_CUDA(E, sv_malloc((void**)&d_rowptr, ((size_t)num_cases + 1) * 8));
+        SV_CUDA(E, sv_malloc((void**)&d_col, std::max<uint64_t>(nnz, 1) * 4));
+        SV_CUDA(E, sv_malloc((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4));
+        SV_CUDA(E, sv_malloc((void**)&d_y, std::max<size_t>(num_cases, 1) * 4));
+        SV_CUDA(E, cudaMemcpyAsync(d_rowptr, rowptr, ((size_t)num_cases + 1) * 8, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemcpyAsync(d_col, feature_id, nnz * 4, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemcpyAsync(d_y, target, (size_t)num_cases * 4, cudaMemcpyHostToDevice, st));
+        rc = transpose_on_device(E, st, num_cases, num_cols, nnz, d_rowptr, d_col, d_x, &d_colptr, &d_case, &d_xt);
+        if (rc) why = E->err;
+        else {
+            SV_CUDA(E, cudaMemcpyAsync(h_colptr.data(), d_colptr, ((size_t)num_cols + 1) * 8, cudaMemcpyDeviceToHost, st));
+            SV_CUDA(E, cudaStreamSynchronize(st));
+        }
+        sv_free(d_rowptr); d_rowptr = nullptr; sv_free(d_col); d_col = nullptr; sv_free(d_x); d_x = nullptr;
+    }
+    if (!why.empty()) {
+        if (E->world <= 1) return fail(E, SVBFM_ERR_ARG, why);
+        h_colptr.assign((size_t)num_cols + 1, 0); h_colptr[0] = 1;       // set_csc rejects it (colptr[0] != 0) together with the other ranks
+        int r2 = svbfm_set_csc(h, split, 0, num_cols, h_colptr.data(), nullptr, nullptr, nullptr);
+        (void)r2;
+        return fail(E, SVBFM_ERR_ARG, why);
+    }
+    // the CSC arrays are on the device already: svbfm_set_csc's copies find that out themselves (cudaMemcpyDefault)
+    return svbfm_set_csc(h, split, num_cases, num_cols, h_colptr.data(), d_case, d_xt, d_y);
+}
+
+int svbfm_transpose_csr(int32_t device, uint32_t num_cases, uint32_t num_cols, const uint64_t* rowptr, const uint32_t* feature_id, const float* x,
+                        uint64_t* out_colptr, uint32_t* out_case_id, float* out_x) {
+    if (!rowptr || !out_colptr) { g_create_error = "svbfm_transpose_csr: null argument"; return SVBFM_ERR_ARG; }
+    const uint64_t nnz = rowptr[num_cases];
+    if (nnz >= (1ull << 32) || (nnz && (!feature_id || !x || !out_case_id || !out_x))) { g_create_error = "svbfm_transpose_csr: bad arguments"; return SVBFM_ERR_ARG; }
+    svbfm_config c;
+    memset(&c, 0, sizeof(c));
+    c.struct_size = sizeof(c); c.method = SVBFM_VB; c.num_attribute = 1; c.num_factor = 0; c.device = device;
+    svbfm_t* h = nullptr;
+    int rc = svbfm_create(&h, &c);        // device checks, stream, block cache
+    if (rc) return rc;
+    Engine* E = reinterpret_cast<Engine*>(h);
+    cudaStream_t st = E->stream;
+    uint64_t *d_rowptr = nullptr, *d_colptr = nullptr;
+    uint32_t *d_col = nullptr, *d_case = nullptr;
+    float *d_x = nullptr, *d_xt = nullptr;
+    auto body = [&]() -> int {
+        SV_CUDA(E, sv_malloc((void**)&d_rowptr, ((size_t)num_cases + 1) * 8));
+        SV_CUDA(E, sv_malloc((void**)&d_col, std::max<uint64_t>(nnz, 1) * 4));
+        SV_CUDA(E, sv_malloc((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4));
+        SV_CUDA(E, cudaMemcpyAsync(d_rowptr, rowptr, ((size_t)num_cases + 1) * 8, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemcpyAsync(d_col, feature_id, nnz * 4, cudaMemcpyHostToDevice, st));
+        SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, st));
+        if (int r = transpose_on_device(E, st, num_cases, num_cols, nnz, d_rowptr, d_col, d_x, &d_colptr, &d_case, &d_xt)) return r;
+        SV_CUDA(E, cudaMemcpyAsync(out_colptr, d_colptr, ((size_t)num_cols + 1) * 8, cudaMemcpyDeviceToHost, st));
+        if (nnz) {
+            SV_CUDA(E, cudaMemcpyAsync(out_case_id, d_case, nnz * 4, cudaMemcpyDeviceToHost, st));
+            SV_CUDA(E, cudaMemcpyAsync(out_x, d_xt, nnz * 4, cudaMemcpyDeviceToHost, st));
+        }
+        SV_CUDA(E, cudaStreamSynchronize(st));
+        return 0;
+    };
+    rc = body();
+    if (rc) g_create_error = E->err;
+    for (void* p : {(void*)d_rowptr, (void*)d_colptr, (void*)d_col, (void*)d_case, (void*)d_x, (void*)d_xt}) sv_free(p);
+    svbfm_destroy(h);
+    return rc;
 }
 
 int svbfm_set_state(svbfm_t* h, double w0_mean, double w0_var, const double* w_mean, const double* w_var, const double* v_mean,

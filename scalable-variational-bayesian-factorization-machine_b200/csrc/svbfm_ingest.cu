@@ -357,10 +357,10 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         SV_CUDA(E, cudaStreamWaitEvent(cs, E->copy_event, 0));
     }
     SV_CUDA(E, cudaMemcpyAsync(S.colptr, S.h_colptr.data(), ((size_t)S.ncols_ext + 1) * 8, cudaMemcpyHostToDevice, st));
-    SV_CUDA(E, cudaMemcpyAsync(S.crow, case_id, nnz * 4, cudaMemcpyHostToDevice, st));
-    SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, cs));
+    SV_CUDA(E, cudaMemcpyAsync(S.crow, case_id, nnz * 4, cudaMemcpyDefault, st));
+    SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyDefault, cs));
     if (nnz) k_any_not_one<<<std::min<unsigned>(nblk(nnz), 148 * 16), 256, 0, cs>>>(d_x, nnz, d_flags + 0);
-    SV_CUDA(E, cudaMemcpyAsync(S.y, target, (size_t)n * 4, cudaMemcpyHostToDevice, cs));
+    SV_CUDA(E, cudaMemcpyAsync(S.y, target, (size_t)n * 4, cudaMemcpyDefault, cs));
     if (nnz) k_check_case_ids<<<nblk(nnz), 256, 0, st>>>(S.crow, nnz, n, d_flags + 1);
     // CSC -> CSR: feature id per entry, stable sort by case id
     uint32_t *d_colof = nullptr, *d_idx = nullptr, *d_skeys = nullptr, *d_sidx = nullptr;
@@ -702,6 +702,60 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     return 0;
 }
 
+// ---- device transpose: CSR (cases x features, the reference's `data`) -> CSC (features x cases, `data_t`) ------------------
+// Replaces Data::create_data_t (Data.h:457-509) and tools/transpose.cpp:91-162 on the device: entry -> case id (search over the
+// row pointer), one STABLE radix sort of the entries by feature id (cases stay ascending inside a feature, duplicates keep their
+// order: the same bytes as the reference's counting transpose), column pointer by a search over the sorted keys.
+static __global__ void k_row_of_entry(const uint64_t* __restrict__ rowptr, uint32_t n, uint64_t nnz, uint32_t* __restrict__ out) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    uint32_t lo = 0, hi = n;          // rowptr[lo] <= p < rowptr[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (rowptr[mid] <= p) lo = mid; else hi = mid;
+    }
+    out[p] = lo;
+}
+static __global__ void k_check_below(const uint32_t* __restrict__ v, uint64_t n, uint32_t bound, uint32_t* flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && v[i] >= bound) *flag = 1;
+}
+
+// d_rowptr / d_col / d_x: device CSR. Outputs (device, sv_malloc'ed, owned by the caller): column pointer [ncols + 1], case ids, values
+int transpose_on_device(Engine* E, cudaStream_t st, uint32_t n, uint32_t ncols, uint64_t nnz, const uint64_t* d_rowptr, const uint32_t* d_col, const float* d_x,
+                        uint64_t** d_colptr, uint32_t** d_case, float** d_xt) {
+    *d_colptr = nullptr; *d_case = nullptr; *d_xt = nullptr;
+    uint32_t *d_row = nullptr, *d_idx = nullptr, *d_skeys = nullptr, *d_sidx = nullptr, *d_flag = nullptr;
+    struct Temps { std::vector<void**> v; ~Temps() { for (void** p : v) { sv_free(*p); *p = nullptr; } } } temps;
+    for (void** p : {(void**)&d_row, (void**)&d_idx, (void**)&d_skeys, (void**)&d_sidx, (void**)&d_flag}) temps.v.push_back(p);
+    cudaStream_t keep = E->stream;
+    struct StreamGuard { Engine* E; cudaStream_t s; ~StreamGuard() { E->stream = s; } } guard{E, keep};
+    E->stream = st;                                    // sort_pairs works on the engine's stream
+    SV_CUDA(E, sv_malloc((void**)d_colptr, ((size_t)ncols + 1) * 8));
+    SV_CUDA(E, sv_malloc((void**)d_case, std::max<uint64_t>(nnz, 1) * 4));
+    SV_CUDA(E, sv_malloc((void**)d_xt, std::max<uint64_t>(nnz, 1) * 4));
+    SV_CUDA(E, sv_malloc((void**)&d_flag, 4));
+    SV_CUDA(E, cudaMemsetAsync(d_flag, 0, 4, st));
+    if (nnz) {
+        SV_CUDA(E, sv_malloc((void**)&d_row, nnz * 4));
+        SV_CUDA(E, sv_malloc((void**)&d_idx, nnz * 4));
+        k_row_of_entry<<<nblk(nnz), 256, 0, st>>>(d_rowptr, n, nnz, d_row);
+        k_check_below<<<nblk(nnz), 256, 0, st>>>(d_col, nnz, ncols, d_flag);
+        k_iota<<<nblk(nnz), 256, 0, st>>>(d_idx, nnz);
+        uint32_t bad = 0;
+        SV_CUDA(E, cudaMemcpyAsync(&bad, d_flag, 4, cudaMemcpyDeviceToHost, st));
+        SV_CUDA(E, cudaStreamSynchronize(st));
+        if (bad) return fail(E, SVBFM_ERR_ARG, "feature id out of range in transpose");
+        if (int rc = sort_pairs(E, d_col, d_idx, nnz, std::max<uint32_t>(ncols, 1), &d_skeys, &d_sidx)) return rc;
+        k_gather_u32<<<nblk(nnz), 256, 0, st>>>(d_row, d_sidx, nnz, *d_case);
+        k_gather_f32<<<nblk(nnz), 256, 0, st>>>(d_x, d_sidx, nnz, *d_xt);
+        k_rowptr_from_sorted<<<nblk((uint64_t)ncols + 1), 256, 0, st>>>(d_skeys, nnz, ncols, *d_colptr);
+    } else SV_CUDA(E, cudaMemsetAsync(*d_colptr, 0, ((size_t)ncols + 1) * 8, st));
+    SV_CUDA(E, cudaStreamSynchronize(st));
+    SV_CUDA(E, cudaGetLastError());
+    return 0;
+}
+
 // ---- cross shards: the second residual copy on its own shard (svbfm_set_csc(SVBFM_TRAIN_SECOND); svbfm_internal.h Engine::xs) ----
 void set_side_views(Engine* E) {
     const DevSplit& S = E->tr;
@@ -734,17 +788,14 @@ void free_second(Engine* E) {
     E->blk1.clear();
 }
 
-struct BlockTable { uint32_t blk[17]; int world; };
-// common record slots of the cross-shard layout: field f, block r, position k inside the block -> base[f] + r * max[f] + k.
-// First field: k = column - block start. Second field: the same, unless `ranked` (then only the columns OUTSIDE this
-// rank's block are zeroed here; the own block is filled by k_slot_scatter and the ranks' pieces are summed)
-static __global__ void k_xs_slots(uint32_t c0, uint32_t c1, BlockTable bt, uint32_t base, uint32_t mx, int zero_only, uint32_t* __restrict__ slot) {
+// common record slots of the cross-shard layout: field f, column j -> base[f] + (j - first column of the field): the blocks of a
+// field are contiguous column ranges, so every rank's block is one contiguous run of slots (no padding). Second field with
+// `ranked`: the columns OUTSIDE this rank's block are zeroed here, the own block is ordered by popularity (k_slot_scatter) and the
+// ranks' pieces are summed.
+static __global__ void k_xs_slots(uint32_t c0, uint32_t c1, uint32_t base, int zero_only, uint32_t* __restrict__ slot) {
     uint32_t j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= c1) return;
-    if (zero_only) { slot[j] = 0; return; }
-    int r = 0;
-    while (r + 1 < bt.world && j >= bt.blk[r + 1]) r++;
-    slot[j] = base + (uint32_t)r * mx + (j - bt.blk[r]);
+    slot[j] = zero_only ? 0u : base + (j - c0);
 }
 static __global__ void k_invert_slots(const uint32_t* __restrict__ slot, uint32_t c0, uint32_t c1, uint32_t* __restrict__ col_of_slot) {
     uint32_t j = c0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -909,23 +960,17 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
         if (dev_alloc(E, &E->sec.y, 1)) return SVBFM_ERR_OOM;
     }
 
-    // ---- common record slots: slot-contiguous blocks, padded to the largest block, so that the records of a field travel by
-    // one in-place allgather. Second field: inside a block by popularity (descending column length, known to the block's owner)
-    BlockTable b0{}, b1{};
-    b0.world = b1.world = E->world;
-    uint32_t mx0 = 1, mx1 = 1;
-    for (int r = 0; r <= E->world; r++) { b0.blk[r] = E->blk[r]; b1.blk[r] = E->blk1[r]; }
-    for (int r = 0; r < E->world; r++) { mx0 = std::max(mx0, E->blk[r + 1] - E->blk[r]); mx1 = std::max(mx1, E->blk1[r + 1] - E->blk1[r]); }
-    E->slot_base[0] = 0; E->slot_max[0] = mx0;
-    E->slot_base[1] = (uint32_t)E->world * mx0; E->slot_max[1] = mx1;
-    const size_t total_slots = (size_t)E->world * ((size_t)mx0 + mx1);
-    if (total_slots >= (1ull << 32)) { free_second(E); return fail(E, SVBFM_ERR_ARG, "set_csc(TRAIN_SECOND): too many record slots"); }
+    // ---- common record slots: the fields one after the other in column order, so that a rank's block is a contiguous run of slots.
+    // Second field: inside a block by popularity (descending column length, known to the block's owner)
+    const uint32_t nc0 = r0.col_end - r0.col_begin, nc1 = r1.col_end - r1.col_begin;
+    E->slot_base[0] = 0; E->slot_base[1] = nc0;
+    E->slot_max[0] = nc0; E->slot_max[1] = nc1;      // slots of the field
+    const size_t total_slots = (size_t)nc0 + nc1;
     SV_CUDA(E, sv_malloc((void**)&d_new, (size_t)E->D * 4));
     SV_CUDA(E, cudaMemsetAsync(d_new, 0, (size_t)E->D * 4, st));
-    const uint32_t nc0 = r0.col_end - r0.col_begin, nc1 = r1.col_end - r1.col_begin;
-    if (nc0) k_xs_slots<<<nblk(nc0), 256, 0, st>>>(r0.col_begin, r0.col_end, b0, E->slot_base[0], mx0, 0, d_new);
+    if (nc0) k_xs_slots<<<nblk(nc0), 256, 0, st>>>(r0.col_begin, r0.col_end, E->slot_base[0], 0, d_new);
     const bool ranked = E->want_rec_rank;
-    if (nc1) k_xs_slots<<<nblk(nc1), 256, 0, st>>>(r1.col_begin, r1.col_end, b1, E->slot_base[1], mx1, ranked ? 1 : 0, d_new);
+    if (nc1) k_xs_slots<<<nblk(nc1), 256, 0, st>>>(r1.col_begin, r1.col_end, E->slot_base[1], ranked ? 1 : 0, d_new);
     if (ranked) {
         const uint32_t c0 = E->blk1[E->rank], nb = E->blk1[E->rank + 1] - c0;
         if (nb) {
@@ -934,7 +979,7 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
             SV_CUDA(E, sv_malloc((void**)&d_sv, (size_t)nb * 4));
             k_slot_keys<<<nblk(nb), 256, 0, st>>>(E->sec.colptr, c0, nb, d_sk, d_sv);
             int rc = sort_pairs(E, d_sk, d_sv, nb, 1ull << 32, &d_ks, &d_vs);
-            if (!rc) { k_slot_scatter<<<nblk(nb), 256, 0, st>>>(d_vs, E->slot_base[1] + (uint32_t)E->rank * mx1, nb, d_new); cudaStreamSynchronize(st); }
+            if (!rc) { k_slot_scatter<<<nblk(nb), 256, 0, st>>>(d_vs, E->slot_base[1] + (c0 - r1.col_begin), nb, d_new); cudaStreamSynchronize(st); }
             sv_free(d_sk); sv_free(d_sv); sv_free(d_ks); sv_free(d_vs);
             if (rc) return rc;
         }
@@ -965,7 +1010,7 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
         if (sv_malloc((void**)&E->d_cpack, total_slots * 32 /* sizeof(ColPack) */) != cudaSuccess) return fail(E, SVBFM_ERR_OOM, "cudaMalloc: record slots");
         E->cpack_cap = total_slots;
     }
-    if (int rc = setup_exchange(E, (size_t)E->world * std::max(mx0, mx1))) return rc;
+    if (int rc = setup_exchange(E, std::max<size_t>(std::max(nc0, nc1), 1))) return rc;
     // ---- tiles of the second side on the new shard (the first side keeps its own), second residual copy, tile sums
     const uint64_t TS = 1ull << E->ts_shift;
     std::vector<uint32_t> heavy;

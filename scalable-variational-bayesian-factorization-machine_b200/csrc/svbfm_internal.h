@@ -234,7 +234,7 @@ struct Engine {
         uint32_t* rcol = nullptr;          // [n][2] {first-field column, second-field column} of every entry (re-prediction)
         float* y = nullptr;                // [n] targets in entry order
     } sec;
-    uint32_t slot_base[2] = {0, 0}, slot_max[2] = {0, 0};   // record slots of field f: [slot_base[f] + r * slot_max[f], + block size) for rank r
+    uint32_t slot_base[2] = {0, 0}, slot_max[2] = {0, 0};   // record slots of field f: [slot_base[f], + slot_max[f]) in column order of the blocks (no padding)
     size_t cpack_cap = 0;             // records allocated in d_cpack
     // {new mean, new var} of the columns finalized in a step, slot order. One device allocation holds 16 flag words and two such
     // stages (one per field). A rank's k_finalize leaves its block in its own stage; when the ranks can map each other's
@@ -244,7 +244,7 @@ struct Engine {
     uint32_t* d_col_of_slot = nullptr; // [slots of both fields] column of every record slot (padding: unused)
     unsigned char* d_xipc = nullptr;  // [256 B flags | stage 0 | stage 1]
     double2* d_xstage = nullptr;      // stage 0 (inside d_xipc)
-    size_t xstage_cap = 0;            // columns per stage: world * max(slot_max)
+    size_t xstage_cap = 0;            // columns per stage: the larger field
     bool p2p = false;
     unsigned char* peer_base[16] = {nullptr};   // [world] rank r's allocation as mapped here (own: d_xipc)
     uint64_t xs_epoch = 0;            // exchanges done: the value a rank writes into the others' flag words when its stores of an exchange are out
@@ -264,6 +264,8 @@ void set_side_views(Engine* E);
 int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t num_cases, uint32_t num_cols, const uint64_t* colptr,
                  const uint32_t* case_id, const float* x, const float* target);
 void free_split(Engine* E, DevSplit& S);
+int transpose_on_device(Engine* E, cudaStream_t st, uint32_t num_cases, uint32_t num_cols, uint64_t nnz, const uint64_t* d_rowptr, const uint32_t* d_col,
+                        const float* d_x, uint64_t** d_colptr, uint32_t** d_case, float** d_xt);      // svbfm_ingest.cu: CSR -> CSC on the device
 int stream_tile_cols(Engine* E);   // svbfm_engine.cu: first column of every implicit tile (k_tile_col0)
 int allreduce(Engine* E, void* buf, size_t count, int dtype /*nccl*/, int op /*nccl*/);
 int detect_exclusive_blocks(Engine* E);   // svbfm_engine.cu; collective (every rank calls it after the train split is in)

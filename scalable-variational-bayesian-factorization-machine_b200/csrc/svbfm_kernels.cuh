@@ -633,6 +633,7 @@ __device__ __forceinline__ void entry_terms(double ei, float xf, float xof, cons
 // Used by the TMA variant of k_stream. Under tests/emu the copy happens at issue and the barrier keeps the same
 // phase / transaction arithmetic, so that a wait on a stage that was never armed shows up as a deadlock.
 #if defined(SVBFM_EMULATED)
+#include <sched.h>
 struct SvMbar { uint32_t phase, pending, init; int64_t tx; };
 static inline void sv_mbar_init(SvMbar* b, uint32_t count) { b->phase = 0; b->pending = count; b->init = count; b->tx = 0; }
 static inline void sv_mbar_flip(SvMbar* b) { if (b->pending == 0 && b->tx == 0) { b->phase ^= 1; b->pending = b->init; } }
@@ -1731,8 +1732,8 @@ __global__ void k_pack_h4(uint32_t c0, uint32_t c1, const double2* __restrict__ 
 // record of the column for the passes that follow (write_records) -- and brings its parameter table up to date. The tables stay
 // complete and bit-identical on every rank without a block exchange at the end of the iteration.
 struct RemoteRecArgs {
-    uint32_t slot_max;           // slots per block; the field's stage is [world][slot_max]
-    uint32_t cnt[16];            // columns in rank q's block
+    uint32_t n;                  // slots (= columns) of the field; the field's stage is [n] in slot order
+    uint32_t bnd[17];            // rank q's block is the slots [bnd[q], bnd[q + 1])
     int world, me;
     const uint32_t* col_of_slot; // [slots of both fields] column of every record slot
     const double2* src[16];      // rank q's stage: its own block is current there (p2p: the peer's memory; else the local allgather buffer)
@@ -1756,15 +1757,22 @@ __global__ void __launch_bounds__(256) k_records_remote(RemoteRecArgs a) {
         }
         if (t < a.flags.n && t != a.flags.me) {
             volatile unsigned long long* f = a.flags.p[a.flags.me] + t;
-            while (*f < a.epoch) {}
+#if defined(SVBFM_EMULATED)
+            while (*f < a.epoch) sched_yield();
+#else
+            // a rank that died never raises its flag: give up after ~20 s of polling (an L2 round trip each) instead of hanging the
+            // GPU; word 16 of the own flag block counts the timeouts and the host turns them into SVBFM_ERR_NCCL
+            unsigned long long polls = 0;
+            while (*f < a.epoch) if (++polls > (1ull << 25)) { atomicAdd(a.flags.p[a.flags.me] + 16, 1ull); break; }
+#endif
         }
-        __syncthreads();
-        __threadfence_system();
+        __syncthreads();       // the fetches below depend on the flag values through this barrier and bypass L1: no fence needed
     }
-    // one thread per slot of the OTHER ranks' blocks, in slot order: the fetch from a peer's memory is coalesced
+    // one thread per slot of the field, in slot order: the fetch from a peer's memory is coalesced; the own block is done already
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t q = t / a.slot_max, k = t - q * a.slot_max;
-    if (q >= (uint32_t)a.world || q == (uint32_t)a.me || k >= a.cnt[q]) return;
+    if (t >= a.n || (t >= a.bnd[a.me] && t < a.bnd[a.me + 1])) return;
+    int q = 0;
+    while (q + 1 < a.world && t >= a.bnd[q + 1]) q++;
     const uint32_t sj = a.stage_base + t;
     const uint32_t j = a.col_of_slot[sj];
     const double2 nw = __ldcg(a.src[q] + t), old = a.pf[j];          // written by another GPU: not through L1

@@ -322,6 +322,10 @@ inline void parse_text_file(const std::string& filename, ParsedText& out, bool k
 
 struct DataSet {
     bool has_x = true, has_xt = true;
+    // device_transpose: the learner takes the cases row-wise (svbfm_set_csr) and the DEVICE builds the transposed matrix (SURVEY
+    // section 8f rank 1): a text file is parsed into `x` only, binary input needs <name>.x + <name>.y only (<name>.xt is used when
+    // it is there: nothing to transpose then). csr_only says which of the two the load ended with.
+    bool device_transpose = false, csr_only = false;
     SparseMatrix x;       // cases x features (CSR of X)
     SparseMatrix xt;      // features x cases (CSC of X), case ids ascending inside a feature
     std::vector<float> target;
@@ -388,7 +392,8 @@ struct DataSet {
         if (!forced_num_feature)
             std::cout << "num_rows=" << x.num_rows << "\tnum_values=" << x.nnz() << "\tnum_features=" << num_feature << "\tmin_target=" << min_target
                       << "\tmax_target=" << max_target << std::endl;
-        if (has_xt) transpose(x, (uint32_t)num_feature, xt);
+        csr_only = device_transpose;
+        if (has_xt && !csr_only) transpose(x, (uint32_t)num_feature, xt);
     }
 
     // Data::load (Data.h:106-171): binary files next to `filename` win over the text file
@@ -396,6 +401,21 @@ struct DataSet {
         int from = 0;
         if ((!has_x || file_exists(filename + ".data")) && (!has_xt || file_exists(filename + ".datat")) && file_exists(filename + ".target")) from = 1;
         else if ((!has_x || file_exists(filename + ".x")) && (!has_xt || file_exists(filename + ".xt")) && file_exists(filename + ".y")) from = 2;
+        csr_only = false;
+        if (from == 0 && device_transpose) {      // the rows alone will do: <name>.data / <name>.x without the transposed file
+            const bool legacy = file_exists(filename + ".data") && file_exists(filename + ".target");
+            if (legacy || (file_exists(filename + ".x") && file_exists(filename + ".y"))) {
+                read_y_file(filename + (legacy ? ".target" : ".y"), target);
+                read_x_file(filename + (legacy ? ".data" : ".x"), x);
+                if (target.size() != x.num_rows) throw std::string("target and data disagree on the number of cases");
+                num_feature = (int)x.num_cols;
+                csr_only = true;
+                scan_targets();
+                std::cout << "num_cases=" << num_cases << "\tnum_values=" << x.nnz() << "\tnum_features=" << num_feature << "\tmin_target=" << min_target
+                          << "\tmax_target=" << max_target << std::endl;
+                return;
+            }
+        }
         if (from == 0) { load_text(filename); return; }
         read_y_file(filename + (from == 1 ? ".target" : ".y"), target);
         uint64_t num_values = 0;

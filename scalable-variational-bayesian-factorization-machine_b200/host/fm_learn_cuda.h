@@ -206,6 +206,14 @@ protected:
 
     // hands data_t + target of this rank's shard of cases to the engine
     void push(int split, DataSet& d) {
+        if (d.csr_only) {       // rows as loaded: a rank's shard is a slice of the row pointer; the device transposes (svbfm_set_csr)
+            const uint32_t lo = (uint32_t)((uint64_t)d.num_cases * shard.rank / shard.world), hi = (uint32_t)((uint64_t)d.num_cases * (shard.rank + 1) / shard.world);
+            const uint64_t e0 = d.x.ptr[lo];
+            std::vector<uint64_t> rp(d.x.ptr.begin() + lo, d.x.ptr.begin() + hi + 1);
+            for (uint64_t& v : rp) v -= e0;
+            ck(svbfm_set_csr(h_, split, hi - lo, (uint32_t)d.num_feature, rp.data(), d.x.id.data() + e0, d.x.val.data() + e0, d.target.data() + lo), "svbfm_set_csr");
+            return;
+        }
         if (shard.world <= 1) {
             ck(svbfm_set_csc(h_, split, d.num_cases, d.xt.num_rows, d.xt.ptr.data(), d.xt.id.data(), d.xt.val.data(), d.target.data()), "svbfm_set_csc");
             return;

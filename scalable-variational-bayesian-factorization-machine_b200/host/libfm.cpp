@@ -135,6 +135,8 @@ int main(int argc, char** argv) {
 
         bool is_mcmc = method == "mcmc";
         DataSet train(!is_mcmc, true), test(!is_mcmc, true);     // libfm.cpp:137-146
+        // the transposed matrix is built on the device unless a <name>.xt is there already (SVBFM_HOST_TRANSPOSE=1: on the host, as before)
+        train.device_transpose = test.device_transpose = (method != "vb_online") && !getenv("SVBFM_HOST_TRANSPOSE");
         if (method != "vb_online") {
             std::cout << "Loading train...\t" << std::endl;
             train.load(cmd.get(p_train));

@@ -127,3 +127,37 @@ def test_cli_save_and_load_model_resume_bit_for_bit(built, tmp_path):
     other = [EXE, "-task", "r", "-train", "train", "-test", "test", "-dim", "1,1,2", "-method", "vb", "-iter", "1", "-load_model", "model.bin"]
     p = subprocess.run(other, cwd=tmp_path, capture_output=True, text=True)
     assert "ERROR" in p.stderr and "dimensions" in p.stderr
+
+
+@pytest.mark.parametrize("name", ["g1_train", "g2_train"])
+def test_transpose_tool_on_the_device_writes_the_reference_bytes(built, tmp_path, name):
+    """`transpose --device 0` (svbfm_transpose_csr: entry -> case id, one stable radix sort by feature id on the
+    GPU) writes the .xt the unmodified reference tool wrote (tests/golden/*.xt), byte for byte."""
+    BIN = os.path.join(sv.PKG_DIR, "bin")
+    env = dict(os.environ, SVBFM_LIB=sv.LIB_PATH)
+    p = subprocess.run([os.path.join(BIN, "transpose"), "--ifile", os.path.join(G, name + ".x"), "--ofile", str(tmp_path / "out.xt"), "--device", "0"],
+                       capture_output=True, text=True, env=env)
+    assert p.returncode == 0 and not p.stderr.strip(), p.stderr
+    assert open(tmp_path / "out.xt", "rb").read() == open(os.path.join(G, name + ".xt"), "rb").read()
+
+
+def test_cli_rows_only_binary_input_is_transposed_on_the_device(built, tmp_path):
+    """`-train name` with only name.x + name.y next to it (no name.xt): the CLI hands the rows to svbfm_set_csr and the device builds the
+    transposed matrix; text input takes the same route. Same numbers as the reference's run on the text file; with SVBFM_HOST_TRANSPOSE=1
+    (host transpose + svbfm_set_csc, the round-1 path) the files are identical."""
+    c = GOLD[0]
+    BIN = os.path.join(sv.PKG_DIR, "bin")
+    for s in ("train", "test"):
+        src = os.path.join(G, f"{c['data']}_{s}.libfm")
+        shutil.copy(src, tmp_path / (s + ".txt"))
+        subprocess.run([os.path.join(BIN, "convert"), "--ifile", src, "--ofilex", str(tmp_path / f"{s}.x"), "--ofiley", str(tmp_path / f"{s}.y")],
+                       check=True, capture_output=True)
+    base = ["-task", "r", "-dim", c["dim"], "-method", "vb", "-iter", "3", "-seed", str(c["seed"])]
+    outs = []
+    for train, test, env in (("train", "test", {}), ("train.txt", "test.txt", {}), ("train.txt", "test.txt", {"SVBFM_HOST_TRANSPOSE": "1"})):
+        p = subprocess.run([EXE, "-train", train, "-test", test] + base, cwd=tmp_path, capture_output=True, text=True, env=dict(os.environ, **env))
+        assert "ERROR" not in p.stderr, p.stderr
+        outs.append((open(tmp_path / "test_rmse_114_vb").read(), open(tmp_path / "free_energy_114_vb").read()))
+    assert outs[0] == outs[1] == outs[2]
+    for a, b in zip([float(x) for x in outs[0][0].split()], c["test_rmse"][:3]):
+        assert abs(a - b) <= TOL * b

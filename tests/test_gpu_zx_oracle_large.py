@@ -1,0 +1,83 @@
+"""-m gpu: oracle comparisons at sizes the small parity cases do not reach ("what's weak" 3 and 4).
+
+* VB on the MovieLens-1M shape (1 M ratings, 6040 x 3952, K = 20) for three iterations against the C oracle, with the tile sizes the engine
+  picks itself (256 entries at this size) and with 4096-entry tiles (the size of the 200 M runs): the heaviest users span hundreds of tiles,
+  so k_combine_span, the light spans of k_finalize and the windows of k_stream all run on real column lengths. About 15 s of oracle time.
+* MCMC hyper-parameter draws (k_mcmc_hyper: alpha, lambda_w, lambda_v[f]; mcmc.h:901-1089): their means over sweeps 10..30 against three
+  oracle seeds. The engine draws from Philox, the oracle from libc rand(): matched in distribution, so the bound is the oracle's own
+  seed-to-seed spread plus a few percent; a Gamma shape or rate that is off by a factor fails by a wide margin."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import svbfm_b200 as sv
+from helpers import make_learner, rel, to_csc, two_field
+
+pytestmark = pytest.mark.gpu
+synth = sv.submodule("synth")
+
+
+@pytest.mark.parametrize("tile_entries", [0, 4096])
+def test_vb_ml1m_shape_against_the_oracle(built, tile_entries):
+    U, I, N, Nt, K = synth.SHAPES["ml1m"]
+    model = synth.planted_model(U, I, 901)
+    u, i, y = synth.ratings(N, U, I, model, 902)
+    ut, it, yt = synth.ratings(Nt, U, I, model, 903)
+    tr, te = ob.Csr(*synth.to_csr(u, i, y, U)), ob.Csr(*synth.to_csr(ut, it, yt, U))
+    L = make_learner("vb", tr, te, K, num_iter=3, tile_entries=tile_entries)
+    hist = L.learn(to_csc(tr), to_csc(te))
+    info = L.engine.info()
+    assert info["fused_schedule"] & 1
+    top_user = int(np.bincount(u).max())
+    assert top_user > 8 * (tile_entries or 256), "the heaviest column must span more tiles than the light-span limit"
+    orc = ob.Oracle("vb", tr, te, K=K, seed=42)
+    for k, s in enumerate(hist):
+        o = orc.iterate()
+        for name in ("test_rmse", "train_stat", "free_energy", "alpha"):
+            assert rel(getattr(s, name), getattr(o, name)) < 1e-7, (k, name, getattr(s, name), getattr(o, name))
+    so, sg = orc.get_state(), L.engine.get_state()
+    for name in ("w_mean", "w_var", "v_mean", "v_var"):
+        assert np.max(np.abs(so[name] - sg[name])) < 1e-9, name
+    e_orc, _ = orc.get_train_cache(want_t=False)
+    assert np.max(np.abs(e_orc - L.engine.get_residuals())) < 1e-9
+    assert L.engine.copies_max_diff() == 0.0
+    L.engine.close()
+
+
+def test_mcmc_hyper_parameter_trajectories(built):
+    tr, te = two_field(200000, 20000, 1000, 800, seed=27)
+    K, first, last = 4, 10, 30
+    D = max(tr.n_feat, te.n_feat) + 1
+
+    def means(traj):
+        a = np.asarray(traj[first:last])
+        return a.mean(0)
+
+    per_seed = []
+    for seed in (42, 43, 44):
+        orc = ob.Oracle("mcmc", tr, te, K=K, seed=seed)
+        t = []
+        for _ in range(last):
+            orc.iterate()
+            h = orc.get_hyper()
+            t.append([h["alpha"], h["sigma_w"][0]] + list(h["sigma_v"][0]))
+        per_seed.append(means(t))
+    per_seed = np.asarray(per_seed)
+    E = sv.Engine("mcmc", D, K, 1, 1, float(tr.y.min()), float(tr.y.max()), seed=42)
+    E.set_csc(sv.TRAIN, to_csc(tr)); E.set_csc(sv.TEST, to_csc(te))
+    E.set_state(sv.host_init_state(42, D, K, 0.1, sv.MCMC)); E.begin()
+    t = []
+    for _ in range(last):
+        E.run(1)
+        h = E.get_hyper()
+        t.append([h["alpha"], h["sigma_w"][0]] + list(h["sigma_v"][0]))
+    E.close()
+    got, want, spread = means(t), per_seed.mean(0), per_seed.max(0) - per_seed.min(0)
+    names = ["alpha", "lambda_w"] + [f"lambda_v[{f}]" for f in range(K)]
+    # the factors of a sampled run are exchangeable: compare lambda_v as a sorted set, alpha and lambda_w one to one
+    got_v, want_v = np.sort(got[2:]), np.sort(want[2:])
+    for k in range(2):
+        assert abs(got[k] - want[k]) <= 0.03 * abs(want[k]) + 3 * spread[k], (names[k], got[k], want[k], spread[k])
+    for a, b in zip(got_v, want_v):
+        assert abs(a - b) <= 0.25 * abs(b) + 3 * float(spread[2:].max()), ("lambda_v", got_v, want_v, spread[2:])
+    assert abs(got_v.mean() - want_v.mean()) <= 0.10 * want_v.mean() + 2 * float(spread[2:].max()), (got_v, want_v)
