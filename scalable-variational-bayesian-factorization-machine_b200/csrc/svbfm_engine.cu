@@ -358,7 +358,9 @@ static int exchange_records(Engine* E, int run, const Run& r, double2* pf, const
     for (int q = 0; q <= E->world; q++) a.bnd[q] = blk[q] - r.col_begin;
     a.col_of_slot = E->d_col_of_slot; a.stage_base = E->slot_base[run];
     a.pf = pf; a.p_next = rp->p_next; a.p_prev = rp->p_prev; a.rec_mode = rp->rec_mode; a.mcmc = mcmc ? 1 : 0; a.cpack = E->d_cpack;
-    if (a.n) { k_records_remote<<<nblk(a.n), 256, 0, st>>>(a); LAUNCHED(E); }
+    const uint32_t n_remote = a.n - (a.bnd[E->rank + 1] - a.bnd[E->rank]);
+    // (launched even without remote slots: the flags of an exchange are raised and awaited by every rank)
+    if (a.n) { k_records_remote<<<std::max(1u, nblk(n_remote)), 256, 0, st>>>(a); LAUNCHED(E); }
     return 0;
 }
 

@@ -950,7 +950,8 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
     if (!excl1 || (uint64_t)tot != E->n_total) {
         free_second(E);
         return fail(E, SVBFM_ERR_ARG, !excl1 ? "set_csc(TRAIN_SECOND): the ranks' shards must cover disjoint, rank-ordered blocks of the second field's columns"
-                                             : "set_csc(TRAIN_SECOND): the second shards do not hold the same number of cases as the train split");
+                                             : "set_csc(TRAIN_SECOND): the second shards hold " + std::to_string((uint64_t)tot) + " cases, the train split " +
+                                                   std::to_string(E->n_total) + " (this rank: " + std::to_string(n) + " and " + std::to_string(S.n) + ")");
     }
     if (dev_alloc(E, &E->sec.colptr, (size_t)nc_ext + 1)) return SVBFM_ERR_OOM;
     SV_CUDA(E, cudaMemcpyAsync(E->sec.colptr, E->sec.h_colptr.data(), ((size_t)nc_ext + 1) * 8, cudaMemcpyHostToDevice, st));
