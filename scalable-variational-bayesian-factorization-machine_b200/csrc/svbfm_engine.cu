@@ -336,8 +336,15 @@ static int exchange_records(Engine* E, int run, const Run& r, double2* pf, const
     const std::vector<uint32_t>& blk = run ? E->blk1 : E->blk;
     RemoteRecArgs a{};
     if (E->p2p) {
+        // push this rank's block into every rank's stage, then flags (inside k_records_remote)
+        ProfScope pc(E, 10);
+        PushArgs pa{};
+        const uint32_t own0 = blk[E->rank] - r.col_begin, own = blk[E->rank + 1] - blk[E->rank];
+        pa.src = stage_of(E, E->d_xipc, run) + own0; pa.n = own; pa.world = E->world; pa.me = E->rank;
+        for (int q = 0; q < E->world; q++) pa.dst[q] = stage_of(E, E->peer_base[q], run) + own0;
+        if (own) { k_push_block<<<std::min<unsigned>(nblk(own), 148 * 8), 256, 0, st>>>(pa); LAUNCHED(E); }
         a.flags.n = E->world; a.flags.me = E->rank;
-        for (int q = 0; q < E->world; q++) { a.flags.p[q] = reinterpret_cast<unsigned long long*>(E->peer_base[q]); a.src[q] = stage_of(E, E->peer_base[q], run); }
+        for (int q = 0; q < E->world; q++) { a.flags.p[q] = reinterpret_cast<unsigned long long*>(E->peer_base[q]); a.src[q] = stage_of(E, E->d_xipc, run); }
         a.epoch = ++E->xs_epoch;
     } else {
         // no peer mappings: every rank broadcasts its block of the stage (blocks differ in size: one grouped collective)
