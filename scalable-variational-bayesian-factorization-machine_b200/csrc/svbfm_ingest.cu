@@ -1011,7 +1011,12 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
         if (sv_malloc((void**)&E->d_cpack, total_slots * 32 /* sizeof(ColPack) */) != cudaSuccess) return fail(E, SVBFM_ERR_OOM, "cudaMalloc: record slots");
         E->cpack_cap = total_slots;
     }
-    if (int rc = setup_exchange(E, std::max<size_t>(std::max(nc0, nc1), 1))) return rc;
+    {
+        // a stage holds a field in slot order; without peer mappings (fallback) stage 0 holds [world] blocks padded to the largest one
+        uint32_t mx = 1;
+        for (int r = 0; r < E->world; r++) mx = std::max(mx, std::max(E->blk[r + 1] - E->blk[r], E->blk1[r + 1] - E->blk1[r]));
+        if (int rc = setup_exchange(E, std::max<size_t>(std::max<size_t>(nc0, nc1), (size_t)E->world * mx))) return rc;
+    }
     // ---- tiles of the second side on the new shard (the first side keeps its own), second residual copy, tile sums
     const uint64_t TS = 1ull << E->ts_shift;
     std::vector<uint32_t> heavy;

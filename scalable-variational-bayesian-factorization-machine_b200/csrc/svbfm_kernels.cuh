@@ -1746,25 +1746,10 @@ struct RemoteRecArgs {
     PeerFlags flags;             // p2p: flag words of every rank (n = 0: the stage was filled by a collective)
     unsigned long long epoch;    // number of this exchange
 };
-// p2p: this rank's block of the stage (contiguous, just written by k_finalize) goes into the same place of every other rank's stage:
-// coalesced 16-byte stores over NVLink (posted writes: ~5x the throughput the first version got out of 16-byte LOADS from the peers,
-// 122 GB/s, profiles/r02_h3_*). Thread i takes element i of the block for every peer, the peers in the order me + 1, me + 2, ...
-struct PushArgs { const double2* src; double2* dst[16]; uint32_t n; int world, me; };
-__global__ void __launch_bounds__(256) k_push_block(PushArgs a) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
-        const double2 v = a.src[i];
-        for (int k = 1; k < a.world; k++) {
-            int q = a.me + k; if (q >= a.world) q -= a.world;
-            a.dst[q][i] = v;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) __threadfence_system();      // cumulative: the CTA's stores are out before the flag of the exchange is raised
-}
 __global__ void __launch_bounds__(256) k_records_remote(RemoteRecArgs a) {
     if (a.flags.n) {
-        // this rank's k_push_block (earlier on the stream) has stored its block into every rank's stage: say so to every rank, then
-        // wait until every other rank has said the same. Block 0 is dispatched first; the waiting blocks depend on other GPUs only.
+        // this rank's k_finalize (earlier on the stream) has left its block in its stage: say so to every rank, then wait until every
+        // other rank has said the same. Block 0 is dispatched first; the waiting blocks depend on other GPUs only.
         const int t = (int)threadIdx.x;
         if (blockIdx.x == 0 && t < a.flags.n && t != a.flags.me) {
             __threadfence_system();
@@ -1783,7 +1768,12 @@ __global__ void __launch_bounds__(256) k_records_remote(RemoteRecArgs a) {
         }
         __syncthreads();       // the fetches below depend on the flag values through this barrier and bypass L1: no fence needed
     }
-    // One thread per slot of the OTHER ranks' blocks (their {mean, var} are in this rank's stage now), in slot order.
+    // One thread per slot of the OTHER ranks' blocks; inside a block in slot order (the fetch from the peer's memory is coalesced).
+    // The blocks are taken in the order me + 1, me + 2, ... (mod world): at any time every rank serves one reader instead of all of
+    // them. Measured at 8 GPUs, 200 M ratings (ms per iteration; the exchange's share): this kernel 29.7 (10.0); every rank starting
+    // at block 0 30.8 (11.1); the owner PUSHING its block into every rank's stage with coalesced 16-byte stores from a kernel of
+    // its own 34.2 (14.3); in-place ncclAllGather of the same 16 B per column 31.1 (10.0) (profiles/r02_f_*, r02_h2_*, r02_h3_*,
+    // r02_j_*): ~14 MB per rank and exchange move at 150 - 190 GB/s whichever way; the time follows a rank's remote slots.
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;      // index among the remote slots, rotated order
     int q = a.me;
     bool found = false;
