@@ -123,3 +123,51 @@ def test_reference_tree_binding_on_the_emulator(emu_lib):
            f + "::test_vb_cuda_equals_vb_in_the_reference_binary[g1-1,1,4]", f + "::test_als_cuda_equals_als_in_the_reference_binary"]
     r = subprocess.run(cmd, env=dict(os.environ, SVBFM_EMU_PRELOAD=emu_lib), cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "2 passed" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+def test_round2_cli_paths_on_the_emulator(emu_lib):
+    """The CLI-level additions of round 2 with the emulated engine preloaded into bin/libFM and bin/transpose: -save_model / -load_model
+    (bit-for-bit resume), `transpose --device` against the reference tool's bytes, rows-only binary input through svbfm_set_csr."""
+    f = os.path.join(ROOT, "tests", "test_gpu_golden_cli.py")
+    cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider",
+           f + "::test_cli_save_and_load_model_resume_bit_for_bit", f + "::test_transpose_tool_on_the_device_writes_the_reference_bytes",
+           f + "::test_cli_rows_only_binary_input_is_transposed_on_the_device"]
+    r = subprocess.run(cmd, env=dict(os.environ, SVBFM_LIB=emu_lib, LD_PRELOAD=emu_lib), cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "4 passed" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+def test_device_transpose_and_row_wise_ingest_on_the_emulator(emu_lib):
+    """svbfm_transpose_csr against the host transpose (one-hot and ragged multi-hot data with real values) and svbfm_set_csr against
+    svbfm_set_csc: identical statistics."""
+    code = r'''
+import sys, os
+sys.path[:0] = [ROOT, ROOT + "/oracle", ROOT + "/tests"]
+import numpy as np
+import svbfm_b200 as sv
+from helpers import two_field, ragged, to_csc
+for tr in (two_field(5000, 10, 120, 90, seed=3)[0], ragged(3000, 10, 60, seed=4)[0]):
+    csc = to_csc(tr)
+    cp, ci, xt = sv.transpose_csr(tr.rowptr, tr.col, tr.val, tr.n_feat)
+    assert np.array_equal(cp, csc.colptr) and np.array_equal(ci, csc.case_id) and np.array_equal(xt, csc.x)
+try:
+    sv.transpose_csr(np.array([0, 1], dtype=np.uint64), np.array([7], dtype=np.uint32), np.ones(1, dtype=np.float32), 3)
+    raise SystemExit("a feature id beyond num_cols must be refused")
+except sv.SvbfmError as ex:
+    assert "out of range" in str(ex)
+for (tr, te), K in ((two_field(6000, 600, 100, 80, seed=5), 3), (ragged(2000, 300, 40, seed=6), 2)):
+    D = max(tr.n_feat, te.n_feat) + 1
+    out = []
+    for mode in ("csc", "csr"):
+        E = sv.Engine("vb", D, K, 1, 1, float(tr.y.min()), float(tr.y.max()), seed=42)
+        if mode == "csc":
+            E.set_csc(sv.TRAIN, to_csc(tr)); E.set_csc(sv.TEST, to_csc(te))
+        else:
+            E.set_csr(sv.TRAIN, tr.rowptr, tr.col, tr.val, tr.y, tr.n_feat); E.set_csr(sv.TEST, te.rowptr, te.col, te.val, te.y, te.n_feat)
+        E.set_state(sv.host_init_state(42, D, K, 0.1, sv.VB)); E.begin()
+        out.append([(s.test_rmse, s.free_energy, s.alpha) for s in E.run(3)])
+        E.close()
+    assert out[0] == out[1], out
+print("ROW_WISE_OK")
+'''.replace("ROOT", repr(ROOT))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SVBFM_LIB=emu_lib), cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ROW_WISE_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
