@@ -80,6 +80,7 @@ def parse_args():
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="strong (default): the workload's N ratings are split over the GPUs (BASELINE's metric: the 200 M sweep at 1/2/4/8 GPUs); "
                          "weak: every GPU holds its own N ratings (global N x gpus)")
+    ap.add_argument("--ship-x", action="store_true", help="hand over an explicit array of ones as the values instead of x = NULL")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of the other BASELINE configs (N = 1 only)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the single-GPU re-run of the first iterations (parity_vs_n1)")
     return ap.parse_args()
@@ -286,9 +287,11 @@ class Problem:
             n = int(uu.numel())
             pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
             cp, ci, ty = pin(colptr), pin(case_id), pin(yy.contiguous())
-            x = torch.ones(2 * n, dtype=torch.float32).pin_memory()
+            # one-hot indicator data: every value is 1, which the interface expresses as x = NULL (include/svbfm.h; the CLI's loaders
+            # find it out while they parse); --ship-x hands over the 4 bytes per entry of ones as round 1 did
+            x = torch.ones(2 * n, dtype=torch.float32).pin_memory() if cx.a.ship_x else None
             d = sv.CscData.__new__(sv.CscData)
-            d.colptr, d.case_id, d.x, d.target = cp.numpy().view(np.uint64), ci.numpy().view(np.uint32), x.numpy(), ty.numpy()
+            d.colptr, d.case_id, d.x, d.target = cp.numpy().view(np.uint64), ci.numpy().view(np.uint32), (x.numpy() if x is not None else None), ty.numpy()
             d.num_cases, d.num_feature = n, U + I
             d._keep = (cp, ci, x, ty)
             return d
@@ -315,8 +318,9 @@ class Problem:
     def h2d_bytes(self):
         tr, te, st = self.train, self.test, self.state
         t2 = self.train2
-        return (sum(x.nbytes for x in (tr.colptr, tr.case_id, tr.x, tr.target, te.colptr, te.case_id, te.x, te.target)) +
-                (sum(x.nbytes for x in (t2.colptr, t2.case_id, t2.x, t2.target)) if t2 is not None else 0) +
+        nb = lambda *arrs: sum(x.nbytes for x in arrs if x is not None)
+        return (nb(tr.colptr, tr.case_id, tr.x, tr.target, te.colptr, te.case_id, te.x, te.target) +
+                (nb(t2.colptr, t2.case_id, t2.x, t2.target) if t2 is not None else 0) +
                 st["w_mean"].nbytes + st["w_var"].nbytes + st["v_mean"].nbytes + st["v_var"].nbytes)
 
     def _tick(self, name, t0):

@@ -105,6 +105,8 @@ int svbfm_set_groups(svbfm_t* h, const uint32_t* attr_group /*[D]*/, uint32_t nu
 int svbfm_set_csc(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_cols,
                   const uint64_t* colptr /*[num_cols+1]*/, const uint32_t* case_id /*[nnz]*/,
                   const float* x /*[nnz]*/, const float* target /*[num_cases]*/);
+/* x may be NULL (here, in svbfm_set_csr and in svbfm_transpose_csr): every value is 1 (one-hot indicator data; the loaders of
+ * host/data.h notice it while they parse): a third of the entry bytes neither cross the bus nor get checked on the device. */
 /* The same split handed over ROW-wise: CSR of this rank's cases as the reference's `data` holds it (DataSubset::data, Data.h:87;
  * the rows of a binary .x file or of a parsed text file), features in any order inside a case. The transposed matrix the sweeps
  * run on is built on the device (replaces Data::create_data_t, Data.h:457-509, and tools/transpose.cpp:91-162 for this path): the

@@ -144,7 +144,7 @@ class CscData:
     def __init__(self, colptr, case_id, x, target, num_cases=None):
         self.colptr = np.ascontiguousarray(colptr, dtype=np.uint64)
         self.case_id = np.ascontiguousarray(case_id, dtype=np.uint32)
-        self.x = np.ascontiguousarray(x, dtype=np.float32)
+        self.x = None if x is None else np.ascontiguousarray(x, dtype=np.float32)      # None: every value is 1 (not shipped)
         self.target = np.ascontiguousarray(target, dtype=np.float32)
         self.num_cases = int(num_cases) if num_cases is not None else len(self.target)
         self.num_feature = len(self.colptr) - 1          # data_t->getNumRows() = max id + 1
@@ -209,7 +209,8 @@ class Engine:
     def set_csr(self, split, rowptr, feature_id, x, target, num_feature):
         """The split row-wise (CSR of the cases, like a parsed text file or a binary .x file): the device builds the transposed matrix."""
         rowptr = np.ascontiguousarray(rowptr, dtype=np.uint64); feature_id = np.ascontiguousarray(feature_id, dtype=np.uint32)
-        x = np.ascontiguousarray(x, dtype=np.float32); target = np.ascontiguousarray(target, dtype=np.float32)
+        x = None if x is None else np.ascontiguousarray(x, dtype=np.float32)
+        target = np.ascontiguousarray(target, dtype=np.float32)
         n = len(rowptr) - 1
         self._ck(lib().svbfm_set_csr(self.h, split, n, int(num_feature), _p(rowptr), _p(feature_id), _p(x), _p(target)), "svbfm_set_csr")
         if split == TRAIN:

@@ -1030,7 +1030,7 @@ int svbfm_set_csc(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_co
     if (E->begun) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc after svbfm_begin");
     SV_CUDA(E, cudaSetDevice(E->dev));
     if (split == SVBFM_TRAIN_SECOND) return ingest_second(E, num_cases, num_cols, colptr, case_id, x, target);      // validates its arguments collectively
-    if (colptr[num_cols] > 0 && (!case_id || !x)) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc: null entry arrays");
+    if (colptr[num_cols] > 0 && !case_id) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc: null entry arrays");
     if (num_cases > 0 && !target) return fail(E, SVBFM_ERR_ARG, "svbfm_set_csc: null target");
     bool is_train = split == SVBFM_TRAIN;
     DevSplit& S = is_train ? E->tr : E->te;
@@ -1073,7 +1073,7 @@ int svbfm_set_csr(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_co
     std::string why;
     if (rowptr[0] != 0) why = "svbfm_set_csr: rowptr[0] != 0";
     else if (nnz >= (1ull << 32)) why = "svbfm_set_csr: more than 2^32-1 entries per rank are not supported";
-    else if (nnz > 0 && (!feature_id || !x)) why = "svbfm_set_csr: null entry arrays";
+    else if (nnz > 0 && !feature_id) why = "svbfm_set_csr: null entry arrays";
     else if (num_cases > 0 && !target) why = "svbfm_set_csr: null target";
     else for (uint32_t i = 0; i < num_cases && why.empty(); i++) if (rowptr[i + 1] < rowptr[i]) why = "svbfm_set_csr: rowptr not monotone";
     if (!why.empty() && E->world <= 1) return fail(E, SVBFM_ERR_ARG, why);
@@ -1089,11 +1089,11 @@ int svbfm_set_csr(svbfm_t* h, int32_t split, uint32_t num_cases, uint32_t num_co
     if (why.empty()) {
         SV_CUDA(E, sv_malloc((void**)&d_rowptr, ((size_t)num_cases + 1) * 8));
         SV_CUDA(E, sv_malloc((void**)&d_col, std::max<uint64_t>(nnz, 1) * 4));
-        SV_CUDA(E, sv_malloc((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4));
+        if (x) SV_CUDA(E, sv_malloc((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4));
         SV_CUDA(E, sv_malloc((void**)&d_y, std::max<size_t>(num_cases, 1) * 4));
         SV_CUDA(E, cudaMemcpyAsync(d_rowptr, rowptr, ((size_t)num_cases + 1) * 8, cudaMemcpyHostToDevice, st));
         SV_CUDA(E, cudaMemcpyAsync(d_col, feature_id, nnz * 4, cudaMemcpyHostToDevice, st));
-        SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, st));
+        if (x) SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, st));
         SV_CUDA(E, cudaMemcpyAsync(d_y, target, (size_t)num_cases * 4, cudaMemcpyHostToDevice, st));
         rc = transpose_on_device(E, st, num_cases, num_cols, nnz, d_rowptr, d_col, d_x, &d_colptr, &d_case, &d_xt);
         if (rc) why = E->err;
@@ -1118,7 +1118,7 @@ int svbfm_transpose_csr(int32_t device, uint32_t num_cases, uint32_t num_cols, c
                         uint64_t* out_colptr, uint32_t* out_case_id, float* out_x) {
     if (!rowptr || !out_colptr) { g_create_error = "svbfm_transpose_csr: null argument"; return SVBFM_ERR_ARG; }
     const uint64_t nnz = rowptr[num_cases];
-    if (nnz >= (1ull << 32) || (nnz && (!feature_id || !x || !out_case_id || !out_x))) { g_create_error = "svbfm_transpose_csr: bad arguments"; return SVBFM_ERR_ARG; }
+    if (nnz >= (1ull << 32) || (nnz && (!feature_id || !out_case_id || (x && !out_x)))) { g_create_error = "svbfm_transpose_csr: bad arguments"; return SVBFM_ERR_ARG; }
     svbfm_config c;
     memset(&c, 0, sizeof(c));
     c.struct_size = sizeof(c); c.method = SVBFM_VB; c.num_attribute = 1; c.num_factor = 0; c.device = device;
@@ -1133,15 +1133,15 @@ int svbfm_transpose_csr(int32_t device, uint32_t num_cases, uint32_t num_cols, c
     auto body = [&]() -> int {
         SV_CUDA(E, sv_malloc((void**)&d_rowptr, ((size_t)num_cases + 1) * 8));
         SV_CUDA(E, sv_malloc((void**)&d_col, std::max<uint64_t>(nnz, 1) * 4));
-        SV_CUDA(E, sv_malloc((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4));
+        if (x) SV_CUDA(E, sv_malloc((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4));
         SV_CUDA(E, cudaMemcpyAsync(d_rowptr, rowptr, ((size_t)num_cases + 1) * 8, cudaMemcpyHostToDevice, st));
         SV_CUDA(E, cudaMemcpyAsync(d_col, feature_id, nnz * 4, cudaMemcpyHostToDevice, st));
-        SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, st));
+        if (x) SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, st));
         if (int r = transpose_on_device(E, st, num_cases, num_cols, nnz, d_rowptr, d_col, d_x, &d_colptr, &d_case, &d_xt)) return r;
         SV_CUDA(E, cudaMemcpyAsync(out_colptr, d_colptr, ((size_t)num_cols + 1) * 8, cudaMemcpyDeviceToHost, st));
         if (nnz) {
             SV_CUDA(E, cudaMemcpyAsync(out_case_id, d_case, nnz * 4, cudaMemcpyDeviceToHost, st));
-            SV_CUDA(E, cudaMemcpyAsync(out_x, d_xt, nnz * 4, cudaMemcpyDeviceToHost, st));
+            if (x) SV_CUDA(E, cudaMemcpyAsync(out_x, d_xt, nnz * 4, cudaMemcpyDeviceToHost, st));
         }
         SV_CUDA(E, cudaStreamSynchronize(st));
         return 0;

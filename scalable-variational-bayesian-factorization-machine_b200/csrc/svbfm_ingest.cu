@@ -343,7 +343,7 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     if (dev_alloc(E, &S.y, n)) return SVBFM_ERR_OOM;
     float* d_x = nullptr;
     temps.own((void**)&d_x);
-    SV_CUDA(E, sv_malloc((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4));
+    if (x) SV_CUDA(E, sv_malloc((void**)&d_x, std::max<uint64_t>(nnz, 1) * 4));       // x == null: every value is 1 (nothing to ship or to check)
     // The values and the targets are not needed before the CSR gather / the case re-ordering: they travel on a second stream
     // while the main stream sorts the case ids (pinned host buffers; with pageable memory the copies serialise anyway).
     cudaStream_t cs = E->copy_stream ? E->copy_stream : st;
@@ -358,8 +358,10 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
     }
     SV_CUDA(E, cudaMemcpyAsync(S.colptr, S.h_colptr.data(), ((size_t)S.ncols_ext + 1) * 8, cudaMemcpyHostToDevice, st));
     SV_CUDA(E, cudaMemcpyAsync(S.crow, case_id, nnz * 4, cudaMemcpyDefault, st));
-    SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyDefault, cs));
-    if (nnz) k_any_not_one<<<std::min<unsigned>(nblk(nnz), 148 * 16), 256, 0, cs>>>(d_x, nnz, d_flags + 0);
+    if (x) {
+        SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyDefault, cs));
+        if (nnz) k_any_not_one<<<std::min<unsigned>(nblk(nnz), 148 * 16), 256, 0, cs>>>(d_x, nnz, d_flags + 0);
+    }
     SV_CUDA(E, cudaMemcpyAsync(S.y, target, (size_t)n * 4, cudaMemcpyDefault, cs));
     if (nnz) k_check_case_ids<<<nblk(nnz), 256, 0, st>>>(S.crow, nnz, n, d_flags + 1);
     // CSC -> CSR: feature id per entry, stable sort by case id
@@ -748,7 +750,8 @@ int transpose_on_device(Engine* E, cudaStream_t st, uint32_t n, uint32_t ncols, 
         if (bad) return fail(E, SVBFM_ERR_ARG, "feature id out of range in transpose");
         if (int rc = sort_pairs(E, d_col, d_idx, nnz, std::max<uint32_t>(ncols, 1), &d_skeys, &d_sidx)) return rc;
         k_gather_u32<<<nblk(nnz), 256, 0, st>>>(d_row, d_sidx, nnz, *d_case);
-        k_gather_f32<<<nblk(nnz), 256, 0, st>>>(d_x, d_sidx, nnz, *d_xt);
+        if (d_x) k_gather_f32<<<nblk(nnz), 256, 0, st>>>(d_x, d_sidx, nnz, *d_xt);
+        else { sv_free(*d_xt); *d_xt = nullptr; }                                  // every value is 1
         k_rowptr_from_sorted<<<nblk((uint64_t)ncols + 1), 256, 0, st>>>(d_skeys, nnz, ncols, *d_colptr);
     } else SV_CUDA(E, cudaMemsetAsync(*d_colptr, 0, ((size_t)ncols + 1) * 8, st));
     SV_CUDA(E, cudaStreamSynchronize(st));
@@ -868,7 +871,7 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
         const uint64_t nnz = colptr[ncols];
         off1 = colptr[std::min(r1.col_begin, ncols)];
         if (nnz != 2ull * n || off1 != n) why = "every case needs exactly one entry in each of the two fields";
-        else if (n && (!case_id || !x || !target)) why = "null entry arrays";
+        else if (n && (!case_id || !target)) why = "null entry arrays";
         else if (ncols > nc_ext) why = "more columns than the train split";
     }
     uint32_t* d_flags = nullptr;      // [0] x != 1   [1] case id out of range   [2] not one entry per case and field
@@ -888,18 +891,18 @@ int ingest_second(Engine* E, uint32_t n, uint32_t ncols, const uint64_t* colptr,
         const uint64_t nnz = 2ull * n;
         SV_CUDA(E, sv_malloc((void**)&d_case, nnz * 4));
         SV_CUDA(E, sv_malloc((void**)&d_colof, nnz * 4));
-        SV_CUDA(E, sv_malloc((void**)&d_x, nnz * 4));
+        if (x) SV_CUDA(E, sv_malloc((void**)&d_x, nnz * 4));
         SV_CUDA(E, sv_malloc((void**)&d_t, (size_t)n * 4));
         SV_CUDA(E, sv_malloc((void**)&d_cp, ((size_t)ncols + 1) * 8));
         SV_CUDA(E, sv_malloc((void**)&d_user, (size_t)n * 4));
         SV_CUDA(E, sv_malloc((void**)&d_seen, (size_t)n * 4));
         SV_CUDA(E, cudaMemcpyAsync(d_cp, colptr, ((size_t)ncols + 1) * 8, cudaMemcpyHostToDevice, st));
         SV_CUDA(E, cudaMemcpyAsync(d_case, case_id, nnz * 4, cudaMemcpyHostToDevice, st));
-        SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, st));
+        if (x) SV_CUDA(E, cudaMemcpyAsync(d_x, x, nnz * 4, cudaMemcpyHostToDevice, st));
         SV_CUDA(E, cudaMemcpyAsync(d_t, target, (size_t)n * 4, cudaMemcpyHostToDevice, st));
         SV_CUDA(E, cudaMemsetAsync(d_user, 0xff, (size_t)n * 4, st));
         SV_CUDA(E, cudaMemsetAsync(d_seen, 0, (size_t)n * 4, st));
-        k_any_not_one<<<std::min<unsigned>(nblk(nnz), 148 * 16), 256, 0, st>>>(d_x, nnz, d_flags + 0);
+        if (x) k_any_not_one<<<std::min<unsigned>(nblk(nnz), 148 * 16), 256, 0, st>>>(d_x, nnz, d_flags + 0);
         k_col_of_entry<<<nblk(nnz), 256, 0, st>>>(d_cp, ncols, nnz, d_colof);
         if (dev_alloc(E, &E->sec.oc, n)) return SVBFM_ERR_OOM;
         if (dev_alloc(E, &E->sec.rcol, (size_t)n * 2)) return SVBFM_ERR_OOM;

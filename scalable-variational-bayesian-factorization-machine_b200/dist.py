@@ -19,7 +19,7 @@ def shard_csc(data, rank, world):
     col_of = np.repeat(np.arange(data.num_feature, dtype=np.int64), np.diff(data.colptr.astype(np.int64)))
     colptr = np.zeros(data.num_feature + 1, dtype=np.uint64)
     np.cumsum(np.bincount(col_of[keep], minlength=data.num_feature), out=colptr[1:])
-    return CscData(colptr, (data.case_id[keep] - lo).astype(np.uint32), data.x[keep], data.target[lo:hi])
+    return CscData(colptr, (data.case_id[keep] - lo).astype(np.uint32), (data.x[keep] if data.x is not None else None), data.target[lo:hi])
 
 
 def block_bounds(colptr, first_field_cols, world):
@@ -49,7 +49,7 @@ def shard_csc_by_block(data, rank, world, first_field_cols):
     col_of = np.repeat(np.arange(data.num_feature, dtype=np.int64), np.diff(cp))
     colptr = np.zeros(data.num_feature + 1, dtype=np.uint64)
     np.cumsum(np.bincount(col_of[keep], minlength=data.num_feature), out=colptr[1:])
-    return CscData(colptr, local[data.case_id[keep]].astype(np.uint32), data.x[keep], data.target[mine]), mine
+    return CscData(colptr, local[data.case_id[keep]].astype(np.uint32), (data.x[keep] if data.x is not None else None), data.target[mine]), mine
 
 
 def second_block_bounds(colptr, first_field_cols, num_cols, world):
@@ -78,7 +78,7 @@ def shard_csc_by_second_block(data, rank, world, first_field_cols):
     col_of = np.repeat(np.arange(data.num_feature, dtype=np.int64), np.diff(cp))
     colptr = np.zeros(data.num_feature + 1, dtype=np.uint64)
     np.cumsum(np.bincount(col_of[keep], minlength=data.num_feature), out=colptr[1:])
-    return CscData(colptr, local[data.case_id[keep]].astype(np.uint32), data.x[keep], data.target[mine]), mine
+    return CscData(colptr, local[data.case_id[keep]].astype(np.uint32), (data.x[keep] if data.x is not None else None), data.target[mine]), mine
 
 
 def broadcast_unique_id(get_id, rank, device=None):

@@ -205,17 +205,23 @@ protected:
     }
 
     // hands data_t + target of this rank's shard of cases to the engine
+    static bool all_ones(const std::vector<float>& v) {
+        for (float f : v) if (f != 1.0f) return false;
+        return true;
+    }
     void push(int split, DataSet& d) {
+        // one-hot indicator data: the values are not shipped at all (x = NULL: include/svbfm.h)
+        const bool ones = all_ones(d.csr_only ? d.x.val : d.xt.val);
         if (d.csr_only) {       // rows as loaded: a rank's shard is a slice of the row pointer; the device transposes (svbfm_set_csr)
             const uint32_t lo = (uint32_t)((uint64_t)d.num_cases * shard.rank / shard.world), hi = (uint32_t)((uint64_t)d.num_cases * (shard.rank + 1) / shard.world);
             const uint64_t e0 = d.x.ptr[lo];
             std::vector<uint64_t> rp(d.x.ptr.begin() + lo, d.x.ptr.begin() + hi + 1);
             for (uint64_t& v : rp) v -= e0;
-            ck(svbfm_set_csr(h_, split, hi - lo, (uint32_t)d.num_feature, rp.data(), d.x.id.data() + e0, d.x.val.data() + e0, d.target.data() + lo), "svbfm_set_csr");
+            ck(svbfm_set_csr(h_, split, hi - lo, (uint32_t)d.num_feature, rp.data(), d.x.id.data() + e0, ones ? nullptr : d.x.val.data() + e0, d.target.data() + lo), "svbfm_set_csr");
             return;
         }
         if (shard.world <= 1) {
-            ck(svbfm_set_csc(h_, split, d.num_cases, d.xt.num_rows, d.xt.ptr.data(), d.xt.id.data(), d.xt.val.data(), d.target.data()), "svbfm_set_csc");
+            ck(svbfm_set_csc(h_, split, d.num_cases, d.xt.num_rows, d.xt.ptr.data(), d.xt.id.data(), ones ? nullptr : d.xt.val.data(), d.target.data()), "svbfm_set_csc");
             return;
         }
         uint32_t lo = (uint32_t)((uint64_t)d.num_cases * shard.rank / shard.world), hi = (uint32_t)((uint64_t)d.num_cases * (shard.rank + 1) / shard.world);

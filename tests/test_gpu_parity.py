@@ -310,6 +310,28 @@ def test_reset_reuses_handle(built):
     assert h1 == h2
 
 
+def test_values_may_be_null_for_one_hot_data(built):
+    """x = NULL in svbfm_set_csc / svbfm_set_csr says "every value is 1": same statistics, bit for bit, as an explicit array of ones,
+    column-wise and row-wise (the device transpose)."""
+    tr, te = two_field(6000, 600, 100, 80, seed=5)
+    D = max(tr.n_feat, te.n_feat) + 1
+    out = []
+    for mode in ("ones", "null", "rows_null"):
+        E = sv.Engine("vb", D, 3, 1, 1, float(tr.y.min()), float(tr.y.max()), seed=42)
+        a, b = to_csc(tr), to_csc(te)
+        if mode == "null":
+            a.x = b.x = None
+        if mode == "rows_null":
+            E.set_csr(sv.TRAIN, tr.rowptr, tr.col, None, tr.y, tr.n_feat); E.set_csr(sv.TEST, te.rowptr, te.col, None, te.y, te.n_feat)
+        else:
+            E.set_csc(sv.TRAIN, a); E.set_csc(sv.TEST, b)
+        assert E.info()["all_ones"] == 1 and E.info()["fused_schedule"] & 1
+        E.set_state(sv.host_init_state(42, D, 3, 0.1, sv.VB)); E.begin()
+        out.append([(s.test_rmse, s.free_energy, s.alpha) for s in E.run(3)])
+        E.close()
+    assert out[0] == out[1] == out[2]
+
+
 def test_reset_onto_a_larger_split_vb_online(built):
     """A long-lived vb_online handle that is reset onto a LARGER train split: the per-case / per-entry batch buffers follow the new
     split (they used to keep the first split's size). Same statistics as a fresh handle on the larger split, bit for bit."""
