@@ -209,7 +209,64 @@ protected:
         for (float f : v) if (f != 1.0f) return false;
         return true;
     }
+    // Several GPUs, vb / mcmc on two complete one-hot fields with x = 1 (`u:1 i:1` rows, every first id below every second id): cross
+    // shards: this rank's block of first-field columns goes in as SVBFM_TRAIN, its block of second-field columns
+    // as SVBFM_TRAIN_SECOND; both block sets are cut where the running cost `entries + 8 per column` passes rank / world of the total.
+    // SVBFM_SHARD=range keeps contiguous case ranges (both fields allreduced). Returns false when the data does not qualify.
+    bool push_cross(DataSet& d) {
+        const char* mode = getenv("SVBFM_SHARD");
+        if (shard.world <= 1 || method == SVBFM_VB_ONLINE || task != 0 || !d.csr_only || (mode && std::string(mode) == "range")) return false;
+        const uint32_t n = d.num_cases;
+        const SparseMatrix& x = d.x;
+        if (n == 0 || x.nnz() != 2ull * n || !all_ones(x.val)) return false;
+        uint32_t max0 = 0, min1 = 0xffffffffu;
+        for (uint32_t i = 0; i < n; i++) {
+            if (x.ptr[i + 1] - x.ptr[i] != 2) return false;
+            const uint32_t a = x.id[2ull * i], b = x.id[2ull * i + 1];
+            if (a >= b) return false;
+            max0 = std::max(max0, a); min1 = std::min(min1, b);
+        }
+        if (max0 >= min1) return false;
+        const uint32_t nf = (uint32_t)d.num_feature, c1 = min1;               // fields: [0, c1) and [c1, nf)
+        std::vector<uint64_t> cnt(nf, 0);
+        for (uint64_t p = 0; p < x.nnz(); p++) cnt[x.id[p]]++;
+        auto cuts = [&](uint32_t lo, uint32_t hi) {
+            double total = 0;
+            for (uint32_t j = lo; j < hi; j++) total += (double)cnt[j] + (cnt[j] ? 8.0 : 0.0);
+            std::vector<uint32_t> b(shard.world + 1, hi);
+            b[0] = lo;
+            double run = 0; int r = 1;
+            for (uint32_t j = lo; j < hi && r < shard.world; j++) {
+                run += (double)cnt[j] + (cnt[j] ? 8.0 : 0.0);
+                while (r < shard.world && run >= total * r / shard.world) b[r++] = j + 1;
+            }
+            return b;
+        };
+        const std::vector<uint32_t> b0 = cuts(0, c1), b1 = cuts(c1, nf);
+        for (int which = 0; which < 2; which++) {
+            const uint32_t lo = which ? b1[shard.rank] : b0[shard.rank], hi = which ? b1[shard.rank + 1] : b0[shard.rank + 1];
+            std::vector<uint64_t> rp(1, 0);
+            std::vector<uint32_t> ids;
+            std::vector<float> y;
+            for (uint32_t i = 0; i < n; i++) {
+                const uint32_t key = x.id[2ull * i + which];
+                if (key < lo || key >= hi) continue;
+                ids.push_back(x.id[2ull * i]); ids.push_back(x.id[2ull * i + 1]);
+                rp.push_back(ids.size());
+                y.push_back(d.target[i]);
+            }
+            int rc = svbfm_set_csr(h_, which ? SVBFM_TRAIN_SECOND : SVBFM_TRAIN, (uint32_t)y.size(), nf, rp.data(), ids.data(), nullptr, y.data());
+            if (rc != 0 && which == 1) {      // refused on every rank alike: the user-block shard stands by itself (item sums allreduced)
+                if (root()) std::cout << "cross shards refused (" << svbfm_last_error(h_) << "): user-block shards" << std::endl;
+                return true;
+            }
+            ck(rc, "svbfm_set_csr");
+        }
+        if (root()) std::cout << "multi-GPU: cross shards (first field by blocks of columns for the first residual copy, second field for the second)" << std::endl;
+        return true;
+    }
     void push(int split, DataSet& d) {
+        if (split == SVBFM_TRAIN && push_cross(d)) return;
         // one-hot indicator data: the values are not shipped at all (x = NULL: include/svbfm.h)
         const bool ones = all_ones(d.csr_only ? d.x.val : d.xt.val);
         if (d.csr_only) {       // rows as loaded: a rank's shard is a slice of the row pointer; the device transposes (svbfm_set_csr)

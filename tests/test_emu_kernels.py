@@ -171,3 +171,36 @@ print("ROW_WISE_OK")
 '''.replace("ROOT", repr(ROOT))
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SVBFM_LIB=emu_lib), cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ROW_WISE_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("shard", ["cross", "range"])
+def test_cli_two_ranks_on_the_emulator(emu_lib, tmp_path, shard):
+    """bin/libFM as two PROCESSES (WORLD_SIZE / RANK / SVBFM_COMM_FILE, fake NCCL, emulated engine preloaded): the id record with its
+    launch nonce, cross shards from the CLI (the default for two one-hot fields) and contiguous case ranges (SVBFM_SHARD=range) write
+    the files of the single-process run; a stale record of an earlier launch in the same path is ignored and removed."""
+    G = os.path.join(ROOT, "tests", "golden")
+    exe = os.path.join(ROOT, "scalable-variational-bayesian-factorization-machine_b200", "bin", "libFM")
+    build_dir = os.path.dirname(emu_lib)
+    args = [exe, "-task", "r", "-train", os.path.join(G, "g1_train.libfm"), "-test", os.path.join(G, "g1_test.libfm"), "-dim", "1,1,4", "-method", "vb",
+            "-iter", "4", "-seed", "42"]
+    base = dict(os.environ, SVBFM_LIB=emu_lib, LD_PRELOAD=emu_lib, LD_LIBRARY_PATH=build_dir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    one = tmp_path / "one"; one.mkdir()
+    r = subprocess.run(args, env=base, cwd=one, capture_output=True, text=True, timeout=600)
+    assert "ERROR" not in r.stderr, r.stderr
+    want = [float(v) for v in open(one / "test_rmse_114_vb").read().split()]
+    want_f = [float(v) for v in open(one / "free_energy_114_vb").read().split()]
+    idfile = tmp_path / "comm_id"
+    idfile.write_bytes(b"SVBFMID1" + bytes(136))          # a record of some earlier launch: wrong nonce
+    dirs, procs = [], []
+    for rank in range(2):
+        d = tmp_path / f"rank{rank}"; d.mkdir(); dirs.append(d)
+        env = dict(base, WORLD_SIZE="2", RANK=str(rank), LOCAL_RANK="0", SVBFM_COMM_FILE=str(idfile), SVBFM_COMM_NONCE="test-launch", SVBFM_SHARD=shard)
+        procs.append(subprocess.Popen(args, env=env, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all("ERROR" not in e for _, e in outs), [e for _, e in outs]
+    assert ("cross shards (first field" in outs[0][0]) == (shard == "cross"), outs[0][0][-2000:]
+    got = [float(v) for v in open(dirs[0] / "test_rmse_114_vb").read().split()]
+    got_f = [float(v) for v in open(dirs[0] / "free_energy_114_vb").read().split()]
+    assert len(got) == 4 and all(abs(a - b) <= 1e-5 * b for a, b in zip(got, want)), (got, want)
+    assert all(abs(a - b) <= 1e-5 * abs(b) for a, b in zip(got_f, want_f)), (got_f, want_f)
+    assert not idfile.exists()                             # rank 0 removes the record once the communicator stands
