@@ -62,6 +62,27 @@ struct OtherView {            // F == 2 only: for every CSC entry, the feature i
 struct alignas(32) ColPack { double mu, sg, delta, h4; };
 struct alignas(32) OwnPack { double mu_red, h_oth, d_own, pad; };
 
+// the 32-byte record gather of k_stream. SV_REC_LOAD (tuning macro): 0 plain load (LDG.E.256); 1 ld.global.nc (read-only path);
+// 2 ld.global.nc with L1::evict_last (keep the hot records of a Zipf-shaped field in L1); 3 L1::no_allocate (L2 only)
+#ifndef SV_REC_LOAD
+#define SV_REC_LOAD 0
+#endif
+__device__ __forceinline__ ColPack sv_load_record(const ColPack* p) {
+#if SV_REC_LOAD == 0 || defined(SVBFM_EMULATED)
+    return *p;
+#else
+    ColPack r;
+#if SV_REC_LOAD == 1
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.mu), "=d"(r.sg), "=d"(r.delta), "=d"(r.h4) : "l"(p));
+#elif SV_REC_LOAD == 2
+    asm volatile("ld.global.nc.L1::evict_last.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.mu), "=d"(r.sg), "=d"(r.delta), "=d"(r.h4) : "l"(p));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.mu), "=d"(r.sg), "=d"(r.delta), "=d"(r.h4) : "l"(p));
+#endif
+    return r;
+#endif
+}
+
 template <int FT, bool ONES, bool VAR>
 __device__ __forceinline__ void others(const RowView& rv, const OtherView& ov, const double2* __restrict__ pf, uint64_t p, uint32_t i, uint32_t j,
                                        double& h, double& h1, double& h2) {
@@ -918,11 +939,11 @@ __global__ void __launch_bounds__(32 * SV_STREAM_WARPS, ONES ? SV_STREAM_MINB : 
     auto gather = [&](uint32_t q0, const uint32_t (&oc)[U], ColPack (&g)[U]) {
         if ((STEADY || need_rec) && q_end - q0 >= 32 * U) {
 #pragma unroll
-            for (int u = 0; u < U; u++) g[u] = a.rec[oc[u]];
+            for (int u = 0; u < U; u++) g[u] = sv_load_record(a.rec + oc[u]);
         } else {
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                if (need_rec && q0 + u * 32 + lane < q_end) g[u] = a.rec[oc[u]];
+                if (need_rec && q0 + u * 32 + lane < q_end) g[u] = sv_load_record(a.rec + oc[u]);
                 else g[u] = ColPack{0.0, 0.0, 0.0, 0.0};
             }
         }
