@@ -330,7 +330,9 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
         fa.col_count = E->d_col_count;
         fa.update_t = IS_V ? (f == E->K - 1) : 1;      // t_vj advances once per batch (vbo.h:399-402), t_wj per w update (:520)
         int update_params = IS_V ? 1 : (E->cfg.k1 != 0);   // with k1 = 0 the w pass only counts the batch entries per column
-        k_finalize_vbo<KIND><<<nblk(ncols), 256, 0, st>>>(fa, E->d_cnt_col, 0.5, 1u, update_params);
+        uint32_t nthreads = ncols;
+        if (rp && rp->run >= 0 && E->bv.on && E->bv.clist[rp->run]) { fa.col_list = E->bv.clist[rp->run]; fa.n_list = E->bv.nclist[rp->run]; nthreads = fa.n_list; }
+        if (nthreads) k_finalize_vbo<KIND><<<nblk(nthreads), 256, 0, st>>>(fa, E->d_cnt_col, 0.5, 1u, update_params);
     } else {
         if (ncols) k_finalize<KIND><<<nblk(ncols), 256, 0, st>>>(fa);
     }
@@ -448,6 +450,7 @@ static void launch_stream(Engine* E, int side, bool has_own, bool own_is_w, bool
     a.oc = sv.oc; a.xv = sv.xv; a.xo = sv.xo;
     a.e = side ? E->d_e2 : E->d_e;
     a.rec = E->d_cpack; a.own = E->d_opack;
+    a.rec_no_alloc = (E->rec_na_mask >> side) & 1;
     a.has_own = has_own; a.own_is_w = own_is_w; a.has_oth = has_oth; a.oth_is_w = oth_is_w;
     a.colsum = E->d_colsum;
     constexpr int KIND = MCMC ? (W ? KIND_MC_W : KIND_MC_V) : (W ? KIND_VB_W : KIND_VB_V);
@@ -890,6 +893,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     if (const char* tm = getenv("SVBFM_STREAM_TMA")) E->stream_tma = atoi(tm) != 0;      // default on; 0: plain loads (A/B runs, tests)
     if (const char* rr = getenv("SVBFM_REC_RANK")) E->want_rec_rank = atoi(rr) != 0;    // default on; 0: records in column order
     if (const char* gr = getenv("SVBFM_GRAPH")) E->use_graph = atoi(gr) != 0;
+    if (const char* na = getenv("SVBFM_REC_NA")) E->rec_na_mask = atoi(na);              // bit s: side s gathers its records past L1 (default 2)
     if (const char* te = getenv("SVBFM_TILE_ENTRIES")) if (atoi(te) >= 32) E->tile_entries = (uint32_t)atoi(te);   // tuning knob
     // implicit tiles of the stream schedule: 4096 entries unless the caller (or the knob) says otherwise
     uint32_t ts = (cfg->tile_entries || getenv("SVBFM_TILE_ENTRIES")) ? E->tile_entries : 4096u;
@@ -943,7 +947,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_gcnt[0], E->d_vbo_gcnt[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_gcnt[0], E->d_vbo_gcnt[1], E->d_vbo_clist[0], E->d_vbo_clist[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) sv_free(p);
     cudaStreamSynchronize(E->stream);
     if (E->copy_stream) { cudaStreamSynchronize(E->copy_stream); cudaStreamDestroy(E->copy_stream); }
@@ -1397,6 +1401,8 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
                 // view indexed by global column id: view[j] = first position in idx of column j of batch b
                 E->bv.colptr[ri] = reinterpret_cast<const uint64_t*>(E->d_vbo_colptr[ri]) + (size_t)b * nc - r.col_begin;
                 E->bv.gcnt[ri] = E->d_vbo_gcnt[ri] ? E->d_vbo_gcnt[ri] + (size_t)b * nc - r.col_begin : nullptr;
+                E->bv.clist[ri] = E->d_vbo_clist[ri] ? E->d_vbo_clist[ri] + E->vbo_clist_off[ri][b] : nullptr;
+                E->bv.nclist[ri] = E->d_vbo_clist[ri] ? E->vbo_clist_off[ri][b + 1] - E->vbo_clist_off[ri][b] : 0u;
                 if (E->bv.ntiles) {
                     k_tile_col0<<<nblk(E->bv.ntiles), 256, 0, st>>>(E->bv.colptr[ri], r.col_begin, r.col_end, E->bv.ntiles, E->vbo_ts_shift,
                                                                    E->d_vbo_tile_col0 + (ri ? E->vbo_max_tiles : 0)); LAUNCHED(E);

@@ -141,6 +141,8 @@ struct Engine {
     uint32_t* d_vbo_idx[2] = {nullptr, nullptr};           // [n] each
     unsigned long long* d_vbo_colptr[2] = {nullptr, nullptr};   // [num_batch * ncols(run) + 1] each
     uint32_t* d_vbo_gcnt[2] = {nullptr, nullptr};          // sharded: [num_batch * ncols(run)] GLOBAL number of batch entries per column
+    uint32_t* d_vbo_clist[2] = {nullptr, nullptr};         // the non-empty columns of every batch (column ids, batch after batch): what a batch's finalize walks
+    std::vector<uint32_t> vbo_clist_off[2];                // [num_batch + 1] first list entry of every batch
     uint32_t* d_vbo_tile_col0 = nullptr;                   // [2][vbo_max_tiles]
     double* d_vbo_partial = nullptr;                       // [2][vbo_max_tiles][2][4]
     uint32_t vbo_max_tiles = 0;
@@ -150,6 +152,8 @@ struct Engine {
         bool lists = false;                                 // prediction / reductions / w0 shift of the batch walk its case list too
         const uint64_t* colptr[2] = {nullptr, nullptr};
         const uint32_t* gcnt[2] = {nullptr, nullptr};       // sharded: global batch entries per column (same indexing as colptr)
+        const uint32_t* clist[2] = {nullptr, nullptr};      // the batch's non-empty columns of run 0 / 1 (null: all columns)
+        uint32_t nclist[2] = {0, 0};
         uint64_t entry0 = 0;
         uint32_t n = 0, ntiles = 0;
     } bv;
@@ -192,6 +196,7 @@ struct Engine {
     uint64_t graph_replays = 0;
     bool stream_tma = true;            // k_stream's all-ones streams go through a shared-memory ring of bulk copies (SVBFM_STREAM_TMA=0: plain loads)
     bool rec_rank = false;
+    int rec_na_mask = 2;               // bit s: the pass over side s gathers its records with L1::no_allocate (kernels.cuh sv_load_record)
     double* d_dT = nullptr;           // [D]
     double* d_red_partial = nullptr;  // reduction scratch
     double* d_grp_sums = nullptr;     // [(K+1)][G][2]

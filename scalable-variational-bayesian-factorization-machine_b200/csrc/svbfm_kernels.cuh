@@ -62,23 +62,19 @@ struct OtherView {            // F == 2 only: for every CSC entry, the feature i
 struct alignas(32) ColPack { double mu, sg, delta, h4; };
 struct alignas(32) OwnPack { double mu_red, h_oth, d_own, pad; };
 
-// the 32-byte record gather of k_stream. SV_REC_LOAD (tuning macro): 0 plain load (LDG.E.256); 1 ld.global.nc (read-only path);
-// 2 ld.global.nc with L1::evict_last (keep the hot records of a Zipf-shaped field in L1); 3 L1::no_allocate (L2 only)
-#ifndef SV_REC_LOAD
-#define SV_REC_LOAD 0
-#endif
-__device__ __forceinline__ ColPack sv_load_record(const ColPack* p) {
-#if SV_REC_LOAD == 0 || defined(SVBFM_EMULATED)
+// The 32-byte record gather of k_stream. `no_alloc`: ld.global.nc.L1::no_allocate (the line goes from L2 to the registers without
+// taking an L1 line). Measured at 200 M ratings, K = 50 (gpurun call r2k, profiles/r02_k_*): the pass over the SECOND field gathers
+// the first field's records in column-id order with little reuse between requests: 47.5 -> 43.5 ms per iteration without the
+// allocation; the pass over the FIRST field gathers the rank-ordered records of the second (hot head dense in a few KB): 46.5 -> 61.8 ms
+// without it. ld.global.nc alone and nc + L1::evict_last change nothing (108.2 / 108.6 against 107.9 ms per iteration).
+__device__ __forceinline__ ColPack sv_load_record(const ColPack* p, bool no_alloc) {
+#if defined(SVBFM_EMULATED)
+    (void)no_alloc;
     return *p;
 #else
+    if (!no_alloc) return *p;
     ColPack r;
-#if SV_REC_LOAD == 1
-    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.mu), "=d"(r.sg), "=d"(r.delta), "=d"(r.h4) : "l"(p));
-#elif SV_REC_LOAD == 2
-    asm volatile("ld.global.nc.L1::evict_last.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.mu), "=d"(r.sg), "=d"(r.delta), "=d"(r.h4) : "l"(p));
-#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.mu), "=d"(r.sg), "=d"(r.delta), "=d"(r.h4) : "l"(p));
-#endif
     return r;
 #endif
 }
@@ -384,6 +380,8 @@ struct FinalizeArgs {
     const double* col_count;     // [D]
     const uint64_t* colptr;      // batch column sizes come from colsum C-slot instead (see engine)
     const uint32_t* gcnt;        // vb_online on the sharded stream schedule: global batch entries of every column (indexed like span.colptr)
+    const uint32_t* col_list;    // vb_online on the stream schedule: the batch's non-empty columns of the run (null: every column c0 .. c1)
+    uint32_t n_list;
     int update_t;                // vb_online: 1 when this sweep advances t_cnt (w: always; v: f == 0)
 };
 
@@ -468,6 +466,11 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
 template <int KIND>
 __global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __restrict__ cnt_arr, double lamda, uint32_t t0, int update_params) {
     uint32_t j = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.col_list) {        // empty columns are skipped anyway (vbo.h:367, 394) and nothing reads their delta on the stream schedule
+        const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+        if (t >= a.n_list) return;
+        j = a.col_list[t];
+    }
     if (j >= a.c1) return;
     double A, B, C1, C2;
     double cnt;
@@ -577,6 +580,7 @@ struct StreamArgs {
     const float* xo;
     double* e;                // this side's copy of the residuals, index = entry - entry0
     const ColPack* rec;       // records of the other side's columns
+    int rec_no_alloc;         // gather them without allocating L1 lines (sv_load_record)
     const OwnPack* own;       // constants of this side's columns
     int has_own, own_is_w;    // a pending update of this side (own_is_w: it was a w step, h = 1)
     int has_oth, oth_is_w;    // a pending update of the other side
@@ -767,6 +771,7 @@ __global__ void __launch_bounds__(32 * SV_STREAM_WARPS, ONES ? SV_STREAM_MINB : 
     const bool has_oth = STEADY ? true : (a.has_oth != 0), oth_is_w = STEADY ? false : (a.oth_is_w != 0);
     const bool pend = has_own | has_oth;
     const bool need_rec = (IS_V && REDUCE) || has_oth || (has_own && !own_is_w);
+    const bool rec_na = a.rec_no_alloc != 0;
 
     // next batch of the streams (issued one batch ahead)
     uint32_t oc_n[U]; float xs_n[U], xo_n[U]; double e_n[U];
@@ -939,11 +944,11 @@ __global__ void __launch_bounds__(32 * SV_STREAM_WARPS, ONES ? SV_STREAM_MINB : 
     auto gather = [&](uint32_t q0, const uint32_t (&oc)[U], ColPack (&g)[U]) {
         if ((STEADY || need_rec) && q_end - q0 >= 32 * U) {
 #pragma unroll
-            for (int u = 0; u < U; u++) g[u] = sv_load_record(a.rec + oc[u]);
+            for (int u = 0; u < U; u++) g[u] = sv_load_record(a.rec + oc[u], rec_na);
         } else {
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                if (need_rec && q0 + u * 32 + lane < q_end) g[u] = sv_load_record(a.rec + oc[u]);
+                if (need_rec && q0 + u * 32 + lane < q_end) g[u] = sv_load_record(a.rec + oc[u], rec_na);
                 else g[u] = ColPack{0.0, 0.0, 0.0, 0.0};
             }
         }
