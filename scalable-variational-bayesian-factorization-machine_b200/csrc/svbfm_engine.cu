@@ -451,6 +451,10 @@ static void launch_stream(Engine* E, int side, bool has_own, bool own_is_w, bool
     a.e = side ? E->d_e2 : E->d_e;
     a.rec = E->d_cpack; a.own = E->d_opack;
     a.rec_no_alloc = (E->rec_na_mask >> side) & 1;
+    // rank layout, one GPU: the first field's pass keeps the records of the rec_hot most popular second-field columns in L1 and
+    // fetches the others past it (a cold record would take a 128-byte line for its 32 bytes and push a hot one out)
+    a.rec_hot_end = 0xffffffffu;
+    if (side == 0 && E->rec_rank && !E->xs && E->rec_hot > 0) a.rec_hot_end = E->runs[1].col_begin + (uint32_t)E->rec_hot;
     a.has_own = has_own; a.own_is_w = own_is_w; a.has_oth = has_oth; a.oth_is_w = oth_is_w;
     a.colsum = E->d_colsum;
     constexpr int KIND = MCMC ? (W ? KIND_MC_W : KIND_MC_V) : (W ? KIND_VB_W : KIND_VB_V);
@@ -894,6 +898,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     if (const char* rr = getenv("SVBFM_REC_RANK")) E->want_rec_rank = atoi(rr) != 0;    // default on; 0: records in column order
     if (const char* gr = getenv("SVBFM_GRAPH")) E->use_graph = atoi(gr) != 0;
     if (const char* na = getenv("SVBFM_REC_NA")) E->rec_na_mask = atoi(na);              // bit s: side s gathers its records past L1 (default 2)
+    if (const char* rh = getenv("SVBFM_REC_HOT")) E->rec_hot = atoi(rh);                // first-field pass: records of the rank layout kept in L1 (0: all)
     if (const char* te = getenv("SVBFM_TILE_ENTRIES")) if (atoi(te) >= 32) E->tile_entries = (uint32_t)atoi(te);   // tuning knob
     // implicit tiles of the stream schedule: 4096 entries unless the caller (or the knob) says otherwise
     uint32_t ts = (cfg->tile_entries || getenv("SVBFM_TILE_ENTRIES")) ? E->tile_entries : 4096u;

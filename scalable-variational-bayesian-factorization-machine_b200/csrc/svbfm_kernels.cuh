@@ -466,27 +466,68 @@ __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
 template <int KIND>
 __global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __restrict__ cnt_arr, double lamda, uint32_t t0, int update_params) {
     uint32_t j = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    bool act = j < a.c1;
     if (a.col_list) {        // empty columns are skipped anyway (vbo.h:367, 394) and nothing reads their delta on the stream schedule
         const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-        if (t >= a.n_list) return;
-        j = a.col_list[t];
+        act = t < a.n_list;
+        j = act ? a.col_list[t] : a.c0;
+        act = act && j < a.c1;
     }
-    if (j >= a.c1) return;
-    double A, B, C1, C2;
-    double cnt;
+    double A = 0.0, B = 0.0, C1 = 0.0, C2 = 0.0;
+    double cnt = 0.0;
     if (a.span.colptr) {
         // stream schedule: colptr is the batch's own column pointer, so the column's batch entries are counted directly.
-        // Records of a skipped column are not written: no entry of the batch refers to it.
-        cnt = a.gcnt ? (double)a.gcnt[j] : (double)(a.span.colptr[j + 1] - a.span.colptr[j]);
-        if (cnt == 0.0 || !update_params) { a.delta[j] = 0.0; return; }
-        bool empty;
-        if (a.from_colsum || !span_sum(j, a.span, a.partial, A, B, C1, C2, empty)) {
+        // Records of a skipped column are not written: no entry of the batch refers to it. No thread leaves before the
+        // cooperative part below: the lanes of a warp sum a long span together.
+        if (act) cnt = a.gcnt ? (double)a.gcnt[j] : (double)(a.span.colptr[j + 1] - a.span.colptr[j]);
+        const bool live = act && cnt != 0.0 && update_params;
+        if (act && !live) a.delta[j] = 0.0;
+        uint64_t T0 = 0, T1 = 0;
+        bool from_cs = true;                    // colsum[j] holds the sums (one-tile column, or summed before)
+        if (live && !a.from_colsum) {
+            const uint64_t b = a.span.colptr[j], e = a.span.colptr[j + 1];
+            if (e > b) {
+                T0 = (b - a.span.entry0) >> a.span.ts_shift; T1 = (e - 1 - a.span.entry0) >> a.span.ts_shift;
+                from_cs = (T0 == T1);
+            }
+        }
+        // a column over 32 tiles and more (the heaviest users of a batch span hundreds of 256-entry tiles): all lanes of the warp take
+        // its pieces together, fixed order; one thread alone needed ~90 us for the longest and every finalize of the batch waited for it
+        const unsigned lane = threadIdx.x & 31;
+        unsigned long_mask = __ballot_sync(0xffffffffu, live && !from_cs && (T1 - T0 >= 32));
+        while (long_mask) {
+            const int src = __ffs(long_mask) - 1;
+            long_mask &= long_mask - 1;
+            const uint64_t t0s = __shfl_sync(0xffffffffu, T0, src), t1s = __shfl_sync(0xffffffffu, T1, src);
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+            for (uint64_t T = t0s + lane; T <= t1s; T += 32) {
+                const double2* p = reinterpret_cast<const double2*>(a.partial + (T * 2 + (T == t0s ? 1 : 0)) * 4);
+                double2 x = p[0], y = p[1];
+                v0 += x.x; v1 += x.y; v2 += y.x; v3 += y.y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                v2 += __shfl_xor_sync(0xffffffffu, v2, o); v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+            }
+            if ((int)lane == src) { A = v0; B = v1; C1 = v2; C2 = v3; from_cs = false; T1 = T0 = 0; cnt = -cnt; }    // marked: sums are in registers
+        }
+        if (!live) return;
+        if (cnt < 0.0) cnt = -cnt;              // a long span: done above
+        else if (from_cs) {
             const double2* p = reinterpret_cast<const double2*>(a.colsum + (size_t)j * 4);
             double2 x = p[0], y = p[1];
             A = x.x; B = x.y; C1 = y.x; C2 = y.y;
+        } else {
+            for (uint64_t T = T0; T <= T1; T++) {
+                const double2* p = reinterpret_cast<const double2*>(a.partial + (T * 2 + (T == T0 ? 1 : 0)) * 4);
+                double2 x = p[0], y = p[1];
+                A += x.x; B += x.y; C1 += y.x; C2 += y.y;
+            }
         }
         if constexpr (KIND == KIND_VBO_V) B = C1 + C2;
     } else {
+        if (!act) return;
         load_colsum(j, a.col_tile0, a.partial, a.colsum, a.from_colsum, A, B, C1, C2);
         if constexpr (KIND == KIND_VBO_W) { cnt = C1; cnt_arr[j] = cnt; }   // the w pass also counts the batch entries of the column
         else cnt = cnt_arr[j];
@@ -581,6 +622,7 @@ struct StreamArgs {
     double* e;                // this side's copy of the residuals, index = entry - entry0
     const ColPack* rec;       // records of the other side's columns
     int rec_no_alloc;         // gather them without allocating L1 lines (sv_load_record)
+    uint32_t rec_hot_end;     // ... or only the records from this slot on (rank layout: the slots below are the hot head that L1 should keep)
     const OwnPack* own;       // constants of this side's columns
     int has_own, own_is_w;    // a pending update of this side (own_is_w: it was a w step, h = 1)
     int has_oth, oth_is_w;    // a pending update of the other side
@@ -944,11 +986,11 @@ __global__ void __launch_bounds__(32 * SV_STREAM_WARPS, ONES ? SV_STREAM_MINB : 
     auto gather = [&](uint32_t q0, const uint32_t (&oc)[U], ColPack (&g)[U]) {
         if ((STEADY || need_rec) && q_end - q0 >= 32 * U) {
 #pragma unroll
-            for (int u = 0; u < U; u++) g[u] = sv_load_record(a.rec + oc[u], rec_na);
+            for (int u = 0; u < U; u++) g[u] = sv_load_record(a.rec + oc[u], rec_na || oc[u] >= a.rec_hot_end);
         } else {
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                if (need_rec && q0 + u * 32 + lane < q_end) g[u] = sv_load_record(a.rec + oc[u], rec_na);
+                if (need_rec && q0 + u * 32 + lane < q_end) g[u] = sv_load_record(a.rec + oc[u], rec_na || oc[u] >= a.rec_hot_end);
                 else g[u] = ColPack{0.0, 0.0, 0.0, 0.0};
             }
         }

@@ -310,6 +310,22 @@ def test_reset_reuses_handle(built):
     assert h1 == h2
 
 
+def test_vb_online_long_spans_in_a_batch(built):
+    """vb_online on the stream schedule with 32-entry tiles and ten users: every user's column spans ~60 tiles of a batch, which the
+    lanes of a warp sum together in k_finalize_vbo (a single thread used to walk them: the critical path of every finalize at 200 M)."""
+    tr, te = two_field(40000, 500, 10, 700, seed=77)
+    want = []
+    orc = ob.Oracle("vb_online", tr, te, K=2, seed=42, num_batch=2)
+    for _ in range(2):
+        s = orc.iterate()
+        want.append((s.test_rmse, s.free_energy, s.alpha))
+    L = make_learner("vb_online", tr, te, 2, num_iter=2, num_batch=2, tile_entries=32)
+    for it, s in enumerate(L.learn(to_csc(tr), to_csc(te))):
+        assert rel(s.test_rmse, want[it][0]) < VB_TOL and rel(s.free_energy, want[it][1]) < VB_TOL and rel(s.alpha, want[it][2]) < VB_TOL
+    assert L.engine.info()["fused_schedule"] & 1
+    L.engine.close()
+
+
 def test_values_may_be_null_for_one_hot_data(built):
     """x = NULL in svbfm_set_csc / svbfm_set_csr says "every value is 1": same statistics, bit for bit, as an explicit array of ones,
     column-wise and row-wise (the device transpose)."""
