@@ -462,7 +462,8 @@ def parity_vs_single_gpu(cx, a, warm_hist, hist, tol=1e-6):
 
 
 OTHER_CONFIGS = [   # (workload, method, steps, warmup): BASELINE.json configs 2-5 next to the headline (which is kdd200m vb)
-    ("ml1m", "vb", 20, 5), ("ml10m", "vb", 10, 3), ("ml10m", "mcmc", 10, 3), ("netflix", "vb", 3, 2), ("kdd200m", "vb_online", 1, 1), ("kdd200m", "mcmc", 3, 2)]
+    # (steps sized so that every timed region lasts at least half a second: the clock sampler ticks every 100 ms)
+    ("ml1m", "vb", 400, 20), ("ml10m", "vb", 60, 5), ("ml10m", "mcmc", 60, 5), ("netflix", "vb", 6, 2), ("kdd200m", "vb_online", 1, 1), ("kdd200m", "mcmc", 4, 2)]
 
 
 def other_configs(cx, a, peak):
