@@ -440,7 +440,7 @@ static void launch_stream(Engine* E, int side, bool has_own, bool own_is_w, bool
     a.c0 = r.col_begin; a.c1 = r.col_end; a.real0 = sv.entry0; a.ts_shift = E->ts_shift;
     if (E->bv.on) {
         a.colptr = E->bv.colptr[side]; a.entry0 = E->bv.entry0; a.n = E->bv.n; a.ntiles = E->bv.ntiles; a.ts_shift = E->vbo_ts_shift;
-        a.tile_col0 = E->d_vbo_tile_col0 + (side ? E->vbo_max_tiles : 0); a.idx = E->d_vbo_idx[side];
+        a.tile_col0 = E->d_vbo_tile_col0 + (side ? E->vbo_max_tiles : 0); a.idx = E->bv.packed ? nullptr : E->d_vbo_idx[side];
         a.partial = E->d_vbo_partial + (side ? (size_t)E->vbo_max_tiles * 8 : 0);
     } else {
         a.colptr = sv.colptr; a.entry0 = a.real0; a.n = sv.n; a.ntiles = E->s_ntiles[side];
@@ -449,6 +449,10 @@ static void launch_stream(Engine* E, int side, bool has_own, bool own_is_w, bool
     }
     a.oc = sv.oc; a.xv = sv.xv; a.xo = sv.xo;
     a.e = side ? E->d_e2 : E->d_e;
+    if (E->bv.on && E->bv.packed) {     // the batch's own contiguous streams (k_vbo_pack): entry k of the pass is element k
+        a.real0 = 0; a.oc = E->d_vbo_ocb[side]; a.e = E->d_vbo_eb[side];
+        if (sv.xv) { a.xv = E->d_vbo_xb[side][0]; a.xo = E->d_vbo_xb[side][1]; }
+    }
     a.rec = E->d_cpack; a.own = E->d_opack;
     a.rec_no_alloc = (E->rec_na_mask >> side) & 1;
     // rank layout, one GPU: the first field's pass keeps the records of the rec_hot most popular second-field columns in L1 and
@@ -547,6 +551,12 @@ int stream_tile_cols(Engine* E) {
 
 // every e_i += w0_delta, on both copies
 static void shift_e(Engine* E) {
+    if (E->bv.on && E->bv.packed) {
+        const uint32_t n = E->bv.n, grid = std::max(1u, std::min<unsigned>(nblk(n), SV_RGRID));
+        k_shift_e<<<grid, 256, 0, E->stream>>>(E->d_vbo_eb[0], n, E->d_sc); LAUNCHED(E);
+        k_shift_e<<<grid, 256, 0, E->stream>>>(E->d_vbo_eb[1], n, E->d_sc); LAUNCHED(E);
+        return;
+    }
     if (E->bv.on && E->bv.lists) {      // vb_online batch on the stream schedule: only the entries of the batch are live
         const uint32_t n = E->bv.n, grid = std::max(1u, std::min<unsigned>(nblk(n), SV_RGRID));
         k_shift_e_list<<<grid, 256, 0, E->stream>>>(E->d_e, E->d_vbo_idx[0] + E->bv.entry0, n, E->d_sc); LAUNCHED(E);
@@ -568,6 +578,12 @@ static void sync_e2(Engine* E) {
 // sum e, sum e^2, sum clamp(e)^2 -> red[0..2] (global)
 static int reduce_e(Engine* E, int batch = -1) {
     cudaStream_t st = E->stream;
+    if (E->bv.on && E->bv.packed) {     // packed batch: its residuals are one contiguous array
+        const uint32_t n = E->bv.n, grid = std::max(1u, std::min<unsigned>(nblk(n), SV_RGRID));
+        k_reduce_e<<<grid, 256, 0, st>>>(E->d_vbo_eb[0], n, E->d_sc, E->d_red_partial, nullptr, 0u); LAUNCHED(E);
+        k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, grid, 3, RED(E->d_sc, 0), 0); LAUNCHED(E);
+        return allreduce_sum_f64(E, RED(E->d_sc, 0), 3);
+    }
     if (E->bv.on && E->bv.lists) {      // vb_online batch on the stream schedule: the batch's own case list (positions in e = device case ids)
         const uint32_t n = E->bv.n, grid = std::max(1u, std::min<unsigned>(nblk(n), SV_RGRID));
         k_reduce_e_list<<<grid, 256, 0, st>>>(E->d_e, E->d_vbo_idx[0] + E->bv.entry0, n, E->d_sc, E->d_red_partial); LAUNCHED(E);
@@ -898,6 +914,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     if (const char* rr = getenv("SVBFM_REC_RANK")) E->want_rec_rank = atoi(rr) != 0;    // default on; 0: records in column order
     if (const char* gr = getenv("SVBFM_GRAPH")) E->use_graph = atoi(gr) != 0;
     if (const char* na = getenv("SVBFM_REC_NA")) E->rec_na_mask = atoi(na);              // bit s: side s gathers its records past L1 (default 2)
+    if (const char* vp = getenv("SVBFM_VBO_PACK")) E->vbo_pack = atoi(vp) != 0;          // default on; 0: the batch passes read through the index lists
     if (const char* rh = getenv("SVBFM_REC_HOT")) E->rec_hot = atoi(rh);                // first-field pass: records of the rank layout kept in L1 (0: all)
     if (const char* te = getenv("SVBFM_TILE_ENTRIES")) if (atoi(te) >= 32) E->tile_entries = (uint32_t)atoi(te);   // tuning knob
     // implicit tiles of the stream schedule: 4096 entries unless the caller (or the knob) says otherwise
@@ -952,7 +969,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_gcnt[0], E->d_vbo_gcnt[1], E->d_vbo_clist[0], E->d_vbo_clist[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_gcnt[0], E->d_vbo_gcnt[1], E->d_vbo_clist[0], E->d_vbo_clist[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_vbo_eb[0], E->d_vbo_eb[1], E->d_vbo_ocb[0], E->d_vbo_ocb[1], E->d_vbo_xb[0][0], E->d_vbo_xb[0][1], E->d_vbo_xb[1][0], E->d_vbo_xb[1][1], E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) sv_free(p);
     cudaStreamSynchronize(E->stream);
     if (E->copy_stream) { cudaStreamSynchronize(E->copy_stream); cudaStreamDestroy(E->copy_stream); }
@@ -1385,15 +1402,15 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
     cudaEvent_t t0, t1, t2;
     cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
     cudaEventRecord(t0, st);
+    // on the stream schedule the prediction, the reductions and the w0 shift of a batch walk the batch's own case list
+    // (E->bv) instead of masking the whole arrays; SVBFM_VBO_FULL_PASSES=1 keeps the masked passes (for comparison)
+    const bool full_passes = getenv("SVBFM_VBO_FULL_PASSES") != nullptr;
     for (uint32_t b = 0; b < num_batch; b++) {
         k_vbo_batch_begin<<<1, 1, 0, st>>>(E->d_sc, E->d_batch_n, b); LAUNCHED(E);
         const uint32_t nb_cases = use_streams ? (uint32_t)(E->vbo_off[b + 1] - E->vbo_off[b]) : 0u;
-        // on the stream schedule the prediction, the reductions and the w0 shift of a batch walk the batch's own case list
-        // (E->bv) instead of masking the whole arrays; SVBFM_VBO_FULL_PASSES=1 keeps the masked passes (for comparison)
-        const bool full_passes = getenv("SVBFM_VBO_FULL_PASSES") != nullptr;
-        struct BvGuard { Engine* E; ~BvGuard() { E->bv.on = false; } } bv_guard{E};      // every exit leaves the whole-run views in force
+        struct BvGuard { Engine* E; ~BvGuard() { E->bv.on = false; E->bv.packed = false; } } bv_guard{E};      // every exit leaves the whole-run views in force
         const bool batch_streams = use_streams && (nb_cases || E->world > 1);      // sharded: a rank without cases in the batch still takes part in the collectives
-        if (batch_streams) { E->bv.on = true; E->bv.lists = !full_passes; E->bv.entry0 = E->vbo_off[b]; E->bv.n = nb_cases; }
+        if (batch_streams) { E->bv.on = true; E->bv.lists = !full_passes; E->bv.packed = false; E->bv.entry0 = E->vbo_off[b]; E->bv.n = nb_cases; }
         // fresh y-hat, T for the cases of the batch (vbos.h:120-127)
         if (int rc = predict<PRED_VB_TRAIN>(E, S, E->d_e, 6, 1, (int)b)) return rc;
         SV_CUDA(E, cudaMemcpyAsync(&E->d_sc->sum_t, RED(E->d_sc, 6), 8, cudaMemcpyDeviceToDevice, st));
@@ -1413,8 +1430,24 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
                                                                    E->d_vbo_tile_col0 + (ri ? E->vbo_max_tiles : 0)); LAUNCHED(E);
                 }
             }
-            // second residual copy for the entries of the batch
-            if (nb_cases) {
+            if (E->vbo_pack && E->bv.lists) {
+                // the batch's residuals (both entry orders), other-column ids and x values as contiguous streams
+                if (nb_cases) {
+                    VboPackArgs pa{};
+                    pa.e = E->d_e; pa.crow1 = S.crow + S.h_colptr[r1.col_begin]; pa.n = nb_cases;
+                    for (int ri = 0; ri < 2; ri++) {
+                        const Engine::SideView& sv = E->side[ri];
+                        pa.idx[ri] = E->d_vbo_idx[ri] + E->vbo_off[b];
+                        pa.oc[ri] = sv.oc + sv.entry0;
+                        pa.xv[ri] = sv.xv ? sv.xv + sv.entry0 : nullptr; pa.xo[ri] = sv.xo ? sv.xo + sv.entry0 : nullptr;
+                        pa.eb[ri] = E->d_vbo_eb[ri]; pa.ocb[ri] = E->d_vbo_ocb[ri];
+                        pa.xvb[ri] = E->d_vbo_xb[ri][0]; pa.xob[ri] = E->d_vbo_xb[ri][1];
+                    }
+                    k_vbo_pack<<<nblk(nb_cases), 256, 0, st>>>(pa); LAUNCHED(E);
+                }
+                E->bv.packed = true;
+            } else if (nb_cases) {
+                // second residual copy for the entries of the batch
                 k_gather_e_idx<<<nblk(nb_cases), 256, 0, st>>>(E->d_e, S.crow + S.h_colptr[r1.col_begin], E->d_vbo_idx[1], (uint32_t)E->vbo_off[b],
                                                                 (uint32_t)E->vbo_off[b + 1], E->d_e2); LAUNCHED(E);
             }
@@ -1434,6 +1467,10 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
                     if (int rc = sweep_run<KIND_VBO_V>(E, r, f, (int)b)) return rc;
         }
         if (int rc = reduce_e(E, (int)b)) return rc;
+        if (E->bv.on && E->bv.packed && nb_cases) {      // the batch's residuals back into e / e2
+            k_vbo_unpack<<<nblk(nb_cases), 256, 0, st>>>(E->d_vbo_eb[0], E->d_vbo_eb[1], E->d_vbo_idx[0] + E->vbo_off[b], E->d_vbo_idx[1] + E->vbo_off[b], nb_cases,
+                                                        E->d_e, E->d_e2); LAUNCHED(E);
+        }
         k_reduce_dT<<<SV_GGRID, 256, 0, st>>>(E->d_dT, E->D, E->d_red_partial); LAUNCHED(E);
         if (use_streams && E->world > 1) {       // sharded stream schedule: every rank holds its own share of d(sum T)
             k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_GGRID, 1, RED(E->d_sc, 6), 0); LAUNCHED(E);

@@ -1129,6 +1129,23 @@ int vbo_stream_prepare(Engine* E, uint32_t num_batch) {
         if (dev_alloc(E, &E->d_vbo_partial, (size_t)max_tiles * 2 * 8)) return SVBFM_ERR_OOM;
         E->vbo_max_tiles = max_tiles;
     }
+    // the batch in flight as contiguous streams (engine: k_vbo_pack)
+    uint64_t max_batch = 1;
+    for (uint32_t b = 0; b < num_batch; b++) max_batch = std::max<uint64_t>(max_batch, E->vbo_off[b + 1] - E->vbo_off[b]);
+    const bool with_x = E->side[0].xv != nullptr;
+    if (E->vbo_pack && (max_batch > E->vbo_batch_cap || (with_x && !E->d_vbo_xb[0][0]))) {
+        for (int ri = 0; ri < 2; ri++) {
+            sv_free(E->d_vbo_eb[ri]); sv_free(E->d_vbo_ocb[ri]); sv_free(E->d_vbo_xb[ri][0]); sv_free(E->d_vbo_xb[ri][1]);
+            E->d_vbo_eb[ri] = nullptr; E->d_vbo_ocb[ri] = nullptr; E->d_vbo_xb[ri][0] = nullptr; E->d_vbo_xb[ri][1] = nullptr;
+        }
+        E->vbo_batch_cap = 0;
+        for (int ri = 0; ri < 2; ri++) {
+            if (dev_alloc(E, &E->d_vbo_eb[ri], max_batch)) return SVBFM_ERR_OOM;
+            if (dev_alloc(E, &E->d_vbo_ocb[ri], max_batch)) return SVBFM_ERR_OOM;
+            if (with_x && (dev_alloc(E, &E->d_vbo_xb[ri][0], max_batch) || dev_alloc(E, &E->d_vbo_xb[ri][1], max_batch))) return SVBFM_ERR_OOM;
+        }
+        E->vbo_batch_cap = (uint32_t)max_batch;
+    }
     uint32_t *d_keys = nullptr, *d_vals = nullptr, *d_skeys = nullptr;
     SV_CUDA(E, sv_malloc((void**)&d_keys, std::max<size_t>(n, 1) * 4));
     SV_CUDA(E, sv_malloc((void**)&d_vals, std::max<size_t>(n, 1) * 4));

@@ -147,9 +147,18 @@ struct Engine {
     double* d_vbo_partial = nullptr;                       // [2][vbo_max_tiles][2][4]
     uint32_t vbo_max_tiles = 0;
     std::vector<uint64_t> vbo_off;                         // [num_batch + 1] first entry of every batch in idx
+    // ... and the batch in flight packed into contiguous streams (k_vbo_pack): a batch is a random 1/num_batch of the cases, so
+    // reading its residuals and other-column ids through idx costs a 32-byte sector per 8- / 4-byte value in each of the
+    // 2 (K + 1) passes of the batch; packed once per batch, the passes stream them like a whole-run pass does
+    double* d_vbo_eb[2] = {nullptr, nullptr};              // [vbo_batch_cap] residuals of the batch in idx order of run 0 / run 1
+    uint32_t* d_vbo_ocb[2] = {nullptr, nullptr};           // [vbo_batch_cap] other-column id / record slot of every batch entry
+    float* d_vbo_xb[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side][own x, other x][vbo_batch_cap] (x != 1 only)
+    uint32_t vbo_batch_cap = 0;
+    bool vbo_pack = true;                                  // SVBFM_VBO_PACK=0: the passes read through idx (round 1 / 2 path, kept for comparison)
     struct BatchView {                                      // what launch_stream / combine_finalize use instead of the whole run
         bool on = false;
         bool lists = false;                                 // prediction / reductions / w0 shift of the batch walk its case list too
+        bool packed = false;                                // the batch's streams are packed (d_vbo_eb / d_vbo_ocb): passes, reductions and shifts run on them
         const uint64_t* colptr[2] = {nullptr, nullptr};
         const uint32_t* gcnt[2] = {nullptr, nullptr};       // sharded: global batch entries per column (same indexing as colptr)
         const uint32_t* clist[2] = {nullptr, nullptr};      // the batch's non-empty columns of run 0 / 1 (null: all columns)

@@ -1149,6 +1149,45 @@ __global__ void k_gather_e_idx(const double* __restrict__ e, const uint32_t* __r
     e2[p] = e[crow1[p]];
 }
 
+// The batch in flight as contiguous streams. A batch is a random 1 / num_batch of the cases: read through idx, every 8-byte
+// residual and 4-byte column id of a pass costs a 32-byte sector (ncu, 200 M ratings in 100 batches: 588 MB from HBM per pass
+// for 40 MB of entries, profiles/r02_n_*). Packed once per batch (this kernel: one such scattered read), the 2 (K + 1) passes,
+// the reductions and the w0 shifts of the batch stream them; k_vbo_unpack puts the residuals back at the end of the batch so
+// that e / e2 read as before (svbfm_get_residuals, svbfm_copies_max_diff).
+struct VboPackArgs {
+    const double* e;               // residuals in device case order (fresh prediction of the batch's cases)
+    const uint32_t* idx[2];        // the batch's entries of run 0 / run 1 (positions inside the run), already offset to the batch
+    const uint32_t* crow1;         // case of every entry of run 1
+    const uint32_t* oc[2];         // other-column ids of run 0 / run 1, offset to the run's first entry
+    const float* xv[2];            // own x / other x of the runs (null: all ones)
+    const float* xo[2];
+    uint32_t n;
+    double* eb[2];
+    uint32_t* ocb[2];
+    float* xvb[2];
+    float* xob[2];
+};
+__global__ void __launch_bounds__(256) k_vbo_pack(VboPackArgs a) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n) return;
+    const uint32_t p0 = __ldcs(a.idx[0] + k), p1 = __ldcs(a.idx[1] + k);
+    a.eb[0][k] = a.e[p0];                          // run 0's entry order is the device case order
+    a.eb[1][k] = a.e[__ldg(a.crow1 + p1)];
+    a.ocb[0][k] = __ldg(a.oc[0] + p0);
+    a.ocb[1][k] = __ldg(a.oc[1] + p1);
+    if (a.xv[0]) {
+        a.xvb[0][k] = __ldg(a.xv[0] + p0); a.xob[0][k] = __ldg(a.xo[0] + p0);
+        a.xvb[1][k] = __ldg(a.xv[1] + p1); a.xob[1][k] = __ldg(a.xo[1] + p1);
+    }
+}
+__global__ void __launch_bounds__(256) k_vbo_unpack(const double* __restrict__ eb0, const double* __restrict__ eb1, const uint32_t* __restrict__ idx0,
+                                                    const uint32_t* __restrict__ idx1, uint32_t n, double* __restrict__ e, double* __restrict__ e2) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    e[__ldcs(idx0 + k)] = eb0[k];
+    e2[__ldcs(idx1 + k)] = eb1[k];
+}
+
 // sharded stream schedule: block exchange of run 0's parameters. row 0 = w (when present), then one row per factor.
 struct BlockXchg {
     double2* pw;              // null: no w row

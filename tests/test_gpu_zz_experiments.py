@@ -71,6 +71,27 @@ def test_vb_online_batch_lists_equal_masked_passes(built, monkeypatch):
         assert all(rel(x, y) < 1e-10 for x, y in zip(a, b)), (a, b)
 
 
+@pytest.mark.parametrize("values,tile_entries", [(False, 0), (False, 64), (True, 64)])
+def test_vb_online_packed_batches_equal_index_lists(built, monkeypatch, values, tile_entries):
+    """vb_online on the stream schedule: the batch in flight packed into contiguous streams (default; all-ones data then goes
+    through the bulk-copy ring like a whole-run pass) against passes that read through the batch's index lists
+    (SVBFM_VBO_PACK=0). Same operands in the same order: the statistics, the parameters and the residuals both runs leave
+    behind are bit-identical."""
+    tr, te = two_field(16000, 1600, 260, 190, seed=22, values=values)
+    out, res, par = [], [], []
+    for packed in ("1", "0"):
+        monkeypatch.setenv("SVBFM_VBO_PACK", packed)
+        L = make_learner("vb_online", tr, te, 3, num_iter=3, num_batch=7, tile_entries=tile_entries)
+        out.append([(s.test_rmse, s.free_energy, s.alpha) for s in L.learn(to_csc(tr), to_csc(te))])
+        assert L.engine.info()["fused_schedule"] & 1
+        res.append(L.engine.get_residuals())
+        par.append(np.concatenate([np.ravel(x) for x in L.engine.get_state().values()]))
+        assert L.engine.copies_max_diff() == 0.0
+        L.engine.close()
+    assert out[0] == out[1], out
+    assert np.array_equal(res[0], res[1]) and np.array_equal(par[0], par[1])
+
+
 # ---- binary classification (-task c) for mcmc / als: SURVEY section 8(f) rank 4. Built and emulator-checked without a GPU.
 def _binary_two_field(n, nt, U, I, seed, values=False):
     tr, te = two_field(n, nt, U, I, seed=seed, values=values)
