@@ -450,7 +450,7 @@ static void launch_stream(Engine* E, int side, bool has_own, bool own_is_w, bool
     a.oc = sv.oc; a.xv = sv.xv; a.xo = sv.xo;
     a.e = side ? E->d_e2 : E->d_e;
     if (E->bv.on && E->bv.packed) {     // the batch's own contiguous streams (k_vbo_pack): entry k of the pass is element k
-        a.real0 = 0; a.oc = E->d_vbo_ocb[side]; a.e = E->d_vbo_eb[side];
+        a.real0 = 0; a.oc = E->d_vbo_ocb[side]; a.e = E->d_vbo_eb[side]; a.ownc = E->d_vbo_ownb[side];
         if (sv.xv) { a.xv = E->d_vbo_xb[side][0]; a.xo = E->d_vbo_xb[side][1]; }
     }
     a.rec = E->d_cpack; a.own = E->d_opack;
@@ -471,6 +471,16 @@ static void launch_stream(Engine* E, int side, bool has_own, bool own_is_w, bool
         if (a.idx) { if constexpr (!MCMC) k_stream<KIND, ONES, REDUCE, STEADY, true><<<grid, ST, 0, E->stream>>>(a); } \
         else k_stream<KIND, ONES, REDUCE, STEADY, false><<<grid, ST, 0, E->stream>>>(a);                           \
     } while (0)
+    if constexpr (!MCMC) {
+        if (E->bv.on && E->bv.packed && E->vbo_rows) {      // a packed vb_online batch: rows of 32 entries reduced at once (k_stream_rows)
+#define CALL_R(ONES, STEADY) k_stream_rows<KIND, ONES, REDUCE, STEADY><<<grid, ST, 0, E->stream>>>(a)
+            if (steady) { if (S.all_ones) CALL_R(true, true); else CALL_R(false, true); }
+            else { if (S.all_ones) CALL_R(true, false); else CALL_R(false, false); }
+#undef CALL_R
+            LAUNCHED(E);
+            return;
+        }
+    }
     // all-ones streams are staged through shared memory by bulk copies (SVBFM_STREAM_TMA=0: plain loads); needs 16-byte aligned stream starts
     const bool tma = E->stream_tma && S.all_ones && !a.idx && (a.real0 % 4 == 0);
     if (tma) {
@@ -914,6 +924,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     if (const char* rr = getenv("SVBFM_REC_RANK")) E->want_rec_rank = atoi(rr) != 0;    // default on; 0: records in column order
     if (const char* gr = getenv("SVBFM_GRAPH")) E->use_graph = atoi(gr) != 0;
     if (const char* na = getenv("SVBFM_REC_NA")) E->rec_na_mask = atoi(na);              // bit s: side s gathers its records past L1 (default 2)
+    if (const char* vr = getenv("SVBFM_VBO_ROWS")) E->vbo_rows = atoi(vr) != 0;          // default on; 0: packed batches through k_stream
     if (const char* vp = getenv("SVBFM_VBO_PACK")) E->vbo_pack = atoi(vp) != 0;          // default on; 0: the batch passes read through the index lists
     if (const char* rh = getenv("SVBFM_REC_HOT")) E->rec_hot = atoi(rh);                // first-field pass: records of the rank layout kept in L1 (0: all)
     if (const char* te = getenv("SVBFM_TILE_ENTRIES")) if (atoi(te) >= 32) E->tile_entries = (uint32_t)atoi(te);   // tuning knob
@@ -969,7 +980,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_gcnt[0], E->d_vbo_gcnt[1], E->d_vbo_clist[0], E->d_vbo_clist[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_vbo_eb[0], E->d_vbo_eb[1], E->d_vbo_ocb[0], E->d_vbo_ocb[1], E->d_vbo_xb[0][0], E->d_vbo_xb[0][1], E->d_vbo_xb[1][0], E->d_vbo_xb[1][1], E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_gcnt[0], E->d_vbo_gcnt[1], E->d_vbo_clist[0], E->d_vbo_clist[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_vbo_eb[0], E->d_vbo_eb[1], E->d_vbo_ocb[0], E->d_vbo_ocb[1], E->d_vbo_ownb[0], E->d_vbo_ownb[1], E->d_vbo_xb[0][0], E->d_vbo_xb[0][1], E->d_vbo_xb[1][0], E->d_vbo_xb[1][1], E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) sv_free(p);
     cudaStreamSynchronize(E->stream);
     if (E->copy_stream) { cudaStreamSynchronize(E->copy_stream); cudaStreamDestroy(E->copy_stream); }
@@ -1434,13 +1445,13 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
                 // the batch's residuals (both entry orders), other-column ids and x values as contiguous streams
                 if (nb_cases) {
                     VboPackArgs pa{};
-                    pa.e = E->d_e; pa.crow1 = S.crow + S.h_colptr[r1.col_begin]; pa.n = nb_cases;
+                    pa.e = E->d_e; pa.rcol = S.rcol; pa.crow1 = S.crow + S.h_colptr[r1.col_begin]; pa.n = nb_cases;
                     for (int ri = 0; ri < 2; ri++) {
                         const Engine::SideView& sv = E->side[ri];
                         pa.idx[ri] = E->d_vbo_idx[ri] + E->vbo_off[b];
                         pa.oc[ri] = sv.oc + sv.entry0;
                         pa.xv[ri] = sv.xv ? sv.xv + sv.entry0 : nullptr; pa.xo[ri] = sv.xo ? sv.xo + sv.entry0 : nullptr;
-                        pa.eb[ri] = E->d_vbo_eb[ri]; pa.ocb[ri] = E->d_vbo_ocb[ri];
+                        pa.eb[ri] = E->d_vbo_eb[ri]; pa.ocb[ri] = E->d_vbo_ocb[ri]; pa.ownb[ri] = E->d_vbo_ownb[ri];
                         pa.xvb[ri] = E->d_vbo_xb[ri][0]; pa.xob[ri] = E->d_vbo_xb[ri][1];
                     }
                     k_vbo_pack<<<nblk(nb_cases), 256, 0, st>>>(pa); LAUNCHED(E);

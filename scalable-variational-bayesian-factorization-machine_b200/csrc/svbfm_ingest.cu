@@ -1135,13 +1135,14 @@ int vbo_stream_prepare(Engine* E, uint32_t num_batch) {
     const bool with_x = E->side[0].xv != nullptr;
     if (E->vbo_pack && (max_batch > E->vbo_batch_cap || (with_x && !E->d_vbo_xb[0][0]))) {
         for (int ri = 0; ri < 2; ri++) {
-            sv_free(E->d_vbo_eb[ri]); sv_free(E->d_vbo_ocb[ri]); sv_free(E->d_vbo_xb[ri][0]); sv_free(E->d_vbo_xb[ri][1]);
-            E->d_vbo_eb[ri] = nullptr; E->d_vbo_ocb[ri] = nullptr; E->d_vbo_xb[ri][0] = nullptr; E->d_vbo_xb[ri][1] = nullptr;
+            sv_free(E->d_vbo_eb[ri]); sv_free(E->d_vbo_ocb[ri]); sv_free(E->d_vbo_ownb[ri]); sv_free(E->d_vbo_xb[ri][0]); sv_free(E->d_vbo_xb[ri][1]);
+            E->d_vbo_eb[ri] = nullptr; E->d_vbo_ocb[ri] = nullptr; E->d_vbo_ownb[ri] = nullptr; E->d_vbo_xb[ri][0] = nullptr; E->d_vbo_xb[ri][1] = nullptr;
         }
         E->vbo_batch_cap = 0;
         for (int ri = 0; ri < 2; ri++) {
             if (dev_alloc(E, &E->d_vbo_eb[ri], max_batch)) return SVBFM_ERR_OOM;
             if (dev_alloc(E, &E->d_vbo_ocb[ri], max_batch)) return SVBFM_ERR_OOM;
+            if (dev_alloc(E, &E->d_vbo_ownb[ri], max_batch)) return SVBFM_ERR_OOM;
             if (with_x && (dev_alloc(E, &E->d_vbo_xb[ri][0], max_batch) || dev_alloc(E, &E->d_vbo_xb[ri][1], max_batch))) return SVBFM_ERR_OOM;
         }
         E->vbo_batch_cap = (uint32_t)max_batch;

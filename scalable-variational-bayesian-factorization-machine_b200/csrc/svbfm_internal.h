@@ -152,8 +152,10 @@ struct Engine {
     // 2 (K + 1) passes of the batch; packed once per batch, the passes stream them like a whole-run pass does
     double* d_vbo_eb[2] = {nullptr, nullptr};              // [vbo_batch_cap] residuals of the batch in idx order of run 0 / run 1
     uint32_t* d_vbo_ocb[2] = {nullptr, nullptr};           // [vbo_batch_cap] other-column id / record slot of every batch entry
+    uint32_t* d_vbo_ownb[2] = {nullptr, nullptr};          // [vbo_batch_cap] own column of every batch entry (k_stream_rows)
     float* d_vbo_xb[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side][own x, other x][vbo_batch_cap] (x != 1 only)
     uint32_t vbo_batch_cap = 0;
+    bool vbo_rows = true;                                  // SVBFM_VBO_ROWS=0: packed batches go through k_stream instead of k_stream_rows
     bool vbo_pack = true;                                  // SVBFM_VBO_PACK=0: the passes read through idx (round 1 / 2 path, kept for comparison)
     struct BatchView {                                      // what launch_stream / combine_finalize use instead of the whole run
         bool on = false;

@@ -617,6 +617,7 @@ struct StreamArgs {
     uint32_t ntiles, ts_shift;
     const uint32_t* tile_col0;
     const uint32_t* oc;       // [nnz] other column of every entry
+    const uint32_t* ownc;     // k_stream_rows: own column of every entry, indexed like oc (a packed vb_online batch carries it)
     const float* xv;          // [nnz] own x, other x (null when all ones)
     const float* xo;
     double* e;                // this side's copy of the residuals, index = entry - entry0
@@ -1007,6 +1008,125 @@ __global__ void __launch_bounds__(32 * SV_STREAM_WARPS, ONES ? SV_STREAM_MINB : 
     if constexpr (REDUCE) if (!done) emit(cur_b, next_b);   // column j continues in the next tile
 }
 
+// ---- k_stream_rows: the same pass for streams whose columns are a handful of entries (a packed vb_online batch: 2 M entries of the
+// 200 M shape end ~340 k columns, six entries per column). k_stream walks the columns of a tile one after the other: every column
+// end is a dependent chain of a warp reduction and a window step (~60 instructions, ~250 cycles), 750 instructions per 32 entries on
+// such a batch (ncu, profiles/r02_n_*). Here every lane knows the column of its entry (a.ownc, packed with the batch), fetches that
+// column's constants itself, and a row of 32 entries is reduced at once:
+//   * the column that is open at the start of the row keeps per-lane sums across rows and is reduced when it ends (exactly
+//     k_stream's arithmetic: the same per-lane sums, the same butterfly);
+//   * the columns that begin and end inside the row take one segmented scan over the lanes (5 steps whatever their number) and
+//     their last lanes write the sums;
+//   * the row's last column becomes the open one.
+// Same outputs as k_stream (colsum for a column inside the tile, partial[t][0 / 1] for the piece of a column that began before the
+// tile / runs past it), so the finalize kernels do not care which of the two ran. Fixed order everywhere: reproducible.
+template <int KIND, bool ONES, bool REDUCE, bool STEADY>
+__global__ void __launch_bounds__(128, 8) k_stream_rows(StreamArgs a) {
+    static_assert(KIND == KIND_VB_W || KIND == KIND_VB_V, "vb / vb_online passes");
+    constexpr bool IS_V = (KIND == KIND_VB_V);
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= a.ntiles) return;
+    const uint32_t q_begin = t << a.ts_shift;
+    const uint32_t q_end = (a.n - q_begin > (1u << a.ts_shift)) ? q_begin + (1u << a.ts_shift) : a.n;
+    const uint32_t* __restrict__ ocp = a.oc + a.real0;
+    const uint32_t* __restrict__ cp = a.ownc + a.real0;
+    const float* __restrict__ xvp = ONES ? nullptr : a.xv + a.real0;
+    const float* __restrict__ xop = ONES ? nullptr : a.xo + a.real0;
+    double* __restrict__ ep = a.e;
+    const bool has_own = STEADY ? true : (a.has_own != 0), own_is_w = STEADY ? false : (a.own_is_w != 0);
+    const bool has_oth = STEADY ? true : (a.has_oth != 0), oth_is_w = STEADY ? false : (a.oth_is_w != 0);
+    const bool pend = has_own | has_oth;
+    const bool need_rec = (IS_V && REDUCE) || has_oth || (has_own && !own_is_w);
+
+    // the open column: per-lane sums across rows
+    uint32_t open_col = __ldg(cp + q_begin);
+    bool open_prev = q_begin > 0 && __ldg(cp + q_begin - 1) == open_col;       // it began in an earlier tile
+    double A = 0.0, B = 0.0, C1 = 0.0, C2 = 0.0;
+    auto emit_open = [&](bool whole) {
+        double* out = whole ? a.colsum + (size_t)open_col * 4 : a.partial + ((size_t)t * 2 + (open_prev ? 0 : 1)) * 4;
+        if constexpr (KIND == KIND_VB_V) {          // slot B stays 0: B = C1 + C2 (finalize)
+            double k = warp_sum4(A, 0.0, C1, C2, lane);
+            if ((lane & 7) == 0) out[lane >> 3] = k;
+        } else {
+            double k = warp_sum2(A, B, lane);
+            if ((lane & 15) == 0) out[lane >> 4] = k;
+        }
+        A = B = C1 = C2 = 0.0;
+    };
+
+    // streams of the next row, issued one row ahead
+    uint32_t c_n, oc_n; double e_n; float xs_n = 1.0f, xo_n = 1.0f;
+    auto load_row = [&](uint32_t row_b) {
+        const uint32_t k = row_b + lane;
+        const bool ok = k < q_end;
+        c_n = ok ? __ldg(cp + k) : 0xffffffffu;
+        oc_n = ok ? __ldg(ocp + k) : 0u;
+        e_n = ok ? ep[k] : 0.0;
+        if constexpr (!ONES) { xs_n = ok ? __ldg(xvp + k) : 1.0f; xo_n = ok ? __ldg(xop + k) : 1.0f; }
+    };
+    load_row(q_begin);
+    for (uint32_t row_b = q_begin; row_b < q_end; row_b += 32) {
+        const uint32_t k = row_b + lane;
+        const bool ok = k < q_end;
+        const uint32_t c = c_n, oc = oc_n;
+        const double e0 = e_n;
+        const float xs = xs_n, xo = xo_n;
+        // constants of the lane's own column, record of its other column
+        double mu = 0.0, h_oth = 0.0, d_own = 0.0;
+        if (ok) {
+            const double2 m = *reinterpret_cast<const double2*>(&a.own[c]);
+            mu = m.x; h_oth = m.y; d_own = a.own[c].d_own;
+        }
+        ColPack g = ColPack{0.0, 0.0, 0.0, 0.0};
+        if (need_rec && ok) g = sv_load_record(a.rec + oc, a.rec_no_alloc != 0);
+        if (row_b + 32 < q_end) load_row(row_b + 32);
+        double ei = e0;
+        if (ok) {
+            ei = apply_pending<ONES>(e0, xs, xo, g, h_oth, d_own, has_own, own_is_w, has_oth, oth_is_w);
+            if (pend) ep[k] = ei;
+        }
+        if constexpr (REDUCE) {
+            double tA = 0.0, tB = 0.0, tC1 = 0.0, tC2 = 0.0;
+            if (ok) entry_terms<KIND>(ei, xs, xo, g, mu, tA, tB, tC1, tC2);
+            const bool in_open = (c == open_col);
+            if (in_open) { A += tA; B += tB; C1 += tC1; C2 += tC2; }
+            const uint32_t last_lane = (q_end - row_b >= 32) ? 31u : q_end - row_b - 1;
+            const uint32_t c_last = __shfl_sync(FULL, c, (int)last_lane);
+            if (c_last != open_col) {                       // the open column ends inside this row (uniform)
+                emit_open(!open_prev);
+                const bool in_last = ok && (c == c_last);
+                const bool interior = ok && !in_open && !in_last;
+                if (__any_sync(FULL, interior)) {
+                    // segmented inclusive scan over the lanes, keyed by the column (the entries are in column order)
+                    double s0 = interior ? tA : 0.0, s1 = interior ? (IS_V ? tC1 : tB) : 0.0, s2 = interior ? tC2 : 0.0;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t cc = __shfl_up_sync(FULL, c, d);
+                        const bool take = (lane >= (uint32_t)d) && (cc == c);
+                        const double u0 = __shfl_up_sync(FULL, s0, d), u1 = __shfl_up_sync(FULL, s1, d);
+                        if (take) { s0 += u0; s1 += u1; }
+                        if constexpr (IS_V) { const double u2 = __shfl_up_sync(FULL, s2, d); if (take) s2 += u2; }
+                    }
+                    const uint32_t c_up = __shfl_down_sync(FULL, c, 1);
+                    if (interior && c_up != c) {            // last lane of its column (an interior lane is never lane 31 of a full row)
+                        double2* out = reinterpret_cast<double2*>(a.colsum + (size_t)c * 4);
+                        if constexpr (IS_V) { out[0] = make_double2(s0, 0.0); out[1] = make_double2(s1, s2); }
+                        else out[0] = make_double2(s0, s1);
+                    }
+                }
+                if (in_last) { A = tA; B = tB; C1 = tC1; C2 = tC2; }
+                open_col = c_last; open_prev = false;
+            }
+        }
+    }
+    if constexpr (REDUCE) {
+        const bool runs_on = q_end < a.n && __ldg(cp + q_end) == open_col;
+        emit_open(!open_prev && !runs_on);
+    }
+}
+
 // pass 2 in CASE order (streaming): the run's columns are case-disjoint, so every case has at most one feature
 // inside [c0, c1); e_i += x * h * delta_j with delta and the parameters served from L2. Used when the run covers
 // a large share of the cases; the CSC-order kernel above is kept for small runs.
@@ -1161,9 +1281,11 @@ struct VboPackArgs {
     const uint32_t* oc[2];         // other-column ids of run 0 / run 1, offset to the run's first entry
     const float* xv[2];            // own x / other x of the runs (null: all ones)
     const float* xo[2];
+    const uint32_t* rcol;          // [n][2] the two columns of every case (device case order)
     uint32_t n;
     double* eb[2];
     uint32_t* ocb[2];
+    uint32_t* ownb[2];             // own column of every batch entry (what k_stream_rows keys its row reductions by)
     float* xvb[2];
     float* xob[2];
 };
@@ -1171,8 +1293,11 @@ __global__ void __launch_bounds__(256) k_vbo_pack(VboPackArgs a) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.n) return;
     const uint32_t p0 = __ldcs(a.idx[0] + k), p1 = __ldcs(a.idx[1] + k);
+    const uint32_t i1 = __ldg(a.crow1 + p1);
     a.eb[0][k] = a.e[p0];                          // run 0's entry order is the device case order
-    a.eb[1][k] = a.e[__ldg(a.crow1 + p1)];
+    a.eb[1][k] = a.e[i1];
+    a.ownb[0][k] = __ldg(a.rcol + 2 * (size_t)p0);
+    a.ownb[1][k] = __ldg(a.rcol + 2 * (size_t)i1 + 1);
     a.ocb[0][k] = __ldg(a.oc[0] + p0);
     a.ocb[1][k] = __ldg(a.oc[1] + p1);
     if (a.xv[0]) {

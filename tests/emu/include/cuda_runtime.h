@@ -137,7 +137,14 @@ static inline T __shfl_down_sync(unsigned mask, T v, unsigned d, int width = 32)
     int s = ((lane & (width - 1)) + (int)d < width) ? lane + (int)d : lane;
     return __shfl_sync(mask, v, s, 32);
 }
+template <typename T>
+static inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int width = 32) {
+    int lane = emu::lane_id();
+    int s = ((lane & (width - 1)) >= (int)d) ? lane - (int)d : lane;
+    return __shfl_sync(mask, v, s, 32);
+}
 static inline unsigned __ballot_sync(unsigned mask, bool pred) { return emu::warp_ballot(mask, pred); }
+static inline int __any_sync(unsigned mask, bool pred) { return emu::warp_ballot(mask, pred) != 0u; }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { (void)emu::warp_ballot(mask, false); }
 static inline void __syncthreads() { emu::block_barrier(); }
 

@@ -71,16 +71,18 @@ def test_vb_online_batch_lists_equal_masked_passes(built, monkeypatch):
         assert all(rel(x, y) < 1e-10 for x, y in zip(a, b)), (a, b)
 
 
-@pytest.mark.parametrize("values,tile_entries", [(False, 0), (False, 64), (True, 64)])
+@pytest.mark.parametrize("values,tile_entries", [(False, 0), (False, 64), (True, 64), (False, 32)])
 def test_vb_online_packed_batches_equal_index_lists(built, monkeypatch, values, tile_entries):
-    """vb_online on the stream schedule: the batch in flight packed into contiguous streams (default; all-ones data then goes
-    through the bulk-copy ring like a whole-run pass) against passes that read through the batch's index lists
-    (SVBFM_VBO_PACK=0). Same operands in the same order: the statistics, the parameters and the residuals both runs leave
-    behind are bit-identical."""
+    """vb_online on the stream schedule: the batch in flight packed into contiguous streams against passes that read through the
+    batch's index lists (SVBFM_VBO_PACK=0). Packed and swept by k_stream (SVBFM_VBO_ROWS=0; all-ones data then goes through the
+    bulk-copy ring like a whole-run pass): same operands in the same order, so statistics, parameters and residuals are
+    bit-identical. Packed and swept by k_stream_rows (the default): the columns that begin and end inside a row of 32 entries
+    are summed by a segmented scan instead of the butterfly, everything else is the same arithmetic: equal to rounding."""
     tr, te = two_field(16000, 1600, 260, 190, seed=22, values=values)
     out, res, par = [], [], []
-    for packed in ("1", "0"):
+    for packed, rows in (("0", "0"), ("1", "0"), ("1", "1")):
         monkeypatch.setenv("SVBFM_VBO_PACK", packed)
+        monkeypatch.setenv("SVBFM_VBO_ROWS", rows)
         L = make_learner("vb_online", tr, te, 3, num_iter=3, num_batch=7, tile_entries=tile_entries)
         out.append([(s.test_rmse, s.free_energy, s.alpha) for s in L.learn(to_csc(tr), to_csc(te))])
         assert L.engine.info()["fused_schedule"] & 1
@@ -90,6 +92,10 @@ def test_vb_online_packed_batches_equal_index_lists(built, monkeypatch, values, 
         L.engine.close()
     assert out[0] == out[1], out
     assert np.array_equal(res[0], res[1]) and np.array_equal(par[0], par[1])
+    for a, b in zip(out[0], out[2]):
+        assert all(rel(x, y) < 1e-10 for x, y in zip(a, b)), (a, b)
+    assert np.max(np.abs(res[0] - res[2])) < 1e-9 and np.max(np.abs(par[0] - par[2])) < 1e-9
+    assert not np.array_equal(par[0], par[2]) or tile_entries == 0      # (the rows kernel did run: its sums round differently)
 
 
 # ---- binary classification (-task c) for mcmc / als: SURVEY section 8(f) rank 4. Built and emulator-checked without a GPU.
