@@ -328,6 +328,7 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
         fa.nat = IS_V ? E->d_nat_v + (size_t)f * E->D : E->d_nat_w;
         fa.t_cnt = IS_V ? E->d_t_v : E->d_t_w;
         fa.col_count = E->d_col_count;
+        fa.pfT = (IS_V && E->vbo_pvT_live) ? E->d_pvT : nullptr;
         fa.update_t = IS_V ? (f == E->K - 1) : 1;      // t_vj advances once per batch (vbo.h:399-402), t_wj per w update (:520)
         int update_params = IS_V ? 1 : (E->cfg.k1 != 0);   // with k1 = 0 the w pass only counts the batch entries per column
         uint32_t nthreads = ncols;
@@ -628,6 +629,25 @@ static int predict(Engine* E, const DevSplit& S, double* e_out, int red_slot, in
     unsigned grid = std::max(1u, std::min<unsigned>(nblk(S.n), SV_RGRID));
     bool listed = false;
     if constexpr (MODE == PRED_VB_TRAIN) {
+        if (E->bv.on && E->bv.lists && E->vbo_pvT_live) {
+            // ... by the warp-per-case kernel over the transposed parameters (k_finalize_vbo keeps d_pvT current during the epoch)
+            Predict2Args p{};
+            p.rcol = S.rcol; p.rval = S.rval; p.y = S.y; p.n = E->bv.n; p.pw = E->d_pw; p.pvT = E->d_pvT; p.K = E->K; p.k0 = E->cfg.k0; p.k1 = E->cfg.k1;
+            p.sc = E->d_sc; p.e = e_out; p.partial = E->d_red_partial; p.list = E->d_vbo_idx[0] + E->bv.entry0;
+            const unsigned g2 = std::max(1u, std::min<unsigned>((p.n + 255) / 256, SV_RGRID / 2));
+            const int ns = E->K <= 32 ? 1 : (E->K <= 64 ? 2 : (E->K <= 128 ? 4 : 8));
+#define CALL_P2L(NS)                                                                        \
+            do {                                                                            \
+                if (S.all_ones) k_predict2<false, true, NS, 32, true><<<g2, 256, 0, st>>>(p); \
+                else k_predict2<false, false, NS, 32, true><<<g2, 256, 0, st>>>(p);          \
+            } while (0)
+            if (ns == 1) CALL_P2L(1); else if (ns == 2) CALL_P2L(2); else if (ns == 4) CALL_P2L(4); else CALL_P2L(8);
+#undef CALL_P2L
+            LAUNCHED(E);
+            k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, g2 * 8, 1, RED(E->d_sc, red_slot), 0); LAUNCHED(E);
+            if (int rc = allreduce_sum_f64(E, RED(E->d_sc, red_slot), nred)) return rc;
+            return check_launch(E, "predict (batch list)");
+        }
         if (E->bv.on && E->bv.lists) {     // vb_online batch on the stream schedule: walk the batch's own case list
             listed = true;
             a.list = E->d_vbo_idx[0] + E->bv.entry0; a.nlist = E->bv.n;
@@ -924,6 +944,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     if (const char* rr = getenv("SVBFM_REC_RANK")) E->want_rec_rank = atoi(rr) != 0;    // default on; 0: records in column order
     if (const char* gr = getenv("SVBFM_GRAPH")) E->use_graph = atoi(gr) != 0;
     if (const char* na = getenv("SVBFM_REC_NA")) E->rec_na_mask = atoi(na);              // bit s: side s gathers its records past L1 (default 2)
+    if (const char* v2 = getenv("SVBFM_VBO_PREDICT2")) E->vbo_predict2 = atoi(v2) != 0;  // default on; 0: the batch predictions walk the [K][D] matrix (k_predict)
     if (const char* vr = getenv("SVBFM_VBO_ROWS")) E->vbo_rows = atoi(vr) != 0;          // default on; 0: packed batches through k_stream
     if (const char* vp = getenv("SVBFM_VBO_PACK")) E->vbo_pack = atoi(vp) != 0;          // default on; 0: the batch passes read through the index lists
     if (const char* rh = getenv("SVBFM_REC_HOT")) E->rec_hot = atoi(rh);                // first-field pass: records of the rank layout kept in L1 (0: all)
@@ -1404,18 +1425,27 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
     SV_CUDA(E, cudaMemsetAsync(E->d_stats, 0, sizeof(DevStats), st));
     // two complete fields on one GPU: every batch is swept by the stream schedule on its own entries (batch index lists built once
     // per epoch) instead of scanning the whole design matrix with a batch mask per (batch, factor, field)
-    const bool use_streams = E->vbo_streams && (S.n > 0 || E->world > 1) &&      // sharded: the same decision on every rank, cases or not
-                             (uint64_t)num_batch * std::max(E->runs[0].col_end - E->runs[0].col_begin, E->runs[1].col_end - E->runs[1].col_begin) < (1ull << 31);
-    if (use_streams) {
-        if (!E->d_e2 && dev_alloc(E, &E->d_e2, S.n)) return SVBFM_ERR_OOM;
-        if (int rc = vbo_stream_prepare(E, num_batch)) return rc;
-    }
-    cudaEvent_t t0, t1, t2;
-    cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
-    cudaEventRecord(t0, st);
     // on the stream schedule the prediction, the reductions and the w0 shift of a batch walk the batch's own case list
     // (E->bv) instead of masking the whole arrays; SVBFM_VBO_FULL_PASSES=1 keeps the masked passes (for comparison)
     const bool full_passes = getenv("SVBFM_VBO_FULL_PASSES") != nullptr;
+    const bool use_streams = E->vbo_streams && (S.n > 0 || E->world > 1) &&      // sharded: the same decision on every rank, cases or not
+                             (uint64_t)num_batch * std::max(E->runs[0].col_end - E->runs[0].col_begin, E->runs[1].col_end - E->runs[1].col_begin) < (1ull << 31);
+    E->vbo_pvT_live = false;
+    if (use_streams) {
+        if (!E->d_e2 && dev_alloc(E, &E->d_e2, S.n)) return SVBFM_ERR_OOM;
+        if (int rc = vbo_stream_prepare(E, num_batch)) return rc;
+        // the batches' fresh predictions read the factor parameters as [D][K] rows (k_predict2 over the batch's case list): transposed
+        // once per epoch, kept current by k_finalize_vbo
+        if (E->vbo_predict2 && !full_passes && E->K >= 1 && E->K <= 256) {
+            if (!E->d_pvT && dev_alloc(E, &E->d_pvT, (size_t)E->K * E->D)) return SVBFM_ERR_OOM;
+            k_transpose_params<<<dim3((E->D + 31) / 32, (E->K + 31) / 32), dim3(32, 8), 0, st>>>(E->d_pv, E->D, E->K, E->d_pvT); LAUNCHED(E);
+            E->vbo_pvT_live = true;
+        }
+    }
+    struct PvTGuard { Engine* E; ~PvTGuard() { E->vbo_pvT_live = false; } } pvt_guard{E};      // the copy is only kept current inside an epoch
+    cudaEvent_t t0, t1, t2;
+    cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
+    cudaEventRecord(t0, st);
     for (uint32_t b = 0; b < num_batch; b++) {
         k_vbo_batch_begin<<<1, 1, 0, st>>>(E->d_sc, E->d_batch_n, b); LAUNCHED(E);
         const uint32_t nb_cases = use_streams ? (uint32_t)(E->vbo_off[b + 1] - E->vbo_off[b]) : 0u;

@@ -155,6 +155,8 @@ struct Engine {
     uint32_t* d_vbo_ownb[2] = {nullptr, nullptr};          // [vbo_batch_cap] own column of every batch entry (k_stream_rows)
     float* d_vbo_xb[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side][own x, other x][vbo_batch_cap] (x != 1 only)
     uint32_t vbo_batch_cap = 0;
+    bool vbo_predict2 = true;                              // SVBFM_VBO_PREDICT2=0: batch predictions by k_predict over the [K][D] matrix
+    bool vbo_pvT_live = false;                             // inside an epoch: d_pvT is the current transposed copy (k_finalize_vbo writes both)
     bool vbo_rows = true;                                  // SVBFM_VBO_ROWS=0: packed batches go through k_stream instead of k_stream_rows
     bool vbo_pack = true;                                  // SVBFM_VBO_PACK=0: the passes read through idx (round 1 / 2 path, kept for comparison)
     struct BatchView {                                      // what launch_stream / combine_finalize use instead of the whole run

@@ -380,6 +380,8 @@ struct FinalizeArgs {
     const double* col_count;     // [D]
     const uint64_t* colptr;      // batch column sizes come from colsum C-slot instead (see engine)
     const uint32_t* gcnt;        // vb_online on the sharded stream schedule: global batch entries of every column (indexed like span.colptr)
+    double2* pfT;                // vb_online on the stream schedule: [D][K] transposed copy of the factor parameters, kept current for the
+                                 // batch predictions (k_predict2 over the batch's case list); null: none
     const uint32_t* col_list;    // vb_online on the stream schedule: the batch's non-empty columns of the run (null: every column c0 .. c1)
     uint32_t n_list;
     int update_t;                // vb_online: 1 when this sweep advances t_cnt (w: always; v: f == 0)
@@ -554,6 +556,7 @@ __global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __
     bool skip = false;
     if (isnan(mu) || isinf(mu)) { mu = mu_dash; bad++; skip = true; }
     a.pf[j] = make_double2(mu, sg);
+    if constexpr (KIND == KIND_VBO_V) if (a.pfT) a.pfT[(size_t)j * a.K + a.f] = make_double2(mu, sg);
     a.delta[j] = skip ? 0.0 : (mu_dash - mu);
     if (!skip) {
         if constexpr (KIND == KIND_VBO_W) a.dT[j] += B_local * (sg - sg_dash);
@@ -1494,11 +1497,12 @@ struct Predict2Args {
     const Scalars* sc;
     double* e;
     double* partial;          // [warps] sum T (vb) / sum of squared clamped errors (mcmc)
+    const uint32_t* list;     // LIST: the cases to predict, n of them (a vb_online batch: its cases in device order, i.e. sorted by first-field column)
 };
 
 // G = lanes per case: 32 (one case per warp step) or 16 (two cases per warp step, one per half-warp: the fixed cost of a
 // step -- shuffles of the case's columns, reduction, bookkeeping -- is shared by two cases)
-template <bool MCMC, bool ONES, int NS, int G>
+template <bool MCMC, bool ONES, int NS, int G, bool LIST = false>
 __global__ void __launch_bounds__(256) k_predict2(Predict2Args a) {
     static_assert(G == 32 || G == 16, "lanes per case");
     const uint32_t lane = threadIdx.x & 31, gl = lane & (G - 1), gbase = lane & ~(uint32_t)(G - 1);
@@ -1512,8 +1516,9 @@ __global__ void __launch_bounds__(256) k_predict2(Predict2Args a) {
 #pragma unroll
     for (int s = 0; s < NS; s++) Pu[s] = make_double2(0.0, 0.0);
     for (uint32_t b = b0; b < b1; b++) {
-        const uint32_t i = b * 32 + lane;
+        uint32_t i = b * 32 + lane;
         const bool ok = i < a.n;
+        if constexpr (LIST) i = ok ? __ldcs(a.list + i) : 0u;
         uint2 c = ok ? __ldcs(reinterpret_cast<const uint2*>(a.rcol) + i) : make_uint2(0u, 0u);
         float2 xv = make_float2(1.0f, 1.0f);
         if constexpr (!ONES) if (ok) xv = __ldcs(reinterpret_cast<const float2*>(a.rval) + i);
