@@ -260,6 +260,7 @@ struct RecPlan {
     int rec_mode = 0;
     const double2* p_next = nullptr;
     const double2* p_prev = nullptr;
+    bool carry = false;            // vb_online, compact columns: not the first step of the batch
 };
 
 // tiles -> column sums (-> allreduce when sharded) -> per-column update
@@ -324,6 +325,12 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
         fa.stage_base = E->slot_base[rp->run];
     }
     if (rp && rp->run >= 0 && E->bv.on) fa.gcnt = E->bv.gcnt[rp->run];
+    if (rp && rp->run >= 0 && E->bv.on && E->bv.compact) {
+        fa.cc = E->d_vbo_cc; fa.cid0 = rp->run ? E->bv.nclist[0] : 0u;
+        fa.ccptr = reinterpret_cast<const uint64_t*>(E->d_vbo_ccptr) + (rp->run ? E->bv.nclist[0] + 1 : 0u);
+        fa.colsum = E->d_vbo_colsum_c; fa.opack = E->d_vbo_opack_c; fa.dT = E->d_vbo_dT_c;
+        fa.nextp_c = E->d_vbo_nextp_c; fa.prevm_c = E->d_vbo_prevm_c; fa.carry = rp->carry ? 1 : 0;
+    }
     if constexpr (KIND == KIND_VBO_W || KIND == KIND_VBO_V) {
         fa.nat = IS_V ? E->d_nat_v + (size_t)f * E->D : E->d_nat_w;
         fa.t_cnt = IS_V ? E->d_t_v : E->d_t_w;
@@ -462,6 +469,7 @@ static void launch_stream(Engine* E, int side, bool has_own, bool own_is_w, bool
     if (side == 0 && E->rec_rank && !E->xs && E->rec_hot > 0) a.rec_hot_end = E->runs[1].col_begin + (uint32_t)E->rec_hot;
     a.has_own = has_own; a.own_is_w = own_is_w; a.has_oth = has_oth; a.oth_is_w = oth_is_w;
     a.colsum = E->d_colsum;
+    if (E->bv.on && E->bv.compact) { a.own = E->d_vbo_opack_c; a.colsum = E->d_vbo_colsum_c; }      // own-column ids of the packed batch are compact
     constexpr int KIND = MCMC ? (W ? KIND_MC_W : KIND_MC_V) : (W ? KIND_VB_W : KIND_VB_V);
     constexpr unsigned SW = SV_STREAM_WARPS, ST = 32 * SV_STREAM_WARPS;
     unsigned grid = (a.ntiles + SW - 1) / SW;
@@ -509,6 +517,10 @@ static int sweep_streams(Engine* E) {
     k_pack_init<<<nblk(r1.col_end - r0.col_begin), 256, 0, st>>>(r0.col_begin, r0.col_end, r1.col_begin, r1.col_end, table(steps[0]), E->d_cpack, E->d_opack,
                                                                           E->rec_rank ? E->d_rec_slot : nullptr);
     LAUNCHED(E);
+    if (E->bv.on && E->bv.compact) {
+        const uint32_t nc = E->bv.nclist[0] + E->bv.nclist[1];
+        if (nc) { k_vbo_opack_init<<<nblk(nc), 256, 0, st>>>(E->d_vbo_cc, E->bv.nclist[0], nc, table(steps[0]), E->d_vbo_opack_c); LAUNCHED(E); }
+    }
     constexpr int KW = FLAVOR == 1 ? KIND_MC_W : (FLAVOR == 2 ? KIND_VBO_W : KIND_VB_W);
     constexpr int KV = FLAVOR == 1 ? KIND_MC_V : (FLAVOR == 2 ? KIND_VBO_V : KIND_VB_V);
     const int batch = E->bv.on ? 0 : -1;
@@ -516,6 +528,7 @@ static int sweep_streams(Engine* E) {
         const int s = steps[k];
         const bool first = (k == 0), prev_w = (!first && steps[k - 1] < 0), w = (s < 0);
         RecPlan rp;
+        rp.carry = !first;
         rp.p_next = (k + 1 < steps.size()) ? table(steps[k + 1]) : nullptr;
         {   // first field: pending U(s-1), I(s-1) + pass 1
             ProfScope ps(E, w ? 9 : 6);
@@ -944,6 +957,7 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     if (const char* rr = getenv("SVBFM_REC_RANK")) E->want_rec_rank = atoi(rr) != 0;    // default on; 0: records in column order
     if (const char* gr = getenv("SVBFM_GRAPH")) E->use_graph = atoi(gr) != 0;
     if (const char* na = getenv("SVBFM_REC_NA")) E->rec_na_mask = atoi(na);              // bit s: side s gathers its records past L1 (default 2)
+    if (const char* vc = getenv("SVBFM_VBO_COMPACT")) E->vbo_compact = atoi(vc) != 0;    // default on; 0: global column ids in the batch passes / finalizes
     if (const char* v2 = getenv("SVBFM_VBO_PREDICT2")) E->vbo_predict2 = atoi(v2) != 0;  // default on; 0: the batch predictions walk the [K][D] matrix (k_predict)
     if (const char* vr = getenv("SVBFM_VBO_ROWS")) E->vbo_rows = atoi(vr) != 0;          // default on; 0: packed batches through k_stream
     if (const char* vp = getenv("SVBFM_VBO_PACK")) E->vbo_pack = atoi(vp) != 0;          // default on; 0: the batch passes read through the index lists
@@ -1001,7 +1015,7 @@ void svbfm_destroy(svbfm_t* h) {
     void* ptrs[] = {E->d_group, E->d_n_per_group, E->d_tile_col, E->d_tile_begin, E->d_tile_len, E->d_exec_order, E->d_col_tile0, E->d_heavy_cols, E->d_pw, E->d_pv,
                     E->d_hyper_w, E->d_hyper_v, E->d_mu_w, E->d_mu_v, E->d_sc, E->d_nat_w, E->d_nat_v, E->d_t_w, E->d_t_v, E->d_col_count,
                     E->d_e, E->d_partial, E->d_colsum, E->d_delta, E->d_dT, E->d_red_partial, E->d_grp_sums, E->d_pred_test,
-                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_gcnt[0], E->d_vbo_gcnt[1], E->d_vbo_clist[0], E->d_vbo_clist[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_vbo_eb[0], E->d_vbo_eb[1], E->d_vbo_ocb[0], E->d_vbo_ocb[1], E->d_vbo_ownb[0], E->d_vbo_ownb[1], E->d_vbo_xb[0][0], E->d_vbo_xb[0][1], E->d_vbo_xb[1][0], E->d_vbo_xb[1][1], E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
+                    E->d_pred_sum, E->d_stats, E->d_cpack, E->d_opack, E->d_ab, E->d_xchg, E->d_pvT, E->d_vbo_idx[0], E->d_vbo_idx[1], E->d_vbo_colptr[0], E->d_vbo_colptr[1], E->d_vbo_gcnt[0], E->d_vbo_gcnt[1], E->d_vbo_clist[0], E->d_vbo_clist[1], E->d_vbo_tile_col0, E->d_vbo_partial, E->d_vbo_eb[0], E->d_vbo_eb[1], E->d_vbo_ocb[0], E->d_vbo_ocb[1], E->d_vbo_ownb[0], E->d_vbo_ownb[1], E->d_vbo_cpos[0], E->d_vbo_cpos[1], E->d_vbo_cc, E->d_vbo_ccptr, E->d_vbo_opack_c, E->d_vbo_colsum_c, E->d_vbo_dT_c, E->d_vbo_nextp_c, E->d_vbo_prevm_c, E->d_vbo_xb[0][0], E->d_vbo_xb[0][1], E->d_vbo_xb[1][0], E->d_vbo_xb[1][1], E->d_e2, E->d_stile_col0, E->d_span_heavy, E->d_rec_slot, E->d_rbatch, E->d_cbatch, E->d_cnt_col, E->d_batch_cnt, E->d_batch_n};
     for (void* p : ptrs) sv_free(p);
     cudaStreamSynchronize(E->stream);
     if (E->copy_stream) { cudaStreamSynchronize(E->copy_stream); cudaStreamDestroy(E->copy_stream); }
@@ -1449,9 +1463,9 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
     for (uint32_t b = 0; b < num_batch; b++) {
         k_vbo_batch_begin<<<1, 1, 0, st>>>(E->d_sc, E->d_batch_n, b); LAUNCHED(E);
         const uint32_t nb_cases = use_streams ? (uint32_t)(E->vbo_off[b + 1] - E->vbo_off[b]) : 0u;
-        struct BvGuard { Engine* E; ~BvGuard() { E->bv.on = false; E->bv.packed = false; } } bv_guard{E};      // every exit leaves the whole-run views in force
+        struct BvGuard { Engine* E; ~BvGuard() { E->bv.on = false; E->bv.packed = false; E->bv.compact = false; } } bv_guard{E};      // every exit leaves the whole-run views in force
         const bool batch_streams = use_streams && (nb_cases || E->world > 1);      // sharded: a rank without cases in the batch still takes part in the collectives
-        if (batch_streams) { E->bv.on = true; E->bv.lists = !full_passes; E->bv.packed = false; E->bv.entry0 = E->vbo_off[b]; E->bv.n = nb_cases; }
+        if (batch_streams) { E->bv.on = true; E->bv.lists = !full_passes; E->bv.packed = false; E->bv.compact = false; E->bv.entry0 = E->vbo_off[b]; E->bv.n = nb_cases; }
         // fresh y-hat, T for the cases of the batch (vbos.h:120-127)
         if (int rc = predict<PRED_VB_TRAIN>(E, S, E->d_e, 6, 1, (int)b)) return rc;
         SV_CUDA(E, cudaMemcpyAsync(&E->d_sc->sum_t, RED(E->d_sc, 6), 8, cudaMemcpyDeviceToDevice, st));
@@ -1472,9 +1486,25 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
                 }
             }
             if (E->vbo_pack && E->bv.lists) {
+                // the batch's non-empty columns as a dense id space (one GPU, k_stream_rows)
+                const bool compact = E->vbo_compact && E->vbo_rows && E->world == 1 && E->d_vbo_cc && E->bv.clist[0] && E->bv.clist[1];
+                if (compact && E->bv.nclist[0] + E->bv.nclist[1]) {
+                    VboColsArgs ca{};
+                    for (int ri = 0; ri < 2; ri++) { ca.clist[ri] = E->bv.clist[ri]; ca.nl[ri] = E->bv.nclist[ri]; ca.colptr[ri] = E->bv.colptr[ri]; }
+                    ca.rec_slot = E->rec_rank ? E->d_rec_slot : nullptr; ca.group = E->d_group; ca.t_v = E->d_t_v; ca.col_count = E->d_col_count;
+                    ca.cc = E->d_vbo_cc; ca.ccptr = reinterpret_cast<uint64_t*>(E->d_vbo_ccptr); ca.dT_c = E->d_vbo_dT_c;
+                    k_vbo_cols<<<nblk(ca.nl[0] + ca.nl[1]), 256, 0, st>>>(ca); LAUNCHED(E);
+                }
                 // the batch's residuals (both entry orders), other-column ids and x values as contiguous streams
                 if (nb_cases) {
                     VboPackArgs pa{};
+                    if (compact) {
+                        for (int ri = 0; ri < 2; ri++) {
+                            const Run& r = ri ? r1 : r0;
+                            pa.cpos[ri] = E->d_vbo_cpos[ri] + (size_t)b * (r.col_end - r.col_begin) - r.col_begin;
+                            pa.csub[ri] = E->vbo_clist_off[ri][b] - (ri ? E->bv.nclist[0] : 0u);
+                        }
+                    }
                     pa.e = E->d_e; pa.rcol = S.rcol; pa.crow1 = S.crow + S.h_colptr[r1.col_begin]; pa.n = nb_cases;
                     for (int ri = 0; ri < 2; ri++) {
                         const Engine::SideView& sv = E->side[ri];
@@ -1486,7 +1516,7 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
                     }
                     k_vbo_pack<<<nblk(nb_cases), 256, 0, st>>>(pa); LAUNCHED(E);
                 }
-                E->bv.packed = true;
+                E->bv.packed = true; E->bv.compact = compact;
             } else if (nb_cases) {
                 // second residual copy for the entries of the batch
                 k_gather_e_idx<<<nblk(nb_cases), 256, 0, st>>>(E->d_e, S.crow + S.h_colptr[r1.col_begin], E->d_vbo_idx[1], (uint32_t)E->vbo_off[b],
@@ -1512,7 +1542,8 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
             k_vbo_unpack<<<nblk(nb_cases), 256, 0, st>>>(E->d_vbo_eb[0], E->d_vbo_eb[1], E->d_vbo_idx[0] + E->vbo_off[b], E->d_vbo_idx[1] + E->vbo_off[b], nb_cases,
                                                         E->d_e, E->d_e2); LAUNCHED(E);
         }
-        k_reduce_dT<<<SV_GGRID, 256, 0, st>>>(E->d_dT, E->D, E->d_red_partial); LAUNCHED(E);
+        if (E->bv.on && E->bv.compact) { k_reduce_dT<<<SV_GGRID, 256, 0, st>>>(E->d_vbo_dT_c, E->bv.nclist[0] + E->bv.nclist[1], E->d_red_partial); LAUNCHED(E); }
+        else { k_reduce_dT<<<SV_GGRID, 256, 0, st>>>(E->d_dT, E->D, E->d_red_partial); LAUNCHED(E); }
         if (use_streams && E->world > 1) {       // sharded stream schedule: every rank holds its own share of d(sum T)
             k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, SV_GGRID, 1, RED(E->d_sc, 6), 0); LAUNCHED(E);
             if (int rc = allreduce_sum_f64(E, RED(E->d_sc, 6), 1)) return rc;

@@ -1197,10 +1197,12 @@ int vbo_stream_prepare(Engine* E, uint32_t num_batch) {
                 if (se == cudaSuccess) se = cudaStreamSynchronize(st);
                 if (n_sel) k_vbo_clist_cols<<<nblk(n_sel), 256, 0, st>>>(d_sel, n_sel, nc, r.col_begin);
             }
-            sv_free(scan_tmp); sv_free(d_flag); sv_free(d_pos); sv_free(d_off);
-            if (se != cudaSuccess) { sv_free(d_sel); return fail(E, SVBFM_ERR_CUDA, std::string("vb_online column lists: ") + cudaGetErrorString(se)); }
+            sv_free(scan_tmp); sv_free(d_flag); sv_free(d_off);
+            if (se != cudaSuccess) { sv_free(d_pos); sv_free(d_sel); return fail(E, SVBFM_ERR_CUDA, std::string("vb_online column lists: ") + cudaGetErrorString(se)); }
             E->d_vbo_clist[ri] = d_sel;
-        }
+            sv_free(E->d_vbo_cpos[ri]);
+            E->d_vbo_cpos[ri] = d_pos;       // kept: the compact column ids of a batch (engine: k_vbo_pack)
+        } else { sv_free(E->d_vbo_cpos[ri]); E->d_vbo_cpos[ri] = nullptr; }
         size_t tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, E->d_vbo_colptr[ri], E->d_vbo_colptr[ri], (int64_t)ncp, st);
         void* tmp = nullptr;
@@ -1210,6 +1212,27 @@ int vbo_stream_prepare(Engine* E, uint32_t num_batch) {
         if (e != cudaSuccess) return fail(E, SVBFM_ERR_CUDA, std::string("vb_online scan: ") + cudaGetErrorString(e));
     }
     sv_free(d_keys); sv_free(d_vals);
+    // dense per-batch column arrays (one GPU, column lists built for both fields)
+    if (E->vbo_compact && E->world == 1 && E->d_vbo_cpos[0] && E->d_vbo_cpos[1]) {
+        uint32_t cap = 1;
+        for (uint32_t b = 0; b < num_batch; b++)
+            cap = std::max(cap, (E->vbo_clist_off[0][b + 1] - E->vbo_clist_off[0][b]) + (E->vbo_clist_off[1][b + 1] - E->vbo_clist_off[1][b]));
+        if (cap > E->vbo_cols_cap) {
+            sv_free(E->d_vbo_cc); sv_free(E->d_vbo_ccptr); sv_free(E->d_vbo_opack_c); sv_free(E->d_vbo_colsum_c); sv_free(E->d_vbo_dT_c);
+            sv_free(E->d_vbo_nextp_c); sv_free(E->d_vbo_prevm_c);
+            E->d_vbo_cc = nullptr; E->d_vbo_ccptr = nullptr; E->d_vbo_opack_c = nullptr; E->d_vbo_colsum_c = nullptr; E->d_vbo_dT_c = nullptr;
+            E->d_vbo_nextp_c = nullptr; E->d_vbo_prevm_c = nullptr;
+            E->vbo_cols_cap = 0;
+            SV_CUDA(E, sv_malloc((void**)&E->d_vbo_cc, (size_t)cap * 32));
+            SV_CUDA(E, sv_malloc((void**)&E->d_vbo_opack_c, (size_t)cap * 32));
+            if (dev_alloc(E, &E->d_vbo_ccptr, (size_t)cap + 2)) return SVBFM_ERR_OOM;
+            if (dev_alloc(E, &E->d_vbo_colsum_c, (size_t)cap * 4)) return SVBFM_ERR_OOM;
+            if (dev_alloc(E, &E->d_vbo_dT_c, cap)) return SVBFM_ERR_OOM;
+            if (dev_alloc(E, &E->d_vbo_nextp_c, cap)) return SVBFM_ERR_OOM;
+            if (dev_alloc(E, &E->d_vbo_prevm_c, cap)) return SVBFM_ERR_OOM;
+            E->vbo_cols_cap = cap;
+        }
+    }
     SV_CUDA(E, cudaGetLastError());
     return 0;
 }

@@ -155,6 +155,18 @@ struct Engine {
     uint32_t* d_vbo_ownb[2] = {nullptr, nullptr};          // [vbo_batch_cap] own column of every batch entry (k_stream_rows)
     float* d_vbo_xb[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side][own x, other x][vbo_batch_cap] (x != 1 only)
     uint32_t vbo_batch_cap = 0;
+    // ... and, on one GPU, the batch's non-empty columns as a dense id space (kernels.cuh VboCol): per epoch the rank of every
+    // (batch, column) among the non-empty pairs, per batch the column table and dense column sums / own constants / d(sum T)
+    uint32_t* d_vbo_cpos[2] = {nullptr, nullptr};          // [num_batch * ncols(run) + 1] exclusive scan of the non-empty flags
+    struct VboCol* d_vbo_cc = nullptr;                     // [vbo_cols_cap]
+    unsigned long long* d_vbo_ccptr = nullptr;             // [vbo_cols_cap + 2]
+    struct OwnPack* d_vbo_opack_c = nullptr;               // [vbo_cols_cap]
+    double* d_vbo_colsum_c = nullptr;                      // [vbo_cols_cap][4]
+    double* d_vbo_dT_c = nullptr;                          // [vbo_cols_cap]
+    double2* d_vbo_nextp_c = nullptr;                      // [vbo_cols_cap] carried from one step's finalize to the next (FinalizeArgs)
+    double* d_vbo_prevm_c = nullptr;                       // [vbo_cols_cap]
+    uint32_t vbo_cols_cap = 0;
+    bool vbo_compact = true;                               // SVBFM_VBO_COMPACT=0: global column ids in the batch passes and finalizes
     bool vbo_predict2 = true;                              // SVBFM_VBO_PREDICT2=0: batch predictions by k_predict over the [K][D] matrix
     bool vbo_pvT_live = false;                             // inside an epoch: d_pvT is the current transposed copy (k_finalize_vbo writes both)
     bool vbo_rows = true;                                  // SVBFM_VBO_ROWS=0: packed batches go through k_stream instead of k_stream_rows
@@ -162,6 +174,7 @@ struct Engine {
     struct BatchView {                                      // what launch_stream / combine_finalize use instead of the whole run
         bool on = false;
         bool lists = false;                                 // prediction / reductions / w0 shift of the batch walk its case list too
+        bool compact = false;                               // ... and its columns are a dense id space (d_vbo_cc): first field [0, nl0), second [nl0, nl0 + nl1)
         bool packed = false;                                // the batch's streams are packed (d_vbo_eb / d_vbo_ocb): passes, reductions and shifts run on them
         const uint64_t* colptr[2] = {nullptr, nullptr};
         const uint32_t* gcnt[2] = {nullptr, nullptr};       // sharded: global batch entries per column (same indexing as colptr)

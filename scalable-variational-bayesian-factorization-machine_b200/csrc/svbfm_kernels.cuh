@@ -344,6 +344,12 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint32_t c0, uint
     return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
 
+// vb_online, one GPU: what a finalize needs about a non-empty column of the batch in flight and what does not change inside the batch,
+// gathered once per batch (k_vbo_cols) and read coalesced by the 2 (K + 1) finalizes of the batch (index: the column's position in
+// the batch's column lists, first field first -- the same ids the packed batch carries as own-column ids, so the column sums, the
+// own-column constants and d(sum T) of the batch live in dense arrays as well)
+struct alignas(32) VboCol { uint32_t j, slot, group, t_v; double col_count, cnt; };
+
 struct PeerFlags { unsigned long long* p[16]; int n, me; };      // p[r]: rank r's 16 flag words; a rank writes word `me` of every other rank
 
 struct FinalizeArgs {
@@ -380,6 +386,12 @@ struct FinalizeArgs {
     const double* col_count;     // [D]
     const uint64_t* colptr;      // batch column sizes come from colsum C-slot instead (see engine)
     const uint32_t* gcnt;        // vb_online on the sharded stream schedule: global batch entries of every column (indexed like span.colptr)
+    const VboCol* cc;            // vb_online, compact columns: the batch's non-empty columns of BOTH fields (null: global column ids everywhere)
+    const uint64_t* ccptr;       // ... [n_list + 1] the batch's column pointer at this field's non-empty columns
+    uint32_t cid0;               // ... first compact id of this field (colsum / opack / dT are indexed by cid0 + t)
+    double2* nextp_c;            // ... what the step before read as p_next[j]: this step's own parameters (valid when `carry`)
+    double* prevm_c;             // ... the new mean the step before gave the column: this step's p_prev[j].x (valid when `carry`)
+    int carry;                   // ... not the first step of the batch: the two arrays above replace two scattered 16-byte reads per column
     double2* pfT;                // vb_online on the stream schedule: [D][K] transposed copy of the factor parameters, kept current for the
                                  // batch predictions (k_predict2 over the batch's case list); null: none
     const uint32_t* col_list;    // vb_online on the stream schedule: the batch's non-empty columns of the run (null: every column c0 .. c1)
@@ -388,18 +400,26 @@ struct FinalizeArgs {
 };
 
 // stream schedule: the records of column j for the passes that follow its update (see k_stream)
-__device__ __forceinline__ void write_records(const FinalizeArgs& a, uint32_t j, double new_mean, double new_var, double dlt, double mu_old) {
+// (sj: the column's record slot, oi: its index in opack)
+__device__ __forceinline__ void write_records_at(const FinalizeArgs& a, uint32_t j, uint32_t sj, size_t oi, double new_mean, double new_var, double dlt,
+                                                 double mu_old) {
     if (!a.rec_mode) return;
     double2 N = a.p_next ? a.p_next[j] : make_double2(0.0, 0.0);
-    const uint32_t sj = a.rec_slot ? a.rec_slot[j] : j;
     if (a.stage) a.stage[sj - a.stage_base] = make_double2(new_mean, new_var);
     if (a.rec_mode == 1) {
-        a.cpack[sj] = ColPack{new_mean, new_var, dlt, a.p_prev ? a.p_prev[j].x : 0.0};
-        a.opack[j] = OwnPack{N.x, new_mean, dlt, 0.0};
+        double prev = 0.0;
+        if (a.p_prev) prev = (a.cc && a.carry) ? a.prevm_c[oi] : a.p_prev[j].x;
+        a.cpack[sj] = ColPack{new_mean, new_var, dlt, prev};
+        a.opack[oi] = OwnPack{N.x, new_mean, dlt, 0.0};
     } else {
         a.cpack[sj] = ColPack{N.x, N.y, dlt, mu_old};
-        a.opack[j] = OwnPack{N.x, N.x, dlt, 0.0};
+        a.opack[oi] = OwnPack{N.x, N.x, dlt, 0.0};
     }
+    if (a.cc) { a.nextp_c[oi] = N; a.prevm_c[oi] = new_mean; }
+}
+__device__ __forceinline__ void write_records(const FinalizeArgs& a, uint32_t j, double new_mean, double new_var, double dlt, double mu_old) {
+    if (!a.rec_mode) return;
+    write_records_at(a, j, a.rec_slot ? a.rec_slot[j] : j, j, new_mean, new_var, dlt, mu_old);
 }
 
 template <int KIND>
@@ -469,25 +489,36 @@ template <int KIND>
 __global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __restrict__ cnt_arr, double lamda, uint32_t t0, int update_params) {
     uint32_t j = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
     bool act = j < a.c1;
-    if (a.col_list) {        // empty columns are skipped anyway (vbo.h:367, 394) and nothing reads their delta on the stream schedule
-        const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-        act = t < a.n_list;
-        j = act ? a.col_list[t] : a.c0;
+    const uint32_t tl = blockIdx.x * blockDim.x + threadIdx.x;
+    VboCol cs = VboCol{0u, 0u, 0u, 0u, 0.0, 0.0};
+    if (a.cc) {              // compact columns: thread tl takes the tl-th non-empty column of this field
+        act = tl < a.n_list;
+        if (act) cs = a.cc[a.cid0 + tl];
+        j = act ? cs.j : a.c0;
+    } else if (a.col_list) { // empty columns are skipped anyway (vbo.h:367, 394) and nothing reads their delta on the stream schedule
+        act = tl < a.n_list;
+        j = act ? a.col_list[tl] : a.c0;
         act = act && j < a.c1;
     }
+    const size_t ci = a.cc ? (size_t)a.cid0 + tl : (size_t)j;       // index of the column in colsum / dT / opack
     double A = 0.0, B = 0.0, C1 = 0.0, C2 = 0.0;
     double cnt = 0.0;
     if (a.span.colptr) {
         // stream schedule: colptr is the batch's own column pointer, so the column's batch entries are counted directly.
         // Records of a skipped column are not written: no entry of the batch refers to it. No thread leaves before the
         // cooperative part below: the lanes of a warp sum a long span together.
-        if (act) cnt = a.gcnt ? (double)a.gcnt[j] : (double)(a.span.colptr[j + 1] - a.span.colptr[j]);
+        uint64_t cb = 0, ce = 0;
+        if (act) {
+            if (a.cc) { cb = a.ccptr[tl]; ce = a.ccptr[tl + 1]; }
+            else { cb = a.span.colptr[j]; ce = a.span.colptr[j + 1]; }
+            cnt = a.gcnt ? (double)a.gcnt[j] : (double)(ce - cb);
+        }
         const bool live = act && cnt != 0.0 && update_params;
-        if (act && !live) a.delta[j] = 0.0;
+        if (act && !live && !a.cc) a.delta[j] = 0.0;
         uint64_t T0 = 0, T1 = 0;
         bool from_cs = true;                    // colsum[j] holds the sums (one-tile column, or summed before)
         if (live && !a.from_colsum) {
-            const uint64_t b = a.span.colptr[j], e = a.span.colptr[j + 1];
+            const uint64_t b = cb, e = ce;
             if (e > b) {
                 T0 = (b - a.span.entry0) >> a.span.ts_shift; T1 = (e - 1 - a.span.entry0) >> a.span.ts_shift;
                 from_cs = (T0 == T1);
@@ -517,7 +548,7 @@ __global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __
         if (!live) return;
         if (cnt < 0.0) cnt = -cnt;              // a long span: done above
         else if (from_cs) {
-            const double2* p = reinterpret_cast<const double2*>(a.colsum + (size_t)j * 4);
+            const double2* p = reinterpret_cast<const double2*>(a.colsum + ci * 4);
             double2 x = p[0], y = p[1];
             A = x.x; B = x.y; C1 = y.x; C2 = y.y;
         } else {
@@ -537,15 +568,15 @@ __global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __
     }
     const double B_local = B;                                 // this rank's share (d(sum T) of a w column)
     if (a.ab) { double2 g2 = a.ab[j]; A = g2.x; B = g2.y; }   // sharded: global sums after the allreduce
-    uint32_t g = a.group[j];
+    uint32_t g = a.cc ? cs.group : a.group[j];
     double hy = (a.f < 0) ? a.hyper[g] : a.hyper[(size_t)g * a.K + a.f];
     double alpha = a.sc->alpha;
-    double2 P = a.pf[j];
+    double2 P = (a.cc && a.carry) ? a.nextp_c[ci] : a.pf[j];
     double mu_dash = P.x, sg_dash = P.y;
     double2 N = a.nat[j];                                     // {eta1, eta2}
-    uint32_t tc = a.t_cnt[j];
+    uint32_t tc = (a.cc && KIND == KIND_VBO_V) ? cs.t_v : a.t_cnt[j];     // (t_vj does not move inside a batch: it advances with the last factor)
     double rho = pow((double)(t0 + tc), -lamda);              // vbo.h:521 / :406 (rate in force for this batch)
-    double cj = a.col_count[j];
+    double cj = a.cc ? cs.col_count : a.col_count[j];
     double eta2 = (1.0 - rho) * N.y + rho * (hy + alpha * cj * (B / cnt));      // vbo.h:515 / :579
     double eta1 = (1.0 - rho) * N.x + rho * cj * alpha * (A / cnt);             // vbo.h:516 / :580
     a.nat[j] = make_double2(eta1, eta2);
@@ -557,13 +588,48 @@ __global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __
     if (isnan(mu) || isinf(mu)) { mu = mu_dash; bad++; skip = true; }
     a.pf[j] = make_double2(mu, sg);
     if constexpr (KIND == KIND_VBO_V) if (a.pfT) a.pfT[(size_t)j * a.K + a.f] = make_double2(mu, sg);
-    a.delta[j] = skip ? 0.0 : (mu_dash - mu);
+    if (!a.cc) a.delta[j] = skip ? 0.0 : (mu_dash - mu);      // (nothing reads delta on the stream schedule: the passes take it from the records)
     if (!skip) {
-        if constexpr (KIND == KIND_VBO_W) a.dT[j] += B_local * (sg - sg_dash);
-        else a.dT[j] += (C1 + C2) * (sg - sg_dash) + C1 * (mu * mu - mu_dash * mu_dash);
+        if constexpr (KIND == KIND_VBO_W) a.dT[ci] += B_local * (sg - sg_dash);
+        else a.dT[ci] += (C1 + C2) * (sg - sg_dash) + C1 * (mu * mu - mu_dash * mu_dash);
     }
-    write_records(a, j, mu, sg, skip ? 0.0 : (mu_dash - mu), mu_dash);
+    if (a.cc) write_records_at(a, j, cs.slot, ci, mu, sg, skip ? 0.0 : (mu_dash - mu), mu_dash);
+    else write_records(a, j, mu, sg, skip ? 0.0 : (mu_dash - mu), mu_dash);
     if (bad) atomicAdd(&a.sc->nan_inf, (unsigned long long)bad);
+}
+
+// per batch: the compact column table (see VboCol), the batch's column pointer at the non-empty columns, d(sum T) cleared
+struct VboColsArgs {
+    const uint32_t* clist[2];      // the batch's non-empty columns of run 0 / run 1
+    uint32_t nl[2];
+    const uint64_t* colptr[2];     // the batch's column pointers, indexed by global column id
+    const uint32_t* rec_slot;      // null: the column id
+    const uint32_t* group;
+    const uint32_t* t_v;
+    const double* col_count;
+    VboCol* cc;                    // [nl[0] + nl[1]]
+    uint64_t* ccptr;               // [nl[0] + 1] then [nl[1] + 1]
+    double* dT_c;                  // [nl[0] + nl[1]]
+};
+__global__ void __launch_bounds__(256) k_vbo_cols(VboColsArgs a) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nl[0] + a.nl[1]) return;
+    const int ri = t >= a.nl[0] ? 1 : 0;
+    const uint32_t tt = t - (ri ? a.nl[0] : 0u);
+    const uint32_t j = a.clist[ri][tt];
+    const uint64_t b = a.colptr[ri][j], e = a.colptr[ri][j + 1];
+    a.cc[t] = VboCol{j, a.rec_slot ? a.rec_slot[j] : j, a.group[j], a.t_v[j], a.col_count[j], (double)(e - b)};
+    a.ccptr[t + ri] = b;
+    if (tt + 1 == a.nl[ri]) a.ccptr[t + ri + 1] = e;
+    a.dT_c[t] = 0.0;
+}
+// own-column constants before the first step (k_pack_init's opack, compact)
+__global__ void __launch_bounds__(256) k_vbo_opack_init(const VboCol* __restrict__ cc, uint32_t nl0, uint32_t n, const double2* __restrict__ p0,
+                                                        OwnPack* __restrict__ opack_c) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double m = p0[cc[t].j].x;
+    opack_c[t] = t < nl0 ? OwnPack{m, 0.0, 0.0, 0.0} : OwnPack{m, m, 0.0, 0.0};
 }
 
 // pass 2: e_i += x * h * delta_j   (vb.h:571 / :638; mcmc.h:716 / :833)
@@ -1289,6 +1355,9 @@ struct VboPackArgs {
     double* eb[2];
     uint32_t* ocb[2];
     uint32_t* ownb[2];             // own column of every batch entry (what k_stream_rows keys its row reductions by)
+    const uint32_t* cpos[2];       // compact columns (null: global ids): rank of (batch, column) among the epoch's non-empty pairs, offset to
+                                   // this batch and indexed by global column id; ownb then holds cpos[ri][j] - csub[ri]
+    uint32_t csub[2];
     float* xvb[2];
     float* xob[2];
 };
@@ -1299,8 +1368,10 @@ __global__ void __launch_bounds__(256) k_vbo_pack(VboPackArgs a) {
     const uint32_t i1 = __ldg(a.crow1 + p1);
     a.eb[0][k] = a.e[p0];                          // run 0's entry order is the device case order
     a.eb[1][k] = a.e[i1];
-    a.ownb[0][k] = __ldg(a.rcol + 2 * (size_t)p0);
-    a.ownb[1][k] = __ldg(a.rcol + 2 * (size_t)i1 + 1);
+    uint32_t j0 = __ldg(a.rcol + 2 * (size_t)p0), j1 = __ldg(a.rcol + 2 * (size_t)i1 + 1);
+    if (a.cpos[0]) { j0 = __ldg(a.cpos[0] + j0) - a.csub[0]; j1 = __ldg(a.cpos[1] + j1) - a.csub[1]; }
+    a.ownb[0][k] = j0;
+    a.ownb[1][k] = j1;
     a.ocb[0][k] = __ldg(a.oc[0] + p0);
     a.ocb[1][k] = __ldg(a.oc[1] + p1);
     if (a.xv[0]) {

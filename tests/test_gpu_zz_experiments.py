@@ -77,12 +77,14 @@ def test_vb_online_packed_batches_equal_index_lists(built, monkeypatch, values, 
     batch's index lists (SVBFM_VBO_PACK=0). Packed and swept by k_stream (SVBFM_VBO_ROWS=0; all-ones data then goes through the
     bulk-copy ring like a whole-run pass): same operands in the same order, so statistics, parameters and residuals are
     bit-identical. Packed and swept by k_stream_rows (the default): the columns that begin and end inside a row of 32 entries
-    are summed by a segmented scan instead of the butterfly, everything else is the same arithmetic: equal to rounding."""
+    are summed by a segmented scan instead of the butterfly, everything else is the same arithmetic: equal to rounding.
+    SVBFM_VBO_COMPACT=0 keeps global column ids in k_stream_rows / k_finalize_vbo."""
     tr, te = two_field(16000, 1600, 260, 190, seed=22, values=values)
     out, res, par = [], [], []
-    for packed, rows in (("0", "0"), ("1", "0"), ("1", "1")):
+    for packed, rows, compact in (("0", "0", "1"), ("1", "0", "1"), ("1", "1", "1"), ("1", "1", "0")):
         monkeypatch.setenv("SVBFM_VBO_PACK", packed)
         monkeypatch.setenv("SVBFM_VBO_ROWS", rows)
+        monkeypatch.setenv("SVBFM_VBO_COMPACT", compact)
         L = make_learner("vb_online", tr, te, 3, num_iter=3, num_batch=7, tile_entries=tile_entries)
         out.append([(s.test_rmse, s.free_energy, s.alpha) for s in L.learn(to_csc(tr), to_csc(te))])
         assert L.engine.info()["fused_schedule"] & 1
@@ -96,6 +98,8 @@ def test_vb_online_packed_batches_equal_index_lists(built, monkeypatch, values, 
         assert all(rel(x, y) < 1e-10 for x, y in zip(a, b)), (a, b)
     assert np.max(np.abs(res[0] - res[2])) < 1e-9 and np.max(np.abs(par[0] - par[2])) < 1e-9
     assert not np.array_equal(par[0], par[2]) or tile_entries == 0      # (the rows kernel did run: its sums round differently)
+    # the batch's non-empty columns as a dense id space (default on one GPU) against global column ids: only the addresses differ
+    assert out[2] == out[3] and np.array_equal(res[2], res[3]) and np.array_equal(par[2], par[3])
 
 
 @pytest.mark.parametrize("values,K", [(False, 3), (True, 40)])
