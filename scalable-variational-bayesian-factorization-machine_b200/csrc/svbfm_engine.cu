@@ -335,7 +335,6 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
         fa.nat = IS_V ? E->d_nat_v + (size_t)f * E->D : E->d_nat_w;
         fa.t_cnt = IS_V ? E->d_t_v : E->d_t_w;
         fa.col_count = E->d_col_count;
-        fa.pfT = (IS_V && E->vbo_pvT_live) ? E->d_pvT : nullptr;
         fa.update_t = IS_V ? (f == E->K - 1) : 1;      // t_vj advances once per batch (vbo.h:399-402), t_wj per w update (:520)
         int update_params = IS_V ? 1 : (E->cfg.k1 != 0);   // with k1 = 0 the w pass only counts the batch entries per column
         uint32_t nthreads = ncols;
@@ -642,25 +641,6 @@ static int predict(Engine* E, const DevSplit& S, double* e_out, int red_slot, in
     unsigned grid = std::max(1u, std::min<unsigned>(nblk(S.n), SV_RGRID));
     bool listed = false;
     if constexpr (MODE == PRED_VB_TRAIN) {
-        if (E->bv.on && E->bv.lists && E->vbo_pvT_live) {
-            // ... by the warp-per-case kernel over the transposed parameters (k_finalize_vbo keeps d_pvT current during the epoch)
-            Predict2Args p{};
-            p.rcol = S.rcol; p.rval = S.rval; p.y = S.y; p.n = E->bv.n; p.pw = E->d_pw; p.pvT = E->d_pvT; p.K = E->K; p.k0 = E->cfg.k0; p.k1 = E->cfg.k1;
-            p.sc = E->d_sc; p.e = e_out; p.partial = E->d_red_partial; p.list = E->d_vbo_idx[0] + E->bv.entry0;
-            const unsigned g2 = std::max(1u, std::min<unsigned>((p.n + 255) / 256, SV_RGRID / 2));
-            const int ns = E->K <= 32 ? 1 : (E->K <= 64 ? 2 : (E->K <= 128 ? 4 : 8));
-#define CALL_P2L(NS)                                                                        \
-            do {                                                                            \
-                if (S.all_ones) k_predict2<false, true, NS, 32, true><<<g2, 256, 0, st>>>(p); \
-                else k_predict2<false, false, NS, 32, true><<<g2, 256, 0, st>>>(p);          \
-            } while (0)
-            if (ns == 1) CALL_P2L(1); else if (ns == 2) CALL_P2L(2); else if (ns == 4) CALL_P2L(4); else CALL_P2L(8);
-#undef CALL_P2L
-            LAUNCHED(E);
-            k_reduce_final<<<1, 256, 0, st>>>(E->d_red_partial, g2 * 8, 1, RED(E->d_sc, red_slot), 0); LAUNCHED(E);
-            if (int rc = allreduce_sum_f64(E, RED(E->d_sc, red_slot), nred)) return rc;
-            return check_launch(E, "predict (batch list)");
-        }
         if (E->bv.on && E->bv.lists) {     // vb_online batch on the stream schedule: walk the batch's own case list
             listed = true;
             a.list = E->d_vbo_idx[0] + E->bv.entry0; a.nlist = E->bv.n;
@@ -687,21 +667,23 @@ static int predict(Engine* E, const DevSplit& S, double* e_out, int red_slot, in
 template <int MODE>   // PRED_VB_TRAIN or PRED_MC_TRAIN
 static int predict_train(Engine* E, int red_slot) {
     const DevSplit& S = E->tr;
-    if (red_slot >= 0 && (!E->streams || E->K < 1 || E->K > 256 || getenv("SVBFM_NO_PREDICT2"))) return predict<MODE>(E, S, E->d_e, red_slot, 1);
+    if (red_slot >= 0 && (!E->streams || E->K < 1 || E->K > 256 || E->no_predict2)) return predict<MODE>(E, S, E->d_e, red_slot, 1);
     cudaStream_t st = E->stream;
     if (!E->d_pvT && dev_alloc(E, &E->d_pvT, (size_t)E->K * E->D)) return SVBFM_ERR_OOM;
-    k_transpose_params<<<dim3((E->D + 31) / 32, (E->K + 31) / 32), dim3(32, 8), 0, st>>>(E->d_pv, E->D, E->K, E->d_pvT); LAUNCHED(E);
+    constexpr bool MC = (MODE == PRED_MC_TRAIN);
+    if (MC) { k_transpose_means<<<dim3((E->D + 31) / 32, (E->K + 31) / 32), dim3(32, 8), 0, st>>>(E->d_pv, E->D, E->K, reinterpret_cast<double*>(E->d_pvT)); LAUNCHED(E); }
+    else { k_transpose_params<<<dim3((E->D + 31) / 32, (E->K + 31) / 32), dim3(32, 8), 0, st>>>(E->d_pv, E->D, E->K, E->d_pvT); LAUNCHED(E); }
     Predict2Args a{};
-    a.rcol = S.rcol; a.rval = S.rval; a.y = S.y; a.n = S.n; a.pw = E->d_pw; a.pvT = E->d_pvT; a.K = E->K; a.k0 = E->cfg.k0; a.k1 = E->cfg.k1;
+    a.rcol = S.rcol; a.rval = S.rval; a.y = S.y; a.n = S.n; a.pw = E->d_pw; a.pvT = E->d_pvT; a.pvTm = reinterpret_cast<const double*>(E->d_pvT);
+    a.K = E->K; a.k0 = E->cfg.k0; a.k1 = E->cfg.k1;
     a.sc = E->d_sc; a.e = E->d_e; a.partial = E->d_red_partial;
     if (red_slot < 0) {      // cross shards: the residuals of the second copy's cases; their sums are not used (the first copy holds every case once)
         a.rcol = E->sec.rcol; a.rval = nullptr; a.y = E->sec.y; a.n = E->sec.n; a.e = E->d_e2;
     }
     const unsigned grid = std::max(1u, std::min<unsigned>((a.n + 255) / 256, SV_RGRID / 2));   // partial[] holds grid * 8 <= SV_RGRID * 4 sums
-    constexpr bool MC = (MODE == PRED_MC_TRAIN);
     // a warp per case. Half a warp per case (two cases share the fixed cost of a warp step) is built too, but measured slower
     // (begin 57 ms instead of 40 ms at 200 M cases, K = 50): opt-in for experiments
-    const bool half = E->K <= 128 && getenv("SVBFM_PREDICT2_HALFWARP");
+    const bool half = E->K <= 128 && E->predict2_half;
     const int per = half ? 16 : 32;
     const int ns = E->K <= per ? 1 : (E->K <= 2 * per ? 2 : (E->K <= 4 * per ? 4 : 8));
 #define CALL_P2(NS)                                                                                  \
@@ -724,7 +706,7 @@ static int predict_train(Engine* E, int red_slot) {
 }
 static int predict_second(Engine* E) {
     const bool mc = E->cfg.method == SVBFM_MCMC;
-    if (E->K < 1 || E->K > 256 || getenv("SVBFM_NO_PREDICT2")) {      // the case-wise kernel on a view of the shard (its sums go to a scratch slot)
+    if (E->K < 1 || E->K > 256 || E->no_predict2) {      // the case-wise kernel on a view of the shard (its sums go to a scratch slot)
         DevSplit V;
         V.n = E->sec.n; V.nnz = 2ull * E->sec.n; V.rcol = E->sec.rcol; V.uniformF = 2; V.all_ones = true; V.y = E->sec.y;
         return mc ? predict<PRED_MC_TRAIN>(E, V, E->d_e2, 7, 1) : predict<PRED_VB_TRAIN>(E, V, E->d_e2, 7, 1);
@@ -957,8 +939,10 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     if (const char* rr = getenv("SVBFM_REC_RANK")) E->want_rec_rank = atoi(rr) != 0;    // default on; 0: records in column order
     if (const char* gr = getenv("SVBFM_GRAPH")) E->use_graph = atoi(gr) != 0;
     if (const char* na = getenv("SVBFM_REC_NA")) E->rec_na_mask = atoi(na);              // bit s: side s gathers its records past L1 (default 2)
+    E->no_predict2 = getenv("SVBFM_NO_PREDICT2") != nullptr;          // knobs of the per-iteration paths are read once, here
+    E->predict2_half = getenv("SVBFM_PREDICT2_HALFWARP") != nullptr;
+    E->vbo_full_passes = getenv("SVBFM_VBO_FULL_PASSES") != nullptr;
     if (const char* vc = getenv("SVBFM_VBO_COMPACT")) E->vbo_compact = atoi(vc) != 0;    // default on; 0: global column ids in the batch passes / finalizes
-    if (const char* v2 = getenv("SVBFM_VBO_PREDICT2")) E->vbo_predict2 = atoi(v2) != 0;  // default on; 0: the batch predictions walk the [K][D] matrix (k_predict)
     if (const char* vr = getenv("SVBFM_VBO_ROWS")) E->vbo_rows = atoi(vr) != 0;          // default on; 0: packed batches through k_stream
     if (const char* vp = getenv("SVBFM_VBO_PACK")) E->vbo_pack = atoi(vp) != 0;          // default on; 0: the batch passes read through the index lists
     if (const char* rh = getenv("SVBFM_REC_HOT")) E->rec_hot = atoi(rh);                // first-field pass: records of the rank layout kept in L1 (0: all)
@@ -1441,22 +1425,13 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
     // per epoch) instead of scanning the whole design matrix with a batch mask per (batch, factor, field)
     // on the stream schedule the prediction, the reductions and the w0 shift of a batch walk the batch's own case list
     // (E->bv) instead of masking the whole arrays; SVBFM_VBO_FULL_PASSES=1 keeps the masked passes (for comparison)
-    const bool full_passes = getenv("SVBFM_VBO_FULL_PASSES") != nullptr;
+    const bool full_passes = E->vbo_full_passes;
     const bool use_streams = E->vbo_streams && (S.n > 0 || E->world > 1) &&      // sharded: the same decision on every rank, cases or not
                              (uint64_t)num_batch * std::max(E->runs[0].col_end - E->runs[0].col_begin, E->runs[1].col_end - E->runs[1].col_begin) < (1ull << 31);
-    E->vbo_pvT_live = false;
     if (use_streams) {
         if (!E->d_e2 && dev_alloc(E, &E->d_e2, S.n)) return SVBFM_ERR_OOM;
         if (int rc = vbo_stream_prepare(E, num_batch)) return rc;
-        // the batches' fresh predictions read the factor parameters as [D][K] rows (k_predict2 over the batch's case list): transposed
-        // once per epoch, kept current by k_finalize_vbo
-        if (E->vbo_predict2 && !full_passes && E->K >= 1 && E->K <= 256) {
-            if (!E->d_pvT && dev_alloc(E, &E->d_pvT, (size_t)E->K * E->D)) return SVBFM_ERR_OOM;
-            k_transpose_params<<<dim3((E->D + 31) / 32, (E->K + 31) / 32), dim3(32, 8), 0, st>>>(E->d_pv, E->D, E->K, E->d_pvT); LAUNCHED(E);
-            E->vbo_pvT_live = true;
-        }
     }
-    struct PvTGuard { Engine* E; ~PvTGuard() { E->vbo_pvT_live = false; } } pvt_guard{E};      // the copy is only kept current inside an epoch
     cudaEvent_t t0, t1, t2;
     cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2);
     cudaEventRecord(t0, st);

@@ -167,8 +167,8 @@ struct Engine {
     double* d_vbo_prevm_c = nullptr;                       // [vbo_cols_cap]
     uint32_t vbo_cols_cap = 0;
     bool vbo_compact = true;                               // SVBFM_VBO_COMPACT=0: global column ids in the batch passes and finalizes
-    bool vbo_predict2 = true;                              // SVBFM_VBO_PREDICT2=0: batch predictions by k_predict over the [K][D] matrix
-    bool vbo_pvT_live = false;                             // inside an epoch: d_pvT is the current transposed copy (k_finalize_vbo writes both)
+    bool no_predict2 = false, predict2_half = false;      // SVBFM_NO_PREDICT2 / SVBFM_PREDICT2_HALFWARP (read at svbfm_create)
+    bool vbo_full_passes = false;                          // SVBFM_VBO_FULL_PASSES=1: masked passes over the whole arrays per batch (comparison)
     bool vbo_rows = true;                                  // SVBFM_VBO_ROWS=0: packed batches go through k_stream instead of k_stream_rows
     bool vbo_pack = true;                                  // SVBFM_VBO_PACK=0: the passes read through idx (round 1 / 2 path, kept for comparison)
     struct BatchView {                                      // what launch_stream / combine_finalize use instead of the whole run

@@ -392,8 +392,6 @@ struct FinalizeArgs {
     double2* nextp_c;            // ... what the step before read as p_next[j]: this step's own parameters (valid when `carry`)
     double* prevm_c;             // ... the new mean the step before gave the column: this step's p_prev[j].x (valid when `carry`)
     int carry;                   // ... not the first step of the batch: the two arrays above replace two scattered 16-byte reads per column
-    double2* pfT;                // vb_online on the stream schedule: [D][K] transposed copy of the factor parameters, kept current for the
-                                 // batch predictions (k_predict2 over the batch's case list); null: none
     const uint32_t* col_list;    // vb_online on the stream schedule: the batch's non-empty columns of the run (null: every column c0 .. c1)
     uint32_t n_list;
     int update_t;                // vb_online: 1 when this sweep advances t_cnt (w: always; v: f == 0)
@@ -587,7 +585,6 @@ __global__ void __launch_bounds__(256) k_finalize_vbo(FinalizeArgs a, double* __
     bool skip = false;
     if (isnan(mu) || isinf(mu)) { mu = mu_dash; bad++; skip = true; }
     a.pf[j] = make_double2(mu, sg);
-    if constexpr (KIND == KIND_VBO_V) if (a.pfT) a.pfT[(size_t)j * a.K + a.f] = make_double2(mu, sg);
     if (!a.cc) a.delta[j] = skip ? 0.0 : (mu_dash - mu);      // (nothing reads delta on the stream schedule: the passes take it from the records)
     if (!skip) {
         if constexpr (KIND == KIND_VBO_W) a.dT[ci] += B_local * (sg - sg_dash);
@@ -1089,8 +1086,14 @@ __global__ void __launch_bounds__(32 * SV_STREAM_WARPS, ONES ? SV_STREAM_MINB : 
 //   * the row's last column becomes the open one.
 // Same outputs as k_stream (colsum for a column inside the tile, partial[t][0 / 1] for the piece of a column that began before the
 // tile / runs past it), so the finalize kernels do not care which of the two ran. Fixed order everywhere: reproducible.
+// Measured on a B200 (profiles/r02_q_*, 2 M-entry batches): tiles of 128 / 256 / 512 entries 32.0 / 34.2 / 35.8 ms per 1020 passes
+// (1024: 53.4); the gathers of row r + 1 issued before row r is reduced (streams two rows ahead, 64 registers): 33.7 against 34.2,
+// dropped.
+#ifndef SV_ROWS_MINB
+#define SV_ROWS_MINB 8
+#endif
 template <int KIND, bool ONES, bool REDUCE, bool STEADY>
-__global__ void __launch_bounds__(128, 8) k_stream_rows(StreamArgs a) {
+__global__ void __launch_bounds__(128, SV_ROWS_MINB) k_stream_rows(StreamArgs a) {
     static_assert(KIND == KIND_VB_W || KIND == KIND_VB_V, "vb / vb_online passes");
     constexpr bool IS_V = (KIND == KIND_VB_V);
     constexpr unsigned FULL = 0xffffffffu;
@@ -1557,23 +1560,38 @@ __global__ void k_transpose_params(const double2* __restrict__ pv, uint32_t D, i
     }
 }
 
+// the means alone (mcmc / als carry no variances: half the bytes per gathered row)
+__global__ void k_transpose_means(const double2* __restrict__ pv, uint32_t D, int K, double* __restrict__ pvTm) {
+    __shared__ double tile[32][33];
+    uint32_t j0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        uint32_t f = f0 + r, j = j0 + threadIdx.x;
+        if (f < (uint32_t)K && j < D) tile[r][threadIdx.x] = pv[(size_t)f * D + j].x;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        uint32_t j = j0 + r, f = f0 + threadIdx.x;
+        if (f < (uint32_t)K && j < D) pvTm[(size_t)j * K + f] = tile[threadIdx.x][r];
+    }
+}
+
 struct Predict2Args {
     const uint32_t* rcol;     // [2n] CSR of the two-field cases
     const float* rval;        // [2n] or null
     const float* y;
     uint32_t n;
     const double2* pw;
-    const double2* pvT;       // [D][K]
+    const double2* pvT;       // [D][K] {mean, variance} (vb)
+    const double* pvTm;       // [D][K] means (mcmc)
     int K, k0, k1;
     const Scalars* sc;
     double* e;
     double* partial;          // [warps] sum T (vb) / sum of squared clamped errors (mcmc)
-    const uint32_t* list;     // LIST: the cases to predict, n of them (a vb_online batch: its cases in device order, i.e. sorted by first-field column)
 };
 
 // G = lanes per case: 32 (one case per warp step) or 16 (two cases per warp step, one per half-warp: the fixed cost of a
 // step -- shuffles of the case's columns, reduction, bookkeeping -- is shared by two cases)
-template <bool MCMC, bool ONES, int NS, int G, bool LIST = false>
+template <bool MCMC, bool ONES, int NS, int G>
 __global__ void __launch_bounds__(256) k_predict2(Predict2Args a) {
     static_assert(G == 32 || G == 16, "lanes per case");
     const uint32_t lane = threadIdx.x & 31, gl = lane & (G - 1), gbase = lane & ~(uint32_t)(G - 1);
@@ -1587,9 +1605,8 @@ __global__ void __launch_bounds__(256) k_predict2(Predict2Args a) {
 #pragma unroll
     for (int s = 0; s < NS; s++) Pu[s] = make_double2(0.0, 0.0);
     for (uint32_t b = b0; b < b1; b++) {
-        uint32_t i = b * 32 + lane;
+        const uint32_t i = b * 32 + lane;
         const bool ok = i < a.n;
-        if constexpr (LIST) i = ok ? __ldcs(a.list + i) : 0u;
         uint2 c = ok ? __ldcs(reinterpret_cast<const uint2*>(a.rcol) + i) : make_uint2(0u, 0u);
         float2 xv = make_float2(1.0f, 1.0f);
         if constexpr (!ONES) if (ok) xv = __ldcs(reinterpret_cast<const float2*>(a.rval) + i);
@@ -1611,7 +1628,8 @@ __global__ void __launch_bounds__(256) k_predict2(Predict2Args a) {
 #pragma unroll
                 for (int s = 0; s < NS; s++) {
                     int f = (int)gl + G * s;
-                    Pu[s] = f < a.K ? __ldg(&a.pvT[(size_t)u * a.K + f]) : make_double2(0.0, 0.0);
+                    if constexpr (MCMC) Pu[s] = make_double2(f < a.K ? __ldg(&a.pvTm[(size_t)u * a.K + f]) : 0.0, 0.0);
+                    else Pu[s] = f < a.K ? __ldg(&a.pvT[(size_t)u * a.K + f]) : make_double2(0.0, 0.0);
                 }
                 u_prev = u;
             }
@@ -1619,7 +1637,9 @@ __global__ void __launch_bounds__(256) k_predict2(Predict2Args a) {
 #pragma unroll
             for (int s = 0; s < NS; s++) {
                 int f = (int)gl + G * s;
-                double2 Pj = (valid && f < a.K) ? __ldg(&a.pvT[(size_t)j * a.K + f]) : make_double2(0.0, 0.0);
+                double2 Pj = make_double2(0.0, 0.0);
+                if constexpr (MCMC) { if (valid && f < a.K) Pj.x = __ldg(&a.pvTm[(size_t)j * a.K + f]); }
+                else if (valid && f < a.K) Pj = __ldg(&a.pvT[(size_t)j * a.K + f]);
                 double mu_u = Pu[s].x * xu, mu_j = Pj.x * xj;
                 double sm = mu_u + mu_j;                                    // vb.h:115
                 double q = mu_u * mu_u + mu_j * mu_j;                       // vb.h:159 / :241

@@ -102,24 +102,6 @@ def test_vb_online_packed_batches_equal_index_lists(built, monkeypatch, values, 
     assert out[2] == out[3] and np.array_equal(res[2], res[3]) and np.array_equal(par[2], par[3])
 
 
-@pytest.mark.parametrize("values,K", [(False, 3), (True, 40)])
-def test_vb_online_batch_prediction_over_transposed_parameters(built, monkeypatch, values, K):
-    """vb_online on the stream schedule: the fresh prediction of a batch by the warp-per-case kernel over the [D][K] copy of the
-    factor parameters that k_finalize_vbo keeps current (default) against the case-wise kernel over the [K][D] matrix
-    (SVBFM_VBO_PREDICT2=0). Same formulas, factor sums in another order; over three epochs a stale row of the copy would show."""
-    tr, te = two_field(9000, 900, 150, 110, seed=23, values=values)
-    out, par = [], []
-    for p2 in ("1", "0"):
-        monkeypatch.setenv("SVBFM_VBO_PREDICT2", p2)
-        L = make_learner("vb_online", tr, te, K, num_iter=3, num_batch=6, tile_entries=64)
-        out.append([(s.test_rmse, s.free_energy, s.alpha) for s in L.learn(to_csc(tr), to_csc(te))])
-        par.append(np.concatenate([np.ravel(x) for x in L.engine.get_state().values()]))
-        L.engine.close()
-    for a, b in zip(*out):
-        assert all(rel(x, y) < 1e-10 for x, y in zip(a, b)), (a, b)
-    assert np.max(np.abs(par[0] - par[1])) < 1e-9
-
-
 # ---- binary classification (-task c) for mcmc / als: SURVEY section 8(f) rank 4. Built and emulator-checked without a GPU.
 def _binary_two_field(n, nt, U, I, seed, values=False):
     tr, te = two_field(n, nt, U, I, seed=seed, values=values)
