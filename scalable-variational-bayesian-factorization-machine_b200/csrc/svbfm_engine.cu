@@ -272,7 +272,7 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
     (void)batch;
     ProfScope ps(E, (IS_V ? 0 : 3) + 1);
     uint32_t ncols = r.col_end - r.col_begin;
-    bool from_colsum = false, use_ab = false, span_fold = false;
+    bool from_colsum = false, use_ab = false;
     SpanView sp{nullptr, 0, E->ts_shift, SV_SPAN_LIGHT};
     const double* partial = E->d_partial;
     if (rp && rp->run >= 0 && E->bv.on) {        // one vb_online batch: its own column pointer; any span is summed in k_finalize_vbo
@@ -288,12 +288,8 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
         sp.colptr = E->side[rp->run].colptr; sp.entry0 = E->side[rp->run].entry0;
         partial = E->d_partial + (rp->run ? (size_t)E->s_ntiles[0] * 8 : 0);
         uint32_t nh = E->span_heavy_n[rp->run], h0 = rp->run ? E->span_heavy_n[0] : 0;
-        // columns over SV_SPAN_LIGHT tiles: summed inside k_finalize when it reads the pieces itself (span_fold), by a CTA per column in
-        // front of the allreduce of complete local sums otherwise
-        const bool via_allreduce = E->world > 1 && !(rp->run == 0 && E->excl0) && !E->xs;
-        span_fold = E->span_fold && !via_allreduce;
-        if (nh && !span_fold) { k_combine_span<<<nh, 128, 0, st>>>(E->d_span_heavy, h0, sp, partial, E->d_colsum); LAUNCHED(E); }
-        if (via_allreduce) {
+        if (nh) { k_combine_span<<<nh, 128, 0, st>>>(E->d_span_heavy, h0, sp, partial, E->d_colsum); LAUNCHED(E); }
+        if (E->world > 1 && !(rp->run == 0 && E->excl0) && !E->xs) {
             k_combine_light_span<KIND == KIND_VB_V><<<nblk(ncols), 256, 0, st>>>(r.col_begin, r.col_end, sp, partial, E->d_colsum, E->d_ab); LAUNCHED(E);
             ProfScope pc(E, 10);      // includes the wait for the slowest rank
             if (int rc = allreduce_sum_f64(E, reinterpret_cast<double*>(E->d_ab + r.col_begin), (size_t)ncols * 2)) return rc;
@@ -321,7 +317,7 @@ static int combine_finalize(Engine* E, const Run& r, int f, int batch = -1, cons
     fa.pf = pf; fa.group = E->d_group; fa.hyper = IS_V ? E->d_hyper_v : E->d_hyper_w;
     fa.hyper_mu = IS_V ? E->d_mu_v : E->d_mu_w; fa.sc = E->d_sc; fa.delta = E->d_delta; fa.dT = E->d_dT;
     fa.seed = E->cfg.seed; fa.do_sample = E->cfg.do_sample;
-    fa.span = sp; fa.ab = use_ab ? E->d_ab : nullptr; fa.span_fold = span_fold ? 1 : 0;
+    fa.span = sp; fa.ab = use_ab ? E->d_ab : nullptr;
     if (rp) { fa.cpack = E->d_cpack; fa.opack = E->d_opack; fa.rec_mode = rp->rec_mode; fa.p_next = rp->p_next; fa.p_prev = rp->p_prev; }
     fa.rec_slot = E->rec_rank ? E->d_rec_slot : nullptr;
     if (rp && rp->run >= 0 && E->xs) {
@@ -943,7 +939,6 @@ int svbfm_create(svbfm_t** out, const svbfm_config* cfg) {
     if (const char* rr = getenv("SVBFM_REC_RANK")) E->want_rec_rank = atoi(rr) != 0;    // default on; 0: records in column order
     if (const char* gr = getenv("SVBFM_GRAPH")) E->use_graph = atoi(gr) != 0;
     if (const char* na = getenv("SVBFM_REC_NA")) E->rec_na_mask = atoi(na);              // bit s: side s gathers its records past L1 (default 2)
-    if (const char* sf = getenv("SVBFM_SPAN_FOLD")) E->span_fold = atoi(sf) != 0;        // default on; 0: a k_combine_span launch in front of every finalize
     E->no_predict2 = getenv("SVBFM_NO_PREDICT2") != nullptr;          // knobs of the per-iteration paths are read once, here
     E->predict2_half = getenv("SVBFM_PREDICT2_HALFWARP") != nullptr;
     E->vbo_full_passes = getenv("SVBFM_VBO_FULL_PASSES") != nullptr;

@@ -131,7 +131,6 @@ struct Engine {
     uint32_t* d_stile_col0 = nullptr;  // [s_ntiles[0] + s_ntiles[1]] first column of every implicit tile
     uint32_t* d_span_heavy = nullptr;  // columns spanning more than SV_SPAN_LIGHT tiles, run 0 then run 1
     uint32_t span_heavy_n[2] = {0, 0};
-    bool span_fold = true;             // k_finalize sums those columns' pieces itself (SVBFM_SPAN_FOLD=0: k_combine_span in front)
     double* d_e2 = nullptr;            // [n] residuals in the entry order of run 1
     struct OwnPack* d_opack = nullptr; // [D] own-side constants of the next pass
     double2* d_ab = nullptr;           // [D] sharded: {A, B} of every column, the allreduce buffer

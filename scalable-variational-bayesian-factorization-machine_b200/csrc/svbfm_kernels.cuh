@@ -256,6 +256,9 @@ __global__ void k_combine_light(uint32_t c0, uint32_t c1, const uint32_t* __rest
 // columns. A column that lies inside one tile has its sums written straight to colsum[j]; a column that crosses
 // tile borders leaves one piece per tile: partial[T][1] in the tile where it starts, partial[T][0] in the others.
 #define SV_SPAN_LIGHT 8u      // columns spanning more tiles than this are combined by a CTA (k_combine_span)
+// (Summing those columns inside k_finalize instead -- the lanes of a warp over the pieces, one launch less per step and field -- was
+// measured and dropped, profiles/r02_r_*: the heaviest column's ~2000 / ~3400 pieces sit on the critical path of the finalize,
+// ML-10M shape 9.7 -> 10.8 ms per iteration, 200 M + 2 ms; ML-1M shape 1.53 -> 1.49 ms: a launch gap is ~1 us on a B200.)
 
 struct SpanView {
     const uint64_t* colptr;   // null: the explicit-tile layout (col_tile0 / partial[tile][4]) is in use
@@ -388,8 +391,6 @@ struct FinalizeArgs {
     const uint32_t* gcnt;        // vb_online on the sharded stream schedule: global batch entries of every column (indexed like span.colptr)
     const VboCol* cc;            // vb_online, compact columns: the batch's non-empty columns of BOTH fields (null: global column ids everywhere)
     const uint64_t* ccptr;       // ... [n_list + 1] the batch's column pointer at this field's non-empty columns
-    int span_fold;               // stream schedule: k_finalize sums the pieces of the columns over SV_SPAN_LIGHT tiles itself (the lanes of a warp
-                                 // together, fixed order) instead of reading what a k_combine_span launch left in colsum
     uint32_t cid0;               // ... first compact id of this field (colsum / opack / dT are indexed by cid0 + t)
     double2* nextp_c;            // ... what the step before read as p_next[j]: this step's own parameters (valid when `carry`)
     double* prevm_c;             // ... the new mean the step before gave the column: this step's p_prev[j].x (valid when `carry`)
@@ -426,46 +427,11 @@ template <int KIND>
 __global__ void __launch_bounds__(256) k_finalize(FinalizeArgs a) {
     static_assert(KIND <= KIND_MC_V, "vb_online uses k_finalize_vbo");
     uint32_t j = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
-    const bool act = j < a.c1;
-    double A = 0.0, B = 0.0, C1 = 0.0, C2 = 0.0;
-    bool have = false;                          // the sums are in registers already
-    if (a.span.colptr && a.span_fold && !a.from_colsum) {       // (uniform)
-        // a column over more tiles than span_sum walks alone: all lanes of the warp take its pieces together (one launch less
-        // per step and field than a k_combine_span pass in front; no thread leaves before this part)
-        uint64_t T0 = 0, T1 = 0;
-        bool heavy = false;
-        if (act) {
-            const uint64_t b = a.span.colptr[j], e = a.span.colptr[j + 1];
-            if (e > b) {
-                T0 = (b - a.span.entry0) >> a.span.ts_shift; T1 = (e - 1 - a.span.entry0) >> a.span.ts_shift;
-                heavy = T1 - T0 > (uint64_t)a.span.light_limit;
-            }
-        }
-        const unsigned lane = threadIdx.x & 31;
-        unsigned heavy_mask = __ballot_sync(0xffffffffu, heavy);
-        while (heavy_mask) {
-            const int src = __ffs(heavy_mask) - 1;
-            heavy_mask &= heavy_mask - 1;
-            const uint64_t t0s = __shfl_sync(0xffffffffu, T0, src), t1s = __shfl_sync(0xffffffffu, T1, src);
-            double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-            for (uint64_t T = t0s + lane; T <= t1s; T += 32) {
-                const double2* p = reinterpret_cast<const double2*>(a.partial + (T * 2 + (T == t0s ? 1 : 0)) * 4);
-                double2 x = p[0], y = p[1];
-                v0 += x.x; v1 += x.y; v2 += y.x; v3 += y.y;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-                v2 += __shfl_xor_sync(0xffffffffu, v2, o); v3 += __shfl_xor_sync(0xffffffffu, v3, o);
-            }
-            if ((int)lane == src) { A = v0; B = v1; C1 = v2; C2 = v3; have = true; }
-        }
-    }
-    if (!act) return;
+    if (j >= a.c1) return;
+    double A, B, C1, C2;
     if (a.span.colptr) {
         bool empty;
-        if (have) {}
-        else if (a.from_colsum || !span_sum(j, a.span, a.partial, A, B, C1, C2, empty)) {
+        if (a.from_colsum || !span_sum(j, a.span, a.partial, A, B, C1, C2, empty)) {
             const double2* p = reinterpret_cast<const double2*>(a.colsum + (size_t)j * 4);
             double2 x = p[0], y = p[1];
             A = x.x; B = x.y; C1 = y.x; C2 = y.y;

@@ -98,31 +98,11 @@ def test_vb_online_packed_batches_equal_index_lists(built, monkeypatch, values, 
         assert all(rel(x, y) < 1e-10 for x, y in zip(a, b)), (a, b)
     assert np.max(np.abs(res[0] - res[2])) < 1e-9 and np.max(np.abs(par[0] - par[2])) < 1e-9
     assert not np.array_equal(par[0], par[2]) or tile_entries == 0      # (the rows kernel did run: its sums round differently)
-    # the batch's non-empty columns as a dense id space (default on one GPU) against global column ids: only the addresses differ
-    assert out[2] == out[3] and np.array_equal(res[2], res[3]) and np.array_equal(par[2], par[3])
-
-
-@pytest.mark.parametrize("method", ["vb", "mcmc"])
-def test_span_sums_folded_into_the_finalize(built, monkeypatch, method):
-    """Stream schedule: the pieces of a column that spans more than 8 tiles are summed inside k_finalize (the lanes of a warp
-    together; default) or by a k_combine_span launch in front of it (SVBFM_SPAN_FOLD=0). 64-entry tiles on Zipf columns: the
-    popular ones span dozens of tiles. Same pieces, another fixed order of the sum."""
-    tr, te = two_field(30000, 2000, 120, 90, seed=31)
-    out, par = [], []
-    for fold in ("1", "0"):
-        monkeypatch.setenv("SVBFM_SPAN_FOLD", fold)
-        kw = dict(do_sample=False, do_multilevel=False) if method == "mcmc" else {}
-        L = make_learner(method, tr, te, 3, num_iter=3, tile_entries=64, **kw)
-        out.append([(s.test_rmse, s.train_stat if method == "mcmc" else s.free_energy, s.alpha) for s in L.learn(to_csc(tr), to_csc(te))])
-        assert L.engine.info()["fused_schedule"] & 1
-        par.append(np.concatenate([np.ravel(x) for x in L.engine.get_state().values()]))
-        launches = L.engine.info()["kernel_launches"]
-        L.engine.close()
-        out[-1].append(launches)
-    for a, b in zip(out[0][:-1], out[1][:-1]):
-        assert all(rel(x, y) < 1e-10 for x, y in zip(a, b)), (a, b)
-    assert np.max(np.abs(par[0] - par[1])) < 1e-9
-    assert out[0][-1] < out[1][-1]          # (the k_combine_span launches are gone)
+    # the batch's non-empty columns as a dense id space (default on one GPU) against global column ids: the addresses differ, and
+    # d(sum T) of a batch is summed over the dense array instead of over all columns (the same values between other zeros)
+    for a, b in zip(out[2], out[3]):
+        assert all(rel(x, y) < 1e-12 for x, y in zip(a, b)), (a, b)
+    assert np.max(np.abs(res[2] - res[3])) < 1e-11 and np.max(np.abs(par[2] - par[3])) < 1e-11
 
 
 # ---- binary classification (-task c) for mcmc / als: SURVEY section 8(f) rank 4. Built and emulator-checked without a GPU.
