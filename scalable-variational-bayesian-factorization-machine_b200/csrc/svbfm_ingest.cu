@@ -582,8 +582,10 @@ int ingest_split(Engine* E, DevSplit& S, bool is_train, uint32_t n, uint32_t nco
         if (E->ts_auto) {
             // A pass is one warp per tile: 148 SMs x 7 CTAs x 4 warps = 4144 warps are resident at a time. 4096-entry tiles (the best
             // size at 200 M entries) leave most SMs idle below ~15 M entries per field (1 M ratings: 244 warps on
-            // 31 SMs). Aim at four waves of warps, with tiles between 256 and 4096 entries.
-            const uint64_t want = (uint64_t)n / (4144ull * 4);
+            // 31 SMs). Aim at two waves of warps on one GPU (ML-10M shape, profiles/r02_s_*: 256 / 512 / 1024 / 2048 entries 9.85 / 8.62 /
+            // 8.32 / 8.84 ms per iteration; ML-1M shape: 128 / 256 / 512 entries 1.24 / 1.11 / 1.17 ms), at four on a shard of several
+            // GPUs (the sizes the strong-scaling runs of DESIGN.md section 5 were measured with), with tiles between 256 and 4096 entries.
+            const uint64_t want = (uint64_t)n / (4144ull * (E->world > 1 ? 4 : 2));
             E->ts_shift = 8;
             while (E->ts_shift < 12 && (2ull << E->ts_shift) <= want) E->ts_shift++;
         }
