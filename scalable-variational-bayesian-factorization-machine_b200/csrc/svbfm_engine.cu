@@ -1003,6 +1003,7 @@ void svbfm_destroy(svbfm_t* h) {
     for (void* p : ptrs) sv_free(p);
     cudaStreamSynchronize(E->stream);
     if (E->copy_stream) { cudaStreamSynchronize(E->copy_stream); cudaStreamDestroy(E->copy_stream); }
+    sv_owner_release(E);      // everything this handle cached is idle: the next handle may take it
     if (E->copy_event) cudaEventDestroy(E->copy_event);
     if (E->own_stream) cudaStreamDestroy(E->own_stream);
     delete E;
@@ -1013,6 +1014,7 @@ int svbfm_set_stream(svbfm_t* h, void* cuda_stream) {
     Engine* E = reinterpret_cast<Engine*>(h);
     if (!E) return SVBFM_ERR_ARG;
     cudaStreamSynchronize(E->stream);
+    sv_owner_release(E);      // blocks this handle cached were last used on the stream it leaves: idle now
     E->stream = cuda_stream ? (cudaStream_t)cuda_stream : E->own_stream;
     return SVBFM_OK;
 }

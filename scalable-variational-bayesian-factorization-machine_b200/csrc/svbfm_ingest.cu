@@ -17,6 +17,7 @@
 #include "svbfm_internal.h"
 
 #include <map>
+#include <tuple>
 #include <mutex>
 #include <unordered_map>
 
@@ -26,11 +27,27 @@ namespace svb {
 namespace {
 struct BlockCache {
     std::mutex mu;
-    std::multimap<std::pair<int, size_t>, void*> free_blocks;          // (device, bytes) -> block
-    std::unordered_map<void*, std::pair<int, size_t>> live;            // block -> (device, bytes)
+    // (device, bytes, owner) -> block. A freed block goes back under the handle that allocated it: kernels of that handle's stream may
+    // still be using it, and only work queued on the same stream afterwards is ordered behind them. Owner null: idle blocks anyone may
+    // take (their owner synchronized its stream: svbfm_destroy, svbfm_set_stream).
+    std::multimap<std::tuple<int, size_t, const void*>, void*> free_blocks;
+    struct Live { int dev; size_t bytes; const void* owner; };
+    std::unordered_map<void*, Live> live;
 };
 BlockCache& cache() { static BlockCache c; return c; }
+thread_local const void* t_owner = nullptr;
 }  // namespace
+
+void sv_set_owner(const void* owner) { t_owner = owner; }
+void sv_owner_release(const void* owner) {
+    if (!owner) return;
+    BlockCache& c = cache();
+    std::lock_guard<std::mutex> g(c.mu);
+    std::vector<std::pair<std::tuple<int, size_t, const void*>, void*>> moved;
+    for (auto f = c.free_blocks.begin(); f != c.free_blocks.end();)
+        if (std::get<2>(f->first) == owner) { moved.push_back({{std::get<0>(f->first), std::get<1>(f->first), nullptr}, f->second}); f = c.free_blocks.erase(f); } else ++f;
+    for (auto& m : moved) c.free_blocks.insert(m);
+}
 
 cudaError_t sv_malloc(void** p, size_t bytes) {
     bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
@@ -38,11 +55,12 @@ cudaError_t sv_malloc(void** p, size_t bytes) {
     cudaGetDevice(&dev);
     BlockCache& c = cache();
     std::lock_guard<std::mutex> g(c.mu);
-    auto it = c.free_blocks.find({dev, bytes});
+    auto it = c.free_blocks.find({dev, bytes, t_owner});
+    if (it == c.free_blocks.end() && t_owner) it = c.free_blocks.find({dev, bytes, nullptr});
     if (it != c.free_blocks.end()) {
         *p = it->second;
         c.free_blocks.erase(it);
-        c.live[*p] = {dev, bytes};
+        c.live[*p] = {dev, bytes, t_owner};
         return cudaSuccess;
     }
     cudaError_t e = cudaMalloc(p, bytes);
@@ -50,10 +68,10 @@ cudaError_t sv_malloc(void** p, size_t bytes) {
         cudaGetLastError();
         cudaDeviceSynchronize();
         for (auto f = c.free_blocks.begin(); f != c.free_blocks.end();)
-            if (f->first.first == dev) { cudaFree(f->second); f = c.free_blocks.erase(f); } else ++f;
+            if (std::get<0>(f->first) == dev) { cudaFree(f->second); f = c.free_blocks.erase(f); } else ++f;
         e = cudaMalloc(p, bytes);
     }
-    if (e == cudaSuccess) c.live[*p] = {dev, bytes};
+    if (e == cudaSuccess) c.live[*p] = {dev, bytes, t_owner};
     return e;
 }
 cudaError_t sv_free(void* p) {
@@ -62,7 +80,7 @@ cudaError_t sv_free(void* p) {
     std::lock_guard<std::mutex> g(c.mu);
     auto it = c.live.find(p);
     if (it == c.live.end()) return cudaFree(p);
-    c.free_blocks.insert({it->second, p});
+    c.free_blocks.insert({{it->second.dev, it->second.bytes, it->second.owner}, p});
     c.live.erase(it);
     return cudaSuccess;
 }
@@ -71,7 +89,7 @@ void sv_cache_release() {
     std::lock_guard<std::mutex> g(c.mu);
     int cur = 0;
     cudaGetDevice(&cur);
-    for (auto& f : c.free_blocks) { cudaSetDevice(f.first.first); cudaFree(f.second); }
+    for (auto& f : c.free_blocks) { cudaSetDevice(std::get<0>(f.first)); cudaFree(f.second); }
     c.free_blocks.clear();
     cudaSetDevice(cur);
 }

@@ -29,6 +29,8 @@ namespace svb {
 cudaError_t sv_malloc(void** p, size_t bytes);
 cudaError_t sv_free(void* p);          // null-tolerant
 void sv_cache_release();               // hand every cached block back to the driver
+void sv_set_owner(const void* owner);  // this thread now allocates / frees for `owner` (a handle; SV_CUDA and dev_alloc set it)
+void sv_owner_release(const void* owner);   // the owner's stream is idle: its cached blocks may go to any handle
 }
 
 namespace svb {
@@ -312,6 +314,7 @@ int vbo_stream_prepare(Engine* E, uint32_t num_batch);   // svbfm_ingest.cu: per
 int fail(Engine* E, int code, const std::string& msg);
 #define SV_CUDA(E, call)                                                                                   \
     do {                                                                                                   \
+        svb::sv_set_owner(E);       /* the block cache hands out and takes back blocks per handle */       \
         cudaError_t _e = (call);                                                                           \
         if (_e != cudaSuccess)                                                                             \
             return svb::fail((E), SVBFM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));   \
@@ -320,6 +323,7 @@ int fail(Engine* E, int code, const std::string& msg);
 template <typename T>
 int dev_alloc(Engine* E, T** p, size_t count) {
     if (count == 0) count = 1;
+    sv_set_owner(E);
     cudaError_t e = sv_malloc((void**)p, count * sizeof(T));
     if (e != cudaSuccess) return fail(E, SVBFM_ERR_OOM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     E->dev_bytes += count * sizeof(T);

@@ -1084,8 +1084,8 @@ __global__ void __launch_bounds__(32 * SV_STREAM_WARPS, ONES ? SV_STREAM_MINB : 
 // column's constants itself, and a row of 32 entries is reduced at once:
 //   * the column that is open at the start of the row keeps per-lane sums across rows and is reduced when it ends (exactly
 //     k_stream's arithmetic: the same per-lane sums, the same butterfly);
-//   * the columns that begin and end inside the row take one segmented scan over the lanes (5 steps whatever their number) and
-//     their last lanes write the sums;
+//   * the columns that begin and end inside the row take one segmented scan over the lanes (as many steps as the longest of them
+//     needs, whatever their number) and their last lanes write the sums;
 //   * the row's last column becomes the open one.
 // Same outputs as k_stream (colsum for a column inside the tile, partial[t][0 / 1] for the piece of a column that began before the
 // tile / runs past it), so the finalize kernels do not care which of the two ran. Fixed order everywhere: reproducible.
@@ -1174,18 +1174,23 @@ __global__ void __launch_bounds__(128, SV_ROWS_MINB) k_stream_rows(StreamArgs a)
                 const bool in_last = ok && (c == c_last);
                 const bool interior = ok && !in_open && !in_last;
                 if (__any_sync(FULL, interior)) {
-                    // segmented inclusive scan over the lanes, keyed by the column (the entries are in column order)
+                    // segmented inclusive scan over the lanes (the entries are in column order). Bit l of H: lane l starts a column;
+                    // pos: the lane's distance from the head of its column; the scan takes steps only up to the longest interior
+                    // column of the row (uniform) -- a handful of entries on the rows that have such columns at all
+                    const uint32_t c_dn = __shfl_up_sync(FULL, c, 1);
+                    const unsigned H = __ballot_sync(FULL, lane == 0 || c_dn != c);
+                    const uint32_t pos = lane - (31u - (uint32_t)__clz(H & (FULL >> (31u - lane))));
+                    const uint32_t longest = __reduce_max_sync(FULL, interior ? pos : 0u);
                     double s0 = interior ? tA : 0.0, s1 = interior ? (IS_V ? tC1 : tB) : 0.0, s2 = interior ? tC2 : 0.0;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t cc = __shfl_up_sync(FULL, c, d);
-                        const bool take = (lane >= (uint32_t)d) && (cc == c);
+                        if ((uint32_t)d > longest) break;
+                        const bool take = pos >= (uint32_t)d;       // lane - d lies in the lane's own column
                         const double u0 = __shfl_up_sync(FULL, s0, d), u1 = __shfl_up_sync(FULL, s1, d);
                         if (take) { s0 += u0; s1 += u1; }
                         if constexpr (IS_V) { const double u2 = __shfl_up_sync(FULL, s2, d); if (take) s2 += u2; }
                     }
-                    const uint32_t c_up = __shfl_down_sync(FULL, c, 1);
-                    if (interior && c_up != c) {            // last lane of its column (an interior lane is never lane 31 of a full row)
+                    if (interior && lane < 31u && ((H >> (lane + 1)) & 1u)) {     // last lane of its column (an interior lane is never the row's last lane)
                         double2* out = reinterpret_cast<double2*>(a.colsum + (size_t)c * 4);
                         if constexpr (IS_V) { out[0] = make_double2(s0, 0.0); out[1] = make_double2(s1, s2); }
                         else out[0] = make_double2(s0, s1);

@@ -145,6 +145,10 @@ static inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int width = 32) {
 }
 static inline unsigned __ballot_sync(unsigned mask, bool pred) { return emu::warp_ballot(mask, pred); }
 static inline int __any_sync(unsigned mask, bool pred) { return emu::warp_ballot(mask, pred) != 0u; }
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+    for (int o = 16; o > 0; o >>= 1) { unsigned w = __shfl_xor_sync(mask, v, o); v = w > v ? w : v; }
+    return v;
+}
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { (void)emu::warp_ballot(mask, false); }
 static inline void __syncthreads() { emu::block_barrier(); }
 

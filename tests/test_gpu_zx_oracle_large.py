@@ -3,6 +3,7 @@
 * VB on the MovieLens-1M shape (1 M ratings, 6040 x 3952, K = 20) for three iterations against the C oracle, with the tile sizes the engine
   picks itself (256 entries at this size) and with 4096-entry tiles (the size of the 200 M runs): the heaviest users span hundreds of tiles,
   so k_combine_span, the light spans of k_finalize and the windows of k_stream all run on real column lengths. About 15 s of oracle time.
+* vb_online on the same shape (K = 8, 10 batches per epoch, two epochs): packed batches, k_stream_rows, dense column ids, long spans.
 * MCMC hyper-parameter draws (k_mcmc_hyper: alpha, lambda_w, lambda_v[f]; mcmc.h:901-1089): their means over sweeps 10..30 against three
   oracle seeds. The engine draws from Philox, the oracle from libc rand(): matched in distribution, so the bound is the oracle's own
   seed-to-seed spread plus a few percent; a Gamma shape or rate that is off by a factor fails by a wide margin."""
@@ -40,6 +41,34 @@ def test_vb_ml1m_shape_against_the_oracle(built, tile_entries):
         assert np.max(np.abs(so[name] - sg[name])) < 1e-9, name
     e_orc, _ = orc.get_train_cache(want_t=False)
     assert np.max(np.abs(e_orc - L.engine.get_residuals())) < 1e-9
+    assert L.engine.copies_max_diff() == 0.0
+    L.engine.close()
+
+
+def test_vb_online_ml1m_shape_against_the_oracle(built):
+    """vb_online on the MovieLens-1M shape, K = 8, 10 batches per epoch, two epochs against the C oracle (same libc shuffle stream:
+    the oracle runs first). A batch of 100 k entries touches ~5 k users and ~3 k items, a handful of entries per column for most and
+    thousands for the popular ones: the packed batch, k_stream_rows (open columns across rows and tiles, segmented scans inside a
+    row), the dense column ids and the long-span sums of k_finalize_vbo all run on real column lengths with the tile size the engine
+    picks itself. About 10 s of oracle time."""
+    U, I, N, Nt, _ = synth.SHAPES["ml1m"]
+    K, B = 8, 10
+    model = synth.planted_model(U, I, 911)
+    u, i, y = synth.ratings(N, U, I, model, 912)
+    ut, it, yt = synth.ratings(Nt, U, I, model, 913)
+    tr, te = ob.Csr(*synth.to_csr(u, i, y, U)), ob.Csr(*synth.to_csr(ut, it, yt, U))
+    orc = ob.Oracle("vb_online", tr, te, K=K, seed=42, num_batch=B)
+    want = [orc.iterate() for _ in range(2)]
+    so = orc.get_state()
+    L = make_learner("vb_online", tr, te, K, num_iter=2, num_batch=B)
+    hist = L.learn(to_csc(tr), to_csc(te))
+    assert L.engine.info()["fused_schedule"] & 1
+    for k, (s, o) in enumerate(zip(hist, want)):
+        for name in ("test_rmse", "free_energy", "alpha"):
+            assert rel(getattr(s, name), getattr(o, name)) < 1e-7, (k, name, getattr(s, name), getattr(o, name))
+    sg = L.engine.get_state()
+    for name in ("w_mean", "w_var", "v_mean", "v_var"):
+        assert np.max(np.abs(so[name] - sg[name])) < 1e-9, name
     assert L.engine.copies_max_diff() == 0.0
     L.engine.close()
 
