@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # quick ones that between them reach k_stream (VB, MCMC, small tiles, x != 1), the general per-run schedule, k_predict /
 # k_predict2, the finalize / hyper-parameter kernels and the device ingest
 SUBSET = ["test_vb_two_field_onehot", "test_vb_ragged_multihot", "test_vb_groups_and_small_tiles", "test_mcmc_als_exact",
-          "test_vb_values_no_reorder", "test_stream_schedule_sorted_input", "test_vb_k_zero_and_empty_test_columns"]
+          "test_vb_values_no_reorder", "test_stream_schedule_sorted_input", "test_vb_k_zero_and_empty_test_columns",
+          "test_vb_online_vs_oracle"]      # vb_online: packed batches, k_stream_rows, dense column ids against the oracle
 
 
 @pytest.fixture(scope="module")
@@ -64,14 +65,16 @@ def test_two_ranks_on_the_emulator(emu_lib, tmp_path):
 
 def test_experimental_variants_on_the_emulator(emu_lib):
     """One case each of the kernel variants behind knobs: the bulk-copy ring of k_stream against plain loads (bit-identical; misaligned
-    second field, partial last batch) and the records in column order (SVBFM_REC_RANK=0)."""
+    second field, partial last batch), the records in column order (SVBFM_REC_RANK=0), and the vb_online batch passes four ways (index
+    lists, packed through k_stream, packed through k_stream_rows with dense and with global column ids)."""
     env = dict(os.environ, SVBFM_LIB=emu_lib)
     cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider",
            os.path.join(ROOT, "tests", "test_gpu_zzz_tma_ring.py") + "::test_stream_tma_ring[256-20002]",
            os.path.join(ROOT, "tests", "test_gpu_zz_experiments.py") + "::test_rec_rank_layout[0-64]",
+           os.path.join(ROOT, "tests", "test_gpu_zz_experiments.py") + "::test_vb_online_packed_batches_equal_index_lists[True-64]",
            os.path.join(ROOT, "tests", "test_gpu_zy_errors.py")]           # and the error convention of the C-ABI
     r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0 and "4 passed" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and "5 passed" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
 
 
 def test_full_size_properties_on_divided_shapes(emu_lib):
