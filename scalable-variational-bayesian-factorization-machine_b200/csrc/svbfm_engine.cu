@@ -1457,7 +1457,7 @@ int svbfm_vb_online_epoch(svbfm_t* h, const uint32_t* batch_of_case, uint32_t nu
                 E->bv.gcnt[ri] = E->d_vbo_gcnt[ri] ? E->d_vbo_gcnt[ri] + (size_t)b * nc - r.col_begin : nullptr;
                 E->bv.clist[ri] = E->d_vbo_clist[ri] ? E->d_vbo_clist[ri] + E->vbo_clist_off[ri][b] : nullptr;
                 E->bv.nclist[ri] = E->d_vbo_clist[ri] ? E->vbo_clist_off[ri][b + 1] - E->vbo_clist_off[ri][b] : 0u;
-                if (E->bv.ntiles) {
+                if (E->bv.ntiles && !(E->vbo_pack && E->vbo_rows && E->bv.lists)) {      // (k_stream_rows needs no first column per tile)
                     k_tile_col0<<<nblk(E->bv.ntiles), 256, 0, st>>>(E->bv.colptr[ri], r.col_begin, r.col_end, E->bv.ntiles, E->vbo_ts_shift,
                                                                    E->d_vbo_tile_col0 + (ri ? E->vbo_max_tiles : 0)); LAUNCHED(E);
                 }
