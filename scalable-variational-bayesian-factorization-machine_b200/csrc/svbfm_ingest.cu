@@ -50,7 +50,11 @@ void sv_owner_release(const void* owner) {
 }
 
 cudaError_t sv_malloc(void** p, size_t bytes) {
+#if defined(SVBFM_EMULATED)
+    bytes = (std::max<size_t>(bytes, 1) + 31) & ~(size_t)31;        // tests/emu: the guard page of SVBFM_EMU_GUARD=1 sits at the buffer's own end
+#else
     bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+#endif
     int dev = 0;
     cudaGetDevice(&dev);
     BlockCache& c = cache();

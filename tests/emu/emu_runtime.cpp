@@ -275,8 +275,29 @@ struct SharedBlock { int fd; size_t bytes; bool opened; };
 std::map<void*, SharedBlock>& shared_blocks() { static std::map<void*, SharedBlock> m; return m; }
 struct IpcRecord { char magic[8]; int pid, fd; size_t bytes; };
 }  // namespace
+// SVBFM_EMU_GUARD=1 ("electric fence"; compute-sanitizer is not available on the GPU pool): every allocation ends 0 .. 31 bytes
+// in front of an inaccessible page (32: the alignment of the record structs), and is preceded by one, so a kernel that reads or writes past the end of a buffer (or in
+// front of its page) stops the process with SIGSEGV at the access instead of reading a neighbour's bytes. IPC is off in this mode.
+namespace {
+struct GuardBlock { void* base; size_t bytes; };
+std::map<void*, GuardBlock>& guard_blocks() { static std::map<void*, GuardBlock> m; return m; }
+bool guard_mode() { static const bool on = getenv("SVBFM_EMU_GUARD") != nullptr; return on; }
+}  // namespace
 cudaError_t cudaMalloc(void** p, size_t n) {
     if (g_capture) g_capture_broken = true;     // not allowed while capturing
+    if (guard_mode()) {
+        const size_t data = (std::max<size_t>(n, 1) + 31) / 32 * 32, pages = (data + 4095) / 4096;
+        const size_t bytes = (pages + 2) * 4096;
+        unsigned char* base = static_cast<unsigned char*>(mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+        if (base == MAP_FAILED) return cudaErrorMemoryAllocation;
+        mprotect(base, 4096, PROT_NONE);
+        mprotect(base + (pages + 1) * 4096, 4096, PROT_NONE);
+        unsigned char* d = base + (pages + 1) * 4096 - data;          // the buffer's (32-byte rounded) end is the guard page
+        memset(d, 0xcd, data);
+        guard_blocks()[d] = GuardBlock{base, bytes};
+        *p = d;
+        return cudaSuccess;
+    }
     if (n >= 65536) {
         const size_t bytes = (n + 4095) / 4096 * 4096;
         int fd = memfd_create("svbfm_emu", 0);
@@ -297,6 +318,10 @@ cudaError_t cudaMalloc(void** p, size_t n) {
     return cudaSuccess;
 }
 cudaError_t cudaFree(void* p) {
+    if (guard_mode()) {
+        auto g = guard_blocks().find(p);
+        if (g != guard_blocks().end()) { munmap(g->second.base, g->second.bytes); guard_blocks().erase(g); return cudaSuccess; }
+    }
     auto it = shared_blocks().find(p);
     if (it != shared_blocks().end()) { munmap(p, it->second.bytes); close(it->second.fd); shared_blocks().erase(it); return cudaSuccess; }
     free(p);

@@ -77,6 +77,20 @@ def test_experimental_variants_on_the_emulator(emu_lib):
     assert r.returncode == 0 and "5 passed" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
 
 
+def test_no_access_outside_the_device_buffers(emu_lib):
+    """SVBFM_EMU_GUARD=1: the emulator ends every device allocation in front of an inaccessible page (and the block cache of the emulated
+    build keeps the caller's sizes), so a kernel that reads or writes past a buffer dies with SIGSEGV at the access. compute-sanitizer is
+    not available on the GPU pool; this is the bounds check of the index arithmetic. VB and als on ragged / two-field data with small
+    tiles, and the vb_online batch passes four ways (k_vbo_pack, k_stream_rows, dense column ids, k_finalize_vbo's long spans)."""
+    env = dict(os.environ, SVBFM_LIB=emu_lib, SVBFM_EMU_GUARD="1")
+    t = os.path.join(ROOT, "tests", "test_gpu_parity.py")
+    cmd = [sys.executable, "-m", "pytest", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider",
+           t + "::test_vb_groups_and_small_tiles", t + "::test_mcmc_als_exact", t + "::test_vb_ragged_multihot", t + "::test_vb_online_long_spans_in_a_batch",
+           os.path.join(ROOT, "tests", "test_gpu_zz_experiments.py") + "::test_vb_online_packed_batches_equal_index_lists[False-32]"]
+    r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "5 passed" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
+
+
 def test_full_size_properties_on_divided_shapes(emu_lib):
     """tests/test_gpu_zzzz_full_size.py (first-principles checks of the handed-back state at BASELINE's full sizes) on shapes divided
     down to a few thousand ratings: proves the test's own arithmetic (torch fp64 restatement of y-hat, T, the hyper-parameters and the
